@@ -1,0 +1,176 @@
+"""TEST INFRASTRUCTURE - restatement of the Krylov drivers the reference calls.
+
+The drivers live in KrylovMethods.jl 0.6.0 (Manifest.toml:35-41, git-tree-sha1
+ceb12d552f1d2a1d6395c771cee0e0bc3b069e08), an un-vendored dependency that is NOT
+under /root/reference.  The algorithms below restate the published package from
+memory and are anchored on the reference's call sites
+(src/Multigrid/SolveFuncs.jl:93-130, MGcycle.jl:164-174).  PARITY UNPINNED:
+"same Krylov iteration count" is therefore defined against THIS restatement.
+
+Calling convention kept from the package: ``A`` and ``M`` are functions that
+may return aliased buffers (SolveFuncs.jl:59,66-69), so results are copied
+where the package copies them.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import kernels as K
+
+
+def cg(A, b, tol=1e-2, maxIter=100, M=None, x=None, out=0):
+    """KrylovMethods.cg: preconditioned CG, stop on ||r||/||b|| <= tol.
+    Returns (x, flag, relres, iter, resvec)."""
+    n = b.shape[0]
+    M = (lambda v: v.copy()) if M is None else M
+    if K.norm(b) == 0:
+        return np.zeros(n, dtype=b.dtype), -9, 0.0, 0, np.array([0.0])
+    if x is None or x.size == 0:
+        x = np.zeros(n, dtype=b.dtype)
+        r = b.copy()
+    else:
+        r = b - A(x)
+    z = M(r)
+    p = z.copy()
+    nr0 = K.norm(b)
+    resvec = np.zeros(maxIter)
+    flag = -1
+    lastIter = 0
+    for it in range(1, maxIter + 1):
+        lastIter = it
+        Ap = A(p)
+        gamma = K.dot(r, z)
+        alpha = gamma / K.dot(p, Ap)
+        if alpha == np.inf or alpha < 0:
+            flag = -2
+            break
+        K.addVectors(alpha, p, x)            # x += alpha*p
+        K.addVectors(-alpha, Ap, r)          # r -= alpha*Ap
+        resvec[it - 1] = K.norm(r) / nr0
+        if resvec[it - 1] <= tol:
+            flag = 0
+            break
+        z = M(r)
+        beta = K.dot(z, r) / gamma
+        p *= beta                            # p = z + beta*p  (scal! then axpy!)
+        K.addVectors(1.0, z, p)
+    return x, flag, resvec[lastIter - 1], lastIter, resvec[:lastIter].copy()
+
+
+def _colnorms(X):
+    return np.sqrt(np.sum((X.conj() * X).real, axis=0))
+
+
+def blockCG(A, B, X=None, M=None, maxIter=20, tol=1e-2, ortho=False, pinvTol=None, out=0):
+    """KrylovMethods.blockCG (O'Leary block CG): stop when the MAXIMUM column
+    relative residual is <= tol.  Returns (X, flag, relres, iter, resmat)."""
+    n, nrhs = B.shape
+    M = (lambda v: v.copy()) if M is None else M
+    if pinvTol is None:
+        pinvTol = np.finfo(np.float64).eps * n
+    if K.norm(np.asfortranarray(B)) == 0:
+        return np.zeros_like(B), -9, 0.0, 0, np.array([0.0])
+    if X is None:
+        X = np.zeros((n, nrhs), dtype=B.dtype, order="F")
+    R = np.array(B, order="F", copy=True)
+    if not np.all(X == 0):
+        R -= A(X)
+    Z = M(R)
+    P = np.array(Z, order="F", copy=True)
+    nB = _colnorms(B)
+    resmat = np.zeros((maxIter, nrhs))
+    flag = -1
+    it = 0
+    for it in range(1, maxIter + 1):
+        Q = A(P)
+        PTQ = P.conj().T @ Q
+        pinvPTQ = np.linalg.pinv(PTQ, rcond=pinvTol)
+        Alpha = pinvPTQ @ (P.conj().T @ R)
+        X += P @ Alpha
+        R -= Q @ Alpha
+        resmat[it - 1, :] = _colnorms(R) / nB
+        if resmat[it - 1, :].max() <= tol:
+            flag = 0
+            break
+        Z = M(R)
+        Beta = -pinvPTQ @ (Q.conj().T @ Z)
+        P = np.asfortranarray(Z + P @ Beta)
+    return X, flag, resmat[it - 1, :].max(), it, resmat[:it, :].copy()
+
+
+def fgmres(A, b, restrt, tol=1e-2, maxIter=100, M=None, x=None, out=0, flexible=False):
+    """KrylovMethods.fgmres: restarted, right-preconditioned (F)GMRES.
+    Orthogonalisation is classical Gram-Schmidt as two gemv calls (t = V'w; w -= V t);
+    the small least-squares problem is solved every inner step for the residual
+    estimate; ``maxIter`` counts restarts; stop on ||r||/||b|| <= tol.
+    Returns (x, flag, relres, iter, resvec)."""
+    n = b.shape[0]
+    T = b.dtype
+    M = (lambda v: v.copy()) if M is None else M
+    if K.norm(b) == 0.0:
+        return np.zeros(n, dtype=T), -9, 0.0, 0, np.array([0.0])
+    if x is None or x.size == 0:
+        x = np.zeros(n, dtype=T)
+        r = b.copy()
+    else:
+        r = b.copy()
+        r -= A(x)
+    rnorm0 = K.norm(b)
+    err = K.norm(r) / rnorm0
+    if err < tol:
+        return x, 0, err, 0, np.array([err])
+    restrt = min(restrt, n - 1)
+    V = np.zeros((n, restrt), dtype=T, order="F")
+    Z = np.zeros((n, restrt), dtype=T, order="F") if flexible else None
+    resvec = np.zeros(restrt * maxIter)
+    flag = -1
+    counter = 0
+    it = 0
+    while it < maxIter:
+        it += 1
+        H = np.zeros((restrt + 1, restrt), dtype=T)
+        xi = np.zeros(restrt + 1, dtype=T)
+        V[...] = 0
+        if flexible:
+            Z[...] = 0
+        betta = K.norm(r)
+        xi[0] = betta
+        w = r * (1.0 / betta)
+        V[:, 0] = w
+        for j in range(restrt):
+            z = M(w)
+            if flexible:
+                Z[:, j] = z
+            w = A(z)
+            counter += 1
+            t = V.conj().T @ w                       # gemv 'C'
+            H[:restrt, j] = t
+            w = w - V @ t                            # gemv 'N'
+            betta = K.norm(np.ascontiguousarray(w))
+            H[j + 1, j] = betta
+            w = w * (1.0 / betta)
+            if j + 1 < restrt:
+                V[:, j + 1] = w
+            Hj = H[:j + 2, :j + 1]
+            y = np.linalg.lstsq(Hj, xi[:j + 2], rcond=None)[0]
+            err = np.linalg.norm(Hj @ y - xi[:j + 2]) / rnorm0
+            resvec[counter - 1] = err
+            if err <= tol:
+                flag = 0
+                break
+        y = np.linalg.pinv(H) @ xi
+        if flexible:
+            w = Z @ y
+        else:
+            w = M(V @ y).copy()
+        x = x + w
+        if flag == 0:
+            break
+        if it < maxIter:
+            r = b.copy()
+            r -= A(x)
+    return x, flag, resvec[counter - 1], it, resvec[:counter].copy()
+
+
+def blockFGMRES(A, B, restrt, tol=1e-2, maxIter=100, M=None, X=None, out=0, flexible=False):
+    raise NotImplementedError("blockFGMRES is a 'next' row (SURVEY.md section 8(f))")
