@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""Benchmark of the multigrid hot path (BASELINE.json metric: V-cycle time & DOF/s, 256^3
+Poisson; SpMV GB/s vs HBM peak).
+
+    python bench.py --gpus 1 --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --steps K --warmup W    # restated reference CPU path
+
+One step = one V(2,2) cycle of the geometric-MG hierarchy (Galerkin, 6 levels, damped Jacobi
+0.8) on the 257^3-node Poisson problem of SURVEY.md section 8(d) cfg2, started from x = 0 as
+the preconditioner closure does (SolveFuncs.jl:59).  `value` is DOF/s with everything
+resident in HBM; `e2e` is the same metric through the host-buffer C-ABI call mgb200_solveMG
+(b and x0 copied host->device, x copied back, per-cycle residual norms computed as the
+reference's solveMG does) with pinned host buffers.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------
+def build_problem(cells, levels, nrhs=1, seed=0):
+    import multigrid_jl_b200 as mg
+    t0 = time.time()
+    M = mg.getRegularMesh([0, 1, 0, 1, 0, 1], [cells] * 3)
+    A = mg.poisson_shifted(M, 1e-4)
+    p = mg.getMGparam(np.float64, np.int64, levels, 8, 20, 1e-8, "Jac", 0.8, 2, 2, 'V')
+    mg.MGsetup(A, M, p, nrhs)
+    rng = np.random.default_rng(seed)
+    shape = (A.shape[0],) if nrhs == 1 else (A.shape[0], nrhs)
+    b = np.asfortranarray(A @ rng.random(shape))
+    b /= np.linalg.norm(b)
+    log(f"[bench] host setup {cells}^3 cells, {p.levels} levels: {time.time() - t0:.1f} s, "
+        f"rows {[a.shape[0] for a in p.As]}, nnz {[a.nnz for a in p.As]}")
+    return A, M, p, b
+
+
+def cycle_bytes(p, nrhs=1, pre=2, post=2, sv=8):
+    """Algorithmic bytes of one V(pre,post) cycle from x = 0."""
+    total = 0.0
+    per_level = []
+    m = nrhs
+    for l in range(len(p.As) - 1):
+        n, nnz = p.As[l].shape[0], p.As[l].nnz
+        nc, nnzP = p.As[l + 1].shape[0], p.Ps[l].nnz
+        sweep = nnz * (sv + 4) + 4 * (n + 1) + (3 * m + 1) * n * sv
+        resid = nnz * (sv + 4) + 4 * (n + 1) + 3 * n * sv * m
+        restrict = nnzP * 12 + 4 * (nc + 1) + (n + nc) * sv * m
+        prolong = nnzP * 12 + 4 * (n + 1) + (nc + 2 * n) * sv * m
+        first = (2 * m + 1) * n * sv
+        lvl = first + (pre - 1) * sweep + resid + restrict + prolong + post * sweep
+        per_level.append(lvl)
+        total += lvl
+    return total, per_level
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if (t0 is None or t >= t0 - 0.05) and (t1 is None or t <= t1 + 0.15)]
+        if not rows:
+            rows = [r for (_, r) in self.rows]
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline (restated reference path = oracle)
+# ---------------------------------------------------------------------------------------------
+def cpu_cycles(p, b, ncycles, nthreads=None):
+    """Time `ncycles` preconditioner-style V-cycles (z = 0; recursiveCycle) of the unfused,
+    reference-order CPU restatement on all host cores."""
+    from oracle import cycle as oc
+    from oracle import kernels as K
+    o = oc.OracleMG(p, numCores=nthreads)
+    MMG = oc.getMultigridPreconditioner(o, b)
+    MMG(b)  # warm-up (page faults, thread pool)
+    times = []
+    for _ in range(ncycles):
+        t0 = time.perf_counter()
+        MMG(b)
+        times.append(time.perf_counter() - t0)
+    return times, (K.max_threads() if nthreads is None else nthreads)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cells, levels = args.cells, args.levels
+    A, M, p, b = build_problem(cells, levels)
+    N = A.shape[0]
+    for _ in range(max(args.warmup - 1, 0)):
+        pass  # cpu_cycles does one warm-up cycle itself; more would only add wall time
+    times, cores = cpu_cycles(p, b, max(args.steps, 1))
+    tmax = float(np.mean(times))
+    val = N / tmax
+    nbytes, _ = cycle_bytes(p)
+    out = {
+        "impl": "reference", "metric": "vcycle_dof_per_s", "value": val, "unit": "DOF/s", "n_gpus": args.gpus,
+        "steps": len(times), "warmup": 1, "ms_per_step": tmax * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"cfg2: 3D Poisson {cells}^3 cells ({cells + 1}^3 nodes), geometric MG Galerkin "
+                               f"{p.levels} levels, damped Jacobi 0.8, one V(2,2) cycle from x=0 per step"},
+        "cpu_baseline": {"value": val, "unit": "DOF/s", "cores": cores, "kind": "port",
+                         "sample": f"{len(times)} full V(2,2) cycles of the same hierarchy (unfused reference order, "
+                                   f"OpenMP row-parallel SpMV, Int64 indices)",
+                         "effective_gbs": nbytes / tmax / 1e9},
+        "e2e": {"value": val, "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import multigrid_jl_b200 as mg
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the solve phase has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    cells, levels = args.cells, args.levels
+    A, M, p, b = build_problem(cells, levels, seed=rank)
+    N = A.shape[0]
+    t0 = time.time()
+    dev = mg.DeviceHierarchy(p, device=local_rank)
+    p.device = dev
+    log(f"[bench] upload {time.time() - t0:.1f} s; kernel config level 1 A: {dev.kernel_config(1, 0)}, "
+        f"P: {dev.kernel_config(1, 1)}, R: {dev.kernel_config(1, 2)}; level 2 A: {dev.kernel_config(2, 0)}")
+
+    # parity guard: the timed configuration must reproduce the oracle's first cycle on a small twin
+    # (full-size parity is covered by tests/; here we only make sure the run is not vacuous)
+    x = np.zeros_like(b)
+    xx, it, res = dev.solveMG(b, x, 0.0, 2)
+    assert res[2] < res[1] < res[0], "cycle does not reduce the residual"
+    log(f"[bench] relres after 1,2 cycles: {res[1] / res[0]:.4e} {res[2] / res[0]:.4e}")
+
+    # ---- device-resident V-cycles ------------------------------------------------------------
+    db, dx = dev.device_buffers()  # b is already resident from the solve above
+    for _ in range(max(args.warmup, 3)):
+        dev.cycle_device(True)
+    dev.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = dev.launch_count()
+    tw0 = time.time()
+    dev.event_record(0)
+    for _ in range(args.steps):
+        dev.cycle_device(True)
+    dev.event_record(1)
+    ms = dev.event_elapsed_ms(0, 1)
+    dev.synchronize()
+    tw1 = time.time()
+    launches = dev.launch_count() - launches0
+    clocks = sampler.stop(tw0, tw1)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = N * world / (ms_per_step * 1e-3)
+
+    # ---- per-kernel timing of the same steps (CUDA events on the launching stream) --------------
+    dev.profile_enable(True)
+    for _ in range(args.steps):
+        dev.cycle_device(True)
+    prof = dev.profile_report()
+    dev.profile_enable(False)
+    hbm_peak, peak_src = measured_peaks()
+    dom = max(prof, key=lambda r: r["total_ms"])
+    tot_ms = sum(r["total_ms"] for r in prof)
+    kern = []
+    for r in sorted(prof, key=lambda r: -r["total_ms"]):
+        gbs = r["bytes"] / (r["total_ms"] * 1e-3) / 1e9 if r["total_ms"] > 0 else 0.0
+        kern.append({"kind": r["kind"], "level": r["level"], "launches": r["launches"],
+                     "avg_us": 1e3 * r["total_ms"] / r["launches"], "gbs": gbs, "share": r["total_ms"] / tot_ms})
+    log("[bench] per-kernel (events): " + json.dumps(kern[:8]))
+    achieved = dom["bytes"] / (dom["total_ms"] * 1e-3) / 1e9
+    nbytes, per_level = cycle_bytes(p)
+    roofline = {"bound": "hbm", "kernel": f"{dom['kind']} level {dom['level']} (fused Jacobi sweep x' = x + d.*(b - A x))"
+                if dom["kind"] == "sweep" else f"{dom['kind']} level {dom['level']}",
+                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "peak_source": peak_src, "traffic": None,
+                "share_of_step": dom["total_ms"] / tot_ms,
+                "cycle_algorithmic_gb": nbytes / 1e9,
+                "cycle_achieved_gbs": nbytes / (ms_per_step * 1e-3) / 1e9,
+                "cycle_frac": nbytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak}
+
+    # ---- end to end through the host-buffer C ABI ----------------------------------------------
+    cyc = args.e2e_cycles
+    hb = torch.empty(N, dtype=torch.float64).pin_memory()
+    hx = torch.empty(N, dtype=torch.float64).pin_memory()
+    hb.numpy()[:] = b
+    import ctypes
+    from multigrid_jl_b200.device import lib, _check
+    res = np.zeros(cyc + 1)
+    itc = ctypes.c_int(0)
+
+    def e2e_step():
+        hx.zero_()
+        _check(lib().mgb200_solveMG(dev.h, ctypes.c_void_p(hb.data_ptr()), ctypes.c_void_p(hx.data_ptr()),
+                                    ctypes.c_double(0.0), cyc, ctypes.byref(itc), res.ctypes.data_as(ctypes.c_void_p)))
+    e2e_step()
+    n_e2e = max(2, min(args.steps, 5))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        e2e_step()
+    te = (time.perf_counter() - t0) / n_e2e
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([te], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        te = float(t.item())
+    e2e = {"value": N * world * cyc / te, "unit": "DOF/s", "h2d_bytes_per_step": 2 * N * 8, "d2h_bytes_per_step": N * 8 + 8 * (cyc + 1),
+           "call": f"mgb200_solveMG (host buffers, pinned), {cyc} V(2,2) cycles per call incl. per-cycle residual norms",
+           "ms_per_call": te * 1e3}
+
+    out = {
+        "metric": "vcycle_dof_per_s", "value": value, "unit": "DOF/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"cfg2: 3D Poisson {cells}^3 cells ({cells + 1}^3 nodes), geometric MG Galerkin "
+                               f"{p.levels} levels, damped Jacobi 0.8, one V(2,2) cycle from x=0 per step",
+                   "rows": N, "nnz_fine": int(p.As[0].nnz), "l2_policy": "inputs larger than L2 (fine-level matrix "
+                   f"{p.As[0].nnz * 12 / 1e6:.0f} MB streamed every sweep)", "replicas": world},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+        "kernels": kern[:10],
+    }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        # bounded CPU sample: full cycles of the same hierarchy on all host cores
+        times, cores = cpu_cycles(p, b, args.cpu_cycles)
+        tc = float(np.mean(times))
+        out["cpu_baseline"] = {"value": N / tc, "unit": "DOF/s", "cores": cores, "kind": "port",
+                               "sample": f"{len(times)} full V(2,2) cycles of the same {cells + 1}^3 hierarchy "
+                                         f"(restated reference CPU path, unfused, OpenMP)",
+                               "ms_per_cycle": tc * 1e3, "effective_gbs": nbytes / tc / 1e9}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    dev.destroy()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells", type=int, default=256)
+    ap.add_argument("--levels", type=int, default=6)
+    ap.add_argument("--e2e-cycles", type=int, default=10)
+    ap.add_argument("--cpu-cycles", type=int, default=5)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    import __graft_entry__ as g
+    if args.impl == "reference":
+        g.build_oracle()
+        run_reference(args)
+    else:
+        if not os.path.exists(g.LIB):
+            g.build_cuda()
+        g.build_oracle()
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

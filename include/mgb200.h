@@ -1,0 +1,160 @@
+/*
+ * mgb200 - B200-native multigrid solve phase behind the API of JuliaInv/Multigrid.jl.
+ *
+ * C ABI of libmgb200.so: plain pointers and sizes, no C++/torch types.  The entry points
+ * take exactly what the reference's own FFI style passes (ccall with the raw arrays of a
+ * Julia SparseMatrixCSC: colptr / rowval / nzval, 1-based Int64 indices, dense column-major
+ * n x nrhs right-hand sides; cf. src/Multigrid/parRelax.jl:61-79, Vanka.jl:436-452,
+ * src/ParallelJuliaSolver/parallelJuliaSolver.jl:214-238 of the reference).
+ *
+ * Storage convention (src/Multigrid/MGdef.jl:75-77, SpMatMul.jl:4-13): the hierarchy holds
+ * the ADJOINT matrices  As[l] = A_l^H,  Ps[l] = P_l^T,  Rs[l] = R_l^T  in CSC, so the CSC
+ * arrays are the CSR arrays of conj(operator).  Upload converts once: indices - index_base,
+ * Int64 -> Int32, values conjugated.  Host arrays are only read during the call (Julia may
+ * move them afterwards); the device owns its copies until mgb200_destroy.
+ *
+ * Levels are numbered 1..levels as in the reference.  All functions return 0 on success and a
+ * negative status otherwise (-1 bad argument / state, -2 CUDA error, -3 NCCL error);
+ * mgb200_last_error() gives the message of the last failure on the calling thread.
+ *
+ * One handle drives one GPU on one stream and is not re-entrant.  Multi-GPU runs use one
+ * process (or Julia worker) per GPU; see mgb200_dist_* below.
+ */
+#ifndef MGB200_H
+#define MGB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mgb200_hierarchy* mgb200_handle;
+
+/* value types (VAL of MGparam{VAL,IND}, src/Multigrid/MGdef.jl:91) */
+#define MGB200_FP64 0
+#define MGB200_CFP64 1
+
+/* relaxation kinds */
+#define MGB200_RELAX_DIAG 0     /* "Jac" and "SPAI": x += d .* r (MGcycle.jl:122-136)          */
+#define MGB200_RELAX_JACGMRES 1 /* "Jac-GMRES": FGMRES_relaxation with D as preconditioner      */
+
+const char* mgb200_last_error(void);
+int mgb200_version(void);
+
+/* getMGparam + the device part of MGsetup (MGdef.jl:149-161).  relax_pre/relax_post hold
+ * param.relaxPre(l), param.relaxPost(l) for l = 1..levels.  cycle_type is 'V','F','W' or 'K'. */
+int mgb200_create(mgb200_handle* h, int val_type, int levels, int nrhs, char cycle_type,
+                  int relax_kind, const int64_t* relax_pre, const int64_t* relax_post, int device);
+
+/* clear! (MGdef.jl:179-189) */
+int mgb200_destroy(mgb200_handle h);
+
+/* Upload level l < levels of the hierarchy: As[l], Ps[l], Rs[l], relaxPrecs[l].
+ *   n   = size(As[l],2) rows of A_l;  nc = rows of A_{l+1}
+ *   A:  colptr[n+1],  rowval, nzval (VAL)             CSC of A_l^H   (n x n)
+ *   P:  colptr[n+1],  rowval, nzval (real Float64)    CSC of P_l^T   (nc x n)
+ *   R:  colptr[nc+1], rowval, nzval (real Float64)    CSC of R_l^T   (n x nc)
+ *   d:  relaxPrecs[l] (VAL, length n)
+ * index_base is 1 for Julia arrays, 0 for C/NumPy arrays. */
+int mgb200_upload_level(mgb200_handle h, int level, int64_t n, int64_t nc,
+                        const int64_t* a_colptr, const int64_t* a_rowval, const void* a_nzval,
+                        const int64_t* p_colptr, const int64_t* p_rowval, const double* p_nzval,
+                        const int64_t* r_colptr, const int64_t* r_rowval, const double* r_nzval,
+                        const void* d, int index_base);
+
+/* defineCoarsestAinv (MGsetup.jl:323-355, default branch): As[end] = A_L^H in CSC; densified,
+ * LU-factorised with partial pivoting and prepared for solves on the device. */
+int mgb200_upload_coarsest(mgb200_handle h, int64_t n, const int64_t* colptr, const int64_t* rowval,
+                           const void* nzval, int index_base);
+
+/* Optional: the matrix the Krylov drivers multiply with when it is not As[1]
+ * (solveCG_MG(AT,param,...) takes AT separately, SolveFuncs.jl:77-82).  CSC of A^H. */
+int mgb200_set_krylov_matrix(mgb200_handle h, int64_t n, const int64_t* colptr, const int64_t* rowval,
+                             const void* nzval, int index_base);
+
+/* adjustMemoryForNumRHS (MGsetup.jl:166-223) */
+int mgb200_adjust_nrhs(mgb200_handle h, int nrhs);
+
+/* setters that mirror mutable MGparam fields */
+int mgb200_set_cycle(mgb200_handle h, char cycle_type, const int64_t* relax_pre, const int64_t* relax_post);
+
+/* ---- solve phase, host buffers (column-major n x nrhs, VAL) --------------------------------- */
+
+/* x = recursiveCycle(param,b,x,1) (MGcycle.jl:1-118); x is read and overwritten. */
+int mgb200_cycle(mgb200_handle h, const void* b, void* x);
+
+/* solveMG (SolveFuncs.jl:3-39).  resvec must hold max_iter+1 doubles: resvec[0] = res_init,
+ * resvec[k] = ||b - A x_k|| after cycle k.  *iter = cycles done. */
+int mgb200_solveMG(mgb200_handle h, const void* b, void* x, double tol, int max_iter, int* iter,
+                   double* resvec);
+
+/* solveCG_MG (SolveFuncs.jl:103-116): KrylovMethods.cg (nrhs = 1) or blockCG (nrhs > 1) with one
+ * cycle as preconditioner.  resvec: max_iter doubles (nrhs = 1) or max_iter*nrhs (block, row k =
+ * column relative residuals of iteration k).  flag: 0 converged, -1 max_iter, -2 breakdown, -9 b = 0. */
+int mgb200_solveCG(mgb200_handle h, const void* b, void* x, double tol, int max_iter, int* iter,
+                   int* flag, double* resvec);
+
+/* solveGMRES_MG (SolveFuncs.jl:120-132): KrylovMethods.fgmres(A,b,inner; flexible) with one cycle
+ * as right preconditioner; max_iter counts restarts.  resvec: inner*max_iter doubles,
+ * *nres = number of entries written. */
+int mgb200_solveFGMRES(mgb200_handle h, const void* b, void* x, int inner, int flexible, double tol,
+                       int max_iter, int* iter, int* flag, double* resvec, int* nres);
+
+/* SpMatMul(alpha,AT,x,beta,y) (SpMatMul.jl:4-26) on an uploaded matrix:
+ * which = 0: A_l, 1: P_l, 2: R_l.  (alpha,beta) must be one of (1,0),(1,1),(-1,1),(-1,0). */
+int mgb200_spmatmul(mgb200_handle h, int level, int which, double alpha, const void* x, double beta,
+                    void* y);
+
+/* ---- solve phase, device-resident buffers (RHS-fastest layout x[i*nrhs + j]) ----------------- */
+
+/* Fine-level device buffers of the hierarchy (memCycle[1].b / .x of the reference). */
+int mgb200_device_buffers(mgb200_handle h, void** d_b, void** d_x);
+
+/* One cycle with b already in the device buffer.  x_is_zero != 0 is the preconditioner call
+ * (z .= 0; recursiveCycle) of getMultigridPreconditioner (SolveFuncs.jl:59).  *d_x_out aliases
+ * an internal buffer, as the reference's closure returns memCycle[1].x. */
+int mgb200_cycle_device(mgb200_handle h, int x_is_zero, void** d_x_out);
+
+/* Same as the host-buffer solvers with b in the device b buffer and x in the device x buffer. */
+int mgb200_solveMG_device(mgb200_handle h, double tol, int max_iter, int* iter, double* resvec);
+int mgb200_solveCG_device(mgb200_handle h, double tol, int max_iter, int* iter, int* flag, double* resvec);
+
+int mgb200_synchronize(mgb200_handle h);
+
+/* ---- introspection / measurement -------------------------------------------------------------- */
+
+/* Kernel selection made at upload for matrix `which` of `level` (see mgb200_spmatmul):
+ * out[0] = threads per row, out[1] = rows per CTA, out[2] = shared bytes per CTA,
+ * out[3] = 1 if the TMA-staged kernel is used, 0 for the row-per-warp fallback,
+ * out[4] = nnz, out[5] = max row length. */
+int mgb200_kernel_config(mgb200_handle h, int level, int which, int64_t* out);
+
+/* CUDA-event timing of every kernel launch (off by default).  The report is a sequence of
+ * records {kind, level, launches, total_ms, algorithmic_bytes}: 5 doubles each; returns the
+ * number of records written (<= max_records) in *nrec and resets the counters. */
+int mgb200_profile_enable(mgb200_handle h, int on);
+int mgb200_profile_report(mgb200_handle h, double* records, int max_records, int* nrec);
+int64_t mgb200_launch_count(mgb200_handle h);
+
+/* CUDA events on the library's own stream (torch.cuda.Event only sees torch's stream):
+ * record event slot idx (0..15); elapsed waits for slot i1 and returns the time from i0 to i1. */
+int mgb200_event_record(mgb200_handle h, int idx);
+int mgb200_event_elapsed_ms(mgb200_handle h, int i0, int i1, double* ms);
+
+/* kinds used in profile records */
+#define MGB200_K_SWEEP 0    /* x' = x + d.*(b - A x)         */
+#define MGB200_K_RESID 1    /* r = b - A x                    */
+#define MGB200_K_SPMV 2     /* y = A x                        */
+#define MGB200_K_RESTRICT 3 /* bc = R r                       */
+#define MGB200_K_PROLONG 4  /* x += P xc                      */
+#define MGB200_K_DIAG 5     /* x = d.*b (first sweep, x = 0)  */
+#define MGB200_K_COARSE 6   /* coarsest dense solve           */
+#define MGB200_K_REDUCE 7   /* dots / norms                   */
+#define MGB200_K_VECTOR 8   /* axpy-class vector updates      */
+#define MGB200_K_COPY 9     /* copies / layout changes        */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGB200_H */

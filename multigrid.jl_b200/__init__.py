@@ -18,3 +18,6 @@ from .mgsetup import (MGsetup, getRelaxPrec, getSPAIprec, adjustMemoryForNumRHS,
                       replaceMatrixInHierarchy, transposeHierarchy, defineCoarsestAinv)
 from .sa_amg import (SA_AMGsetup, getAggregation, getStrengthMatrix, neighborhoodAggregationNew,
                      aggrArray2P)
+from .device import DeviceHierarchy, uploadHierarchy, MGB200Error, LIB_PATH
+from .solve import (solveMG, solveCG_MG, solveGMRES_MG, getMultigridPreconditioner, recursiveCycle,
+                    SpMatMul)

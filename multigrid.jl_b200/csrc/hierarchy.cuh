@@ -1,0 +1,252 @@
+// Device-resident multigrid hierarchy: storage, kernel selection, launch wrappers.
+#pragma once
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include "common.cuh"
+#include "csr_kernels.cuh"
+#include "dense_lu.cuh"
+#include "vec_kernels.cuh"
+
+namespace mgb200 {
+
+enum Kind {
+    K_SWEEP = 0, K_RESID = 1, K_SPMV = 2, K_RESTRICT = 3, K_PROLONG = 4, K_DIAG = 5, K_COARSE = 6,
+    K_REDUCE = 7, K_VECTOR = 8, K_COPY = 9, K_NKINDS = 10
+};
+
+static inline int env_int(const char* name, int dflt) {
+    const char* s = std::getenv(name);
+    return s ? std::atoi(s) : dflt;
+}
+
+template <typename T>
+static T* dev_alloc(size_t n) {
+    T* p = nullptr;
+    MGB_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    return p;
+}
+template <typename T>
+static void dev_free(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------
+// CSR matrix on the device + the kernel configuration chosen from its row-length statistics
+// ---------------------------------------------------------------------------------------------
+template <typename TA>
+struct Csr {
+    int n_rows = 0, n_cols = 0;
+    long long nnz = 0;
+    int* rowptr = nullptr;
+    int* colind = nullptr;
+    TA* val = nullptr;
+    int tpr = 1;        // threads per row
+    int rpc = 256;      // rows per CTA
+    int cap = 0;        // staged elements per CTA (multiple of 4)
+    int max_len = 0;
+    bool staged = true; // TMA-staged kernel, else row-per-warp fallback
+    size_t smem = 0;
+    bool present() const { return rowptr != nullptr; }
+    void release() {
+        dev_free(rowptr);
+        dev_free(colind);
+        dev_free(val);
+        n_rows = n_cols = 0;
+        nnz = 0;
+    }
+};
+
+struct ProfRec {
+    int kind, level;
+    double bytes;
+    cudaEvent_t e0, e1;
+};
+
+struct Context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    ReduceWs red{nullptr, nullptr};
+    double* scal = nullptr;        // device scalars (64 doubles)
+    double* scal_host = nullptr;   // pinned mirror
+    int smem_budget = 56 * 1024;
+    int max_smem_optin = 0;
+    int sm_count = 148;
+    bool profiling = false;
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<cudaEvent_t> user_ev;
+    long long launches = 0;
+
+    void init(int dev) {
+        device = dev;
+        MGB_CUDA(cudaSetDevice(dev));
+        MGB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        red.partials = dev_alloc<double>((size_t)RED_MAX_BLOCKS * 2 * (MAXK + 2));
+        red.counter = dev_alloc<unsigned>(1);
+        MGB_CUDA(cudaMemset(red.counter, 0, sizeof(unsigned)));
+        scal = dev_alloc<double>(256);
+        MGB_CUDA(cudaMemset(scal, 0, 256 * sizeof(double)));
+        MGB_CUDA(cudaMallocHost(&scal_host, 256 * sizeof(double)));
+        MGB_CUDA(cudaDeviceGetAttribute(&max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        MGB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+        smem_budget = env_int("MGB200_SMEM_BUDGET", 56 * 1024);
+    }
+    void destroy() {
+        if (!stream) return;
+        cudaSetDevice(device);
+        cudaStreamSynchronize(stream);
+        for (auto& r : prof) {
+            cudaEventDestroy(r.e0);
+            cudaEventDestroy(r.e1);
+        }
+        prof.clear();
+        for (auto e : ev_pool) cudaEventDestroy(e);
+        ev_pool.clear();
+        for (auto e : user_ev) cudaEventDestroy(e);
+        user_ev.clear();
+        dev_free(red.partials);
+        dev_free(red.counter);
+        dev_free(scal);
+        if (scal_host) cudaFreeHost(scal_host);
+        scal_host = nullptr;
+        cudaStreamDestroy(stream);
+        stream = nullptr;
+    }
+    cudaEvent_t get_event() {
+        if (!ev_pool.empty()) {
+            cudaEvent_t e = ev_pool.back();
+            ev_pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        MGB_CUDA(cudaEventCreate(&e));
+        return e;
+    }
+    void sync() { MGB_CUDA(cudaStreamSynchronize(stream)); }
+    int red_blocks(long long n) const {
+        long long b = (n + RED_THREADS * 4 - 1) / (RED_THREADS * 4);
+        return (int)std::max<long long>(1, std::min<long long>(b, std::min(RED_MAX_BLOCKS, sm_count * 8)));
+    }
+    int ew_blocks(long long n) const {
+        long long b = (n + 255) / 256;
+        return (int)std::max<long long>(1, std::min<long long>(b, (long long)sm_count * 16));
+    }
+};
+
+// RAII launch bracket: counts the launch and, when profiling, times it with CUDA events on the
+// launching stream.
+struct Launch {
+    Context& c;
+    bool rec;
+    ProfRec r;
+    Launch(Context& ctx, int kind, int level, double bytes) : c(ctx), rec(ctx.profiling) {
+        c.launches++;
+        if (rec) {
+            r.kind = kind;
+            r.level = level;
+            r.bytes = bytes;
+            r.e0 = c.get_event();
+            r.e1 = c.get_event();
+            cudaEventRecord(r.e0, c.stream);
+        }
+    }
+    ~Launch() {
+        if (rec) {
+            cudaEventRecord(r.e1, c.stream);
+            c.prof.push_back(r);
+        }
+    }
+};
+
+#define MGB_LAUNCH_CHECK() MGB_CUDA(cudaGetLastError())
+
+// ---------------------------------------------------------------------------------------------
+// upload: host CSC-of-adjoint (Int64, index_base) -> device CSR-of-operator (Int32)
+// ---------------------------------------------------------------------------------------------
+template <typename TA>
+static void upload_csr(Context& ctx, Csr<TA>& M, long long n_rows, long long n_cols, const int64_t* colptr,
+                       const int64_t* rowval, const TA* nzval, int base, bool conjugate) {
+    MGB_CHECK(n_rows > 0 && n_rows < (1LL << 31) - 8, "matrix rows out of range");
+    MGB_CHECK(colptr && rowval && nzval, "null matrix array");
+    const long long nnz = colptr[n_rows] - base;
+    MGB_CHECK(nnz >= 0 && nnz < (1LL << 31) - 64, "nnz does not fit 32-bit device indices");
+    M.release();
+    M.n_rows = (int)n_rows;
+    M.n_cols = (int)n_cols;
+    M.nnz = nnz;
+    M.rowptr = dev_alloc<int>(n_rows + 1);
+    M.colind = dev_alloc<int>(nnz + 16);
+    M.val = dev_alloc<TA>(nnz + 16);
+    MGB_CUDA(cudaMemsetAsync(M.colind + nnz, 0, 16 * sizeof(int), ctx.stream));
+    MGB_CUDA(cudaMemsetAsync(M.val + nnz, 0, 16 * sizeof(TA), ctx.stream));
+    const long long chunk = 32LL << 20;  // elements per staging pass
+    long long* tmp = dev_alloc<long long>(std::min<long long>(chunk, std::max(nnz, n_rows + 1)));
+    // row pointers
+    for (long long o = 0; o < n_rows + 1; o += chunk) {
+        long long c = std::min(chunk, n_rows + 1 - o);
+        MGB_CUDA(cudaMemcpyAsync(tmp, colptr + o, c * sizeof(long long), cudaMemcpyHostToDevice, ctx.stream));
+        convert_index_kernel<<<ctx.ew_blocks(c), 256, 0, ctx.stream>>>(tmp, M.rowptr + o, c, base);
+        MGB_LAUNCH_CHECK();
+    }
+    for (long long o = 0; o < nnz; o += chunk) {
+        long long c = std::min(chunk, nnz - o);
+        MGB_CUDA(cudaMemcpyAsync(tmp, rowval + o, c * sizeof(long long), cudaMemcpyHostToDevice, ctx.stream));
+        convert_index_kernel<<<ctx.ew_blocks(c), 256, 0, ctx.stream>>>(tmp, M.colind + o, c, base);
+        MGB_LAUNCH_CHECK();
+    }
+    ctx.sync();
+    dev_free(tmp);
+    TA* vtmp = dev_alloc<TA>(std::min<long long>(chunk, std::max<long long>(nnz, 1)));
+    for (long long o = 0; o < nnz; o += chunk) {
+        long long c = std::min(chunk, nnz - o);
+        MGB_CUDA(cudaMemcpyAsync(vtmp, nzval + o, c * sizeof(TA), cudaMemcpyHostToDevice, ctx.stream));
+        conj_copy_kernel<TA><<<ctx.ew_blocks(c), 256, 0, ctx.stream>>>(vtmp, M.val + o, c, conjugate ? 1 : 0);
+        MGB_LAUNCH_CHECK();
+    }
+    ctx.sync();
+    dev_free(vtmp);
+
+    // ---- kernel selection from row-length statistics --------------------------------------
+    int* dstat = dev_alloc<int>(2);
+    MGB_CUDA(cudaMemsetAsync(dstat, 0, 2 * sizeof(int), ctx.stream));
+    max_rowlen_kernel<<<cdiv(n_rows, 256), 256, 0, ctx.stream>>>(M.rowptr, M.n_rows, dstat);
+    MGB_LAUNCH_CHECK();
+    int hstat[2];
+    MGB_CUDA(cudaMemcpyAsync(hstat, dstat, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+    ctx.sync();
+    M.max_len = hstat[0];
+    const double mean = (double)nnz / (double)n_rows;
+    int tpr = 1;
+    while (tpr < 32 && mean > 40.0 * tpr) tpr *= 2;
+    tpr = env_int("MGB200_TPR", tpr);
+    int nt = env_int("MGB200_NT", 256);
+    M.tpr = tpr;
+    M.staged = false;
+    for (; nt >= 32 && nt >= tpr; nt /= 2) {
+        int rpc = nt / tpr;
+        MGB_CUDA(cudaMemsetAsync(dstat + 1, 0, sizeof(int), ctx.stream));
+        int nchunks = cdiv(n_rows, rpc);
+        chunk_span_kernel<<<cdiv(nchunks, 256), 256, 0, ctx.stream>>>(M.rowptr, M.n_rows, rpc, dstat + 1);
+        MGB_LAUNCH_CHECK();
+        MGB_CUDA(cudaMemcpyAsync(hstat + 1, dstat + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+        ctx.sync();
+        size_t bytes = 16 + (size_t)hstat[1] * (sizeof(TA) + sizeof(int));
+        if (bytes <= (size_t)ctx.smem_budget || (nt / 2 < 32 || nt / 2 < tpr)) {
+            if (bytes <= (size_t)ctx.max_smem_optin - 1024) {
+                M.rpc = rpc;
+                M.cap = hstat[1];
+                M.smem = bytes;
+                M.staged = true;
+            }
+            break;
+        }
+    }
+    dev_free(dstat);
+}
+
+}  // namespace mgb200

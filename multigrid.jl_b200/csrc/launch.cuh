@@ -1,0 +1,180 @@
+// Launch wrappers: pick the kernel instantiation chosen at upload and account the
+// algorithmic bytes of SURVEY.md section 8(d) for every launch.
+#pragma once
+#include "hierarchy.cuh"
+
+namespace mgb200 {
+
+// algorithmic bytes of one CSR pass (device format of the accounting: 4-byte column indices
+// and row pointers, every vector read or written exactly once)
+template <typename TA, typename TV>
+static double csr_bytes(const Csr<TA>& M, int mode, int m) {
+    double b = (double)M.nnz * (sizeof(TA) + 4) + 4.0 * (M.n_rows + 1);
+    const double sv = sizeof(TV);
+    switch (mode) {
+        case MODE_SPMV: b += ((double)M.n_cols + M.n_rows) * sv * m; break;           // read x, write y
+        case MODE_ADD: b += ((double)M.n_cols + 2.0 * M.n_rows) * sv * m; break;      // read x, read+write y
+        case MODE_RESID: b += (3.0 * M.n_rows) * sv * m; break;                       // x, b, r
+        case MODE_SWEEP: b += (3.0 * m + 1.0) * M.n_rows * sv; break;                 // x, b, x', d
+    }
+    return b;
+}
+
+template <typename TA, typename TV, int TPR>
+static void launch_stream_mode(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d,
+                               TV* y) {
+    const int grid = cdiv(M.n_rows, M.rpc);
+    const int nt = M.rpc * TPR;
+#define MGB_CASE(MODE)                                                                                   \
+    case MODE: {                                                                                         \
+        auto kern = csr_stream_kernel<TA, TV, TPR, MODE>;                                                \
+        if (M.smem > 48 * 1024)                                                                          \
+            MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M.smem)); \
+        kern<<<grid, nt, M.smem, ctx.stream>>>(M.n_rows, M.rowptr, M.colind, M.val, x, b, d, y, M.rpc,   \
+                                               M.cap);                                                   \
+    } break;
+    switch (mode) {
+        MGB_CASE(MODE_SPMV)
+        MGB_CASE(MODE_ADD)
+        MGB_CASE(MODE_RESID)
+        MGB_CASE(MODE_SWEEP)
+    }
+#undef MGB_CASE
+    MGB_LAUNCH_CHECK();
+}
+
+template <typename TA, typename TV>
+static void launch_mrhs_mode(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d,
+                             TV* y, int m) {
+    const int grid = cdiv(M.n_rows, M.rpc);
+    int mp = 1;
+    while (mp < m && mp < 32) mp *= 2;
+    const int nt = 256;
+#define MGB_CASE(MODE)                                                                                   \
+    case MODE: {                                                                                         \
+        auto kern = csr_stream_mrhs_kernel<TA, TV, MODE>;                                                \
+        if (M.smem > 48 * 1024)                                                                          \
+            MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M.smem)); \
+        kern<<<grid, nt, M.smem, ctx.stream>>>(M.n_rows, M.rowptr, M.colind, M.val, x, b, d, y, M.rpc,   \
+                                               M.cap, m, mp);                                            \
+    } break;
+    switch (mode) {
+        MGB_CASE(MODE_SPMV)
+        MGB_CASE(MODE_ADD)
+        MGB_CASE(MODE_RESID)
+        MGB_CASE(MODE_SWEEP)
+    }
+#undef MGB_CASE
+    MGB_LAUNCH_CHECK();
+}
+
+template <typename TA, typename TV>
+static void launch_rowwarp_mode(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b,
+                                const TV* d, TV* y, int m) {
+    const int grid = cdiv((long long)M.n_rows * 32, 256);
+    switch (mode) {
+        case MODE_SPMV:
+            csr_rowwarp_kernel<TA, TV, MODE_SPMV><<<grid, 256, 0, ctx.stream>>>(M.n_rows, M.rowptr, M.colind, M.val, x, b, d, y, m);
+            break;
+        case MODE_ADD:
+            csr_rowwarp_kernel<TA, TV, MODE_ADD><<<grid, 256, 0, ctx.stream>>>(M.n_rows, M.rowptr, M.colind, M.val, x, b, d, y, m);
+            break;
+        case MODE_RESID:
+            csr_rowwarp_kernel<TA, TV, MODE_RESID><<<grid, 256, 0, ctx.stream>>>(M.n_rows, M.rowptr, M.colind, M.val, x, b, d, y, m);
+            break;
+        case MODE_SWEEP:
+            csr_rowwarp_kernel<TA, TV, MODE_SWEEP><<<grid, 256, 0, ctx.stream>>>(M.n_rows, M.rowptr, M.colind, M.val, x, b, d, y, m);
+            break;
+    }
+    MGB_LAUNCH_CHECK();
+}
+
+// y = op(M x): the one entry point the cycle uses for A, P and R.
+template <typename TA, typename TV>
+static void csr_apply(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d, TV* y,
+                      int m, int kind, int level) {
+    MGB_CHECK(M.present(), "matrix not uploaded");
+    Launch L(ctx, kind, level, csr_bytes<TA, TV>(M, mode, m));
+    if (!M.staged) {
+        launch_rowwarp_mode<TA, TV>(ctx, M, mode, x, b, d, y, m);
+    } else if (m > 1) {
+        launch_mrhs_mode<TA, TV>(ctx, M, mode, x, b, d, y, m);
+    } else {
+        switch (M.tpr) {
+            case 1: launch_stream_mode<TA, TV, 1>(ctx, M, mode, x, b, d, y); break;
+            case 2: launch_stream_mode<TA, TV, 2>(ctx, M, mode, x, b, d, y); break;
+            case 4: launch_stream_mode<TA, TV, 4>(ctx, M, mode, x, b, d, y); break;
+            case 8: launch_stream_mode<TA, TV, 8>(ctx, M, mode, x, b, d, y); break;
+            case 16: launch_stream_mode<TA, TV, 16>(ctx, M, mode, x, b, d, y); break;
+            default: launch_stream_mode<TA, TV, 32>(ctx, M, mode, x, b, d, y); break;
+        }
+    }
+}
+
+// ---- reductions / vector ops -----------------------------------------------------------------
+template <typename TV>
+static void dev_dot(Context& ctx, long long n, const TV* x, const TV* y, double* out) {
+    Launch L(ctx, K_REDUCE, 0, 2.0 * n * sizeof(TV));
+    dot_kernel<TV><<<ctx.red_blocks(n), RED_THREADS, 0, ctx.stream>>>(n, x, y, ctx.red, out);
+    MGB_LAUNCH_CHECK();
+}
+template <typename TV>
+static void dev_norm2sq(Context& ctx, long long n, const TV* x, double* out) {
+    Launch L(ctx, K_REDUCE, 0, 1.0 * n * sizeof(TV));
+    norm2sq_kernel<TV><<<ctx.red_blocks(n), RED_THREADS, 0, ctx.stream>>>(n, x, ctx.red, out);
+    MGB_LAUNCH_CHECK();
+}
+// t[c] = <V[:,c], w>, c < k  -> out (2 doubles per column)
+template <typename TV>
+static void dev_multi_dot(Context& ctx, long long n, const TV* V, long long ld, int k, const TV* w, double* out) {
+    for (int c0 = 0; c0 < k; c0 += 8) {
+        int kk = std::min(8, k - c0);
+        Launch L(ctx, K_REDUCE, 0, (1.0 + kk) * n * sizeof(TV));
+        if (kk <= 2)
+            multi_dot_kernel<TV, 2><<<ctx.red_blocks(n), RED_THREADS, 0, ctx.stream>>>(n, V + c0 * ld, ld, kk, w, ctx.red, out + 2 * c0);
+        else if (kk <= 4)
+            multi_dot_kernel<TV, 4><<<ctx.red_blocks(n), RED_THREADS, 0, ctx.stream>>>(n, V + c0 * ld, ld, kk, w, ctx.red, out + 2 * c0);
+        else
+            multi_dot_kernel<TV, 8><<<ctx.red_blocks(n), RED_THREADS, 0, ctx.stream>>>(n, V + c0 * ld, ld, kk, w, ctx.red, out + 2 * c0);
+        MGB_LAUNCH_CHECK();
+    }
+}
+// w = beta*w + sum_c coef[c] V[:,c]; if norm_out: *norm_out = ||w||^2
+template <typename TV>
+static void dev_multi_axpy(Context& ctx, long long n, const TV* V, long long ld, int k, const TV* coef,
+                           double beta, TV* w, double* norm_out) {
+    MGB_CHECK(k <= MAXK, "too many basis columns");
+    Coefs<TV> c;
+    for (int i = 0; i < MAXK; ++i) c.c[i] = (i < k) ? coef[i] : VT<TV>::zero();
+    Launch L(ctx, K_VECTOR, 0, (2.0 + k) * n * sizeof(TV));
+    if (norm_out)
+        multi_axpy_kernel<TV, true><<<ctx.red_blocks(n), RED_THREADS, 0, ctx.stream>>>(n, V, ld, k, c, beta, w, ctx.red, norm_out);
+    else
+        multi_axpy_kernel<TV, false><<<ctx.red_blocks(n), RED_THREADS, 0, ctx.stream>>>(n, V, ld, k, c, beta, w, ctx.red, nullptr);
+    MGB_LAUNCH_CHECK();
+}
+template <typename TV>
+static void dev_axpby(Context& ctx, long long n, TV a, const TV* x, TV b, TV* y, bool b_is_zero) {
+    Launch L(ctx, K_VECTOR, 0, (b_is_zero ? 2.0 : 3.0) * n * sizeof(TV));
+    axpby_kernel<TV><<<ctx.ew_blocks(n), 256, 0, ctx.stream>>>(n, a, x, b, y, b_is_zero ? 1 : 0);
+    MGB_LAUNCH_CHECK();
+}
+template <typename TV>
+static void dev_copy(Context& ctx, long long n, const TV* src, TV* dst) {
+    if (src == dst) return;
+    Launch L(ctx, K_COPY, 0, 2.0 * n * sizeof(TV));
+    MGB_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(TV), cudaMemcpyDeviceToDevice, ctx.stream));
+}
+template <typename TV>
+static void dev_zero(Context& ctx, long long n, TV* dst) {
+    Launch L(ctx, K_COPY, 0, 1.0 * n * sizeof(TV));
+    MGB_CUDA(cudaMemsetAsync(dst, 0, n * sizeof(TV), ctx.stream));
+}
+// read k doubles from a device scalar array (synchronises the stream)
+static inline void read_scalars(Context& ctx, const double* dptr, int k, double* out) {
+    MGB_CUDA(cudaMemcpyAsync(ctx.scal_host, dptr, k * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+    ctx.sync();
+    std::memcpy(out, ctx.scal_host, k * sizeof(double));
+}
+
+}  // namespace mgb200

@@ -1,0 +1,408 @@
+// C ABI of libmgb200.so (declared in include/mgb200.h).
+#include "../../include/mgb200.h"
+
+#include <cmath>
+#include <array>
+#include <cstring>
+#include <map>
+#include <string>
+#include <type_traits>
+
+#include "solver.cuh"
+
+using namespace mgb200;
+
+struct mgb200_hierarchy {
+    int val_type;
+    HierarchyBase* impl;
+};
+
+static thread_local std::string g_last_error;
+
+#define MGB_TRY try {
+#define MGB_CATCH                                         \
+    }                                                     \
+    catch (const Error& e) {                              \
+        g_last_error = e.what();                          \
+        return e.code;                                    \
+    }                                                     \
+    catch (const std::exception& e) {                     \
+        g_last_error = e.what();                          \
+        return -1;                                        \
+    }                                                     \
+    return 0;
+
+template <typename F>
+static void dispatch(mgb200_handle h, F&& f) {
+    MGB_CHECK(h && h->impl, "null handle");
+    if (h->val_type == MGB200_FP64) {
+        auto* H = static_cast<Hierarchy<double>*>(h->impl);
+        MGB_CUDA(cudaSetDevice(H->ctx.device));
+        f(H);
+    } else {
+        auto* H = static_cast<Hierarchy<cplx>*>(h->impl);
+        MGB_CUDA(cudaSetDevice(H->ctx.device));
+        f(H);
+    }
+}
+// generic body for both value types; `H` is the typed hierarchy pointer
+#define MGB_BOTH(h, ...) dispatch(h, [&](auto* H) { __VA_ARGS__; })
+
+template <typename TV>
+static void spmatmul_impl(Hierarchy<TV>* H, int level, int which, double alpha, const void* x, double beta,
+                          void* y) {
+    MGB_CHECK(level >= 1 && level <= H->levels, "level out of range");
+    MGB_CHECK(which >= 0 && which <= 2, "which must be 0 (A), 1 (P) or 2 (R)");
+    Level<TV>& lv = H->L[level - 1];
+    int mode;
+    if (alpha == 1.0 && beta == 0.0) mode = MODE_SPMV;
+    else if (alpha == 1.0 && beta == 1.0) mode = MODE_ADD;
+    else if (alpha == -1.0 && (beta == 1.0 || beta == 0.0)) mode = MODE_RESID;
+    else throw Error(-1, "mgb200_spmatmul: (alpha,beta) must be one of (1,0),(1,1),(-1,1),(-1,0)");
+    long long nx, ny;
+    const int m = H->m;
+    Context& ctx = H->ctx;
+    auto run = [&](auto& M) {
+        nx = M.n_cols;
+        ny = M.n_rows;
+        TV* dx = dev_alloc<TV>(nx * m);
+        TV* dy = dev_alloc<TV>(ny * m);
+        TV* db = dev_alloc<TV>(ny * m);
+        H->h2d_vec(x, dx, nx);
+        if (beta == 1.0) H->h2d_vec(y, dy, ny);
+        if (mode == MODE_RESID) {
+            if (beta == 1.0) MGB_CUDA(cudaMemcpyAsync(db, dy, ny * m * sizeof(TV), cudaMemcpyDeviceToDevice, ctx.stream));
+            else MGB_CUDA(cudaMemsetAsync(db, 0, ny * m * sizeof(TV), ctx.stream));
+        }
+        typedef typename std::remove_reference<decltype(*M.val)>::type TA;
+        csr_apply<TA, TV>(ctx, M, mode, dx, db, nullptr, dy, m, K_SPMV, level);
+        H->d2h_vec(dy, y, ny);
+        dev_free(dx);
+        dev_free(dy);
+        dev_free(db);
+    };
+    if (which == 0) {
+        MGB_CHECK(lv.A.present(), "matrix not uploaded");
+        run(lv.A);
+    } else if (which == 1) {
+        MGB_CHECK(lv.P.present(), "matrix not uploaded");
+        run(lv.P);
+    } else {
+        MGB_CHECK(lv.R.present(), "matrix not uploaded");
+        run(lv.R);
+    }
+}
+
+extern "C" {
+
+const char* mgb200_last_error(void) { return g_last_error.c_str(); }
+int mgb200_version(void) { return 100; }
+
+int mgb200_create(mgb200_handle* h, int val_type, int levels, int nrhs, char cycle_type, int relax_kind,
+                  const int64_t* relax_pre, const int64_t* relax_post, int device) {
+    MGB_TRY
+    MGB_CHECK(h != nullptr, "null handle pointer");
+    MGB_CHECK(val_type == MGB200_FP64 || val_type == MGB200_CFP64, "val_type must be MGB200_FP64 or MGB200_CFP64");
+    MGB_CHECK(relax_kind == 0 || relax_kind == 1, "relax_kind must be 0 (diagonal) or 1 (Jac-GMRES)");
+    MGB_CHECK(relax_pre && relax_post, "relax_pre / relax_post required");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        throw Error(-2, std::string("mgb200 needs a CUDA device and has no CPU fallback: ") +
+                            (e != cudaSuccess ? cudaGetErrorString(e) : "no device found"));
+    MGB_CHECK(device >= 0 && device < ndev, "device index out of range");
+    mgb200_hierarchy* hh = new mgb200_hierarchy;
+    hh->val_type = val_type;
+    hh->impl = nullptr;
+    try {
+        if (val_type == MGB200_FP64)
+            hh->impl = new Hierarchy<double>(levels, nrhs, cycle_type, relax_kind, relax_pre, relax_post, device);
+        else
+            hh->impl = new Hierarchy<cplx>(levels, nrhs, cycle_type, relax_kind, relax_pre, relax_post, device);
+    } catch (...) {
+        delete hh;
+        throw;
+    }
+    hh->impl->val_type = val_type;
+    *h = hh;
+    MGB_CATCH
+}
+
+int mgb200_destroy(mgb200_handle h) {
+    MGB_TRY
+    if (h) {
+        delete h->impl;
+        delete h;
+    }
+    MGB_CATCH
+}
+
+int mgb200_upload_level(mgb200_handle h, int level, int64_t n, int64_t nc, const int64_t* a_colptr,
+                        const int64_t* a_rowval, const void* a_nzval, const int64_t* p_colptr,
+                        const int64_t* p_rowval, const double* p_nzval, const int64_t* r_colptr,
+                        const int64_t* r_rowval, const double* r_nzval, const void* d, int index_base) {
+    MGB_TRY
+    MGB_BOTH(h, H->upload_level(level, n, nc, a_colptr, a_rowval, a_nzval, p_colptr, p_rowval, p_nzval,
+                                r_colptr, r_rowval, r_nzval, d, index_base));
+    MGB_CATCH
+}
+
+int mgb200_upload_coarsest(mgb200_handle h, int64_t n, const int64_t* colptr, const int64_t* rowval,
+                           const void* nzval, int index_base) {
+    MGB_TRY
+    MGB_BOTH(h, H->upload_coarsest(n, colptr, rowval, nzval, index_base));
+    MGB_CATCH
+}
+
+int mgb200_set_krylov_matrix(mgb200_handle h, int64_t n, const int64_t* colptr, const int64_t* rowval,
+                             const void* nzval, int index_base) {
+    MGB_TRY
+    MGB_BOTH(h, H->set_krylov_matrix(n, colptr, rowval, nzval, index_base));
+    MGB_CATCH
+}
+
+int mgb200_adjust_nrhs(mgb200_handle h, int nrhs) {
+    MGB_TRY
+    MGB_BOTH(h, H->adjust_nrhs(nrhs));
+    MGB_CATCH
+}
+
+int mgb200_set_cycle(mgb200_handle h, char cycle_type, const int64_t* relax_pre, const int64_t* relax_post) {
+    MGB_TRY
+    MGB_BOTH(h, H->set_cycle(cycle_type, relax_pre, relax_post));
+    MGB_CATCH
+}
+
+int mgb200_cycle(mgb200_handle h, const void* b, void* x) {
+    MGB_TRY
+    MGB_CHECK(b && x, "null vector");
+    MGB_BOTH(h, {
+        H->ensure_work();
+        const long long n = H->L[0].n;
+        H->h2d_vec(b, H->L[0].b, n);
+        H->h2d_vec(x, H->ucur, n);
+        const bool xzero = (H->norm(n * H->m, H->ucur) == 0.0);  // `if norm(x)>0.0` (MGcycle.jl:29)
+        H->cycle_top(xzero);
+        H->d2h_vec(H->ucur, x, n);
+    });
+    MGB_CATCH
+}
+
+int mgb200_solveMG(mgb200_handle h, const void* b, void* x, double tol, int max_iter, int* iter, double* resvec) {
+    MGB_TRY
+    MGB_CHECK(b && x && iter && resvec, "null argument");
+    MGB_BOTH(h, {
+        H->ensure_work();
+        const long long n = H->L[0].n;
+        H->h2d_vec(b, H->L[0].b, n);
+        H->h2d_vec(x, H->ucur, n);
+        *iter = H->solveMG(tol, max_iter, resvec);
+        H->d2h_vec(H->ucur, x, n);
+    });
+    MGB_CATCH
+}
+
+int mgb200_solveCG(mgb200_handle h, const void* b, void* x, double tol, int max_iter, int* iter, int* flag,
+                   double* resvec) {
+    MGB_TRY
+    MGB_CHECK(b && x && iter && flag && resvec, "null argument");
+    MGB_BOTH(h, {
+        H->ensure_work();
+        const long long n = H->L[0].n;
+        H->h2d_vec(b, H->L[0].b, n);
+        H->h2d_vec(x, H->ucur, n);
+        *iter = H->solveCG(H->ucur, tol, max_iter, flag, resvec);
+        H->d2h_vec(H->ucur, x, n);
+    });
+    MGB_CATCH
+}
+
+int mgb200_solveFGMRES(mgb200_handle h, const void* b, void* x, int inner, int flexible, double tol,
+                       int max_iter, int* iter, int* flag, double* resvec, int* nres) {
+    MGB_TRY
+    MGB_CHECK(b && x && iter && flag && resvec && nres, "null argument");
+    MGB_BOTH(h, {
+        H->ensure_work();
+        const long long n = H->L[0].n;
+        H->h2d_vec(b, H->L[0].b, n);
+        H->h2d_vec(x, H->ucur, n);
+        *iter = H->solveFGMRES(H->ucur, inner, flexible != 0, tol, max_iter, flag, resvec, nres);
+        H->d2h_vec(H->ucur, x, n);
+    });
+    MGB_CATCH
+}
+
+int mgb200_spmatmul(mgb200_handle h, int level, int which, double alpha, const void* x, double beta, void* y) {
+    MGB_TRY
+    MGB_CHECK(x && y, "null vector");
+    MGB_BOTH(h, spmatmul_impl(H, level, which, alpha, x, beta, y));
+    MGB_CATCH
+}
+
+int mgb200_device_buffers(mgb200_handle h, void** d_b, void** d_x) {
+    MGB_TRY
+    MGB_BOTH(h, {
+        H->ensure_work();
+        if (d_b) *d_b = H->L[0].b;
+        if (d_x) *d_x = H->ucur;
+    });
+    MGB_CATCH
+}
+
+int mgb200_cycle_device(mgb200_handle h, int x_is_zero, void** d_x_out) {
+    MGB_TRY
+    MGB_BOTH(h, {
+        void* p = H->cycle_top(x_is_zero != 0);
+        if (d_x_out) *d_x_out = p;
+    });
+    MGB_CATCH
+}
+
+int mgb200_solveMG_device(mgb200_handle h, double tol, int max_iter, int* iter, double* resvec) {
+    MGB_TRY
+    MGB_CHECK(iter && resvec, "null argument");
+    MGB_BOTH(h, *iter = H->solveMG(tol, max_iter, resvec));
+    MGB_CATCH
+}
+
+int mgb200_solveCG_device(mgb200_handle h, double tol, int max_iter, int* iter, int* flag, double* resvec) {
+    MGB_TRY
+    MGB_CHECK(iter && flag && resvec, "null argument");
+    MGB_BOTH(h, {
+        H->ensure_work();
+        *iter = H->solveCG(H->ucur, tol, max_iter, flag, resvec);
+    });
+    MGB_CATCH
+}
+
+int mgb200_synchronize(mgb200_handle h) {
+    MGB_TRY
+    MGB_BOTH(h, H->ctx.sync());
+    MGB_CATCH
+}
+
+int mgb200_kernel_config(mgb200_handle h, int level, int which, int64_t* out) {
+    MGB_TRY
+    MGB_CHECK(out, "null output");
+    MGB_BOTH(h, {
+        MGB_CHECK(level >= 1 && level <= H->levels, "level out of range");
+        auto& lv = H->L[level - 1];
+        auto fill = [&](auto& M) {
+            out[0] = M.tpr;
+            out[1] = M.rpc;
+            out[2] = (int64_t)M.smem;
+            out[3] = M.staged ? 1 : 0;
+            out[4] = M.nnz;
+            out[5] = M.max_len;
+        };
+        if (which == 0) fill(lv.A);
+        else if (which == 1) fill(lv.P);
+        else fill(lv.R);
+    });
+    MGB_CATCH
+}
+
+int mgb200_profile_enable(mgb200_handle h, int on) {
+    MGB_TRY
+    MGB_BOTH(h, {
+        H->ctx.sync();
+        H->ctx.profiling = (on != 0);
+    });
+    MGB_CATCH
+}
+
+int mgb200_profile_report(mgb200_handle h, double* records, int max_records, int* nrec) {
+    MGB_TRY
+    MGB_CHECK(records && nrec, "null argument");
+    MGB_BOTH(h, {
+        Context& c = H->ctx;
+        c.sync();
+        std::map<std::pair<int, int>, std::array<double, 3>> agg;
+        for (auto& r : c.prof) {
+            float ms = 0.f;
+            MGB_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+            auto& a = agg[std::make_pair(r.kind, r.level)];
+            a[0] += 1.0;
+            a[1] += ms;
+            a[2] += r.bytes;
+            c.ev_pool.push_back(r.e0);
+            c.ev_pool.push_back(r.e1);
+        }
+        c.prof.clear();
+        int k = 0;
+        for (auto& kv : agg) {
+            if (k >= max_records) break;
+            records[5 * k + 0] = kv.first.first;
+            records[5 * k + 1] = kv.first.second;
+            records[5 * k + 2] = kv.second[0];
+            records[5 * k + 3] = kv.second[1];
+            records[5 * k + 4] = kv.second[2];
+            ++k;
+        }
+        *nrec = k;
+    });
+    MGB_CATCH
+}
+
+int mgb200_event_record(mgb200_handle h, int idx) {
+    MGB_TRY
+    MGB_CHECK(idx >= 0 && idx < 16, "event slot out of range");
+    MGB_BOTH(h, {
+        Context& c = H->ctx;
+        if (c.user_ev.empty()) {
+            c.user_ev.resize(16);
+            for (auto& e : c.user_ev) MGB_CUDA(cudaEventCreate(&e));
+        }
+        MGB_CUDA(cudaEventRecord(c.user_ev[idx], c.stream));
+    });
+    MGB_CATCH
+}
+
+int mgb200_event_elapsed_ms(mgb200_handle h, int i0, int i1, double* ms) {
+    MGB_TRY
+    MGB_CHECK(ms && i0 >= 0 && i0 < 16 && i1 >= 0 && i1 < 16, "bad event arguments");
+    MGB_BOTH(h, {
+        Context& c = H->ctx;
+        MGB_CHECK(!c.user_ev.empty(), "no event recorded");
+        MGB_CUDA(cudaEventSynchronize(c.user_ev[i1]));
+        float f = 0.f;
+        MGB_CUDA(cudaEventElapsedTime(&f, c.user_ev[i0], c.user_ev[i1]));
+        *ms = f;
+    });
+    MGB_CATCH
+}
+
+int64_t mgb200_launch_count(mgb200_handle h) {
+    if (!h || !h->impl) return -1;
+    return h->impl->ctx.launches;
+}
+
+// ---- host-only helpers exported for the CPU test-suite (no GPU needed) ---------------------------
+// t = pinv(H) xi for a Hermitian n x n H (row-major, interleaved re/im)
+int mgb200_host_pinv_apply(int n, const double* H, const double* xi, double* t) {
+    MGB_TRY
+    std::vector<zc> Hv((size_t)n * n), xv(n), tv;
+    for (int i = 0; i < n * n; ++i) Hv[i] = zc(H[2 * i], H[2 * i + 1]);
+    for (int i = 0; i < n; ++i) xv[i] = zc(xi[2 * i], xi[2 * i + 1]);
+    hermitian_pinv_apply(n, Hv, xv, tv);
+    for (int i = 0; i < n; ++i) {
+        t[2 * i] = tv[i].real();
+        t[2 * i + 1] = tv[i].imag();
+    }
+    MGB_CATCH
+}
+// least squares on a (cols+1) x cols Hessenberg block (row-major, ld = cols); returns the residual in *res
+int mgb200_host_hessenberg_lsq(int cols, const double* H, const double* xi, double* y, double* res) {
+    MGB_TRY
+    std::vector<zc> Hv((size_t)(cols + 1) * cols), xv(cols + 1), yv;
+    for (int i = 0; i < (cols + 1) * cols; ++i) Hv[i] = zc(H[2 * i], H[2 * i + 1]);
+    for (int i = 0; i < cols + 1; ++i) xv[i] = zc(xi[2 * i], xi[2 * i + 1]);
+    *res = hessenberg_lsq(Hv, cols, cols + 1, cols, xv, yv);
+    for (int i = 0; i < cols; ++i) {
+        y[2 * i] = yv[i].real();
+        y[2 * i + 1] = yv[i].imag();
+    }
+    MGB_CATCH
+}
+
+}  // extern "C"

@@ -1,0 +1,134 @@
+// Tiny dense host-side linear algebra for the Krylov control flow (inner x inner problems,
+// inner <= 32): Hermitian pseudo-inverse (FGMRES_relaxation, src/Multigrid/FGMRES.jl:99-104) and
+// the Hessenberg least-squares problem of restarted (F)GMRES.  These are O(inner^3) scalar
+// operations on values that are already on the host for the stopping tests.
+#pragma once
+#include <cmath>
+#include <complex>
+#include <limits>
+#include <vector>
+
+namespace mgb200 {
+
+typedef std::complex<double> zc;
+
+// Cyclic Jacobi eigen-decomposition of a real symmetric N x N matrix (row-major, overwritten);
+// V receives the eigenvectors as columns.
+static inline void jacobi_eig_sym(int N, std::vector<double>& A, std::vector<double>& V) {
+    V.assign((size_t)N * N, 0.0);
+    for (int i = 0; i < N; ++i) V[(size_t)i * N + i] = 1.0;
+    for (int sweep = 0; sweep < 100; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < N; ++i)
+            for (int j = 0; j < N; ++j) (i == j ? diag : off) += A[(size_t)i * N + j] * A[(size_t)i * N + j];
+        if (off <= 1e-60 || off <= 1e-32 * diag) break;
+        for (int p = 0; p < N - 1; ++p)
+            for (int q = p + 1; q < N; ++q) {
+                double apq = A[(size_t)p * N + q];
+                if (apq == 0.0) continue;
+                double app = A[(size_t)p * N + p], aqq = A[(size_t)q * N + q];
+                double theta = (aqq - app) / (2.0 * apq);
+                double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < N; ++k) {
+                    double akp = A[(size_t)k * N + p], akq = A[(size_t)k * N + q];
+                    A[(size_t)k * N + p] = c * akp - s * akq;
+                    A[(size_t)k * N + q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < N; ++k) {
+                    double apk = A[(size_t)p * N + k], aqk = A[(size_t)q * N + k];
+                    A[(size_t)p * N + k] = c * apk - s * aqk;
+                    A[(size_t)q * N + k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < N; ++k) {
+                    double vkp = V[(size_t)k * N + p], vkq = V[(size_t)k * N + q];
+                    V[(size_t)k * N + p] = c * vkp - s * vkq;
+                    V[(size_t)k * N + q] = s * vkp + c * vkq;
+                }
+            }
+    }
+}
+
+// t = pinv(H) * xi for Hermitian H (n x n, row-major).  Singular values <= eps*n*max are
+// dropped, the rule of Julia's LinearAlgebra.pinv default (rtol = eps*min(size)).
+// A complex Hermitian H = A + iB is embedded as the real symmetric [[A,-B],[B,A]].
+static inline void hermitian_pinv_apply(int n, const std::vector<zc>& H, const std::vector<zc>& xi,
+                                        std::vector<zc>& t) {
+    const int N = 2 * n;
+    std::vector<double> M((size_t)N * N), V;
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            double a = H[(size_t)i * n + j].real(), b = H[(size_t)i * n + j].imag();
+            M[(size_t)i * N + j] = a;
+            M[(size_t)i * N + (j + n)] = -b;
+            M[(size_t)(i + n) * N + j] = b;
+            M[(size_t)(i + n) * N + (j + n)] = a;
+        }
+    jacobi_eig_sym(N, M, V);
+    double smax = 0.0;
+    for (int i = 0; i < N; ++i) smax = std::max(smax, std::fabs(M[(size_t)i * N + i]));
+    const double tol = std::numeric_limits<double>::epsilon() * n * smax;
+    std::vector<double> rhs(N), out(N, 0.0);
+    for (int i = 0; i < n; ++i) {
+        rhs[i] = xi[i].real();
+        rhs[i + n] = xi[i].imag();
+    }
+    for (int e = 0; e < N; ++e) {
+        double lam = M[(size_t)e * N + e];
+        if (!(std::fabs(lam) > tol)) continue;
+        double proj = 0.0;
+        for (int k = 0; k < N; ++k) proj += V[(size_t)k * N + e] * rhs[k];
+        proj /= lam;
+        for (int k = 0; k < N; ++k) out[k] += V[(size_t)k * N + e] * proj;
+    }
+    t.resize(n);
+    for (int i = 0; i < n; ++i) t[i] = zc(out[i], out[i + n]);
+}
+
+// min_y || H(0:rows,0:cols) y - xi(0:rows) ||, H row-major with leading dimension ldh,
+// rows = cols+1 (Hessenberg block).  Householder QR on a copy; returns the residual norm.
+static inline double hessenberg_lsq(const std::vector<zc>& H, int ldh, int rows, int cols,
+                                    const std::vector<zc>& xi, std::vector<zc>& y) {
+    std::vector<zc> A((size_t)rows * cols), b(rows);
+    for (int i = 0; i < rows; ++i) {
+        b[i] = xi[i];
+        for (int j = 0; j < cols; ++j) A[(size_t)i * cols + j] = H[(size_t)i * ldh + j];
+    }
+    for (int k = 0; k < cols; ++k) {
+        double nrm = 0.0;
+        for (int i = k; i < rows; ++i) nrm += std::norm(A[(size_t)i * cols + k]);
+        nrm = std::sqrt(nrm);
+        if (nrm == 0.0) continue;
+        zc akk = A[(size_t)k * cols + k];
+        zc phase = (std::abs(akk) == 0.0) ? zc(1.0, 0.0) : akk / std::abs(akk);
+        zc alpha = -phase * nrm;
+        std::vector<zc> v(rows - k);
+        for (int i = k; i < rows; ++i) v[i - k] = A[(size_t)i * cols + k];
+        v[0] -= alpha;
+        double vn = 0.0;
+        for (auto& e : v) vn += std::norm(e);
+        if (vn == 0.0) continue;
+        for (int j = k; j < cols; ++j) {
+            zc s = 0.0;
+            for (int i = k; i < rows; ++i) s += std::conj(v[i - k]) * A[(size_t)i * cols + j];
+            s *= 2.0 / vn;
+            for (int i = k; i < rows; ++i) A[(size_t)i * cols + j] -= s * v[i - k];
+        }
+        zc s = 0.0;
+        for (int i = k; i < rows; ++i) s += std::conj(v[i - k]) * b[i];
+        s *= 2.0 / vn;
+        for (int i = k; i < rows; ++i) b[i] -= s * v[i - k];
+    }
+    y.assign(cols, zc(0.0, 0.0));
+    for (int k = cols - 1; k >= 0; --k) {
+        zc s = b[k];
+        for (int j = k + 1; j < cols; ++j) s -= A[(size_t)k * cols + j] * y[j];
+        zc akk = A[(size_t)k * cols + k];
+        y[k] = (std::abs(akk) == 0.0) ? zc(0.0, 0.0) : s / akk;
+    }
+    double res = 0.0;
+    for (int i = cols; i < rows; ++i) res += std::norm(b[i]);
+    return std::sqrt(res);
+}
+
+}  // namespace mgb200

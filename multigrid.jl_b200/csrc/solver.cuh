@@ -1,0 +1,669 @@
+// Device-resident multigrid cycle and Krylov drivers.
+//
+//   Hierarchy::cycle            <- recursiveCycle           src/Multigrid/MGcycle.jl:1-118
+//   Hierarchy::relax            <- relax                    src/Multigrid/MGcycle.jl:122-136
+//   Hierarchy::solve_coarsest   <- solveCoarsest            src/Multigrid/MGcycle.jl:138-181
+//   Hierarchy::fgmres_relaxation<- FGMRES_relaxation        src/Multigrid/FGMRES.jl:48-126
+//   Hierarchy::solveMG          <- solveMG                  src/Multigrid/SolveFuncs.jl:3-39
+//   Hierarchy::solveCG          <- solveCG_MG -> KrylovMethods.cg      SolveFuncs.jl:103-116
+//   Hierarchy::solveFGMRES      <- solveGMRES_MG -> KrylovMethods.fgmres SolveFuncs.jl:120-132
+//
+// The control flow runs on the host and only enqueues kernels; the V/F/W cycles contain no
+// host synchronisation at all (the reference's data-dependent `if norm(x)>0` is replaced by a
+// host-tracked "x is known to be zero" flag, which is result-identical: r - A*0 == r).
+#pragma once
+#include <functional>
+
+#include "launch.cuh"
+#include "smalldense.h"
+
+namespace mgb200 {
+
+template <typename TV>
+struct FgmresMem {  // FGMRESmem (FGMRES.jl:3-8): Z and V(=AZ) are (n*m) x inner
+    TV* Z = nullptr;
+    TV* AZ = nullptr;
+    TV* Az = nullptr;   // result buffer of Afun
+    TV* vp0 = nullptr;  // v_prec (x of the recursive call / D.*v) ...
+    TV* vp1 = nullptr;  // ... and its ping-pong partner
+    int inner = 0;
+    void release() {
+        dev_free(Z); dev_free(AZ); dev_free(Az); dev_free(vp0); dev_free(vp1);
+        inner = 0;
+    }
+};
+
+template <typename TV>
+struct Level {
+    long long n = 0;
+    Csr<TV> A;
+    Csr<double> P, R;
+    TV* d = nullptr;
+    TV *b = nullptr, *r = nullptr, *x0 = nullptr, *x1 = nullptr;  // CYCLEmem + ping-pong partner of x
+    FgmresMem<TV> memRelax, memK;
+    void release_work() {
+        dev_free(b); dev_free(r); dev_free(x0); dev_free(x1);
+        memRelax.release();
+        memK.release();
+    }
+    void release() {
+        release_work();
+        A.release(); P.release(); R.release();
+        dev_free(d);
+        n = 0;
+    }
+};
+
+template <typename TV>
+struct Coarsest {
+    int n = 0;
+    TV* linv = nullptr;
+    TV* uinv = nullptr;
+    int* perm = nullptr;
+    TV* y = nullptr;  // n*m scratch
+    void release() {
+        dev_free(linv); dev_free(uinv); dev_free(perm); dev_free(y);
+        n = 0;
+    }
+};
+
+struct HierarchyBase {
+    virtual ~HierarchyBase() {}
+    int val_type = 0;
+    Context ctx;
+};
+
+template <typename TV>
+struct Hierarchy : HierarchyBase {
+    int levels = 0;
+    int m = 1;  // nrhs
+    char cycle_type = 'V';
+    int relax_kind = 0;
+    std::vector<int> pre, post;
+    std::vector<Level<TV>> L;  // L[0] finest ... L[levels-1] coarsest (only n, b, r, x used there)
+    Coarsest<TV> coarse;
+    Csr<TV> Akry;              // optional Krylov matrix
+    bool work_ready = false;
+    // Krylov workspace (fine level)
+    TV *kr = nullptr, *kp = nullptr, *kAp = nullptr, *kw = nullptr, *kV = nullptr, *kZ = nullptr;
+    int kV_cols = 0;
+    TV* hstage = nullptr;  // device staging for host<->device layout changes
+    long long hstage_n = 0;
+    // the caller's x (level-1 iterate of solveMG / the Krylov iterate) and its ping-pong partner;
+    // L[0].x0/x1 are memCycle[1].x, the z of the preconditioner closure (SolveFuncs.jl:50,59)
+    TV *ux0 = nullptr, *ux1 = nullptr, *ucur = nullptr;
+
+    Hierarchy(int nlevels, int nrhs, char ct, int rk, const int64_t* rpre, const int64_t* rpost, int dev) {
+        MGB_CHECK(nlevels >= 1, "levels must be >= 1");
+        MGB_CHECK(nrhs >= 1, "nrhs must be >= 1");
+        levels = nlevels;
+        m = nrhs;
+        relax_kind = rk;
+        L.resize(levels);
+        set_cycle(ct, rpre, rpost);
+        ctx.init(dev);
+    }
+    ~Hierarchy() override {
+        cudaSetDevice(ctx.device);
+        if (ctx.stream) cudaStreamSynchronize(ctx.stream);
+        for (auto& l : L) l.release();
+        coarse.release();
+        Akry.release();
+        free_krylov();
+        dev_free(hstage);
+        dev_free(ux0);
+        dev_free(ux1);
+        ctx.destroy();
+    }
+    void set_cycle(char ct, const int64_t* rpre, const int64_t* rpost) {
+        MGB_CHECK(ct == 'V' || ct == 'F' || ct == 'W' || ct == 'K', "cycle_type must be V, F, W or K");
+        cycle_type = ct;
+        if (rpre && rpost) {
+            pre.assign(levels, 0);
+            post.assign(levels, 0);
+            for (int l = 0; l < levels; ++l) {
+                pre[l] = (int)rpre[l];
+                post[l] = (int)rpost[l];
+            }
+        }
+        work_ready = false;
+    }
+    void free_krylov() {
+        dev_free(kr); dev_free(kp); dev_free(kAp); dev_free(kw); dev_free(kV); dev_free(kZ);
+        kV_cols = 0;
+    }
+
+    // ---- upload ---------------------------------------------------------------------------
+    void upload_level(int level, long long n, long long nc, const int64_t* acp, const int64_t* arv,
+                      const void* anz, const int64_t* pcp, const int64_t* prv, const double* pnz,
+                      const int64_t* rcp, const int64_t* rrv, const double* rnz, const void* d, int base) {
+        MGB_CHECK(level >= 1 && level < levels, "upload_level: level must be in 1..levels-1");
+        MGB_CHECK(base == 0 || base == 1, "index_base must be 0 or 1");
+        MGB_CUDA(cudaSetDevice(ctx.device));
+        Level<TV>& lv = L[level - 1];
+        lv.n = n;
+        upload_csr<TV>(ctx, lv.A, n, n, acp, arv, static_cast<const TV*>(anz), base, true);
+        upload_csr<double>(ctx, lv.P, n, nc, pcp, prv, pnz, base, false);
+        upload_csr<double>(ctx, lv.R, nc, n, rcp, rrv, rnz, base, false);
+        dev_free(lv.d);
+        lv.d = dev_alloc<TV>(n);
+        MGB_CUDA(cudaMemcpy(lv.d, d, n * sizeof(TV), cudaMemcpyHostToDevice));
+        L[level].n = nc;
+        work_ready = false;
+    }
+
+    void upload_coarsest(long long n, const int64_t* cp, const int64_t* rv, const void* nz, int base) {
+        MGB_CHECK(n >= 1 && n <= 46000, "coarsest grid size out of range for the dense device LU");
+        MGB_CUDA(cudaSetDevice(ctx.device));
+        Level<TV>& lv = L[levels - 1];
+        lv.n = n;
+        upload_csr<TV>(ctx, lv.A, n, n, cp, rv, static_cast<const TV*>(nz), base, true);
+        coarse.release();
+        coarse.n = (int)n;
+        const int N = (int)n;
+        TV* a = dev_alloc<TV>((size_t)N * N);
+        MGB_CUDA(cudaMemsetAsync(a, 0, (size_t)N * N * sizeof(TV), ctx.stream));
+        densify_kernel<TV><<<cdiv(N, 128), 128, 0, ctx.stream>>>(N, lv.A.rowptr, lv.A.colind, lv.A.val, a);
+        MGB_LAUNCH_CHECK();
+        int* piv = dev_alloc<int>(N + 1);
+        int* info = piv + N;
+        MGB_CUDA(cudaMemsetAsync(info, 0, sizeof(int), ctx.stream));
+        for (int k = 0; k < N; ++k) {
+            lu_pivot_kernel<TV><<<1, 256, 0, ctx.stream>>>(a, N, k, piv, info);
+            const int rem = N - k - 1;
+            if (rem > 0) {
+                dim3 blk(32, 8), grd(cdiv(rem, 32), cdiv(rem, 8));
+                lu_update_kernel<TV><<<grd, blk, 0, ctx.stream>>>(a, N, k);
+            }
+        }
+        MGB_LAUNCH_CHECK();
+        std::vector<int> hpiv(N + 1);
+        MGB_CUDA(cudaMemcpyAsync(hpiv.data(), piv, (N + 1) * sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+        ctx.sync();
+        MGB_CHECK(hpiv[N] == 0, "coarsest matrix is exactly singular (zero pivot in LU)");
+        std::vector<int> perm(N);
+        for (int i = 0; i < N; ++i) perm[i] = i;
+        for (int k = 0; k < N; ++k) std::swap(perm[k], perm[hpiv[k]]);
+        coarse.perm = dev_alloc<int>(N);
+        MGB_CUDA(cudaMemcpy(coarse.perm, perm.data(), N * sizeof(int), cudaMemcpyHostToDevice));
+        coarse.linv = dev_alloc<TV>((size_t)N * N);
+        coarse.uinv = dev_alloc<TV>((size_t)N * N);
+        lower_inverse_kernel<TV><<<cdiv(N, 64), 64, 0, ctx.stream>>>(a, N, coarse.linv);
+        upper_inverse_kernel<TV><<<cdiv(N, 64), 64, 0, ctx.stream>>>(a, N, coarse.uinv);
+        MGB_LAUNCH_CHECK();
+        ctx.sync();
+        dev_free(a);
+        dev_free(piv);
+        work_ready = false;
+    }
+
+    void set_krylov_matrix(long long n, const int64_t* cp, const int64_t* rv, const void* nz, int base) {
+        MGB_CUDA(cudaSetDevice(ctx.device));
+        MGB_CHECK(n == L[0].n, "Krylov matrix size differs from the fine level");
+        upload_csr<TV>(ctx, Akry, n, n, cp, rv, static_cast<const TV*>(nz), base, true);
+    }
+
+    // ---- workspaces (adjustMemoryForNumRHS, MGsetup.jl:166-223) -----------------------------
+    void adjust_nrhs(int nrhs) {
+        MGB_CHECK(nrhs >= 1, "nrhs must be >= 1");
+        if (nrhs != m) {
+            m = nrhs;
+            work_ready = false;
+        }
+    }
+    void ensure_work() {
+        if (work_ready) return;
+        MGB_CUDA(cudaSetDevice(ctx.device));
+        for (int l = 0; l < levels; ++l) {
+            Level<TV>& lv = L[l];
+            MGB_CHECK(lv.n > 0, "hierarchy level not uploaded");
+            if (l < levels - 1) MGB_CHECK(lv.A.present() && lv.P.present() && lv.R.present(), "hierarchy level not uploaded");
+            lv.release_work();
+            const size_t nm = (size_t)lv.n * m;
+            lv.b = dev_alloc<TV>(nm);
+            lv.r = dev_alloc<TV>(nm);
+            lv.x0 = dev_alloc<TV>(nm);
+            lv.x1 = dev_alloc<TV>(nm);
+            MGB_CUDA(cudaMemsetAsync(lv.x0, 0, nm * sizeof(TV), ctx.stream));
+            MGB_CUDA(cudaMemsetAsync(lv.x1, 0, nm * sizeof(TV), ctx.stream));
+            MGB_CUDA(cudaMemsetAsync(lv.b, 0, nm * sizeof(TV), ctx.stream));
+            if (l < levels - 1 && relax_kind == 1) {
+                alloc_fgmres(lv.memRelax, nm, std::max(std::max(pre[l], post[l]), 1));
+            }
+            // memKcycle[level] of the reference belongs to level+1 (MGsetup.jl:213-215): sized here
+            // for level l (1-based l+1 >= 2) and used when the parent recurses into it.
+            if (cycle_type == 'K' && l >= 1 && l < levels - 1) alloc_fgmres(lv.memK, nm, 2);
+        }
+        MGB_CHECK(coarse.n == (int)L[levels - 1].n, "coarsest factorisation missing (mgb200_upload_coarsest)");
+        dev_free(coarse.y);
+        coarse.y = dev_alloc<TV>((size_t)coarse.n * m);
+        free_krylov();
+        dev_free(hstage);
+        hstage_n = 0;
+        dev_free(ux0);
+        dev_free(ux1);
+        ux0 = dev_alloc<TV>((size_t)L[0].n * m);
+        ux1 = dev_alloc<TV>((size_t)L[0].n * m);
+        MGB_CUDA(cudaMemsetAsync(ux0, 0, (size_t)L[0].n * m * sizeof(TV), ctx.stream));
+        MGB_CUDA(cudaMemsetAsync(ux1, 0, (size_t)L[0].n * m * sizeof(TV), ctx.stream));
+        ucur = ux0;
+        ctx.sync();
+        work_ready = true;
+    }
+    void alloc_fgmres(FgmresMem<TV>& mem, size_t nm, int inner) {
+        mem.release();
+        mem.inner = inner;
+        mem.Z = dev_alloc<TV>(nm * inner);
+        mem.AZ = dev_alloc<TV>(nm * inner);
+        mem.Az = dev_alloc<TV>(nm);
+        mem.vp0 = dev_alloc<TV>(nm);
+        mem.vp1 = dev_alloc<TV>(nm);
+    }
+    void ensure_krylov(int vcols, bool needZ) {
+        const size_t nm = (size_t)L[0].n * m;
+        if (!kr) {
+            kr = dev_alloc<TV>(nm);
+            kp = dev_alloc<TV>(nm);
+            kAp = dev_alloc<TV>(nm);
+            kw = dev_alloc<TV>(nm);
+        }
+        if (vcols > kV_cols || (needZ && !kZ)) {
+            dev_free(kV);
+            dev_free(kZ);
+            kV_cols = std::max(vcols, kV_cols);
+            kV = dev_alloc<TV>(nm * kV_cols);
+            kZ = dev_alloc<TV>(nm * kV_cols);
+        }
+    }
+
+    // ---- building blocks ----------------------------------------------------------------------
+    const Csr<TV>& krylov_A() const { return Akry.present() ? Akry : L[0].A; }
+
+    void apply_A(const Csr<TV>& A, const TV* x, TV* y, int level) {  // y = A x   (getAfun, SolveFuncs.jl:65-71)
+        csr_apply<TV, TV>(ctx, A, MODE_SPMV, x, nullptr, nullptr, y, m, K_SPMV, level);
+    }
+    void residual(const Csr<TV>& A, const TV* b, const TV* x, TV* r, int level) {  // r = b - A x
+        csr_apply<TV, TV>(ctx, A, MODE_RESID, x, b, nullptr, r, m, K_RESID, level);
+    }
+    double norm(long long n, const TV* x) {
+        dev_norm2sq<TV>(ctx, n, x, ctx.scal + 8);
+        double v;
+        read_scalars(ctx, ctx.scal + 8, 1, &v);
+        return std::sqrt(v);
+    }
+    zc dot(long long n, const TV* x, const TV* y) {
+        dev_dot<TV>(ctx, n, x, y, ctx.scal + 10);
+        double v[2];
+        read_scalars(ctx, ctx.scal + 10, 2, v);
+        return zc(v[0], v[1]);
+    }
+    static TV to_tv(zc a) { return VT<TV>::make(a.real(), a.imag()); }
+
+    // relax (MGcycle.jl:122-136) fused: each sweep is  x' = x + d.*(b - A x).  With x known to be
+    // zero the first sweep is x = d.*b.  Returns the buffer holding the result (x or scratch).
+    TV* relax(int l, const TV* b, TV* x, TV* scratch, int numit, bool xzero) {
+        Level<TV>& lv = L[l];
+        int sweeps = std::max(numit, 1);  // numit = 0 still does one update (MGcycle.jl:134)
+        if (xzero) {
+            Launch La(ctx, K_DIAG, l + 1, (2.0 * m + 1.0) * lv.n * sizeof(TV));
+            diag_scale_kernel<TV><<<ctx.ew_blocks(lv.n * m), 256, 0, ctx.stream>>>(lv.n, m, lv.d, b, x);
+            MGB_LAUNCH_CHECK();
+            sweeps -= 1;
+        }
+        for (int s = 0; s < sweeps; ++s) {
+            csr_apply<TV, TV>(ctx, lv.A, MODE_SWEEP, x, b, lv.d, scratch, m, K_SWEEP, l + 1);
+            std::swap(x, scratch);
+        }
+        return x;
+    }
+
+    void solve_coarsest(const TV* b, TV* x) {  // x = A_L^{-1} b  (MGcycle.jl:176-179)
+        const int n = coarse.n;
+        Launch La(ctx, K_COARSE, levels, (double)n * n * sizeof(TV));
+        const int grid = cdiv((long long)n * m * 32, 256);
+        lower_apply_kernel<TV><<<grid, 256, 0, ctx.stream>>>(n, m, coarse.linv, coarse.perm, b, coarse.y);
+        upper_apply_kernel<TV><<<grid, 256, 0, ctx.stream>>>(n, m, coarse.uinv, coarse.y, x);
+        MGB_LAUNCH_CHECK();
+    }
+
+    typedef std::function<TV*(const TV*)> PrecFn;
+
+    // FGMRES_relaxation (FGMRES.jl:48-126).  x0 += Z t.  Returns the number of inner steps done.
+    int fgmres_relaxation(const Csr<TV>& A, int level, const TV* r0, TV* x0, int inner, const PrecFn& prec,
+                          double TOL, FgmresMem<TV>& mem, long long n) {
+        const long long nm = n * m;
+        MGB_CHECK(mem.inner == inner, "FGMRES_relaxation: size of Krylov subspace is different than inner");
+        MGB_CHECK(inner <= MAXK, "FGMRES_relaxation: inner too large");
+        dev_zero<TV>(ctx, nm * inner, mem.Z);   // resetMem (FGMRES.jl:10-15)
+        dev_zero<TV>(ctx, nm * inner, mem.AZ);
+        const double rnorm0 = norm(nm, r0);
+        std::vector<zc> H((size_t)inner * inner, zc(0, 0)), xi(inner, zc(0, 0)), t(inner, zc(0, 0));
+        const TV* w = nullptr;
+        int done = 0;
+        for (int j = 0; j < inner; ++j) {
+            const TV* z = prec(j == 0 ? r0 : w);
+            dev_copy<TV>(ctx, nm, z, mem.Z + (size_t)j * nm);
+            apply_A(A, z, mem.Az, level);
+            w = mem.Az;
+            dev_copy<TV>(ctx, nm, w, mem.AZ + (size_t)j * nm);
+            // t = AZ^H w over all `inner` columns (unused ones are zero), xi[j] = <w, r0>
+            dev_multi_dot<TV>(ctx, nm, mem.AZ, nm, inner, w, ctx.scal + 16);
+            dev_dot<TV>(ctx, nm, w, r0, ctx.scal + 16 + 2 * inner);
+            std::vector<double> hv(2 * inner + 2);
+            read_scalars(ctx, ctx.scal + 16, 2 * inner + 2, hv.data());
+            for (int i = 0; i < inner; ++i) t[i] = zc(hv[2 * i], hv[2 * i + 1]);
+            xi[j] = zc(hv[2 * inner], hv[2 * inner + 1]);
+            for (int i = 0; i < inner; ++i) H[(size_t)i * inner + j] = t[i];
+            for (int i = 0; i < inner; ++i) H[(size_t)j * inner + i] = std::conj(t[i]);
+            std::vector<zc> Hs((size_t)inner * inner);
+            for (int a = 0; a < inner; ++a)
+                for (int c = 0; c < inner; ++c)
+                    Hs[(size_t)a * inner + c] = 0.5 * H[(size_t)a * inner + c] + 0.5 * std::conj(H[(size_t)c * inner + a]);
+            H = Hs;
+            hermitian_pinv_apply(inner, H, xi, t);
+            zc tHt(0, 0), txi(0, 0);
+            for (int a = 0; a < inner; ++a) {
+                zc Ht(0, 0);
+                for (int c = 0; c < inner; ++c) Ht += H[(size_t)a * inner + c] * t[c];
+                tHt += std::conj(t[a]) * Ht;
+                txi += std::conj(t[a]) * xi[a];
+            }
+            const double rn = std::sqrt(std::fabs((tHt - 2.0 * txi + rnorm0 * rnorm0).real()));
+            done = j + 1;
+            if (rn < TOL) break;
+        }
+        std::vector<TV> coef(inner);
+        for (int i = 0; i < inner; ++i) coef[i] = to_tv(t[i]);
+        dev_multi_axpy<TV>(ctx, nm, mem.Z, nm, inner, coef.data(), 1.0, x0, nullptr);  // x0 += Z t
+        return done;
+    }
+
+    // recursiveCycle (MGcycle.jl:1-118).  l is 0-based.  x holds the iterate, scratch is its
+    // ping-pong partner; returns the buffer with the result.  ctype is passed down explicitly
+    // (the reference flips param.cycleType for the V leg of an F cycle, :82-84).
+    TV* cycle(int l, const TV* b, TV* x, TV* scratch, bool xzero, char ctype) {
+        if (l == levels - 1) {  // only when levels == 1 (MGcycle.jl:13-18)
+            solve_coarsest(b, x);
+            return x;
+        }
+        Level<TV>& lv = L[l];
+        Level<TV>& lc = L[l + 1];
+        const int npre = pre[l], npost = post[l];
+        TV* xc_cur;
+        // ---- pre-relaxation ----
+        if (relax_kind == 1) {
+            if (xzero) dev_zero<TV>(ctx, lv.n * m, x);
+            if (xzero) dev_copy<TV>(ctx, lv.n * m, b, lv.r); else residual(lv.A, b, x, lv.r, l + 1);
+            jac_gmres(l, lv.r, x, std::max(npre, 1));
+        } else {
+            TV* xn = relax(l, b, x, scratch, npre, xzero);
+            if (xn != x) std::swap(x, scratch);
+        }
+        residual(lv.A, b, x, lv.r, l + 1);                                          // :58-60
+        csr_apply<double, TV>(ctx, lv.R, MODE_SPMV, lv.r, nullptr, nullptr, lc.b, m, K_RESTRICT, l + 1);  // :66
+        if (l + 1 == levels - 1) {
+            solve_coarsest(lc.b, lc.x0);                                           // :67-69
+            xc_cur = lc.x0;
+        } else if (ctype == 'K') {                                                 // :72-76
+            FgmresMem<TV>& mk = lc.memK;
+            dev_zero<TV>(ctx, lc.n * m, lc.x0);
+            PrecFn mmg = [&, this](const TV* v) -> TV* { return cycle(l + 1, v, mk.vp0, mk.vp1, true, 'K'); };
+            fgmres_relaxation(lc.A, l + 2, lc.b, lc.x0, 2, mmg, 1e-5, mk, lc.n);
+            xc_cur = lc.x0;
+        } else {
+            xc_cur = cycle(l + 1, lc.b, lc.x0, lc.x1, true, ctype);                // :78
+            if (ctype == 'W') {
+                TV* other = (xc_cur == lc.x0) ? lc.x1 : lc.x0;
+                xc_cur = cycle(l + 1, lc.b, xc_cur, other, false, 'W');            // :79-80
+            } else if (ctype == 'F') {
+                TV* other = (xc_cur == lc.x0) ? lc.x1 : lc.x0;
+                xc_cur = cycle(l + 1, lc.b, xc_cur, other, false, 'V');            // :81-85
+            }
+        }
+        csr_apply<double, TV>(ctx, lv.P, MODE_ADD, xc_cur, nullptr, nullptr, x, m, K_PROLONG, l + 1);  // :90
+        // ---- post-relaxation (:92-103) ----
+        if (relax_kind == 1) {
+            residual(lv.A, b, x, lv.r, l + 1);
+            jac_gmres(l, lv.r, x, std::max(npost, 1));
+            return x;
+        }
+        return relax(l, b, x, scratch, npost, false);
+    }
+
+    // "Jac-GMRES" smoother: FGMRES_relaxation with MM(v) = D.*v (MGcycle.jl:33-36,48-51,96-99)
+    void jac_gmres(int l, const TV* r, TV* x, int inner) {
+        Level<TV>& lv = L[l];
+        FgmresMem<TV>& mem = lv.memRelax;
+        if (mem.inner != inner) alloc_fgmres(mem, (size_t)lv.n * m, inner);
+        PrecFn mm = [&, this](const TV* v) -> TV* {
+            // y = D .* v  (0 + d*v is exact)
+            Launch La(ctx, K_DIAG, l + 1, (2.0 * m + 1.0) * lv.n * sizeof(TV));
+            diag_scale_kernel<TV><<<ctx.ew_blocks(lv.n * m), 256, 0, ctx.stream>>>(lv.n, m, lv.d, v, mem.vp0);
+            MGB_LAUNCH_CHECK();
+            return mem.vp0;
+        };
+        fgmres_relaxation(lv.A, l + 1, r, x, inner, mm, 1e-5, mem, lv.n);
+    }
+
+    // one cycle on the caller's buffers (b in L[0].b, x in ucur); the result pointer is returned
+    TV* cycle_top(bool xzero) {
+        ensure_work();
+        TV* other = (ucur == ux0) ? ux1 : ux0;
+        ucur = cycle(0, L[0].b, ucur, other, xzero, cycle_type);
+        return ucur;
+    }
+
+    // ---- solveMG (SolveFuncs.jl:3-39) on the device buffers L[0].b / xcur ---------------------
+    int solveMG(double tol, int max_iter, double* resvec) {
+        ensure_work();
+        Level<TV>& lv = L[0];
+        const long long nm = lv.n * m;
+        TV*& xcur = ucur;
+        bool xzero = (norm(nm, xcur) == 0.0);
+        double res;
+        if (xzero) {
+            res = norm(nm, lv.b);
+        } else {
+            residual(lv.A, lv.b, xcur, lv.r, 1);
+            res = norm(nm, lv.r);
+        }
+        const double res_init = res;
+        resvec[0] = res_init;
+        int iter = 0;
+        for (int count = 1; count <= max_iter; ++count) {
+            TV* other = (xcur == ux0) ? ux1 : ux0;
+            xcur = cycle(0, lv.b, xcur, other, xzero, cycle_type);
+            xzero = false;
+            residual(lv.A, lv.b, xcur, lv.r, 1);
+            iter += 1;
+            res = norm(nm, lv.r);
+            resvec[count] = res;
+            if (res / res_init < tol) break;
+        }
+        return iter;
+    }
+
+    // getMultigridPreconditioner (SolveFuncs.jl:43-63): z .= 0; recursiveCycle(param,r,z,1); z
+    TV* precondition(const TV* r) {
+        Level<TV>& lv = L[0];
+        return cycle(0, r, lv.x0, lv.x1, true, cycle_type);
+    }
+
+    // ---- KrylovMethods.cg with M = one cycle (solveCG_MG, SolveFuncs.jl:103-116) --------------
+    // b: L[0].b, x: in/out buffer xk (n).  resvec[max_iter].  Returns iterations; flag out.
+    int solveCG(TV* xk, double tol, int max_iter, int* flag, double* resvec) {
+        ensure_work();
+        MGB_CHECK(m == 1, "solveCG: block CG (nrhs > 1) goes through solveBlockCG");
+        MGB_CHECK(!VT<TV>::is_complex, "KrylovMethods.cg compares alpha < 0 and is real-only");
+        ensure_krylov(0, false);
+        Level<TV>& lv = L[0];
+        const long long n = lv.n;
+        const Csr<TV>& A = krylov_A();
+        const TV* b = lv.b;
+        const double nb = norm(n, b);
+        if (nb == 0.0) {
+            dev_zero<TV>(ctx, n, xk);
+            *flag = -9;
+            resvec[0] = 0.0;
+            return 0;
+        }
+        residual(A, b, xk, kr, 1);                       // r = b - A(x)
+        TV* z = precondition(kr);                        // z = M(r)
+        dev_copy<TV>(ctx, n, z, kp);                     // p = copy(z)
+        double* s = ctx.scal;                            // s[0]=gamma s[2]=delta s[4]=rr s[6]=gamma_new
+        dev_dot<TV>(ctx, n, kr, z, s + 0);
+        *flag = -1;
+        int last = 0;
+        for (int it = 1; it <= max_iter; ++it) {
+            last = it;
+            apply_A(A, kp, kAp, 1);                      // Ap = A(p)
+            dev_dot<TV>(ctx, n, kp, kAp, s + 2);         // delta = <p,Ap>   (gamma = <r,z> already in s[0])
+            {
+                Launch La(ctx, K_VECTOR, 0, 6.0 * n * sizeof(TV));
+                cg_update_kernel<TV><<<ctx.red_blocks(n), RED_THREADS, 0, ctx.stream>>>(n, s, kp, kAp, xk, kr, ctx.red, s + 4);
+                MGB_LAUNCH_CHECK();
+            }
+            double hv[6];
+            read_scalars(ctx, s, 6, hv);
+            const double alpha = hv[0] / hv[2];
+            if (std::isinf(alpha) || alpha < 0.0) {
+                *flag = -2;
+                break;
+            }
+            resvec[it - 1] = std::sqrt(hv[4]) / nb;
+            if (resvec[it - 1] <= tol) {
+                *flag = 0;
+                break;
+            }
+            z = precondition(kr);
+            dev_dot<TV>(ctx, n, z, kr, s + 6);           // <z,r>
+            {
+                Launch La(ctx, K_VECTOR, 0, 3.0 * n * sizeof(TV));
+                cg_direction_kernel<TV><<<ctx.ew_blocks(n), 256, 0, ctx.stream>>>(n, s + 6, s + 0, z, kp);
+                MGB_LAUNCH_CHECK();
+            }
+            // gamma for the next iteration: dot(r,z) == dot(z,r) bit for bit in real arithmetic
+            MGB_CUDA(cudaMemcpyAsync(s + 0, s + 6, 2 * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
+        }
+        return last;
+    }
+
+    // ---- KrylovMethods.fgmres with M = one cycle (solveGMRES_MG, SolveFuncs.jl:120-132) ---------
+    int solveFGMRES(TV* xk, int restrt, bool flexible, double tol, int max_iter, int* flag, double* resvec,
+                    int* nres) {
+        ensure_work();
+        MGB_CHECK(m == 1, "solveFGMRES: blockFGMRES (nrhs > 1) is not provided yet");
+        Level<TV>& lv = L[0];
+        const long long n = lv.n;
+        restrt = (int)std::min<long long>(restrt, n - 1);
+        MGB_CHECK(restrt >= 1 && restrt <= MAXK, "fgmres: restart length must be in 1..32");
+        ensure_krylov(restrt, true);
+        const Csr<TV>& A = krylov_A();
+        const TV* b = lv.b;
+        *nres = 0;
+        const double rnorm0 = norm(n, b);
+        if (rnorm0 == 0.0) {
+            dev_zero<TV>(ctx, n, xk);
+            *flag = -9;
+            return 0;
+        }
+        residual(A, b, xk, kr, 1);
+        double err = norm(n, kr) / rnorm0;
+        if (err < tol) {
+            *flag = 0;
+            resvec[0] = err;
+            *nres = 1;
+            return 0;
+        }
+        *flag = -1;
+        int counter = 0, it = 0;
+        const int ldh = restrt;
+        while (it < max_iter) {
+            it += 1;
+            std::vector<zc> H((size_t)(restrt + 1) * ldh, zc(0, 0)), xi(restrt + 1, zc(0, 0)), y;
+            double betta = norm(n, kr);
+            xi[0] = betta;
+            dev_axpby<TV>(ctx, n, VT<TV>::from_real(1.0 / betta), kr, VT<TV>::zero(), kw, true);  // w = r/betta
+            dev_copy<TV>(ctx, n, kw, kV);
+            int jdone = 0;
+            for (int j = 0; j < restrt; ++j) {
+                TV* z = precondition(kw);                                        // z = M(w)
+                if (flexible) dev_copy<TV>(ctx, n, z, kZ + (size_t)j * n);
+                apply_A(A, z, kw, 1);                                            // w = A(z)
+                counter += 1;
+                dev_multi_dot<TV>(ctx, n, kV, n, j + 1, kw, ctx.scal + 16);      // t = V'w
+                std::vector<double> hv(2 * (j + 1));
+                read_scalars(ctx, ctx.scal + 16, 2 * (j + 1), hv.data());
+                std::vector<TV> coef(j + 1);
+                for (int i = 0; i <= j; ++i) {
+                    H[(size_t)i * ldh + j] = zc(hv[2 * i], hv[2 * i + 1]);
+                    coef[i] = to_tv(-H[(size_t)i * ldh + j]);
+                }
+                dev_multi_axpy<TV>(ctx, n, kV, n, j + 1, coef.data(), 1.0, kw, ctx.scal + 12);  // w -= V t, ||w||^2
+                double nw2;
+                read_scalars(ctx, ctx.scal + 12, 1, &nw2);
+                betta = std::sqrt(nw2);
+                H[(size_t)(j + 1) * ldh + j] = betta;
+                dev_axpby<TV>(ctx, n, VT<TV>::from_real(1.0 / betta), kw, VT<TV>::zero(), kw, true);  // w *= 1/betta
+                if (j + 1 < restrt) dev_copy<TV>(ctx, n, kw, kV + (size_t)(j + 1) * n);
+                err = hessenberg_lsq(H, ldh, j + 2, j + 1, xi, y) / rnorm0;
+                resvec[counter - 1] = err;
+                jdone = j + 1;
+                if (err <= tol) {
+                    *flag = 0;
+                    break;
+                }
+            }
+            hessenberg_lsq(H, ldh, jdone + 1, jdone, xi, y);                      // y = pinv(H)*xi
+            std::vector<TV> coef(jdone);
+            for (int i = 0; i < jdone; ++i) coef[i] = to_tv(y[i]);
+            if (flexible) {
+                dev_multi_axpy<TV>(ctx, n, kZ, n, jdone, coef.data(), 1.0, xk, nullptr);  // x += Z y
+            } else {
+                dev_multi_axpy<TV>(ctx, n, kV, n, jdone, coef.data(), 0.0, kAp, nullptr);  // V y
+                TV* z = precondition(kAp);
+                dev_axpby<TV>(ctx, n, VT<TV>::one(), z, VT<TV>::one(), xk, false);        // x += M(V y)
+            }
+            if (*flag == 0) break;
+            if (it < max_iter) residual(A, b, xk, kr, 1);
+        }
+        *nres = counter;
+        return it;
+    }
+
+    // ---- host <-> device layout helpers -------------------------------------------------------
+    void h2d_vec(const void* host, TV* dst, long long n) {
+        const long long nm = n * m;
+        if (m == 1) {
+            MGB_CUDA(cudaMemcpyAsync(dst, host, nm * sizeof(TV), cudaMemcpyHostToDevice, ctx.stream));
+            return;
+        }
+        if (hstage_n < nm) {
+            dev_free(hstage);
+            hstage = dev_alloc<TV>(nm);
+            hstage_n = nm;
+        }
+        MGB_CUDA(cudaMemcpyAsync(hstage, host, nm * sizeof(TV), cudaMemcpyHostToDevice, ctx.stream));
+        colmajor_to_rhsfast_kernel<TV><<<ctx.ew_blocks(nm), 256, 0, ctx.stream>>>(n, m, hstage, dst);
+        MGB_LAUNCH_CHECK();
+    }
+    void d2h_vec(const TV* src, void* host, long long n) {
+        const long long nm = n * m;
+        if (m == 1) {
+            MGB_CUDA(cudaMemcpyAsync(host, src, nm * sizeof(TV), cudaMemcpyDeviceToHost, ctx.stream));
+            ctx.sync();
+            return;
+        }
+        if (hstage_n < nm) {
+            dev_free(hstage);
+            hstage = dev_alloc<TV>(nm);
+            hstage_n = nm;
+        }
+        rhsfast_to_colmajor_kernel<TV><<<ctx.ew_blocks(nm), 256, 0, ctx.stream>>>(n, m, src, hstage);
+        MGB_LAUNCH_CHECK();
+        MGB_CUDA(cudaMemcpyAsync(host, hstage, nm * sizeof(TV), cudaMemcpyDeviceToHost, ctx.stream));
+        ctx.sync();
+    }
+};
+
+}  // namespace mgb200
