@@ -142,6 +142,11 @@ int64_t mgb200_launch_count(mgb200_handle h);
 int mgb200_event_record(mgb200_handle h, int idx);
 int mgb200_event_elapsed_ms(mgb200_handle h, int i0, int i1, double* ms);
 
+/* cudaProfilerStart / cudaProfilerStop, so that `ncu --profile-from-start off` captures exactly
+ * the timed region of bench.py. */
+int mgb200_profiler_start(void);
+int mgb200_profiler_stop(void);
+
 /* kinds used in profile records */
 #define MGB200_K_SWEEP 0    /* x' = x + d.*(b - A x)         */
 #define MGB200_K_RESID 1    /* r = b - A x                    */

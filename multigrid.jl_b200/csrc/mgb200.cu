@@ -8,6 +8,8 @@
 #include <string>
 #include <type_traits>
 
+#include <cuda_profiler_api.h>
+
 #include "solver.cuh"
 
 using namespace mgb200;
@@ -369,6 +371,17 @@ int mgb200_event_elapsed_ms(mgb200_handle h, int i0, int i1, double* ms) {
         MGB_CUDA(cudaEventElapsedTime(&f, c.user_ev[i0], c.user_ev[i1]));
         *ms = f;
     });
+    MGB_CATCH
+}
+
+int mgb200_profiler_start(void) {
+    MGB_TRY
+    MGB_CUDA(cudaProfilerStart());
+    MGB_CATCH
+}
+int mgb200_profiler_stop(void) {
+    MGB_TRY
+    MGB_CUDA(cudaProfilerStop());
     MGB_CATCH
 }
 
