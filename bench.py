@@ -121,6 +121,16 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(rows), "power_w_max": max(r[3] for r in rows)}
 
 
+def ncu_traffic(cells, dom):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)
+        return t[f"cfg2_{cells}"][f"{dom['kind']}_level{dom['level']}"]["traffic_bytes"]
+    except Exception:
+        return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -265,7 +275,7 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": f"{dom['kind']} level {dom['level']} (fused Jacobi sweep x' = x + d.*(b - A x))"
                 if dom["kind"] == "sweep" else f"{dom['kind']} level {dom['level']}",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "peak_source": peak_src, "traffic": None,
+                "peak_source": peak_src, "traffic": ncu_traffic(cells, dom),
                 "share_of_step": dom["total_ms"] / tot_ms,
                 "cycle_algorithmic_gb": nbytes / 1e9,
                 "cycle_achieved_gbs": nbytes / (ms_per_step * 1e-3) / 1e9,
