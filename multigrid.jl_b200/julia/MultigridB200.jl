@@ -1,0 +1,130 @@
+# ccall shim that re-points the solve phase of Multigrid.jl at libmgb200.so.
+#
+# It cannot be executed in this repository's build image (no Julia); it is the binding a
+# maintainer adds next to src/Multigrid/SolveFuncs.jl.  The host-side setup (MGsetup,
+# SA_AMGsetup, getMGparam, ...) stays untouched; only the functions below change.
+#
+# The library is located like the reference's own native libs (src/Multigrid/parRelax.jl:3,
+# Vanka.jl:7): deps/builds/<name>.
+module MultigridB200
+
+using SparseArrays, LinearAlgebra
+using Multigrid   # the reference package: MGparam, MGsetup, SA_AMGsetup, hierarchyExists, ...
+
+const libmgb200 = joinpath(dirname(pathof(Multigrid)), "..", "deps", "builds", "libmgb200")
+
+const MGB200_FP64  = Cint(0)
+const MGB200_CFP64 = Cint(1)
+valtype_code(::Type{Float64})    = MGB200_FP64
+valtype_code(::Type{ComplexF64}) = MGB200_CFP64
+
+check(status::Cint) = status == 0 ? nothing :
+    error("mgb200 status $status: ", unsafe_string(ccall((:mgb200_last_error, libmgb200), Cstring, ())))
+
+mutable struct DeviceHierarchy
+    handle::Ptr{Cvoid}
+end
+
+"""
+    uploadHierarchy(param; device=0) -> DeviceHierarchy
+
+Hands the raw CSC arrays of param.As / Ps / Rs (adjoint storage, 1-based Int64: MGdef.jl:75-77)
+and param.relaxPrecs to the device.  Julia owns the arrays; the library copies during the call.
+"""
+function uploadHierarchy(param::MGparam{VAL,Int64}; device::Integer=0) where {VAL}
+    hierarchyExists(param) || error("You have to do a setup first.")
+    levels = length(param.As)
+    nrhs = length(param.memCycle) > 0 ? size(param.memCycle[1].x, 2) : 1
+    pre  = Int64[param.relaxPre(l)  for l = 1:levels]
+    post = Int64[param.relaxPost(l) for l = 1:levels]
+    relaxKind = param.relaxType == "Jac-GMRES" ? Cint(1) : Cint(0)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:mgb200_create, libmgb200), Cint,
+                (Ref{Ptr{Cvoid}}, Cint, Cint, Cint, Cchar, Cint, Ptr{Int64}, Ptr{Int64}, Cint),
+                h, valtype_code(VAL), levels, nrhs, Cchar(param.cycleType), relaxKind, pre, post, device))
+    for l = 1:levels-1
+        AT, PT, RT = param.As[l], param.Ps[l], param.Rs[l]
+        d = convert(Vector{VAL}, param.relaxPrecs[l])
+        check(ccall((:mgb200_upload_level, libmgb200), Cint,
+                    (Ptr{Cvoid}, Cint, Int64, Int64,
+                     Ptr{Int64}, Ptr{Int64}, Ptr{VAL},
+                     Ptr{Int64}, Ptr{Int64}, Ptr{Float64},
+                     Ptr{Int64}, Ptr{Int64}, Ptr{Float64},
+                     Ptr{VAL}, Cint),
+                    h[], l, size(AT, 2), size(param.As[l+1], 2),
+                    AT.colptr, AT.rowval, AT.nzval,
+                    PT.colptr, PT.rowval, PT.nzval,
+                    RT.colptr, RT.rowval, RT.nzval,
+                    d, 1))
+    end
+    AL = param.As[end]
+    check(ccall((:mgb200_upload_coarsest, libmgb200), Cint,
+                (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{VAL}, Cint),
+                h[], size(AL, 2), AL.colptr, AL.rowval, AL.nzval, 1))
+    dev = DeviceHierarchy(h[])
+    finalizer(d -> ccall((:mgb200_destroy, libmgb200), Cint, (Ptr{Cvoid},), d.handle), dev)
+    return dev
+end
+
+# ---- src/Multigrid/SolveFuncs.jl:3-39 -----------------------------------------------------------
+function solveMG(param::MGparam{VAL,Int64}, dev::DeviceHierarchy, b::Array{VAL}, x::Array{VAL},
+                 verbose::Bool) where {VAL}
+    check(ccall((:mgb200_adjust_nrhs, libmgb200), Cint, (Ptr{Cvoid}, Cint), dev.handle, size(b, 2)))
+    iter = Ref{Cint}(0)
+    resvec = zeros(param.maxOuterIter + 1)
+    check(ccall((:mgb200_solveMG, libmgb200), Cint,
+                (Ptr{Cvoid}, Ptr{VAL}, Ptr{VAL}, Cdouble, Cint, Ref{Cint}, Ptr{Cdouble}),
+                dev.handle, b, x, param.relativeTol, param.maxOuterIter, iter, resvec))
+    if verbose
+        for k = 1:iter[]
+            println("Cycle ", k, " done with relres: ", resvec[k+1] / resvec[1],
+                    ". Convergence factor: ", resvec[k+1] / resvec[k])
+        end
+    end
+    return x, param, Int(iter[])
+end
+
+# ---- src/Multigrid/SolveFuncs.jl:103-116 ----------------------------------------------------------
+function solveCG_MG(AT::SparseMatrixCSC{VAL,Int64}, param::MGparam{VAL,Int64}, dev::DeviceHierarchy,
+                    b::Array{VAL}, x0::Array{VAL}, verbose::Bool=false) where {VAL}
+    check(ccall((:mgb200_adjust_nrhs, libmgb200), Cint, (Ptr{Cvoid}, Cint), dev.handle, size(b, 2)))
+    if AT !== param.As[1]
+        check(ccall((:mgb200_set_krylov_matrix, libmgb200), Cint,
+                    (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{VAL}, Cint),
+                    dev.handle, size(AT, 2), AT.colptr, AT.rowval, AT.nzval, 1))
+    end
+    iter = Ref{Cint}(0); flag = Ref{Cint}(0)
+    resvec = zeros(param.maxOuterIter * size(b, 2))
+    check(ccall((:mgb200_solveCG, libmgb200), Cint,
+                (Ptr{Cvoid}, Ptr{VAL}, Ptr{VAL}, Cdouble, Cint, Ref{Cint}, Ref{Cint}, Ptr{Cdouble}),
+                dev.handle, b, x0, param.relativeTol, param.maxOuterIter, iter, flag, resvec))
+    return x0, param, Int(iter[])
+end
+
+# ---- src/Multigrid/SolveFuncs.jl:120-132 ----------------------------------------------------------
+function solveGMRES_MG(AT::SparseMatrixCSC{VAL,Int64}, param::MGparam{VAL,Int64}, dev::DeviceHierarchy,
+                       b::Array{VAL}, x0::Array{VAL}, flexible::Bool, inner::Int64,
+                       verbose::Bool=false) where {VAL}
+    check(ccall((:mgb200_adjust_nrhs, libmgb200), Cint, (Ptr{Cvoid}, Cint), dev.handle, size(b, 2)))
+    iter = Ref{Cint}(0); flag = Ref{Cint}(0); nres = Ref{Cint}(0)
+    resvec = zeros(inner * param.maxOuterIter)
+    check(ccall((:mgb200_solveFGMRES, libmgb200), Cint,
+                (Ptr{Cvoid}, Ptr{VAL}, Ptr{VAL}, Cint, Cint, Cdouble, Cint, Ref{Cint}, Ref{Cint},
+                 Ptr{Cdouble}, Ref{Cint}),
+                dev.handle, b, x0, inner, flexible, param.relativeTol, param.maxOuterIter, iter, flag,
+                resvec, nres))
+    return x0, param, Int(iter[]), resvec[1:nres[]]
+end
+
+# ---- src/Multigrid/SolveFuncs.jl:43-63: r -> z (one cycle from z = 0) -----------------------------
+function getMultigridPreconditioner(param::MGparam{VAL,Int64}, dev::DeviceHierarchy, B::Array) where {VAL}
+    check(ccall((:mgb200_adjust_nrhs, libmgb200), Cint, (Ptr{Cvoid}, Cint), dev.handle, size(B, 2)))
+    z = zeros(VAL, size(B))
+    return function (r::Array{VAL})
+        z .= 0.0
+        check(ccall((:mgb200_cycle, libmgb200), Cint, (Ptr{Cvoid}, Ptr{VAL}, Ptr{VAL}), dev.handle, r, z))
+        return z
+    end
+end
+
+end # module
