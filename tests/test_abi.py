@@ -1,0 +1,106 @@
+"""The C-ABI library loads on a CPU-only box, exports every symbol include/mgb200.h declares, and
+fails loudly (no CPU fallback) when asked to compute without a GPU.  No compute calls here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "mgb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mgb200_[a-zA-Z0-9_]+)\s*\(", src)))
+
+
+def test_exports_every_declared_symbol():
+    from multigrid_jl_b200 import device
+    L = device.lib()
+    names = _declared()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/mgb200.h but not exported"
+    assert L.mgb200_version() >= 100
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    import multigrid_jl_b200 as mg
+    M = mg.getRegularMesh([0, 1, 0, 1], [8, 8])
+    p = mg.getMGparam(np.float64, np.int64, 2, 8, 5, 1e-8, "Jac", 0.8, 2, 2, 'V')
+    mg.MGsetup(mg.poisson_shifted(M), M, p, 1)
+    b = np.ones(81)
+    with pytest.raises(mg.MGB200Error, match="no CPU fallback"):
+        mg.solveMG(p, b, np.zeros(81))
+    with pytest.raises(mg.MGB200Error):
+        mg.solveCG_MG(p.As[0], p, b, np.zeros(81))
+
+
+def test_null_handle_is_an_error_not_a_crash():
+    from multigrid_jl_b200 import device
+    L = device.lib()
+    it = ctypes.c_int(0)
+    res = np.zeros(4)
+    st = L.mgb200_solveMG(None, None, None, ctypes.c_double(1e-6), 3, ctypes.byref(it), res.ctypes.data_as(ctypes.c_void_p))
+    assert st == -1 and b"null" in L.mgb200_last_error()
+
+
+def test_product_package_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "multigrid.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f"{f} imports the oracle"
+                assert "libmg_oracle" not in txt and "oracle/" not in txt, f"{f} links the oracle"
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5])
+@pytest.mark.parametrize("cplx", [False, True])
+def test_host_pinv_matches_numpy(n, cplx):
+    """hermitian_pinv_apply (smalldense.h) = Julia/numpy pinv rule on FGMRES_relaxation's H."""
+    from multigrid_jl_b200 import device
+    L = device.lib()
+    rng = np.random.default_rng(n)
+    B = rng.standard_normal((n, n)) + (1j * rng.standard_normal((n, n)) if cplx else 0)
+    H = B @ B.conj().T
+    if n >= 3:                      # rank-deficient case: unused basis columns are zero rows/cols
+        H[-1, :] = 0
+        H[:, -1] = 0
+    xi = rng.standard_normal(n) + (1j * rng.standard_normal(n) if cplx else 0)
+    Hc = np.ascontiguousarray(H, dtype=np.complex128)
+    xc = np.ascontiguousarray(xi, dtype=np.complex128)
+    t = np.zeros(n, dtype=np.complex128)
+    assert L.mgb200_host_pinv_apply(n, Hc.ctypes.data_as(ctypes.c_void_p), xc.ctypes.data_as(ctypes.c_void_p),
+                                    t.ctypes.data_as(ctypes.c_void_p)) == 0
+    ref = np.linalg.pinv(Hc, rcond=np.finfo(float).eps * n) @ xc
+    np.testing.assert_allclose(t, ref, rtol=1e-9, atol=1e-12 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("cols", [1, 2, 5, 10])
+def test_host_hessenberg_lsq_matches_numpy(cols):
+    from multigrid_jl_b200 import device
+    L = device.lib()
+    rng = np.random.default_rng(cols)
+    H = np.triu(rng.standard_normal((cols + 1, cols)) + 1j * rng.standard_normal((cols + 1, cols)), -1)
+    xi = np.zeros(cols + 1, dtype=np.complex128)
+    xi[0] = 2.5
+    Hc = np.ascontiguousarray(H)
+    y = np.zeros(cols, dtype=np.complex128)
+    res = ctypes.c_double(0)
+    assert L.mgb200_host_hessenberg_lsq(cols, Hc.ctypes.data_as(ctypes.c_void_p), xi.ctypes.data_as(ctypes.c_void_p),
+                                        y.ctypes.data_as(ctypes.c_void_p), ctypes.byref(res)) == 0
+    yr = np.linalg.lstsq(Hc, xi, rcond=None)[0]
+    np.testing.assert_allclose(y, yr, rtol=1e-10, atol=1e-13)
+    assert abs(res.value - np.linalg.norm(Hc @ yr - xi)) < 1e-12
