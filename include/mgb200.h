@@ -122,6 +122,33 @@ int mgb200_solveCG_device(mgb200_handle h, double tol, int max_iter, int* iter, 
 
 int mgb200_synchronize(mgb200_handle h);
 
+/* ---- multi-GPU: one process per GPU, rows partitioned in contiguous ranges ---------------------
+ * (z-slabs of the reference's DomainDecomposition layout, src/DomainDecomposition/DDIndices.jl:41-47).
+ * Call order: create -> dist_init -> dist_upload_level for the distributed levels (fine ones),
+ * upload_level / upload_coarsest with the GLOBAL matrices for the replicated (coarse) levels.
+ * Vectors passed to the solve entry points then hold only the owned rows of this rank. */
+
+/* 128-byte NCCL unique id, created on one rank and distributed by the caller (e.g. torch.distributed,
+ * Julia Distributed); the same bytes go to every rank's mgb200_dist_init. */
+int mgb200_dist_unique_id(char* out128);
+int mgb200_dist_init(mgb200_handle h, int rank, int world, const char* unique_id128);
+
+/* Owned rows of level l: like mgb200_upload_level, but every CSC block has one column per OWNED row
+ * (A, P: rows row_offsets[rank] .. row_offsets[rank+1]-1 of level l; R: the owned rows of level l+1
+ * given by coarse_row_offsets) and its row indices are GLOBAL column indices of the operator.
+ * row_offsets / coarse_row_offsets have world+1 entries. */
+int mgb200_dist_upload_level(mgb200_handle h, int level, int64_t n_global, const int64_t* row_offsets,
+                             int64_t nc_global, const int64_t* coarse_row_offsets,
+                             const int64_t* a_colptr, const int64_t* a_rowval, const void* a_nzval,
+                             const int64_t* p_colptr, const int64_t* p_rowval, const double* p_nzval,
+                             const int64_t* r_colptr, const int64_t* r_rowval, const double* r_nzval,
+                             const void* d, int index_base);
+
+/* Host-only planning helper (no GPU): sorted unique ghost ids of a row slab [lo,hi) and the column
+ * indices remapped to the [owned | ghost] layout.  ghosts must hold nnz entries. */
+int mgb200_host_plan_ghosts(int64_t nnz, const int64_t* cols, int64_t lo, int64_t hi, int64_t* ghosts,
+                            int64_t* n_ghost, int64_t* local_cols);
+
 /* ---- introspection / measurement -------------------------------------------------------------- */
 
 /* Kernel selection made at upload for matrix `which` of `level` (see mgb200_spmatmul):

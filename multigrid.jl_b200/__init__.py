@@ -21,3 +21,4 @@ from .sa_amg import (SA_AMGsetup, getAggregation, getStrengthMatrix, neighborhoo
 from .device import DeviceHierarchy, uploadHierarchy, MGB200Error, LIB_PATH
 from .solve import (solveMG, solveCG_MG, solveGMRES_MG, getMultigridPreconditioner, recursiveCycle,
                     SpMatMul)
+from .dist_setup import (slab_planes, setup_slab_hierarchy, poisson_window_operator, DistHierarchy, DistLevel)

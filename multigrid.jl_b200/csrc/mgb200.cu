@@ -163,6 +163,51 @@ int mgb200_set_krylov_matrix(mgb200_handle h, int64_t n, const int64_t* colptr, 
     MGB_CATCH
 }
 
+int mgb200_dist_unique_id(char* out128) {
+    MGB_TRY
+    MGB_CHECK(out128, "null output");
+    nccl().load();
+    ncclUniqueId id;
+    MGB_NCCL(nccl().GetUniqueId(&id));
+    static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+    std::memcpy(out128, &id, sizeof(id));
+    MGB_CATCH
+}
+
+int mgb200_dist_init(mgb200_handle h, int rank, int world, const char* unique_id128) {
+    MGB_TRY
+    MGB_CHECK(world == 1 || unique_id128, "null unique id");
+    MGB_BOTH(h, H->dist_init(rank, world, unique_id128));
+    MGB_CATCH
+}
+
+int mgb200_dist_upload_level(mgb200_handle h, int level, int64_t n_global, const int64_t* row_offsets,
+                             int64_t nc_global, const int64_t* coarse_row_offsets, const int64_t* a_colptr,
+                             const int64_t* a_rowval, const void* a_nzval, const int64_t* p_colptr,
+                             const int64_t* p_rowval, const double* p_nzval, const int64_t* r_colptr,
+                             const int64_t* r_rowval, const double* r_nzval, const void* d, int index_base) {
+    MGB_TRY
+    MGB_CHECK(row_offsets && coarse_row_offsets && a_colptr && a_rowval && a_nzval && p_colptr && p_rowval &&
+                  p_nzval && r_colptr && r_rowval && r_nzval && d, "null argument");
+    MGB_BOTH(h, H->dist_upload_level(level, n_global, row_offsets, nc_global, coarse_row_offsets, a_colptr,
+                                     a_rowval, a_nzval, p_colptr, p_rowval, p_nzval, r_colptr, r_rowval,
+                                     r_nzval, d, index_base));
+    MGB_CATCH
+}
+
+int mgb200_host_plan_ghosts(int64_t nnz, const int64_t* cols, int64_t lo, int64_t hi, int64_t* ghosts,
+                            int64_t* n_ghost, int64_t* local_cols) {
+    MGB_TRY
+    MGB_CHECK(cols && ghosts && n_ghost && local_cols, "null argument");
+    std::vector<long long> g;
+    collect_ghosts(cols, nnz, lo, hi, g);
+    sort_unique(g);
+    *n_ghost = (int64_t)g.size();
+    for (size_t i = 0; i < g.size(); ++i) ghosts[i] = g[i];
+    for (int64_t k = 0; k < nnz; ++k) local_cols[k] = to_local(cols[k], lo, hi, g);
+    MGB_CATCH
+}
+
 int mgb200_adjust_nrhs(mgb200_handle h, int nrhs) {
     MGB_TRY
     MGB_BOTH(h, H->adjust_nrhs(nrhs));

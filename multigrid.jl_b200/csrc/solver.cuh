@@ -14,6 +14,7 @@
 #pragma once
 #include <functional>
 
+#include "dist.cuh"
 #include "launch.cuh"
 #include "smalldense.h"
 
@@ -41,6 +42,14 @@ struct Level {
     TV* d = nullptr;
     TV *b = nullptr, *r = nullptr, *x0 = nullptr, *x1 = nullptr;  // CYCLEmem + ping-pong partner of x
     FgmresMem<TV> memRelax, memK;
+    // ---- multi-GPU row partition (dist.cuh) ----
+    long long nalloc = 0;          // rows allocated per vector: owned + ghost (== n when not distributed)
+    DistSpace sp;                  // vector space of this level
+    HostRows<TV> hA;               // staged owned rows with global columns (until finalisation)
+    HostRows<double> hP, hR;
+    std::vector<TV> hd;
+    std::vector<long long> coarse_row_offsets;  // row partition of level l+1 (R output / P input)
+    long long nc_global = 0;
     void release_work() {
         dev_free(b); dev_free(r); dev_free(x0); dev_free(x1);
         memRelax.release();
@@ -50,6 +59,7 @@ struct Level {
         release_work();
         A.release(); P.release(); R.release();
         dev_free(d);
+        sp.release();
         n = 0;
     }
 };
@@ -92,6 +102,8 @@ struct Hierarchy : HierarchyBase {
     // the caller's x (level-1 iterate of solveMG / the Krylov iterate) and its ping-pong partner;
     // L[0].x0/x1 are memCycle[1].x, the z of the preconditioner closure (SolveFuncs.jl:50,59)
     TV *ux0 = nullptr, *ux1 = nullptr, *ucur = nullptr;
+    Comm comm;                 // NCCL communicator (world == 1: inactive)
+    bool dist_finalized = true;
 
     Hierarchy(int nlevels, int nrhs, char ct, int rk, const int64_t* rpre, const int64_t* rpost, int dev) {
         MGB_CHECK(nlevels >= 1, "levels must be >= 1");
@@ -113,6 +125,8 @@ struct Hierarchy : HierarchyBase {
         dev_free(hstage);
         dev_free(ux0);
         dev_free(ux1);
+        if (comm.comm) nccl().CommDestroy(comm.comm);
+        comm.comm = nullptr;
         ctx.destroy();
     }
     void set_cycle(char ct, const int64_t* rpre, const int64_t* rpost) {
@@ -148,7 +162,10 @@ struct Hierarchy : HierarchyBase {
         dev_free(lv.d);
         lv.d = dev_alloc<TV>(n);
         MGB_CUDA(cudaMemcpy(lv.d, d, n * sizeof(TV), cudaMemcpyHostToDevice));
+        lv.nalloc = n;
+        lv.sp.dist = false;
         L[level].n = nc;
+        L[level].nalloc = nc;
         work_ready = false;
     }
 
@@ -157,6 +174,7 @@ struct Hierarchy : HierarchyBase {
         MGB_CUDA(cudaSetDevice(ctx.device));
         Level<TV>& lv = L[levels - 1];
         lv.n = n;
+        lv.nalloc = n;
         upload_csr<TV>(ctx, lv.A, n, n, cp, rv, static_cast<const TV*>(nz), base, true);
         coarse.release();
         coarse.n = (int)n;
@@ -203,6 +221,167 @@ struct Hierarchy : HierarchyBase {
         upload_csr<TV>(ctx, Akry, n, n, cp, rv, static_cast<const TV*>(nz), base, true);
     }
 
+    // ---- multi-GPU: communicator, staged slab upload, finalisation -----------------------------
+    void dist_init(int rank, int world, const char* unique_id) {
+        MGB_CHECK(world >= 1 && rank >= 0 && rank < world, "bad rank / world");
+        MGB_CUDA(cudaSetDevice(ctx.device));
+        comm.rank = rank;
+        comm.world = world;
+        if (world > 1) {
+            nccl().load();
+            ncclUniqueId id;
+            std::memcpy(&id, unique_id, sizeof(id));
+            MGB_NCCL(nccl().CommInitRank(&comm.comm, world, id, rank));
+        }
+    }
+
+    // stage the owned rows of level `level` (1-based): CSC-of-adjoint blocks whose columns are the
+    // owned rows and whose row indices are GLOBAL operator-column indices.
+    template <typename TA>
+    static void stage_rows(HostRows<TA>& H, long long n_rows, const int64_t* cp, const int64_t* rv,
+                           const TA* nz, int base, bool conjugate) {
+        H.n_rows = n_rows;
+        H.rowptr.resize(n_rows + 1);
+        for (long long i = 0; i <= n_rows; ++i) H.rowptr[i] = cp[i] - base;
+        const long long nnz = H.rowptr[n_rows];
+        H.col.resize(nnz);
+        H.val.resize(nnz);
+        for (long long k = 0; k < nnz; ++k) {
+            H.col[k] = rv[k] - base;
+            H.val[k] = conjugate ? conj_(nz[k]) : nz[k];
+        }
+    }
+    void dist_upload_level(int level, long long n_global, const int64_t* row_offsets, long long nc_global,
+                           const int64_t* coarse_row_offsets, const int64_t* acp, const int64_t* arv,
+                           const void* anz, const int64_t* pcp, const int64_t* prv, const double* pnz,
+                           const int64_t* rcp, const int64_t* rrv, const double* rnz, const void* d, int base) {
+        MGB_CHECK(level >= 1 && level < levels, "dist_upload_level: level must be in 1..levels-1");
+        MGB_CHECK(base == 0 || base == 1, "index_base must be 0 or 1");
+        Level<TV>& lv = L[level - 1];
+        const int w = comm.world, r = comm.rank;
+        lv.sp.dist = true;
+        lv.sp.n_global = n_global;
+        lv.sp.row_offsets.assign(row_offsets, row_offsets + w + 1);
+        lv.sp.lo = row_offsets[r];
+        lv.sp.hi = row_offsets[r + 1];
+        lv.sp.n_owned = lv.sp.hi - lv.sp.lo;
+        lv.n = lv.sp.n_owned;
+        lv.nc_global = nc_global;
+        lv.coarse_row_offsets.assign(coarse_row_offsets, coarse_row_offsets + w + 1);
+        const long long nc_owned = coarse_row_offsets[r + 1] - coarse_row_offsets[r];
+        stage_rows<TV>(lv.hA, lv.n, acp, arv, static_cast<const TV*>(anz), base, true);
+        stage_rows<double>(lv.hP, lv.n, pcp, prv, pnz, base, false);
+        stage_rows<double>(lv.hR, nc_owned, rcp, rrv, rnz, base, false);
+        lv.hd.assign(static_cast<const TV*>(d), static_cast<const TV*>(d) + lv.n);
+        dist_finalized = false;
+        work_ready = false;
+    }
+
+    // Build the ghost sets, exchange the request lists, remap the columns into the
+    // [owned | ghost] layouts and upload the CSR matrices.  Collective over all ranks.
+    void finalize_dist() {
+        const int w = comm.world, r = comm.rank;
+        // 1. ghost union per distributed level space: columns of A_l, R_l and P_{l-1}
+        for (int l = 0; l < levels - 1; ++l) {
+            Level<TV>& lv = L[l];
+            if (!lv.sp.dist) continue;
+            MGB_CHECK(lv.hA.present(), "distributed level staged twice or not at all");
+            DistSpace& sp = lv.sp;
+            sp.ghosts.clear();
+            collect_ghosts(lv.hA.col.data(), (long long)lv.hA.col.size(), sp.lo, sp.hi, sp.ghosts);
+            collect_ghosts(lv.hR.col.data(), (long long)lv.hR.col.size(), sp.lo, sp.hi, sp.ghosts);
+            if (l > 0 && L[l - 1].sp.dist)
+                collect_ghosts(L[l - 1].hP.col.data(), (long long)L[l - 1].hP.col.size(), sp.lo, sp.hi, sp.ghosts);
+            sort_unique(sp.ghosts);
+            sp.n_ghost = (long long)sp.ghosts.size();
+            lv.nalloc = sp.n_owned + sp.n_ghost;
+            MGB_CHECK(lv.nalloc < (1LL << 31) - 8, "local vector too long for 32-bit indices");
+            sp.recv_cnt.assign(w, 0);
+            sp.recv_off.assign(w, 0);
+            for (long long g : sp.ghosts) {
+                MGB_CHECK(g >= 0 && g < sp.n_global, "column index outside the global range");
+                sp.recv_cnt[sp.owner_of(g)]++;
+            }
+            for (int p = 1; p < w; ++p) sp.recv_off[p] = sp.recv_off[p - 1] + sp.recv_cnt[p - 1];
+            MGB_CHECK(sp.recv_cnt[r] == 0, "ghost owned by self");
+        }
+        // 2. request exchange (who needs what from me) over NCCL
+        for (int l = 0; l < levels - 1; ++l) {
+            Level<TV>& lv = L[l];
+            if (!lv.sp.dist) continue;
+            DistSpace& sp = lv.sp;
+            sp.send_cnt.assign(w, 0);
+            sp.send_off.assign(w, 0);
+            sp.release();
+            if (w == 1) continue;
+            int* d_cnt = dev_alloc<int>((size_t)w * w);
+            MGB_CUDA(cudaMemcpyAsync(d_cnt + (size_t)r * w, sp.recv_cnt.data(), w * sizeof(int), cudaMemcpyHostToDevice, ctx.stream));
+            MGB_NCCL(nccl().AllGather(d_cnt + (size_t)r * w, d_cnt, (size_t)w, ncclInt32, comm.comm, ctx.stream));
+            std::vector<int> all((size_t)w * w);
+            MGB_CUDA(cudaMemcpyAsync(all.data(), d_cnt, (size_t)w * w * sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+            ctx.sync();
+            dev_free(d_cnt);
+            for (int q = 0; q < w; ++q) sp.send_cnt[q] = all[(size_t)q * w + r];
+            for (int q = 1; q < w; ++q) sp.send_off[q] = sp.send_off[q - 1] + sp.send_cnt[q - 1];
+            sp.n_send = sp.send_off[w - 1] + sp.send_cnt[w - 1];
+            long long* d_req = dev_alloc<long long>(std::max<long long>(sp.n_ghost, 1));
+            long long* d_got = dev_alloc<long long>(std::max(sp.n_send, 1));
+            MGB_CUDA(cudaMemcpyAsync(d_req, sp.ghosts.data(), sp.n_ghost * sizeof(long long), cudaMemcpyHostToDevice, ctx.stream));
+            MGB_NCCL(nccl().GroupStart());
+            for (int p = 0; p < w; ++p) {
+                if (sp.recv_cnt[p] > 0) MGB_NCCL(nccl().Send(d_req + sp.recv_off[p], sp.recv_cnt[p], ncclInt64, p, comm.comm, ctx.stream));
+                if (sp.send_cnt[p] > 0) MGB_NCCL(nccl().Recv(d_got + sp.send_off[p], sp.send_cnt[p], ncclInt64, p, comm.comm, ctx.stream));
+            }
+            MGB_NCCL(nccl().GroupEnd());
+            std::vector<long long> got(std::max(sp.n_send, 1));
+            MGB_CUDA(cudaMemcpyAsync(got.data(), d_got, sp.n_send * sizeof(long long), cudaMemcpyDeviceToHost, ctx.stream));
+            ctx.sync();
+            dev_free(d_req);
+            dev_free(d_got);
+            std::vector<int> idx(std::max(sp.n_send, 1));
+            for (int k = 0; k < sp.n_send; ++k) {
+                MGB_CHECK(got[k] >= sp.lo && got[k] < sp.hi, "peer requested a row this rank does not own");
+                idx[k] = (int)(got[k] - sp.lo);
+            }
+            sp.d_send_idx = dev_alloc<int>(std::max(sp.n_send, 1));
+            MGB_CUDA(cudaMemcpy(sp.d_send_idx, idx.data(), sp.n_send * sizeof(int), cudaMemcpyHostToDevice));
+        }
+        // 3. remap columns and upload
+        for (int l = 0; l < levels - 1; ++l) {
+            Level<TV>& lv = L[l];
+            if (!lv.sp.dist) continue;
+            DistSpace& sp = lv.sp;
+            for (auto& c : lv.hA.col) c = to_local(c, sp.lo, sp.hi, sp.ghosts);
+            for (auto& c : lv.hR.col) c = to_local(c, sp.lo, sp.hi, sp.ghosts);
+            Level<TV>& lc = L[l + 1];
+            long long pcols;
+            if (lc.sp.dist) {
+                // lc's ghost set already contains P's columns (step 1)
+                for (auto& c : lv.hP.col) c = to_local(c, lc.sp.lo, lc.sp.hi, lc.sp.ghosts);
+                pcols = lc.sp.n_owned + lc.sp.n_ghost;
+            } else {
+                pcols = lv.nc_global;
+                MGB_CHECK(lc.n == 0 || lc.n == lv.nc_global, "replicated coarse level size mismatch");
+                lc.n = lv.nc_global;
+                if (lc.nalloc < lc.n) lc.nalloc = lc.n;
+            }
+            upload_csr<TV>(ctx, lv.A, lv.hA.n_rows, lv.nalloc, lv.hA.rowptr.data(), lv.hA.col.data(), lv.hA.val.data(), 0, false);
+            upload_csr<double>(ctx, lv.P, lv.hP.n_rows, pcols, lv.hP.rowptr.data(), lv.hP.col.data(), lv.hP.val.data(), 0, false);
+            upload_csr<double>(ctx, lv.R, lv.hR.n_rows, lv.nalloc, lv.hR.rowptr.data(), lv.hR.col.data(), lv.hR.val.data(), 0, false);
+            dev_free(lv.d);
+            lv.d = dev_alloc<TV>(lv.n);
+            MGB_CUDA(cudaMemcpy(lv.d, lv.hd.data(), lv.n * sizeof(TV), cudaMemcpyHostToDevice));
+        }
+        for (int l = 0; l < levels - 1; ++l) {
+            L[l].hA.clear();
+            L[l].hP.clear();
+            L[l].hR.clear();
+            L[l].hd.clear();
+            L[l].hd.shrink_to_fit();
+        }
+        dist_finalized = true;
+    }
+
     // ---- workspaces (adjustMemoryForNumRHS, MGsetup.jl:166-223) -----------------------------
     void adjust_nrhs(int nrhs) {
         MGB_CHECK(nrhs >= 1, "nrhs must be >= 1");
@@ -214,12 +393,19 @@ struct Hierarchy : HierarchyBase {
     void ensure_work() {
         if (work_ready) return;
         MGB_CUDA(cudaSetDevice(ctx.device));
+        if (!dist_finalized) finalize_dist();
         for (int l = 0; l < levels; ++l) {
             Level<TV>& lv = L[l];
             MGB_CHECK(lv.n > 0, "hierarchy level not uploaded");
             if (l < levels - 1) MGB_CHECK(lv.A.present() && lv.P.present() && lv.R.present(), "hierarchy level not uploaded");
             lv.release_work();
-            const size_t nm = (size_t)lv.n * m;
+            if (lv.nalloc < lv.n) lv.nalloc = lv.n;
+            const size_t nm = (size_t)lv.nalloc * m;
+            if (lv.sp.dist && lv.sp.n_send > 0) {
+                if (lv.sp.sendbuf) cudaFree(lv.sp.sendbuf);
+                lv.sp.sendbuf_bytes = (size_t)lv.sp.n_send * m * sizeof(TV);
+                MGB_CUDA(cudaMalloc(&lv.sp.sendbuf, lv.sp.sendbuf_bytes));
+            }
             lv.b = dev_alloc<TV>(nm);
             lv.r = dev_alloc<TV>(nm);
             lv.x0 = dev_alloc<TV>(nm);
@@ -242,10 +428,10 @@ struct Hierarchy : HierarchyBase {
         hstage_n = 0;
         dev_free(ux0);
         dev_free(ux1);
-        ux0 = dev_alloc<TV>((size_t)L[0].n * m);
-        ux1 = dev_alloc<TV>((size_t)L[0].n * m);
-        MGB_CUDA(cudaMemsetAsync(ux0, 0, (size_t)L[0].n * m * sizeof(TV), ctx.stream));
-        MGB_CUDA(cudaMemsetAsync(ux1, 0, (size_t)L[0].n * m * sizeof(TV), ctx.stream));
+        ux0 = dev_alloc<TV>((size_t)L[0].nalloc * m);
+        ux1 = dev_alloc<TV>((size_t)L[0].nalloc * m);
+        MGB_CUDA(cudaMemsetAsync(ux0, 0, (size_t)L[0].nalloc * m * sizeof(TV), ctx.stream));
+        MGB_CUDA(cudaMemsetAsync(ux1, 0, (size_t)L[0].nalloc * m * sizeof(TV), ctx.stream));
         ucur = ux0;
         ctx.sync();
         work_ready = true;
@@ -260,7 +446,7 @@ struct Hierarchy : HierarchyBase {
         mem.vp1 = dev_alloc<TV>(nm);
     }
     void ensure_krylov(int vcols, bool needZ) {
-        const size_t nm = (size_t)L[0].n * m;
+        const size_t nm = (size_t)L[0].nalloc * m;
         if (!kr) {
             kr = dev_alloc<TV>(nm);
             kp = dev_alloc<TV>(nm);
@@ -280,22 +466,66 @@ struct Hierarchy : HierarchyBase {
     const Csr<TV>& krylov_A() const { return Akry.present() ? Akry : L[0].A; }
 
     void apply_A(const Csr<TV>& A, const TV* x, TV* y, int level) {  // y = A x   (getAfun, SolveFuncs.jl:65-71)
+        exchange(level - 1, const_cast<TV*>(x));
         csr_apply<TV, TV>(ctx, A, MODE_SPMV, x, nullptr, nullptr, y, m, K_SPMV, level);
     }
     void residual(const Csr<TV>& A, const TV* b, const TV* x, TV* r, int level) {  // r = b - A x
+        exchange(level - 1, const_cast<TV*>(x));
         csr_apply<TV, TV>(ctx, A, MODE_RESID, x, b, nullptr, r, m, K_RESID, level);
     }
-    double norm(long long n, const TV* x) {
+    // reductions over a distributed level are completed by an in-place all-reduce on the stream
+    void allreduce(int l, double* dptr, int k) {
+        if (!comm.active() || !L[l].sp.dist) return;
+        Launch La(ctx, K_REDUCE, l + 1, 0.0);
+        MGB_NCCL(nccl().AllReduce(dptr, dptr, (size_t)k, ncclDouble, ncclSum, comm.comm, ctx.stream));
+    }
+    double norm(long long n, const TV* x, int l = 0) {
         dev_norm2sq<TV>(ctx, n, x, ctx.scal + 8);
+        allreduce(l, ctx.scal + 8, 1);
         double v;
         read_scalars(ctx, ctx.scal + 8, 1, &v);
         return std::sqrt(v);
     }
-    zc dot(long long n, const TV* x, const TV* y) {
+    zc dot(long long n, const TV* x, const TV* y, int l = 0) {
         dev_dot<TV>(ctx, n, x, y, ctx.scal + 10);
+        allreduce(l, ctx.scal + 10, 2);
         double v[2];
         read_scalars(ctx, ctx.scal + 10, 2, v);
         return zc(v[0], v[1]);
+    }
+
+    // halo exchange of a level-l vector laid out [owned | ghost] (dist.cuh)
+    void exchange(int l, TV* v) {
+        if (!comm.active() || l < 0 || l >= levels || !L[l].sp.dist) return;
+        DistSpace& sp = L[l].sp;
+        Launch La(ctx, K_COPY, l + 1, 2.0 * sp.n_ghost * m * sizeof(TV));
+        TV* sb = static_cast<TV*>(sp.sendbuf);
+        if (sp.n_send > 0) {
+            pack_kernel<TV><<<ctx.ew_blocks((long long)sp.n_send * m), 256, 0, ctx.stream>>>(v, sp.d_send_idx, sp.n_send, m, sb);
+            MGB_LAUNCH_CHECK();
+        }
+        const size_t per = (size_t)m * (sizeof(TV) / sizeof(double));
+        MGB_NCCL(nccl().GroupStart());
+        for (int p = 0; p < comm.world; ++p) {
+            if (sp.send_cnt[p] > 0)
+                MGB_NCCL(nccl().Send(sb + (size_t)sp.send_off[p] * m, sp.send_cnt[p] * per, ncclDouble, p, comm.comm, ctx.stream));
+            if (sp.recv_cnt[p] > 0)
+                MGB_NCCL(nccl().Recv(v + ((size_t)sp.n_owned + sp.recv_off[p]) * m, sp.recv_cnt[p] * per, ncclDouble, p, comm.comm, ctx.stream));
+        }
+        MGB_NCCL(nccl().GroupEnd());
+    }
+    // assemble a replicated level-l vector from the owned pieces computed by each rank
+    void allgather_rows(int l, TV* v, const std::vector<long long>& offs) {
+        if (!comm.active()) return;
+        Launch La(ctx, K_COPY, l + 1, 1.0 * L[l].n * m * sizeof(TV));
+        const size_t per = (size_t)m * (sizeof(TV) / sizeof(double));
+        MGB_NCCL(nccl().GroupStart());
+        for (int p = 0; p < comm.world; ++p) {
+            const long long cnt = offs[p + 1] - offs[p];
+            if (cnt > 0)
+                MGB_NCCL(nccl().Broadcast(v + (size_t)offs[p] * m, v + (size_t)offs[p] * m, cnt * per, ncclDouble, p, comm.comm, ctx.stream));
+        }
+        MGB_NCCL(nccl().GroupEnd());
     }
     static TV to_tv(zc a) { return VT<TV>::make(a.real(), a.imag()); }
 
@@ -311,6 +541,7 @@ struct Hierarchy : HierarchyBase {
             sweeps -= 1;
         }
         for (int s = 0; s < sweeps; ++s) {
+            exchange(l, x);
             csr_apply<TV, TV>(ctx, lv.A, MODE_SWEEP, x, b, lv.d, scratch, m, K_SWEEP, l + 1);
             std::swap(x, scratch);
         }
@@ -336,7 +567,7 @@ struct Hierarchy : HierarchyBase {
         MGB_CHECK(inner <= MAXK, "FGMRES_relaxation: inner too large");
         dev_zero<TV>(ctx, nm * inner, mem.Z);   // resetMem (FGMRES.jl:10-15)
         dev_zero<TV>(ctx, nm * inner, mem.AZ);
-        const double rnorm0 = norm(nm, r0);
+        const double rnorm0 = norm(nm, r0, level - 1);
         std::vector<zc> H((size_t)inner * inner, zc(0, 0)), xi(inner, zc(0, 0)), t(inner, zc(0, 0));
         const TV* w = nullptr;
         int done = 0;
@@ -349,6 +580,7 @@ struct Hierarchy : HierarchyBase {
             // t = AZ^H w over all `inner` columns (unused ones are zero), xi[j] = <w, r0>
             dev_multi_dot<TV>(ctx, nm, mem.AZ, nm, inner, w, ctx.scal + 16);
             dev_dot<TV>(ctx, nm, w, r0, ctx.scal + 16 + 2 * inner);
+            allreduce(level - 1, ctx.scal + 16, 2 * inner + 2);
             std::vector<double> hv(2 * inner + 2);
             read_scalars(ctx, ctx.scal + 16, 2 * inner + 2, hv.data());
             for (int i = 0; i < inner; ++i) t[i] = zc(hv[2 * i], hv[2 * i + 1]);
@@ -400,7 +632,15 @@ struct Hierarchy : HierarchyBase {
             if (xn != x) std::swap(x, scratch);
         }
         residual(lv.A, b, x, lv.r, l + 1);                                          // :58-60
-        csr_apply<double, TV>(ctx, lv.R, MODE_SPMV, lv.r, nullptr, nullptr, lc.b, m, K_RESTRICT, l + 1);  // :66
+        exchange(l, lv.r);
+        if (lv.sp.dist && !lc.sp.dist) {
+            // last distributed level: each rank restricts its own coarse rows, then the pieces are gathered
+            csr_apply<double, TV>(ctx, lv.R, MODE_SPMV, lv.r, nullptr, nullptr,
+                                  lc.b + (size_t)lv.coarse_row_offsets[comm.rank] * m, m, K_RESTRICT, l + 1);
+            allgather_rows(l + 1, lc.b, lv.coarse_row_offsets);
+        } else {
+            csr_apply<double, TV>(ctx, lv.R, MODE_SPMV, lv.r, nullptr, nullptr, lc.b, m, K_RESTRICT, l + 1);  // :66
+        }
         if (l + 1 == levels - 1) {
             solve_coarsest(lc.b, lc.x0);                                           // :67-69
             xc_cur = lc.x0;
@@ -420,6 +660,7 @@ struct Hierarchy : HierarchyBase {
                 xc_cur = cycle(l + 1, lc.b, xc_cur, other, false, 'V');            // :81-85
             }
         }
+        exchange(l + 1, xc_cur);
         csr_apply<double, TV>(ctx, lv.P, MODE_ADD, xc_cur, nullptr, nullptr, x, m, K_PROLONG, l + 1);  // :90
         // ---- post-relaxation (:92-103) ----
         if (relax_kind == 1) {
@@ -512,17 +753,20 @@ struct Hierarchy : HierarchyBase {
         dev_copy<TV>(ctx, n, z, kp);                     // p = copy(z)
         double* s = ctx.scal;                            // s[0]=gamma s[2]=delta s[4]=rr s[6]=gamma_new
         dev_dot<TV>(ctx, n, kr, z, s + 0);
+        allreduce(0, s + 0, 2);
         *flag = -1;
         int last = 0;
         for (int it = 1; it <= max_iter; ++it) {
             last = it;
             apply_A(A, kp, kAp, 1);                      // Ap = A(p)
             dev_dot<TV>(ctx, n, kp, kAp, s + 2);         // delta = <p,Ap>   (gamma = <r,z> already in s[0])
+            allreduce(0, s + 2, 2);
             {
                 Launch La(ctx, K_VECTOR, 0, 6.0 * n * sizeof(TV));
                 cg_update_kernel<TV><<<ctx.red_blocks(n), RED_THREADS, 0, ctx.stream>>>(n, s, kp, kAp, xk, kr, ctx.red, s + 4);
                 MGB_LAUNCH_CHECK();
             }
+            allreduce(0, s + 4, 1);
             double hv[6];
             read_scalars(ctx, s, 6, hv);
             const double alpha = hv[0] / hv[2];
@@ -537,6 +781,7 @@ struct Hierarchy : HierarchyBase {
             }
             z = precondition(kr);
             dev_dot<TV>(ctx, n, z, kr, s + 6);           // <z,r>
+            allreduce(0, s + 6, 2);
             {
                 Launch La(ctx, K_VECTOR, 0, 3.0 * n * sizeof(TV));
                 cg_direction_kernel<TV><<<ctx.ew_blocks(n), 256, 0, ctx.stream>>>(n, s + 6, s + 0, z, kp);
@@ -578,6 +823,7 @@ struct Hierarchy : HierarchyBase {
         *flag = -1;
         int counter = 0, it = 0;
         const int ldh = restrt;
+        const long long ldv = L[0].nalloc;   // basis columns are allocated with ghost space
         while (it < max_iter) {
             it += 1;
             std::vector<zc> H((size_t)(restrt + 1) * ldh, zc(0, 0)), xi(restrt + 1, zc(0, 0)), y;
@@ -588,10 +834,11 @@ struct Hierarchy : HierarchyBase {
             int jdone = 0;
             for (int j = 0; j < restrt; ++j) {
                 TV* z = precondition(kw);                                        // z = M(w)
-                if (flexible) dev_copy<TV>(ctx, n, z, kZ + (size_t)j * n);
+                if (flexible) dev_copy<TV>(ctx, n, z, kZ + (size_t)j * ldv);
                 apply_A(A, z, kw, 1);                                            // w = A(z)
                 counter += 1;
-                dev_multi_dot<TV>(ctx, n, kV, n, j + 1, kw, ctx.scal + 16);      // t = V'w
+                dev_multi_dot<TV>(ctx, n, kV, ldv, j + 1, kw, ctx.scal + 16);    // t = V'w
+                allreduce(0, ctx.scal + 16, 2 * (j + 1));
                 std::vector<double> hv(2 * (j + 1));
                 read_scalars(ctx, ctx.scal + 16, 2 * (j + 1), hv.data());
                 std::vector<TV> coef(j + 1);
@@ -599,13 +846,14 @@ struct Hierarchy : HierarchyBase {
                     H[(size_t)i * ldh + j] = zc(hv[2 * i], hv[2 * i + 1]);
                     coef[i] = to_tv(-H[(size_t)i * ldh + j]);
                 }
-                dev_multi_axpy<TV>(ctx, n, kV, n, j + 1, coef.data(), 1.0, kw, ctx.scal + 12);  // w -= V t, ||w||^2
+                dev_multi_axpy<TV>(ctx, n, kV, ldv, j + 1, coef.data(), 1.0, kw, ctx.scal + 12);  // w -= V t, ||w||^2
+                allreduce(0, ctx.scal + 12, 1);
                 double nw2;
                 read_scalars(ctx, ctx.scal + 12, 1, &nw2);
                 betta = std::sqrt(nw2);
                 H[(size_t)(j + 1) * ldh + j] = betta;
                 dev_axpby<TV>(ctx, n, VT<TV>::from_real(1.0 / betta), kw, VT<TV>::zero(), kw, true);  // w *= 1/betta
-                if (j + 1 < restrt) dev_copy<TV>(ctx, n, kw, kV + (size_t)(j + 1) * n);
+                if (j + 1 < restrt) dev_copy<TV>(ctx, n, kw, kV + (size_t)(j + 1) * ldv);
                 err = hessenberg_lsq(H, ldh, j + 2, j + 1, xi, y) / rnorm0;
                 resvec[counter - 1] = err;
                 jdone = j + 1;
@@ -618,9 +866,9 @@ struct Hierarchy : HierarchyBase {
             std::vector<TV> coef(jdone);
             for (int i = 0; i < jdone; ++i) coef[i] = to_tv(y[i]);
             if (flexible) {
-                dev_multi_axpy<TV>(ctx, n, kZ, n, jdone, coef.data(), 1.0, xk, nullptr);  // x += Z y
+                dev_multi_axpy<TV>(ctx, n, kZ, ldv, jdone, coef.data(), 1.0, xk, nullptr);  // x += Z y
             } else {
-                dev_multi_axpy<TV>(ctx, n, kV, n, jdone, coef.data(), 0.0, kAp, nullptr);  // V y
+                dev_multi_axpy<TV>(ctx, n, kV, ldv, jdone, coef.data(), 0.0, kAp, nullptr);  // V y
                 TV* z = precondition(kAp);
                 dev_axpby<TV>(ctx, n, VT<TV>::one(), z, VT<TV>::one(), xk, false);        // x += M(V y)
             }
