@@ -149,6 +149,12 @@ int mgb200_dist_upload_level(mgb200_handle h, int level, int64_t n_global, const
 int mgb200_host_plan_ghosts(int64_t nnz, const int64_t* cols, int64_t lo, int64_t hi, int64_t* ghosts,
                             int64_t* n_ghost, int64_t* local_cols);
 
+/* Host-only helpers exported for the CPU test-suite (the tiny dense algebra of the Krylov control
+ * flow, csrc/smalldense.h): complex numbers are interleaved (re, im), matrices row-major. */
+int mgb200_host_pinv_apply(int n, const double* H, const double* xi, double* t);
+int mgb200_host_general_pinv(int n, const double* A, double rtol, double* P);
+int mgb200_host_hessenberg_lsq(int cols, const double* H, const double* xi, double* y, double* res);
+
 /* ---- introspection / measurement -------------------------------------------------------------- */
 
 /* Kernel selection made at upload for matrix `which` of `level` (see mgb200_spmatmul):

@@ -258,7 +258,8 @@ int mgb200_solveCG(mgb200_handle h, const void* b, void* x, double tol, int max_
         const long long n = H->L[0].n;
         H->h2d_vec(b, H->L[0].b, n);
         H->h2d_vec(x, H->ucur, n);
-        *iter = H->solveCG(H->ucur, tol, max_iter, flag, resvec);
+        if (H->m == 1) *iter = H->solveCG(H->ucur, tol, max_iter, flag, resvec);
+        else *iter = H->solveBlockCG(H->ucur, tol, max_iter, flag, resvec, -1.0);
         H->d2h_vec(H->ucur, x, n);
     });
     MGB_CATCH
@@ -317,7 +318,8 @@ int mgb200_solveCG_device(mgb200_handle h, double tol, int max_iter, int* iter, 
     MGB_CHECK(iter && flag && resvec, "null argument");
     MGB_BOTH(h, {
         H->ensure_work();
-        *iter = H->solveCG(H->ucur, tol, max_iter, flag, resvec);
+        if (H->m == 1) *iter = H->solveCG(H->ucur, tol, max_iter, flag, resvec);
+        else *iter = H->solveBlockCG(H->ucur, tol, max_iter, flag, resvec, -1.0);
     });
     MGB_CATCH
 }
@@ -446,6 +448,18 @@ int mgb200_host_pinv_apply(int n, const double* H, const double* xi, double* t) 
     for (int i = 0; i < n; ++i) {
         t[2 * i] = tv[i].real();
         t[2 * i + 1] = tv[i].imag();
+    }
+    MGB_CATCH
+}
+// P = pinv(A) for a general n x n complex matrix (row-major, interleaved re/im), cut-off rtol*max(sigma)
+int mgb200_host_general_pinv(int n, const double* A, double rtol, double* P) {
+    MGB_TRY
+    std::vector<zc> Av((size_t)n * n), Pv;
+    for (int i = 0; i < n * n; ++i) Av[i] = zc(A[2 * i], A[2 * i + 1]);
+    general_pinv(n, Av, rtol, Pv);
+    for (int i = 0; i < n * n; ++i) {
+        P[2 * i] = Pv[i].real();
+        P[2 * i + 1] = Pv[i].imag();
     }
     MGB_CATCH
 }

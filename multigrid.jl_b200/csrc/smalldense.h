@@ -85,6 +85,73 @@ static inline void hermitian_pinv_apply(int n, const std::vector<zc>& H, const s
     for (int i = 0; i < n; ++i) t[i] = zc(out[i], out[i + n]);
 }
 
+// Pseudo-inverse of a general n x n complex matrix (row-major) by one-sided Jacobi SVD on the real
+// embedding [[A,-B],[B,A]]; singular values <= rtol * max are dropped (numpy / Julia pinv rule).
+static inline void general_pinv(int n, const std::vector<zc>& Ain, double rtol, std::vector<zc>& Pout) {
+    const int N = 2 * n;
+    std::vector<double> W((size_t)N * N), V((size_t)N * N, 0.0);
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            double a = Ain[(size_t)i * n + j].real(), b = Ain[(size_t)i * n + j].imag();
+            W[(size_t)i * N + j] = a;
+            W[(size_t)i * N + (j + n)] = -b;
+            W[(size_t)(i + n) * N + j] = b;
+            W[(size_t)(i + n) * N + (j + n)] = a;
+        }
+    for (int i = 0; i < N; ++i) V[(size_t)i * N + i] = 1.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double maxoff = 0.0;
+        for (int p = 0; p < N - 1; ++p)
+            for (int q = p + 1; q < N; ++q) {
+                double alpha = 0, beta = 0, gamma = 0;
+                for (int k = 0; k < N; ++k) {
+                    double wp = W[(size_t)k * N + p], wq = W[(size_t)k * N + q];
+                    alpha += wp * wp;
+                    beta += wq * wq;
+                    gamma += wp * wq;
+                }
+                if (gamma == 0.0) continue;
+                double off = std::fabs(gamma) / std::sqrt(alpha * beta);
+                if (!(off > 1e-15)) continue;
+                maxoff = std::max(maxoff, off);
+                double zeta = (beta - alpha) / (2.0 * gamma);
+                double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+                double c = 1.0 / std::sqrt(1.0 + t * t), s = c * t;
+                for (int k = 0; k < N; ++k) {
+                    double wp = W[(size_t)k * N + p], wq = W[(size_t)k * N + q];
+                    W[(size_t)k * N + p] = c * wp - s * wq;
+                    W[(size_t)k * N + q] = s * wp + c * wq;
+                    double vp = V[(size_t)k * N + p], vq = V[(size_t)k * N + q];
+                    V[(size_t)k * N + p] = c * vp - s * vq;
+                    V[(size_t)k * N + q] = s * vp + c * vq;
+                }
+            }
+        if (maxoff <= 1e-15) break;
+    }
+    std::vector<double> sig(N);
+    double smax = 0.0;
+    for (int j = 0; j < N; ++j) {
+        double s2 = 0.0;
+        for (int k = 0; k < N; ++k) s2 += W[(size_t)k * N + j] * W[(size_t)k * N + j];
+        sig[j] = std::sqrt(s2);
+        smax = std::max(smax, sig[j]);
+    }
+    // pinv(M) = V diag(1/sigma) U^T with U[:,j] = W[:,j]/sigma_j  =>  pinv(M)[r][c] = sum_j V[r][j] W[c][j] / sigma_j^2
+    std::vector<double> Pm((size_t)N * N, 0.0);
+    for (int j = 0; j < N; ++j) {
+        if (!(sig[j] > rtol * smax)) continue;
+        const double inv = 1.0 / (sig[j] * sig[j]);
+        for (int r = 0; r < N; ++r) {
+            const double vr = V[(size_t)r * N + j] * inv;
+            if (vr == 0.0) continue;
+            for (int c = 0; c < N; ++c) Pm[(size_t)r * N + c] += vr * W[(size_t)c * N + j];
+        }
+    }
+    Pout.resize((size_t)n * n);
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) Pout[(size_t)i * n + j] = zc(Pm[(size_t)i * N + j], Pm[(size_t)(i + n) * N + j]);
+}
+
 // min_y || H(0:rows,0:cols) y - xi(0:rows) ||, H row-major with leading dimension ldh,
 // rows = cols+1 (Hessenberg block).  Householder QR on a copy; returns the residual norm.
 static inline double hessenberg_lsq(const std::vector<zc>& H, int ldh, int rows, int cols,

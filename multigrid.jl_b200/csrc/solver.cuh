@@ -125,6 +125,10 @@ struct Hierarchy : HierarchyBase {
         dev_free(hstage);
         dev_free(ux0);
         dev_free(ux1);
+        dev_free(gram_ws);
+        dev_free(gram_partials);
+        dev_free(gram_counter);
+        dev_free(kq);
         if (comm.comm) nccl().CommDestroy(comm.comm);
         comm.comm = nullptr;
         ctx.destroy();
@@ -143,7 +147,7 @@ struct Hierarchy : HierarchyBase {
         work_ready = false;
     }
     void free_krylov() {
-        dev_free(kr); dev_free(kp); dev_free(kAp); dev_free(kw); dev_free(kV); dev_free(kZ);
+        dev_free(kr); dev_free(kp); dev_free(kAp); dev_free(kw); dev_free(kV); dev_free(kZ); dev_free(kq);
         kV_cols = 0;
     }
 
@@ -791,6 +795,131 @@ struct Hierarchy : HierarchyBase {
             MGB_CUDA(cudaMemcpyAsync(s + 0, s + 6, 2 * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
         }
         return last;
+    }
+
+    // ---- KrylovMethods.blockCG with M = one cycle (solveCG_MG with nrhs > 1, SolveFuncs.jl:113) ----
+    // O'Leary block CG on n x m blocks (RHS-fastest on the device).  resmat: max_iter x m (row-major).
+    double* gram_ws = nullptr;      // device: 3 Gram results (2 m^2 doubles each) + m x m coefficient matrix
+    double* gram_partials = nullptr;
+    unsigned* gram_counter = nullptr;
+    TV* kq = nullptr;               // spare n x m block (P ping-pong)
+    void gram(long long n, const TV* X, const TV* Y, double* out) {
+        Launch La(ctx, K_REDUCE, 0, 2.0 * n * m * sizeof(TV));
+        const int blocks = (int)std::max<long long>(1, std::min<long long>((n + GRAM_ROWS - 1) / GRAM_ROWS,
+                                                                           std::min(GRAM_MAX_BLOCKS, ctx.sm_count * 4)));
+        const size_t smem = 2 * (size_t)GRAM_ROWS * m * sizeof(TV);
+        if (smem > 48 * 1024)
+            MGB_CUDA(cudaFuncSetAttribute(gram_kernel<TV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gram_kernel<TV><<<blocks, GRAM_THREADS, smem, ctx.stream>>>(n, m, X, Y, gram_partials, gram_counter, out);
+        MGB_LAUNCH_CHECK();
+        allreduce(0, out, 2 * m * m);
+    }
+    void read_matrix(const double* dptr, std::vector<zc>& M) {
+        std::vector<double> h(2 * (size_t)m * m);
+        MGB_CUDA(cudaMemcpyAsync(h.data(), dptr, h.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+        ctx.sync();
+        M.resize((size_t)m * m);
+        for (int i = 0; i < m * m; ++i) M[i] = zc(h[2 * i], h[2 * i + 1]);
+    }
+    // out = base + X * C   (C: m x m host matrix)
+    void block_axpy(long long n, const TV* X, const std::vector<zc>& C, const TV* base, TV* out) {
+        std::vector<TV> hc((size_t)m * m);
+        for (int i = 0; i < m * m; ++i) hc[i] = to_tv(C[i]);
+        TV* dC = reinterpret_cast<TV*>(gram_ws + 6 * (size_t)m * m);
+        MGB_CUDA(cudaMemcpyAsync(dC, hc.data(), hc.size() * sizeof(TV), cudaMemcpyHostToDevice, ctx.stream));
+        ctx.sync();  // hc is a stack temporary
+        Launch La(ctx, K_VECTOR, 0, 3.0 * n * m * sizeof(TV));
+        if ((size_t)m * m * sizeof(TV) > 48 * 1024)
+            MGB_CUDA(cudaFuncSetAttribute(block_axpy_kernel<TV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)m * m * sizeof(TV))));
+        block_axpy_kernel<TV><<<ctx.ew_blocks(n * m), 256, (size_t)m * m * sizeof(TV), ctx.stream>>>(n, m, X, dC, base, out);
+        MGB_LAUNCH_CHECK();
+    }
+    void colnorms(long long n, const TV* R, std::vector<double>& out) {
+        {
+            Launch La(ctx, K_REDUCE, 0, 1.0 * n * m * sizeof(TV));
+            colnorm2_kernel<TV><<<ctx.red_blocks(n * m), RED_THREADS, 0, ctx.stream>>>(n, m, R, gram_partials, gram_counter, gram_ws);
+            MGB_LAUNCH_CHECK();
+        }
+        allreduce(0, gram_ws, m);
+        out.resize(m);
+        MGB_CUDA(cudaMemcpyAsync(out.data(), gram_ws, m * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+        ctx.sync();
+        for (auto& v : out) v = std::sqrt(v);
+    }
+    static void matmul_small(int m, const std::vector<zc>& A, const std::vector<zc>& B, std::vector<zc>& C, double sgn) {
+        C.assign((size_t)m * m, zc(0, 0));
+        for (int i = 0; i < m; ++i)
+            for (int k = 0; k < m; ++k) {
+                const zc a = A[(size_t)i * m + k];
+                for (int j = 0; j < m; ++j) C[(size_t)i * m + j] += sgn * a * B[(size_t)k * m + j];
+            }
+    }
+    int solveBlockCG(TV* xk, double tol, int max_iter, int* flag, double* resmat, double pinv_tol) {
+        ensure_work();
+        MGB_CHECK(m >= 1 && m <= 64, "blockCG supports up to 64 right-hand sides");
+        ensure_krylov(0, false);
+        Level<TV>& lv = L[0];
+        const long long n = lv.n, nm = n * m;
+        const size_t nma = (size_t)lv.nalloc * m;
+        if (!gram_ws) {
+            gram_ws = dev_alloc<double>(6 * (size_t)64 * 64 + 2 * (size_t)64 * 64 + 64);
+            gram_partials = dev_alloc<double>((size_t)GRAM_MAX_BLOCKS * 2 * 64 * 64);
+            gram_counter = dev_alloc<unsigned>(1);
+            MGB_CUDA(cudaMemset(gram_counter, 0, sizeof(unsigned)));
+        }
+        if (!kq) kq = dev_alloc<TV>(nma);
+        const Csr<TV>& A = krylov_A();
+        const TV* B = lv.b;
+        if (norm(nm, B) == 0.0) {
+            dev_zero<TV>(ctx, nm, xk);
+            *flag = -9;
+            return 0;
+        }
+        if (pinv_tol < 0) {  // package default: eps * size(B,1) of the GLOBAL problem
+            long long nglob = lv.sp.dist ? lv.sp.n_global : n;
+            pinv_tol = std::numeric_limits<double>::epsilon() * (double)nglob;
+        }
+        TV *R = kr, *P = kp, *Q = kAp, *Pn = kq;
+        if (norm(nm, xk) == 0.0) dev_copy<TV>(ctx, nm, B, R);
+        else residual(A, B, xk, R, 1);                       // R = B - A(X)
+        TV* Z = precondition(R);
+        dev_copy<TV>(ctx, nm, Z, P);
+        std::vector<double> nB, nR;
+        colnorms(n, B, nB);
+        std::vector<zc> PTQ, PTR, QTZ, Pinv, Alpha, Beta;
+        *flag = -1;
+        int it = 0;
+        for (it = 1; it <= max_iter; ++it) {
+            apply_A(A, P, Q, 1);                             // Q = A(P)
+            gram(n, P, Q, gram_ws + 0);
+            gram(n, P, R, gram_ws + 2 * (size_t)m * m);
+            read_matrix(gram_ws + 0, PTQ);
+            read_matrix(gram_ws + 2 * (size_t)m * m, PTR);
+            general_pinv(m, PTQ, pinv_tol, Pinv);
+            matmul_small(m, Pinv, PTR, Alpha, 1.0);          // Alpha = pinv(P'Q) (P'R)
+            block_axpy(n, P, Alpha, xk, xk);                 // X += P Alpha
+            std::vector<zc> nAlpha(Alpha);
+            for (auto& v : nAlpha) v = -v;
+            block_axpy(n, Q, nAlpha, R, R);                  // R -= Q Alpha
+            colnorms(n, R, nR);
+            double mx = 0.0;
+            for (int j = 0; j < m; ++j) {
+                resmat[(size_t)(it - 1) * m + j] = nR[j] / nB[j];
+                mx = std::max(mx, nR[j] / nB[j]);
+            }
+            if (mx <= tol) {
+                *flag = 0;
+                break;
+            }
+            Z = precondition(R);
+            gram(n, Q, Z, gram_ws + 4 * (size_t)m * m);
+            read_matrix(gram_ws + 4 * (size_t)m * m, QTZ);
+            matmul_small(m, Pinv, QTZ, Beta, -1.0);          // Beta = -pinv(P'Q) (Q'Z)
+            block_axpy(n, P, Beta, Z, Pn);                   // P = Z + P Beta
+            std::swap(P, Pn);
+        }
+        if (it > max_iter) it = max_iter;
+        return it;
     }
 
     // ---- KrylovMethods.fgmres with M = one cycle (solveGMRES_MG, SolveFuncs.jl:120-132) ---------

@@ -175,6 +175,144 @@ __global__ void rhsfast_to_colmajor_kernel(long long n, int m, const TV* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
+// block-Krylov pieces (KrylovMethods.blockCG, SolveFuncs.jl:113): n x m blocks stored RHS-fastest.
+// ---------------------------------------------------------------------------------------------
+constexpr int GRAM_ROWS = 32;      // rows staged per tile
+constexpr int GRAM_THREADS = 256;
+constexpr int GRAM_MAX_BLOCKS = 592;
+
+// G = X^H Y  (m x m, row-major, interleaved re/im):  G[a][b] = sum_i conj(X[i,a]) * Y[i,b].
+// Tiles of GRAM_ROWS rows of X and Y are staged in shared memory; each thread owns the (a,b) pairs
+// p = tid, tid+256, ...  Per-CTA partial Gram matrices are combined in block order by the last CTA.
+template <typename TV>
+__global__ void __launch_bounds__(GRAM_THREADS) gram_kernel(long long n, int m, const TV* __restrict__ X,
+                                                            const TV* __restrict__ Y, double* __restrict__ partials,
+                                                            unsigned* __restrict__ counter, double* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char gsm[];
+    TV* xs = reinterpret_cast<TV*>(gsm);
+    TV* ys = xs + (size_t)GRAM_ROWS * m;
+    __shared__ bool is_last;
+    const int mm = m * m;
+    constexpr int MAXP = 16;  // pairs per thread: m <= 64
+    double accr[MAXP], acci[MAXP];
+#pragma unroll
+    for (int q = 0; q < MAXP; ++q) accr[q] = acci[q] = 0.0;
+    const long long ntiles = (n + GRAM_ROWS - 1) / GRAM_ROWS;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const long long r0 = t * GRAM_ROWS;
+        const int rows = (int)min((long long)GRAM_ROWS, n - r0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < rows * m; e += GRAM_THREADS) {
+            xs[e] = X[r0 * m + e];
+            ys[e] = Y[r0 * m + e];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < MAXP; ++q) {
+            const int p = threadIdx.x + q * GRAM_THREADS;
+            if (p < mm) {
+                const int a = p / m, b = p % m;
+                double sr = accr[q], si = acci[q];
+                for (int r = 0; r < rows; ++r) {
+                    TV pr = conj_(xs[r * m + a]) * ys[r * m + b];
+                    sr += VT<TV>::re(pr);
+                    si += VT<TV>::im(pr);
+                }
+                accr[q] = sr;
+                acci[q] = si;
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < MAXP; ++q) {
+        const int p = threadIdx.x + q * GRAM_THREADS;
+        if (p < mm) {
+            partials[((size_t)blockIdx.x * mm + p) * 2] = accr[q];
+            partials[((size_t)blockIdx.x * mm + p) * 2 + 1] = acci[q];
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tk = atomicAdd(counter, 1u);
+        is_last = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        for (int p = threadIdx.x; p < 2 * mm; p += GRAM_THREADS) {
+            double a = 0.0;
+            for (unsigned bIdx = 0; bIdx < gridDim.x; ++bIdx) a += __ldcg(partials + (size_t)bIdx * mm * 2 + p);
+            out[p] = a;
+        }
+        if (threadIdx.x == 0) *counter = 0u;
+    }
+}
+
+// out[i,b] = base[i,b] + sum_a X[i,a] * C[a,b]   (C: m x m row-major on the device; out may alias base,
+// never X).  base == nullptr means 0.
+template <typename TV>
+__global__ void block_axpy_kernel(long long n, int m, const TV* __restrict__ X, const TV* __restrict__ C,
+                                  const TV* base, TV* out) {
+    extern __shared__ __align__(16) unsigned char csm[];
+    TV* cs = reinterpret_cast<TV*>(csm);
+    for (int e = threadIdx.x; e < m * m; e += blockDim.x) cs[e] = C[e];
+    __syncthreads();
+    const long long total = n * m;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long i = t / m;
+        const int b = (int)(t % m);
+        TV acc = base ? base[t] : VT<TV>::zero();
+        const TV* xr = X + i * m;
+        for (int a = 0; a < m; ++a) acc = acc + xr[a] * cs[a * m + b];
+        out[t] = acc;
+    }
+}
+
+// out[b] = sum_i |R[i,b]|^2 for b < m  (deterministic two-stage reduction, m <= 64)
+template <typename TV>
+__global__ void __launch_bounds__(RED_THREADS) colnorm2_kernel(long long n, int m, const TV* __restrict__ R,
+                                                               double* __restrict__ partials,
+                                                               unsigned* __restrict__ counter, double* __restrict__ out) {
+    __shared__ double sacc[RED_THREADS];
+    __shared__ bool is_last;
+    // thread -> column b = tid % mp, row phase = tid / mp
+    int mp = 1;
+    while (mp < m) mp <<= 1;
+    const int rows_per_pass = RED_THREADS / mp;
+    const int b = threadIdx.x % mp, ph = threadIdx.x / mp;
+    double a = 0.0;
+    if (b < m && rows_per_pass > 0) {
+        for (long long i = (long long)blockIdx.x * rows_per_pass + ph; i < n; i += (long long)gridDim.x * rows_per_pass)
+            a += abs2(R[i * m + b]);
+    }
+    sacc[threadIdx.x] = a;
+    __syncthreads();
+    if (threadIdx.x < mp) {
+        double s = 0.0;
+        for (int q = 0; q < rows_per_pass; ++q) s += sacc[q * mp + threadIdx.x];
+        if (threadIdx.x < m) partials[(size_t)blockIdx.x * m + threadIdx.x] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tk = atomicAdd(counter, 1u);
+        is_last = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        if (threadIdx.x < m) {
+            double s = 0.0;
+            for (unsigned bIdx = 0; bIdx < gridDim.x; ++bIdx) s += __ldcg(partials + (size_t)bIdx * m + threadIdx.x);
+            out[threadIdx.x] = s;
+        }
+        if (threadIdx.x == 0) *counter = 0u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // PCG pieces with device-resident scalars (no host round trip between the kernels)
 //   scal[0..1] = gamma = <r,z>, scal[2..3] = delta = <p,Ap>
 // cg_update:  alpha = gamma/delta; if alpha is Inf or negative nothing is changed (the host

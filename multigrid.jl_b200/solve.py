@@ -39,8 +39,19 @@ def solveMG(param: MGparam, b, x, verbose: bool = False):
     return x, param, it
 
 
+def _same_storage(a, b):
+    return (a.shape == b.shape and a.nnz == b.nnz and a.dtype == b.dtype
+            and a.data.__array_interface__["data"][0] == b.data.__array_interface__["data"][0]
+            and a.indices.__array_interface__["data"][0] == b.indices.__array_interface__["data"][0])
+
+
 def _krylov_matrix(dev, AT, param):
+    """The AT argument of solveCG_MG / solveGMRES_MG (SolveFuncs.jl:77-82): uploaded separately only
+    when it is not the matrix the hierarchy was built from."""
     if AT is None or AT is param.As[0]:
+        return
+    import scipy.sparse as sp
+    if sp.issparse(AT) and AT.format == "csc" and _same_storage(AT, param.As[0]):
         return
     dev.set_krylov_matrix(AT)
 

@@ -104,3 +104,21 @@ def test_host_hessenberg_lsq_matches_numpy(cols):
     yr = np.linalg.lstsq(Hc, xi, rcond=None)[0]
     np.testing.assert_allclose(y, yr, rtol=1e-10, atol=1e-13)
     assert abs(res.value - np.linalg.norm(Hc @ yr - xi)) < 1e-12
+
+
+@pytest.mark.parametrize("n,cplx,rank_def", [(1, False, False), (4, False, False), (6, True, False), (5, True, True),
+                                             (32, False, False)])
+def test_host_general_pinv_matches_numpy(n, cplx, rank_def):
+    """general_pinv (one-sided Jacobi SVD) = numpy pinv with the same cut-off; used by blockCG."""
+    from multigrid_jl_b200 import device
+    L = device.lib()
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n, n)) + (1j * rng.standard_normal((n, n)) if cplx else 0)
+    if rank_def:
+        A[:, -1] = A[:, 0] * 2.0
+    Ac = np.ascontiguousarray(A, dtype=np.complex128)
+    P = np.zeros((n, n), dtype=np.complex128)
+    assert L.mgb200_host_general_pinv(n, Ac.ctypes.data_as(ctypes.c_void_p), ctypes.c_double(1e-10),
+                                      P.ctypes.data_as(ctypes.c_void_p)) == 0
+    ref = np.linalg.pinv(Ac, rcond=1e-10)
+    np.testing.assert_allclose(P, ref, rtol=1e-8, atol=1e-10 * np.abs(ref).max())

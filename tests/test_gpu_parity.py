@@ -145,6 +145,21 @@ def test_solveFGMRES_iteration_count(kind, n, levels, flexible):
     assert np.linalg.norm(b - A @ x) <= 1.01e-8 * np.linalg.norm(b)
 
 
+@pytest.mark.parametrize("kind,n,levels,nrhs", [("poisson", [32, 32], 3, 4), ("poisson", [16, 16, 16], 3, 32),
+                                                  ("diffusion", [24, 24], 3, 3)])
+def test_blockCG_iteration_count(kind, n, levels, nrhs):
+    """solveCG_MG with nrhs > 1 -> KrylovMethods.blockCG (SolveFuncs.jl:113)."""
+    import multigrid_jl_b200 as mg
+    A, AT, M, p, b = make_problem(kind, n, levels, nrhs=nrhs, maxit=30, tol=1e-8)
+    oc, o = _oracle(p)
+    x_ref, it_ref, flag_ref, res_ref = oc.solveCG_MG(AT, o, b, np.zeros_like(b))
+    x = np.zeros_like(b)
+    x, _, it = mg.solveCG_MG(AT, p, b, x)
+    assert it == it_ref and p.last_flag == flag_ref == 0
+    np.testing.assert_allclose(p.last_resvec, res_ref, rtol=1e-6, atol=1e-14)
+    assert np.abs(np.linalg.norm(b - A @ x, axis=0) / np.linalg.norm(b, axis=0)).max() <= 1.01e-8
+
+
 def test_sa_amg_hierarchy():
     """SA-AMG hierarchy (long, irregular rows) through the same device cycle."""
     import multigrid_jl_b200 as mg
