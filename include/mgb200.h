@@ -163,9 +163,30 @@ int mgb200_host_hessenberg_lsq(int cols, const double* H, const double* xi, doub
  * out[4] = nnz, out[5] = max row length. */
 int mgb200_kernel_config(mgb200_handle h, int level, int which, int64_t* out);
 
+/* Stencil-dictionary form of matrix `which` of `level` (csrc/pattern.cuh): when the rows of an uploaded CSR
+ * matrix are copies of a few (column-offset, value) stencils the device keeps one 16-bit pattern id per row
+ * and a small dictionary instead of streaming 12-20 bytes per non-zero; results are bit-identical.
+ * out[0] = 1 if in use, out[1] = 1 if offsets are row-relative (no per-row base column), out[2] = patterns,
+ * out[3] = dictionary entries, out[4] = 1 if relaxPrecs[level] is folded into the dictionary (which = 0). */
+int mgb200_pattern_info(mgb200_handle h, int level, int which, int64_t* out);
+
+/* Runtime options: "patterns" (1/0: use the stencil dictionary where available; set before upload to skip
+ * building it), "graphs" (1/0: replay V/F/W cycles from CUDA graphs), "smem_budget" (bytes per CTA used when
+ * choosing the rows per CTA of the CSR-stream kernel at upload). */
+int mgb200_set_option(mgb200_handle h, const char* key, int64_t value);
+
+/* Host-only (no GPU): the row deduplication behind the stencil dictionary, exported for the CPU test-suite.
+ * Input: CSR arrays (row pointers colptr[n_rows+1], Int64 columns, Float64 values).  info[0] = 1 if the matrix
+ * deduplicates within max_patterns / max_entries, info[1] = row-relative, info[2] = patterns, info[3] = entries.
+ * Outputs (caller-allocated): pid[n_rows], c0[n_rows], pat_off[max_patterns+1], delta/val[max_entries]. */
+int mgb200_host_build_patterns(int64_t n_rows, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+                               int index_base, int max_patterns, int max_entries, int64_t* info, uint16_t* pid,
+                               int32_t* c0, int32_t* pat_off, int32_t* delta, double* val);
+
 /* CUDA-event timing of every kernel launch (off by default).  The report is a sequence of
- * records {kind, level, launches, total_ms, algorithmic_bytes}: 5 doubles each; returns the
- * number of records written (<= max_records) in *nrec and resets the counters. */
+ * records {kind, level, launches, total_ms, algorithmic_bytes, format_bytes}: 6 doubles each
+ * (format_bytes = what the device format really streams, e.g. the stencil-dictionary form); returns
+ * the number of records written (<= max_records) in *nrec and resets the counters. */
 int mgb200_profile_enable(mgb200_handle h, int on);
 int mgb200_profile_report(mgb200_handle h, double* records, int max_records, int* nrec);
 int64_t mgb200_launch_count(mgb200_handle h);

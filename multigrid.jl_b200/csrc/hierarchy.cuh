@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "csr_kernels.cuh"
 #include "dense_lu.cuh"
+#include "pattern.cuh"
 #include "vec_kernels.cuh"
 
 namespace mgb200 {
@@ -51,8 +52,10 @@ struct Csr {
     int max_len = 0;
     bool staged = true; // TMA-staged kernel, else row-per-warp fallback
     size_t smem = 0;
+    PatDict<TA> pat;    // stencil-dictionary form (pattern.cuh), when the rows deduplicate
     bool present() const { return rowptr != nullptr; }
     void release() {
+        pat.release();
         dev_free(rowptr);
         dev_free(colind);
         dev_free(val);
@@ -63,7 +66,8 @@ struct Csr {
 
 struct ProfRec {
     int kind, level;
-    double bytes;
+    double bytes;      // algorithmic bytes (SURVEY 8(d) accounting)
+    double fmt_bytes;  // bytes of the device format actually streamed (== bytes for plain CSR)
     cudaEvent_t e0, e1;
 };
 
@@ -74,6 +78,8 @@ struct Context {
     double* scal = nullptr;        // device scalars (64 doubles)
     double* scal_host = nullptr;   // pinned mirror
     int smem_budget = 56 * 1024;
+    int use_patterns = 1;          // 0: always stream CSR (MGB200_PATTERNS / mgb200_set_option)
+    int use_graphs = 1;            // 0: never replay cycles from CUDA graphs
     int max_smem_optin = 0;
     int sm_count = 148;
     bool profiling = false;
@@ -95,6 +101,8 @@ struct Context {
         MGB_CUDA(cudaDeviceGetAttribute(&max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
         MGB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
         smem_budget = env_int("MGB200_SMEM_BUDGET", 56 * 1024);
+        use_patterns = env_int("MGB200_PATTERNS", 1);
+        use_graphs = env_int("MGB200_GRAPHS", 1);
     }
     void destroy() {
         if (!stream) return;
@@ -144,12 +152,13 @@ struct Launch {
     Context& c;
     bool rec;
     ProfRec r;
-    Launch(Context& ctx, int kind, int level, double bytes) : c(ctx), rec(ctx.profiling) {
+    Launch(Context& ctx, int kind, int level, double bytes, double fmt_bytes = -1.0) : c(ctx), rec(ctx.profiling) {
         c.launches++;
         if (rec) {
             r.kind = kind;
             r.level = level;
             r.bytes = bytes;
+            r.fmt_bytes = fmt_bytes < 0 ? bytes : fmt_bytes;
             r.e0 = c.get_event();
             r.e1 = c.get_event();
             cudaEventRecord(r.e0, c.stream);
@@ -170,7 +179,8 @@ struct Launch {
 // ---------------------------------------------------------------------------------------------
 template <typename TA>
 static void upload_csr(Context& ctx, Csr<TA>& M, long long n_rows, long long n_cols, const int64_t* colptr,
-                       const int64_t* rowval, const TA* nzval, int base, bool conjugate) {
+                       const int64_t* rowval, const TA* nzval, int base, bool conjugate,
+                       bool want_patterns = true) {
     MGB_CHECK(n_rows > 0 && n_rows < (1LL << 31) - 8, "matrix rows out of range");
     MGB_CHECK(colptr && rowval && nzval, "null matrix array");
     const long long nnz = colptr[n_rows] - base;
@@ -247,6 +257,13 @@ static void upload_csr(Context& ctx, Csr<TA>& M, long long n_rows, long long n_c
         }
     }
     dev_free(dstat);
+
+    // ---- stencil dictionary (pattern.cuh): deduplicate the rows on the host ---------------------
+    if (want_patterns && ctx.use_patterns && n_cols < (1LL << 31) - 8) {
+        HostPatterns<TA> hp;
+        if (build_patterns<TA>(n_rows, colptr, rowval, nzval, base, conjugate, PAT_MAX_PATTERNS, PAT_MAX_ENTRIES, hp))
+            upload_patterns<TA>(M.pat, hp, n_rows);
+    }
 }
 
 }  // namespace mgb200

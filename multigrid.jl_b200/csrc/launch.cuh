@@ -89,13 +89,58 @@ static void launch_rowwarp_mode(Context& ctx, const Csr<TA>& M, int mode, const 
     MGB_LAUNCH_CHECK();
 }
 
+// vector bytes of one pass (the part of csr_bytes that is not the matrix)
+template <typename TA, typename TV>
+static double vec_bytes(const Csr<TA>& M, int mode, int m, bool d_from_dict) {
+    const double sv = sizeof(TV);
+    switch (mode) {
+        case MODE_SPMV: return ((double)M.n_cols + M.n_rows) * sv * m;
+        case MODE_ADD: return ((double)M.n_cols + 2.0 * M.n_rows) * sv * m;
+        case MODE_RESID: return (3.0 * M.n_rows) * sv * m;
+        default: return (3.0 * m + (d_from_dict ? 0.0 : 1.0)) * M.n_rows * sv;
+    }
+}
+
+// stencil-dictionary kernel (pattern.cuh), one right-hand side
+template <typename TA, typename TV>
+static void launch_pattern_mode(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d,
+                                const TV* dpat, TV* y) {
+    const PatDict<TA>& D = M.pat;
+    const int nt = 256, grid = cdiv(M.n_rows, nt);
+#define MGB_PL(MODE, RR, DP) \
+    pat_kernel<TA, TV, MODE, RR, DP><<<grid, nt, 0, ctx.stream>>>(M.n_rows, D.pid, D.c0, D.pat_off, D.ent, dpat, x, b, d, y)
+#define MGB_PCASE(MODE)                                     \
+    case MODE:                                              \
+        if (D.rowrel) {                                     \
+            if (MODE == MODE_SWEEP && dpat) MGB_PL(MODE, true, true); \
+            else MGB_PL(MODE, true, false);                 \
+        } else {                                            \
+            if (MODE == MODE_SWEEP && dpat) MGB_PL(MODE, false, true); \
+            else MGB_PL(MODE, false, false);                \
+        }                                                   \
+        break;
+    switch (mode) {
+        MGB_PCASE(MODE_SPMV)
+        MGB_PCASE(MODE_ADD)
+        MGB_PCASE(MODE_RESID)
+        MGB_PCASE(MODE_SWEEP)
+    }
+#undef MGB_PCASE
+#undef MGB_PL
+    MGB_LAUNCH_CHECK();
+}
+
 // y = op(M x): the one entry point the cycle uses for A, P and R.
 template <typename TA, typename TV>
 static void csr_apply(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d, TV* y,
-                      int m, int kind, int level) {
+                      int m, int kind, int level, const TV* dpat = nullptr) {
     MGB_CHECK(M.present(), "matrix not uploaded");
-    Launch L(ctx, kind, level, csr_bytes<TA, TV>(M, mode, m));
-    if (!M.staged) {
+    const bool use_pat = M.pat.present && m == 1 && ctx.use_patterns;
+    const double fmt = use_pat ? M.pat.matrix_bytes(M.n_rows) + vec_bytes<TA, TV>(M, mode, m, dpat != nullptr) : -1.0;
+    Launch L(ctx, kind, level, csr_bytes<TA, TV>(M, mode, m), fmt);
+    if (use_pat) {
+        launch_pattern_mode<TA, TV>(ctx, M, mode, x, b, d, dpat, y);
+    } else if (!M.staged) {
         launch_rowwarp_mode<TA, TV>(ctx, M, mode, x, b, d, y, m);
     } else if (m > 1) {
         launch_mrhs_mode<TA, TV>(ctx, M, mode, x, b, d, y, m);

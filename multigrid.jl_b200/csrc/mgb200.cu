@@ -351,6 +351,63 @@ int mgb200_kernel_config(mgb200_handle h, int level, int which, int64_t* out) {
     MGB_CATCH
 }
 
+int mgb200_pattern_info(mgb200_handle h, int level, int which, int64_t* out) {
+    MGB_TRY
+    MGB_CHECK(out, "null output");
+    MGB_BOTH(h, {
+        MGB_CHECK(level >= 1 && level <= H->levels, "level out of range");
+        auto& lv = H->L[level - 1];
+        auto fill = [&](auto& M) {
+            out[0] = (M.pat.present && H->ctx.use_patterns) ? 1 : 0;
+            out[1] = M.pat.rowrel ? 1 : 0;
+            out[2] = M.pat.npat;
+            out[3] = M.pat.nent;
+        };
+        if (which == 0) fill(lv.A);
+        else if (which == 1) fill(lv.P);
+        else fill(lv.R);
+        out[4] = (which == 0 && lv.dpat != nullptr) ? 1 : 0;
+    });
+    MGB_CATCH
+}
+
+int mgb200_set_option(mgb200_handle h, const char* key, int64_t value) {
+    MGB_TRY
+    MGB_CHECK(key, "null key");
+    MGB_BOTH(h, {
+        const std::string k(key);
+        if (k == "patterns") H->ctx.use_patterns = (int)value;
+        else if (k == "graphs") H->ctx.use_graphs = (int)value;
+        else if (k == "smem_budget") H->ctx.smem_budget = (int)value;
+        else throw Error(-1, "mgb200_set_option: unknown key " + k);
+        H->invalidate_graphs();
+    });
+    MGB_CATCH
+}
+
+int mgb200_host_build_patterns(int64_t n_rows, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+                               int index_base, int max_patterns, int max_entries, int64_t* info, uint16_t* pid,
+                               int32_t* c0, int32_t* pat_off, int32_t* delta, double* val) {
+    MGB_TRY
+    MGB_CHECK(colptr && rowval && nzval && info && pid && c0 && pat_off && delta && val, "null argument");
+    HostPatterns<double> hp;
+    const bool ok = build_patterns<double>(n_rows, colptr, rowval, nzval, index_base, false, max_patterns,
+                                           max_entries, hp);
+    info[0] = ok ? 1 : 0;
+    info[1] = info[2] = info[3] = 0;
+    if (ok) {
+        info[1] = hp.rowrel ? 1 : 0;
+        info[2] = hp.npat();
+        info[3] = (int64_t)hp.delta.size();
+        std::memcpy(pid, hp.pid.data(), n_rows * sizeof(uint16_t));
+        if (!hp.rowrel) std::memcpy(c0, hp.c0.data(), n_rows * sizeof(int32_t));
+        std::memcpy(pat_off, hp.pat_off.data(), hp.pat_off.size() * sizeof(int32_t));
+        std::memcpy(delta, hp.delta.data(), hp.delta.size() * sizeof(int32_t));
+        std::memcpy(val, hp.val.data(), hp.val.size() * sizeof(double));
+    }
+    MGB_CATCH
+}
+
 int mgb200_profile_enable(mgb200_handle h, int on) {
     MGB_TRY
     MGB_BOTH(h, {
@@ -366,7 +423,7 @@ int mgb200_profile_report(mgb200_handle h, double* records, int max_records, int
     MGB_BOTH(h, {
         Context& c = H->ctx;
         c.sync();
-        std::map<std::pair<int, int>, std::array<double, 3>> agg;
+        std::map<std::pair<int, int>, std::array<double, 4>> agg;
         for (auto& r : c.prof) {
             float ms = 0.f;
             MGB_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
@@ -374,6 +431,7 @@ int mgb200_profile_report(mgb200_handle h, double* records, int max_records, int
             a[0] += 1.0;
             a[1] += ms;
             a[2] += r.bytes;
+            a[3] += r.fmt_bytes;
             c.ev_pool.push_back(r.e0);
             c.ev_pool.push_back(r.e1);
         }
@@ -381,11 +439,12 @@ int mgb200_profile_report(mgb200_handle h, double* records, int max_records, int
         int k = 0;
         for (auto& kv : agg) {
             if (k >= max_records) break;
-            records[5 * k + 0] = kv.first.first;
-            records[5 * k + 1] = kv.first.second;
-            records[5 * k + 2] = kv.second[0];
-            records[5 * k + 3] = kv.second[1];
-            records[5 * k + 4] = kv.second[2];
+            records[6 * k + 0] = kv.first.first;
+            records[6 * k + 1] = kv.first.second;
+            records[6 * k + 2] = kv.second[0];
+            records[6 * k + 3] = kv.second[1];
+            records[6 * k + 4] = kv.second[2];
+            records[6 * k + 5] = kv.second[3];
             ++k;
         }
         *nrec = k;

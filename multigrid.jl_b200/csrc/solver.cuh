@@ -13,6 +13,8 @@
 // host-tracked "x is known to be zero" flag, which is result-identical: r - A*0 == r).
 #pragma once
 #include <functional>
+#include <map>
+#include <tuple>
 
 #include "dist.cuh"
 #include "launch.cuh"
@@ -40,6 +42,7 @@ struct Level {
     Csr<TV> A;
     Csr<double> P, R;
     TV* d = nullptr;
+    TV* dpat = nullptr;            // d as a function of A's pattern id, when it is one (pattern.cuh)
     TV *b = nullptr, *r = nullptr, *x0 = nullptr, *x1 = nullptr;  // CYCLEmem + ping-pong partner of x
     FgmresMem<TV> memRelax, memK;
     // ---- multi-GPU row partition (dist.cuh) ----
@@ -59,6 +62,7 @@ struct Level {
         release_work();
         A.release(); P.release(); R.release();
         dev_free(d);
+        dev_free(dpat);
         sp.release();
         n = 0;
     }
@@ -104,6 +108,18 @@ struct Hierarchy : HierarchyBase {
     TV *ux0 = nullptr, *ux1 = nullptr, *ucur = nullptr;
     Comm comm;                 // NCCL communicator (world == 1: inactive)
     bool dist_finalized = true;
+    // V/F/W cycles have no host synchronisation: each (buffers, x-is-zero, type) variant is captured
+    // once into a CUDA graph and replayed, which removes the launch gaps of the coarse levels
+    struct GraphEntry {
+        cudaGraphExec_t exec;
+        TV* result;
+        long long launches;
+    };
+    std::map<std::tuple<const TV*, TV*, TV*, bool, char>, GraphEntry> graphs;
+    void invalidate_graphs() {
+        for (auto& kv : graphs) cudaGraphExecDestroy(kv.second.exec);
+        graphs.clear();
+    }
 
     Hierarchy(int nlevels, int nrhs, char ct, int rk, const int64_t* rpre, const int64_t* rpost, int dev) {
         MGB_CHECK(nlevels >= 1, "levels must be >= 1");
@@ -118,6 +134,7 @@ struct Hierarchy : HierarchyBase {
     ~Hierarchy() override {
         cudaSetDevice(ctx.device);
         if (ctx.stream) cudaStreamSynchronize(ctx.stream);
+        invalidate_graphs();
         for (auto& l : L) l.release();
         coarse.release();
         Akry.release();
@@ -136,6 +153,7 @@ struct Hierarchy : HierarchyBase {
     void set_cycle(char ct, const int64_t* rpre, const int64_t* rpost) {
         MGB_CHECK(ct == 'V' || ct == 'F' || ct == 'W' || ct == 'K', "cycle_type must be V, F, W or K");
         cycle_type = ct;
+        invalidate_graphs();
         if (rpre && rpost) {
             pre.assign(levels, 0);
             post.assign(levels, 0);
@@ -166,11 +184,37 @@ struct Hierarchy : HierarchyBase {
         dev_free(lv.d);
         lv.d = dev_alloc<TV>(n);
         MGB_CUDA(cudaMemcpy(lv.d, d, n * sizeof(TV), cudaMemcpyHostToDevice));
+        fold_d(lv, static_cast<const TV*>(d));
         lv.nalloc = n;
         lv.sp.dist = false;
         L[level].n = nc;
         L[level].nalloc = nc;
         work_ready = false;
+    }
+
+    // relaxPrecs[l] as a function of A_l's pattern id: d folds into the dictionary when every row of
+    // a pattern carries bit-identical d (constant-coefficient stencils)
+    void fold_d(Level<TV>& lv, const TV* d) {
+        dev_free(lv.dpat);
+        PatDict<TV>& D = lv.A.pat;
+        if (!D.present || D.host_pid.empty()) return;
+        std::vector<TV> dp(D.npat);
+        std::vector<char> seen(D.npat, 0);
+        bool ok = true;
+        for (long long i = 0; i < lv.n && ok; ++i) {
+            const int p = D.host_pid[i];
+            if (!seen[p]) {
+                seen[p] = 1;
+                dp[p] = d[i];
+            } else if (std::memcmp(&dp[p], &d[i], sizeof(TV)) != 0) {
+                ok = false;
+            }
+        }
+        D.host_pid.clear();
+        D.host_pid.shrink_to_fit();
+        if (!ok) return;
+        lv.dpat = dev_alloc<TV>(D.npat);
+        MGB_CUDA(cudaMemcpy(lv.dpat, dp.data(), D.npat * sizeof(TV), cudaMemcpyHostToDevice));
     }
 
     void upload_coarsest(long long n, const int64_t* cp, const int64_t* rv, const void* nz, int base) {
@@ -179,7 +223,7 @@ struct Hierarchy : HierarchyBase {
         Level<TV>& lv = L[levels - 1];
         lv.n = n;
         lv.nalloc = n;
-        upload_csr<TV>(ctx, lv.A, n, n, cp, rv, static_cast<const TV*>(nz), base, true);
+        upload_csr<TV>(ctx, lv.A, n, n, cp, rv, static_cast<const TV*>(nz), base, true, false);
         coarse.release();
         coarse.n = (int)n;
         const int N = (int)n;
@@ -375,6 +419,7 @@ struct Hierarchy : HierarchyBase {
             dev_free(lv.d);
             lv.d = dev_alloc<TV>(lv.n);
             MGB_CUDA(cudaMemcpy(lv.d, lv.hd.data(), lv.n * sizeof(TV), cudaMemcpyHostToDevice));
+            fold_d(lv, lv.hd.data());
         }
         for (int l = 0; l < levels - 1; ++l) {
             L[l].hA.clear();
@@ -397,6 +442,7 @@ struct Hierarchy : HierarchyBase {
     void ensure_work() {
         if (work_ready) return;
         MGB_CUDA(cudaSetDevice(ctx.device));
+        invalidate_graphs();
         if (!dist_finalized) finalize_dist();
         for (int l = 0; l < levels; ++l) {
             Level<TV>& lv = L[l];
@@ -538,15 +584,21 @@ struct Hierarchy : HierarchyBase {
     TV* relax(int l, const TV* b, TV* x, TV* scratch, int numit, bool xzero) {
         Level<TV>& lv = L[l];
         int sweeps = std::max(numit, 1);  // numit = 0 still does one update (MGcycle.jl:134)
+        const TV* dpat = (lv.dpat && m == 1 && ctx.use_patterns) ? lv.dpat : nullptr;
         if (xzero) {
-            Launch La(ctx, K_DIAG, l + 1, (2.0 * m + 1.0) * lv.n * sizeof(TV));
-            diag_scale_kernel<TV><<<ctx.ew_blocks(lv.n * m), 256, 0, ctx.stream>>>(lv.n, m, lv.d, b, x);
+            if (dpat) {
+                Launch La(ctx, K_DIAG, l + 1, 3.0 * lv.n * sizeof(TV), lv.n * (2.0 * sizeof(TV) + 2.0));
+                diag_scale_pat_kernel<TV><<<ctx.ew_blocks(lv.n), 256, 0, ctx.stream>>>(lv.n, lv.A.pat.pid, dpat, b, x);
+            } else {
+                Launch La(ctx, K_DIAG, l + 1, (2.0 * m + 1.0) * lv.n * sizeof(TV));
+                diag_scale_kernel<TV><<<ctx.ew_blocks(lv.n * m), 256, 0, ctx.stream>>>(lv.n, m, lv.d, b, x);
+            }
             MGB_LAUNCH_CHECK();
             sweeps -= 1;
         }
         for (int s = 0; s < sweeps; ++s) {
             exchange(l, x);
-            csr_apply<TV, TV>(ctx, lv.A, MODE_SWEEP, x, b, lv.d, scratch, m, K_SWEEP, l + 1);
+            csr_apply<TV, TV>(ctx, lv.A, MODE_SWEEP, x, b, lv.d, scratch, m, K_SWEEP, l + 1, dpat);
             std::swap(x, scratch);
         }
         return x;
@@ -690,11 +742,45 @@ struct Hierarchy : HierarchyBase {
         fgmres_relaxation(lv.A, l + 1, r, x, inner, mm, 1e-5, mem, lv.n);
     }
 
+    // cycle from the finest level, replayed from a CUDA graph when the cycle has no host read-backs
+    TV* cycle_fine(const TV* b, TV* x, TV* scratch, bool xzero, char ctype) {
+        const bool can = ctx.use_graphs && !ctx.profiling && relax_kind == 0 && ctype != 'K' && !comm.active() &&
+                         levels > 1;
+        if (!can) return cycle(0, b, x, scratch, xzero, ctype);
+        const auto key = std::make_tuple(b, x, scratch, xzero, ctype);
+        auto it = graphs.find(key);
+        if (it == graphs.end()) {
+            const long long l0 = ctx.launches;
+            MGB_CUDA(cudaStreamBeginCapture(ctx.stream, cudaStreamCaptureModeThreadLocal));
+            TV* res = nullptr;
+            cudaGraph_t g = nullptr;
+            try {
+                res = cycle(0, b, x, scratch, xzero, ctype);
+            } catch (...) {
+                cudaStreamEndCapture(ctx.stream, &g);
+                if (g) cudaGraphDestroy(g);
+                throw;
+            }
+            MGB_CUDA(cudaStreamEndCapture(ctx.stream, &g));
+            GraphEntry e;
+            e.result = res;
+            e.launches = ctx.launches - l0;
+            ctx.launches = l0;
+            cudaError_t err = cudaGraphInstantiate(&e.exec, g, 0);
+            cudaGraphDestroy(g);
+            MGB_CUDA(err);
+            it = graphs.emplace(key, e).first;
+        }
+        MGB_CUDA(cudaGraphLaunch(it->second.exec, ctx.stream));
+        ctx.launches += it->second.launches;
+        return it->second.result;
+    }
+
     // one cycle on the caller's buffers (b in L[0].b, x in ucur); the result pointer is returned
     TV* cycle_top(bool xzero) {
         ensure_work();
         TV* other = (ucur == ux0) ? ux1 : ux0;
-        ucur = cycle(0, L[0].b, ucur, other, xzero, cycle_type);
+        ucur = cycle_fine(L[0].b, ucur, other, xzero, cycle_type);
         return ucur;
     }
 
@@ -717,7 +803,7 @@ struct Hierarchy : HierarchyBase {
         int iter = 0;
         for (int count = 1; count <= max_iter; ++count) {
             TV* other = (xcur == ux0) ? ux1 : ux0;
-            xcur = cycle(0, lv.b, xcur, other, xzero, cycle_type);
+            xcur = cycle_fine(lv.b, xcur, other, xzero, cycle_type);
             xzero = false;
             residual(lv.A, lv.b, xcur, lv.r, 1);
             iter += 1;
@@ -731,7 +817,7 @@ struct Hierarchy : HierarchyBase {
     // getMultigridPreconditioner (SolveFuncs.jl:43-63): z .= 0; recursiveCycle(param,r,z,1); z
     TV* precondition(const TV* r) {
         Level<TV>& lv = L[0];
-        return cycle(0, r, lv.x0, lv.x1, true, cycle_type);
+        return cycle_fine(r, lv.x0, lv.x1, true, cycle_type);
     }
 
     // ---- KrylovMethods.cg with M = one cycle (solveCG_MG, SolveFuncs.jl:103-116) --------------

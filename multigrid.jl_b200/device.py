@@ -289,18 +289,28 @@ class DeviceHierarchy:
         return dict(threads_per_row=int(out[0]), rows_per_cta=int(out[1]), smem_bytes=int(out[2]),
                     staged=bool(out[3]), nnz=int(out[4]), max_row_len=int(out[5]))
 
+    def pattern_info(self, level, which):
+        """Stencil-dictionary form of matrix ``which`` (0 A, 1 P, 2 R) of ``level`` (csrc/pattern.cuh)."""
+        out = np.zeros(5, dtype=np.int64)
+        _check(lib().mgb200_pattern_info(self.h, int(level), int(which), _ptr(out)))
+        return dict(in_use=bool(out[0]), row_relative=bool(out[1]), patterns=int(out[2]), entries=int(out[3]),
+                    d_folded=bool(out[4]))
+
+    def set_option(self, key: str, value: int):
+        _check(lib().mgb200_set_option(self.h, ctypes.c_char_p(key.encode()), ctypes.c_int64(int(value))))
+
     def profile_enable(self, on=True):
         _check(lib().mgb200_profile_enable(self.h, int(bool(on))))
 
     def profile_report(self):
-        rec = np.zeros(5 * 256)
+        rec = np.zeros(6 * 256)
         n = ctypes.c_int(0)
         _check(lib().mgb200_profile_report(self.h, _ptr(rec), 256, ctypes.byref(n)))
         out = []
         for k in range(n.value):
-            kind, level, cnt, ms, byts = rec[5 * k:5 * k + 5]
+            kind, level, cnt, ms, byts, fbyts = rec[6 * k:6 * k + 6]
             out.append(dict(kind=KIND_NAMES[int(kind)], level=int(level), launches=int(cnt),
-                            total_ms=float(ms), bytes=float(byts)))
+                            total_ms=float(ms), bytes=float(byts), format_bytes=float(fbyts)))
         return out
 
     def event_record(self, idx):
@@ -313,6 +323,30 @@ class DeviceHierarchy:
 
     def launch_count(self):
         return int(lib().mgb200_launch_count(self.h))
+
+
+def host_build_patterns(M, max_patterns=4096, max_entries=1 << 16):
+    """Host-only row deduplication behind the stencil dictionary (csrc/pattern.cuh) applied to the CSC arrays
+    of ``M`` read as CSR (i.e. to the operator M^T).  Returns None when the matrix has no such structure."""
+    M = sp.csc_matrix(M)
+    if not M.has_sorted_indices:
+        M.sort_indices()
+    n = M.shape[1]
+    cp, rv, nz = _i64(M.indptr), _i64(M.indices), np.ascontiguousarray(M.data, dtype=np.float64)
+    info = np.zeros(4, dtype=np.int64)
+    pid = np.zeros(max(n, 1), dtype=np.uint16)
+    c0 = np.zeros(max(n, 1), dtype=np.int32)
+    po = np.zeros(max_patterns + 1, dtype=np.int32)
+    de = np.zeros(max_entries, dtype=np.int32)
+    va = np.zeros(max_entries)
+    _check(lib().mgb200_host_build_patterns(ctypes.c_int64(n), _ptr(cp), _ptr(rv), _ptr(nz), 0, int(max_patterns),
+                                            int(max_entries), _ptr(info), _ptr(pid), _ptr(c0), _ptr(po), _ptr(de),
+                                            _ptr(va)))
+    if not info[0]:
+        return None
+    npat, nent = int(info[2]), int(info[3])
+    return dict(row_relative=bool(info[1]), pid=pid[:n], c0=c0[:n], pat_off=po[:npat + 1], delta=de[:nent],
+                val=va[:nent])
 
 
 def uploadHierarchy(param, device: int = 0):

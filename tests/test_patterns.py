@@ -1,0 +1,125 @@
+"""Stencil dictionary (csrc/pattern.cuh): the host-side row deduplication must reproduce the CSR
+arrays bit for bit (CPU), and the device kernels that use it must give results identical to the
+CSR-stream kernels (GPU)."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import make_problem
+
+
+def _rebuild(M, pat):
+    """CSR arrays of the operator from the dictionary form."""
+    M = sp.csc_matrix(M)
+    M.sort_indices()
+    n = M.shape[1]
+    cols, vals, ptr = [], [], [0]
+    for i in range(n):
+        p = pat["pid"][i]
+        k0, k1 = pat["pat_off"][p], pat["pat_off"][p + 1]
+        base = i if pat["row_relative"] else pat["c0"][i]
+        cols.extend(base + pat["delta"][k0:k1])
+        vals.extend(pat["val"][k0:k1])
+        ptr.append(len(cols))
+    return np.array(ptr), np.array(cols), np.array(vals)
+
+
+@pytest.mark.parametrize("n,levels", [([16, 16], 3), ([8, 8, 8], 3), ([12, 10, 6], 2)])
+def test_host_patterns_reproduce_csr(n, levels):
+    from multigrid_jl_b200 import device
+    A, AT, M, p, b = _cpu_problem(n, levels)
+    for l in range(levels - 1):
+        for name, mat, rowrel in (("A", p.As[l], True), ("P", p.Ps[l], False), ("R", p.Rs[l], False)):
+            mat = sp.csc_matrix(mat)
+            mat.sort_indices()
+            pat = device.host_build_patterns(mat)
+            if pat is None:      # tiny coarse matrices are not worth a dictionary
+                assert mat.shape[1] < 8 * 27
+                continue
+            assert pat["row_relative"] == rowrel, (name, l)
+            ptr, cols, vals = _rebuild(mat, pat)
+            assert np.array_equal(ptr, mat.indptr)
+            assert np.array_equal(cols, mat.indices)
+            assert np.array_equal(vals.view(np.int64), np.ascontiguousarray(mat.data, dtype=np.float64).view(np.int64))
+            assert len(pat["pat_off"]) - 1 <= 27 if mat.shape[0] == mat.shape[1] else True
+
+
+def test_host_patterns_reject_unstructured():
+    from multigrid_jl_b200 import device
+    rng = np.random.default_rng(3)
+    M = sp.random(3000, 3000, density=0.003, random_state=rng, format="csc") + sp.identity(3000, format="csc")
+    assert device.host_build_patterns(M) is None
+    # structured sparsity but row-dependent values: no value dictionary either
+    T = sp.diags([rng.random(2999), rng.random(3000) + 2.0, rng.random(2999)], [-1, 0, 1], format="csc")
+    assert device.host_build_patterns(T) is None
+
+
+def test_host_patterns_empty_rows_and_caps():
+    from multigrid_jl_b200 import device
+    n = 4000
+    d = np.ones(n)
+    d[::7] = 0.0
+    M = sp.diags([d], [0], format="csc")
+    M.eliminate_zeros()
+    pat = device.host_build_patterns(M)
+    assert pat is not None and len(pat["pat_off"]) - 1 == 2
+    ptr, cols, vals = _rebuild(M, pat)
+    M.sort_indices()
+    assert np.array_equal(ptr, M.indptr) and np.array_equal(cols, M.indices)
+    # a cap of one pattern cannot hold two
+    assert device.host_build_patterns(M, max_patterns=1) is None
+
+
+def _cpu_problem(n, levels):
+    import multigrid_jl_b200 as mg
+    dom = [0.0, 1.0] * len(n)
+    M = mg.getRegularMesh(dom, n)
+    A = mg.poisson_shifted(M, 1e-4)
+    p = mg.getMGparam(np.float64, np.int64, levels, 8, 4, 1e-12, "Jac", 0.8, 2, 2, 'V')
+    mg.MGsetup(A, M, p, 1)
+    return A, A, M, p, None
+
+
+# ---- GPU: dictionary kernels vs CSR-stream kernels, graph replay vs eager launches ------------------
+
+def _solve(kind, n, levels, cycle, env):
+    import multigrid_jl_b200 as mg
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        A, AT, M, p, b = make_problem(kind, n, levels, cycle=cycle, maxit=5)
+        x = np.zeros_like(b)
+        x, _, it = mg.solveMG(p, b, x)
+        info = [p.device.pattern_info(l + 1, w) for l in range(levels - 1) for w in range(3)]
+        res = p.last_resvec.copy()
+        p.device.destroy()
+        return x, res, it, info
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,n,levels", [("poisson", [64, 64], 4), ("poisson", [24, 24, 24], 3),
+                                           ("helmholtz", [48, 48], 3), ("helmholtz", [16, 16, 16], 3),
+                                           ("diffusion", [24, 24, 12], 3)])
+@pytest.mark.parametrize("cycle", ['V', 'W', 'F'])
+def test_pattern_and_graph_paths_bit_identical(kind, n, levels, cycle):
+    x0, r0, it0, info0 = _solve(kind, n, levels, cycle, {"MGB200_PATTERNS": "0", "MGB200_GRAPHS": "0"})
+    x1, r1, it1, info1 = _solve(kind, n, levels, cycle, {"MGB200_PATTERNS": "1", "MGB200_GRAPHS": "0"})
+    x2, r2, it2, info2 = _solve(kind, n, levels, cycle, {"MGB200_PATTERNS": "1", "MGB200_GRAPHS": "1"})
+    assert not any(i["in_use"] for i in info0)
+    if kind != "diffusion":
+        assert info1[0]["in_use"] and info1[0]["row_relative"] and info1[0]["d_folded"]   # A_1
+        assert info1[1]["in_use"] and not info1[1]["row_relative"]                            # P_1
+        assert info1[2]["in_use"]                                                             # R_1
+    else:
+        assert not info1[0]["in_use"]      # variable coefficients: no value dictionary for A
+    assert it0 == it1 == it2
+    assert np.array_equal(r0, r1) and np.array_equal(r1, r2)
+    assert np.array_equal(x0, x1) and np.array_equal(x1, x2)
