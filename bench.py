@@ -343,6 +343,7 @@ def run_ours(args):
     fmt_achieved = dom["format_bytes"] / (dom["total_ms"] * 1e-3) / 1e9
     fmt_cycle = sum(r["format_bytes"] for r in prof) / args.steps
     pinfo = dev.pattern_info(1, 0)
+    dinfo = dev.dist_info() if world > 1 else None
     nbytes = nbytes_cycle
     roofline = {"bound": "hbm", "kernel": f"{dom['kind']} level {dom['level']} (fused Jacobi sweep x' = x + d.*(b - A x))"
                 if dom["kind"] == "sweep" else f"{dom['kind']} level {dom['level']}",
@@ -404,7 +405,10 @@ def run_ours(args):
         "config": {"workload": workload, "rows": N_total,
                    "l2_policy": "inputs larger than L2 (fine-level vectors b, x, x', r: 4 x 136 MB per GPU touched every "
                                 "cycle, plus the CSR arrays when the CSR-stream kernels run; L2 is 126 MB)",
-                   "parallelism": f"row-partitioned z-slabs x{world}" if world > 1 else "single GPU"},
+                   "parallelism": f"row-partitioned z-slabs x{world}" if world > 1 else "single GPU",
+                   "halo_exchange": (None if world == 1 else
+                                     ("own put/wait kernels over NVLink peer memory (CUDA IPC), cycle replayed from a "
+                                      "CUDA graph" if dinfo["p2p"] else "ncclSend/ncclRecv"))},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         "kernels": kern[:10],
     }

@@ -126,7 +126,11 @@ int mgb200_synchronize(mgb200_handle h);
  * (z-slabs of the reference's DomainDecomposition layout, src/DomainDecomposition/DDIndices.jl:41-47).
  * Call order: create -> dist_init -> dist_upload_level for the distributed levels (fine ones),
  * upload_level / upload_coarsest with the GLOBAL matrices for the replicated (coarse) levels.
- * Vectors passed to the solve entry points then hold only the owned rows of this rank. */
+ * Vectors passed to the solve entry points then hold only the owned rows of this rank.
+ * On the device a distributed level keeps its vectors as [ghost rows below | owned rows | ghost rows above], so a
+ * stencil matrix keeps its row-relative structure (and its stencil dictionary) on every slab.  Ghost rows travel
+ * over NVLink peer memory written by the library's own kernels when the ranks can map each other's memory
+ * (cudaIpc), otherwise through ncclSend/ncclRecv; Krylov scalars always use ncclAllReduce. */
 
 /* 128-byte NCCL unique id, created on one rank and distributed by the caller (e.g. torch.distributed,
  * Julia Distributed); the same bytes go to every rank's mgb200_dist_init. */
@@ -143,6 +147,11 @@ int mgb200_dist_upload_level(mgb200_handle h, int level, int64_t n_global, const
                              const int64_t* p_colptr, const int64_t* p_rowval, const double* p_nzval,
                              const int64_t* r_colptr, const int64_t* r_rowval, const double* r_nzval,
                              const void* d, int index_base);
+
+/* out[0] = world, out[1] = rank, out[2] = 1 if halo exchange and coarse gather run over NVLink peer memory
+ * (CUDA IPC, csrc/p2p.cuh; 0: NCCL send/recv, e.g. when MGB200_P2P=0 or the peers are not IPC reachable),
+ * out[3] = number of row-partitioned levels.  Collective on first use (it finalises the distributed setup). */
+int mgb200_dist_info(mgb200_handle h, int64_t* out);
 
 /* Host-only planning helper (no GPU): sorted unique ghost ids of a row slab [lo,hi) and the column
  * indices remapped to the [owned | ghost] layout.  ghosts must hold nnz entries. */
@@ -172,7 +181,8 @@ int mgb200_pattern_info(mgb200_handle h, int level, int which, int64_t* out);
 
 /* Runtime options: "patterns" (1/0: use the stencil dictionary where available; set before upload to skip
  * building it), "graphs" (1/0: replay V/F/W cycles from CUDA graphs), "smem_budget" (bytes per CTA used when
- * choosing the rows per CTA of the CSR-stream kernel at upload). */
+ * choosing the rows per CTA of the CSR-stream kernel at upload), "pattern_rows_per_thread" (1, 2 or 4 rows
+ * per thread of the stencil-dictionary kernel). */
 int mgb200_set_option(mgb200_handle h, const char* key, int64_t value);
 
 /* Host-only (no GPU): the row deduplication behind the stencil dictionary, exported for the CPU test-suite.

@@ -1,8 +1,9 @@
 // Multi-GPU row partition: ghost maps, halo exchange and scalar all-reduces over NCCL.
 //
-// One process per GPU.  A distributed level keeps its vectors as [owned rows | ghost rows]; the
+// One process per GPU.  A distributed level keeps its vectors as [ghosts below | owned rows | ghosts
+// above] with the vector pointer at the first owned row (lower ghosts have negative indices); the
 // CSR column indices are remapped into that layout at finalisation, so the compute kernels are
-// exactly the single-GPU ones.  Communication per operator application = one halo exchange of
+// exactly the single-GPU ones and stencil matrices keep their row-relative structure.  Communication per operator application = one halo exchange of
 // the input vector (ncclSend/ncclRecv pairs inside one group, peers are the slab neighbours for
 // the z-slab layout of src/DomainDecomposition/DDIndices.jl:41-47) and, for Krylov scalars,
 // an in-place ncclAllReduce on a few doubles.  Coarse levels are replicated: the restricted
@@ -110,11 +111,21 @@ static inline void sort_unique(std::vector<long long>& v) {
     std::sort(v.begin(), v.end());
     v.erase(std::unique(v.begin(), v.end()), v.end());
 }
-// global id -> local index in the [owned | ghost] layout
+// global id -> local index in the [owned | ghost] layout (host planner of the CPU test-suite)
 static inline long long to_local(long long c, long long lo, long long hi, const std::vector<long long>& ghosts) {
     if (c >= lo && c < hi) return c - lo;
     auto it = std::lower_bound(ghosts.begin(), ghosts.end(), c);
     return (hi - lo) + (it - ghosts.begin());
+}
+// global id -> index relative to the first OWNED row in the [ghosts below lo | owned | ghosts above hi]
+// layout the device uses: lower ghosts get negative indices.  For a z-slab the ghost planes are the
+// contiguous global ranges next to [lo,hi), so the map is the pure shift c - lo and a stencil matrix keeps
+// its row-relative column offsets (the stencil dictionary of pattern.cuh survives the partition).
+static inline long long to_local_split(long long c, long long lo, long long hi, const std::vector<long long>& ghosts,
+                                       long long n_lo) {
+    if (c >= lo && c < hi) return c - lo;
+    const long long g = std::lower_bound(ghosts.begin(), ghosts.end(), c) - ghosts.begin();
+    return g < n_lo ? g - n_lo : (hi - lo) + (g - n_lo);
 }
 
 // vector space of one distributed level
@@ -124,6 +135,7 @@ struct DistSpace {
     std::vector<long long> row_offsets;  // world + 1
     long long lo = 0, hi = 0;            // owned global range
     long long n_owned = 0, n_ghost = 0;
+    long long n_lo = 0;                  // ghosts with global id < lo: they sit IN FRONT of the owned rows
     std::vector<long long> ghosts;       // sorted global ids
     std::vector<int> recv_cnt, recv_off; // per peer (ghosts are grouped by owner because owners hold ranges)
     std::vector<int> send_cnt, send_off;
@@ -131,6 +143,8 @@ struct DistSpace {
     int n_send = 0;
     void* sendbuf = nullptr;             // n_send * m * sizeof(TV)
     size_t sendbuf_bytes = 0;
+    // position of ghost number g relative to the first owned row
+    long long ghost_pos(long long g) const { return g < n_lo ? g - n_lo : n_owned + (g - n_lo); }
     int owner_of(long long gid) const {
         auto it = std::upper_bound(row_offsets.begin(), row_offsets.end(), gid);
         return (int)(it - row_offsets.begin()) - 1;

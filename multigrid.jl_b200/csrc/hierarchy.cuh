@@ -4,6 +4,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "common.cuh"
@@ -30,9 +32,41 @@ static T* dev_alloc(size_t n) {
     MGB_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
     return p;
 }
+// Vectors of a row-partitioned level keep their lower ghost rows IN FRONT of the owned rows (dist.cuh): the
+// pointer handed out is base + pad.  The registry lets dev_free release such a pointer like any other.
+struct PaddedRegistry {
+    std::mutex mu;
+    std::unordered_map<const void*, void*> base;
+};
+static PaddedRegistry& padded_registry() {
+    static PaddedRegistry r;
+    return r;
+}
+template <typename T>
+static T* vec_alloc(size_t total, size_t pad, cudaStream_t stream) {
+    T* b = dev_alloc<T>(total);
+    MGB_CUDA(cudaMemsetAsync(b, 0, std::max<size_t>(total, 1) * sizeof(T), stream));
+    if (pad == 0) return b;
+    PaddedRegistry& r = padded_registry();
+    std::lock_guard<std::mutex> g(r.mu);
+    r.base[b + pad] = b;
+    return b + pad;
+}
 template <typename T>
 static void dev_free(T*& p) {
-    if (p) cudaFree(p);
+    if (p) {
+        void* b = p;
+        {
+            PaddedRegistry& r = padded_registry();
+            std::lock_guard<std::mutex> g(r.mu);
+            auto it = r.base.find(p);
+            if (it != r.base.end()) {
+                b = it->second;
+                r.base.erase(it);
+            }
+        }
+        cudaFree(b);
+    }
     p = nullptr;
 }
 
@@ -80,6 +114,7 @@ struct Context {
     int smem_budget = 56 * 1024;
     int use_patterns = 1;          // 0: always stream CSR (MGB200_PATTERNS / mgb200_set_option)
     int use_graphs = 1;            // 0: never replay cycles from CUDA graphs
+    int pat_rpt = 1;               // rows per thread of the stencil-dictionary kernel (1, 2 or 4)
     int max_smem_optin = 0;
     int sm_count = 148;
     bool profiling = false;
@@ -103,6 +138,8 @@ struct Context {
         smem_budget = env_int("MGB200_SMEM_BUDGET", 56 * 1024);
         use_patterns = env_int("MGB200_PATTERNS", 1);
         use_graphs = env_int("MGB200_GRAPHS", 1);
+        pat_rpt = env_int("MGB200_PAT_RPT", 1);
+        if (pat_rpt != 1 && pat_rpt != 2 && pat_rpt != 4) pat_rpt = 1;
     }
     void destroy() {
         if (!stream) return;

@@ -56,6 +56,7 @@ static void spmatmul_impl(Hierarchy<TV>* H, int level, int which, double alpha, 
     MGB_CHECK(level >= 1 && level <= H->levels, "level out of range");
     MGB_CHECK(which >= 0 && which <= 2, "which must be 0 (A), 1 (P) or 2 (R)");
     Level<TV>& lv = H->L[level - 1];
+    MGB_CHECK(!lv.sp.dist, "mgb200_spmatmul is not available on row-partitioned levels");
     int mode;
     if (alpha == 1.0 && beta == 0.0) mode = MODE_SPMV;
     else if (alpha == 1.0 && beta == 1.0) mode = MODE_ADD;
@@ -205,6 +206,21 @@ int mgb200_host_plan_ghosts(int64_t nnz, const int64_t* cols, int64_t lo, int64_
     *n_ghost = (int64_t)g.size();
     for (size_t i = 0; i < g.size(); ++i) ghosts[i] = g[i];
     for (int64_t k = 0; k < nnz; ++k) local_cols[k] = to_local(cols[k], lo, hi, g);
+    MGB_CATCH
+}
+
+int mgb200_dist_info(mgb200_handle h, int64_t* out) {
+    MGB_TRY
+    MGB_CHECK(out, "null output");
+    MGB_BOTH(h, {
+        if (H->comm.active()) H->ensure_work();
+        out[0] = H->comm.world;
+        out[1] = H->comm.rank;
+        out[2] = H->p2p.on ? 1 : 0;
+        int nd = 0;
+        for (auto& l : H->L) nd += l.sp.dist ? 1 : 0;
+        out[3] = nd;
+    });
     MGB_CATCH
 }
 
@@ -378,6 +394,10 @@ int mgb200_set_option(mgb200_handle h, const char* key, int64_t value) {
         const std::string k(key);
         if (k == "patterns") H->ctx.use_patterns = (int)value;
         else if (k == "graphs") H->ctx.use_graphs = (int)value;
+        else if (k == "pattern_rows_per_thread") {
+            MGB_CHECK(value == 1 || value == 2 || value == 4, "pattern_rows_per_thread must be 1, 2 or 4");
+            H->ctx.pat_rpt = (int)value;
+        }
         else if (k == "smem_budget") H->ctx.smem_budget = (int)value;
         else throw Error(-1, "mgb200_set_option: unknown key " + k);
         H->invalidate_graphs();

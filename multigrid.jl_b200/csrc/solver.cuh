@@ -18,6 +18,7 @@
 
 #include "dist.cuh"
 #include "launch.cuh"
+#include "p2p.cuh"
 #include "smalldense.h"
 
 namespace mgb200 {
@@ -107,6 +108,7 @@ struct Hierarchy : HierarchyBase {
     // L[0].x0/x1 are memCycle[1].x, the z of the preconditioner closure (SolveFuncs.jl:50,59)
     TV *ux0 = nullptr, *ux1 = nullptr, *ucur = nullptr;
     Comm comm;                 // NCCL communicator (world == 1: inactive)
+    P2P p2p;                   // halo exchange / coarse gather over NVLink peer memory (p2p.cuh)
     bool dist_finalized = true;
     // V/F/W cycles have no host synchronisation: each (buffers, x-is-zero, type) variant is captured
     // once into a CUDA graph and replayed, which removes the launch gaps of the coarse levels
@@ -135,6 +137,7 @@ struct Hierarchy : HierarchyBase {
         cudaSetDevice(ctx.device);
         if (ctx.stream) cudaStreamSynchronize(ctx.stream);
         invalidate_graphs();
+        p2p_release();
         for (auto& l : L) l.release();
         coarse.release();
         Akry.release();
@@ -342,6 +345,7 @@ struct Hierarchy : HierarchyBase {
                 collect_ghosts(L[l - 1].hP.col.data(), (long long)L[l - 1].hP.col.size(), sp.lo, sp.hi, sp.ghosts);
             sort_unique(sp.ghosts);
             sp.n_ghost = (long long)sp.ghosts.size();
+            sp.n_lo = std::lower_bound(sp.ghosts.begin(), sp.ghosts.end(), sp.lo) - sp.ghosts.begin();
             lv.nalloc = sp.n_owned + sp.n_ghost;
             MGB_CHECK(lv.nalloc < (1LL << 31) - 8, "local vector too long for 32-bit indices");
             sp.recv_cnt.assign(w, 0);
@@ -399,13 +403,13 @@ struct Hierarchy : HierarchyBase {
             Level<TV>& lv = L[l];
             if (!lv.sp.dist) continue;
             DistSpace& sp = lv.sp;
-            for (auto& c : lv.hA.col) c = to_local(c, sp.lo, sp.hi, sp.ghosts);
-            for (auto& c : lv.hR.col) c = to_local(c, sp.lo, sp.hi, sp.ghosts);
+            for (auto& c : lv.hA.col) c = to_local_split(c, sp.lo, sp.hi, sp.ghosts, sp.n_lo);
+            for (auto& c : lv.hR.col) c = to_local_split(c, sp.lo, sp.hi, sp.ghosts, sp.n_lo);
             Level<TV>& lc = L[l + 1];
             long long pcols;
             if (lc.sp.dist) {
                 // lc's ghost set already contains P's columns (step 1)
-                for (auto& c : lv.hP.col) c = to_local(c, lc.sp.lo, lc.sp.hi, lc.sp.ghosts);
+                for (auto& c : lv.hP.col) c = to_local_split(c, lc.sp.lo, lc.sp.hi, lc.sp.ghosts, lc.sp.n_lo);
                 pcols = lc.sp.n_owned + lc.sp.n_ghost;
             } else {
                 pcols = lv.nc_global;
@@ -456,19 +460,17 @@ struct Hierarchy : HierarchyBase {
                 lv.sp.sendbuf_bytes = (size_t)lv.sp.n_send * m * sizeof(TV);
                 MGB_CUDA(cudaMalloc(&lv.sp.sendbuf, lv.sp.sendbuf_bytes));
             }
-            lv.b = dev_alloc<TV>(nm);
-            lv.r = dev_alloc<TV>(nm);
-            lv.x0 = dev_alloc<TV>(nm);
-            lv.x1 = dev_alloc<TV>(nm);
-            MGB_CUDA(cudaMemsetAsync(lv.x0, 0, nm * sizeof(TV), ctx.stream));
-            MGB_CUDA(cudaMemsetAsync(lv.x1, 0, nm * sizeof(TV), ctx.stream));
-            MGB_CUDA(cudaMemsetAsync(lv.b, 0, nm * sizeof(TV), ctx.stream));
+            const size_t pad = vec_pad(l);
+            lv.b = vec_alloc<TV>(nm, pad, ctx.stream);
+            lv.r = vec_alloc<TV>(nm, pad, ctx.stream);
+            lv.x0 = vec_alloc<TV>(nm, pad, ctx.stream);
+            lv.x1 = vec_alloc<TV>(nm, pad, ctx.stream);
             if (l < levels - 1 && relax_kind == 1) {
-                alloc_fgmres(lv.memRelax, nm, std::max(std::max(pre[l], post[l]), 1));
+                alloc_fgmres(lv.memRelax, nm, std::max(std::max(pre[l], post[l]), 1), pad);
             }
             // memKcycle[level] of the reference belongs to level+1 (MGsetup.jl:213-215): sized here
             // for level l (1-based l+1 >= 2) and used when the parent recurses into it.
-            if (cycle_type == 'K' && l >= 1 && l < levels - 1) alloc_fgmres(lv.memK, nm, 2);
+            if (cycle_type == 'K' && l >= 1 && l < levels - 1) alloc_fgmres(lv.memK, nm, 2, pad);
         }
         MGB_CHECK(coarse.n == (int)L[levels - 1].n, "coarsest factorisation missing (mgb200_upload_coarsest)");
         dev_free(coarse.y);
@@ -478,37 +480,39 @@ struct Hierarchy : HierarchyBase {
         hstage_n = 0;
         dev_free(ux0);
         dev_free(ux1);
-        ux0 = dev_alloc<TV>((size_t)L[0].nalloc * m);
-        ux1 = dev_alloc<TV>((size_t)L[0].nalloc * m);
-        MGB_CUDA(cudaMemsetAsync(ux0, 0, (size_t)L[0].nalloc * m * sizeof(TV), ctx.stream));
-        MGB_CUDA(cudaMemsetAsync(ux1, 0, (size_t)L[0].nalloc * m * sizeof(TV), ctx.stream));
+        ux0 = vec_alloc<TV>((size_t)L[0].nalloc * m, vec_pad(0), ctx.stream);
+        ux1 = vec_alloc<TV>((size_t)L[0].nalloc * m, vec_pad(0), ctx.stream);
         ucur = ux0;
         ctx.sync();
+        p2p_setup();
         work_ready = true;
     }
-    void alloc_fgmres(FgmresMem<TV>& mem, size_t nm, int inner) {
+    // elements in front of the first owned row of a level-l vector (lower ghost rows, dist.cuh)
+    size_t vec_pad(int l) const { return L[l].sp.dist ? (size_t)L[l].sp.n_lo * m : 0; }
+    void alloc_fgmres(FgmresMem<TV>& mem, size_t nm, int inner, size_t pad) {
         mem.release();
         mem.inner = inner;
-        mem.Z = dev_alloc<TV>(nm * inner);
-        mem.AZ = dev_alloc<TV>(nm * inner);
-        mem.Az = dev_alloc<TV>(nm);
-        mem.vp0 = dev_alloc<TV>(nm);
-        mem.vp1 = dev_alloc<TV>(nm);
+        mem.Z = vec_alloc<TV>(nm * inner, pad, ctx.stream);
+        mem.AZ = vec_alloc<TV>(nm * inner, pad, ctx.stream);
+        mem.Az = vec_alloc<TV>(nm, pad, ctx.stream);
+        mem.vp0 = vec_alloc<TV>(nm, pad, ctx.stream);
+        mem.vp1 = vec_alloc<TV>(nm, pad, ctx.stream);
     }
     void ensure_krylov(int vcols, bool needZ) {
         const size_t nm = (size_t)L[0].nalloc * m;
+        const size_t pad = vec_pad(0);
         if (!kr) {
-            kr = dev_alloc<TV>(nm);
-            kp = dev_alloc<TV>(nm);
-            kAp = dev_alloc<TV>(nm);
-            kw = dev_alloc<TV>(nm);
+            kr = vec_alloc<TV>(nm, pad, ctx.stream);
+            kp = vec_alloc<TV>(nm, pad, ctx.stream);
+            kAp = vec_alloc<TV>(nm, pad, ctx.stream);
+            kw = vec_alloc<TV>(nm, pad, ctx.stream);
         }
         if (vcols > kV_cols || (needZ && !kZ)) {
             dev_free(kV);
             dev_free(kZ);
             kV_cols = std::max(vcols, kV_cols);
-            kV = dev_alloc<TV>(nm * kV_cols);
-            kZ = dev_alloc<TV>(nm * kV_cols);
+            kV = vec_alloc<TV>(nm * kV_cols, pad, ctx.stream);
+            kZ = vec_alloc<TV>(nm * kV_cols, pad, ctx.stream);
         }
     }
 
@@ -544,11 +548,21 @@ struct Hierarchy : HierarchyBase {
         return zc(v[0], v[1]);
     }
 
-    // halo exchange of a level-l vector laid out [owned | ghost] (dist.cuh)
+    // halo exchange of a level-l vector laid out [ghosts below | owned | ghosts above], v at the first owned row
     void exchange(int l, TV* v) {
         if (!comm.active() || l < 0 || l >= levels || !L[l].sp.dist) return;
         DistSpace& sp = L[l].sp;
         Launch La(ctx, K_COPY, l + 1, 2.0 * sp.n_ghost * m * sizeof(TV));
+        if (p2p.on) {
+            // put into the neighbours' receive buffers over NVLink, then wait for theirs and unpack (p2p.cuh)
+            ChanDev<TV>* cd = static_cast<ChanDev<TV>*>(p2p.chan[l].dev);
+            const long long work = std::max<long long>((long long)sp.n_send, sp.n_ghost) * m;
+            const int g = (int)std::max<long long>(1, std::min<long long>((work + 1023) / 1024, 64));
+            p2p_halo_kernel<TV><<<g, 256, 0, ctx.stream>>>(cd, v, sp.d_send_idx, sp.n_send, sp.n_ghost, sp.n_lo,
+                                                            sp.n_owned, m, p2p.epoch + l, p2p.ticket + l);
+            MGB_LAUNCH_CHECK();
+            return;
+        }
         TV* sb = static_cast<TV*>(sp.sendbuf);
         if (sp.n_send > 0) {
             pack_kernel<TV><<<ctx.ew_blocks((long long)sp.n_send * m), 256, 0, ctx.stream>>>(v, sp.d_send_idx, sp.n_send, m, sb);
@@ -560,7 +574,7 @@ struct Hierarchy : HierarchyBase {
             if (sp.send_cnt[p] > 0)
                 MGB_NCCL(nccl().Send(sb + (size_t)sp.send_off[p] * m, sp.send_cnt[p] * per, ncclDouble, p, comm.comm, ctx.stream));
             if (sp.recv_cnt[p] > 0)
-                MGB_NCCL(nccl().Recv(v + ((size_t)sp.n_owned + sp.recv_off[p]) * m, sp.recv_cnt[p] * per, ncclDouble, p, comm.comm, ctx.stream));
+                MGB_NCCL(nccl().Recv(v + sp.ghost_pos(sp.recv_off[p]) * m, sp.recv_cnt[p] * per, ncclDouble, p, comm.comm, ctx.stream));
         }
         MGB_NCCL(nccl().GroupEnd());
     }
@@ -568,6 +582,14 @@ struct Hierarchy : HierarchyBase {
     void allgather_rows(int l, TV* v, const std::vector<long long>& offs) {
         if (!comm.active()) return;
         Launch La(ctx, K_COPY, l + 1, 1.0 * L[l].n * m * sizeof(TV));
+        if (p2p.on && p2p.gather_level == l) {
+            ChanDev<TV>* cd = static_cast<ChanDev<TV>*>(p2p.chan[levels].dev);
+            const long long off = offs[comm.rank] * m, cnt = (offs[comm.rank + 1] - offs[comm.rank]) * m;
+            const int g = (int)std::max<long long>(1, std::min<long long>((L[l].n * m + 1023) / 1024, 64));
+            p2p_gather_kernel<TV><<<g, 256, 0, ctx.stream>>>(cd, v, off, cnt, m, p2p.epoch + levels, p2p.ticket + levels);
+            MGB_LAUNCH_CHECK();
+            return;
+        }
         const size_t per = (size_t)m * (sizeof(TV) / sizeof(double));
         MGB_NCCL(nccl().GroupStart());
         for (int p = 0; p < comm.world; ++p) {
@@ -576,6 +598,162 @@ struct Hierarchy : HierarchyBase {
                 MGB_NCCL(nccl().Broadcast(v + (size_t)offs[p] * m, v + (size_t)offs[p] * m, cnt * per, ncclDouble, p, comm.comm, ctx.stream));
         }
         MGB_NCCL(nccl().GroupEnd());
+    }
+
+    // ---- peer-memory exchange (p2p.cuh): IPC block, channel tables -------------------------------------
+    void p2p_release() {
+        if (!p2p.block && p2p.peer.empty()) return;
+        cudaSetDevice(ctx.device);
+        if (ctx.stream) cudaStreamSynchronize(ctx.stream);
+        for (int q = 0; q < (int)p2p.peer.size(); ++q)
+            if (q != comm.rank && p2p.peer[q]) cudaIpcCloseMemHandle(p2p.peer[q]);
+        p2p.peer.clear();
+        for (auto& c : p2p.chan) {
+            if (c.dev) cudaFree(c.dev);
+            c.dev = nullptr;
+        }
+        p2p.chan.clear();
+        // The exported block itself is NOT freed here: a peer may still have it mapped (ranks tear down at
+        // different times and cudaFree of memory that is still imported elsewhere is undefined).  It is a few
+        // MB and goes away with the process.
+        p2p.block = nullptr;
+        p2p.block_bytes = 0;
+        dev_free(p2p.epoch);
+        dev_free(p2p.ticket);
+        p2p.on = false;
+        p2p.gather_level = -1;
+    }
+    void nccl_allgather_bytes(const void* mine, size_t bytes, std::vector<unsigned char>& all) {
+        const int w = comm.world, r = comm.rank;
+        unsigned char* d = dev_alloc<unsigned char>(bytes * w);
+        MGB_CUDA(cudaMemcpyAsync(d + bytes * r, mine, bytes, cudaMemcpyHostToDevice, ctx.stream));
+        MGB_NCCL(nccl().AllGather(d + bytes * r, d, bytes, ncclInt8, comm.comm, ctx.stream));
+        all.resize(bytes * w);
+        MGB_CUDA(cudaMemcpyAsync(all.data(), d, bytes * w, cudaMemcpyDeviceToHost, ctx.stream));
+        ctx.sync();
+        dev_free(d);
+    }
+    // collective over all ranks (called from ensure_work)
+    void p2p_setup() {
+        p2p_release();
+        if (!comm.active() || env_int("MGB200_P2P", 1) == 0 || comm.world > P2P_MAXW) return;
+        const int w = comm.world, r = comm.rank;
+        const int nchan = levels + 1;
+        auto align = [](size_t v) { return (v + 255) / 256 * 256; };
+        p2p.chan.assign(nchan, ChanHost());
+        size_t off = align((size_t)nchan * P2P_MAXW * sizeof(unsigned long long));
+        for (int l = 0; l < levels - 1; ++l) {
+            if (!L[l].sp.dist) continue;
+            p2p.chan[l].used = true;
+            p2p.chan[l].rows = L[l].sp.n_ghost;
+            if (!L[l + 1].sp.dist) {
+                p2p.gather_level = l + 1;
+                p2p.chan[levels].used = true;
+                p2p.chan[levels].rows = L[l].nc_global;
+            }
+        }
+        for (auto& c : p2p.chan) {
+            if (!c.used) continue;
+            for (int par = 0; par < 2; ++par) {
+                c.buf_off[par] = off;
+                off += align((size_t)std::max<long long>(c.rows, 1) * m * sizeof(TV));
+            }
+        }
+        p2p.block_bytes = off;
+        int ok = 1;
+        cudaIpcMemHandle_t mine;
+        std::memset(&mine, 0, sizeof(mine));
+        if (cudaMalloc(&p2p.block, p2p.block_bytes) != cudaSuccess) {
+            p2p.block = nullptr;
+            ok = 0;
+        } else {
+            MGB_CUDA(cudaMemset(p2p.block, 0, p2p.block_bytes));
+            if (cudaIpcGetMemHandle(&mine, p2p.block) != cudaSuccess) ok = 0;
+        }
+        cudaGetLastError();
+        // table: handle | ok | per channel {buf_off[2], recv_off[w]}
+        const size_t per_chan = 2 + (size_t)w;
+        std::vector<long long> tab(8 + 1 + per_chan * nchan, 0);
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+        std::memcpy(tab.data(), &mine, 64);
+        tab[8] = ok;
+        for (int c = 0; c < nchan; ++c) {
+            long long* t = tab.data() + 9 + per_chan * c;
+            t[0] = (long long)p2p.chan[c].buf_off[0];
+            t[1] = (long long)p2p.chan[c].buf_off[1];
+            if (c < levels && p2p.chan[c].used)
+                for (int q = 0; q < w; ++q) t[2 + q] = L[c].sp.recv_off[q];
+        }
+        std::vector<unsigned char> allb;
+        nccl_allgather_bytes(tab.data(), tab.size() * sizeof(long long), allb);
+        const long long* all = reinterpret_cast<const long long*>(allb.data());
+        auto T = [&](int q) { return all + (size_t)q * tab.size(); };
+        for (int q = 0; q < w; ++q) ok = ok && (int)T(q)[8];
+        p2p.peer.assign(w, nullptr);
+        if (ok) {
+            p2p.peer[r] = p2p.block;
+            for (int q = 0; q < w && ok; ++q) {
+                if (q == r) continue;
+                cudaIpcMemHandle_t hq;
+                std::memcpy(&hq, T(q), 64);
+                void* ptr = nullptr;
+                if (cudaIpcOpenMemHandle(&ptr, hq, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    ok = 0;
+                    cudaGetLastError();
+                } else {
+                    p2p.peer[q] = static_cast<unsigned char*>(ptr);
+                }
+            }
+        }
+        // every rank must reach the same verdict (and nobody may publish before all blocks are zeroed)
+        {
+            int* dflag = dev_alloc<int>(1);
+            MGB_CUDA(cudaMemcpyAsync(dflag, &ok, sizeof(int), cudaMemcpyHostToDevice, ctx.stream));
+            MGB_NCCL(nccl().AllReduce(dflag, dflag, 1, ncclInt32, ncclMin, comm.comm, ctx.stream));
+            MGB_CUDA(cudaMemcpyAsync(&ok, dflag, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+            ctx.sync();
+            dev_free(dflag);
+        }
+        if (!ok) {
+            p2p_release();
+            return;
+        }
+        for (int c = 0; c < nchan; ++c) {
+            ChanHost& ch = p2p.chan[c];
+            if (!ch.used) continue;
+            ChanDev<TV> cd;
+            std::memset(static_cast<void*>(&cd), 0, sizeof(cd));
+            cd.world = w;
+            cd.rank = r;
+            const bool gather = (c == levels);
+            const Level<TV>& lg = gather ? L[p2p.gather_level - 1] : L[c];
+            for (int par = 0; par < 2; ++par) cd.rbuf[par] = reinterpret_cast<const TV*>(p2p.block + ch.buf_off[par]);
+            cd.send_off[0] = 0;
+            for (int q = 0; q < w; ++q) {
+                const long long* tq = T(q) + 9 + per_chan * c;
+                const long long land = gather ? lg.coarse_row_offsets[r] : tq[2 + r];
+                for (int par = 0; par < 2; ++par)
+                    cd.dst[par][q] = reinterpret_cast<TV*>(p2p.peer[q] + tq[par]) + land * m;
+                cd.flag_dst[q] = reinterpret_cast<unsigned long long*>(p2p.peer[q]) + (size_t)c * P2P_MAXW + r;
+                cd.flag_src[q] = reinterpret_cast<const unsigned long long*>(p2p.block) + (size_t)c * P2P_MAXW + q;
+                if (gather) {
+                    cd.send_off[q + 1] = 0;
+                    cd.recv_off[q] = (int)lg.coarse_row_offsets[q];
+                    cd.recv_cnt[q] = (int)(lg.coarse_row_offsets[q + 1] - lg.coarse_row_offsets[q]);
+                } else {
+                    cd.send_off[q + 1] = cd.send_off[q] + lg.sp.send_cnt[q];
+                    cd.recv_off[q] = lg.sp.recv_off[q];
+                    cd.recv_cnt[q] = lg.sp.recv_cnt[q];
+                }
+            }
+            MGB_CUDA(cudaMalloc(&ch.dev, sizeof(cd)));
+            MGB_CUDA(cudaMemcpy(ch.dev, &cd, sizeof(cd), cudaMemcpyHostToDevice));
+        }
+        p2p.epoch = dev_alloc<unsigned long long>(nchan);
+        p2p.ticket = dev_alloc<unsigned>(nchan);
+        MGB_CUDA(cudaMemset(p2p.epoch, 0, nchan * sizeof(unsigned long long)));
+        MGB_CUDA(cudaMemset(p2p.ticket, 0, nchan * sizeof(unsigned)));
+        p2p.on = true;
     }
     static TV to_tv(zc a) { return VT<TV>::make(a.real(), a.imag()); }
 
@@ -731,7 +909,7 @@ struct Hierarchy : HierarchyBase {
     void jac_gmres(int l, const TV* r, TV* x, int inner) {
         Level<TV>& lv = L[l];
         FgmresMem<TV>& mem = lv.memRelax;
-        if (mem.inner != inner) alloc_fgmres(mem, (size_t)lv.n * m, inner);
+        if (mem.inner != inner) alloc_fgmres(mem, (size_t)lv.nalloc * m, inner, vec_pad(l));
         PrecFn mm = [&, this](const TV* v) -> TV* {
             // y = D .* v  (0 + d*v is exact)
             Launch La(ctx, K_DIAG, l + 1, (2.0 * m + 1.0) * lv.n * sizeof(TV));
@@ -744,8 +922,8 @@ struct Hierarchy : HierarchyBase {
 
     // cycle from the finest level, replayed from a CUDA graph when the cycle has no host read-backs
     TV* cycle_fine(const TV* b, TV* x, TV* scratch, bool xzero, char ctype) {
-        const bool can = ctx.use_graphs && !ctx.profiling && relax_kind == 0 && ctype != 'K' && !comm.active() &&
-                         levels > 1;
+        const bool can = ctx.use_graphs && !ctx.profiling && relax_kind == 0 && ctype != 'K' &&
+                         (!comm.active() || p2p.on) && levels > 1;
         if (!can) return cycle(0, b, x, scratch, xzero, ctype);
         const auto key = std::make_tuple(b, x, scratch, xzero, ctype);
         auto it = graphs.find(key);
@@ -953,7 +1131,7 @@ struct Hierarchy : HierarchyBase {
             gram_counter = dev_alloc<unsigned>(1);
             MGB_CUDA(cudaMemset(gram_counter, 0, sizeof(unsigned)));
         }
-        if (!kq) kq = dev_alloc<TV>(nma);
+        if (!kq) kq = vec_alloc<TV>(nma, vec_pad(0), ctx.stream);
         const Csr<TV>& A = krylov_A();
         const TV* B = lv.b;
         if (norm(nm, B) == 0.0) {

@@ -296,6 +296,11 @@ class DeviceHierarchy:
         return dict(in_use=bool(out[0]), row_relative=bool(out[1]), patterns=int(out[2]), entries=int(out[3]),
                     d_folded=bool(out[4]))
 
+    def dist_info(self):
+        out = np.zeros(4, dtype=np.int64)
+        _check(lib().mgb200_dist_info(self.h, _ptr(out)))
+        return dict(world=int(out[0]), rank=int(out[1]), p2p=bool(out[2]), dist_levels=int(out[3]))
+
     def set_option(self, key: str, value: int):
         _check(lib().mgb200_set_option(self.h, ctypes.c_char_p(key.encode()), ctypes.c_int64(int(value))))
 
