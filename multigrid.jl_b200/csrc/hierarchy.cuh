@@ -114,7 +114,6 @@ struct Context {
     int smem_budget = 56 * 1024;
     int use_patterns = 1;          // 0: always stream CSR (MGB200_PATTERNS / mgb200_set_option)
     int use_graphs = 1;            // 0: never replay cycles from CUDA graphs
-    int pat_rpt = 1;               // rows per thread of the stencil-dictionary kernel (1, 2 or 4)
     int max_smem_optin = 0;
     int sm_count = 148;
     bool profiling = false;
@@ -138,8 +137,6 @@ struct Context {
         smem_budget = env_int("MGB200_SMEM_BUDGET", 56 * 1024);
         use_patterns = env_int("MGB200_PATTERNS", 1);
         use_graphs = env_int("MGB200_GRAPHS", 1);
-        pat_rpt = env_int("MGB200_PAT_RPT", 1);
-        if (pat_rpt != 1 && pat_rpt != 2 && pat_rpt != 4) pat_rpt = 1;
     }
     void destroy() {
         if (!stream) return;

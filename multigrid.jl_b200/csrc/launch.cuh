@@ -102,15 +102,13 @@ static double vec_bytes(const Csr<TA>& M, int mode, int m, bool d_from_dict) {
 }
 
 // stencil-dictionary kernel (pattern.cuh), one right-hand side
-template <typename TA, typename TV, int RPT>
-static void launch_pattern_rpt(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d,
-                               const TV* dpat, TV* y) {
+template <typename TA, typename TV>
+static void launch_pattern_mode(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d,
+                                const TV* dpat, TV* y) {
     const PatDict<TA>& D = M.pat;
-    const int nt = D.nthreads;
-    const int grid = cdiv(M.n_rows, (long long)D.stride * RPT) * D.nchunk;
-#define MGB_PL(MODE, RR, DP)                                                                                \
-    pat_kernel<TA, TV, MODE, RR, DP, RPT><<<grid, nt, 0, ctx.stream>>>(M.n_rows, D.stride, D.nchunk, D.pid, D.c0, \
-                                                                        D.hdr, D.ent, dpat, x, b, d, y)
+    const int nt = 256, grid = cdiv(M.n_rows, nt);
+#define MGB_PL(MODE, RR, DP) \
+    pat_kernel<TA, TV, MODE, RR, DP><<<grid, nt, 0, ctx.stream>>>(M.n_rows, D.pid, D.c0, D.pat_off, D.ent, dpat, x, b, d, y)
 #define MGB_PCASE(MODE)                                     \
     case MODE:                                              \
         if (D.rowrel) {                                     \
@@ -130,18 +128,6 @@ static void launch_pattern_rpt(Context& ctx, const Csr<TA>& M, int mode, const T
 #undef MGB_PCASE
 #undef MGB_PL
     MGB_LAUNCH_CHECK();
-}
-template <typename TA, typename TV>
-static void launch_pattern_mode(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d,
-                                const TV* dpat, TV* y) {
-    // rows per thread: more rows amortise the dictionary loads, fewer keep small grids wide
-    int rpt = ctx.pat_rpt;
-    while (rpt > 1 && (long long)M.n_rows < (long long)ctx.sm_count * 2 * M.pat.stride * rpt) rpt /= 2;
-    switch (rpt) {
-        case 1: launch_pattern_rpt<TA, TV, 1>(ctx, M, mode, x, b, d, dpat, y); break;
-        case 2: launch_pattern_rpt<TA, TV, 2>(ctx, M, mode, x, b, d, dpat, y); break;
-        default: launch_pattern_rpt<TA, TV, 4>(ctx, M, mode, x, b, d, dpat, y); break;
-    }
 }
 
 // y = op(M x): the one entry point the cycle uses for A, P and R.

@@ -394,10 +394,6 @@ int mgb200_set_option(mgb200_handle h, const char* key, int64_t value) {
         const std::string k(key);
         if (k == "patterns") H->ctx.use_patterns = (int)value;
         else if (k == "graphs") H->ctx.use_graphs = (int)value;
-        else if (k == "pattern_rows_per_thread") {
-            MGB_CHECK(value == 1 || value == 2 || value == 4, "pattern_rows_per_thread must be 1, 2 or 4");
-            H->ctx.pat_rpt = (int)value;
-        }
         else if (k == "smem_budget") H->ctx.smem_budget = (int)value;
         else throw Error(-1, "mgb200_set_option: unknown key " + k);
         H->invalidate_graphs();

@@ -27,6 +27,13 @@
 namespace mgb200 {
 
 constexpr int P2P_MAXW = 16;
+constexpr int P2P_TRACE_ROWS = 1024;   // MGB200_P2P_TRACE=1: per exchange {start, published, peers arrived, end} of CTA 0
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 // device-resident description of one channel
 template <typename TV>
@@ -92,9 +99,13 @@ __device__ __forceinline__ void p2p_wait(const ChanDev<TV>* cd, unsigned long lo
 template <typename TV>
 __global__ void p2p_halo_kernel(const ChanDev<TV>* __restrict__ cd, TV* __restrict__ v,
                                 const int* __restrict__ send_idx, int n_send, long long n_ghost, long long n_lo,
-                                long long n_owned, int m, unsigned long long* epoch, unsigned* ticket) {
+                                long long n_owned, int m, unsigned long long* epoch, unsigned* ticket,
+                                unsigned long long* trace) {
     const unsigned long long e = *epoch + 1;
     const int par = (int)(e & 1);
+    const bool tr = trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    unsigned long long* trow = trace + (e % P2P_TRACE_ROWS) * 4;
+    if (tr) trow[0] = globaltimer_ns();
     const long long total = (long long)n_send * m;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
          t += (long long)gridDim.x * blockDim.x) {
@@ -104,7 +115,9 @@ __global__ void p2p_halo_kernel(const ChanDev<TV>* __restrict__ cd, TV* __restri
         cd->dst[par][q][(long long)(i - cd->send_off[q]) * m + j] = v[(long long)send_idx[i] * m + j];
     }
     p2p_publish(cd, e, epoch, ticket, false);
+    if (tr) trow[1] = globaltimer_ns();
     p2p_wait(cd, e);
+    if (tr) trow[2] = globaltimer_ns();
     const TV* rb = cd->rbuf[par];
     const long long tot2 = n_ghost * m;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < tot2;
@@ -114,6 +127,7 @@ __global__ void p2p_halo_kernel(const ChanDev<TV>* __restrict__ cd, TV* __restri
         const long long pos = g < n_lo ? g - n_lo : n_owned + (g - n_lo);
         v[pos * m + j] = ld_cv(rb + t);
     }
+    if (tr) trow[3] = globaltimer_ns();
 }
 
 // Gather of a replicated vector in one kernel: my piece v[off .. off+cnt) (element units) goes to the same place
@@ -158,6 +172,7 @@ struct P2P {
     unsigned long long* epoch = nullptr;     // per channel, device
     unsigned* ticket = nullptr;              // per channel, device
     int gather_level = -1;                   // level index (0-based) of the first replicated level
+    unsigned long long* trace = nullptr;     // per halo channel P2P_TRACE_ROWS x 4 timestamps (MGB200_P2P_TRACE=1)
 };
 
 }  // namespace mgb200

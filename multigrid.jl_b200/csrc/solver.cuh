@@ -559,7 +559,8 @@ struct Hierarchy : HierarchyBase {
             const long long work = std::max<long long>((long long)sp.n_send, sp.n_ghost) * m;
             const int g = (int)std::max<long long>(1, std::min<long long>((work + 1023) / 1024, 64));
             p2p_halo_kernel<TV><<<g, 256, 0, ctx.stream>>>(cd, v, sp.d_send_idx, sp.n_send, sp.n_ghost, sp.n_lo,
-                                                            sp.n_owned, m, p2p.epoch + l, p2p.ticket + l);
+                                                            sp.n_owned, m, p2p.epoch + l, p2p.ticket + l,
+                                                            p2p.trace ? p2p.trace + (size_t)l * P2P_TRACE_ROWS * 4 : nullptr);
             MGB_LAUNCH_CHECK();
             return;
         }
@@ -605,6 +606,7 @@ struct Hierarchy : HierarchyBase {
         if (!p2p.block && p2p.peer.empty()) return;
         cudaSetDevice(ctx.device);
         if (ctx.stream) cudaStreamSynchronize(ctx.stream);
+        p2p_trace_report();
         for (int q = 0; q < (int)p2p.peer.size(); ++q)
             if (q != comm.rank && p2p.peer[q]) cudaIpcCloseMemHandle(p2p.peer[q]);
         p2p.peer.clear();
@@ -622,6 +624,30 @@ struct Hierarchy : HierarchyBase {
         dev_free(p2p.ticket);
         p2p.on = false;
         p2p.gather_level = -1;
+    }
+    // MGB200_P2P_TRACE=1: phase times of the last exchanges of every halo channel, printed at teardown
+    void p2p_trace_report() {
+        if (!p2p.trace) return;
+        const int nchan = levels + 1;
+        std::vector<unsigned long long> h((size_t)nchan * P2P_TRACE_ROWS * 4);
+        cudaMemcpy(h.data(), p2p.trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+        for (int l = 0; l < levels; ++l) {
+            double put = 0, wait = 0, unpack = 0;
+            int cnt = 0;
+            for (int k = 0; k < P2P_TRACE_ROWS; ++k) {
+                const unsigned long long* t = h.data() + ((size_t)l * P2P_TRACE_ROWS + k) * 4;
+                if (!t[0] || !t[3] || t[3] < t[0]) continue;
+                put += (double)(t[1] - t[0]);
+                wait += (double)(t[2] - t[1]);
+                unpack += (double)(t[3] - t[2]);
+                ++cnt;
+            }
+            if (cnt)
+                std::fprintf(stderr, "[mgb200 p2p trace] rank %d level %d: %d exchanges, put+publish %.2f us, wait %.2f us, "
+                             "unpack %.2f us (CTA 0)\n", comm.rank, l + 1, cnt, put / cnt * 1e-3, wait / cnt * 1e-3,
+                             unpack / cnt * 1e-3);
+        }
+        dev_free(p2p.trace);
     }
     void nccl_allgather_bytes(const void* mine, size_t bytes, std::vector<unsigned char>& all) {
         const int w = comm.world, r = comm.rank;
@@ -748,6 +774,10 @@ struct Hierarchy : HierarchyBase {
             }
             MGB_CUDA(cudaMalloc(&ch.dev, sizeof(cd)));
             MGB_CUDA(cudaMemcpy(ch.dev, &cd, sizeof(cd), cudaMemcpyHostToDevice));
+        }
+        if (env_int("MGB200_P2P_TRACE", 0)) {
+            p2p.trace = dev_alloc<unsigned long long>((size_t)nchan * P2P_TRACE_ROWS * 4);
+            MGB_CUDA(cudaMemset(p2p.trace, 0, (size_t)nchan * P2P_TRACE_ROWS * 4 * sizeof(unsigned long long)));
         }
         p2p.epoch = dev_alloc<unsigned long long>(nchan);
         p2p.ticket = dev_alloc<unsigned>(nchan);

@@ -1,0 +1,856 @@
+// Micro-benchmark behind the design of the stencil-dictionary kernel (csrc/pattern.cuh): the fused Jacobi sweep
+// x' = x + d.*(b - A x) of a 7-point (257^3) and a 27-point (129^3) stencil matrix in dictionary form, with the
+// dictionary read through different paths.  All variants must produce bit-identical output.
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -lineinfo -o gpurun_out/microbench_pat tools/microbench_pat.cu
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+#include <vector>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e_), __LINE__); exit(1); } } while (0)
+
+struct __align__(16) Ent { double v; int delta; int pad; };
+
+constexpr int MAXE = 384, MAXP = 32;
+struct Params { Ent e[MAXE]; int hdr[MAXP]; double dp[MAXP]; };
+
+__device__ __forceinline__ Ent ldg_ent(const Ent* p) {
+    const int4 q = __ldg(reinterpret_cast<const int4*>(p));
+    Ent e; e.v = __hiloint2double(q.y, q.x); e.delta = q.z; e.pad = 0; return e;
+}
+
+// V0: dictionary in global memory (LDG.128 per entry), one row per thread
+__global__ void __launch_bounds__(256) k_global(int n, const uint16_t* __restrict__ pid, const int* __restrict__ hdr,
+                                                const Ent* __restrict__ ent, const double* __restrict__ dp,
+                                                const double* __restrict__ x, const double* __restrict__ b,
+                                                double* __restrict__ y) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    const int p = pid[row];
+    const int h = __ldg(hdr + p), k0 = h & 0xFFFFF, k1 = k0 + (h >> 20);
+    const double bv = b[row], xv = x[row], dv = __ldg(dp + p);
+    double acc = 0.0;
+#pragma unroll 4
+    for (int k = k0; k < k1; ++k) {
+        const Ent e = ldg_ent(ent + k);
+        acc = acc + e.v * __ldg(x + row + e.delta);
+    }
+    y[row] = xv + dv * (bv - acc);
+}
+
+// V1: dictionary staged in shared memory by every CTA (LDS.128 broadcast)
+__global__ void __launch_bounds__(256) k_smem(int n, int nent, int npat, const uint16_t* __restrict__ pid,
+                                              const int* __restrict__ hdr, const Ent* __restrict__ ent,
+                                              const double* __restrict__ dp, const double* __restrict__ x,
+                                              const double* __restrict__ b, double* __restrict__ y) {
+    __shared__ Ent se[MAXE];
+    __shared__ int sh[MAXP];
+    __shared__ double sd[MAXP];
+    for (int i = threadIdx.x; i < nent; i += blockDim.x) se[i] = ent[i];
+    for (int i = threadIdx.x; i < npat; i += blockDim.x) { sh[i] = hdr[i]; sd[i] = dp[i]; }
+    __syncthreads();
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    const int p = pid[row];
+    const int h = sh[p], k0 = h & 0xFFFFF, k1 = k0 + (h >> 20);
+    const double bv = b[row], xv = x[row], dv = sd[p];
+    double acc = 0.0;
+#pragma unroll 4
+    for (int k = k0; k < k1; ++k) {
+        const Ent e = se[k];
+        acc = acc + e.v * __ldg(x + row + e.delta);
+    }
+    y[row] = xv + dv * (bv - acc);
+}
+
+// V2: like V1 with split arrays (LDS.64 value + LDS.32 offset)
+__global__ void __launch_bounds__(256) k_smem_split(int n, int nent, int npat, const uint16_t* __restrict__ pid,
+                                                    const int* __restrict__ hdr, const Ent* __restrict__ ent,
+                                                    const double* __restrict__ dp, const double* __restrict__ x,
+                                                    const double* __restrict__ b, double* __restrict__ y) {
+    __shared__ double sv[MAXE];
+    __shared__ int sdl[MAXE];
+    __shared__ int sh[MAXP];
+    __shared__ double sd[MAXP];
+    for (int i = threadIdx.x; i < nent; i += blockDim.x) { sv[i] = ent[i].v; sdl[i] = ent[i].delta; }
+    for (int i = threadIdx.x; i < npat; i += blockDim.x) { sh[i] = hdr[i]; sd[i] = dp[i]; }
+    __syncthreads();
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    const int p = pid[row];
+    const int h = sh[p], k0 = h & 0xFFFFF, k1 = k0 + (h >> 20);
+    const double bv = b[row], xv = x[row], dv = sd[p];
+    double acc = 0.0;
+#pragma unroll 4
+    for (int k = k0; k < k1; ++k) acc = acc + sv[k] * __ldg(x + row + sdl[k]);
+    y[row] = xv + dv * (bv - acc);
+}
+
+// V3: dictionary in the kernel parameters (constant bank, LDC)
+__global__ void __launch_bounds__(256) k_param(const __grid_constant__ Params P, int n, const uint16_t* __restrict__ pid,
+                                               const double* __restrict__ x, const double* __restrict__ b,
+                                               double* __restrict__ y) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    const int p = pid[row];
+    const int h = P.hdr[p], k0 = h & 0xFFFFF, k1 = k0 + (h >> 20);
+    const double bv = b[row], xv = x[row], dv = P.dp[p];
+    double acc = 0.0;
+#pragma unroll 4
+    for (int k = k0; k < k1; ++k) acc = acc + P.e[k].v * __ldg(x + row + P.e[k].delta);
+    y[row] = xv + dv * (bv - acc);
+}
+
+// V4: warp-uniform fast path: when all lanes share the pattern, lane k holds entry k and the warp broadcasts it
+// with shuffles (no per-lane dictionary load at all); mixed warps fall back to the global dictionary
+__global__ void __launch_bounds__(256) k_shfl(int n, const uint16_t* __restrict__ pid, const int* __restrict__ hdr,
+                                              const Ent* __restrict__ ent, const double* __restrict__ dp,
+                                              const double* __restrict__ x, const double* __restrict__ b,
+                                              double* __restrict__ y) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = row < n;
+    const int lane = threadIdx.x & 31;
+    const int p = ok ? pid[row] : 0xFFFF;
+    const int p0 = __shfl_sync(0xffffffffu, p, 0);
+    const bool uni = __all_sync(0xffffffffu, p == p0);
+    if (uni && p0 != 0xFFFF) {
+        const int h = __ldg(hdr + p0), k0 = h & 0xFFFFF, len = h >> 20;
+        const double bv = b[row], xv = x[row], dv = __ldg(dp + p0);
+        double acc = 0.0;
+        for (int c = 0; c < len; c += 32) {
+            Ent mine; mine.v = 0.0; mine.delta = 0;
+            if (c + lane < len) mine = ldg_ent(ent + k0 + c + lane);
+            const int cnt = min(32, len - c);
+            for (int k = 0; k < cnt; ++k) {
+                const double v = __shfl_sync(0xffffffffu, mine.v, k);
+                const int dl = __shfl_sync(0xffffffffu, mine.delta, k);
+                acc = acc + v * __ldg(x + row + dl);
+            }
+        }
+        y[row] = xv + dv * (bv - acc);
+        return;
+    }
+    if (!ok) return;
+    const int h = __ldg(hdr + p), k0 = h & 0xFFFFF, k1 = k0 + (h >> 20);
+    const double bv = b[row], xv = x[row], dv = __ldg(dp + p);
+    double acc = 0.0;
+#pragma unroll 4
+    for (int k = k0; k < k1; ++k) {
+        const Ent e = ldg_ent(ent + k);
+        acc = acc + e.v * __ldg(x + row + e.delta);
+    }
+    y[row] = xv + dv * (bv - acc);
+}
+
+// V5: constant-memory dictionary
+__constant__ Params cP;
+__global__ void __launch_bounds__(256) k_const(int n, const uint16_t* __restrict__ pid, const double* __restrict__ x,
+                                               const double* __restrict__ b, double* __restrict__ y) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    const int p = pid[row];
+    const int h = cP.hdr[p], k0 = h & 0xFFFFF, k1 = k0 + (h >> 20);
+    const double bv = b[row], xv = x[row], dv = cP.dp[p];
+    double acc = 0.0;
+#pragma unroll 4
+    for (int k = k0; k < k1; ++k) acc = acc + cP.e[k].v * __ldg(x + row + cP.e[k].delta);
+    y[row] = xv + dv * (bv - acc);
+}
+
+
+// V7: x windows staged in shared memory with TMA bulk copies, dictionary in the kernel parameters.
+// The column offsets of the whole dictionary are clustered into windows [lo, hi]; a CTA of 256 consecutive rows
+// needs x[row0 + lo .. row0 + 255 + hi] of every window: one bulk copy each, issued by one thread, no registers.
+struct Win { int lo_even, len, sbase; };
+struct ParamsT { Ent e[MAXE]; int hdr[MAXP]; double dp[MAXP]; Win w[16]; int nwin, centre, total; };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const uint32_t a = smem_u32(bar);
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+__global__ void __launch_bounds__(256) k_tma(const __grid_constant__ ParamsT P, int n, int vlo, int vhi,
+                                             const uint16_t* __restrict__ pid, const double* __restrict__ x,
+                                             const double* __restrict__ b, double* __restrict__ y) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    double* sx = reinterpret_cast<double*>(smem_raw + 16);
+    const int t = threadIdx.x;
+    const int row0 = blockIdx.x * 256;
+    const int row = row0 + t;
+    if (t == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        uint32_t bytes = 0;
+        for (int g = 0; g < P.nwin; ++g) {
+            const int s0 = row0 + P.w[g].lo_even, s = max(s0, vlo), e = min(s0 + P.w[g].len, vhi);
+            if (e > s) bytes += (uint32_t)(e - s) * 8u;
+        }
+        mbar_expect_tx(bar, bytes);
+        for (int g = 0; g < P.nwin; ++g) {
+            const int s0 = row0 + P.w[g].lo_even, s = max(s0, vlo), e = min(s0 + P.w[g].len, vhi);
+            if (e > s) bulk_g2s(sx + P.w[g].sbase + (s - s0), x + s, (uint32_t)(e - s) * 8u, bar);
+        }
+    }
+    __syncthreads();   // barrier initialised before anybody waits on it
+    int p = 0;
+    double bv = 0.0;
+    if (row < n) {
+        p = pid[row];
+        bv = b[row];
+    }
+    const int h = P.hdr[p], k0 = h & 0xFFFFF, k1 = k0 + (h >> 20);
+    const double dv = P.dp[p];
+    mbar_wait(bar, 0);
+    if (row >= n) return;
+    double acc = 0.0;
+    const double* sxt = sx + t;
+#pragma unroll 4
+    for (int k = k0; k < k1; ++k) acc = acc + P.e[k].v * sxt[P.e[k].delta];
+    y[row] = sxt[P.centre] + dv * (bv - acc);
+}
+
+
+// V8: persistent CTAs, multi-stage TMA pipeline over row tiles: while the CTA computes tile i the copies of
+// tiles i+1 .. i+STAGES-1 (x windows, b tile, pid tile) are already in flight.  Nothing waits on a DRAM round
+// trip except the first tile of every CTA.
+template <int STAGES>
+__global__ void __launch_bounds__(256) k_tma_pipe(const __grid_constant__ ParamsT P, int n, int ntiles, int vlo, int vhi,
+                                                  const uint16_t* __restrict__ pid, const double* __restrict__ x,
+                                                  const double* __restrict__ b, double* __restrict__ y) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+    const int stage_bytes = (P.total + 256) * 8 + 512;
+    unsigned char* stage0 = smem_raw + 64;
+    const int t = threadIdx.x;
+    if (t == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(full + s, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    auto issue = [&](int tile, int s) {
+        double* sx = reinterpret_cast<double*>(stage0 + (size_t)s * stage_bytes);
+        double* sb = sx + P.total;
+        uint16_t* sp = reinterpret_cast<uint16_t*>(sb + 256);
+        const int row0 = tile * 256;
+        uint32_t bytes = 0;
+        for (int g = 0; g < P.nwin; ++g) {
+            const int s0 = row0 + P.w[g].lo_even, a = max(s0, vlo), e = min(s0 + P.w[g].len, vhi);
+            if (e > a) bytes += (uint32_t)(e - a) * 8u;
+        }
+        const int be = min(row0 + 256, vhi);
+        const int pe = min(row0 + 256, (n + 7) & ~7);
+        bytes += (uint32_t)(be - row0) * 8u + (uint32_t)(pe - row0) * 2u;
+        mbar_expect_tx(full + s, bytes);
+        for (int g = 0; g < P.nwin; ++g) {
+            const int s0 = row0 + P.w[g].lo_even, a = max(s0, vlo), e = min(s0 + P.w[g].len, vhi);
+            if (e > a) bulk_g2s(sx + P.w[g].sbase + (a - s0), x + a, (uint32_t)(e - a) * 8u, full + s);
+        }
+        bulk_g2s(sb, b + row0, (uint32_t)(be - row0) * 8u, full + s);
+        bulk_g2s(sp, pid + row0, (uint32_t)(pe - row0) * 2u, full + s);
+    };
+    if (t == 0) {
+        for (int i = 0; i < STAGES - 1; ++i) {
+            const int tile = blockIdx.x + i * gridDim.x;
+            if (tile < ntiles) issue(tile, i);
+        }
+    }
+    int i = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+        const int s = i % STAGES;
+        if (t == 0) {
+            const int nt = tile + (STAGES - 1) * gridDim.x;
+            if (nt < ntiles) issue(nt, (i + STAGES - 1) % STAGES);
+        }
+        mbar_wait(full + s, (i / STAGES) & 1);
+        const double* sx = reinterpret_cast<const double*>(stage0 + (size_t)s * stage_bytes);
+        const double* sb = sx + P.total;
+        const uint16_t* sp = reinterpret_cast<const uint16_t*>(sb + 256);
+        const int row = tile * 256 + t;
+        if (row < n) {
+            const int p = sp[t];
+            const int h = P.hdr[p], k0 = h & 0xFFFFF, k1 = k0 + (h >> 20);
+            const double dv = P.dp[p], bv = sb[t];
+            const double* sxt = sx + t;
+            double acc = 0.0;
+#pragma unroll 4
+            for (int k = k0; k < k1; ++k) acc = acc + P.e[k].v * sxt[P.e[k].delta];
+            y[row] = sxt[P.centre] + dv * (bv - acc);
+        }
+        __syncthreads();
+    }
+}
+
+
+// V9: TMA-staged x windows for a tile of 256*RPT rows, dictionary in shared memory, every thread owns RPT rows
+// that are 256 apart: one dictionary load (LDS.128 broadcast) serves RPT gathers (LDS.64) when the rows share the
+// pattern; threads with mixed patterns walk their rows one by one.
+template <int RPT>
+__global__ void __launch_bounds__(256) k_tma_rpt(const __grid_constant__ ParamsT P, int n, int nent, int npat, int vlo, int vhi,
+                                                 const uint16_t* __restrict__ pid, const Ent* __restrict__ gent,
+                                                 const double* __restrict__ x, const double* __restrict__ b,
+                                                 double* __restrict__ y) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    Ent* se = reinterpret_cast<Ent*>(smem_raw + 16);
+    double* sx = reinterpret_cast<double*>(smem_raw + 16 + MAXE * sizeof(Ent));
+    const int wtotal = P.total + P.nwin * 256 * (RPT - 1);      // every window is 256*(RPT-1) longer than in P
+    double* sb = sx + wtotal;
+    uint16_t* sp = reinterpret_cast<uint16_t*>(sb + 256 * RPT);
+    const int t = threadIdx.x;
+    const int row0 = blockIdx.x * 256 * RPT;
+    if (t == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        uint32_t bytes = 0;
+        for (int g = 0; g < P.nwin; ++g) {
+            const int s0 = row0 + P.w[g].lo_even, a = max(s0, vlo), e = min(s0 + P.w[g].len + 256 * (RPT - 1), vhi);
+            if (e > a) bytes += (uint32_t)(e - a) * 8u;
+        }
+        const int be = min(row0 + 256 * RPT, vhi), pe = min(row0 + 256 * RPT, (n + 7) & ~7);
+        bytes += (uint32_t)(be - row0) * 8u + (uint32_t)(pe - row0) * 2u;
+        mbar_expect_tx(bar, bytes);
+        for (int g = 0; g < P.nwin; ++g) {
+            const int s0 = row0 + P.w[g].lo_even, a = max(s0, vlo), e = min(s0 + P.w[g].len + 256 * (RPT - 1), vhi);
+            if (e > a) bulk_g2s(sx + P.w[g].sbase + g * 256 * (RPT - 1) + (a - s0), x + a, (uint32_t)(e - a) * 8u, bar);
+        }
+        bulk_g2s(sb, b + row0, (uint32_t)(be - row0) * 8u, bar);
+        bulk_g2s(sp, pid + row0, (uint32_t)(pe - row0) * 2u, bar);
+    }
+    // dictionary: entry offsets are re-based for the longer windows
+    for (int i = t; i < nent; i += 256) {
+        Ent e = gent[i];
+        int g = 0;
+        while (g + 1 < P.nwin && e.delta >= P.w[g + 1].sbase) ++g;
+        e.delta += g * 256 * (RPT - 1);
+        se[i] = e;
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+    int p[RPT], k0[RPT], len[RPT];
+    bool uni = true;
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+        const int row = row0 + t + 256 * j;
+        p[j] = row < n ? sp[t + 256 * j] : 0xFFFF;
+        uni = uni && (p[j] == p[0]);
+    }
+    int gc = 0;
+    while (gc + 1 < P.nwin && P.centre + P.w[gc + 1].lo_even >= P.w[gc + 1].sbase) ++gc;   // window of delta 0
+    double acc[RPT];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) acc[j] = 0.0;
+    const double* sxt = sx + t;
+    if (uni && p[0] != 0xFFFF) {
+        const int h = P.hdr[p[0]], kk0 = h & 0xFFFFF, kk1 = kk0 + (h >> 20);
+#pragma unroll 2
+        for (int k = kk0; k < kk1; ++k) {
+            const Ent e = se[k];
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) acc[j] = acc[j] + e.v * sxt[e.delta + 256 * j];
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            if (p[j] == 0xFFFF) continue;
+            const int h = P.hdr[p[j]], kk0 = h & 0xFFFFF, kk1 = kk0 + (h >> 20);
+            for (int k = kk0; k < kk1; ++k) {
+                const Ent e = se[k];
+                acc[j] = acc[j] + e.v * sxt[e.delta + 256 * j];
+            }
+        }
+    }
+    const int coff = P.centre + gc * 256 * (RPT - 1);
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+        const int row = row0 + t + 256 * j;
+        if (row < n) y[row] = sxt[coff + 256 * j] + P.dp[p[j]] * (sb[t + 256 * j] - acc[j]);
+    }
+}
+
+
+// V10: persistent CTAs (NT threads, tile = NT rows), STAGES-deep TMA pipeline, dictionary in shared memory.
+template <int STAGES, int NT>
+__global__ void __launch_bounds__(NT) k_pipe_smem(const __grid_constant__ ParamsT P, int n, int nent, int ntiles, int vlo,
+                                                  int vhi, const uint16_t* __restrict__ pid, const Ent* __restrict__ gent,
+                                                  const double* __restrict__ x, const double* __restrict__ b,
+                                                  double* __restrict__ y) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+    Ent* se = reinterpret_cast<Ent*>(smem_raw + 64);
+    int* sh = reinterpret_cast<int*>(se + MAXE);
+    double* sd = reinterpret_cast<double*>(sh + MAXP);
+    unsigned char* stage0 = reinterpret_cast<unsigned char*>(sd + MAXP);
+    const int ext = NT - 256;                                   // every window is `ext` longer than in P
+    const int wtotal = P.total + P.nwin * ext;
+    const int stage_bytes = (wtotal + NT) * 8 + NT * 2;
+    const int t = threadIdx.x;
+    if (t == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(full + s, 1);
+        fence_mbar_init();
+    }
+    for (int i = t; i < nent; i += NT) {
+        Ent e = gent[i];
+        int g = 0;
+        while (g + 1 < P.nwin && e.delta >= P.w[g + 1].sbase) ++g;
+        e.delta += g * ext;
+        se[i] = e;
+    }
+    if (t < MAXP) { sh[t] = P.hdr[t]; sd[t] = P.dp[t]; }
+    int gc = 0;
+    while (gc + 1 < P.nwin && P.w[gc + 1].lo_even <= 0) ++gc;    // window that holds delta 0
+    const int coff = P.centre + gc * ext;
+    __syncthreads();
+    auto issue = [&](int tile, int s) {
+        double* sx = reinterpret_cast<double*>(stage0 + (size_t)s * stage_bytes);
+        double* sb = sx + wtotal;
+        uint16_t* sp = reinterpret_cast<uint16_t*>(sb + NT);
+        const int row0 = tile * NT;
+        uint32_t bytes = 0;
+        for (int g = 0; g < P.nwin; ++g) {
+            const int s0 = row0 + P.w[g].lo_even, a = max(s0, vlo), e = min(s0 + P.w[g].len + ext, vhi);
+            if (e > a) bytes += (uint32_t)(e - a) * 8u;
+        }
+        const int be = min(row0 + NT, vhi), pe = min(row0 + NT, (n + 7) & ~7);
+        bytes += (uint32_t)(be - row0) * 8u + (uint32_t)(pe - row0) * 2u;
+        mbar_expect_tx(full + s, bytes);
+        for (int g = 0; g < P.nwin; ++g) {
+            const int s0 = row0 + P.w[g].lo_even, a = max(s0, vlo), e = min(s0 + P.w[g].len + ext, vhi);
+            if (e > a) bulk_g2s(sx + P.w[g].sbase + g * ext + (a - s0), x + a, (uint32_t)(e - a) * 8u, full + s);
+        }
+        bulk_g2s(sb, b + row0, (uint32_t)(be - row0) * 8u, full + s);
+        bulk_g2s(sp, pid + row0, (uint32_t)(pe - row0) * 2u, full + s);
+    };
+    if (t == 0) {
+        for (int i = 0; i < STAGES - 1; ++i) {
+            const int tile = blockIdx.x + i * gridDim.x;
+            if (tile < ntiles) issue(tile, i);
+        }
+    }
+    int i = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+        const int s = i % STAGES;
+        if (t == 0) {
+            const int nt = tile + (STAGES - 1) * gridDim.x;
+            if (nt < ntiles) issue(nt, (i + STAGES - 1) % STAGES);
+        }
+        mbar_wait(full + s, (i / STAGES) & 1);
+        const double* sx = reinterpret_cast<const double*>(stage0 + (size_t)s * stage_bytes);
+        const double* sb = sx + wtotal;
+        const uint16_t* sp = reinterpret_cast<const uint16_t*>(sb + NT);
+        const int row = tile * NT + t;
+        if (row < n) {
+            const int p = sp[t];
+            const int h = sh[p], k0 = h & 0xFFFFF, k1 = k0 + (h >> 20);
+            const double dv = sd[p], bv = sb[t];
+            const double* sxt = sx + t;
+            double acc = 0.0;
+#pragma unroll 4
+            for (int k = k0; k < k1; ++k) {
+                const Ent e = se[k];
+                acc = acc + e.v * sxt[e.delta];
+            }
+            y[row] = sxt[coff] + dv * (bv - acc);
+        }
+        __syncthreads();
+    }
+}
+
+
+// V11: V10 + RPT rows per thread (rows t + NT*j of the tile): one dictionary load serves RPT gathers.
+// PW holds windows built for a tile of NT*RPT rows (offsets closer than a tile are merged into one window).
+template <int STAGES, int NT, int RPT>
+__global__ void __launch_bounds__(NT) k_pipe_rpt(const __grid_constant__ ParamsT P, int n, int nent, int ntiles, int vlo,
+                                                 int vhi, const uint16_t* __restrict__ pid, const Ent* __restrict__ gent,
+                                                 const double* __restrict__ x, const double* __restrict__ b,
+                                                 double* __restrict__ y) {
+    constexpr int TILE = NT * RPT;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+    Ent* se = reinterpret_cast<Ent*>(smem_raw + 64);
+    int* sh = reinterpret_cast<int*>(se + MAXE);
+    double* sd = reinterpret_cast<double*>(sh + MAXP);
+    unsigned char* stage0 = reinterpret_cast<unsigned char*>(sd + MAXP);
+    const int wtotal = P.total;
+    const int stage_bytes = (wtotal + TILE) * 8 + TILE * 2;
+    const int t = threadIdx.x;
+    if (t == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(full + s, 1);
+        fence_mbar_init();
+    }
+    for (int i = t; i < nent; i += NT) se[i] = gent[i];
+    if (t < MAXP) { sh[t] = P.hdr[t]; sd[t] = P.dp[t]; }
+    const int coff = P.centre;
+    __syncthreads();
+    auto issue = [&](int tile, int s) {
+        double* sx = reinterpret_cast<double*>(stage0 + (size_t)s * stage_bytes);
+        double* sb = sx + wtotal;
+        uint16_t* sp = reinterpret_cast<uint16_t*>(sb + TILE);
+        const int row0 = tile * TILE;
+        uint32_t bytes = 0;
+        for (int g = 0; g < P.nwin; ++g) {
+            const int s0 = row0 + P.w[g].lo_even, a = max(s0, vlo), e = min(s0 + P.w[g].len, vhi);
+            if (e > a) bytes += (uint32_t)(e - a) * 8u;
+        }
+        const int be = min(row0 + TILE, vhi), pe = min(row0 + TILE, (n + 7) & ~7);
+        bytes += (uint32_t)(be - row0) * 8u + (uint32_t)(pe - row0) * 2u;
+        mbar_expect_tx(full + s, bytes);
+        for (int g = 0; g < P.nwin; ++g) {
+            const int s0 = row0 + P.w[g].lo_even, a = max(s0, vlo), e = min(s0 + P.w[g].len, vhi);
+            if (e > a) bulk_g2s(sx + P.w[g].sbase + (a - s0), x + a, (uint32_t)(e - a) * 8u, full + s);
+        }
+        bulk_g2s(sb, b + row0, (uint32_t)(be - row0) * 8u, full + s);
+        bulk_g2s(sp, pid + row0, (uint32_t)(pe - row0) * 2u, full + s);
+    };
+    if (t == 0) {
+        for (int i = 0; i < STAGES - 1; ++i) {
+            const int tile = blockIdx.x + i * gridDim.x;
+            if (tile < ntiles) issue(tile, i);
+        }
+    }
+    int i = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+        const int s = i % STAGES;
+        if (t == 0) {
+            const int nt = tile + (STAGES - 1) * gridDim.x;
+            if (nt < ntiles) issue(nt, (i + STAGES - 1) % STAGES);
+        }
+        mbar_wait(full + s, (i / STAGES) & 1);
+        const double* sx = reinterpret_cast<const double*>(stage0 + (size_t)s * stage_bytes);
+        const double* sb = sx + wtotal;
+        const uint16_t* sp = reinterpret_cast<const uint16_t*>(sb + TILE);
+        const int row0 = tile * TILE;
+        int p[RPT];
+        bool uni = true;
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            p[j] = (row0 + t + NT * j < n) ? sp[t + NT * j] : 0xFFFF;
+            uni = uni && (p[j] == p[0]);
+        }
+        double acc[RPT];
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) acc[j] = 0.0;
+        const double* sxt = sx + t;
+        if (uni) {
+            if (p[0] != 0xFFFF) {
+                const int h = sh[p[0]], k0 = h & 0xFFFFF, k1 = k0 + (h >> 20);
+#pragma unroll 2
+                for (int k = k0; k < k1; ++k) {
+                    const Ent e = se[k];
+#pragma unroll
+                    for (int j = 0; j < RPT; ++j) acc[j] = acc[j] + e.v * sxt[e.delta + NT * j];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) {
+                if (p[j] == 0xFFFF) continue;
+                const int h = sh[p[j]], k0 = h & 0xFFFFF, k1 = k0 + (h >> 20);
+#pragma unroll 2
+                for (int k = k0; k < k1; ++k) {
+                    const Ent e = se[k];
+                    acc[j] = acc[j] + e.v * sxt[e.delta + NT * j];
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            const int row = row0 + t + NT * j;
+            if (row < n) y[row] = sxt[coff + NT * j] + sd[p[j]] * (sb[t + NT * j] - acc[j]);
+        }
+        __syncthreads();
+    }
+}
+
+
+// V12: warp-uniform fast path through the UNIFORM datapath: when all lanes of a warp carry the same pattern id
+// (redux gives the id in a uniform register) the dictionary in the kernel parameters is read with uniform
+// constant loads (one per warp, no per-lane write-back); mixed warps read the global dictionary per lane.
+__global__ void __launch_bounds__(256) k_uniform(const __grid_constant__ Params P, int n, const uint16_t* __restrict__ pid,
+                                                 const int* __restrict__ hdr, const Ent* __restrict__ ent,
+                                                 const double* __restrict__ dp, const double* __restrict__ x,
+                                                 const double* __restrict__ b, double* __restrict__ y) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = row < n;
+    const int p = ok ? pid[row] : 0;
+    const int pu = __reduce_max_sync(0xffffffffu, p);
+    const bool uni = __all_sync(0xffffffffu, p == pu && ok);
+    if (uni) {
+        const int h = __reduce_max_sync(0xffffffffu, P.hdr[pu]);      // re-uniformise: the loop runs on the uniform datapath
+        const int k0 = h & 0xFFFFF, k1 = k0 + (h >> 20);
+        const double bv = b[row], xv = x[row], dv = P.dp[pu];
+        const double* xr = x + row;
+        double acc = 0.0;
+#pragma unroll 4
+        for (int k = k0; k < k1; ++k) acc = acc + P.e[k].v * __ldg(xr + P.e[k].delta);
+        y[row] = xv + dv * (bv - acc);
+        return;
+    }
+    if (!ok) return;
+    const int h = __ldg(hdr + p), k0 = h & 0xFFFFF, k1 = k0 + (h >> 20);
+    const double bv = b[row], xv = x[row], dv = __ldg(dp + p);
+    double acc = 0.0;
+#pragma unroll 4
+    for (int k = k0; k < k1; ++k) {
+        const Ent e = ldg_ent(ent + k);
+        acc = acc + e.v * __ldg(x + row + e.delta);
+    }
+    y[row] = xv + dv * (bv - acc);
+}
+
+// pure streaming reference: y = x + d*(b - x) with the same vector traffic and the pid read (HBM floor)
+__global__ void __launch_bounds__(256) k_stream(int n, const uint16_t* __restrict__ pid, const double* __restrict__ dp,
+                                                const double* __restrict__ x, const double* __restrict__ b,
+                                                double* __restrict__ y) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    const int p = pid[row];
+    y[row] = x[row] + __ldg(dp + p) * (b[row] - x[row]);
+}
+
+static void build(int N, int pts, std::vector<uint16_t>& pid, std::vector<int>& hdr, std::vector<Ent>& ent,
+                  std::vector<double>& dp) {
+    // boundary class per dimension: 0 first, 1 interior, 2 last -> 27 patterns
+    const long long n = (long long)N * N * N;
+    pid.resize(n);
+    hdr.clear(); ent.clear(); dp.clear();
+    for (int c = 0; c < 27; ++c) {
+        const int cx = c % 3, cy = (c / 3) % 3, cz = c / 9;
+        const int k0 = (int)ent.size();
+        for (int dz = -1; dz <= 1; ++dz)
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int nz = (dx != 0) + (dy != 0) + (dz != 0);
+                    if (pts == 7 && nz > 1) continue;
+                    if ((cx == 0 && dx < 0) || (cx == 2 && dx > 0) || (cy == 0 && dy < 0) || (cy == 2 && dy > 0) ||
+                        (cz == 0 && dz < 0) || (cz == 2 && dz > 0)) continue;
+                    Ent e;
+                    e.v = nz == 0 ? 6.0 + 0.01 * c : -1.0 / (1 + nz) - 0.001 * c;
+                    e.delta = dx + N * dy + N * N * dz;
+                    e.pad = 0;
+                    ent.push_back(e);
+                }
+        hdr.push_back(k0 | (((int)ent.size() - k0) << 20));
+        dp.push_back(0.8 / (6.0 + 0.01 * c));
+    }
+    for (int k = 0; k < N; ++k)
+        for (int j = 0; j < N; ++j)
+            for (int i = 0; i < N; ++i) {
+                const int cx = i == 0 ? 0 : (i == N - 1 ? 2 : 1), cy = j == 0 ? 0 : (j == N - 1 ? 2 : 1),
+                          cz = k == 0 ? 0 : (k == N - 1 ? 2 : 1);
+                pid[(size_t)k * N * N + (size_t)j * N + i] = (uint16_t)(cx + 3 * cy + 9 * cz);
+            }
+}
+
+static bool build_windows(const std::vector<Ent>& ent, const std::vector<int>& hdr, const std::vector<double>& dp,
+                          ParamsT& P, size_t& smem, int TILE = 256, int merge_gap = 32) {
+    std::vector<int> ds;
+    for (auto& e : ent) ds.push_back(e.delta);
+    std::sort(ds.begin(), ds.end());
+    ds.erase(std::unique(ds.begin(), ds.end()), ds.end());
+    memset(&P, 0, sizeof(P));
+    int nw = 0, sb = 0;
+    int lo = ds[0], hi = ds[0];
+    auto close = [&](int lo, int hi) {
+        int lo_even = lo & ~1;                        // rounds towards -inf for negative numbers as well
+        int len = (hi - lo_even) + TILE;
+        len = (len + 1) & ~1;
+        P.w[nw].lo_even = lo_even;
+        P.w[nw].len = len;
+        P.w[nw].sbase = sb;
+        sb += len;
+        ++nw;
+    };
+    for (size_t i = 1; i < ds.size(); ++i) {
+        if (ds[i] - hi <= merge_gap) { hi = ds[i]; continue; }   // close offsets share one window
+        if (nw >= 15) return false;
+        close(lo, hi);
+        lo = hi = ds[i];
+    }
+    close(lo, hi);
+    P.nwin = nw;
+    P.total = sb;
+    for (size_t k = 0; k < ent.size(); ++k) {
+        P.e[k] = ent[k];
+        int g = 0;
+        while (!(ent[k].delta >= P.w[g].lo_even && ent[k].delta < P.w[g].lo_even + P.w[g].len - (TILE - 1))) ++g;
+        P.e[k].delta = P.w[g].sbase + (ent[k].delta - P.w[g].lo_even);
+    }
+    {
+        int g = 0;
+        while (!(0 >= P.w[g].lo_even && 0 < P.w[g].lo_even + P.w[g].len - (TILE - 1))) ++g;
+        P.centre = P.w[g].sbase - P.w[g].lo_even;
+    }
+    memcpy(P.hdr, hdr.data(), hdr.size() * 4);
+    memcpy(P.dp, dp.data(), dp.size() * 8);
+    smem = 16 + (size_t)sb * 8;
+    return true;
+}
+
+int main(int argc, char** argv) {
+    const int reps = 20;
+    for (int cfg = 0; cfg < 2; ++cfg) {
+        const int N = cfg == 0 ? 257 : 129, pts = cfg == 0 ? 7 : 27;
+        const int n = N * N * N;
+        std::vector<uint16_t> pid; std::vector<int> hdr; std::vector<Ent> ent; std::vector<double> dp;
+        build(N, pts, pid, hdr, ent, dp);
+        const int nent = (int)ent.size(), npat = (int)hdr.size();
+        if (nent > MAXE) { printf("too many entries %d\n", nent); return 1; }
+        std::vector<double> hx(n), hb(n);
+        srand(1);
+        for (int i = 0; i < n; ++i) { hx[i] = rand() / (double)RAND_MAX; hb[i] = rand() / (double)RAND_MAX; }
+        uint16_t* dpid; int* dhdr; Ent* dent; double *ddp, *dx, *db, *dy, *dref;
+        CK(cudaMalloc(&dpid, n * 2 + 64)); CK(cudaMalloc(&dhdr, npat * 4)); CK(cudaMalloc(&dent, nent * sizeof(Ent)));
+        CK(cudaMalloc(&ddp, npat * 8)); CK(cudaMalloc(&dx, n * 8 + 64)); CK(cudaMalloc(&db, n * 8 + 64)); CK(cudaMalloc(&dy, n * 8));
+        CK(cudaMalloc(&dref, n * 8));
+        CK(cudaMemcpy(dpid, pid.data(), n * 2, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dhdr, hdr.data(), npat * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dent, ent.data(), nent * sizeof(Ent), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(ddp, dp.data(), npat * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dx, hx.data(), n * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(db, hb.data(), n * 8, cudaMemcpyHostToDevice));
+        Params* P = new Params;
+        memset(P, 0, sizeof(Params));
+        memcpy(P->e, ent.data(), nent * sizeof(Ent));
+        memcpy(P->hdr, hdr.data(), npat * 4);
+        memcpy(P->dp, dp.data(), npat * 8);
+        CK(cudaMemcpyToSymbol(cP, P, sizeof(Params)));
+        // flush buffer (larger than L2) between repetitions is not needed: x, b, y are 3 x 136 MB at 257^3;
+        // at 129^3 (3 x 17 MB) the vectors are L2 resident, as they are inside the real cycle
+        const int grid = (n + 255) / 256;
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        int nsm = 0;
+        CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0));
+        ParamsT* PT = new ParamsT;
+        size_t smem_t = 0;
+        if (!build_windows(ent, hdr, dp, *PT, smem_t)) { printf("no windows\n"); return 1; }
+        printf("windows: %d, smem %zu B\n", PT->nwin, smem_t);
+        Ent* dentT;
+        CK(cudaMalloc(&dentT, MAXE * sizeof(Ent)));
+        CK(cudaMemcpy(dentT, PT->e, MAXE * sizeof(Ent), cudaMemcpyHostToDevice));
+        CK(cudaFuncSetAttribute(k_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+        const char* names[] = {"global LDG.128", "smem LDS.128", "smem split", "kernel params (LDC)", "warp shuffle", "__constant__", "stream floor", "TMA windows + LDC", "TMA pipeline 2 stages", "TMA pipeline 3 stages", "TMA pipeline 4 stages", "TMA + smem dict, 2 rows/thr", "TMA + smem dict, 4 rows/thr", "TMA + smem dict, 8 rows/thr", "persist 2st x 1024thr", "persist 3st x 1024thr", "persist 3st x 512thr", "persist 4st x 512thr", "persist 3st x 256thr", "persist 2st 256thr x4 rows", "persist 3st 256thr x4 rows", "persist 2st 512thr x2 rows", "persist 2st 512thr x4 rows", "uniform datapath dict"};
+        ParamsT* PR[4]; Ent* dentR[4]; size_t smR[4]; int gR[4];
+        const int cfgR[4][3] = {{2, 256, 4}, {3, 256, 4}, {2, 512, 2}, {2, 512, 4}};
+        for (int c = 0; c < 4; ++c) {
+            const int tile = cfgR[c][1] * cfgR[c][2];
+            PR[c] = new ParamsT;
+            size_t dummy;
+            if (!build_windows(ent, hdr, dp, *PR[c], dummy, tile, tile)) { printf("no windows\n"); return 1; }
+            CK(cudaMalloc(&dentR[c], MAXE * sizeof(Ent)));
+            CK(cudaMemcpy(dentR[c], PR[c]->e, MAXE * sizeof(Ent), cudaMemcpyHostToDevice));
+            smR[c] = (size_t)64 + MAXE * sizeof(Ent) + MAXP * 12 + (size_t)cfgR[c][0] * ((size_t)(PR[c]->total + tile) * 8 + tile * 2) + 64;
+            int per = (int)std::min<size_t>(2048 / cfgR[c][1], (220 * 1024) / smR[c]);
+            if (per < 1) per = 1;
+            gR[c] = std::min((n + tile - 1) / tile, nsm * per);
+            printf("rpt cfg %d: %d stages x %d thr x %d rows: windows %d, smem %zu, grid %d\n", c, cfgR[c][0], cfgR[c][1], cfgR[c][2], PR[c]->nwin, smR[c], gR[c]);
+        }
+        CK(cudaFuncSetAttribute(k_pipe_rpt<2, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smR[0]));
+        CK(cudaFuncSetAttribute(k_pipe_rpt<3, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smR[1]));
+        CK(cudaFuncSetAttribute(k_pipe_rpt<2, 512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smR[2]));
+        CK(cudaFuncSetAttribute(k_pipe_rpt<2, 512, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smR[3]));
+        auto ps_smem = [&](int st, int nt) { return (size_t)64 + MAXE * sizeof(Ent) + MAXP * 12 + (size_t)st * ((size_t)(PT->total + PT->nwin * (nt - 256) + nt) * 8 + nt * 2) + 64; };
+        auto ps_grid = [&](int st, int nt) { int per = (int)std::min<size_t>(2048 / nt, (220 * 1024) / ps_smem(st, nt)); if (per < 1) per = 1; return std::min((n + nt - 1) / nt, nsm * per); };
+        CK(cudaFuncSetAttribute(k_pipe_smem<2, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps_smem(2, 1024)));
+        CK(cudaFuncSetAttribute(k_pipe_smem<3, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>(ps_smem(3, 1024), 227 * 1024)));
+        CK(cudaFuncSetAttribute(k_pipe_smem<3, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps_smem(3, 512)));
+        CK(cudaFuncSetAttribute(k_pipe_smem<4, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps_smem(4, 512)));
+        CK(cudaFuncSetAttribute(k_pipe_smem<3, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps_smem(3, 256)));
+        cudaGetLastError();
+        printf("persist smem/grid: 2x1024 %zu/%d 3x1024 %zu/%d 3x512 %zu/%d 4x512 %zu/%d 3x256 %zu/%d\n", ps_smem(2, 1024), ps_grid(2, 1024), ps_smem(3, 1024), ps_grid(3, 1024), ps_smem(3, 512), ps_grid(3, 512), ps_smem(4, 512), ps_grid(4, 512), ps_smem(3, 256), ps_grid(3, 256));
+        auto rpt_smem = [&](int rpt) { return (size_t)16 + MAXE * sizeof(Ent) + (size_t)(PT->total + PT->nwin * 256 * (rpt - 1) + 256 * rpt) * 8 + 512 * rpt + 64; };
+        CK(cudaFuncSetAttribute(k_tma_rpt<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rpt_smem(2)));
+        CK(cudaFuncSetAttribute(k_tma_rpt<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rpt_smem(4)));
+        CK(cudaFuncSetAttribute(k_tma_rpt<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rpt_smem(8)));
+        printf("rows/thread smem: %zu %zu %zu\n", rpt_smem(2), rpt_smem(4), rpt_smem(8));
+        const int ntiles = (n + 255) / 256;
+        const size_t stage_b = (size_t)(PT->total + 256) * 8 + 512;
+        auto pipe_cfg = [&](int stages, size_t& sm, int& g) {
+            sm = 64 + stages * stage_b;
+            int per = (int)std::min<size_t>(8, (200 * 1024) / sm);
+            if (per < 1) per = 1;
+            g = std::min(ntiles, nsm * per);
+        };
+        size_t sm2, sm3, sm4; int g2, g3, g4;
+        pipe_cfg(2, sm2, g2); pipe_cfg(3, sm3, g3); pipe_cfg(4, sm4, g4);
+        CK(cudaFuncSetAttribute(k_tma_pipe<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+        CK(cudaFuncSetAttribute(k_tma_pipe<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
+        CK(cudaFuncSetAttribute(k_tma_pipe<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4));
+        printf("pipeline: stage %zu B, grids %d/%d/%d\n", stage_b, g2, g3, g4);
+        std::vector<double> href(n), hy(n);
+        for (int v = 0; v < 24; ++v) {
+            if (v >= 14 && v <= 22 && v != 14 && v != 21) continue;
+            if (v >= 1 && v <= 5) continue;
+            if (v >= 7 && v <= 10) continue;
+            if (v >= 11 && v <= 13) continue;
+            auto launch = [&]() {
+                switch (v) {
+                    case 0: k_global<<<grid, 256>>>(n, dpid, dhdr, dent, ddp, dx, db, dy); break;
+                    case 1: k_smem<<<grid, 256>>>(n, nent, npat, dpid, dhdr, dent, ddp, dx, db, dy); break;
+                    case 2: k_smem_split<<<grid, 256>>>(n, nent, npat, dpid, dhdr, dent, ddp, dx, db, dy); break;
+                    case 3: k_param<<<grid, 256>>>(*P, n, dpid, dx, db, dy); break;
+                    case 4: k_shfl<<<grid, 256>>>(n, dpid, dhdr, dent, ddp, dx, db, dy); break;
+                    case 5: k_const<<<grid, 256>>>(n, dpid, dx, db, dy); break;
+                    case 6: k_stream<<<grid, 256>>>(n, dpid, ddp, dx, db, dy); break;
+                    case 7: k_tma<<<grid, 256, smem_t>>>(*PT, n, 0, (n + 1) & ~1, dpid, dx, db, dy); break;
+                    case 8: k_tma_pipe<2><<<g2, 256, sm2>>>(*PT, n, ntiles, 0, (n + 1) & ~1, dpid, dx, db, dy); break;
+                    case 9: k_tma_pipe<3><<<g3, 256, sm3>>>(*PT, n, ntiles, 0, (n + 1) & ~1, dpid, dx, db, dy); break;
+                    case 11: k_tma_rpt<2><<<(n + 511) / 512, 256, rpt_smem(2)>>>(*PT, n, nent, npat, 0, (n + 1) & ~1, dpid, dentT, dx, db, dy); break;
+                    case 12: k_tma_rpt<4><<<(n + 1023) / 1024, 256, rpt_smem(4)>>>(*PT, n, nent, npat, 0, (n + 1) & ~1, dpid, dentT, dx, db, dy); break;
+                    case 13: k_tma_rpt<8><<<(n + 2047) / 2048, 256, rpt_smem(8)>>>(*PT, n, nent, npat, 0, (n + 1) & ~1, dpid, dentT, dx, db, dy); break;
+                    case 14: k_pipe_smem<2, 1024><<<ps_grid(2, 1024), 1024, ps_smem(2, 1024)>>>(*PT, n, nent, (n + 1023) / 1024, 0, (n + 1) & ~1, dpid, dentT, dx, db, dy); break;
+                    case 15: if (ps_smem(3, 1024) <= 227 * 1024) k_pipe_smem<3, 1024><<<ps_grid(3, 1024), 1024, ps_smem(3, 1024)>>>(*PT, n, nent, (n + 1023) / 1024, 0, (n + 1) & ~1, dpid, dentT, dx, db, dy); break;
+                    case 16: k_pipe_smem<3, 512><<<ps_grid(3, 512), 512, ps_smem(3, 512)>>>(*PT, n, nent, (n + 511) / 512, 0, (n + 1) & ~1, dpid, dentT, dx, db, dy); break;
+                    case 17: k_pipe_smem<4, 512><<<ps_grid(4, 512), 512, ps_smem(4, 512)>>>(*PT, n, nent, (n + 511) / 512, 0, (n + 1) & ~1, dpid, dentT, dx, db, dy); break;
+                    case 18: k_pipe_smem<3, 256><<<ps_grid(3, 256), 256, ps_smem(3, 256)>>>(*PT, n, nent, (n + 255) / 256, 0, (n + 1) & ~1, dpid, dentT, dx, db, dy); break;
+                    case 19: k_pipe_rpt<2, 256, 4><<<gR[0], 256, smR[0]>>>(*PR[0], n, nent, (n + 1023) / 1024, 0, (n + 1) & ~1, dpid, dentR[0], dx, db, dy); break;
+                    case 20: k_pipe_rpt<3, 256, 4><<<gR[1], 256, smR[1]>>>(*PR[1], n, nent, (n + 1023) / 1024, 0, (n + 1) & ~1, dpid, dentR[1], dx, db, dy); break;
+                    case 21: k_pipe_rpt<2, 512, 2><<<gR[2], 512, smR[2]>>>(*PR[2], n, nent, (n + 1023) / 1024, 0, (n + 1) & ~1, dpid, dentR[2], dx, db, dy); break;
+                    case 22: k_pipe_rpt<2, 512, 4><<<gR[3], 512, smR[3]>>>(*PR[3], n, nent, (n + 2047) / 2048, 0, (n + 1) & ~1, dpid, dentR[3], dx, db, dy); break;
+                    case 23: k_uniform<<<grid, 256>>>(*P, n, dpid, dhdr, dent, ddp, dx, db, dy); break;
+                    case 10: k_tma_pipe<4><<<g4, 256, sm4>>>(*PT, n, ntiles, 0, (n + 1) & ~1, dpid, dx, db, dy); break;
+                }
+            };
+            CK(cudaMemset(dy, 0, n * 8));
+            for (int w = 0; w < 3; ++w) launch();
+            CK(cudaGetLastError());
+            CK(cudaDeviceSynchronize());
+            CK(cudaEventRecord(e0));
+            for (int r = 0; r < reps; ++r) launch();
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+            CK(cudaMemcpy(hy.data(), dy, n * 8, cudaMemcpyDeviceToHost));
+            bool same = true;
+            if (v == 0) href = hy;
+            else if (v != 6) same = memcmp(href.data(), hy.data(), n * 8) == 0;
+            const double us = 1e3 * ms / reps;
+            printf("%2d-point N=%d  %-22s %8.1f us  %7.1f GB/s (26 B/row)  %s\n", pts, N, names[v], us,
+                   26.0 * n / us / 1e3, v != 6 ? (same ? "bit-identical" : "MISMATCH") : "");
+        }
+        cudaFree(dpid); cudaFree(dhdr); cudaFree(dent); cudaFree(ddp); cudaFree(dx); cudaFree(db); cudaFree(dy); cudaFree(dref);
+        delete P;
+    }
+    return 0;
+}
