@@ -175,12 +175,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(rows), "power_w_max": max(r[3] for r in rows)}
 
 
-def ncu_traffic(cells, dom):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+def ncu_traffic(cells, dom, fmt):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of the
+    device format in use (fmt: "pattern" = stencil dictionary, "csr" = CSR stream)."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             t = json.load(f)
-        return t[f"cfg2_{cells}"][f"{dom['kind']}_level{dom['level']}"]["traffic_bytes"]
+        return t[f"cfg2_{cells}"][f"{dom['kind']}_level{dom['level']}_{fmt}"]["traffic_bytes"]
     except Exception:
         return None
 
@@ -348,7 +349,8 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": f"{dom['kind']} level {dom['level']} (fused Jacobi sweep x' = x + d.*(b - A x))"
                 if dom["kind"] == "sweep" else f"{dom['kind']} level {dom['level']}",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "peak_source": peak_src, "traffic": ncu_traffic(cells, dom),
+                "peak_source": peak_src,
+                "traffic": ncu_traffic(cells, dom, "pattern" if pinfo["in_use"] else "csr"),
                 "share_of_step": dom["total_ms"] / tot_ms,
                 "device_format": ("stencil dictionary (csrc/pattern.cuh): 16-bit pattern id per row, "
                                   f"{pinfo['patterns']} patterns / {pinfo['entries']} entries for A_1, d folded: "

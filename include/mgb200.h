@@ -68,6 +68,12 @@ int mgb200_upload_level(mgb200_handle h, int level, int64_t n, int64_t nc,
 int mgb200_upload_coarsest(mgb200_handle h, int64_t n, const int64_t* colptr, const int64_t* rowval,
                            const void* nzval, int index_base);
 
+/* defineCoarsestAinv with coarseSolveType == "GMRES" (MGsetup.jl:333-334, solveCoarsest MGcycle.jl:152-168):
+ * As[end] in CSC and d = param.LU = conj(relaxParam ./ diag(As[end])) (VAL, length n).  The coarsest solve is then
+ * x = 0; one restart of KrylovMethods.fgmres(10), tol 0.01, right-preconditioned by d.*v (nrhs = 1). */
+int mgb200_upload_coarsest_gmres(mgb200_handle h, int64_t n, const int64_t* colptr, const int64_t* rowval,
+                                 const void* nzval, const void* d, int index_base);
+
 /* Optional: the matrix the Krylov drivers multiply with when it is not As[1]
  * (solveCG_MG(AT,param,...) takes AT separately, SolveFuncs.jl:77-82).  CSC of A^H. */
 int mgb200_set_krylov_matrix(mgb200_handle h, int64_t n, const int64_t* colptr, const int64_t* rowval,
@@ -100,6 +106,13 @@ int mgb200_solveCG(mgb200_handle h, const void* b, void* x, double tol, int max_
  * *nres = number of entries written. */
 int mgb200_solveFGMRES(mgb200_handle h, const void* b, void* x, int inner, int flexible, double tol,
                        int max_iter, int* iter, int* flag, double* resvec, int* nres);
+
+/* solveBiCGSTAB_MG (SolveFuncs.jl:85-99): KrylovMethods.bicgstb with one cycle as M1 (M2 = identity), nrhs = 1.
+ * resvec: max_iter+1 doubles, resvec[0] = initial relative residual.  flag: 0 converged, -1 max_iter,
+ * -2 breakdown, -3 converged after the first half of an iteration, -9 b = 0.  *iter = completed iterations,
+ * *nprec = cycles applied (the reference's nprec = 2*iter + (flag == -3), SolveFuncs.jl:97). */
+int mgb200_solveBiCGSTAB(mgb200_handle h, const void* b, void* x, double tol, int max_iter, int* iter,
+                         int* flag, double* resvec, int* nprec);
 
 /* SpMatMul(alpha,AT,x,beta,y) (SpMatMul.jl:4-26) on an uploaded matrix:
  * which = 0: A_l, 1: P_l, 2: R_l.  (alpha,beta) must be one of (1,0),(1,1),(-1,1),(-1,0). */

@@ -19,6 +19,8 @@ from .mgsetup import (MGsetup, getRelaxPrec, getSPAIprec, adjustMemoryForNumRHS,
 from .sa_amg import (SA_AMGsetup, getAggregation, getStrengthMatrix, neighborhoodAggregationNew,
                      aggrArray2P)
 from .device import DeviceHierarchy, uploadHierarchy, MGB200Error, LIB_PATH
-from .solve import (solveMG, solveCG_MG, solveGMRES_MG, getMultigridPreconditioner, recursiveCycle,
+from .solve import (solveMG, solveCG_MG, solveGMRES_MG, solveBiCGSTAB_MG, getMultigridPreconditioner, recursiveCycle,
                     SpMatMul)
 from .dist_setup import (slab_planes, setup_slab_hierarchy, poisson_window_operator, DistHierarchy, DistLevel)
+from .wrappers import (MGsolver, SA_AMGsolver, getMGsolver, getSA_AMGsolver, solveLinearSystem, setupSolver)
+from . import wrappers

@@ -157,6 +157,14 @@ int mgb200_upload_coarsest(mgb200_handle h, int64_t n, const int64_t* colptr, co
     MGB_CATCH
 }
 
+int mgb200_upload_coarsest_gmres(mgb200_handle h, int64_t n, const int64_t* colptr, const int64_t* rowval,
+                                 const void* nzval, const void* d, int index_base) {
+    MGB_TRY
+    MGB_CHECK(colptr && rowval && nzval && d, "null argument");
+    MGB_BOTH(h, H->upload_coarsest_gmres(n, colptr, rowval, nzval, d, index_base));
+    MGB_CATCH
+}
+
 int mgb200_set_krylov_matrix(mgb200_handle h, int64_t n, const int64_t* colptr, const int64_t* rowval,
                              const void* nzval, int index_base) {
     MGB_TRY
@@ -291,6 +299,21 @@ int mgb200_solveFGMRES(mgb200_handle h, const void* b, void* x, int inner, int f
         H->h2d_vec(b, H->L[0].b, n);
         H->h2d_vec(x, H->ucur, n);
         *iter = H->solveFGMRES(H->ucur, inner, flexible != 0, tol, max_iter, flag, resvec, nres);
+        H->d2h_vec(H->ucur, x, n);
+    });
+    MGB_CATCH
+}
+
+int mgb200_solveBiCGSTAB(mgb200_handle h, const void* b, void* x, double tol, int max_iter, int* iter, int* flag,
+                         double* resvec, int* nprec) {
+    MGB_TRY
+    MGB_CHECK(b && x && iter && flag && resvec && nprec, "null argument");
+    MGB_BOTH(h, {
+        H->ensure_work();
+        const long long n = H->L[0].n;
+        H->h2d_vec(b, H->L[0].b, n);
+        H->h2d_vec(x, H->ucur, n);
+        *iter = H->solveBiCGSTAB(H->ucur, tol, max_iter, flag, resvec, nprec);
         H->d2h_vec(H->ucur, x, n);
     });
     MGB_CATCH

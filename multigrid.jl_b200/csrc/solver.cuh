@@ -72,13 +72,18 @@ struct Level {
 template <typename TV>
 struct Coarsest {
     int n = 0;
+    int kind = 0;     // 0: dense LU (default branch of defineCoarsestAinv), 1: "GMRES" (MGsetup.jl:333-334)
     TV* linv = nullptr;
     TV* uinv = nullptr;
     int* perm = nullptr;
     TV* y = nullptr;  // n*m scratch
+    // coarseSolveType "GMRES": param.LU = conj(relaxParam ./ diag(AT)) and the FGMRES(10) workspace
+    TV *d = nullptr, *r = nullptr, *w = nullptr, *t = nullptr, *V = nullptr, *dv = nullptr;
     void release() {
         dev_free(linv); dev_free(uinv); dev_free(perm); dev_free(y);
+        dev_free(d); dev_free(r); dev_free(w); dev_free(t); dev_free(V); dev_free(dv);
         n = 0;
+        kind = 0;
     }
 };
 
@@ -263,6 +268,30 @@ struct Hierarchy : HierarchyBase {
         ctx.sync();
         dev_free(a);
         dev_free(piv);
+        work_ready = false;
+    }
+
+    // defineCoarsestAinv, coarseSolveType == "GMRES" (MGsetup.jl:333-334): As[end] and the Jacobi weights d
+    void upload_coarsest_gmres(long long n, const int64_t* cp, const int64_t* rv, const void* nz, const void* d,
+                               int base) {
+        MGB_CHECK(n >= 2, "coarsest grid too small for GMRES");
+        MGB_CUDA(cudaSetDevice(ctx.device));
+        Level<TV>& lv = L[levels - 1];
+        lv.n = n;
+        lv.nalloc = n;
+        upload_csr<TV>(ctx, lv.A, n, n, cp, rv, static_cast<const TV*>(nz), base, true);
+        coarse.release();
+        coarse.n = (int)n;
+        coarse.kind = 1;
+        coarse.d = dev_alloc<TV>(n);
+        MGB_CUDA(cudaMemcpy(coarse.d, d, n * sizeof(TV), cudaMemcpyHostToDevice));
+        const int restrt = (int)std::min<long long>(10, n - 1);
+        coarse.r = dev_alloc<TV>(n);
+        coarse.w = dev_alloc<TV>(n);
+        coarse.t = dev_alloc<TV>(n);
+        coarse.dv = dev_alloc<TV>(n);
+        coarse.V = dev_alloc<TV>((size_t)n * restrt);
+        invalidate_graphs();
         work_ready = false;
     }
 
@@ -814,6 +843,24 @@ struct Hierarchy : HierarchyBase {
 
     void solve_coarsest(const TV* b, TV* x) {  // x = A_L^{-1} b  (MGcycle.jl:176-179)
         const int n = coarse.n;
+        if (coarse.kind == 1) {
+            // coarseSolveType "GMRES" (MGcycle.jl:152-168): x .= 0; one restart of fgmres(10), tol 0.01,
+            // right preconditioner M2(v) = d .* v, not flexible
+            MGB_CHECK(m == 1, "coarsest GMRES: blockFGMRES (nrhs > 1) is not provided");
+            dev_zero<TV>(ctx, n, x);
+            FgmresWs ws;
+            ws.r = coarse.r; ws.w = coarse.w; ws.t = coarse.t; ws.V = coarse.V; ws.Z = nullptr;
+            ws.ld = n;
+            PrecFn m2 = [this, n](const TV* v) -> TV* {
+                Launch La(ctx, K_DIAG, levels, 3.0 * n * sizeof(TV));
+                diag_scale_kernel<TV><<<ctx.ew_blocks(n), 256, 0, ctx.stream>>>(n, 1, coarse.d, v, coarse.dv);
+                MGB_LAUNCH_CHECK();
+                return coarse.dv;
+            };
+            int flag = 0, nres = 0;
+            fgmres_core(L[levels - 1].A, levels, n, b, x, 10, false, 0.01, 1, m2, ws, &flag, nullptr, &nres);
+            return;
+        }
         Launch La(ctx, K_COARSE, levels, (double)n * n * sizeof(TV));
         const int grid = cdiv((long long)n * m * 32, 256);
         lower_apply_kernel<TV><<<grid, 256, 0, ctx.stream>>>(n, m, coarse.linv, coarse.perm, b, coarse.y);
@@ -952,7 +999,7 @@ struct Hierarchy : HierarchyBase {
 
     // cycle from the finest level, replayed from a CUDA graph when the cycle has no host read-backs
     TV* cycle_fine(const TV* b, TV* x, TV* scratch, bool xzero, char ctype) {
-        const bool can = ctx.use_graphs && !ctx.profiling && relax_kind == 0 && ctype != 'K' &&
+        const bool can = ctx.use_graphs && !ctx.profiling && relax_kind == 0 && ctype != 'K' && coarse.kind == 0 &&
                          (!comm.active() || p2p.on) && levels > 1;
         if (!can) return cycle(0, b, x, scratch, xzero, ctype);
         const auto key = std::make_tuple(b, x, scratch, xzero, ctype);
@@ -1216,52 +1263,144 @@ struct Hierarchy : HierarchyBase {
         return it;
     }
 
-    // ---- KrylovMethods.fgmres with M = one cycle (solveGMRES_MG, SolveFuncs.jl:120-132) ---------
-    int solveFGMRES(TV* xk, int restrt, bool flexible, double tol, int max_iter, int* flag, double* resvec,
-                    int* nres) {
+    // ---- KrylovMethods.bicgstb with M1 = one cycle, M2 = identity (solveBiCGSTAB_MG, SolveFuncs.jl:85-99) ----
+    // van der Vorst's preconditioned BiCGStab as in the "Templates" book, which the package follows.
+    // resvec: max_iter + 1 doubles (resvec[0] = initial relative residual).  flag: 0 converged, -1 max_iter,
+    // -2 breakdown (rho == 0 or omega == 0), -3 converged after the first half of an iteration, -9 b == 0.
+    // Returns the number of completed iterations; *nprec = cycles applied (2 per iteration, SolveFuncs.jl:97).
+    int solveBiCGSTAB(TV* xk, double tol, int max_iter, int* flag, double* resvec, int* nprec) {
         ensure_work();
-        MGB_CHECK(m == 1, "solveFGMRES: blockFGMRES (nrhs > 1) is not provided yet");
+        MGB_CHECK(m == 1, "solveBiCGSTAB: blockBiCGSTB (nrhs > 1) is not provided");
+        ensure_krylov(1, true);
         Level<TV>& lv = L[0];
         const long long n = lv.n;
-        restrt = (int)std::min<long long>(restrt, n - 1);
-        MGB_CHECK(restrt >= 1 && restrt <= MAXK, "fgmres: restart length must be in 1..32");
-        ensure_krylov(restrt, true);
         const Csr<TV>& A = krylov_A();
         const TV* b = lv.b;
+        TV *r = kr, *rt = kw, *p = kp, *v = kAp, *phat = kV, *t = kZ;
+        *nprec = 0;
+        const double bnrm2 = norm(n, b);
+        if (bnrm2 == 0.0) {
+            dev_zero<TV>(ctx, n, xk);
+            *flag = -9;
+            resvec[0] = 0.0;
+            return 0;
+        }
+        residual(A, b, xk, r, 1);
+        double err = norm(n, r) / bnrm2;
+        resvec[0] = err;
+        if (err < tol) {
+            *flag = 0;
+            return 0;
+        }
+        dev_copy<TV>(ctx, n, r, rt);
+        zc omega(1.0, 0.0), alpha(1.0, 0.0), rho1(1.0, 0.0);
+        *flag = -1;
+        int it = 0;
+        for (it = 1; it <= max_iter; ++it) {
+            const zc rho = dot(n, rt, r);
+            if (rho == zc(0.0, 0.0)) {
+                *flag = -2;
+                break;
+            }
+            if (it > 1) {
+                const zc beta = (rho / rho1) * (alpha / omega);
+                Launch La(ctx, K_VECTOR, 0, 4.0 * n * sizeof(TV));
+                bicg_p_kernel<TV><<<ctx.ew_blocks(n), 256, 0, ctx.stream>>>(n, to_tv(beta), to_tv(omega), r, v, p);
+                MGB_LAUNCH_CHECK();
+            } else {
+                dev_copy<TV>(ctx, n, r, p);
+            }
+            TV* z = precondition(p);                         // p_hat = M2(M1(p)), M2 = identity
+            *nprec += 1;
+            dev_copy<TV>(ctx, n, z, phat);
+            apply_A(A, phat, v, 1);                          // v = A(p_hat)
+            alpha = rho / dot(n, rt, v);
+            dev_axpby<TV>(ctx, n, to_tv(-alpha), v, VT<TV>::one(), r, false);   // s = r - alpha*v (in r)
+            const double snorm = norm(n, r) / bnrm2;
+            if (snorm < tol) {
+                Launch La(ctx, K_VECTOR, 0, 3.0 * n * sizeof(TV));
+                bicg_x_kernel<TV><<<ctx.ew_blocks(n), 256, 0, ctx.stream>>>(n, to_tv(alpha), phat, VT<TV>::zero(), phat, xk, 0);
+                MGB_LAUNCH_CHECK();
+                resvec[it] = snorm;
+                *flag = -3;
+                return it - 1;
+            }
+            z = precondition(r);                             // s_hat
+            *nprec += 1;
+            apply_A(A, z, t, 1);                             // t = A(s_hat)
+            const zc ts = dot(n, t, r), tt = dot(n, t, t);
+            omega = ts / tt;
+            {
+                Launch La(ctx, K_VECTOR, 0, 4.0 * n * sizeof(TV));
+                bicg_x_kernel<TV><<<ctx.ew_blocks(n), 256, 0, ctx.stream>>>(n, to_tv(alpha), phat, to_tv(omega), z, xk, 1);
+                MGB_LAUNCH_CHECK();
+            }
+            dev_axpby<TV>(ctx, n, to_tv(-omega), t, VT<TV>::one(), r, false);   // r = s - omega*t
+            err = norm(n, r) / bnrm2;
+            resvec[it] = err;
+            if (err <= tol) {
+                *flag = 0;
+                break;
+            }
+            if (omega == zc(0.0, 0.0)) {
+                *flag = -2;
+                break;
+            }
+            rho1 = rho;
+        }
+        if (it > max_iter) it = max_iter;
+        return it;
+    }
+
+    // ---- KrylovMethods.fgmres (solveGMRES_MG, SolveFuncs.jl:120-132; coarsest "GMRES", MGcycle.jl:152-168) ----
+    // Restarted right-preconditioned (F)GMRES on level `level` (1-based) with workspace ws; prec(v) returns a
+    // buffer holding M v.  max_iter counts restarts.
+    struct FgmresWs {
+        TV *r = nullptr, *w = nullptr, *t = nullptr, *V = nullptr, *Z = nullptr;
+        long long ld = 0;
+    };
+    int fgmres_core(const Csr<TV>& A, int level, long long n, const TV* b, TV* xk, int restrt, bool flexible,
+                    double tol, int max_iter, const PrecFn& prec, const FgmresWs& ws, int* flag, double* resvec,
+                    int* nres) {
+        const int l = level - 1;
+        restrt = (int)std::min<long long>(restrt, n - 1);
+        MGB_CHECK(restrt >= 1 && restrt <= MAXK, "fgmres: restart length must be in 1..32");
+        MGB_CHECK(!flexible || ws.Z, "fgmres: flexible variant needs the Z workspace");
         *nres = 0;
-        const double rnorm0 = norm(n, b);
+        const double rnorm0 = norm(n, b, l);
         if (rnorm0 == 0.0) {
             dev_zero<TV>(ctx, n, xk);
             *flag = -9;
             return 0;
         }
-        residual(A, b, xk, kr, 1);
-        double err = norm(n, kr) / rnorm0;
+        residual(A, b, xk, ws.r, level);
+        double err = norm(n, ws.r, l) / rnorm0;
         if (err < tol) {
             *flag = 0;
-            resvec[0] = err;
+            if (resvec) resvec[0] = err;
             *nres = 1;
             return 0;
         }
         *flag = -1;
         int counter = 0, it = 0;
         const int ldh = restrt;
-        const long long ldv = L[0].nalloc;   // basis columns are allocated with ghost space
+        const long long ldv = ws.ld;
+        TV* kw_ = ws.w;
         while (it < max_iter) {
             it += 1;
             std::vector<zc> H((size_t)(restrt + 1) * ldh, zc(0, 0)), xi(restrt + 1, zc(0, 0)), y;
-            double betta = norm(n, kr);
+            double betta = norm(n, ws.r, l);
             xi[0] = betta;
-            dev_axpby<TV>(ctx, n, VT<TV>::from_real(1.0 / betta), kr, VT<TV>::zero(), kw, true);  // w = r/betta
-            dev_copy<TV>(ctx, n, kw, kV);
+            dev_axpby<TV>(ctx, n, VT<TV>::from_real(1.0 / betta), ws.r, VT<TV>::zero(), kw_, true);  // w = r/betta
+            dev_copy<TV>(ctx, n, kw_, ws.V);
             int jdone = 0;
             for (int j = 0; j < restrt; ++j) {
-                TV* z = precondition(kw);                                        // z = M(w)
-                if (flexible) dev_copy<TV>(ctx, n, z, kZ + (size_t)j * ldv);
-                apply_A(A, z, kw, 1);                                            // w = A(z)
+                TV* z = prec(kw_);                                               // z = M(w)
+                if (flexible) dev_copy<TV>(ctx, n, z, ws.Z + (size_t)j * ldv);
+                apply_A(A, z, kw_, level);                                       // w = A(z)
                 counter += 1;
-                dev_multi_dot<TV>(ctx, n, kV, ldv, j + 1, kw, ctx.scal + 16);    // t = V'w
-                allreduce(0, ctx.scal + 16, 2 * (j + 1));
+                dev_multi_dot<TV>(ctx, n, ws.V, ldv, j + 1, kw_, ctx.scal + 16);  // t = V'w
+                allreduce(l, ctx.scal + 16, 2 * (j + 1));
                 std::vector<double> hv(2 * (j + 1));
                 read_scalars(ctx, ctx.scal + 16, 2 * (j + 1), hv.data());
                 std::vector<TV> coef(j + 1);
@@ -1269,16 +1408,16 @@ struct Hierarchy : HierarchyBase {
                     H[(size_t)i * ldh + j] = zc(hv[2 * i], hv[2 * i + 1]);
                     coef[i] = to_tv(-H[(size_t)i * ldh + j]);
                 }
-                dev_multi_axpy<TV>(ctx, n, kV, ldv, j + 1, coef.data(), 1.0, kw, ctx.scal + 12);  // w -= V t, ||w||^2
-                allreduce(0, ctx.scal + 12, 1);
+                dev_multi_axpy<TV>(ctx, n, ws.V, ldv, j + 1, coef.data(), 1.0, kw_, ctx.scal + 12);  // w -= V t, ||w||^2
+                allreduce(l, ctx.scal + 12, 1);
                 double nw2;
                 read_scalars(ctx, ctx.scal + 12, 1, &nw2);
                 betta = std::sqrt(nw2);
                 H[(size_t)(j + 1) * ldh + j] = betta;
-                dev_axpby<TV>(ctx, n, VT<TV>::from_real(1.0 / betta), kw, VT<TV>::zero(), kw, true);  // w *= 1/betta
-                if (j + 1 < restrt) dev_copy<TV>(ctx, n, kw, kV + (size_t)(j + 1) * ldv);
+                dev_axpby<TV>(ctx, n, VT<TV>::from_real(1.0 / betta), kw_, VT<TV>::zero(), kw_, true);  // w *= 1/betta
+                if (j + 1 < restrt) dev_copy<TV>(ctx, n, kw_, ws.V + (size_t)(j + 1) * ldv);
                 err = hessenberg_lsq(H, ldh, j + 2, j + 1, xi, y) / rnorm0;
-                resvec[counter - 1] = err;
+                if (resvec) resvec[counter - 1] = err;
                 jdone = j + 1;
                 if (err <= tol) {
                     *flag = 0;
@@ -1289,17 +1428,31 @@ struct Hierarchy : HierarchyBase {
             std::vector<TV> coef(jdone);
             for (int i = 0; i < jdone; ++i) coef[i] = to_tv(y[i]);
             if (flexible) {
-                dev_multi_axpy<TV>(ctx, n, kZ, ldv, jdone, coef.data(), 1.0, xk, nullptr);  // x += Z y
+                dev_multi_axpy<TV>(ctx, n, ws.Z, ldv, jdone, coef.data(), 1.0, xk, nullptr);  // x += Z y
             } else {
-                dev_multi_axpy<TV>(ctx, n, kV, ldv, jdone, coef.data(), 0.0, kAp, nullptr);  // V y
-                TV* z = precondition(kAp);
+                dev_multi_axpy<TV>(ctx, n, ws.V, ldv, jdone, coef.data(), 0.0, ws.t, nullptr);  // V y
+                TV* z = prec(ws.t);
                 dev_axpby<TV>(ctx, n, VT<TV>::one(), z, VT<TV>::one(), xk, false);        // x += M(V y)
             }
             if (*flag == 0) break;
-            if (it < max_iter) residual(A, b, xk, kr, 1);
+            if (it < max_iter) residual(A, b, xk, ws.r, level);
         }
         *nres = counter;
         return it;
+    }
+    int solveFGMRES(TV* xk, int restrt, bool flexible, double tol, int max_iter, int* flag, double* resvec,
+                    int* nres) {
+        ensure_work();
+        MGB_CHECK(m == 1, "solveFGMRES: blockFGMRES (nrhs > 1) is not provided yet");
+        Level<TV>& lv = L[0];
+        restrt = (int)std::min<long long>(restrt, lv.n - 1);
+        MGB_CHECK(restrt >= 1 && restrt <= MAXK, "fgmres: restart length must be in 1..32");
+        ensure_krylov(restrt, true);
+        FgmresWs ws;
+        ws.r = kr; ws.w = kw; ws.t = kAp; ws.V = kV; ws.Z = kZ;
+        ws.ld = lv.nalloc;   // basis columns are allocated with ghost space
+        PrecFn prec = [this](const TV* v) -> TV* { return precondition(v); };
+        return fgmres_core(krylov_A(), 1, lv.n, lv.b, xk, restrt, flexible, tol, max_iter, prec, ws, flag, resvec, nres);
     }
 
     // ---- host <-> device layout helpers -------------------------------------------------------

@@ -142,6 +142,22 @@ __global__ void axpby_kernel(long long n, TV a, const TV* x, TV b, TV* y, int b_
         y[i] = b_is_zero ? a * x[i] : (b * y[i] + a * x[i]);
 }
 
+// BiCGStab updates (KrylovMethods.bicgstb):  p = r + beta*(p - omega*v)   and   x += alpha*phat + omega*shat
+template <typename TV>
+__global__ void bicg_p_kernel(long long n, TV beta, TV omega, const TV* __restrict__ r, const TV* __restrict__ v,
+                              TV* __restrict__ p) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        p[i] = r[i] + beta * (p[i] - omega * v[i]);
+}
+template <typename TV>
+__global__ void bicg_x_kernel(long long n, TV alpha, const TV* __restrict__ phat, TV omega,
+                              const TV* __restrict__ shat, TV* __restrict__ x, int with_shat) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        x[i] = with_shat ? x[i] + (alpha * phat[i] + omega * shat[i]) : x[i] + alpha * phat[i];
+}
+
 // first sweep of a cycle from x = 0:  x = 0 + d .* b   (MGcycle.jl:28-31 skipped, :129)
 template <typename TV>
 __global__ void diag_scale_kernel(long long n, int m, const TV* __restrict__ d, const TV* __restrict__ b,

@@ -67,6 +67,18 @@ def solveCG_MG(AT, param: MGparam, b, x0, verbose: bool = False):
     return x0, param, it
 
 
+def solveBiCGSTAB_MG(AT, param: MGparam, b, x0, verbose: bool = False):
+    """solveBiCGSTAB_MG(AT,param,b,x0,verbose) -> (x, param, iter, nprec)   (SolveFuncs.jl:73-75,85-99)."""
+    if _nrhs(b) != 1:
+        raise NotImplementedError("blockBiCGSTB (nrhs > 1) is not provided on the device path")
+    dev = _device(param, b)
+    _krylov_matrix(dev, AT, param)
+    xx, it, flag, res, nprec = dev.solveBiCGSTAB(b, x0, param.relativeTol, param.maxOuterIter)
+    param.last_resvec, param.last_flag = res, flag
+    x0[...] = xx.reshape(x0.shape)
+    return x0, param, it, nprec
+
+
 def solveGMRES_MG(AT, param: MGparam, b, x0, flexible: bool, inner: int, verbose: bool = False):
     """solveGMRES_MG(AT,param,b,x0,flexible,inner,verbose) -> (x, param, iter, resvec)
     (SolveFuncs.jl:80-82,120-132)."""

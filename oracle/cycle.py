@@ -337,6 +337,19 @@ def solveCG_MG(AT, mg: OracleMG, b, x0):
     return x, it, flag, resvec
 
 
+def solveBiCGSTAB_MG(AT, mg: OracleMG, b, x0):
+    """SolveFuncs.jl:73-75,85-99 -> KrylovMethods.bicgstb (M1 = one cycle, M2 = identity).
+    Returns (x, iter, flag, resvec, nprec)."""
+    from . import krylov
+    b = np.asfortranarray(b)
+    ATc = AT if isinstance(AT, K.CSCAdjoint) else K.CSCAdjoint(AT)
+    Afun = getAfun(ATc, np.zeros(b.shape, dtype=b.dtype, order="F"), mg.numCores)
+    MMG = getMultigridPreconditioner(mg, b)
+    x, flag, rnorm, it, resvec = krylov.bicgstb(Afun, b.reshape(-1), tol=mg.relativeTol,
+                                                maxIter=mg.maxOuterIter, M1=MMG, x=x0)
+    return x, it, flag, resvec, 2 * it + (1 if flag == -3 else 0)
+
+
 def solveGMRES_MG(AT, mg: OracleMG, b, x0, flexible, inner):
     """SolveFuncs.jl:80-82,120-132 -> KrylovMethods.fgmres / blockFGMRES."""
     from . import krylov

@@ -57,6 +57,70 @@ def cg(A, b, tol=1e-2, maxIter=100, M=None, x=None, out=0):
     return x, flag, resvec[lastIter - 1], lastIter, resvec[:lastIter].copy()
 
 
+def bicgstb(A, b, tol=1e-6, maxIter=100, M1=None, M2=None, x=None, out=0):
+    """KrylovMethods.bicgstb: van der Vorst's preconditioned BiCGStab in the form of the "Templates"
+    book (p_hat = M2(M1(p)), v = A p_hat, s = r - alpha v, half-step exit on ||s||/||b|| < tol,
+    s_hat = M2(M1(s)), t = A s_hat, omega = <t,s>/<t,t>).  Returns (x, flag, relres, iter, resvec)
+    with resvec[0] the initial relative residual; flag -3 = converged at the half step, in which case
+    ``iter`` counts the completed full iterations (the reference adds one preconditioner application
+    for it: nprec = 2*iter + (flag == -3), SolveFuncs.jl:97)."""
+    n = b.shape[0]
+    M1 = (lambda v: v.copy()) if M1 is None else M1
+    M2 = (lambda v: v) if M2 is None else M2
+    if K.norm(b) == 0:
+        return np.zeros(n, dtype=b.dtype), -9, 0.0, 0, np.array([0.0])
+    if x is None or x.size == 0:
+        x = np.zeros(n, dtype=b.dtype)
+        r = b.copy()
+    else:
+        r = b - A(x)
+    bnrm2 = K.norm(b)
+    err = K.norm(r) / bnrm2
+    resvec = np.zeros(maxIter + 1)
+    resvec[0] = err
+    if err < tol:
+        return x, 0, err, 0, resvec[:1].copy()
+    omega = alpha = rho1 = 1.0
+    r_tld = r.copy()
+    p = v = None
+    flag = -1
+    it = 0
+    for it in range(1, maxIter + 1):
+        rho = K.dot(r_tld, r)
+        if rho == 0.0:
+            flag = -2
+            break
+        if it > 1:
+            beta = (rho / rho1) * (alpha / omega)
+            p = r + beta * (p - omega * v)
+        else:
+            p = r.copy()
+        p_hat = np.array(M2(M1(p)), copy=True)
+        v = np.array(A(p_hat), copy=True)
+        alpha = rho / K.dot(r_tld, v)
+        s = r - alpha * v
+        snorm = K.norm(s) / bnrm2
+        if snorm < tol:
+            x = x + alpha * p_hat
+            resvec[it] = snorm
+            return x, -3, snorm, it - 1, resvec[:it + 1].copy()
+        s_hat = M2(M1(s))
+        t = np.array(A(s_hat), copy=True)
+        omega = K.dot(t, s) / K.dot(t, t)
+        x = x + (alpha * p_hat + omega * s_hat)
+        r = s - omega * t
+        err = K.norm(r) / bnrm2
+        resvec[it] = err
+        if err <= tol:
+            flag = 0
+            break
+        if omega == 0.0:
+            flag = -2
+            break
+        rho1 = rho
+    return x, flag, resvec[it], it, resvec[:it + 1].copy()
+
+
 def _colnorms(X):
     return np.sqrt(np.sum((X.conj() * X).real, axis=0))
 

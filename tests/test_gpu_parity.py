@@ -105,6 +105,33 @@ def test_block_solveMG(nrhs):
     assert np.linalg.norm(x - x_ref) <= 1e-9 * np.linalg.norm(x_ref)
 
 
+@pytest.mark.parametrize("VAL,n,cycle", [(np.float64, [32, 32], 'V'), (np.complex128, [24, 24], 'W')])
+def test_coarsest_gmres_option(VAL, n, cycle):
+    """coarseSolveType = "GMRES" (MGsetup.jl:333-334, MGcycle.jl:152-168): one restart of fgmres(10) with the
+    Jacobi right preconditioner on the coarsest grid; per-cycle residual norms as the oracle."""
+    import multigrid_jl_b200 as mg
+    M = mg.getRegularMesh([0.0, 1.0, 0.0, 1.0], n)
+    if VAL == np.float64:
+        A = mg.poisson_shifted(M, 1e-4)
+    else:
+        A = mg.helmholtz_shifted(M, (2 * np.pi / (10 * M.h[0]) * 0.35) ** 2, 0.5)
+    AT = A.conj().T.tocsc()
+    AT.sort_indices()
+    p = mg.getMGparam(VAL, np.int64, 3, 8, 5, 1e-12, "Jac", 0.8, 2, 2, cycle, "GMRES")
+    mg.MGsetup(AT, M, p, 1)
+    rng = np.random.default_rng(2)
+    u = rng.random(A.shape[0]) + (1j * rng.random(A.shape[0]) if VAL == np.complex128 else 0)
+    b = (A @ u).astype(VAL)
+    b /= np.linalg.norm(b)
+    oc, o = _oracle(p)
+    _, it_ref, res_ref = oc.solveMG(o, b, np.zeros_like(b))
+    x = np.zeros_like(b)
+    _, _, it = mg.solveMG(p, b, x)
+    assert it == it_ref
+    np.testing.assert_allclose(p.last_resvec, res_ref, rtol=1e-8)
+    assert res_ref[-1] < 0.2 * res_ref[0]
+
+
 def test_jac_gmres_smoother():
     import multigrid_jl_b200 as mg
     A, AT, M, p, b = make_problem("poisson", [32, 32], 3, relax="Jac-GMRES", omega=0.75, pre=1, post=1, maxit=4)
@@ -142,6 +169,24 @@ def test_solveFGMRES_iteration_count(kind, n, levels, flexible):
     assert it == it_ref and p.last_flag == flag_ref
     assert len(res) == len(res_ref)
     np.testing.assert_allclose(res, res_ref, rtol=1e-7)
+    assert np.linalg.norm(b - A @ x) <= 1.01e-8 * np.linalg.norm(b)
+
+
+@pytest.mark.parametrize("kind,n,levels", [("poisson", [64, 64], 3), ("helmholtz", [48, 48], 3),
+                                           ("diffusion", [24, 24, 12], 3)])
+def test_solveBiCGSTAB_iteration_count(kind, n, levels):
+    """solveBiCGSTAB_MG -> KrylovMethods.bicgstb (SolveFuncs.jl:85-99): same iteration count, exit flag,
+    residual history and preconditioner count as the oracle."""
+    import multigrid_jl_b200 as mg
+    A, AT, M, p, b = make_problem(kind, n, levels, maxit=20, tol=1e-8)
+    oc, o = _oracle(p)
+    x_ref, it_ref, flag_ref, res_ref, nprec_ref = oc.solveBiCGSTAB_MG(AT, o, b, np.zeros_like(b))
+    x = np.zeros_like(b)
+    x, _, it, nprec = mg.solveBiCGSTAB_MG(AT, p, b, x)
+    assert it == it_ref and p.last_flag == flag_ref and flag_ref in (0, -3)
+    assert nprec == nprec_ref == 2 * it + (1 if flag_ref == -3 else 0)
+    assert len(p.last_resvec) == len(res_ref)
+    np.testing.assert_allclose(p.last_resvec, res_ref, rtol=1e-6)
     assert np.linalg.norm(b - A @ x) <= 1.01e-8 * np.linalg.norm(b)
 
 

@@ -165,3 +165,25 @@ def test_blockcg_matches_columnwise_solution():
     X, flag, rel, it, resmat = krylov.blockCG(Afun, b, X=np.zeros_like(b), tol=1e-10, maxIter=200)
     assert flag == 0
     np.testing.assert_allclose(Ad @ X, b, atol=2e-10)
+
+
+def test_oracle_bicgstb_solves_nonsymmetric_system():
+    """KrylovMethods.bicgstb restatement: converges on a nonsymmetric diagonally dominant system, with a
+    Jacobi M1 and without, and the returned history is the true relative residual."""
+    import scipy.sparse as sp
+    from oracle import krylov
+    rng = np.random.default_rng(5)
+    n = 400
+    A = sp.diags([-1.0 - 0.3 * rng.random(n - 1), 4.0 + rng.random(n), -1.0 + 0.3 * rng.random(n - 1)], [-1, 0, 1],
+                 format="csr")
+    b = rng.random(n)
+    d = 1.0 / A.diagonal()
+    for M1 in (None, lambda v: d * v):
+        x, flag, rel, it, res = krylov.bicgstb(lambda v: A @ v, b, tol=1e-10, maxIter=200, M1=M1)
+        assert flag in (0, -3) and it < 60
+        assert np.linalg.norm(b - A @ x) / np.linalg.norm(b) <= 2e-10
+        assert abs(res[-1] - np.linalg.norm(b - A @ x) / np.linalg.norm(b)) <= 1e-9
+    # b = 0 and an exact initial guess
+    assert krylov.bicgstb(lambda v: A @ v, np.zeros(n))[1] == -9
+    xs = np.linalg.solve(A.toarray(), b)
+    assert krylov.bicgstb(lambda v: A @ v, b, tol=1e-8, x=xs)[3] == 0
