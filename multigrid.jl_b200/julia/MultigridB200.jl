@@ -58,9 +58,15 @@ function uploadHierarchy(param::MGparam{VAL,Int64}; device::Integer=0) where {VA
                     d, 1))
     end
     AL = param.As[end]
-    check(ccall((:mgb200_upload_coarsest, libmgb200), Cint,
-                (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{VAL}, Cint),
-                h[], size(AL, 2), AL.colptr, AL.rowval, AL.nzval, 1))
+    if param.coarseSolveType == "GMRES"      # MGsetup.jl:333-334: param.LU holds the Jacobi weights
+        check(ccall((:mgb200_upload_coarsest_gmres, libmgb200), Cint,
+                    (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{VAL}, Ptr{VAL}, Cint),
+                    h[], size(AL, 2), AL.colptr, AL.rowval, AL.nzval, param.LU, 1))
+    else
+        check(ccall((:mgb200_upload_coarsest, libmgb200), Cint,
+                    (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{VAL}, Cint),
+                    h[], size(AL, 2), AL.colptr, AL.rowval, AL.nzval, 1))
+    end
     dev = DeviceHierarchy(h[])
     finalizer(d -> ccall((:mgb200_destroy, libmgb200), Cint, (Ptr{Cvoid},), d.handle), dev)
     return dev
@@ -99,6 +105,18 @@ function solveCG_MG(AT::SparseMatrixCSC{VAL,Int64}, param::MGparam{VAL,Int64}, d
                 (Ptr{Cvoid}, Ptr{VAL}, Ptr{VAL}, Cdouble, Cint, Ref{Cint}, Ref{Cint}, Ptr{Cdouble}),
                 dev.handle, b, x0, param.relativeTol, param.maxOuterIter, iter, flag, resvec))
     return x0, param, Int(iter[])
+end
+
+# ---- src/Multigrid/SolveFuncs.jl:85-99 ------------------------------------------------------------
+function solveBiCGSTAB_MG(AT::SparseMatrixCSC{VAL,Int64}, param::MGparam{VAL,Int64}, dev::DeviceHierarchy,
+                          b::Array{VAL}, x0::Array{VAL}, verbose::Bool=false) where {VAL}
+    check(ccall((:mgb200_adjust_nrhs, libmgb200), Cint, (Ptr{Cvoid}, Cint), dev.handle, size(b, 2)))
+    iter = Ref{Cint}(0); flag = Ref{Cint}(0); nprec = Ref{Cint}(0)
+    resvec = zeros(param.maxOuterIter + 1)
+    check(ccall((:mgb200_solveBiCGSTAB, libmgb200), Cint,
+                (Ptr{Cvoid}, Ptr{VAL}, Ptr{VAL}, Cdouble, Cint, Ref{Cint}, Ref{Cint}, Ptr{Cdouble}, Ref{Cint}),
+                dev.handle, b, x0, param.relativeTol, param.maxOuterIter, iter, flag, resvec, nprec))
+    return x0, param, Int(iter[]), Int(nprec[])
 end
 
 # ---- src/Multigrid/SolveFuncs.jl:120-132 ----------------------------------------------------------
