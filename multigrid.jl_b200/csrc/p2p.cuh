@@ -6,17 +6,23 @@
 // straight into each other's memory:
 //
 //   put   : every rank packs the rows its neighbours need and stores them THROUGH NVLINK into the
-//           neighbour's receive buffer (mapped with cudaIpcOpenMemHandle); the last CTA to finish
-//           publishes the exchange number in the neighbour's flag word (fence.sys + st.release.sys).
-//   wait  : the CTAs then poll the local flag words until every source has published this exchange
-//           and copy the receive buffer into the ghost rows of the vector.
+//           neighbour's receive buffer (mapped with cudaIpcOpenMemHandle) as self-validating 8-byte words:
+//           4 bytes of payload + the exchange number.
+//   get   : the same kernel then polls its own receive buffer word by word (the exchange number in the word says
+//           the payload has arrived) and writes the ghost rows of the vector.
 //
-// Put and wait are one ordinary kernel on the hierarchy's stream, so whole V/F/W cycles - exchanges included -
+// No fence, no flag, no ordering between words is needed - an aligned 8-byte store is single-copy atomic - so an
+// exchange costs one NVLink store latency instead of store + fence round trip + flag.  (First version of this
+// file: data, fence.sys, flag with st.release.sys, poll with ld.acquire.sys: 15-30 us per exchange at N = 4-8,
+// profiles/r01c_p2p_trace_n4.log.)
+//
+// Put and get are one ordinary kernel on the hierarchy's stream, so whole V/F/W cycles - exchanges included -
 // are captured into one CUDA graph per rank.  The exchange number lives in device memory and is
-// advanced by the put kernel itself (a replayed graph cannot carry it as a launch argument).
+// advanced by the kernel itself (a replayed graph cannot carry it as a launch argument).
 // Receive buffers are double-buffered on the parity of the exchange number: a rank can only start
-// put e+2 after its wait e+1, i.e. after the neighbour's put e+1, which follows the neighbour's
-// wait e in stream order - so buffer (e mod 2) is free again.
+// exchange e+2 after its exchange e+1 completed, i.e. after the neighbour's put e+1, which follows the
+// neighbour's get e in stream order - so buffer (e mod 2) is free again, and the words it still holds carry
+// exchange number e, never e+2.
 //
 // One channel per distributed level (halo of that level's vectors) and one for the gather of the
 // first replicated level (every rank restricts its own coarse rows and broadcasts the piece).
@@ -48,61 +54,66 @@ struct ChanDev {
     int world, rank;
 };
 
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
+// ---- LL ("low latency") words: every 8-byte word carries 4 bytes of payload and the exchange number ----------
+// An aligned 8-byte store is single-copy atomic, also across NVLink, so the receiver can poll the word itself:
+// no fence, no separate flag, no ordering between words.  (The same idea as NCCL's LL protocol.)  A double
+// travels as two words, a complex number as four; the receive buffers are twice the size of the data.
+__device__ __forceinline__ void st_ll(unsigned long long* p, unsigned lo, unsigned flag) {
+    const unsigned long long w = (unsigned long long)lo | ((unsigned long long)flag << 32);
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
 }
-// receive buffers are written by the peer: read them around L1
-__device__ __forceinline__ double ld_cv(const double* p) { return __ldcv(p); }
-__device__ __forceinline__ cplx ld_cv(const cplx* p) {
-    const double2 v = __ldcv(reinterpret_cast<const double2*>(p));
-    return make_cplx(v.x, v.y);
+__device__ __forceinline__ unsigned ld_ll(const unsigned long long* p, unsigned flag) {
+    unsigned long long w;
+    do {
+        asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+    } while ((unsigned)(w >> 32) != flag);
+    return (unsigned)w;
 }
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+template <typename TV>
+struct LL;
+template <>
+struct LL<double> {
+    static constexpr int W = 2;   // words per element
+    __device__ static __forceinline__ void put(unsigned long long* dst, double v, unsigned flag) {
+        st_ll(dst, (unsigned)__double2loint(v), flag);
+        st_ll(dst + 1, (unsigned)__double2hiint(v), flag);
+    }
+    __device__ static __forceinline__ double get(const unsigned long long* src, unsigned flag) {
+        const unsigned lo = ld_ll(src, flag), hi = ld_ll(src + 1, flag);
+        return __hiloint2double((int)hi, (int)lo);
+    }
+};
+template <>
+struct LL<cplx> {
+    static constexpr int W = 4;
+    __device__ static __forceinline__ void put(unsigned long long* dst, cplx v, unsigned flag) {
+        LL<double>::put(dst, v.x, flag);
+        LL<double>::put(dst + 2, v.y, flag);
+    }
+    __device__ static __forceinline__ cplx get(const unsigned long long* src, unsigned flag) {
+        const double a = LL<double>::get(src, flag), b = LL<double>::get(src + 2, flag);
+        return make_cplx(a, b);
+    }
+};
+
+// The exchange number is advanced by the last CTA to finish (every CTA has read it by then).
+__device__ __forceinline__ void p2p_advance(unsigned long long e, unsigned long long* epoch, unsigned* ticket) {
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1) *epoch = e;
 }
 
-// Publish exchange number e to every destination once ALL CTAs of the kernel have stored their rows: every CTA
-// orders its stores with one system-scope fence behind a CTA barrier and takes a ticket; the last one publishes.
-template <typename TV>
-__device__ __forceinline__ void p2p_publish(const ChanDev<TV>* cd, unsigned long long e, unsigned long long* epoch,
-                                            unsigned* ticket, bool bcast) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        if (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1) {
-            __threadfence_system();
-            for (int q = 0; q < cd->world; ++q) {
-                if (q == cd->rank) continue;
-                if (bcast || cd->send_off[q + 1] > cd->send_off[q]) st_release_sys(cd->flag_dst[q], e);
-            }
-            *epoch = e;
-        }
-    }
-}
-// Wait until every source has published exchange e (one polling thread per CTA, then a CTA barrier).
-template <typename TV>
-__device__ __forceinline__ void p2p_wait(const ChanDev<TV>* cd, unsigned long long e) {
-    if (threadIdx.x == 0) {
-        for (int p = 0; p < cd->world; ++p)
-            if (p != cd->rank && cd->recv_cnt[p] > 0)
-                while (ld_acquire_sys(cd->flag_src[p]) < e) {
-                }
-    }
-    __syncthreads();
-}
-
-// Halo exchange in one kernel: put (gather the owned rows the peers asked for and store them into the peers'
-// buffers), publish, wait for the peers' rows, unpack ghost g of the receive buffer to row ghost_pos(g).
-// The grid is small (<= 64 CTAs), so all CTAs are resident and the polling CTAs cannot starve the publisher.
+// Halo exchange in one kernel: gather the owned rows the peers asked for and store them as LL words straight into
+// the peers' receive buffers (through NVLink); then poll the own receive buffer word by word and write ghost g to
+// row ghost_pos(g).  The grid is small (<= 64 CTAs), all CTAs are resident, nobody waits on another CTA.
 template <typename TV>
 __global__ void p2p_halo_kernel(const ChanDev<TV>* __restrict__ cd, TV* __restrict__ v,
                                 const int* __restrict__ send_idx, int n_send, long long n_ghost, long long n_lo,
                                 long long n_owned, int m, unsigned long long* epoch, unsigned* ticket,
                                 unsigned long long* trace) {
+    constexpr int W = LL<TV>::W;
     const unsigned long long e = *epoch + 1;
     const int par = (int)(e & 1);
+    const unsigned flag = (unsigned)e;
     const bool tr = trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
     unsigned long long* trow = trace + (e % P2P_TRACE_ROWS) * 4;
     if (tr) trow[0] = globaltimer_ns();
@@ -112,47 +123,47 @@ __global__ void p2p_halo_kernel(const ChanDev<TV>* __restrict__ cd, TV* __restri
         const int i = (int)(t / m), j = (int)(t % m);
         int q = 0;
         while (i >= cd->send_off[q + 1]) ++q;
-        cd->dst[par][q][(long long)(i - cd->send_off[q]) * m + j] = v[(long long)send_idx[i] * m + j];
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(cd->dst[par][q]);
+        LL<TV>::put(dst + ((long long)(i - cd->send_off[q]) * m + j) * W, v[(long long)send_idx[i] * m + j], flag);
     }
-    p2p_publish(cd, e, epoch, ticket, false);
     if (tr) trow[1] = globaltimer_ns();
-    p2p_wait(cd, e);
-    if (tr) trow[2] = globaltimer_ns();
-    const TV* rb = cd->rbuf[par];
+    const unsigned long long* rb = reinterpret_cast<const unsigned long long*>(cd->rbuf[par]);
     const long long tot2 = n_ghost * m;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < tot2;
          t += (long long)gridDim.x * blockDim.x) {
         const long long g = t / m;
         const int j = (int)(t % m);
         const long long pos = g < n_lo ? g - n_lo : n_owned + (g - n_lo);
-        v[pos * m + j] = ld_cv(rb + t);
+        v[pos * m + j] = LL<TV>::get(rb + t * W, flag);
     }
-    if (tr) trow[3] = globaltimer_ns();
+    if (tr) trow[2] = trow[3] = globaltimer_ns();
+    p2p_advance(e, epoch, ticket);
 }
 
 // Gather of a replicated vector in one kernel: my piece v[off .. off+cnt) (element units) goes to the same place
-// of every peer's buffer; after the wait the pieces of the other ranks are copied out of my buffer.
+// of every peer's buffer; the pieces of the other ranks are polled out of my buffer (same layout as v).
 template <typename TV>
 __global__ void p2p_gather_kernel(const ChanDev<TV>* __restrict__ cd, TV* __restrict__ v, long long off,
                                   long long cnt, int m, unsigned long long* epoch, unsigned* ticket) {
+    constexpr int W = LL<TV>::W;
     const unsigned long long e = *epoch + 1;
     const int par = (int)(e & 1);
+    const unsigned flag = (unsigned)e;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < cnt;
          t += (long long)gridDim.x * blockDim.x) {
         const TV val = v[off + t];
         for (int q = 0; q < cd->world; ++q)
-            if (q != cd->rank) cd->dst[par][q][t] = val;
+            if (q != cd->rank) LL<TV>::put(reinterpret_cast<unsigned long long*>(cd->dst[par][q]) + t * W, val, flag);
     }
-    p2p_publish(cd, e, epoch, ticket, true);
-    p2p_wait(cd, e);
-    const TV* rb = cd->rbuf[par];
+    const unsigned long long* rb = reinterpret_cast<const unsigned long long*>(cd->rbuf[par]);
     for (int p = 0; p < cd->world; ++p) {
         if (p == cd->rank) continue;
         const long long o = (long long)cd->recv_off[p] * m, c = (long long)cd->recv_cnt[p] * m;
         for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < c;
              t += (long long)gridDim.x * blockDim.x)
-            v[o + t] = ld_cv(rb + o + t);
+            v[o + t] = LL<TV>::get(rb + (o + t) * W, flag);
     }
+    p2p_advance(e, epoch, ticket);
 }
 
 // host side of one channel

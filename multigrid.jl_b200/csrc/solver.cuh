@@ -586,7 +586,9 @@ struct Hierarchy : HierarchyBase {
             // put into the neighbours' receive buffers over NVLink, then wait for theirs and unpack (p2p.cuh)
             ChanDev<TV>* cd = static_cast<ChanDev<TV>*>(p2p.chan[l].dev);
             const long long work = std::max<long long>((long long)sp.n_send, sp.n_ghost) * m;
-            const int g = (int)std::max<long long>(1, std::min<long long>((work + 1023) / 1024, 64));
+            // no CTA of this kernel waits on another one (they poll words written by the peers), so the grid may
+            // be as wide as the copy needs
+            const int g = (int)std::max<long long>(1, std::min<long long>((work + 511) / 512, 2LL * ctx.sm_count));
             p2p_halo_kernel<TV><<<g, 256, 0, ctx.stream>>>(cd, v, sp.d_send_idx, sp.n_send, sp.n_ghost, sp.n_lo,
                                                             sp.n_owned, m, p2p.epoch + l, p2p.ticket + l,
                                                             p2p.trace ? p2p.trace + (size_t)l * P2P_TRACE_ROWS * 4 : nullptr);
@@ -615,7 +617,7 @@ struct Hierarchy : HierarchyBase {
         if (p2p.on && p2p.gather_level == l) {
             ChanDev<TV>* cd = static_cast<ChanDev<TV>*>(p2p.chan[levels].dev);
             const long long off = offs[comm.rank] * m, cnt = (offs[comm.rank + 1] - offs[comm.rank]) * m;
-            const int g = (int)std::max<long long>(1, std::min<long long>((L[l].n * m + 1023) / 1024, 64));
+            const int g = (int)std::max<long long>(1, std::min<long long>((L[l].n * m + 511) / 512, 2LL * ctx.sm_count));
             p2p_gather_kernel<TV><<<g, 256, 0, ctx.stream>>>(cd, v, off, cnt, m, p2p.epoch + levels, p2p.ticket + levels);
             MGB_LAUNCH_CHECK();
             return;
@@ -672,9 +674,8 @@ struct Hierarchy : HierarchyBase {
                 ++cnt;
             }
             if (cnt)
-                std::fprintf(stderr, "[mgb200 p2p trace] rank %d level %d: %d exchanges, put+publish %.2f us, wait %.2f us, "
-                             "unpack %.2f us (CTA 0)\n", comm.rank, l + 1, cnt, put / cnt * 1e-3, wait / cnt * 1e-3,
-                             unpack / cnt * 1e-3);
+                std::fprintf(stderr, "[mgb200 p2p trace] rank %d level %d: %d exchanges, put %.2f us, poll + unpack %.2f us "
+                             "(CTA 0)\n", comm.rank, l + 1, cnt, put / cnt * 1e-3, (wait + unpack) / cnt * 1e-3);
         }
         dev_free(p2p.trace);
     }
@@ -711,7 +712,7 @@ struct Hierarchy : HierarchyBase {
             if (!c.used) continue;
             for (int par = 0; par < 2; ++par) {
                 c.buf_off[par] = off;
-                off += align((size_t)std::max<long long>(c.rows, 1) * m * sizeof(TV));
+                off += align((size_t)std::max<long long>(c.rows, 1) * m * sizeof(TV) * 2);   // LL words: 2x the data
             }
         }
         p2p.block_bytes = off;
@@ -787,8 +788,8 @@ struct Hierarchy : HierarchyBase {
             for (int q = 0; q < w; ++q) {
                 const long long* tq = T(q) + 9 + per_chan * c;
                 const long long land = gather ? lg.coarse_row_offsets[r] : tq[2 + r];
-                for (int par = 0; par < 2; ++par)
-                    cd.dst[par][q] = reinterpret_cast<TV*>(p2p.peer[q] + tq[par]) + land * m;
+                for (int par = 0; par < 2; ++par)   // landing zone in LL words (2 x sizeof(TV) bytes per element)
+                    cd.dst[par][q] = reinterpret_cast<TV*>(p2p.peer[q] + tq[par] + (size_t)land * m * sizeof(TV) * 2);
                 cd.flag_dst[q] = reinterpret_cast<unsigned long long*>(p2p.peer[q]) + (size_t)c * P2P_MAXW + r;
                 cd.flag_src[q] = reinterpret_cast<const unsigned long long*>(p2p.block) + (size_t)c * P2P_MAXW + q;
                 if (gather) {
