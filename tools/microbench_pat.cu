@@ -618,6 +618,277 @@ __global__ void __launch_bounds__(256) k_uniform(const __grid_constant__ Params 
     y[row] = xv + dv * (bv - acc);
 }
 
+
+// V13: V10 + the entries of the DOMINANT pattern (the interior stencil) live in registers: rows that carry it need
+// no dictionary access at all - NE shared-memory gathers, NE products.  Other rows walk the shared dictionary.
+template <int NE, int STAGES, int NT>
+__global__ void __launch_bounds__(NT) k_pipe_reg(const __grid_constant__ ParamsT P, int pstar, int n, int nent, int ntiles,
+                                                 int vlo, int vhi, const uint16_t* __restrict__ pid,
+                                                 const Ent* __restrict__ gent, const double* __restrict__ x,
+                                                 const double* __restrict__ b, double* __restrict__ y) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+    Ent* se = reinterpret_cast<Ent*>(smem_raw + 64);
+    int* sh = reinterpret_cast<int*>(se + MAXE);
+    double* sd = reinterpret_cast<double*>(sh + MAXP);
+    unsigned char* stage0 = reinterpret_cast<unsigned char*>(sd + MAXP);
+    const int ext = NT - 256;
+    const int wtotal = P.total + P.nwin * ext;
+    const int stage_bytes = (wtotal + NT) * 8 + NT * 2;
+    const int t = threadIdx.x;
+    if (t == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(full + s, 1);
+        fence_mbar_init();
+    }
+    for (int i = t; i < nent; i += NT) {
+        Ent e = gent[i];
+        int g = 0;
+        while (g + 1 < P.nwin && e.delta >= P.w[g + 1].sbase) ++g;
+        e.delta += g * ext;
+        se[i] = e;
+    }
+    if (t < MAXP) { sh[t] = P.hdr[t]; sd[t] = P.dp[t]; }
+    int gc = 0;
+    while (gc + 1 < P.nwin && P.w[gc + 1].lo_even <= 0) ++gc;
+    const int coff = P.centre + gc * ext;
+    __syncthreads();
+    double ev[NE];
+    int ed[NE];
+    {
+        const int k0 = sh[pstar] & 0xFFFFF;
+#pragma unroll
+        for (int k = 0; k < NE; ++k) {
+            ev[k] = se[k0 + k].v;
+            ed[k] = se[k0 + k].delta;
+        }
+    }
+    const double dstar = sd[pstar];
+    auto issue = [&](int tile, int s) {
+        double* sx = reinterpret_cast<double*>(stage0 + (size_t)s * stage_bytes);
+        double* sb = sx + wtotal;
+        uint16_t* sp = reinterpret_cast<uint16_t*>(sb + NT);
+        const int row0 = tile * NT;
+        uint32_t bytes = 0;
+        for (int g = 0; g < P.nwin; ++g) {
+            const int s0 = row0 + P.w[g].lo_even, a = max(s0, vlo), e = min(s0 + P.w[g].len + ext, vhi);
+            if (e > a) bytes += (uint32_t)(e - a) * 8u;
+        }
+        const int be = min(row0 + NT, vhi), pe = min(row0 + NT, (n + 7) & ~7);
+        bytes += (uint32_t)(be - row0) * 8u + (uint32_t)(pe - row0) * 2u;
+        mbar_expect_tx(full + s, bytes);
+        for (int g = 0; g < P.nwin; ++g) {
+            const int s0 = row0 + P.w[g].lo_even, a = max(s0, vlo), e = min(s0 + P.w[g].len + ext, vhi);
+            if (e > a) bulk_g2s(sx + P.w[g].sbase + g * ext + (a - s0), x + a, (uint32_t)(e - a) * 8u, full + s);
+        }
+        bulk_g2s(sb, b + row0, (uint32_t)(be - row0) * 8u, full + s);
+        bulk_g2s(sp, pid + row0, (uint32_t)(pe - row0) * 2u, full + s);
+    };
+    if (t == 0) {
+        for (int i = 0; i < STAGES - 1; ++i) {
+            const int tile = blockIdx.x + i * gridDim.x;
+            if (tile < ntiles) issue(tile, i);
+        }
+    }
+    int i = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+        const int s = i % STAGES;
+        if (t == 0) {
+            const int nt = tile + (STAGES - 1) * gridDim.x;
+            if (nt < ntiles) issue(nt, (i + STAGES - 1) % STAGES);
+        }
+        mbar_wait(full + s, (i / STAGES) & 1);
+        const double* sx = reinterpret_cast<const double*>(stage0 + (size_t)s * stage_bytes);
+        const double* sb = sx + wtotal;
+        const uint16_t* sp = reinterpret_cast<const uint16_t*>(sb + NT);
+        const int row = tile * NT + t;
+        if (row < n) {
+            const int p = sp[t];
+            const double* sxt = sx + t;
+            double acc = 0.0, dv;
+            if (p == pstar) {
+                dv = dstar;
+#pragma unroll
+                for (int k = 0; k < NE; ++k) acc = acc + ev[k] * sxt[ed[k]];
+            } else {
+                const int h = sh[p], k0 = h & 0xFFFFF, k1 = k0 + (h >> 20);
+                dv = sd[p];
+                for (int k = k0; k < k1; ++k) {
+                    const Ent e = se[k];
+                    acc = acc + e.v * sxt[e.delta];
+                }
+            }
+            y[row] = sxt[coff] + dv * (sb[t] - acc);
+        }
+        __syncthreads();
+    }
+}
+
+
+// V14: warp-specialised TMA pipeline: one producer warp issues the bulk copies and waits on "empty" barriers, the NT
+// consumer threads wait on "full", compute one row each and release the stage per warp - no CTA-wide barrier.
+// NE > 0: the dominant pattern's entries live in registers (V13); NE == 0: shared dictionary only.
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+template <int NE, int STAGES, int NT>
+__global__ void __launch_bounds__(NT + 32) k_ws(const __grid_constant__ ParamsT P, int pstar, int n, int nent, int ntiles,
+                                                int vlo, int vhi, const uint16_t* __restrict__ pid,
+                                                const Ent* __restrict__ gent, const double* __restrict__ x,
+                                                const double* __restrict__ b, double* __restrict__ y) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* empty = full + 8;
+    Ent* se = reinterpret_cast<Ent*>(smem_raw + 128);
+    int* sh = reinterpret_cast<int*>(se + MAXE);
+    double* sd = reinterpret_cast<double*>(sh + MAXP);
+    unsigned char* stage0 = reinterpret_cast<unsigned char*>(sd + MAXP);
+    const int ext = NT - 256;
+    const int wtotal = P.total + P.nwin * ext;
+    const int stage_bytes = (wtotal + NT) * 8 + NT * 2;
+    const int t = threadIdx.x;
+    if (t == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, NT / 32);
+        }
+        fence_mbar_init();
+    }
+    for (int i = t; i < nent; i += NT + 32) {
+        Ent e = gent[i];
+        int g = 0;
+        while (g + 1 < P.nwin && e.delta >= P.w[g + 1].sbase) ++g;
+        e.delta += g * ext;
+        se[i] = e;
+    }
+    if (t < MAXP) { sh[t] = P.hdr[t]; sd[t] = P.dp[t]; }
+    __syncthreads();
+    if (t >= NT) {                       // ---- producer warp ----
+        if (t == NT) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int s = it % STAGES;
+                if (it >= STAGES) mbar_wait(empty + s, ((it / STAGES) - 1) & 1);
+                double* sx = reinterpret_cast<double*>(stage0 + (size_t)s * stage_bytes);
+                double* sb = sx + wtotal;
+                uint16_t* sp = reinterpret_cast<uint16_t*>(sb + NT);
+                const int row0 = tile * NT;
+                uint32_t bytes = 0;
+                for (int g = 0; g < P.nwin; ++g) {
+                    const int s0 = row0 + P.w[g].lo_even, a = max(s0, vlo), e = min(s0 + P.w[g].len + ext, vhi);
+                    if (e > a) bytes += (uint32_t)(e - a) * 8u;
+                }
+                const int be = min(row0 + NT, vhi), pe = min(row0 + NT, (n + 7) & ~7);
+                bytes += (uint32_t)(be - row0) * 8u + (uint32_t)(pe - row0) * 2u;
+                mbar_expect_tx(full + s, bytes);
+                for (int g = 0; g < P.nwin; ++g) {
+                    const int s0 = row0 + P.w[g].lo_even, a = max(s0, vlo), e = min(s0 + P.w[g].len + ext, vhi);
+                    if (e > a) bulk_g2s(sx + P.w[g].sbase + g * ext + (a - s0), x + a, (uint32_t)(e - a) * 8u, full + s);
+                }
+                bulk_g2s(sb, b + row0, (uint32_t)(be - row0) * 8u, full + s);
+                bulk_g2s(sp, pid + row0, (uint32_t)(pe - row0) * 2u, full + s);
+            }
+        }
+        return;
+    }
+    // ---- consumers ----
+    int gc = 0;
+    while (gc + 1 < P.nwin && P.w[gc + 1].lo_even <= 0) ++gc;
+    const int coff = P.centre + gc * ext;
+    constexpr int NR = NE > 0 ? NE : 1;
+    double ev[NR];
+    int ed[NR];
+    double dstar = 0.0;
+    if (NE > 0) {
+        const int k0 = sh[pstar] & 0xFFFFF;
+#pragma unroll
+        for (int k = 0; k < NR; ++k) {
+            ev[k] = se[k0 + k].v;
+            ed[k] = se[k0 + k].delta;
+        }
+        dstar = sd[pstar];
+    }
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(full + s, (it / STAGES) & 1);
+        const double* sx = reinterpret_cast<const double*>(stage0 + (size_t)s * stage_bytes);
+        const double* sb = sx + wtotal;
+        const uint16_t* sp = reinterpret_cast<const uint16_t*>(sb + NT);
+        const int row = tile * NT + t;
+        double out = 0.0;
+        if (row < n) {
+            const int p = sp[t];
+            const double* sxt = sx + t;
+            double acc = 0.0, dv;
+            if (NE > 0 && p == pstar) {
+                dv = dstar;
+#pragma unroll
+                for (int k = 0; k < NR; ++k) acc = acc + ev[k] * sxt[ed[k]];
+            } else {
+                const int h = sh[p], k0 = h & 0xFFFFF, k1 = k0 + (h >> 20);
+                dv = sd[p];
+#pragma unroll 4
+                for (int k = k0; k < k1; ++k) {
+                    const Ent e = se[k];
+                    acc = acc + e.v * sxt[e.delta];
+                }
+            }
+            out = sxt[coff] + dv * (sb[t] - acc);
+        }
+        __syncwarp();
+        if ((t & 31) == 0) mbar_arrive(empty + s);   // this warp is done reading stage s
+        if (row < n) y[row] = out;
+    }
+}
+
+
+// V15: no shared memory, no TMA: persistent grid-stride threads keep the entries of the dominant pattern in
+// registers and issue its NE gathers back to back (NE is a compile-time constant, so the loads are batched);
+// rows with another pattern read the global dictionary per lane.
+template <int NE, int NT>
+__global__ void __launch_bounds__(NT) k_regdirect(int pstar, int n, const uint16_t* __restrict__ pid,
+                                                  const int* __restrict__ hdr, const Ent* __restrict__ ent,
+                                                  const double* __restrict__ dp, const double* __restrict__ x,
+                                                  const double* __restrict__ b, double* __restrict__ y) {
+    double ev[NE];
+    int ed[NE];
+    {
+        const int k0 = __ldg(hdr + pstar) & 0xFFFFF;
+#pragma unroll
+        for (int k = 0; k < NE; ++k) {
+            const Ent e = ldg_ent(ent + k0 + k);
+            ev[k] = e.v;
+            ed[k] = e.delta;
+        }
+    }
+    const double dstar = __ldg(dp + pstar);
+    for (int row = blockIdx.x * NT + threadIdx.x; row < n; row += gridDim.x * NT) {
+        const int p = pid[row];
+        const double bv = b[row];
+        const double* xr = x + row;
+        double acc = 0.0, dv, xc;
+        if (p == pstar) {
+            double xv[NE];
+#pragma unroll
+            for (int k = 0; k < NE; ++k) xv[k] = __ldg(xr + ed[k]);
+            xc = __ldg(xr);
+#pragma unroll
+            for (int k = 0; k < NE; ++k) acc = acc + ev[k] * xv[k];
+            dv = dstar;
+        } else {
+            const int h = __ldg(hdr + p), k0 = h & 0xFFFFF, k1 = k0 + (h >> 20);
+            dv = __ldg(dp + p);
+            xc = __ldg(xr);
+#pragma unroll 4
+            for (int k = k0; k < k1; ++k) {
+                const Ent e = ldg_ent(ent + k);
+                acc = acc + e.v * __ldg(xr + e.delta);
+            }
+        }
+        y[row] = xc + dv * (bv - acc);
+    }
+}
+
 // pure streaming reference: y = x + d*(b - x) with the same vector traffic and the pid read (HBM floor)
 __global__ void __launch_bounds__(256) k_stream(int n, const uint16_t* __restrict__ pid, const double* __restrict__ dp,
                                                 const double* __restrict__ x, const double* __restrict__ b,
@@ -750,7 +1021,8 @@ int main(int argc, char** argv) {
         CK(cudaMalloc(&dentT, MAXE * sizeof(Ent)));
         CK(cudaMemcpy(dentT, PT->e, MAXE * sizeof(Ent), cudaMemcpyHostToDevice));
         CK(cudaFuncSetAttribute(k_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
-        const char* names[] = {"global LDG.128", "smem LDS.128", "smem split", "kernel params (LDC)", "warp shuffle", "__constant__", "stream floor", "TMA windows + LDC", "TMA pipeline 2 stages", "TMA pipeline 3 stages", "TMA pipeline 4 stages", "TMA + smem dict, 2 rows/thr", "TMA + smem dict, 4 rows/thr", "TMA + smem dict, 8 rows/thr", "persist 2st x 1024thr", "persist 3st x 1024thr", "persist 3st x 512thr", "persist 4st x 512thr", "persist 3st x 256thr", "persist 2st 256thr x4 rows", "persist 3st 256thr x4 rows", "persist 2st 512thr x2 rows", "persist 2st 512thr x4 rows", "uniform datapath dict"};
+        const char* names[] = {"global LDG.128", "smem LDS.128", "smem split", "kernel params (LDC)", "warp shuffle", "__constant__", "stream floor", "TMA windows + LDC", "TMA pipeline 2 stages", "TMA pipeline 3 stages", "TMA pipeline 4 stages", "TMA + smem dict, 2 rows/thr", "TMA + smem dict, 4 rows/thr", "TMA + smem dict, 8 rows/thr", "persist 2st x 1024thr", "persist 3st x 1024thr", "persist 3st x 512thr", "persist 4st x 512thr", "persist 3st x 256thr", "persist 2st 256thr x4 rows", "persist 3st 256thr x4 rows", "persist 2st 512thr x2 rows", "persist 2st 512thr x4 rows", "uniform datapath dict", "reg stencil 2st x 1024thr", "reg stencil 2st x 512thr", "reg stencil 3st x 512thr", "reg stencil 3st x 256thr", "warp-spec dict 2st x 960", "warp-spec dict 3st x 512", "warp-spec dict 4st x 256", "warp-spec reg 2st x 960", "warp-spec reg 3st x 512", "warp-spec reg 4st x 256", "reg direct 256thr x2/SM", "reg direct 256thr x4/SM", "reg direct 256thr x8/SM", "reg direct 128thr x8/SM", "reg direct 1 row/thread"};
+
         ParamsT* PR[4]; Ent* dentR[4]; size_t smR[4]; int gR[4];
         const int cfgR[4][3] = {{2, 256, 4}, {3, 256, 4}, {2, 512, 2}, {2, 512, 4}};
         for (int c = 0; c < 4; ++c) {
@@ -798,8 +1070,33 @@ int main(int argc, char** argv) {
         CK(cudaFuncSetAttribute(k_tma_pipe<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
         CK(cudaFuncSetAttribute(k_tma_pipe<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4));
         printf("pipeline: stage %zu B, grids %d/%d/%d\n", stage_b, g2, g3, g4);
+        auto reg_launch = [&](int st, int nt) {
+            const size_t sm = ps_smem(st, nt);
+            const int gr = ps_grid(st, nt), ntl = (n + nt - 1) / nt;
+#define RL(NE, ST, NT_) { static bool once = false; if (!once) { CK(cudaFuncSetAttribute(k_pipe_reg<NE, ST, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); once = true; } \
+                k_pipe_reg<NE, ST, NT_><<<gr, NT_, sm>>>(*PT, 13, n, nent, ntl, 0, (n + 1) & ~1, dpid, dentT, dx, db, dy); }
+            if (pts == 7) {
+                if (st == 2 && nt == 1024) RL(7, 2, 1024) else if (st == 2 && nt == 512) RL(7, 2, 512) else if (st == 3 && nt == 512) RL(7, 3, 512) else RL(7, 3, 256)
+            } else {
+                if (st == 2 && nt == 1024) RL(27, 2, 1024) else if (st == 2 && nt == 512) RL(27, 2, 512) else if (st == 3 && nt == 512) RL(27, 3, 512) else RL(27, 3, 256)
+            }
+#undef RL
+        };
+        auto ws_launch = [&](int ne, int st, int nt) {
+            const size_t sm = ps_smem(st, nt) + 128;
+            int per = (int)std::min<size_t>(2048 / (nt + 32), (220 * 1024) / sm);
+            if (per < 1) per = 1;
+            const int ntl = (n + nt - 1) / nt, gr = std::min(ntl, nsm * per);
+#define WL(NE, ST, NT_) { static bool once = false; if (!once) { CK(cudaFuncSetAttribute(k_ws<NE, ST, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); once = true; } \
+                k_ws<NE, ST, NT_><<<gr, NT_ + 32, sm>>>(*PT, 13, n, nent, ntl, 0, (n + 1) & ~1, dpid, dentT, dx, db, dy); }
+            if (ne == 0) { if (st == 3 && nt == 512) WL(0, 3, 512) else if (st == 4 && nt == 256) WL(0, 4, 256) else WL(0, 2, 960) }
+            else if (pts == 7) { if (st == 3 && nt == 512) WL(7, 3, 512) else if (st == 4 && nt == 256) WL(7, 4, 256) else WL(7, 2, 960) }
+            else { if (st == 3 && nt == 512) WL(27, 3, 512) else if (st == 4 && nt == 256) WL(27, 4, 256) else WL(27, 2, 960) }
+#undef WL
+        };
         std::vector<double> href(n), hy(n);
-        for (int v = 0; v < 24; ++v) {
+        for (int v = 0; v < 39; ++v) {
+            if (v >= 15 && v <= 33) continue;
             if (v >= 14 && v <= 22 && v != 14 && v != 21) continue;
             if (v >= 1 && v <= 5) continue;
             if (v >= 7 && v <= 10) continue;
@@ -829,6 +1126,21 @@ int main(int argc, char** argv) {
                     case 21: k_pipe_rpt<2, 512, 2><<<gR[2], 512, smR[2]>>>(*PR[2], n, nent, (n + 1023) / 1024, 0, (n + 1) & ~1, dpid, dentR[2], dx, db, dy); break;
                     case 22: k_pipe_rpt<2, 512, 4><<<gR[3], 512, smR[3]>>>(*PR[3], n, nent, (n + 2047) / 2048, 0, (n + 1) & ~1, dpid, dentR[3], dx, db, dy); break;
                     case 23: k_uniform<<<grid, 256>>>(*P, n, dpid, dhdr, dent, ddp, dx, db, dy); break;
+                    case 24: reg_launch(2, 1024); break;
+                    case 25: reg_launch(2, 512); break;
+                    case 26: reg_launch(3, 512); break;
+                    case 27: reg_launch(3, 256); break;
+                    case 28: ws_launch(0, 2, 960); break;
+                    case 29: ws_launch(0, 3, 512); break;
+                    case 30: ws_launch(0, 4, 256); break;
+                    case 31: ws_launch(1, 2, 960); break;
+                    case 32: ws_launch(1, 3, 512); break;
+                    case 33: ws_launch(1, 4, 256); break;
+                    case 34: if (pts == 7) k_regdirect<7, 256><<<nsm * 2, 256>>>(13, n, dpid, dhdr, dent, ddp, dx, db, dy); else k_regdirect<27, 256><<<nsm * 2, 256>>>(13, n, dpid, dhdr, dent, ddp, dx, db, dy); break;
+                    case 35: if (pts == 7) k_regdirect<7, 256><<<nsm * 4, 256>>>(13, n, dpid, dhdr, dent, ddp, dx, db, dy); else k_regdirect<27, 256><<<nsm * 4, 256>>>(13, n, dpid, dhdr, dent, ddp, dx, db, dy); break;
+                    case 36: if (pts == 7) k_regdirect<7, 256><<<nsm * 8, 256>>>(13, n, dpid, dhdr, dent, ddp, dx, db, dy); else k_regdirect<27, 256><<<nsm * 8, 256>>>(13, n, dpid, dhdr, dent, ddp, dx, db, dy); break;
+                    case 37: if (pts == 7) k_regdirect<7, 128><<<nsm * 8, 128>>>(13, n, dpid, dhdr, dent, ddp, dx, db, dy); else k_regdirect<27, 128><<<nsm * 8, 128>>>(13, n, dpid, dhdr, dent, ddp, dx, db, dy); break;
+                    case 38: if (pts == 7) k_regdirect<7, 256><<<grid, 256>>>(13, n, dpid, dhdr, dent, ddp, dx, db, dy); else k_regdirect<27, 256><<<grid, 256>>>(13, n, dpid, dhdr, dent, ddp, dx, db, dy); break;
                     case 10: k_tma_pipe<4><<<g4, 256, sm4>>>(*PT, n, ntiles, 0, (n + 1) & ~1, dpid, dx, db, dy); break;
                 }
             };
