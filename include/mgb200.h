@@ -194,7 +194,8 @@ int mgb200_pattern_info(mgb200_handle h, int level, int which, int64_t* out);
 
 /* Runtime options: "patterns" (1/0: use the stencil dictionary where available; set before upload to skip
  * building it), "graphs" (1/0: replay V/F/W cycles from CUDA graphs), "smem_budget" (bytes per CTA used when
- * choosing the rows per CTA of the CSR-stream kernel at upload). */
+ * choosing the rows per CTA of the CSR-stream kernel at upload), "tma" (1/0: TMA-staged persistent variant of the
+ * dictionary kernel for square stencil operators), "tma_min_rows" (matrices with fewer rows keep the one-pass kernel). */
 int mgb200_set_option(mgb200_handle h, const char* key, int64_t value);
 
 /* Host-only (no GPU): the row deduplication behind the stencil dictionary, exported for the CPU test-suite.

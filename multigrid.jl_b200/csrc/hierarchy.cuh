@@ -42,10 +42,14 @@ static PaddedRegistry& padded_registry() {
     static PaddedRegistry r;
     return r;
 }
+// Every vector carries 4 elements of zeroed slack and starts on a 16-byte boundary (pad rounded up to an even
+// element count), so that the bulk copies of the TMA kernels may round their ranges outwards to even elements.
+static inline size_t even_pad(size_t pad) { return (pad + 1) & ~(size_t)1; }
 template <typename T>
 static T* vec_alloc(size_t total, size_t pad, cudaStream_t stream) {
-    T* b = dev_alloc<T>(total);
-    MGB_CUDA(cudaMemsetAsync(b, 0, std::max<size_t>(total, 1) * sizeof(T), stream));
+    T* b = dev_alloc<T>(total + 4);
+    MGB_CUDA(cudaMemsetAsync(b, 0, (total + 4) * sizeof(T), stream));
+    pad = even_pad(pad);
     if (pad == 0) return b;
     PaddedRegistry& r = padded_registry();
     std::lock_guard<std::mutex> g(r.mu);
@@ -114,6 +118,8 @@ struct Context {
     int smem_budget = 56 * 1024;
     int use_patterns = 1;          // 0: always stream CSR (MGB200_PATTERNS / mgb200_set_option)
     int use_graphs = 1;            // 0: never replay cycles from CUDA graphs
+    int use_tma = 1;               // 0: never use the TMA-staged dictionary kernel (MGB200_TMA)
+    int tma_min_rows = 200000;     // smaller matrices keep the one-pass kernel (too few tiles per SM)
     int max_smem_optin = 0;
     int sm_count = 148;
     bool profiling = false;
@@ -137,6 +143,8 @@ struct Context {
         smem_budget = env_int("MGB200_SMEM_BUDGET", 56 * 1024);
         use_patterns = env_int("MGB200_PATTERNS", 1);
         use_graphs = env_int("MGB200_GRAPHS", 1);
+        use_tma = env_int("MGB200_TMA", 1);
+        tma_min_rows = env_int("MGB200_TMA_MIN_ROWS", 200000);
     }
     void destroy() {
         if (!stream) return;
@@ -295,8 +303,11 @@ static void upload_csr(Context& ctx, Csr<TA>& M, long long n_rows, long long n_c
     // ---- stencil dictionary (pattern.cuh): deduplicate the rows on the host ---------------------
     if (want_patterns && ctx.use_patterns && n_cols < (1LL << 31) - 8) {
         HostPatterns<TA> hp;
-        if (build_patterns<TA>(n_rows, colptr, rowval, nzval, base, conjugate, PAT_MAX_PATTERNS, PAT_MAX_ENTRIES, hp))
+        if (build_patterns<TA>(n_rows, colptr, rowval, nzval, base, conjugate, PAT_MAX_PATTERNS, PAT_MAX_ENTRIES, hp)) {
             upload_patterns<TA>(M.pat, hp, n_rows);
+            M.pat.xlo = 0;                               // input vectors hold n_cols elements (+ slack, vec_alloc)
+            M.pat.xhi = (n_cols + 1) & ~1LL;
+        }
     }
 }
 

@@ -102,10 +102,50 @@ static double vec_bytes(const Csr<TA>& M, int mode, int m, bool d_from_dict) {
 }
 
 // stencil-dictionary kernel (pattern.cuh), one right-hand side
+// TMA-staged variant (pat_tma_kernel): row-relative matrices, SPMV / RESID / SWEEP, large levels
+template <typename TA, typename TV>
+static bool launch_pattern_tma(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d,
+                               const TV* dpat, TV* y) {
+    const PatDict<TA>& D = M.pat;
+    constexpr int NT = TmaTile<TA>::NT;
+    if (!D.tma_ok || !ctx.use_tma || mode == MODE_ADD || sizeof(TA) != sizeof(TV)) return false;
+    if (M.n_rows < ctx.tma_min_rows) return false;
+    // bulk copies need 16-byte aligned global addresses
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || (b && (reinterpret_cast<uintptr_t>(b) & 15)) ||
+        (d && (reinterpret_cast<uintptr_t>(d) & 15)) || x == y)
+        return false;
+    const bool need_b = (mode == MODE_RESID || mode == MODE_SWEEP);
+    const bool need_d = (mode == MODE_SWEEP && !dpat);
+    const size_t head = ((64 + (size_t)D.nent * sizeof(PatEntry<TA>) + (size_t)D.npat * (sizeof(TV) + 4) + 127) / 128) * 128;
+    const int elems = D.plan.total + (need_b ? NT : 0) + (need_d ? NT : 0);
+    const size_t stage = (((size_t)elems * sizeof(TV) + (size_t)NT * 2) + 127) / 128 * 128;
+    const size_t smem = head + 2 * stage;
+    if (smem > (size_t)ctx.max_smem_optin - 1024) return false;
+    const int ntiles = cdiv(M.n_rows, NT);
+    int per = (int)std::min<size_t>(2048 / NT, ((size_t)ctx.max_smem_optin + 1024) / (smem + 1024));
+    per = std::max(per, 1);
+    const int grid = std::min(ntiles, ctx.sm_count * per);
+#define MGB_TL(MODE, DP)                                                                                       \
+    {                                                                                                          \
+        auto kern = pat_tma_kernel<TA, TV, MODE, DP, NT>;                                                      \
+        MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+        kern<<<grid, NT, smem, ctx.stream>>>(D.plan, M.n_rows, ntiles, D.xlo, D.xhi, D.npat, D.nent, D.pid, D.hdr, \
+                                             D.ent_s, dpat, x, b, d, y);                                       \
+    }
+    if (mode == MODE_SPMV) MGB_TL(MODE_SPMV, false)
+    else if (mode == MODE_RESID) MGB_TL(MODE_RESID, false)
+    else if (dpat) MGB_TL(MODE_SWEEP, true)
+    else MGB_TL(MODE_SWEEP, false)
+#undef MGB_TL
+    MGB_LAUNCH_CHECK();
+    return true;
+}
+
 template <typename TA, typename TV>
 static void launch_pattern_mode(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d,
                                 const TV* dpat, TV* y) {
     const PatDict<TA>& D = M.pat;
+    if (D.rowrel && launch_pattern_tma<TA, TV>(ctx, M, mode, x, b, d, dpat, y)) return;
     const int nt = 256, grid = cdiv(M.n_rows, nt);
 #define MGB_PL(MODE, RR, DP) \
     pat_kernel<TA, TV, MODE, RR, DP><<<grid, nt, 0, ctx.stream>>>(M.n_rows, D.pid, D.c0, D.pat_off, D.ent, dpat, x, b, d, y)

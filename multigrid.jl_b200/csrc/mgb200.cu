@@ -68,9 +68,9 @@ static void spmatmul_impl(Hierarchy<TV>* H, int level, int which, double alpha, 
     auto run = [&](auto& M) {
         nx = M.n_cols;
         ny = M.n_rows;
-        TV* dx = dev_alloc<TV>(nx * m);
-        TV* dy = dev_alloc<TV>(ny * m);
-        TV* db = dev_alloc<TV>(ny * m);
+        TV* dx = vec_alloc<TV>(nx * m, 0, ctx.stream);
+        TV* dy = vec_alloc<TV>(ny * m, 0, ctx.stream);
+        TV* db = vec_alloc<TV>(ny * m, 0, ctx.stream);
         H->h2d_vec(x, dx, nx);
         if (beta == 1.0) H->h2d_vec(y, dy, ny);
         if (mode == MODE_RESID) {
@@ -418,6 +418,8 @@ int mgb200_set_option(mgb200_handle h, const char* key, int64_t value) {
         if (k == "patterns") H->ctx.use_patterns = (int)value;
         else if (k == "graphs") H->ctx.use_graphs = (int)value;
         else if (k == "smem_budget") H->ctx.smem_budget = (int)value;
+        else if (k == "tma") H->ctx.use_tma = (int)value;
+        else if (k == "tma_min_rows") H->ctx.tma_min_rows = (int)value;
         else throw Error(-1, "mgb200_set_option: unknown key " + k);
         H->invalidate_graphs();
     });

@@ -190,7 +190,7 @@ struct Hierarchy : HierarchyBase {
         upload_csr<double>(ctx, lv.P, n, nc, pcp, prv, pnz, base, false);
         upload_csr<double>(ctx, lv.R, nc, n, rcp, rrv, rnz, base, false);
         dev_free(lv.d);
-        lv.d = dev_alloc<TV>(n);
+        lv.d = dev_alloc<TV>(n + 4);   // slack for the even-rounded tile copies of the TMA kernel
         MGB_CUDA(cudaMemcpy(lv.d, d, n * sizeof(TV), cudaMemcpyHostToDevice));
         fold_d(lv, static_cast<const TV*>(d));
         lv.nalloc = n;
@@ -206,6 +206,11 @@ struct Hierarchy : HierarchyBase {
         dev_free(lv.dpat);
         PatDict<TV>& D = lv.A.pat;
         if (!D.present || D.host_pid.empty()) return;
+        if (env_int("MGB200_FOLD_D", 1) == 0) {   // tests: keep d as a vector
+            D.host_pid.clear();
+            D.host_pid.shrink_to_fit();
+            return;
+        }
         std::vector<TV> dp(D.npat);
         std::vector<char> seen(D.npat, 0);
         bool ok = true;
@@ -450,9 +455,12 @@ struct Hierarchy : HierarchyBase {
             upload_csr<double>(ctx, lv.P, lv.hP.n_rows, pcols, lv.hP.rowptr.data(), lv.hP.col.data(), lv.hP.val.data(), 0, false);
             upload_csr<double>(ctx, lv.R, lv.hR.n_rows, lv.nalloc, lv.hR.rowptr.data(), lv.hR.col.data(), lv.hR.val.data(), 0, false);
             dev_free(lv.d);
-            lv.d = dev_alloc<TV>(lv.n);
+            lv.d = dev_alloc<TV>(lv.n + 4);
             MGB_CUDA(cudaMemcpy(lv.d, lv.hd.data(), lv.n * sizeof(TV), cudaMemcpyHostToDevice));
             fold_d(lv, lv.hd.data());
+            // input vectors of A_l are laid out [ghosts below | owned | ghosts above] around the vector pointer
+            lv.A.pat.xlo = -(long long)even_pad((size_t)sp.n_lo);
+            lv.A.pat.xhi = (sp.n_owned + (sp.n_ghost - sp.n_lo) + 1) & ~1LL;
         }
         for (int l = 0; l < levels - 1; ++l) {
             L[l].hA.clear();
@@ -517,7 +525,7 @@ struct Hierarchy : HierarchyBase {
         work_ready = true;
     }
     // elements in front of the first owned row of a level-l vector (lower ghost rows, dist.cuh)
-    size_t vec_pad(int l) const { return L[l].sp.dist ? (size_t)L[l].sp.n_lo * m : 0; }
+    size_t vec_pad(int l) const { return L[l].sp.dist ? even_pad((size_t)L[l].sp.n_lo * m) : 0; }
     void alloc_fgmres(FgmresMem<TV>& mem, size_t nm, int inner, size_t pad) {
         mem.release();
         mem.inner = inner;

@@ -110,9 +110,13 @@ def _solve(kind, n, levels, cycle, env):
                                            ("diffusion", [24, 24, 12], 3)])
 @pytest.mark.parametrize("cycle", ['V', 'W', 'F'])
 def test_pattern_and_graph_paths_bit_identical(kind, n, levels, cycle):
-    x0, r0, it0, info0 = _solve(kind, n, levels, cycle, {"MGB200_PATTERNS": "0", "MGB200_GRAPHS": "0"})
-    x1, r1, it1, info1 = _solve(kind, n, levels, cycle, {"MGB200_PATTERNS": "1", "MGB200_GRAPHS": "0"})
-    x2, r2, it2, info2 = _solve(kind, n, levels, cycle, {"MGB200_PATTERNS": "1", "MGB200_GRAPHS": "1"})
+    x0, r0, it0, info0 = _solve(kind, n, levels, cycle, {"MGB200_PATTERNS": "0", "MGB200_GRAPHS": "0", "MGB200_TMA": "0"})
+    x1, r1, it1, info1 = _solve(kind, n, levels, cycle, {"MGB200_PATTERNS": "1", "MGB200_GRAPHS": "0", "MGB200_TMA": "0"})
+    x2, r2, it2, info2 = _solve(kind, n, levels, cycle, {"MGB200_PATTERNS": "1", "MGB200_GRAPHS": "1", "MGB200_TMA": "0"})
+    # TMA-staged persistent variant of the dictionary kernel, forced onto these small levels
+    x3, r3, it3, info3 = _solve(kind, n, levels, cycle, {"MGB200_PATTERNS": "1", "MGB200_GRAPHS": "1", "MGB200_TMA": "1",
+                                                         "MGB200_TMA_MIN_ROWS": "0"})
+    assert it3 == it0 and np.array_equal(r0, r3) and np.array_equal(x0, x3)
     assert not any(i["in_use"] for i in info0)
     if kind != "diffusion":
         assert info1[0]["in_use"] and info1[0]["row_relative"] and info1[0]["d_folded"]   # A_1
@@ -123,3 +127,37 @@ def test_pattern_and_graph_paths_bit_identical(kind, n, levels, cycle):
     assert it0 == it1 == it2
     assert np.array_equal(r0, r1) and np.array_equal(r1, r2)
     assert np.array_equal(x0, x1) and np.array_equal(x1, x2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,n", [("poisson", [40, 36, 28]), ("helmholtz", [33, 31, 17]), ("poisson", [300, 200])])
+def test_tma_kernel_with_vector_d_and_krylov(kind, n):
+    """TMA variant with relaxPrecs kept as a vector (d tile copied per stage), odd sizes (clamped windows, slack
+    elements) and the SpMV / residual modes of the Krylov drivers: identical to the CSR-stream path."""
+    import multigrid_jl_b200 as mg
+
+    def run(env):
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            A, AT, M, p, b = make_problem(kind, n, 3, maxit=12, tol=1e-9)
+            x = np.zeros_like(b)
+            if kind == "poisson":
+                x, _, it = mg.solveCG_MG(AT, p, b, x)
+            else:
+                x, _, it, _ = mg.solveGMRES_MG(AT, p, b, x, True, 5)
+            res = np.array(p.last_resvec, copy=True)
+            p.device.destroy()
+            return x, res, it
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+    xa, ra, ia = run({"MGB200_PATTERNS": "0", "MGB200_TMA": "0", "MGB200_FOLD_D": "1"})
+    xb, rb, ib = run({"MGB200_PATTERNS": "1", "MGB200_TMA": "1", "MGB200_TMA_MIN_ROWS": "0", "MGB200_FOLD_D": "0"})
+    xc, rc, ic = run({"MGB200_PATTERNS": "1", "MGB200_TMA": "1", "MGB200_TMA_MIN_ROWS": "0", "MGB200_FOLD_D": "1"})
+    assert ia == ib == ic
+    assert np.array_equal(ra, rb) and np.array_equal(ra, rc)
+    assert np.array_equal(xa, xb) and np.array_equal(xa, xc)
