@@ -366,6 +366,12 @@ def run_ours(args):
                 "cycle_achieved_gbs": nbytes / (ms_per_step * 1e-3) / 1e9,
                 "cycle_frac": nbytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak / world}
 
+    # ---- stand-alone fine-level SpMV (BASELINE metric "SpMV GB/s vs HBM peak") ---------------------
+    sp_ms, sp_bytes = dev.bench_spmv(1, max(args.steps, 5))
+    spmv = {"level": 1, "us": sp_ms * 1e3, "algorithmic_bytes": sp_bytes,
+            "gbs": sp_bytes / (sp_ms * 1e-3) / 1e9, "frac_of_hbm_peak": sp_bytes / (sp_ms * 1e-3) / 1e9 / hbm_peak,
+            "note": "y = A_1 x per GPU, CUDA events; algorithmic CSR bytes of SURVEY.md 8(d)"}
+
     # ---- end to end through the host-buffer C ABI ----------------------------------------------
     cyc = args.e2e_cycles
     nloc = dev.n
@@ -411,7 +417,7 @@ def run_ours(args):
                    "halo_exchange": (None if world == 1 else
                                      ("own put/wait kernels over NVLink peer memory (CUDA IPC), cycle replayed from a "
                                       "CUDA graph" if dinfo["p2p"] else "ncclSend/ncclRecv"))},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "spmv": spmv,
         "kernels": kern[:10],
     }
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -219,6 +219,11 @@ int64_t mgb200_launch_count(mgb200_handle h);
 int mgb200_event_record(mgb200_handle h, int idx);
 int mgb200_event_elapsed_ms(mgb200_handle h, int i0, int i1, double* ms);
 
+/* Stand-alone SpMV y = A_level x on device-resident buffers (the b and r workspaces of that level), `reps` calls
+ * timed with CUDA events on the library's stream: *ms_per_call and the algorithmic bytes of one call
+ * (nnz*(sv+4) + 4(n+1) + 2 n sv m).  The r workspace is overwritten. */
+int mgb200_bench_spmv(mgb200_handle h, int level, int reps, double* ms_per_call, double* algorithmic_bytes);
+
 /* cudaProfilerStart / cudaProfilerStop, so that `ncu --profile-from-start off` captures exactly
  * the timed region of bench.py. */
 int mgb200_profiler_start(void);

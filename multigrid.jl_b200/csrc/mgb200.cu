@@ -521,6 +521,33 @@ int mgb200_event_elapsed_ms(mgb200_handle h, int i0, int i1, double* ms) {
     MGB_CATCH
 }
 
+// Stand-alone y = A_level x on device-resident buffers, timed with CUDA events on the library's stream
+// (BASELINE metric "SpMV GB/s vs HBM peak"): x = memCycle[level].b, y = memCycle[level].r.
+int mgb200_bench_spmv(mgb200_handle h, int level, int reps, double* ms_per_call, double* algorithmic_bytes) {
+    MGB_TRY
+    MGB_CHECK(ms_per_call && algorithmic_bytes && reps >= 1, "bad argument");
+    MGB_BOTH(h, {
+        H->ensure_work();
+        MGB_CHECK(level >= 1 && level < H->levels, "level out of range");
+        auto& lv = H->L[level - 1];
+        Context& c = H->ctx;
+        typedef typename std::remove_reference<decltype(*lv.b)>::type TV;
+        for (int i = 0; i < 3; ++i) H->apply_A(lv.A, lv.b, lv.r, level);
+        cudaEvent_t e0 = c.get_event(), e1 = c.get_event();
+        MGB_CUDA(cudaEventRecord(e0, c.stream));
+        for (int i = 0; i < reps; ++i) H->apply_A(lv.A, lv.b, lv.r, level);
+        MGB_CUDA(cudaEventRecord(e1, c.stream));
+        MGB_CUDA(cudaEventSynchronize(e1));
+        float f = 0.f;
+        MGB_CUDA(cudaEventElapsedTime(&f, e0, e1));
+        c.ev_pool.push_back(e0);
+        c.ev_pool.push_back(e1);
+        *ms_per_call = f / reps;
+        *algorithmic_bytes = csr_bytes<TV, TV>(lv.A, MODE_SPMV, H->m);
+    });
+    MGB_CATCH
+}
+
 int mgb200_profiler_start(void) {
     MGB_TRY
     MGB_CUDA(cudaProfilerStart());

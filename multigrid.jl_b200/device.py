@@ -332,6 +332,12 @@ class DeviceHierarchy:
                             total_ms=float(ms), bytes=float(byts), format_bytes=float(fbyts)))
         return out
 
+    def bench_spmv(self, level=1, reps=20):
+        """(ms per call, algorithmic bytes per call) of the stand-alone SpMV y = A_level x on device buffers."""
+        ms, nb = ctypes.c_double(0.0), ctypes.c_double(0.0)
+        _check(lib().mgb200_bench_spmv(self.h, int(level), int(reps), ctypes.byref(ms), ctypes.byref(nb)))
+        return ms.value, nb.value
+
     def event_record(self, idx):
         _check(lib().mgb200_event_record(self.h, int(idx)))
 
