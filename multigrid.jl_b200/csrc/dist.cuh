@@ -128,6 +128,21 @@ static inline long long to_local_split(long long c, long long lo, long long hi, 
     return g < n_lo ? g - n_lo : (hi - lo) + (g - n_lo);
 }
 
+// Rows [lo, hi) of a staged matrix (columns already in the split layout: < 0 lower ghost, >= n_in_owned upper
+// ghost) that read owned rows only.  For a z-slab these are all rows but the first and the last plane.
+template <typename TA>
+static void interior_rows(const HostRows<TA>& H, long long n_in_owned, int& lo, int& hi) {
+    long long lo_max = -1, hi_min = H.n_rows;
+    for (long long i = 0; i < H.n_rows; ++i)
+        for (long long k = H.rowptr[i]; k < H.rowptr[i + 1]; ++k) {
+            if (H.col[k] < 0) lo_max = std::max(lo_max, i);
+            else if (H.col[k] >= n_in_owned) hi_min = std::min(hi_min, i);
+        }
+    lo = (int)(lo_max + 1);
+    hi = (int)hi_min;
+    if (hi < lo) lo = hi = 0;
+}
+
 // vector space of one distributed level
 struct DistSpace {
     bool dist = false;

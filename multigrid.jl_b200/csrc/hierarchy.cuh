@@ -91,9 +91,11 @@ struct Csr {
     bool staged = true; // TMA-staged kernel, else row-per-warp fallback
     size_t smem = 0;
     PatDict<TA> pat;    // stencil-dictionary form (pattern.cuh), when the rows deduplicate
+    int int_lo = 0, int_hi = 0;  // row-partitioned levels: rows [int_lo, int_hi) read no ghost row of the input vector
     bool present() const { return rowptr != nullptr; }
     void release() {
         pat.release();
+        int_lo = int_hi = 0;
         dev_free(rowptr);
         dev_free(colind);
         dev_free(val);
@@ -120,6 +122,10 @@ struct Context {
     int use_graphs = 1;            // 0: never replay cycles from CUDA graphs
     int use_tma = 1;               // 0: never use the TMA-staged dictionary kernel (MGB200_TMA)
     int tma_min_rows = 200000;     // smaller matrices keep the one-pass kernel (too few tiles per SM)
+    int split_test = 0;            // > 0: every dictionary pass runs as interior + both ends (test hook)
+    int use_overlap = 1;           // multi-GPU: halo exchange beside the interior rows (MGB200_OVERLAP)
+    cudaStream_t side = nullptr;   // carries the halo exchange of an overlapped pass
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int max_smem_optin = 0;
     int sm_count = 148;
     bool profiling = false;
@@ -145,6 +151,13 @@ struct Context {
         use_graphs = env_int("MGB200_GRAPHS", 1);
         use_tma = env_int("MGB200_TMA", 1);
         tma_min_rows = env_int("MGB200_TMA_MIN_ROWS", 200000);
+        use_overlap = env_int("MGB200_OVERLAP", 1);
+        split_test = env_int("MGB200_SPLIT_TEST", 0);
+        int prio_lo = 0, prio_hi = 0;
+        MGB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        MGB_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, prio_hi));
+        MGB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        MGB_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     }
     void destroy() {
         if (!stream) return;
@@ -164,6 +177,14 @@ struct Context {
         dev_free(scal);
         if (scal_host) cudaFreeHost(scal_host);
         scal_host = nullptr;
+        if (side) {
+            cudaStreamSynchronize(side);
+            cudaStreamDestroy(side);
+        }
+        side = nullptr;
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
+        ev_fork = ev_join = nullptr;
         cudaStreamDestroy(stream);
         stream = nullptr;
     }

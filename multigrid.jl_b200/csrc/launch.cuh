@@ -103,9 +103,12 @@ static double vec_bytes(const Csr<TA>& M, int mode, int m, bool d_from_dict) {
 
 // stencil-dictionary kernel (pattern.cuh), one right-hand side
 // TMA-staged variant (pat_tma_kernel): row-relative matrices, SPMV / RESID / SWEEP, large levels
+// Tiles [t0, t1) of TmaTile::NT rows (t1 < 0: all).  CTAs worth `reserve_threads` threads fewer than the machine holds are launched
+// when another kernel (the halo exchange of the same input vector, on its own stream) must find room beside the
+// persistent CTAs of this one.
 template <typename TA, typename TV>
 static bool launch_pattern_tma(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d,
-                               const TV* dpat, TV* y) {
+                               const TV* dpat, TV* y, int t0 = 0, int t1 = -1, int reserve_threads = 0) {
     const PatDict<TA>& D = M.pat;
     constexpr int NT = TmaTile<TA>::NT;
     if (!D.tma_ok || !ctx.use_tma || mode == MODE_ADD || sizeof(TA) != sizeof(TV)) return false;
@@ -121,15 +124,16 @@ static bool launch_pattern_tma(Context& ctx, const Csr<TA>& M, int mode, const T
     const size_t stage = (((size_t)elems * sizeof(TV) + (size_t)NT * 2) + 127) / 128 * 128;
     const size_t smem = head + 2 * stage;
     if (smem > (size_t)ctx.max_smem_optin - 1024) return false;
-    const int ntiles = cdiv(M.n_rows, NT);
+    const int ntiles = t1 < 0 ? cdiv(M.n_rows, NT) : t1;
+    if (ntiles <= t0) return false;
     int per = (int)std::min<size_t>(2048 / NT, ((size_t)ctx.max_smem_optin + 1024) / (smem + 1024));
     per = std::max(per, 1);
-    const int grid = std::min(ntiles, ctx.sm_count * per);
+    const int grid = std::min(ntiles - t0, std::max(ctx.sm_count, ctx.sm_count * per - cdiv(reserve_threads, NT)));
 #define MGB_TL(MODE, DP)                                                                                       \
     {                                                                                                          \
         auto kern = pat_tma_kernel<TA, TV, MODE, DP, NT>;                                                      \
         MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-        kern<<<grid, NT, smem, ctx.stream>>>(D.plan, M.n_rows, ntiles, D.xlo, D.xhi, D.npat, D.nent, D.pid, D.hdr, \
+        kern<<<grid, NT, smem, ctx.stream>>>(D.plan, M.n_rows, t0, ntiles, D.xlo, D.xhi, D.npat, D.nent, D.pid, D.hdr, \
                                              D.ent_s, dpat, x, b, d, y);                                       \
     }
     if (mode == MODE_SPMV) MGB_TL(MODE_SPMV, false)
@@ -141,14 +145,15 @@ static bool launch_pattern_tma(Context& ctx, const Csr<TA>& M, int mode, const T
     return true;
 }
 
+// one-pass dictionary kernel over the rows [rA, rA + nA) and [rB, rB + nB)
 template <typename TA, typename TV>
-static void launch_pattern_mode(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d,
-                                const TV* dpat, TV* y) {
+static void launch_pattern_rows(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d,
+                                const TV* dpat, TV* y, int rA, int nA, int rB, int nB) {
     const PatDict<TA>& D = M.pat;
-    if (D.rowrel && launch_pattern_tma<TA, TV>(ctx, M, mode, x, b, d, dpat, y)) return;
-    const int nt = 256, grid = cdiv(M.n_rows, nt);
+    if (nA + nB <= 0) return;
+    const int nt = 256, grid = cdiv(nA + nB, nt);
 #define MGB_PL(MODE, RR, DP) \
-    pat_kernel<TA, TV, MODE, RR, DP><<<grid, nt, 0, ctx.stream>>>(M.n_rows, D.pid, D.c0, D.pat_off, D.ent, dpat, x, b, d, y)
+    pat_kernel<TA, TV, MODE, RR, DP><<<grid, nt, 0, ctx.stream>>>(rA, nA, rB, nB, D.pid, D.c0, D.pat_off, D.ent, dpat, x, b, d, y)
 #define MGB_PCASE(MODE)                                     \
     case MODE:                                              \
         if (D.rowrel) {                                     \
@@ -170,6 +175,36 @@ static void launch_pattern_mode(Context& ctx, const Csr<TA>& M, int mode, const 
     MGB_LAUNCH_CHECK();
 }
 
+template <typename TA, typename TV>
+static void launch_pattern_mode(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d,
+                                const TV* dpat, TV* y) {
+    if (M.pat.rowrel && launch_pattern_tma<TA, TV>(ctx, M, mode, x, b, d, dpat, y)) return;
+    launch_pattern_rows<TA, TV>(ctx, M, mode, x, b, d, dpat, y, 0, M.n_rows, 0, 0);
+}
+
+// Split form of a dictionary pass: the rows [lo, hi) first, then `between()` (the caller joins the stream that
+// carried the halo exchange of x), then the remaining rows at both ends.  The interior runs as whole tiles of the
+// TMA-staged kernel when the matrix qualifies (the ends grow to the tile boundaries).  Same threads-per-row and
+// accumulation order as the unsplit pass: bit-identical results.
+template <typename TA, typename TV, typename F>
+static void pattern_apply_split(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d,
+                                const TV* dpat, TV* y, int lo, int hi, int reserve_threads, F&& between) {
+    constexpr int NT = TmaTile<TA>::NT;
+    int a0 = lo, a1 = hi;
+    bool done = false;
+    if (M.pat.rowrel) {
+        const int t0 = cdiv(lo, NT), t1 = hi / NT;
+        if (t1 > t0 && launch_pattern_tma<TA, TV>(ctx, M, mode, x, b, d, dpat, y, t0, t1, reserve_threads)) {
+            a0 = t0 * NT;
+            a1 = t1 * NT;
+            done = true;
+        }
+    }
+    if (!done) launch_pattern_rows<TA, TV>(ctx, M, mode, x, b, d, dpat, y, a0, a1 - a0, 0, 0);
+    between();
+    launch_pattern_rows<TA, TV>(ctx, M, mode, x, b, d, dpat, y, 0, a0, a1, M.n_rows - a1);
+}
+
 // y = op(M x): the one entry point the cycle uses for A, P and R.
 template <typename TA, typename TV>
 static void csr_apply(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d, TV* y,
@@ -178,7 +213,10 @@ static void csr_apply(Context& ctx, const Csr<TA>& M, int mode, const TV* x, con
     const bool use_pat = M.pat.present && m == 1 && ctx.use_patterns;
     const double fmt = use_pat ? M.pat.matrix_bytes(M.n_rows) + vec_bytes<TA, TV>(M, mode, m, dpat != nullptr) : -1.0;
     Launch L(ctx, kind, level, csr_bytes<TA, TV>(M, mode, m), fmt);
-    if (use_pat) {
+    if (use_pat && ctx.split_test > 0 && M.n_rows > 2 * ctx.split_test) {
+        // test hook (mgb200_set_option "split_test"): the split launch sequence of the multi-GPU overlap path
+        pattern_apply_split<TA, TV>(ctx, M, mode, x, b, d, dpat, y, ctx.split_test, M.n_rows - ctx.split_test, 16384, [] {});
+    } else if (use_pat) {
         launch_pattern_mode<TA, TV>(ctx, M, mode, x, b, d, dpat, y);
     } else if (!M.staged) {
         launch_rowwarp_mode<TA, TV>(ctx, M, mode, x, b, d, y, m);
@@ -194,6 +232,21 @@ static void csr_apply(Context& ctx, const Csr<TA>& M, int mode, const TV* x, con
             default: launch_stream_mode<TA, TV, 32>(ctx, M, mode, x, b, d, y); break;
         }
     }
+}
+
+// y = op(M x) with the rows [lo, hi) launched first and `between()` called before the rest (dictionary matrices,
+// one right-hand side: the caller checks pattern_in_use)
+template <typename TA>
+static bool pattern_in_use(const Context& ctx, const Csr<TA>& M, int m) {
+    return M.pat.present && m == 1 && ctx.use_patterns;
+}
+template <typename TA, typename TV, typename F>
+static void csr_apply_split(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d, TV* y,
+                            int kind, int level, const TV* dpat, int lo, int hi, int reserve_threads, F&& between) {
+    MGB_CHECK(pattern_in_use(ctx, M, 1), "split launch needs the stencil-dictionary format");
+    const double fmt = M.pat.matrix_bytes(M.n_rows) + vec_bytes<TA, TV>(M, mode, 1, dpat != nullptr);
+    Launch L(ctx, kind, level, csr_bytes<TA, TV>(M, mode, 1), fmt);
+    pattern_apply_split<TA, TV>(ctx, M, mode, x, b, d, dpat, y, lo, hi, reserve_threads, between);
 }
 
 // ---- reductions / vector ops -----------------------------------------------------------------

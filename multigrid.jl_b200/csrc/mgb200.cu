@@ -420,6 +420,8 @@ int mgb200_set_option(mgb200_handle h, const char* key, int64_t value) {
         else if (k == "smem_budget") H->ctx.smem_budget = (int)value;
         else if (k == "tma") H->ctx.use_tma = (int)value;
         else if (k == "tma_min_rows") H->ctx.tma_min_rows = (int)value;
+        else if (k == "split_test") H->ctx.split_test = (int)value;
+        else if (k == "overlap") H->ctx.use_overlap = (int)value;
         else throw Error(-1, "mgb200_set_option: unknown key " + k);
         H->invalidate_graphs();
     });

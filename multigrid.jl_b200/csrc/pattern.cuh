@@ -373,14 +373,17 @@ __device__ __forceinline__ PatEntry<cplx> ldg_ent(const PatEntry<cplx>* p) {
 
 // y = op(M x) for one right-hand side; MODE as in csr_kernels.cuh (0 SPMV, 1 ADD, 2 RESID, 3 SWEEP).
 // DPAT: the relaxation weights come from the dictionary (dpat[pid]) instead of the vector d.
+// The launch covers two row ranges, [rA, rA + nA) and then [rB, rB + nB) (a whole matrix is (0, n, 0, 0)); the
+// split form serves the rows next to the slab ends after a halo exchange that ran beside the interior rows.
 template <typename TA, typename TV, int MODE, bool ROWREL, bool DPAT>
 __global__ void __launch_bounds__(256)
-pat_kernel(int n_rows, const uint16_t* __restrict__ pid, const int* __restrict__ c0,
+pat_kernel(int rA, int nA, int rB, int nB, const uint16_t* __restrict__ pid, const int* __restrict__ c0,
            const int* __restrict__ pat_off, const PatEntry<TA>* __restrict__ ent,
            const TV* __restrict__ dpat, const TV* __restrict__ x, const TV* __restrict__ b,
            const TV* __restrict__ d, TV* __restrict__ y) {
-    const int row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= n_rows) return;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nA + nB) return;
+    const int row = idx < nA ? rA + idx : rB + (idx - nA);
     const int p = __ldg(reinterpret_cast<const unsigned short*>(pid) + row);
     const int base = ROWREL ? row : __ldg(c0 + row);
     const int k0 = __ldg(pat_off + p), k1 = __ldg(pat_off + p + 1);
@@ -417,7 +420,7 @@ pat_kernel(int n_rows, const uint16_t* __restrict__ pid, const int* __restrict__
 // 105 us against 140 us for the 7-point sweep at 257^3.)
 template <typename TA, typename TV, int MODE, bool DPAT, int NT>
 __global__ void __launch_bounds__(NT)
-pat_tma_kernel(const __grid_constant__ TmaPlan P, int n_rows, int ntiles, long long xlo, long long xhi, int npat,
+pat_tma_kernel(const __grid_constant__ TmaPlan P, int n_rows, int tile0, int ntiles, long long xlo, long long xhi, int npat,
                int nent, const uint16_t* __restrict__ pid, const int* __restrict__ hdr,
                const PatEntry<TA>* __restrict__ ent_s, const TV* __restrict__ dpat, const TV* __restrict__ x,
                const TV* __restrict__ b, const TV* __restrict__ d, TV* __restrict__ y) {
@@ -467,9 +470,10 @@ pat_tma_kernel(const __grid_constant__ TmaPlan P, int n_rows, int ntiles, long l
         if (NEED_D) bulk_g2s(sd, d + row0, (uint32_t)(rend - row0) * (uint32_t)sizeof(TV), full + s);
         bulk_g2s(sp, pid + row0, (uint32_t)(pend - row0) * 2u, full + s);
     };
-    if (t == 0 && (int)blockIdx.x < ntiles) issue(blockIdx.x, 0);
+    // tiles [tile0, ntiles) of the matrix: the whole matrix, or the interior tiles of a split launch
+    if (t == 0 && tile0 + (int)blockIdx.x < ntiles) issue(tile0 + blockIdx.x, 0);
     int i = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+    for (int tile = tile0 + blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
         const int s = i & 1;
         if (t == 0) {
             const int nt = tile + gridDim.x;

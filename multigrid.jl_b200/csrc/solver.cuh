@@ -454,6 +454,10 @@ struct Hierarchy : HierarchyBase {
             upload_csr<TV>(ctx, lv.A, lv.hA.n_rows, lv.nalloc, lv.hA.rowptr.data(), lv.hA.col.data(), lv.hA.val.data(), 0, false);
             upload_csr<double>(ctx, lv.P, lv.hP.n_rows, pcols, lv.hP.rowptr.data(), lv.hP.col.data(), lv.hP.val.data(), 0, false);
             upload_csr<double>(ctx, lv.R, lv.hR.n_rows, lv.nalloc, lv.hR.rowptr.data(), lv.hR.col.data(), lv.hR.val.data(), 0, false);
+            // rows that read no ghost row of their input vector (they may run beside the halo exchange, apply_x)
+            interior_rows(lv.hA, sp.n_owned, lv.A.int_lo, lv.A.int_hi);
+            interior_rows(lv.hR, sp.n_owned, lv.R.int_lo, lv.R.int_hi);
+            if (lc.sp.dist) interior_rows(lv.hP, lc.sp.n_owned, lv.P.int_lo, lv.P.int_hi);
             dev_free(lv.d);
             lv.d = dev_alloc<TV>(lv.n + 4);
             MGB_CUDA(cudaMemcpy(lv.d, lv.hd.data(), lv.n * sizeof(TV), cudaMemcpyHostToDevice));
@@ -557,12 +561,33 @@ struct Hierarchy : HierarchyBase {
     const Csr<TV>& krylov_A() const { return Akry.present() ? Akry : L[0].A; }
 
     void apply_A(const Csr<TV>& A, const TV* x, TV* y, int level) {  // y = A x   (getAfun, SolveFuncs.jl:65-71)
-        exchange(level - 1, const_cast<TV*>(x));
-        csr_apply<TV, TV>(ctx, A, MODE_SPMV, x, nullptr, nullptr, y, m, K_SPMV, level);
+        apply_x<TV>(level - 1, A, MODE_SPMV, const_cast<TV*>(x), nullptr, nullptr, y, K_SPMV, level);
     }
     void residual(const Csr<TV>& A, const TV* b, const TV* x, TV* r, int level) {  // r = b - A x
-        exchange(level - 1, const_cast<TV*>(x));
-        csr_apply<TV, TV>(ctx, A, MODE_RESID, x, b, nullptr, r, m, K_RESID, level);
+        apply_x<TV>(level - 1, A, MODE_RESID, const_cast<TV*>(x), b, nullptr, r, K_RESID, level);
+    }
+    // y = op(M v) for a level-(lin+1) input vector v whose ghost rows must be refreshed first (row-partitioned
+    // levels).  With the peer-memory exchange (p2p.cuh) the refresh runs on a second, high-priority stream BESIDE
+    // the rows that read no ghost; the few rows next to the slab ends follow once both have finished.  The fork and
+    // the join are event dependencies, so the overlap is part of the captured cycle graph.
+    static constexpr int OVERLAP_HALO_CTAS = 64;   // x 256 threads: the room the interior kernel leaves free
+    template <typename TA>
+    void apply_x(int lin, const Csr<TA>& M, int mode, TV* v, const TV* b, const TV* d, TV* y, int kind, int level,
+                 const TV* dpat = nullptr) {
+        const bool need = comm.active() && lin >= 0 && lin < levels && L[lin].sp.dist;
+        const bool split = need && p2p.on && ctx.use_overlap && !ctx.profiling && pattern_in_use(ctx, M, m) &&
+                           2LL * (M.int_hi - M.int_lo) >= M.n_rows;
+        if (!split) {
+            if (need) exchange(lin, v);
+            csr_apply<TA, TV>(ctx, M, mode, v, b, d, y, m, kind, level, dpat);
+            return;
+        }
+        MGB_CUDA(cudaEventRecord(ctx.ev_fork, ctx.stream));
+        MGB_CUDA(cudaStreamWaitEvent(ctx.side, ctx.ev_fork, 0));
+        exchange(lin, v, ctx.side, OVERLAP_HALO_CTAS);
+        MGB_CUDA(cudaEventRecord(ctx.ev_join, ctx.side));
+        csr_apply_split<TA, TV>(ctx, M, mode, v, b, d, y, kind, level, dpat, M.int_lo, M.int_hi, OVERLAP_HALO_CTAS * 256,
+                                [&] { MGB_CUDA(cudaStreamWaitEvent(ctx.stream, ctx.ev_join, 0)); });
     }
     // reductions over a distributed level are completed by an in-place all-reduce on the stream
     void allreduce(int l, double* dptr, int k) {
@@ -586,9 +611,11 @@ struct Hierarchy : HierarchyBase {
     }
 
     // halo exchange of a level-l vector laid out [ghosts below | owned | ghosts above], v at the first owned row
-    void exchange(int l, TV* v) {
+    void exchange(int l, TV* v, cudaStream_t stream = nullptr, int max_ctas = 0) {
         if (!comm.active() || l < 0 || l >= levels || !L[l].sp.dist) return;
         DistSpace& sp = L[l].sp;
+        if (!stream) stream = ctx.stream;
+        MGB_CHECK(stream == ctx.stream || p2p.on, "only the peer-memory exchange runs on a side stream");
         Launch La(ctx, K_COPY, l + 1, 2.0 * sp.n_ghost * m * sizeof(TV));
         if (p2p.on) {
             // put into the neighbours' receive buffers over NVLink, then wait for theirs and unpack (p2p.cuh)
@@ -596,8 +623,9 @@ struct Hierarchy : HierarchyBase {
             const long long work = std::max<long long>((long long)sp.n_send, sp.n_ghost) * m;
             // no CTA of this kernel waits on another one (they poll words written by the peers), so the grid may
             // be as wide as the copy needs
-            const int g = (int)std::max<long long>(1, std::min<long long>((work + 511) / 512, 2LL * ctx.sm_count));
-            p2p_halo_kernel<TV><<<g, 256, 0, ctx.stream>>>(cd, v, sp.d_send_idx, sp.n_send, sp.n_ghost, sp.n_lo,
+            int g = (int)std::max<long long>(1, std::min<long long>((work + 511) / 512, 2LL * ctx.sm_count));
+            if (max_ctas > 0) g = std::min(g, max_ctas);
+            p2p_halo_kernel<TV><<<g, 256, 0, stream>>>(cd, v, sp.d_send_idx, sp.n_send, sp.n_ghost, sp.n_lo,
                                                             sp.n_owned, m, p2p.epoch + l, p2p.ticket + l,
                                                             p2p.trace ? p2p.trace + (size_t)l * P2P_TRACE_ROWS * 4 : nullptr);
             MGB_LAUNCH_CHECK();
@@ -843,8 +871,7 @@ struct Hierarchy : HierarchyBase {
             sweeps -= 1;
         }
         for (int s = 0; s < sweeps; ++s) {
-            exchange(l, x);
-            csr_apply<TV, TV>(ctx, lv.A, MODE_SWEEP, x, b, lv.d, scratch, m, K_SWEEP, l + 1, dpat);
+            apply_x<TV>(l, lv.A, MODE_SWEEP, x, b, lv.d, scratch, K_SWEEP, l + 1, dpat);
             std::swap(x, scratch);
         }
         return x;
@@ -952,14 +979,13 @@ struct Hierarchy : HierarchyBase {
             if (xn != x) std::swap(x, scratch);
         }
         residual(lv.A, b, x, lv.r, l + 1);                                          // :58-60
-        exchange(l, lv.r);
         if (lv.sp.dist && !lc.sp.dist) {
             // last distributed level: each rank restricts its own coarse rows, then the pieces are gathered
-            csr_apply<double, TV>(ctx, lv.R, MODE_SPMV, lv.r, nullptr, nullptr,
-                                  lc.b + (size_t)lv.coarse_row_offsets[comm.rank] * m, m, K_RESTRICT, l + 1);
+            apply_x<double>(l, lv.R, MODE_SPMV, lv.r, nullptr, nullptr,
+                            lc.b + (size_t)lv.coarse_row_offsets[comm.rank] * m, K_RESTRICT, l + 1);
             allgather_rows(l + 1, lc.b, lv.coarse_row_offsets);
         } else {
-            csr_apply<double, TV>(ctx, lv.R, MODE_SPMV, lv.r, nullptr, nullptr, lc.b, m, K_RESTRICT, l + 1);  // :66
+            apply_x<double>(l, lv.R, MODE_SPMV, lv.r, nullptr, nullptr, lc.b, K_RESTRICT, l + 1);  // :66
         }
         if (l + 1 == levels - 1) {
             solve_coarsest(lc.b, lc.x0);                                           // :67-69
@@ -980,8 +1006,7 @@ struct Hierarchy : HierarchyBase {
                 xc_cur = cycle(l + 1, lc.b, xc_cur, other, false, 'V');            // :81-85
             }
         }
-        exchange(l + 1, xc_cur);
-        csr_apply<double, TV>(ctx, lv.P, MODE_ADD, xc_cur, nullptr, nullptr, x, m, K_PROLONG, l + 1);  // :90
+        apply_x<double>(l + 1, lv.P, MODE_ADD, xc_cur, nullptr, nullptr, x, K_PROLONG, l + 1);  // :90
         // ---- post-relaxation (:92-103) ----
         if (relax_kind == 1) {
             residual(lv.A, b, x, lv.r, l + 1);

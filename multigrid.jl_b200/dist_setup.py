@@ -145,13 +145,19 @@ def setup_slab_hierarchy(window_operator, domain, n_cells, param, rank, world, r
     nd = k                      # number of distributed levels: 0..k-1
     # ---- owned planes per level and the fine window -------------------------------------------
     own = [slab_planes(int(cells[l][2]), world) for l in range(nd + 1)]
-    # margins (in planes of each level) so that owned +- 1 halo rows of every distributed level are exact
-    margin = [0] * (nd + 1)
-    margin[nd] = 2
-    for l in range(nd - 1, -1, -1):
-        margin[l] = 2 * margin[l + 1] + 2
+    # Fine window.  Only the plane at a cut end of a window holds inexact rows, on EVERY level: the fine window is a
+    # principal sub-matrix (its edge rows miss the columns outside), and coarse plane k of a windowed Galerkin
+    # product is exact as soon as the fine planes 2k-2 .. 2k+2 lie in the window and the rows of 2k-1 .. 2k+1 are
+    # exact, i.e. from the second coarse plane on.  Ghost planes are needed as column indices only, not as rows.
+    # So the window must hold, for every level l <= nd, the owned planes of that level plus ONE plane on either
+    # side, expressed in fine planes (x 2^l); the slab boundaries of different levels need not coincide
+    # (slab_planes divides the cells of each level separately).  tests/test_dist_gloo.py compares bit for bit.
     align = 2 ** nd
-    wlo, whi = _window(own[0][rank][0], own[0][rank][1], int(cells[0][2]) + 1, margin[0], align)
+    n_planes = int(cells[0][2]) + 1
+    need_lo = min((own[l][rank][0] - 1) * 2 ** l for l in range(nd + 1))
+    need_hi = max(own[l][rank][1] * 2 ** l for l in range(nd + 1))          # last plane needed (inclusive)
+    wlo = max(0, (need_lo // align) * align)
+    whi = min(n_planes, -((-need_hi) // align) * align + 1)
     # ---- windowed Galerkin hierarchy -----------------------------------------------------------
     A = sp.csc_matrix(window_operator(cells[0], wlo, whi))
     if A.dtype != VAL:

@@ -161,3 +161,18 @@ def test_tma_kernel_with_vector_d_and_krylov(kind, n):
     assert ia == ib == ic
     assert np.array_equal(ra, rb) and np.array_equal(ra, rc)
     assert np.array_equal(xa, xb) and np.array_equal(xa, xc)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,n,cycle", [("poisson", [40, 36, 28], 'V'), ("helmholtz", [33, 31, 17], 'W'),
+                                          ("poisson", [300, 200], 'F')])
+@pytest.mark.parametrize("tma", ["0", "1"])
+def test_split_launches_bit_identical(kind, n, cycle, tma):
+    """The multi-GPU overlap path launches every dictionary pass as interior rows + the rows at both ends
+    (pattern_apply_split, launch.cuh).  MGB200_SPLIT_TEST forces that launch sequence on one GPU: the
+    results must not change by a bit, for the one-pass kernel and for the TMA-staged tiles."""
+    base = {"MGB200_PATTERNS": "1", "MGB200_GRAPHS": "1", "MGB200_TMA": tma, "MGB200_TMA_MIN_ROWS": "0"}
+    x0, r0, it0, _ = _solve(kind, n, 3, cycle, dict(base, MGB200_SPLIT_TEST="0"))
+    for rows in ("7", "1500"):
+        x1, r1, it1, _ = _solve(kind, n, 3, cycle, dict(base, MGB200_SPLIT_TEST=rows))
+        assert it0 == it1 and np.array_equal(r0, r1) and np.array_equal(x0, x1)
