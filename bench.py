@@ -51,15 +51,27 @@ def build_problem(cells, levels, nrhs=1, seed=0):
     return A, M, p, b
 
 
-def build_distributed(cells, levels, rank, world, local_rank, gloo_group):
-    """Weak-scaling workload for N > 1: the cfg2 problem stacked N times in z
-    (cells x cells x cells*N), z-slab row partition (one slab of `cells` planes per GPU),
-    Galerkin hierarchy built slab-locally on the host, coarse levels replicated."""
+def weak_scaling_grid(cells, world, layout):
+    """Cells per dimension of the N-GPU weak-scaling workload (cells^3 cells per GPU).  "cube": the grid doubles one
+    dimension at a time, z first - 256x256x512 (N=2), 256x512x512 (N=4), 512^3 (N=8, the north-star size) - and
+    is always cut into z-slabs; "stack": cells x cells x cells*N."""
+    if layout == "cube" and world in (1, 2, 4, 8):
+        f = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}[world]
+        return [cells * f[0], cells * f[1], cells * f[2]]
+    return [cells, cells, cells * world]
+
+
+def build_distributed(cells, levels, rank, world, local_rank, gloo_group, layout="cube"):
+    """Weak-scaling workload for N > 1 (weak_scaling_grid): z-slab row partition following
+    getOriginalBoundingBoxCells with NumCells = [1,1,N], Galerkin hierarchy built slab-locally on the host,
+    coarse levels replicated."""
     import torch.distributed as dist
     import multigrid_jl_b200 as mg
     t0 = time.time()
-    n = [cells, cells, cells * world]
-    dom = [0, 1, 0, 1, 0, float(world)]
+    n = weak_scaling_grid(cells, world, layout)
+    dom = [0, n[0] / cells, 0, n[1] / cells, 0, n[2] / cells]
+    if min(n) > cells:
+        levels += 1          # every dimension doubled: one more level reaches the same coarsest grid
     p = mg.getMGparam(np.float64, np.int64, levels, 8, 20, 1e-8, "Jac", 0.8, 2, 2, 'V')
     p.nrhs = 1
 
@@ -90,7 +102,7 @@ def build_distributed(cells, levels, rank, world, local_rank, gloo_group):
     nb2 = gather(float(np.dot(b, b)))
     b /= np.sqrt(sum(nb2))
     log(f"[bench rank {rank}] upload {time.time() - t0:.1f} s")
-    return dev, p, b, sizes, int(dh.dist_levels[0].n_global)
+    return dev, p, b, sizes, int(dh.dist_levels[0].n_global), n
 
 
 def cycle_bytes_sizes(sizes, nrhs=1, pre=2, post=2, sv=8):
@@ -262,11 +274,12 @@ def run_ours(args):
     cells, levels = args.cells, args.levels
     if world > 1:
         gloo = dist.new_group(backend="gloo")
-        dev, p, b, sizes, N = build_distributed(cells, levels, rank, world, local_rank, gloo)
+        dev, p, b, sizes, N, grid = build_distributed(cells, levels, rank, world, local_rank, gloo, args.layout)
         nbytes_cycle = cycle_bytes_sizes(sizes)
-        workload = (f"cfg2 stacked {world}x in z: 3D Poisson {cells}x{cells}x{cells * world} cells, z-slab row partition "
-                    f"(one {cells}-plane slab per GPU), geometric MG Galerkin {dev.levels} levels, damped Jacobi 0.8, "
-                    f"one V(2,2) cycle from x=0 per step; NCCL halo exchange + coarse all-gather")
+        workload = (f"cfg2 weak-scaled to {world} GPUs: 3D Poisson {grid[0]}x{grid[1]}x{grid[2]} cells ({cells}^3 per GPU), "
+                    f"z-slab row partition ({grid[2] // world} planes of {grid[0] + 1}x{grid[1] + 1} nodes per GPU), geometric "
+                    f"MG Galerkin {dev.levels} levels, damped Jacobi 0.8, one V(2,2) cycle from x=0 per step; halo "
+                    f"exchange + coarse gather inside the cycle")
         N_total = N
     else:
         A, M, p, b = build_problem(cells, levels, seed=rank)
@@ -401,7 +414,19 @@ def run_ours(args):
         t = torch.tensor([te], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         te = float(t.item())
+    # what the host link gives a pinned copy of the same size (explains the gap between e2e and value)
+    dtmp = torch.empty(nloc, dtype=torch.float64, device="cuda")
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dtmp.copy_(hb, non_blocking=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    dtmp.copy_(hb, non_blocking=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = nloc * 8 / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+    del dtmp
     e2e = {"value": N_total * cyc / te, "unit": "DOF/s", "h2d_bytes_per_step": 2 * nloc * 8 * world,
+           "host_link_h2d_gbs": h2d_gbs,
            "d2h_bytes_per_step": (nloc * 8 + 8 * (cyc + 1)) * world,
            "call": f"mgb200_solveMG (host buffers, pinned), {cyc} V(2,2) cycles per call incl. per-cycle residual norms",
            "ms_per_call": te * 1e3}
@@ -415,8 +440,9 @@ def run_ours(args):
                                 "cycle, plus the CSR arrays when the CSR-stream kernels run; L2 is 126 MB)",
                    "parallelism": f"row-partitioned z-slabs x{world}" if world > 1 else "single GPU",
                    "halo_exchange": (None if world == 1 else
-                                     ("own put/wait kernels over NVLink peer memory (CUDA IPC), cycle replayed from a "
-                                      "CUDA graph" if dinfo["p2p"] else "ncclSend/ncclRecv"))},
+                                     ("own kernels over NVLink peer memory (CUDA IPC, self-validating 8-byte words), run "
+                                      "beside the interior rows of the consuming pass; cycle replayed from a CUDA graph"
+                                      if dinfo["p2p"] else "ncclSend/ncclRecv"))},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "spmv": spmv,
         "kernels": kern[:10],
     }
@@ -447,6 +473,8 @@ def main():
     ap.add_argument("--e2e-cycles", type=int, default=10)
     ap.add_argument("--cpu-cycles", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--layout", default="cube", choices=["cube", "stack"],
+                    help="N > 1 weak-scaling grid: doubling dimensions up to 512^3 at N=8 (cube) or stacked in z")
     args = ap.parse_args()
     import __graft_entry__ as g
     if args.impl == "reference":
