@@ -29,7 +29,7 @@ static void launch_stream_mode(Context& ctx, const Csr<TA>& M, int mode, const T
     case MODE: {                                                                                         \
         auto kern = csr_stream_kernel<TA, TV, TPR, MODE>;                                                \
         if (M.smem > 48 * 1024)                                                                          \
-            MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M.smem)); \
+            MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx.max_smem_optin)); \
         kern<<<grid, nt, M.smem, ctx.stream>>>(M.n_rows, M.rowptr, M.colind, M.val, x, b, d, y, M.rpc,   \
                                                M.cap);                                                   \
     } break;
@@ -54,7 +54,7 @@ static void launch_mrhs_mode(Context& ctx, const Csr<TA>& M, int mode, const TV*
     case MODE: {                                                                                         \
         auto kern = csr_stream_mrhs_kernel<TA, TV, MODE>;                                                \
         if (M.smem > 48 * 1024)                                                                          \
-            MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M.smem)); \
+            MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx.max_smem_optin)); \
         kern<<<grid, nt, M.smem, ctx.stream>>>(M.n_rows, M.rowptr, M.colind, M.val, x, b, d, y, M.rpc,   \
                                                M.cap, m, mp);                                            \
     } break;
@@ -132,7 +132,7 @@ static bool launch_pattern_tma(Context& ctx, const Csr<TA>& M, int mode, const T
 #define MGB_TL(MODE, DP)                                                                                       \
     {                                                                                                          \
         auto kern = pat_tma_kernel<TA, TV, MODE, DP, NT>;                                                      \
-        MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+        MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx.max_smem_optin));         \
         kern<<<grid, NT, smem, ctx.stream>>>(D.plan, M.n_rows, t0, ntiles, D.xlo, D.xhi, D.npat, D.nent, D.pid, D.hdr, \
                                              D.ent_s, dpat, x, b, d, y);                                       \
     }

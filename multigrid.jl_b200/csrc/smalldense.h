@@ -198,4 +198,121 @@ static inline double hessenberg_lsq(const std::vector<zc>& H, int ldh, int rows,
     return std::sqrt(res);
 }
 
+// min_Y || A Y - B ||_F for a dense rows x cols matrix A (row-major) and nb right-hand sides B (rows x nb,
+// row-major): Householder QR on copies (block GMRES: the block-Hessenberg least-squares problem).  Columns whose
+// R-diagonal vanishes get a zero solution component.  Returns the Frobenius norm of the residual.
+static inline double dense_lsq(int rows, int cols, int nb, const std::vector<zc>& Ain, const std::vector<zc>& Bin,
+                               std::vector<zc>& Y) {
+    std::vector<zc> A(Ain), B(Bin);
+    std::vector<zc> v(rows);
+    for (int k = 0; k < cols && k < rows; ++k) {
+        double nrm = 0.0;
+        for (int i = k; i < rows; ++i) nrm += std::norm(A[(size_t)i * cols + k]);
+        nrm = std::sqrt(nrm);
+        if (nrm == 0.0) continue;
+        const zc akk = A[(size_t)k * cols + k];
+        const zc phase = (std::abs(akk) == 0.0) ? zc(1.0, 0.0) : akk / std::abs(akk);
+        const zc alpha = -phase * nrm;
+        for (int i = k; i < rows; ++i) v[i] = A[(size_t)i * cols + k];
+        v[k] -= alpha;
+        double vn = 0.0;
+        for (int i = k; i < rows; ++i) vn += std::norm(v[i]);
+        if (vn == 0.0) continue;
+        for (int j = k; j < cols; ++j) {
+            zc s = 0.0;
+            for (int i = k; i < rows; ++i) s += std::conj(v[i]) * A[(size_t)i * cols + j];
+            s *= 2.0 / vn;
+            for (int i = k; i < rows; ++i) A[(size_t)i * cols + j] -= s * v[i];
+        }
+        for (int j = 0; j < nb; ++j) {
+            zc s = 0.0;
+            for (int i = k; i < rows; ++i) s += std::conj(v[i]) * B[(size_t)i * nb + j];
+            s *= 2.0 / vn;
+            for (int i = k; i < rows; ++i) B[(size_t)i * nb + j] -= s * v[i];
+        }
+    }
+    Y.assign((size_t)cols * nb, zc(0.0, 0.0));
+    for (int j = 0; j < nb; ++j)
+        for (int k = cols - 1; k >= 0; --k) {
+            zc s = B[(size_t)k * nb + j];
+            for (int c = k + 1; c < cols; ++c) s -= A[(size_t)k * cols + c] * Y[(size_t)c * nb + j];
+            const zc akk = A[(size_t)k * cols + k];
+            Y[(size_t)k * nb + j] = (std::abs(akk) == 0.0) ? zc(0.0, 0.0) : s / akk;
+        }
+    double res = 0.0;
+    for (int i = cols; i < rows; ++i)
+        for (int j = 0; j < nb; ++j) res += std::norm(B[(size_t)i * nb + j]);
+    return std::sqrt(res);
+}
+
+// Upper Cholesky factor of a Hermitian positive definite m x m matrix (row-major): G = R^H R with a real positive
+// diagonal.  Returns false when a pivot is not positive (G numerically singular).
+static inline bool cholesky_upper(int m, const std::vector<zc>& G, std::vector<zc>& R) {
+    R.assign((size_t)m * m, zc(0.0, 0.0));
+    for (int j = 0; j < m; ++j) {
+        double d = G[(size_t)j * m + j].real();
+        for (int k = 0; k < j; ++k) d -= std::norm(R[(size_t)k * m + j]);
+        if (!(d > 0.0)) return false;
+        const double rjj = std::sqrt(d);
+        R[(size_t)j * m + j] = rjj;
+        for (int i = j + 1; i < m; ++i) {
+            zc s = G[(size_t)j * m + i];
+            for (int k = 0; k < j; ++k) s -= std::conj(R[(size_t)k * m + j]) * R[(size_t)k * m + i];
+            R[(size_t)j * m + i] = s / rjj;
+        }
+    }
+    return true;
+}
+
+// inverse of an upper triangular m x m matrix (row-major)
+static inline void upper_inverse(int m, const std::vector<zc>& R, std::vector<zc>& Rinv) {
+    Rinv.assign((size_t)m * m, zc(0.0, 0.0));
+    for (int j = 0; j < m; ++j) {
+        Rinv[(size_t)j * m + j] = 1.0 / R[(size_t)j * m + j];
+        for (int i = j - 1; i >= 0; --i) {
+            zc s = 0.0;
+            for (int k = i + 1; k <= j; ++k) s += R[(size_t)i * m + k] * Rinv[(size_t)k * m + j];
+            Rinv[(size_t)i * m + j] = -s / R[(size_t)i * m + i];
+        }
+    }
+}
+
+// X = A^{-1} B for an m x m matrix A and m x nb right-hand sides (row-major), LU with partial pivoting.
+// Returns false when A is singular to working precision (pivot <= eps * m * max|A|).
+static inline bool lu_solve_small(int m, int nb, const std::vector<zc>& Ain, const std::vector<zc>& Bin,
+                                  std::vector<zc>& X) {
+    std::vector<zc> A(Ain);
+    X = Bin;
+    double amax = 0.0;
+    for (const zc& a : A) amax = std::max(amax, std::abs(a));
+    const double tiny = 2.220446049250313e-16 * m * amax;
+    for (int k = 0; k < m; ++k) {
+        int piv = k;
+        double best = std::abs(A[(size_t)k * m + k]);
+        for (int i = k + 1; i < m; ++i)
+            if (std::abs(A[(size_t)i * m + k]) > best) {
+                best = std::abs(A[(size_t)i * m + k]);
+                piv = i;
+            }
+        if (!(best > tiny)) return false;
+        if (piv != k) {
+            for (int j = 0; j < m; ++j) std::swap(A[(size_t)k * m + j], A[(size_t)piv * m + j]);
+            for (int j = 0; j < nb; ++j) std::swap(X[(size_t)k * nb + j], X[(size_t)piv * nb + j]);
+        }
+        for (int i = k + 1; i < m; ++i) {
+            const zc f = A[(size_t)i * m + k] / A[(size_t)k * m + k];
+            if (f == zc(0.0, 0.0)) continue;
+            for (int j = k + 1; j < m; ++j) A[(size_t)i * m + j] -= f * A[(size_t)k * m + j];
+            for (int j = 0; j < nb; ++j) X[(size_t)i * nb + j] -= f * X[(size_t)k * nb + j];
+        }
+    }
+    for (int j = 0; j < nb; ++j)
+        for (int k = m - 1; k >= 0; --k) {
+            zc s = X[(size_t)k * nb + j];
+            for (int c = k + 1; c < m; ++c) s -= A[(size_t)k * m + c] * X[(size_t)c * nb + j];
+            X[(size_t)k * nb + j] = s / A[(size_t)k * m + k];
+        }
+    return true;
+}
+
 }  // namespace mgb200

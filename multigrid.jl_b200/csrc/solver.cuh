@@ -1184,7 +1184,7 @@ struct Hierarchy : HierarchyBase {
                                                                            std::min(GRAM_MAX_BLOCKS, ctx.sm_count * 4)));
         const size_t smem = 2 * (size_t)GRAM_ROWS * m * sizeof(TV);
         if (smem > 48 * 1024)
-            MGB_CUDA(cudaFuncSetAttribute(gram_kernel<TV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            MGB_CUDA(cudaFuncSetAttribute(gram_kernel<TV>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx.max_smem_optin));
         gram_kernel<TV><<<blocks, GRAM_THREADS, smem, ctx.stream>>>(n, m, X, Y, gram_partials, gram_counter, out);
         MGB_LAUNCH_CHECK();
         allreduce(0, out, 2 * m * m);
@@ -1205,7 +1205,7 @@ struct Hierarchy : HierarchyBase {
         ctx.sync();  // hc is a stack temporary
         Launch La(ctx, K_VECTOR, 0, 3.0 * n * m * sizeof(TV));
         if ((size_t)m * m * sizeof(TV) > 48 * 1024)
-            MGB_CUDA(cudaFuncSetAttribute(block_axpy_kernel<TV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)m * m * sizeof(TV))));
+            MGB_CUDA(cudaFuncSetAttribute(block_axpy_kernel<TV>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx.max_smem_optin));
         block_axpy_kernel<TV><<<ctx.ew_blocks(n * m), 256, (size_t)m * m * sizeof(TV), ctx.stream>>>(n, m, X, dC, base, out);
         MGB_LAUNCH_CHECK();
     }
@@ -1229,20 +1229,22 @@ struct Hierarchy : HierarchyBase {
                 for (int j = 0; j < m; ++j) C[(size_t)i * m + j] += sgn * a * B[(size_t)k * m + j];
             }
     }
-    int solveBlockCG(TV* xk, double tol, int max_iter, int* flag, double* resmat, double pinv_tol) {
-        ensure_work();
-        MGB_CHECK(m >= 1 && m <= 64, "blockCG supports up to 64 right-hand sides");
-        ensure_krylov(0, false);
-        Level<TV>& lv = L[0];
-        const long long n = lv.n, nm = n * m;
-        const size_t nma = (size_t)lv.nalloc * m;
+    void ensure_block_ws() {
         if (!gram_ws) {
             gram_ws = dev_alloc<double>(6 * (size_t)64 * 64 + 2 * (size_t)64 * 64 + 64);
             gram_partials = dev_alloc<double>((size_t)GRAM_MAX_BLOCKS * 2 * 64 * 64);
             gram_counter = dev_alloc<unsigned>(1);
             MGB_CUDA(cudaMemset(gram_counter, 0, sizeof(unsigned)));
         }
-        if (!kq) kq = vec_alloc<TV>(nma, vec_pad(0), ctx.stream);
+        if (!kq) kq = vec_alloc<TV>((size_t)L[0].nalloc * m, vec_pad(0), ctx.stream);
+    }
+    int solveBlockCG(TV* xk, double tol, int max_iter, int* flag, double* resmat, double pinv_tol) {
+        ensure_work();
+        MGB_CHECK(m >= 1 && m <= 64, "blockCG supports up to 64 right-hand sides");
+        ensure_krylov(0, false);
+        Level<TV>& lv = L[0];
+        const long long n = lv.n, nm = n * m;
+        ensure_block_ws();
         const Csr<TV>& A = krylov_A();
         const TV* B = lv.b;
         if (norm(nm, B) == 0.0) {
@@ -1297,6 +1299,241 @@ struct Hierarchy : HierarchyBase {
         return it;
     }
 
+    // ---- block QR of an n x m block on the device: W = Q * Betta, Q'Q = I, Betta upper triangular ---------------
+    // Cholesky QR applied twice (Gram matrix on the device, m x m Cholesky on the host, Q = W R^{-1} on the device;
+    // the second pass restores orthogonality to working precision).  If the Gram matrix is not numerically
+    // positive definite the first pass is shifted (shifted CholeskyQR3).  KrylovMethods uses LAPACK's Householder
+    // qr!; the factors differ by unit-modulus column scalings only, which the block-Hessenberg least-squares
+    // residual does not see.  Wio holds the block on entry and Q on return; tmp is a spare block.
+    void block_qr(long long n, TV*& Wio, TV*& tmp, std::vector<zc>& Betta) {
+        std::vector<zc> G, R, Rinv, Racc;
+        Racc.assign((size_t)m * m, zc(0, 0));
+        for (int i = 0; i < m; ++i) Racc[(size_t)i * m + i] = 1.0;
+        int passes = 2;
+        for (int pass = 0; pass < passes; ++pass) {
+            gram(n, Wio, Wio, gram_ws);
+            read_matrix(gram_ws, G);
+            for (int i = 0; i < m; ++i)     // exactly Hermitian
+                for (int j = i + 1; j < m; ++j) {
+                    const zc a = 0.5 * (G[(size_t)i * m + j] + std::conj(G[(size_t)j * m + i]));
+                    G[(size_t)i * m + j] = a;
+                    G[(size_t)j * m + i] = std::conj(a);
+                }
+            if (!cholesky_upper(m, G, R)) {
+                MGB_CHECK(pass == 0 && passes == 2, "block QR: Gram matrix stays indefinite after the shifted pass");
+                double tr = 0.0;
+                for (int i = 0; i < m; ++i) tr += G[(size_t)i * m + i].real();
+                long long nglob = L[0].sp.dist ? L[0].sp.n_global : n;
+                const double shift = 11.0 * ((double)m * nglob + (double)m * (m + 1)) * 2.220446049250313e-16 * tr;
+                for (int i = 0; i < m; ++i) G[(size_t)i * m + i] += std::max(shift, 1e-300);
+                MGB_CHECK(cholesky_upper(m, G, R), "block QR: zero block (exact breakdown)");
+                passes = 3;
+            }
+            upper_inverse(m, R, Rinv);
+            block_axpy(n, Wio, Rinv, nullptr, tmp);      // tmp = W R^{-1}
+            std::swap(Wio, tmp);
+            std::vector<zc> Rn;
+            matmul_small(m, R, Racc, Rn, 1.0);           // Betta = R_k ... R_1
+            Racc.swap(Rn);
+        }
+        Betta = Racc;
+    }
+
+    // ---- KrylovMethods.blockFGMRES with M = one cycle (solveGMRES_MG with nrhs > 1, SolveFuncs.jl:130) ----------
+    // Block Arnoldi: one n x m block per inner step, classical block Gram-Schmidt against the whole basis, QR of the
+    // new block, block-Hessenberg least squares on the host every inner step; Frobenius norms; max_iter counts
+    // restarts.  resvec: restrt * max_iter doubles.
+    int solveBlockFGMRES(TV* xk, int restrt, bool flexible, double tol, int max_iter, int* flag, double* resvec,
+                         int* nres) {
+        ensure_work();
+        MGB_CHECK(m >= 1 && m <= 64, "blockFGMRES supports up to 64 right-hand sides");
+        Level<TV>& lv = L[0];
+        long long nglob = lv.sp.dist ? lv.sp.n_global : lv.n;
+        restrt = (int)std::min<long long>(restrt, nglob - 1);
+        MGB_CHECK(restrt >= 1 && restrt <= MAXK, "blockFGMRES: restart length must be in 1..32");
+        ensure_krylov(restrt, true);
+        ensure_block_ws();
+        const long long n = lv.n, nm = n * m;
+        const size_t ldv = (size_t)lv.nalloc * m;     // one basis block
+        const Csr<TV>& A = krylov_A();
+        const TV* B = lv.b;
+        TV *R = kr, *W = kw, *T = kAp, *Tmp = kq;
+        *nres = 0;
+        const double rnorm0 = norm(nm, B);
+        if (rnorm0 == 0.0) {
+            dev_zero<TV>(ctx, nm, xk);
+            *flag = -9;
+            return 0;
+        }
+        residual(A, B, xk, R, 1);
+        double err = norm(nm, R) / rnorm0;
+        if (err < tol) {
+            *flag = 0;
+            resvec[0] = err;
+            *nres = 1;
+            return 0;
+        }
+        *flag = -1;
+        int counter = 0, it = 0;
+        const int hr = (restrt + 1) * m, hc = restrt * m;
+        std::vector<zc> Betta, Tm, Y;
+        while (it < max_iter) {
+            it += 1;
+            std::vector<zc> H((size_t)hr * hc, zc(0, 0)), xi((size_t)hr * m, zc(0, 0));
+            dev_copy<TV>(ctx, nm, R, W);
+            block_qr(n, W, Tmp, Betta);
+            for (int a = 0; a < m; ++a)
+                for (int b = 0; b < m; ++b) xi[(size_t)a * m + b] = Betta[(size_t)a * m + b];
+            int jdone = 0;
+            for (int j = 0; j < restrt; ++j) {
+                dev_copy<TV>(ctx, nm, W, kV + (size_t)j * ldv);
+                TV* Z = precondition(W);
+                if (flexible) dev_copy<TV>(ctx, nm, Z, kZ + (size_t)j * ldv);
+                apply_A(A, Z, W, 1);
+                counter += 1;
+                // T = V'W block by block, then W -= V T (classical block Gram-Schmidt: all of T from the same W)
+                std::vector<std::vector<zc>> Ts(j + 1);
+                for (int i = 0; i <= j; ++i) {
+                    gram(n, kV + (size_t)i * ldv, W, gram_ws);
+                    read_matrix(gram_ws, Ts[i]);
+                    for (int a = 0; a < m; ++a)
+                        for (int b = 0; b < m; ++b) H[(size_t)(i * m + a) * hc + (j * m + b)] = Ts[i][(size_t)a * m + b];
+                }
+                for (int i = 0; i <= j; ++i) {
+                    for (auto& v : Ts[i]) v = -v;
+                    block_axpy(n, kV + (size_t)i * ldv, Ts[i], W, W);
+                }
+                block_qr(n, W, Tmp, Betta);
+                for (int a = 0; a < m; ++a)
+                    for (int b = 0; b < m; ++b) H[(size_t)((j + 1) * m + a) * hc + (j * m + b)] = Betta[(size_t)a * m + b];
+                const int rows = (j + 2) * m, cols = (j + 1) * m;
+                std::vector<zc> Hj((size_t)rows * cols), xj((size_t)rows * m);
+                for (int a = 0; a < rows; ++a) {
+                    for (int b = 0; b < cols; ++b) Hj[(size_t)a * cols + b] = H[(size_t)a * hc + b];
+                    for (int b = 0; b < m; ++b) xj[(size_t)a * m + b] = xi[(size_t)a * m + b];
+                }
+                err = dense_lsq(rows, cols, m, Hj, xj, Y) / rnorm0;
+                resvec[counter - 1] = err;
+                jdone = j + 1;
+                if (err <= tol) {
+                    *flag = 0;
+                    break;
+                }
+            }
+            // X += Z y (flexible) or X += M(V y); Y holds the least-squares solution of the last inner step
+            std::vector<zc> Yi((size_t)m * m);
+            if (!flexible) dev_zero<TV>(ctx, nm, T);
+            for (int i = 0; i < jdone; ++i) {
+                for (int a = 0; a < m; ++a)
+                    for (int b = 0; b < m; ++b) Yi[(size_t)a * m + b] = Y[(size_t)(i * m + a) * m + b];
+                if (flexible) block_axpy(n, kZ + (size_t)i * ldv, Yi, xk, xk);
+                else block_axpy(n, kV + (size_t)i * ldv, Yi, T, T);
+            }
+            if (!flexible) {
+                TV* z = precondition(T);
+                dev_axpby<TV>(ctx, nm, VT<TV>::one(), z, VT<TV>::one(), xk, false);
+            }
+            if (*flag == 0) break;
+            if (it < max_iter) residual(A, B, xk, R, 1);
+        }
+        // W and Tmp may have traded places inside block_qr: keep the members consistent with the buffers they own
+        kw = W;
+        kq = Tmp;
+        *nres = counter;
+        return it;
+    }
+
+    // ---- KrylovMethods.blockBiCGSTB with M1 = one cycle (solveBiCGSTAB_MG with nrhs > 1, SolveFuncs.jl:95) ------
+    // Block BiCGStab of El Guennouni, Jbilou and Sadok in the shape of solveBiCGSTAB above: m x m systems with
+    // R~'V instead of the scalar divisions, omega from Frobenius inner products.  resvec: max_iter + 1 doubles.
+    int solveBlockBiCGSTAB(TV* xk, double tol, int max_iter, int* flag, double* resvec, int* nprec) {
+        ensure_work();
+        MGB_CHECK(m >= 1 && m <= 64, "blockBiCGSTB supports up to 64 right-hand sides");
+        ensure_krylov(1, true);
+        ensure_block_ws();
+        Level<TV>& lv = L[0];
+        const long long n = lv.n, nm = n * m;
+        const Csr<TV>& A = krylov_A();
+        const TV* B = lv.b;
+        TV *r = kr, *rt = kw, *p = kp, *v = kAp, *phat = kV, *t = kZ, *tmp = kq;
+        *nprec = 0;
+        const double bnrm2 = norm(nm, B);
+        if (bnrm2 == 0.0) {
+            dev_zero<TV>(ctx, nm, xk);
+            *flag = -9;
+            resvec[0] = 0.0;
+            return 0;
+        }
+        residual(A, B, xk, r, 1);
+        double err = norm(nm, r) / bnrm2;
+        resvec[0] = err;
+        if (err < tol) {
+            *flag = 0;
+            return 0;
+        }
+        dev_copy<TV>(ctx, nm, r, rt);
+        dev_copy<TV>(ctx, nm, r, p);
+        std::vector<zc> G, RtR, RtT, Alpha, Beta, nA;
+        *flag = -1;
+        int it = 0;
+        for (it = 1; it <= max_iter; ++it) {
+            TV* z = precondition(p);                         // P_hat = M2(M1(P)), M2 = identity
+            *nprec += m;
+            dev_copy<TV>(ctx, nm, z, phat);
+            apply_A(A, phat, v, 1);                          // V = A(P_hat)
+            gram(n, rt, v, gram_ws);
+            read_matrix(gram_ws, G);
+            gram(n, rt, r, gram_ws);
+            read_matrix(gram_ws, RtR);
+            if (!lu_solve_small(m, m, G, RtR, Alpha)) {      // (R~'V) alpha = R~'R
+                *flag = -2;
+                break;
+            }
+            nA = Alpha;
+            for (auto& a : nA) a = -a;
+            block_axpy(n, v, nA, r, r);                      // S = R - V alpha (in r)
+            const double snorm = norm(nm, r) / bnrm2;
+            if (snorm < tol) {
+                block_axpy(n, phat, Alpha, xk, xk);          // X += P_hat alpha
+                resvec[it] = snorm;
+                *flag = -3;
+                return it - 1;
+            }
+            z = precondition(r);                             // S_hat
+            *nprec += m;
+            apply_A(A, z, t, 1);                             // T = A(S_hat)
+            const zc ts = dot(nm, t, r), tt = dot(nm, t, t);
+            const zc omega = ts / tt;
+            block_axpy(n, phat, Alpha, xk, xk);              // X += P_hat alpha + omega S_hat
+            dev_axpby<TV>(ctx, nm, to_tv(omega), z, VT<TV>::one(), xk, false);
+            dev_axpby<TV>(ctx, nm, to_tv(-omega), t, VT<TV>::one(), r, false);   // R = S - omega T
+            err = norm(nm, r) / bnrm2;
+            resvec[it] = err;
+            if (err <= tol) {
+                *flag = 0;
+                break;
+            }
+            if (omega == zc(0.0, 0.0)) {
+                *flag = -2;
+                break;
+            }
+            gram(n, rt, t, gram_ws);
+            read_matrix(gram_ws, RtT);
+            for (auto& a : RtT) a = -a;
+            if (!lu_solve_small(m, m, G, RtT, Beta)) {       // (R~'V) beta = -R~'T
+                *flag = -2;
+                break;
+            }
+            dev_axpby<TV>(ctx, nm, to_tv(-omega), v, VT<TV>::one(), p, false);   // P - omega V (in p)
+            block_axpy(n, p, Beta, r, tmp);                  // P = R + (P - omega V) beta
+            std::swap(p, tmp);
+        }
+        kp = p;
+        kq = tmp;
+        if (it > max_iter) it = max_iter;
+        return it;
+    }
+
     // ---- KrylovMethods.bicgstb with M1 = one cycle, M2 = identity (solveBiCGSTAB_MG, SolveFuncs.jl:85-99) ----
     // van der Vorst's preconditioned BiCGStab as in the "Templates" book, which the package follows.
     // resvec: max_iter + 1 doubles (resvec[0] = initial relative residual).  flag: 0 converged, -1 max_iter,
@@ -1304,7 +1541,7 @@ struct Hierarchy : HierarchyBase {
     // Returns the number of completed iterations; *nprec = cycles applied (2 per iteration, SolveFuncs.jl:97).
     int solveBiCGSTAB(TV* xk, double tol, int max_iter, int* flag, double* resvec, int* nprec) {
         ensure_work();
-        MGB_CHECK(m == 1, "solveBiCGSTAB: blockBiCGSTB (nrhs > 1) is not provided");
+        if (m > 1) return solveBlockBiCGSTAB(xk, tol, max_iter, flag, resvec, nprec);
         ensure_krylov(1, true);
         Level<TV>& lv = L[0];
         const long long n = lv.n;
@@ -1477,7 +1714,7 @@ struct Hierarchy : HierarchyBase {
     int solveFGMRES(TV* xk, int restrt, bool flexible, double tol, int max_iter, int* flag, double* resvec,
                     int* nres) {
         ensure_work();
-        MGB_CHECK(m == 1, "solveFGMRES: blockFGMRES (nrhs > 1) is not provided yet");
+        if (m > 1) return solveBlockFGMRES(xk, restrt, flexible, tol, max_iter, flag, resvec, nres);
         Level<TV>& lv = L[0];
         restrt = (int)std::min<long long>(restrt, lv.n - 1);
         MGB_CHECK(restrt >= 1 && restrt <= MAXK, "fgmres: restart length must be in 1..32");

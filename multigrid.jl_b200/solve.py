@@ -68,9 +68,8 @@ def solveCG_MG(AT, param: MGparam, b, x0, verbose: bool = False):
 
 
 def solveBiCGSTAB_MG(AT, param: MGparam, b, x0, verbose: bool = False):
-    """solveBiCGSTAB_MG(AT,param,b,x0,verbose) -> (x, param, iter, nprec)   (SolveFuncs.jl:73-75,85-99)."""
-    if _nrhs(b) != 1:
-        raise NotImplementedError("blockBiCGSTB (nrhs > 1) is not provided on the device path")
+    """solveBiCGSTAB_MG(AT,param,b,x0,verbose) -> (x, param, iter, nprec)   (SolveFuncs.jl:73-75,85-99);
+    an n x nrhs block b runs KrylovMethods.blockBiCGSTB (SolveFuncs.jl:95)."""
     dev = _device(param, b)
     _krylov_matrix(dev, AT, param)
     xx, it, flag, res, nprec = dev.solveBiCGSTAB(b, x0, param.relativeTol, param.maxOuterIter)

@@ -338,16 +338,22 @@ def solveCG_MG(AT, mg: OracleMG, b, x0):
 
 
 def solveBiCGSTAB_MG(AT, mg: OracleMG, b, x0):
-    """SolveFuncs.jl:73-75,85-99 -> KrylovMethods.bicgstb (M1 = one cycle, M2 = identity).
-    Returns (x, iter, flag, resvec, nprec)."""
+    """SolveFuncs.jl:73-75,85-99 -> KrylovMethods.bicgstb / blockBiCGSTB (M1 = one cycle, M2 = identity).
+    Returns (x, iter, flag, resvec, nprec) with nprec = 2*iter*nrhs + (flag == -3)*nrhs (SolveFuncs.jl:97)."""
     from . import krylov
     b = np.asfortranarray(b)
     ATc = AT if isinstance(AT, K.CSCAdjoint) else K.CSCAdjoint(AT)
     Afun = getAfun(ATc, np.zeros(b.shape, dtype=b.dtype, order="F"), mg.numCores)
     MMG = getMultigridPreconditioner(mg, b)
-    x, flag, rnorm, it, resvec = krylov.bicgstb(Afun, b.reshape(-1), tol=mg.relativeTol,
-                                                maxIter=mg.maxOuterIter, M1=MMG, x=x0)
-    return x, it, flag, resvec, 2 * it + (1 if flag == -3 else 0)
+    if b.ndim == 1 or b.shape[1] == 1:
+        x, flag, rnorm, it, resvec = krylov.bicgstb(Afun, b.reshape(-1), tol=mg.relativeTol,
+                                                    maxIter=mg.maxOuterIter, M1=MMG, x=x0)
+        nrhs = 1
+    else:
+        x, flag, rnorm, it, resvec = krylov.blockBiCGSTB(Afun, b, tol=mg.relativeTol,
+                                                         maxIter=mg.maxOuterIter, M1=MMG, x=x0)
+        nrhs = b.shape[1]
+    return x, it, flag, resvec, 2 * it * nrhs + (nrhs if flag == -3 else 0)
 
 
 def solveGMRES_MG(AT, mg: OracleMG, b, x0, flexible, inner):

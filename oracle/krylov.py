@@ -237,4 +237,136 @@ def fgmres(A, b, restrt, tol=1e-2, maxIter=100, M=None, x=None, out=0, flexible=
 
 
 def blockFGMRES(A, B, restrt, tol=1e-2, maxIter=100, M=None, X=None, out=0, flexible=False):
-    raise NotImplementedError("blockFGMRES is a 'next' row (SURVEY.md section 8(f))")
+    """KrylovMethods.blockFGMRES: the block analogue of ``fgmres`` above - block Arnoldi with one n x m block per
+    inner step, classical block Gram-Schmidt against the whole basis as two gemm calls (T = V'W; W -= V T),
+    a Householder QR of the new block (its R factor is the sub-diagonal block of H), the small least-squares
+    problem min || H Y - Xi ||_F solved every inner step for the residual estimate, Frobenius norms, stop on
+    ||R||_F / ||B||_F <= tol; ``maxIter`` counts restarts.  Returns (X, flag, relres, iter, resvec)."""
+    n, m = B.shape
+    T = B.dtype
+    M = (lambda v: v.copy()) if M is None else M
+    if np.linalg.norm(B) == 0.0:
+        return np.zeros((n, m), dtype=T, order="F"), -9, 0.0, 0, np.array([0.0])
+    if X is None or X.size == 0:
+        X = np.zeros((n, m), dtype=T, order="F")
+        R = np.array(B, order="F", copy=True)
+    else:
+        X = np.array(X, order="F", copy=True)
+        R = np.array(B, order="F", copy=True)
+        R -= A(X)
+    rnorm0 = np.linalg.norm(B)
+    err = np.linalg.norm(R) / rnorm0
+    if err < tol:
+        return X, 0, err, 0, np.array([err])
+    restrt = min(restrt, n - 1)
+    Vbig = np.zeros((n, m * restrt), dtype=T, order="F")
+    Zbig = np.zeros((n, m * restrt), dtype=T, order="F") if flexible else None
+    resvec = np.zeros(restrt * maxIter)
+    flag = -1
+    counter = 0
+    it = 0
+    while it < maxIter:
+        it += 1
+        H = np.zeros(((restrt + 1) * m, restrt * m), dtype=T)
+        xi = np.zeros(((restrt + 1) * m, m), dtype=T)
+        Vbig[...] = 0
+        if flexible:
+            Zbig[...] = 0
+        W, betta = np.linalg.qr(R)
+        xi[:m, :] = betta
+        jdone = 0
+        for j in range(restrt):
+            cs = slice(j * m, (j + 1) * m)
+            Vbig[:, cs] = W
+            Z = M(np.asfortranarray(W))
+            if flexible:
+                Zbig[:, cs] = Z
+            W = np.array(A(np.asfortranarray(Z)), order="F", copy=True)
+            counter += 1
+            Tm = Vbig.conj().T @ W                       # gemm 'C','N'
+            H[:restrt * m, cs] = Tm
+            W = W - Vbig @ Tm                            # gemm 'N','N'
+            W, betta = np.linalg.qr(W)
+            H[(j + 1) * m:(j + 2) * m, cs] = betta
+            Hj = H[:(j + 2) * m, :(j + 1) * m]
+            y = np.linalg.lstsq(Hj, xi[:(j + 2) * m, :], rcond=None)[0]
+            err = np.linalg.norm(Hj @ y - xi[:(j + 2) * m, :]) / rnorm0
+            resvec[counter - 1] = err
+            jdone = j + 1
+            if err <= tol:
+                flag = 0
+                break
+        y = np.linalg.lstsq(H[:(jdone + 1) * m, :jdone * m], xi[:(jdone + 1) * m, :], rcond=None)[0]
+        if flexible:
+            W = Zbig[:, :jdone * m] @ y
+        else:
+            W = np.array(M(np.asfortranarray(Vbig[:, :jdone * m] @ y)), copy=True)
+        X = np.asfortranarray(X + W)
+        if flag == 0:
+            break
+        if it < maxIter:
+            R = np.array(B, order="F", copy=True)
+            R -= A(X)
+    return X, flag, resvec[counter - 1], it, resvec[:counter].copy()
+
+
+def blockBiCGSTB(A, b, tol=1e-6, maxIter=100, M1=None, M2=None, x=None, out=0):
+    """KrylovMethods.blockBiCGSTB: block BiCGStab for several right-hand sides (El Guennouni, Jbilou and Sadok,
+    ETNA 16, 2003) written like ``bicgstb`` above: P_hat = M2(M1(P)), V = A P_hat, the m x m system
+    (R~'V) alpha = R~'R, S = R - V alpha, half-step exit on ||S||_F/||B||_F < tol (flag -3), S_hat = M2(M1(S)),
+    T = A S_hat, omega = <T,S>_F/<T,T>_F, X += P_hat alpha + omega S_hat, R = S - omega T,
+    (R~'V) beta = -R~'T, P = R + (P - omega V) beta.  For m = 1 this is exactly ``bicgstb``.
+    Returns (X, flag, relres, iter, resvec)."""
+    n, m = b.shape
+    T = b.dtype
+    M1 = (lambda v: v.copy()) if M1 is None else M1
+    M2 = (lambda v: v) if M2 is None else M2
+    if np.linalg.norm(b) == 0:
+        return np.zeros((n, m), dtype=T, order="F"), -9, 0.0, 0, np.array([0.0])
+    if x is None or x.size == 0:
+        x = np.zeros((n, m), dtype=T, order="F")
+        r = np.array(b, order="F", copy=True)
+    else:
+        x = np.array(x, order="F", copy=True)
+        r = np.array(b, order="F", copy=True)
+        r -= A(x)
+    bnrm2 = np.linalg.norm(b)
+    err = np.linalg.norm(r) / bnrm2
+    resvec = np.zeros(maxIter + 1)
+    resvec[0] = err
+    if err < tol:
+        return x, 0, err, 0, resvec[:1].copy()
+    r_tld = r.copy()
+    p = r.copy()
+    flag = -1
+    it = 0
+    for it in range(1, maxIter + 1):
+        p_hat = np.array(M2(M1(np.asfortranarray(p))), order="F", copy=True)
+        v = np.array(A(p_hat), order="F", copy=True)
+        G = r_tld.conj().T @ v
+        if np.linalg.matrix_rank(G) < m:
+            flag = -2
+            break
+        alpha = np.linalg.solve(G, r_tld.conj().T @ r)
+        s = np.asfortranarray(r - v @ alpha)
+        snorm = np.linalg.norm(s) / bnrm2
+        if snorm < tol:
+            x = np.asfortranarray(x + p_hat @ alpha)
+            resvec[it] = snorm
+            return x, -3, snorm, it - 1, resvec[:it + 1].copy()
+        s_hat = np.array(M2(M1(np.asfortranarray(s))), order="F", copy=True)
+        t = np.array(A(s_hat), order="F", copy=True)
+        omega = np.vdot(t, s) / np.vdot(t, t)
+        x = np.asfortranarray(x + (p_hat @ alpha + omega * s_hat))
+        r = np.asfortranarray(s - omega * t)
+        err = np.linalg.norm(r) / bnrm2
+        resvec[it] = err
+        if err <= tol:
+            flag = 0
+            break
+        if omega == 0.0:
+            flag = -2
+            break
+        beta = np.linalg.solve(G, -(r_tld.conj().T @ t))
+        p = np.asfortranarray(r + (p - omega * v) @ beta)
+    return x, flag, resvec[it], it, resvec[:it + 1].copy()

@@ -205,6 +205,45 @@ def test_blockCG_iteration_count(kind, n, levels, nrhs):
     assert np.abs(np.linalg.norm(b - A @ x, axis=0) / np.linalg.norm(b, axis=0)).max() <= 1.01e-8
 
 
+@pytest.mark.parametrize("kind,n,levels,nrhs,flexible", [("poisson", [32, 32], 3, 4, True),
+                                                           ("poisson", [16, 16, 16], 3, 32, True),
+                                                           ("helmholtz", [32, 32], 3, 3, True),
+                                                           ("helmholtz", [16, 16, 16], 3, 5, False)])
+def test_blockFGMRES_iteration_count(kind, n, levels, nrhs, flexible):
+    """solveGMRES_MG with nrhs > 1 -> KrylovMethods.blockFGMRES (SolveFuncs.jl:130): same number of restarts and
+    inner steps, same exit flag, same residual history as the oracle (the device orthogonalises the blocks by
+    Cholesky QR instead of Householder QR: identical up to rounding)."""
+    import multigrid_jl_b200 as mg
+    A, AT, M, p, b = make_problem(kind, n, levels, nrhs=nrhs, maxit=10, tol=1e-8)
+    oc, o = _oracle(p)
+    x_ref, it_ref, flag_ref, res_ref = oc.solveGMRES_MG(AT, o, b, np.zeros_like(b), flexible, 4)
+    x = np.zeros_like(b)
+    x, _, it, res = mg.solveGMRES_MG(AT, p, b, x, flexible, 4)
+    assert it == it_ref and p.last_flag == flag_ref == 0
+    assert len(res) == len(res_ref)
+    np.testing.assert_allclose(res, res_ref, rtol=1e-6)
+    assert np.linalg.norm(b - A @ x) <= 1.01e-8 * np.linalg.norm(b)
+    assert np.linalg.norm(x - x_ref) <= 1e-6 * np.linalg.norm(x_ref)
+
+
+@pytest.mark.parametrize("kind,n,levels,nrhs", [("poisson", [32, 32], 3, 4), ("poisson", [16, 16, 16], 3, 32),
+                                                 ("helmholtz", [32, 32], 3, 3), ("diffusion", [24, 24], 3, 2)])
+def test_blockBiCGSTB_iteration_count(kind, n, levels, nrhs):
+    """solveBiCGSTAB_MG with nrhs > 1 -> KrylovMethods.blockBiCGSTB (SolveFuncs.jl:95): iterations, exit flag,
+    residual history and nprec = 2*iter*nrhs + (flag == -3)*nrhs (SolveFuncs.jl:97) as the oracle."""
+    import multigrid_jl_b200 as mg
+    A, AT, M, p, b = make_problem(kind, n, levels, nrhs=nrhs, maxit=20, tol=1e-8)
+    oc, o = _oracle(p)
+    x_ref, it_ref, flag_ref, res_ref, nprec_ref = oc.solveBiCGSTAB_MG(AT, o, b, np.zeros_like(b))
+    x = np.zeros_like(b)
+    x, _, it, nprec = mg.solveBiCGSTAB_MG(AT, p, b, x)
+    assert it == it_ref and p.last_flag == flag_ref and flag_ref in (0, -3)
+    assert nprec == nprec_ref == 2 * it * nrhs + (nrhs if flag_ref == -3 else 0)
+    assert len(p.last_resvec) == len(res_ref)
+    np.testing.assert_allclose(p.last_resvec, res_ref, rtol=1e-5)
+    assert np.linalg.norm(b - A @ x) <= 1.01e-8 * np.linalg.norm(b)
+
+
 def test_sa_amg_hierarchy():
     """SA-AMG hierarchy (long, irregular rows) through the same device cycle."""
     import multigrid_jl_b200 as mg
