@@ -61,16 +61,16 @@ def weak_scaling_grid(cells, world, layout):
     return [cells, cells, cells * world]
 
 
-def build_distributed(cells, levels, rank, world, local_rank, gloo_group, layout="cube"):
+def build_distributed(cells, levels, rank, world, local_rank, gloo_group, layout="cube", grid=None):
     """Weak-scaling workload for N > 1 (weak_scaling_grid): z-slab row partition following
     getOriginalBoundingBoxCells with NumCells = [1,1,N], Galerkin hierarchy built slab-locally on the host,
     coarse levels replicated."""
     import torch.distributed as dist
     import multigrid_jl_b200 as mg
     t0 = time.time()
-    n = weak_scaling_grid(cells, world, layout)
+    n = list(grid) if grid else weak_scaling_grid(cells, world, layout)
     dom = [0, n[0] / cells, 0, n[1] / cells, 0, n[2] / cells]
-    if min(n) > cells:
+    if min(n) > cells and not grid:
         levels += 1          # every dimension doubled: one more level reaches the same coarsest grid
     p = mg.getMGparam(np.float64, np.int64, levels, 8, 20, 1e-8, "Jac", 0.8, 2, 2, 'V')
     p.nrhs = 1
@@ -274,9 +274,11 @@ def run_ours(args):
     cells, levels = args.cells, args.levels
     if world > 1:
         gloo = dist.new_group(backend="gloo")
-        dev, p, b, sizes, N, grid = build_distributed(cells, levels, rank, world, local_rank, gloo, args.layout)
+        dev, p, b, sizes, N, grid = build_distributed(cells, levels, rank, world, local_rank, gloo, args.layout,
+                                                           [int(v) for v in args.grid.split(",")] if args.grid else None)
         nbytes_cycle = cycle_bytes_sizes(sizes)
-        workload = (f"cfg2 weak-scaled to {world} GPUs: 3D Poisson {grid[0]}x{grid[1]}x{grid[2]} cells ({cells}^3 per GPU), "
+        workload = (f"cfg2 weak-scaled to {world} GPUs: 3D Poisson {grid[0]}x{grid[1]}x{grid[2]} cells "
+                    f"({grid[0] * grid[1] * grid[2] / world / cells ** 3:.3g} x {cells}^3 per GPU), "
                     f"z-slab row partition ({grid[2] // world} planes of {grid[0] + 1}x{grid[1] + 1} nodes per GPU), geometric "
                     f"MG Galerkin {dev.levels} levels, damped Jacobi 0.8, one V(2,2) cycle from x=0 per step; halo "
                     f"exchange + coarse gather inside the cycle")
@@ -473,6 +475,7 @@ def main():
     ap.add_argument("--e2e-cycles", type=int, default=10)
     ap.add_argument("--cpu-cycles", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--grid", default="", help="N > 1: explicit cells per dimension n1,n2,n3 (development runs)")
     ap.add_argument("--layout", default="cube", choices=["cube", "stack"],
                     help="N > 1 weak-scaling grid: doubling dimensions up to 512^3 at N=8 (cube) or stacked in z")
     args = ap.parse_args()

@@ -176,6 +176,15 @@ int mgb200_host_plan_ghosts(int64_t nnz, const int64_t* cols, int64_t lo, int64_
 int mgb200_host_pinv_apply(int n, const double* H, const double* xi, double* t);
 int mgb200_host_general_pinv(int n, const double* A, double rtol, double* P);
 int mgb200_host_hessenberg_lsq(int cols, const double* H, const double* xi, double* y, double* res);
+/* block GMRES / block BiCGStab pieces: dense least squares with nb right-hand sides (*res = residual norm);
+ * what = 0 upper Cholesky factor of A (out m x m), what = 1 out = A^{-1} B (m x nb); status -5 when A is not
+ * positive definite / singular */
+int mgb200_host_dense_lsq(int rows, int cols, int nb, const double* A, const double* B, double* Y, double* res);
+int mgb200_host_small_factor(int what, int m, int nb, const double* A, const double* B, double* out);
+/* rows [out[0], out[1]) of a CSR slab that read no ghost row of their input vector (columns relative to the first
+ * owned row: < 0 lower ghost, >= n_in_owned upper ghost): the rows launched beside the halo exchange */
+int mgb200_host_interior_rows(int64_t n_rows, const int64_t* rowptr, const int64_t* cols, int64_t n_in_owned,
+                              int64_t* out);
 
 /* ---- introspection / measurement -------------------------------------------------------------- */
 
@@ -195,7 +204,9 @@ int mgb200_pattern_info(mgb200_handle h, int level, int which, int64_t* out);
 /* Runtime options: "patterns" (1/0: use the stencil dictionary where available; set before upload to skip
  * building it), "graphs" (1/0: replay V/F/W cycles from CUDA graphs), "smem_budget" (bytes per CTA used when
  * choosing the rows per CTA of the CSR-stream kernel at upload), "tma" (1/0: TMA-staged persistent variant of the
- * dictionary kernel for square stencil operators), "tma_min_rows" (matrices with fewer rows keep the one-pass kernel). */
+ * dictionary kernel for square stencil operators), "tma_min_rows" (matrices with fewer rows keep the one-pass kernel),
+ * "overlap" (1/0: multi-GPU, run the halo exchange of an operator's input beside the rows that read no ghost),
+ * "split_test" (rows: single-GPU test hook that forces the split launch sequence of the overlap path). */
 int mgb200_set_option(mgb200_handle h, const char* key, int64_t value);
 
 /* Host-only (no GPU): the row deduplication behind the stencil dictionary, exported for the CPU test-suite.

@@ -606,4 +606,56 @@ int mgb200_host_hessenberg_lsq(int cols, const double* H, const double* xi, doub
     MGB_CATCH
 }
 
+// block-Hessenberg least squares min || A Y - B ||_F (rows x cols, nb right-hand sides); *res = residual norm
+int mgb200_host_dense_lsq(int rows, int cols, int nb, const double* A, const double* B, double* Y, double* res) {
+    MGB_TRY
+    MGB_CHECK(A && B && Y && res && rows >= cols && cols >= 1 && nb >= 1, "bad argument");
+    std::vector<zc> Av((size_t)rows * cols), Bv((size_t)rows * nb), Yv;
+    for (size_t i = 0; i < Av.size(); ++i) Av[i] = zc(A[2 * i], A[2 * i + 1]);
+    for (size_t i = 0; i < Bv.size(); ++i) Bv[i] = zc(B[2 * i], B[2 * i + 1]);
+    *res = dense_lsq(rows, cols, nb, Av, Bv, Yv);
+    for (size_t i = 0; i < Yv.size(); ++i) {
+        Y[2 * i] = Yv[i].real();
+        Y[2 * i + 1] = Yv[i].imag();
+    }
+    MGB_CATCH
+}
+// what = 0: R = upper Cholesky factor of the Hermitian positive definite A (out: m x m); returns status -5 if A is not
+// positive definite.  what = 1: out = A^{-1} B by LU with partial pivoting (B, out: m x nb); -5 if singular.
+int mgb200_host_small_factor(int what, int m, int nb, const double* A, const double* B, double* out) {
+    MGB_TRY
+    MGB_CHECK(A && out && m >= 1, "bad argument");
+    std::vector<zc> Av((size_t)m * m), Ov;
+    for (size_t i = 0; i < Av.size(); ++i) Av[i] = zc(A[2 * i], A[2 * i + 1]);
+    if (what == 0) {
+        if (!cholesky_upper(m, Av, Ov)) throw Error(-5, "matrix is not positive definite");
+    } else {
+        MGB_CHECK(B && nb >= 1, "bad argument");
+        std::vector<zc> Bv((size_t)m * nb);
+        for (size_t i = 0; i < Bv.size(); ++i) Bv[i] = zc(B[2 * i], B[2 * i + 1]);
+        if (!lu_solve_small(m, nb, Av, Bv, Ov)) throw Error(-5, "matrix is singular");
+    }
+    for (size_t i = 0; i < Ov.size(); ++i) {
+        out[2 * i] = Ov[i].real();
+        out[2 * i + 1] = Ov[i].imag();
+    }
+    MGB_CATCH
+}
+// rows [out[0], out[1]) of a CSR slab (columns relative to the first owned row of the input vector: < 0 lower
+// ghost, >= n_in_owned upper ghost) that read owned rows only - the rows that run beside the halo exchange
+int mgb200_host_interior_rows(int64_t n_rows, const int64_t* rowptr, const int64_t* cols, int64_t n_in_owned,
+                              int64_t* out) {
+    MGB_TRY
+    MGB_CHECK(rowptr && cols && out && n_rows >= 0, "bad argument");
+    HostRows<double> H;
+    H.n_rows = n_rows;
+    H.rowptr.assign(rowptr, rowptr + n_rows + 1);
+    H.col.assign(cols, cols + rowptr[n_rows]);
+    int lo = 0, hi = 0;
+    interior_rows(H, n_in_owned, lo, hi);
+    out[0] = lo;
+    out[1] = hi;
+    MGB_CATCH
+}
+
 }  // extern "C"

@@ -122,3 +122,73 @@ def test_host_general_pinv_matches_numpy(n, cplx, rank_def):
                                       P.ctypes.data_as(ctypes.c_void_p)) == 0
     ref = np.linalg.pinv(Ac, rcond=1e-10)
     np.testing.assert_allclose(P, ref, rtol=1e-8, atol=1e-10 * np.abs(ref).max())
+
+
+def _vp(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+@pytest.mark.parametrize("rows,cols,nb", [(2, 1, 1), (8, 4, 4), (15, 10, 5), (96, 64, 32)])
+def test_host_dense_lsq_matches_numpy(rows, cols, nb):
+    """dense_lsq (smalldense.h): the block-Hessenberg least-squares problem of blockFGMRES."""
+    from multigrid_jl_b200 import device
+    L = device.lib()
+    rng = np.random.default_rng(rows)
+    A = np.ascontiguousarray(rng.standard_normal((rows, cols)) + 1j * rng.standard_normal((rows, cols)))
+    B = np.ascontiguousarray(rng.standard_normal((rows, nb)) + 1j * rng.standard_normal((rows, nb)))
+    Y = np.zeros((cols, nb), dtype=np.complex128)
+    res = ctypes.c_double(0)
+    assert L.mgb200_host_dense_lsq(rows, cols, nb, _vp(A), _vp(B), _vp(Y), ctypes.byref(res)) == 0
+    Yr = np.linalg.lstsq(A, B, rcond=None)[0]
+    np.testing.assert_allclose(Y, Yr, rtol=1e-9, atol=1e-12)
+    assert abs(res.value - np.linalg.norm(A @ Yr - B)) < 1e-10
+
+
+@pytest.mark.parametrize("m,cplx", [(1, False), (4, False), (7, True), (32, True)])
+def test_host_cholesky_and_lu_solve(m, cplx):
+    """cholesky_upper / lu_solve_small (smalldense.h): Cholesky QR of blockFGMRES, m x m systems of blockBiCGSTB."""
+    from multigrid_jl_b200 import device
+    L = device.lib()
+    rng = np.random.default_rng(m)
+    C = rng.standard_normal((m + 3, m)) + (1j * rng.standard_normal((m + 3, m)) if cplx else 0)
+    G = np.ascontiguousarray(C.conj().T @ C, dtype=np.complex128)
+    R = np.zeros((m, m), dtype=np.complex128)
+    assert L.mgb200_host_small_factor(0, m, 0, _vp(G), None, _vp(R)) == 0
+    assert np.allclose(np.tril(R, -1), 0) and np.all(np.diag(R).real > 0) and np.allclose(np.diag(R).imag, 0)
+    np.testing.assert_allclose(R.conj().T @ R, G, rtol=1e-12, atol=1e-12 * np.abs(G).max())
+    G[0, 0] = -1.0
+    assert L.mgb200_host_small_factor(0, m, 0, _vp(G), None, _vp(R)) == -5       # not positive definite
+    A = np.ascontiguousarray(rng.standard_normal((m, m)) + (1j * rng.standard_normal((m, m)) if cplx else 0),
+                             dtype=np.complex128)
+    B = np.ascontiguousarray(rng.standard_normal((m, 3)) + 0j)
+    X = np.zeros((m, 3), dtype=np.complex128)
+    assert L.mgb200_host_small_factor(1, m, 3, _vp(A), _vp(B), _vp(X)) == 0
+    np.testing.assert_allclose(A @ X, B, rtol=1e-9, atol=1e-10)
+    if m > 1:
+        A[:, -1] = A[:, 0]
+        assert L.mgb200_host_small_factor(1, m, 3, _vp(A), _vp(B), _vp(X)) == -5   # singular
+
+
+def test_host_interior_rows_of_a_slab():
+    """interior_rows (dist.cuh): rows of a z-slab that read no ghost plane - everything but the first and last
+    plane for a middle slab, nothing cut at a domain end, no interior when a middle row reads both sides."""
+    import scipy.sparse as sp
+    import multigrid_jl_b200 as mg
+    from multigrid_jl_b200 import device
+    L = device.lib()
+    M = mg.getRegularMesh([0, 1, 0, 1, 0, 1], [4, 4, 11])
+    A = sp.csr_matrix(mg.poisson_shifted(M, 1e-4))
+    plane = 25
+    out = np.zeros(2, dtype=np.int64)
+    for lo_pl, hi_pl, expect in ((0, 4, (0, 3 * plane)), (4, 8, (plane, 3 * plane)), (8, 12, (plane, 4 * plane))):
+        S = A[lo_pl * plane:hi_pl * plane]
+        cols = np.ascontiguousarray(S.indices.astype(np.int64) - lo_pl * plane)
+        ptr = np.ascontiguousarray(S.indptr.astype(np.int64))
+        n_owned = (hi_pl - lo_pl) * plane
+        assert L.mgb200_host_interior_rows(ctypes.c_int64(S.shape[0]), _vp(ptr), _vp(cols), ctypes.c_int64(n_owned),
+                                           _vp(out)) == 0
+        assert tuple(out) == expect
+    ptr = np.array([0, 1, 3, 4], dtype=np.int64)
+    cols = np.array([0, -1, 5, 1], dtype=np.int64)     # row 1 reads a lower and an upper ghost
+    assert L.mgb200_host_interior_rows(ctypes.c_int64(3), _vp(ptr), _vp(cols), ctypes.c_int64(3), _vp(out)) == 0
+    assert out[0] == out[1]

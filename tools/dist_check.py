@@ -35,9 +35,14 @@ def main():
         return out
     ok = True
     cases = [("poisson", [32, 32, 32 * world], 5, 'V', np.float64), ("poisson", [32, 32, 32 * world], 5, 'W', np.float64),
-             ("helmholtz", [32, 32, 32 * world], 4, 'V', np.complex128), ("poisson", [16, 16, 16 * world], 4, 'K', np.float64)]
+             ("helmholtz", [32, 32, 32 * world], 4, 'V', np.complex128), ("poisson", [16, 16, 16 * world], 4, 'K', np.float64),
+             # thin slabs of wide planes (the shape of the 512^3 weak-scaling point: few planes per GPU)
+             ("poisson", [32, 64, 8 * world], 4, 'V', np.float64)]
+    only = os.environ.get("DIST_CHECK_CASES")
+    if only:
+        cases = [cases[int(i)] for i in only.split(",")]
     for kind, n, levels, cyc, VAL in cases:
-        dom = [0, 1, 0, 1, 0, float(world)]
+        dom = [0, 1, 0, n[1] / n[0], 0, n[2] / n[0]]
         p = mg.getMGparam(VAL, np.int64, levels, 8, 5, 1e-12, "Jac", 0.8, 2, 2, cyc)
         p.nrhs = 1
         h = 1.0 / n[0]
