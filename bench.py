@@ -258,6 +258,11 @@ def run_reference(args):
 # our arm
 # ---------------------------------------------------------------------------------------------
 def run_ours(args):
+    # Libraries (NCCL's version banner, ...) may write to stdout: keep file descriptor 1 for the ONE JSON line and
+    # send everything else to stderr.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import multigrid_jl_b200 as mg
 
@@ -442,8 +447,8 @@ def run_ours(args):
                                 "cycle, plus the CSR arrays when the CSR-stream kernels run; L2 is 126 MB)",
                    "parallelism": f"row-partitioned z-slabs x{world}" if world > 1 else "single GPU",
                    "halo_exchange": (None if world == 1 else
-                                     ("own kernels over NVLink peer memory (CUDA IPC, self-validating 8-byte words), run "
-                                      "beside the interior rows of the consuming pass; cycle replayed from a CUDA graph"
+                                     ("own kernels over NVLink peer memory (CUDA IPC, self-validating 8-byte words, one "
+                                      "put+poll kernel per exchange); cycle incl. exchanges replayed from a CUDA graph"
                                       if dinfo["p2p"] else "ncclSend/ncclRecv"))},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "spmv": spmv,
         "kernels": kern[:10],
@@ -457,7 +462,8 @@ def run_ours(args):
                                          f"(restated reference CPU path, unfused, OpenMP)",
                                "ms_per_cycle": tc * 1e3, "effective_gbs": nbytes / tc / 1e9}
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
+    os.close(json_fd)
     dev.destroy()
     if world > 1:
         import torch.distributed as dist

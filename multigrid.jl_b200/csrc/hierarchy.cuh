@@ -123,7 +123,8 @@ struct Context {
     int use_tma = 1;               // 0: never use the TMA-staged dictionary kernel (MGB200_TMA)
     int tma_min_rows = 200000;     // smaller matrices keep the one-pass kernel (too few tiles per SM)
     int split_test = 0;            // > 0: every dictionary pass runs as interior + both ends (test hook)
-    int use_overlap = 1;           // multi-GPU: halo exchange beside the interior rows (MGB200_OVERLAP)
+    int use_overlap = 0;           // multi-GPU: halo exchange beside the interior rows (MGB200_OVERLAP=1; measured
+                                   // slower than the serial exchange at N = 2, profiles/r01e_bench_n2_*: default off)
     cudaStream_t side = nullptr;   // carries the halo exchange of an overlapped pass
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int max_smem_optin = 0;
@@ -151,7 +152,7 @@ struct Context {
         use_graphs = env_int("MGB200_GRAPHS", 1);
         use_tma = env_int("MGB200_TMA", 1);
         tma_min_rows = env_int("MGB200_TMA_MIN_ROWS", 200000);
-        use_overlap = env_int("MGB200_OVERLAP", 1);
+        use_overlap = env_int("MGB200_OVERLAP", 0);
         split_test = env_int("MGB200_SPLIT_TEST", 0);
         int prio_lo = 0, prio_hi = 0;
         MGB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));

@@ -418,6 +418,9 @@ pat_kernel(int rA, int nA, int rB, int nB, const uint16_t* __restrict__ pid, con
 // cp.async.bulk + mbarrier) are in flight.  The dictionary is copied to shared memory once per CTA.  One thread
 // still owns one row and accumulates in stored order: bit-identical to pat_kernel.  (tools/microbench_pat.cu:
 // 105 us against 140 us for the 7-point sweep at 257^3.)
+// The per-tile __syncthreads is the top stall in ncu (profiles/r01e_ncu_full_dictionary_kernels_summary.txt), but
+// releasing the stages per warp through `empty` mbarriers instead (each warp arrives, only the issuing thread
+// waits) measured SLOWER: level-1 sweep 119 -> 125 us, level-2 sweep 46 -> 54 us, cycle 1.033 -> 1.090 ms.
 template <typename TA, typename TV, int MODE, bool DPAT, int NT>
 __global__ void __launch_bounds__(NT)
 pat_tma_kernel(const __grid_constant__ TmaPlan P, int n_rows, int tile0, int ntiles, long long xlo, long long xhi, int npat,
