@@ -155,6 +155,7 @@ struct DistSpace {
     std::vector<int> recv_cnt, recv_off; // per peer (ghosts are grouped by owner because owners hold ranges)
     std::vector<int> send_cnt, send_off;
     int* d_send_idx = nullptr;           // local owned indices to pack, concatenated per peer
+    std::vector<int> send_idx_host;      // the same on the host (fused-put planning)
     int n_send = 0;
     void* sendbuf = nullptr;             // n_send * m * sizeof(TV)
     size_t sendbuf_bytes = 0;

@@ -108,7 +108,8 @@ static double vec_bytes(const Csr<TA>& M, int mode, int m, bool d_from_dict) {
 // persistent CTAs of this one.
 template <typename TA, typename TV>
 static bool launch_pattern_tma(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d,
-                               const TV* dpat, TV* y, int t0 = 0, int t1 = -1, int reserve_threads = 0) {
+                               const TV* dpat, TV* y, int t0 = 0, int t1 = -1, int reserve_threads = 0,
+                               const PutPlan& pp = no_put()) {
     const PatDict<TA>& D = M.pat;
     constexpr int NT = TmaTile<TA>::NT;
     if (!D.tma_ok || !ctx.use_tma || mode == MODE_ADD || sizeof(TA) != sizeof(TV)) return false;
@@ -133,7 +134,7 @@ static bool launch_pattern_tma(Context& ctx, const Csr<TA>& M, int mode, const T
     {                                                                                                          \
         auto kern = pat_tma_kernel<TA, TV, MODE, DP, NT>;                                                      \
         MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx.max_smem_optin));         \
-        kern<<<grid, NT, smem, ctx.stream>>>(D.plan, M.n_rows, t0, ntiles, D.xlo, D.xhi, D.npat, D.nent, D.pid, D.hdr, \
+        kern<<<grid, NT, smem, ctx.stream>>>(D.plan, pp, M.n_rows, t0, ntiles, D.xlo, D.xhi, D.npat, D.nent, D.pid, D.hdr, \
                                              D.ent_s, dpat, x, b, d, y);                                       \
     }
     if (mode == MODE_SPMV) MGB_TL(MODE_SPMV, false)
@@ -148,12 +149,12 @@ static bool launch_pattern_tma(Context& ctx, const Csr<TA>& M, int mode, const T
 // one-pass dictionary kernel over the rows [rA, rA + nA) and [rB, rB + nB)
 template <typename TA, typename TV>
 static void launch_pattern_rows(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d,
-                                const TV* dpat, TV* y, int rA, int nA, int rB, int nB) {
+                                const TV* dpat, TV* y, int rA, int nA, int rB, int nB, const PutPlan& pp = no_put()) {
     const PatDict<TA>& D = M.pat;
     if (nA + nB <= 0) return;
     const int nt = 256, grid = cdiv(nA + nB, nt);
 #define MGB_PL(MODE, RR, DP) \
-    pat_kernel<TA, TV, MODE, RR, DP><<<grid, nt, 0, ctx.stream>>>(rA, nA, rB, nB, D.pid, D.c0, D.pat_off, D.ent, dpat, x, b, d, y)
+    pat_kernel<TA, TV, MODE, RR, DP><<<grid, nt, 0, ctx.stream>>>(pp, rA, nA, rB, nB, D.pid, D.c0, D.pat_off, D.ent, dpat, x, b, d, y)
 #define MGB_PCASE(MODE)                                     \
     case MODE:                                              \
         if (D.rowrel) {                                     \
@@ -177,9 +178,9 @@ static void launch_pattern_rows(Context& ctx, const Csr<TA>& M, int mode, const 
 
 template <typename TA, typename TV>
 static void launch_pattern_mode(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d,
-                                const TV* dpat, TV* y) {
-    if (M.pat.rowrel && launch_pattern_tma<TA, TV>(ctx, M, mode, x, b, d, dpat, y)) return;
-    launch_pattern_rows<TA, TV>(ctx, M, mode, x, b, d, dpat, y, 0, M.n_rows, 0, 0);
+                                const TV* dpat, TV* y, const PutPlan& pp = no_put()) {
+    if (M.pat.rowrel && launch_pattern_tma<TA, TV>(ctx, M, mode, x, b, d, dpat, y, 0, -1, 0, pp)) return;
+    launch_pattern_rows<TA, TV>(ctx, M, mode, x, b, d, dpat, y, 0, M.n_rows, 0, 0, pp);
 }
 
 // Split form of a dictionary pass: the rows [lo, hi) first, then `between()` (the caller joins the stream that
@@ -188,36 +189,39 @@ static void launch_pattern_mode(Context& ctx, const Csr<TA>& M, int mode, const 
 // accumulation order as the unsplit pass: bit-identical results.
 template <typename TA, typename TV, typename F>
 static void pattern_apply_split(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d,
-                                const TV* dpat, TV* y, int lo, int hi, int reserve_threads, F&& between) {
+                                const TV* dpat, TV* y, int lo, int hi, int reserve_threads, F&& between,
+                                const PutPlan& pp = no_put()) {
     constexpr int NT = TmaTile<TA>::NT;
     int a0 = lo, a1 = hi;
     bool done = false;
     if (M.pat.rowrel) {
         const int t0 = cdiv(lo, NT), t1 = hi / NT;
-        if (t1 > t0 && launch_pattern_tma<TA, TV>(ctx, M, mode, x, b, d, dpat, y, t0, t1, reserve_threads)) {
+        if (t1 > t0 && launch_pattern_tma<TA, TV>(ctx, M, mode, x, b, d, dpat, y, t0, t1, reserve_threads, pp)) {
             a0 = t0 * NT;
             a1 = t1 * NT;
             done = true;
         }
     }
-    if (!done) launch_pattern_rows<TA, TV>(ctx, M, mode, x, b, d, dpat, y, a0, a1 - a0, 0, 0);
+    if (!done) launch_pattern_rows<TA, TV>(ctx, M, mode, x, b, d, dpat, y, a0, a1 - a0, 0, 0, pp);
     between();
-    launch_pattern_rows<TA, TV>(ctx, M, mode, x, b, d, dpat, y, 0, a0, a1, M.n_rows - a1);
+    launch_pattern_rows<TA, TV>(ctx, M, mode, x, b, d, dpat, y, 0, a0, a1, M.n_rows - a1, pp);
 }
 
-// y = op(M x): the one entry point the cycle uses for A, P and R.
+// y = op(M x): the one entry point the cycle uses for A, P and R.  `pp` (dictionary kernels only - the caller checks
+// pattern_in_use before it relies on the put) makes the kernel store the slab-end rows of y to the neighbours.
 template <typename TA, typename TV>
 static void csr_apply(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d, TV* y,
-                      int m, int kind, int level, const TV* dpat = nullptr) {
+                      int m, int kind, int level, const TV* dpat = nullptr, const PutPlan& pp = no_put()) {
     MGB_CHECK(M.present(), "matrix not uploaded");
     const bool use_pat = M.pat.present && m == 1 && ctx.use_patterns;
+    MGB_CHECK(!pp.on || use_pat, "fused put needs the stencil-dictionary format");
     const double fmt = use_pat ? M.pat.matrix_bytes(M.n_rows) + vec_bytes<TA, TV>(M, mode, m, dpat != nullptr) : -1.0;
     Launch L(ctx, kind, level, csr_bytes<TA, TV>(M, mode, m), fmt);
     if (use_pat && ctx.split_test > 0 && M.n_rows > 2 * ctx.split_test) {
         // test hook (mgb200_set_option "split_test"): the split launch sequence of the multi-GPU overlap path
-        pattern_apply_split<TA, TV>(ctx, M, mode, x, b, d, dpat, y, ctx.split_test, M.n_rows - ctx.split_test, 16384, [] {});
+        pattern_apply_split<TA, TV>(ctx, M, mode, x, b, d, dpat, y, ctx.split_test, M.n_rows - ctx.split_test, 16384, [] {}, pp);
     } else if (use_pat) {
-        launch_pattern_mode<TA, TV>(ctx, M, mode, x, b, d, dpat, y);
+        launch_pattern_mode<TA, TV>(ctx, M, mode, x, b, d, dpat, y, pp);
     } else if (!M.staged) {
         launch_rowwarp_mode<TA, TV>(ctx, M, mode, x, b, d, y, m);
     } else if (m > 1) {
@@ -242,11 +246,12 @@ static bool pattern_in_use(const Context& ctx, const Csr<TA>& M, int m) {
 }
 template <typename TA, typename TV, typename F>
 static void csr_apply_split(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d, TV* y,
-                            int kind, int level, const TV* dpat, int lo, int hi, int reserve_threads, F&& between) {
+                            int kind, int level, const TV* dpat, int lo, int hi, int reserve_threads, F&& between,
+                            const PutPlan& pp = no_put()) {
     MGB_CHECK(pattern_in_use(ctx, M, 1), "split launch needs the stencil-dictionary format");
     const double fmt = M.pat.matrix_bytes(M.n_rows) + vec_bytes<TA, TV>(M, mode, 1, dpat != nullptr);
     Launch L(ctx, kind, level, csr_bytes<TA, TV>(M, mode, 1), fmt);
-    pattern_apply_split<TA, TV>(ctx, M, mode, x, b, d, dpat, y, lo, hi, reserve_threads, between);
+    pattern_apply_split<TA, TV>(ctx, M, mode, x, b, d, dpat, y, lo, hi, reserve_threads, between, pp);
 }
 
 // ---- reductions / vector ops -----------------------------------------------------------------

@@ -422,6 +422,7 @@ int mgb200_set_option(mgb200_handle h, const char* key, int64_t value) {
         else if (k == "tma_min_rows") H->ctx.tma_min_rows = (int)value;
         else if (k == "split_test") H->ctx.split_test = (int)value;
         else if (k == "overlap") H->ctx.use_overlap = (int)value;
+        else if (k == "fused_put") H->use_fused_put = (int)value;
         else throw Error(-1, "mgb200_set_option: unknown key " + k);
         H->invalidate_graphs();
     });

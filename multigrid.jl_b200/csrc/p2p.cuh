@@ -29,6 +29,7 @@
 // If the peers are not IPC/P2P reachable the hierarchy keeps the NCCL path (solver.cuh).
 #pragma once
 #include "dist.cuh"
+#include "ll.cuh"
 
 namespace mgb200 {
 
@@ -54,48 +55,6 @@ struct ChanDev {
     int world, rank;
 };
 
-// ---- LL ("low latency") words: every 8-byte word carries 4 bytes of payload and the exchange number ----------
-// An aligned 8-byte store is single-copy atomic, also across NVLink, so the receiver can poll the word itself:
-// no fence, no separate flag, no ordering between words.  (The same idea as NCCL's LL protocol.)  A double
-// travels as two words, a complex number as four; the receive buffers are twice the size of the data.
-__device__ __forceinline__ void st_ll(unsigned long long* p, unsigned lo, unsigned flag) {
-    const unsigned long long w = (unsigned long long)lo | ((unsigned long long)flag << 32);
-    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
-}
-__device__ __forceinline__ unsigned ld_ll(const unsigned long long* p, unsigned flag) {
-    unsigned long long w;
-    do {
-        asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
-    } while ((unsigned)(w >> 32) != flag);
-    return (unsigned)w;
-}
-template <typename TV>
-struct LL;
-template <>
-struct LL<double> {
-    static constexpr int W = 2;   // words per element
-    __device__ static __forceinline__ void put(unsigned long long* dst, double v, unsigned flag) {
-        st_ll(dst, (unsigned)__double2loint(v), flag);
-        st_ll(dst + 1, (unsigned)__double2hiint(v), flag);
-    }
-    __device__ static __forceinline__ double get(const unsigned long long* src, unsigned flag) {
-        const unsigned lo = ld_ll(src, flag), hi = ld_ll(src + 1, flag);
-        return __hiloint2double((int)hi, (int)lo);
-    }
-};
-template <>
-struct LL<cplx> {
-    static constexpr int W = 4;
-    __device__ static __forceinline__ void put(unsigned long long* dst, cplx v, unsigned flag) {
-        LL<double>::put(dst, v.x, flag);
-        LL<double>::put(dst + 2, v.y, flag);
-    }
-    __device__ static __forceinline__ cplx get(const unsigned long long* src, unsigned flag) {
-        const double a = LL<double>::get(src, flag), b = LL<double>::get(src + 2, flag);
-        return make_cplx(a, b);
-    }
-};
-
 // The exchange number is advanced by the last CTA to finish (every CTA has read it by then).
 __device__ __forceinline__ void p2p_advance(unsigned long long e, unsigned long long* epoch, unsigned* ticket) {
     __syncthreads();
@@ -109,7 +68,7 @@ template <typename TV>
 __global__ void p2p_halo_kernel(const ChanDev<TV>* __restrict__ cd, TV* __restrict__ v,
                                 const int* __restrict__ send_idx, int n_send, long long n_ghost, long long n_lo,
                                 long long n_owned, int m, unsigned long long* epoch, unsigned* ticket,
-                                unsigned long long* trace) {
+                                unsigned long long* trace, int skip_put) {
     constexpr int W = LL<TV>::W;
     const unsigned long long e = *epoch + 1;
     const int par = (int)(e & 1);
@@ -117,7 +76,7 @@ __global__ void p2p_halo_kernel(const ChanDev<TV>* __restrict__ cd, TV* __restri
     const bool tr = trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
     unsigned long long* trow = trace + (e % P2P_TRACE_ROWS) * 4;
     if (tr) trow[0] = globaltimer_ns();
-    const long long total = (long long)n_send * m;
+    const long long total = skip_put ? 0 : (long long)n_send * m;   // skip_put: the producing kernel stored the rows
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
          t += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(t / m), j = (int)(t % m);
@@ -169,6 +128,7 @@ __global__ void p2p_gather_kernel(const ChanDev<TV>* __restrict__ cd, TV* __rest
 // host side of one channel
 struct ChanHost {
     bool used = false;
+    PutPlan put = no_put();    // halo channels whose send sets are the two end ranges of the owned rows (fused put)
     long long rows = 0;        // rows of the receive buffer (per parity): n_ghost (halo) or nc_global (gather)
     size_t buf_off[2] = {0, 0};  // byte offsets of the receive buffers inside my block
     void* dev = nullptr;       // ChanDev<TV> on the device

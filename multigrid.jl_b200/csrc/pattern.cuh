@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "ll.cuh"
 
 namespace mgb200 {
 
@@ -377,7 +378,8 @@ __device__ __forceinline__ PatEntry<cplx> ldg_ent(const PatEntry<cplx>* p) {
 // split form serves the rows next to the slab ends after a halo exchange that ran beside the interior rows.
 template <typename TA, typename TV, int MODE, bool ROWREL, bool DPAT>
 __global__ void __launch_bounds__(256)
-pat_kernel(int rA, int nA, int rB, int nB, const uint16_t* __restrict__ pid, const int* __restrict__ c0,
+pat_kernel(const __grid_constant__ PutPlan pp, int rA, int nA, int rB, int nB, const uint16_t* __restrict__ pid,
+           const int* __restrict__ c0,
            const int* __restrict__ pat_off, const PatEntry<TA>* __restrict__ ent,
            const TV* __restrict__ dpat, const TV* __restrict__ x, const TV* __restrict__ b,
            const TV* __restrict__ d, TV* __restrict__ y) {
@@ -400,16 +402,19 @@ pat_kernel(int rA, int nA, int rB, int nB, const uint16_t* __restrict__ pid, con
         const PatEntry<TA> e = ldg_ent(ent + k);
         acc = acc + e.v * ldg_(x + (base + e.delta));
     }
+    TV out;
     if (MODE == 0) {
-        y[row] = acc;
+        out = acc;
     } else if (MODE == 1) {
-        y[row] = xval + acc;
+        out = xval + acc;
     } else if (MODE == 2) {
-        y[row] = bval - acc;
+        out = bval - acc;
     } else {
         const TV r = bval - acc;
-        y[row] = xval + dval * r;
+        out = xval + dval * r;
     }
+    y[row] = out;
+    if (pp.on) ll_put_edge<TV>(pp, row, out);
 }
 
 // ---- TMA-staged variant ----------------------------------------------------------------------------------
@@ -423,7 +428,7 @@ pat_kernel(int rA, int nA, int rB, int nB, const uint16_t* __restrict__ pid, con
 // waits) measured SLOWER: level-1 sweep 119 -> 125 us, level-2 sweep 46 -> 54 us, cycle 1.033 -> 1.090 ms.
 template <typename TA, typename TV, int MODE, bool DPAT, int NT>
 __global__ void __launch_bounds__(NT)
-pat_tma_kernel(const __grid_constant__ TmaPlan P, int n_rows, int tile0, int ntiles, long long xlo, long long xhi, int npat,
+pat_tma_kernel(const __grid_constant__ TmaPlan P, const __grid_constant__ PutPlan pp, int n_rows, int tile0, int ntiles, long long xlo, long long xhi, int npat,
                int nent, const uint16_t* __restrict__ pid, const int* __restrict__ hdr,
                const PatEntry<TA>* __restrict__ ent_s, const TV* __restrict__ dpat, const TV* __restrict__ x,
                const TV* __restrict__ b, const TV* __restrict__ d, TV* __restrict__ y) {
@@ -498,15 +503,18 @@ pat_tma_kernel(const __grid_constant__ TmaPlan P, int n_rows, int tile0, int nti
                 const PatEntry<TA> e = se[k];
                 acc = acc + e.v * sxt[e.delta];
             }
+            TV out;
             if (MODE == 0) {
-                y[row] = acc;
+                out = acc;
             } else if (MODE == 2) {
-                y[row] = sb[t] - acc;
+                out = sb[t] - acc;
             } else {
                 const TV dval = DPAT ? sdp[p] : sd[t];
                 const TV res = sb[t] - acc;
-                y[row] = sxt[P.centre] + dval * res;
+                out = sxt[P.centre] + dval * res;
             }
+            y[row] = out;
+            if (pp.on) ll_put_edge<TV>(pp, row, out);
         }
         __syncthreads();
     }
@@ -514,13 +522,15 @@ pat_tma_kernel(const __grid_constant__ TmaPlan P, int n_rows, int tile0, int nti
 
 // x = d .* b with d from the dictionary (first sweep of a cycle from x = 0)
 template <typename TV>
-__global__ void diag_scale_pat_kernel(long long n, const uint16_t* __restrict__ pid, const TV* __restrict__ dpat,
-                                      const TV* __restrict__ b, TV* __restrict__ x) {
+__global__ void diag_scale_pat_kernel(const __grid_constant__ PutPlan pp, long long n, const uint16_t* __restrict__ pid,
+                                      const TV* __restrict__ dpat, const TV* __restrict__ b, TV* __restrict__ x) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
         const int p = __ldg(reinterpret_cast<const unsigned short*>(pid) + i);
-        x[i] = VT<TV>::zero() + ldg_(dpat + p) * b[i];
+        const TV out = VT<TV>::zero() + ldg_(dpat + p) * b[i];
+        x[i] = out;
+        if (pp.on) ll_put_edge<TV>(pp, i, out);
     }
 }
 

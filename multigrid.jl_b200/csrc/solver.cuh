@@ -114,6 +114,10 @@ struct Hierarchy : HierarchyBase {
     TV *ux0 = nullptr, *ux1 = nullptr, *ucur = nullptr;
     Comm comm;                 // NCCL communicator (world == 1: inactive)
     P2P p2p;                   // halo exchange / coarse gather over NVLink peer memory (p2p.cuh)
+    // fused put (ll.cuh): put_done[l] = the level-l vector whose slab-end rows its producing kernel has already
+    // stored to the neighbours for the NEXT exchange of channel l; that exchange then only polls and unpacks
+    std::vector<const TV*> put_done;
+    int use_fused_put = 1;
     bool dist_finalized = true;
     // V/F/W cycles have no host synchronisation: each (buffers, x-is-zero, type) variant is captured
     // once into a CUDA graph and replayed, which removes the launch gaps of the coarse levels
@@ -135,8 +139,10 @@ struct Hierarchy : HierarchyBase {
         m = nrhs;
         relax_kind = rk;
         L.resize(levels);
+        put_done.assign(levels, nullptr);
         set_cycle(ct, rpre, rpost);
         ctx.init(dev);
+        use_fused_put = env_int("MGB200_FUSED_PUT", 1);
     }
     ~Hierarchy() override {
         cudaSetDevice(ctx.device);
@@ -431,6 +437,7 @@ struct Hierarchy : HierarchyBase {
             }
             sp.d_send_idx = dev_alloc<int>(std::max(sp.n_send, 1));
             MGB_CUDA(cudaMemcpy(sp.d_send_idx, idx.data(), sp.n_send * sizeof(int), cudaMemcpyHostToDevice));
+            sp.send_idx_host.assign(idx.begin(), idx.begin() + sp.n_send);
         }
         // 3. remap columns and upload
         for (int l = 0; l < levels - 1; ++l) {
@@ -563,8 +570,23 @@ struct Hierarchy : HierarchyBase {
     void apply_A(const Csr<TV>& A, const TV* x, TV* y, int level) {  // y = A x   (getAfun, SolveFuncs.jl:65-71)
         apply_x<TV>(level - 1, A, MODE_SPMV, const_cast<TV*>(x), nullptr, nullptr, y, K_SPMV, level);
     }
-    void residual(const Csr<TV>& A, const TV* b, const TV* x, TV* r, int level) {  // r = b - A x
-        apply_x<TV>(level - 1, A, MODE_RESID, const_cast<TV*>(x), b, nullptr, r, K_RESID, level);
+    // r = b - A x; put_level >= 0: r is a level-(put_level+1) vector that is exchanged next (fused put)
+    void residual(const Csr<TV>& A, const TV* b, const TV* x, TV* r, int level, int put_level = -1) {
+        apply_x<TV>(level - 1, A, MODE_RESID, const_cast<TV*>(x), b, nullptr, r, K_RESID, level, nullptr, put_level);
+    }
+    // Plan for a kernel that produces level-l vector `out` which the NEXT operation on channel l exchanges: the
+    // kernel stores the slab-end rows to the neighbours itself.  Only callers that know that exchange follows may
+    // ask (a put without its exchange would leave words of the same exchange number behind).
+    PutPlan make_put(int l, const Csr<TV>* /*unused*/ = nullptr) {
+        if (l < 0 || l >= levels || !use_fused_put || !p2p.on || !comm.active() || !L[l].sp.dist || m != 1 ||
+            !ctx.use_patterns || ctx.profiling)
+            return no_put();
+        return p2p.chan[l].put;
+    }
+    void note_put(int l, const PutPlan& pp, const TV* out) {
+        if (!pp.on) return;
+        MGB_CHECK(put_done[l] == nullptr, "fused put: the previous put of this channel was never exchanged");
+        put_done[l] = out;
     }
     // y = op(M v) for a level-(lin+1) input vector v whose ghost rows must be refreshed first (row-partitioned
     // levels).  With the peer-memory exchange (p2p.cuh) the refresh runs on a second, high-priority stream BESIDE
@@ -573,13 +595,15 @@ struct Hierarchy : HierarchyBase {
     static constexpr int OVERLAP_HALO_CTAS = 64;   // x 256 threads: the room the interior kernel leaves free
     template <typename TA>
     void apply_x(int lin, const Csr<TA>& M, int mode, TV* v, const TV* b, const TV* d, TV* y, int kind, int level,
-                 const TV* dpat = nullptr) {
+                 const TV* dpat = nullptr, int put_level = -1) {
+        PutPlan pp = (put_level >= 0 && pattern_in_use(ctx, M, m)) ? make_put(put_level) : no_put();
         const bool need = comm.active() && lin >= 0 && lin < levels && L[lin].sp.dist;
         const bool split = need && p2p.on && ctx.use_overlap && !ctx.profiling && pattern_in_use(ctx, M, m) &&
                            2LL * (M.int_hi - M.int_lo) >= M.n_rows;
         if (!split) {
             if (need) exchange(lin, v);
-            csr_apply<TA, TV>(ctx, M, mode, v, b, d, y, m, kind, level, dpat);
+            csr_apply<TA, TV>(ctx, M, mode, v, b, d, y, m, kind, level, dpat, pp);
+            note_put(put_level, pp, y);
             return;
         }
         MGB_CUDA(cudaEventRecord(ctx.ev_fork, ctx.stream));
@@ -587,7 +611,8 @@ struct Hierarchy : HierarchyBase {
         exchange(lin, v, ctx.side, OVERLAP_HALO_CTAS);
         MGB_CUDA(cudaEventRecord(ctx.ev_join, ctx.side));
         csr_apply_split<TA, TV>(ctx, M, mode, v, b, d, y, kind, level, dpat, M.int_lo, M.int_hi, OVERLAP_HALO_CTAS * 256,
-                                [&] { MGB_CUDA(cudaStreamWaitEvent(ctx.stream, ctx.ev_join, 0)); });
+                                [&] { MGB_CUDA(cudaStreamWaitEvent(ctx.stream, ctx.ev_join, 0)); }, pp);
+        note_put(put_level, pp, y);
     }
     // reductions over a distributed level are completed by an in-place all-reduce on the stream
     void allreduce(int l, double* dptr, int k) {
@@ -617,6 +642,12 @@ struct Hierarchy : HierarchyBase {
         if (!stream) stream = ctx.stream;
         MGB_CHECK(stream == ctx.stream || p2p.on, "only the peer-memory exchange runs on a side stream");
         Launch La(ctx, K_COPY, l + 1, 2.0 * sp.n_ghost * m * sizeof(TV));
+        int skip_put = 0;
+        if (put_done[l]) {
+            MGB_CHECK(p2p.on && put_done[l] == v, "fused put: another vector is exchanged than the one that was put");
+            put_done[l] = nullptr;
+            skip_put = 1;
+        }
         if (p2p.on) {
             // put into the neighbours' receive buffers over NVLink, then wait for theirs and unpack (p2p.cuh)
             ChanDev<TV>* cd = static_cast<ChanDev<TV>*>(p2p.chan[l].dev);
@@ -627,7 +658,8 @@ struct Hierarchy : HierarchyBase {
             if (max_ctas > 0) g = std::min(g, max_ctas);
             p2p_halo_kernel<TV><<<g, 256, 0, stream>>>(cd, v, sp.d_send_idx, sp.n_send, sp.n_ghost, sp.n_lo,
                                                             sp.n_owned, m, p2p.epoch + l, p2p.ticket + l,
-                                                            p2p.trace ? p2p.trace + (size_t)l * P2P_TRACE_ROWS * 4 : nullptr);
+                                                            p2p.trace ? p2p.trace + (size_t)l * P2P_TRACE_ROWS * 4 : nullptr,
+                                                            skip_put);
             MGB_LAUNCH_CHECK();
             return;
         }
@@ -840,6 +872,33 @@ struct Hierarchy : HierarchyBase {
             }
             MGB_CUDA(cudaMalloc(&ch.dev, sizeof(cd)));
             MGB_CUDA(cudaMemcpy(ch.dev, &cd, sizeof(cd), cudaMemcpyHostToDevice));
+            // fused put (ll.cuh): possible when the rows the neighbours asked for are exactly the two end ranges of
+            // the owned rows, in order (z-slabs: first plane to the rank below, last plane to the rank above)
+            ch.put = no_put();
+            if (!gather && m == 1) {
+                const DistSpace& sp = lg.sp;
+                bool ok = true;
+                for (int q = 0; q < w; ++q)
+                    if (sp.send_cnt[q] > 0 && q != r - 1 && q != r + 1) ok = false;
+                const int lo_cnt = r > 0 ? sp.send_cnt[r - 1] : 0, hi_cnt = r + 1 < w ? sp.send_cnt[r + 1] : 0;
+                const long long hi_start = sp.n_owned - hi_cnt;
+                if (ok && (int)sp.send_idx_host.size() == sp.n_send) {
+                    for (int k = 0; k < lo_cnt && ok; ++k) ok = sp.send_idx_host[sp.send_off[r - 1] + k] == k;
+                    for (int k = 0; k < hi_cnt && ok; ++k) ok = sp.send_idx_host[sp.send_off[r + 1] + k] == hi_start + k;
+                } else {
+                    ok = false;
+                }
+                if (ok && lo_cnt + hi_cnt > 0) {
+                    ch.put.on = 1;
+                    ch.put.lo_cnt = lo_cnt;
+                    ch.put.hi_cnt = hi_cnt;
+                    ch.put.hi_start = hi_cnt > 0 ? (int)hi_start : 0x7fffffff;
+                    for (int par = 0; par < 2; ++par) {
+                        ch.put.dst_lo[par] = lo_cnt > 0 ? reinterpret_cast<unsigned long long*>(cd.dst[par][r - 1]) : nullptr;
+                        ch.put.dst_hi[par] = hi_cnt > 0 ? reinterpret_cast<unsigned long long*>(cd.dst[par][r + 1]) : nullptr;
+                    }
+                }
+            }
         }
         if (env_int("MGB200_P2P_TRACE", 0)) {
             p2p.trace = dev_alloc<unsigned long long>((size_t)nchan * P2P_TRACE_ROWS * 4);
@@ -849,20 +908,26 @@ struct Hierarchy : HierarchyBase {
         p2p.ticket = dev_alloc<unsigned>(nchan);
         MGB_CUDA(cudaMemset(p2p.epoch, 0, nchan * sizeof(unsigned long long)));
         MGB_CUDA(cudaMemset(p2p.ticket, 0, nchan * sizeof(unsigned)));
+        for (int c = 0; c < levels; ++c) p2p.chan[c].put.epoch = p2p.epoch + c;
+        put_done.assign(levels, nullptr);
         p2p.on = true;
     }
     static TV to_tv(zc a) { return VT<TV>::make(a.real(), a.imag()); }
 
     // relax (MGcycle.jl:122-136) fused: each sweep is  x' = x + d.*(b - A x).  With x known to be
     // zero the first sweep is x = d.*b.  Returns the buffer holding the result (x or scratch).
-    TV* relax(int l, const TV* b, TV* x, TV* scratch, int numit, bool xzero) {
+    // last_exchanged: the caller knows that the vector returned is the next one exchanged on channel l
+    // (fused put, ll.cuh); the intermediate iterates always are (by the next sweep).
+    TV* relax(int l, const TV* b, TV* x, TV* scratch, int numit, bool xzero, bool last_exchanged = false) {
         Level<TV>& lv = L[l];
         int sweeps = std::max(numit, 1);  // numit = 0 still does one update (MGcycle.jl:134)
         const TV* dpat = (lv.dpat && m == 1 && ctx.use_patterns) ? lv.dpat : nullptr;
         if (xzero) {
             if (dpat) {
+                const PutPlan pp = (sweeps > 1 || last_exchanged) ? make_put(l) : no_put();
                 Launch La(ctx, K_DIAG, l + 1, 3.0 * lv.n * sizeof(TV), lv.n * (2.0 * sizeof(TV) + 2.0));
-                diag_scale_pat_kernel<TV><<<ctx.ew_blocks(lv.n), 256, 0, ctx.stream>>>(lv.n, lv.A.pat.pid, dpat, b, x);
+                diag_scale_pat_kernel<TV><<<ctx.ew_blocks(lv.n), 256, 0, ctx.stream>>>(pp, lv.n, lv.A.pat.pid, dpat, b, x);
+                note_put(l, pp, x);
             } else {
                 Launch La(ctx, K_DIAG, l + 1, (2.0 * m + 1.0) * lv.n * sizeof(TV));
                 diag_scale_kernel<TV><<<ctx.ew_blocks(lv.n * m), 256, 0, ctx.stream>>>(lv.n, m, lv.d, b, x);
@@ -871,7 +936,8 @@ struct Hierarchy : HierarchyBase {
             sweeps -= 1;
         }
         for (int s = 0; s < sweeps; ++s) {
-            apply_x<TV>(l, lv.A, MODE_SWEEP, x, b, lv.d, scratch, K_SWEEP, l + 1, dpat);
+            const bool put = (s + 1 < sweeps) || last_exchanged;
+            apply_x<TV>(l, lv.A, MODE_SWEEP, x, b, lv.d, scratch, K_SWEEP, l + 1, dpat, put ? l : -1);
             std::swap(x, scratch);
         }
         return x;
@@ -975,10 +1041,10 @@ struct Hierarchy : HierarchyBase {
             if (xzero) dev_copy<TV>(ctx, lv.n * m, b, lv.r); else residual(lv.A, b, x, lv.r, l + 1);
             jac_gmres(l, lv.r, x, std::max(npre, 1));
         } else {
-            TV* xn = relax(l, b, x, scratch, npre, xzero);
+            TV* xn = relax(l, b, x, scratch, npre, xzero, true);   // the residual below exchanges the result
             if (xn != x) std::swap(x, scratch);
         }
-        residual(lv.A, b, x, lv.r, l + 1);                                          // :58-60
+        residual(lv.A, b, x, lv.r, l + 1, relax_kind == 0 ? l : -1);                // :58-60; r is exchanged for R
         if (lv.sp.dist && !lc.sp.dist) {
             // last distributed level: each rank restricts its own coarse rows, then the pieces are gathered
             apply_x<double>(l, lv.R, MODE_SPMV, lv.r, nullptr, nullptr,
@@ -1006,14 +1072,18 @@ struct Hierarchy : HierarchyBase {
                 xc_cur = cycle(l + 1, lc.b, xc_cur, other, false, 'V');            // :81-85
             }
         }
-        apply_x<double>(l + 1, lv.P, MODE_ADD, xc_cur, nullptr, nullptr, x, K_PROLONG, l + 1);  // :90
+        // the corrected x is exchanged by the first post-sweep
+        apply_x<double>(l + 1, lv.P, MODE_ADD, xc_cur, nullptr, nullptr, x, K_PROLONG, l + 1, nullptr,
+                        relax_kind == 0 ? l : -1);                                  // :90
         // ---- post-relaxation (:92-103) ----
         if (relax_kind == 1) {
             residual(lv.A, b, x, lv.r, l + 1);
             jac_gmres(l, lv.r, x, std::max(npost, 1));
             return x;
         }
-        return relax(l, b, x, scratch, npost, false);
+        // below the finest level the result goes back to a parent that exchanges it next (its prolongation, or the
+        // first sweep of the second visit of a W / F cycle); the K-cycle parent copies it around first
+        return relax(l, b, x, scratch, npost, false, l >= 1 && ctype != 'K');
     }
 
     // "Jac-GMRES" smoother: FGMRES_relaxation with MM(v) = D.*v (MGcycle.jl:33-36,48-51,96-99)
@@ -1031,11 +1101,21 @@ struct Hierarchy : HierarchyBase {
         fgmres_relaxation(lv.A, l + 1, r, x, inner, mm, 1e-5, mem, lv.n);
     }
 
+    // every fused put must have met its exchange by the end of a cycle (a put left behind would leave words that
+    // carry the number of the NEXT exchange in the neighbours' buffers)
+    void check_no_pending_put() {
+        for (int l = 0; l < levels; ++l)
+            MGB_CHECK(put_done[l] == nullptr, "fused put without its exchange at the end of a cycle");
+    }
     // cycle from the finest level, replayed from a CUDA graph when the cycle has no host read-backs
     TV* cycle_fine(const TV* b, TV* x, TV* scratch, bool xzero, char ctype) {
         const bool can = ctx.use_graphs && !ctx.profiling && relax_kind == 0 && ctype != 'K' && coarse.kind == 0 &&
                          (!comm.active() || p2p.on) && levels > 1;
-        if (!can) return cycle(0, b, x, scratch, xzero, ctype);
+        if (!can) {
+            TV* res = cycle(0, b, x, scratch, xzero, ctype);
+            check_no_pending_put();
+            return res;
+        }
         const auto key = std::make_tuple(b, x, scratch, xzero, ctype);
         auto it = graphs.find(key);
         if (it == graphs.end()) {
@@ -1045,6 +1125,7 @@ struct Hierarchy : HierarchyBase {
             cudaGraph_t g = nullptr;
             try {
                 res = cycle(0, b, x, scratch, xzero, ctype);
+                check_no_pending_put();
             } catch (...) {
                 cudaStreamEndCapture(ctx.stream, &g);
                 if (g) cudaGraphDestroy(g);
