@@ -22,6 +22,7 @@
 #pragma once
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <thread>
 #include <unordered_map>
 #include <vector>
@@ -289,9 +290,16 @@ static bool build_tma_plan(const HostPatterns<TA>& H, int tile, TmaPlan& P, std:
         sb += len;
         ++nw;
     };
+    // Two windows cost 2 * tile + their spans, the merged one tile + spans + gap: merge whenever the gap between
+    // neighbouring offsets is below the tile length.  For a lexicographic 3-D stencil the y-neighbour lines then share
+    // the copy of the centre line (3 windows instead of 5 for the 7-point level of cfg2, 3 instead of 9 for the 27-point
+    // levels): less L2 -> shared-memory traffic and a stage small enough for 2 CTAs per SM on the 27-point levels.
+    // MGB200_TMA_GAP restores another threshold (32 = the round-1 plan) for A/B measurements.
+    const char* gs = std::getenv("MGB200_TMA_GAP");
+    const int gap = gs ? std::atoi(gs) : tile - 1;
     int lo = ds[0], hi = ds[0];
     for (size_t i = 1; i < ds.size(); ++i) {
-        if (ds[i] - hi <= 32) {
+        if (ds[i] - hi <= gap) {
             hi = ds[i];
             continue;
         }
