@@ -34,6 +34,8 @@ typedef struct mgb200_hierarchy* mgb200_handle;
 /* value types (VAL of MGparam{VAL,IND}, src/Multigrid/MGdef.jl:91) */
 #define MGB200_FP64 0
 #define MGB200_CFP64 1
+#define MGB200_FP32 2   /* Float32 / ComplexF32 hierarchies (getMGparam(Float32,...): `singlePrecision`, MGdef.jl:119,151;   */
+#define MGB200_CFP32 3  /* MGsetup.jl:31-33,79-82,108-110): every array of the handle, b and x included, is single precision */
 
 /* relaxation kinds */
 #define MGB200_RELAX_DIAG 0     /* "Jac" and "SPAI": x += d .* r (MGcycle.jl:122-136)          */
@@ -53,14 +55,14 @@ int mgb200_destroy(mgb200_handle h);
 /* Upload level l < levels of the hierarchy: As[l], Ps[l], Rs[l], relaxPrecs[l].
  *   n   = size(As[l],2) rows of A_l;  nc = rows of A_{l+1}
  *   A:  colptr[n+1],  rowval, nzval (VAL)             CSC of A_l^H   (n x n)
- *   P:  colptr[n+1],  rowval, nzval (real Float64)    CSC of P_l^T   (nc x n)
- *   R:  colptr[nc+1], rowval, nzval (real Float64)    CSC of R_l^T   (n x nc)
+ *   P:  colptr[n+1],  rowval, nzval (real(VAL))       CSC of P_l^T   (nc x n)
+ *   R:  colptr[nc+1], rowval, nzval (real(VAL))       CSC of R_l^T   (n x nc)
  *   d:  relaxPrecs[l] (VAL, length n)
  * index_base is 1 for Julia arrays, 0 for C/NumPy arrays. */
 int mgb200_upload_level(mgb200_handle h, int level, int64_t n, int64_t nc,
                         const int64_t* a_colptr, const int64_t* a_rowval, const void* a_nzval,
-                        const int64_t* p_colptr, const int64_t* p_rowval, const double* p_nzval,
-                        const int64_t* r_colptr, const int64_t* r_rowval, const double* r_nzval,
+                        const int64_t* p_colptr, const int64_t* p_rowval, const void* p_nzval,
+                        const int64_t* r_colptr, const int64_t* r_rowval, const void* r_nzval,
                         const void* d, int index_base);
 
 /* defineCoarsestAinv (MGsetup.jl:323-355, default branch): As[end] = A_L^H in CSC; densified,
@@ -73,6 +75,14 @@ int mgb200_upload_coarsest(mgb200_handle h, int64_t n, const int64_t* colptr, co
  * x = 0; one restart of KrylovMethods.fgmres(10), tol 0.01, right-preconditioned by d.*v (nrhs = 1). */
 int mgb200_upload_coarsest_gmres(mgb200_handle h, int64_t n, const int64_t* colptr, const int64_t* rowval,
                                  const void* nzval, const void* d, int index_base);
+
+/* Mixed precision (getMultigridPreconditioner with VAL != eltype(B), SolveFuncs.jl:52-60): a double-precision handle
+ * that holds no hierarchy of its own, only the Krylov matrix (mgb200_set_krylov_matrix, mandatory) and the Krylov
+ * vectors; its preconditioner is one cycle of the single-precision hierarchy `inner` (MGB200_FP32 -> an MGB200_FP64
+ * outer handle, MGB200_CFP32 -> MGB200_CFP64):  bl .= r (rounded to single); z .= 0; recursiveCycle(param,bl,z,1);
+ * z2 .= z (widened).  n and nrhs are taken from `inner`, which must outlive the outer handle.  The Krylov drivers
+ * (mgb200_solveCG / solveFGMRES / solveBiCGSTAB and their block forms) run on the outer handle. */
+int mgb200_create_mixed(mgb200_handle* outer, mgb200_handle inner);
 
 /* Optional: the matrix the Krylov drivers multiply with when it is not As[1]
  * (solveCG_MG(AT,param,...) takes AT separately, SolveFuncs.jl:77-82).  CSC of A^H. */
@@ -157,8 +167,8 @@ int mgb200_dist_init(mgb200_handle h, int rank, int world, const char* unique_id
 int mgb200_dist_upload_level(mgb200_handle h, int level, int64_t n_global, const int64_t* row_offsets,
                              int64_t nc_global, const int64_t* coarse_row_offsets,
                              const int64_t* a_colptr, const int64_t* a_rowval, const void* a_nzval,
-                             const int64_t* p_colptr, const int64_t* p_rowval, const double* p_nzval,
-                             const int64_t* r_colptr, const int64_t* r_rowval, const double* r_nzval,
+                             const int64_t* p_colptr, const int64_t* p_rowval, const void* p_nzval,
+                             const int64_t* r_colptr, const int64_t* r_rowval, const void* r_nzval,
                              const void* d, int index_base);
 
 /* out[0] = world, out[1] = rank, out[2] = 1 if halo exchange and coarse gather run over NVLink peer memory

@@ -64,6 +64,37 @@ __host__ __device__ __forceinline__ cplx operator/(cplx a, cplx b) {
     return make_cplx((a.x * b.x + a.y * b.y) / den, (a.y * b.x - a.x * b.y) / den);
 }
 
+
+// Single-precision twins (Float32 / ComplexF32 hierarchies of the reference, `singlePrecision` in MGdef.jl:119,151:
+// the cycle then runs in single precision under a double-precision Krylov method, SolveFuncs.jl:52-60).
+struct __align__(8) cplxf {
+    float x, y;
+};
+__host__ __device__ __forceinline__ cplxf make_cplxf(float a, float b) {
+    cplxf c;
+    c.x = a;
+    c.y = b;
+    return c;
+}
+__host__ __device__ __forceinline__ cplxf operator+(cplxf a, cplxf b) { return make_cplxf(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ cplxf operator-(cplxf a, cplxf b) { return make_cplxf(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ cplxf operator-(cplxf a) { return make_cplxf(-a.x, -a.y); }
+__host__ __device__ __forceinline__ cplxf operator*(cplxf a, cplxf b) {
+    return make_cplxf(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__host__ __device__ __forceinline__ cplxf operator*(float a, cplxf b) { return make_cplxf(a * b.x, a * b.y); }
+__host__ __device__ __forceinline__ cplxf operator*(cplxf b, float a) { return make_cplxf(a * b.x, a * b.y); }
+__host__ __device__ __forceinline__ cplxf operator*(double a, cplxf b) { return make_cplxf((float)a * b.x, (float)a * b.y); }
+__host__ __device__ __forceinline__ cplxf operator*(cplxf b, double a) { return make_cplxf((float)a * b.x, (float)a * b.y); }
+__host__ __device__ __forceinline__ cplxf conj_(cplxf a) { return make_cplxf(a.x, -a.y); }
+__host__ __device__ __forceinline__ float conj_(float a) { return a; }
+__host__ __device__ __forceinline__ double abs2(cplxf a) { return (double)a.x * a.x + (double)a.y * a.y; }
+__host__ __device__ __forceinline__ double abs2(float a) { return (double)a * a; }
+__host__ __device__ __forceinline__ cplxf operator/(cplxf a, cplxf b) {
+    float den = b.x * b.x + b.y * b.y;
+    return make_cplxf((a.x * b.x + a.y * b.y) / den, (a.y * b.x - a.x * b.y) / den);
+}
+
 template <typename T>
 struct VT;
 template <>
@@ -89,6 +120,44 @@ struct VT<cplx> {
     __host__ __device__ static __forceinline__ cplx make(double a, double b) { return make_cplx(a, b); }
 };
 
+template <>
+struct VT<float> {
+    typedef float real_t;
+    static constexpr bool is_complex = false;
+    __host__ __device__ static __forceinline__ float zero() { return 0.0f; }
+    __host__ __device__ static __forceinline__ float one() { return 1.0f; }
+    __host__ __device__ static __forceinline__ float from_real(double a) { return (float)a; }
+    __host__ __device__ static __forceinline__ double re(float a) { return a; }
+    __host__ __device__ static __forceinline__ double im(float) { return 0.0; }
+    __host__ __device__ static __forceinline__ float make(double a, double) { return (float)a; }
+};
+template <>
+struct VT<cplxf> {
+    typedef float real_t;
+    static constexpr bool is_complex = true;
+    __host__ __device__ static __forceinline__ cplxf zero() { return make_cplxf(0.0f, 0.0f); }
+    __host__ __device__ static __forceinline__ cplxf one() { return make_cplxf(1.0f, 0.0f); }
+    __host__ __device__ static __forceinline__ cplxf from_real(double a) { return make_cplxf((float)a, 0.0f); }
+    __host__ __device__ static __forceinline__ double re(cplxf a) { return a.x; }
+    __host__ __device__ static __forceinline__ double im(cplxf a) { return a.y; }
+    __host__ __device__ static __forceinline__ cplxf make(double a, double b) { return make_cplxf((float)a, (float)b); }
+};
+
+// Wide<T>: the double-precision twin of a value type.  The coarsest-grid factorisation of a single-precision hierarchy
+// is held in double precision, as Julia's lu() does for Float32 / ComplexF32 sparse matrices (UMFPACK has no single
+// precision: the matrix is promoted, `LU \ b` returns double precision and `x[:] = z` rounds, MGcycle.jl:176-179).
+template <typename T> struct Wide { typedef T type; };
+template <> struct Wide<float> { typedef double type; };
+template <> struct Wide<cplxf> { typedef cplx type; };
+__host__ __device__ __forceinline__ double widen(double a) { return a; }
+__host__ __device__ __forceinline__ cplx widen(cplx a) { return a; }
+__host__ __device__ __forceinline__ double widen(float a) { return (double)a; }
+__host__ __device__ __forceinline__ cplx widen(cplxf a) { return make_cplx((double)a.x, (double)a.y); }
+__host__ __device__ __forceinline__ void narrow(double a, double& o) { o = a; }
+__host__ __device__ __forceinline__ void narrow(cplx a, cplx& o) { o = a; }
+__host__ __device__ __forceinline__ void narrow(double a, float& o) { o = (float)a; }
+__host__ __device__ __forceinline__ void narrow(cplx a, cplxf& o) { o = make_cplxf((float)a.x, (float)a.y); }
+
 // read-only (non-coherent) loads
 __device__ __forceinline__ double ldg_(const double* p) { return __ldg(p); }
 __device__ __forceinline__ cplx ldg_(const cplx* p) {
@@ -96,6 +165,11 @@ __device__ __forceinline__ cplx ldg_(const cplx* p) {
     return make_cplx(v.x, v.y);
 }
 __device__ __forceinline__ int ldg_(const int* p) { return __ldg(p); }
+__device__ __forceinline__ float ldg_(const float* p) { return __ldg(p); }
+__device__ __forceinline__ cplxf ldg_(const cplxf* p) {
+    float2 v = __ldg(reinterpret_cast<const float2*>(p));
+    return make_cplxf(v.x, v.y);
+}
 
 __device__ __forceinline__ double shfl_xor_(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 __device__ __forceinline__ cplx shfl_xor_(cplx v, int m) {
@@ -104,6 +178,15 @@ __device__ __forceinline__ cplx shfl_xor_(cplx v, int m) {
 __device__ __forceinline__ double shfl_down_(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
 __device__ __forceinline__ cplx shfl_down_(cplx v, int d) {
     return make_cplx(__shfl_down_sync(0xffffffffu, v.x, d), __shfl_down_sync(0xffffffffu, v.y, d));
+}
+
+__device__ __forceinline__ float shfl_xor_(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ cplxf shfl_xor_(cplxf v, int m) {
+    return make_cplxf(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
+}
+__device__ __forceinline__ float shfl_down_(float v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ cplxf shfl_down_(cplxf v, int d) {
+    return make_cplxf(__shfl_down_sync(0xffffffffu, v.x, d), __shfl_down_sync(0xffffffffu, v.y, d));
 }
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

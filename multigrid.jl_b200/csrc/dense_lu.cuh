@@ -12,14 +12,14 @@
 
 namespace mgb200 {
 
-template <typename TV>
+template <typename TV, typename TW>
 __global__ void densify_kernel(int n, const int* __restrict__ rowptr, const int* __restrict__ colind,
-                               const TV* __restrict__ val, TV* __restrict__ a) {
+                               const TV* __restrict__ val, TW* __restrict__ a) {
     int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= n) return;
     for (int k = rowptr[row]; k < rowptr[row + 1]; ++k) {
         // duplicate entries cannot occur in a CSC matrix coming from the reference; plain store
-        a[(size_t)row * n + colind[k]] = val[k];
+        a[(size_t)row * n + colind[k]] = widen(val[k]);
     }
 }
 
@@ -125,33 +125,33 @@ __global__ void upper_inverse_kernel(const TV* __restrict__ lu, int n, TV* __res
 }
 
 // y[i*m+c] = sum_{j<=i} Linv[i][j] * b[perm[j]*m+c]      (one warp per (row, rhs))
-template <typename TV>
-__global__ void lower_apply_kernel(int n, int m, const TV* __restrict__ linv, const int* __restrict__ perm,
-                                   const TV* __restrict__ b, TV* __restrict__ y) {
+template <typename TW, typename TV>
+__global__ void lower_apply_kernel(int n, int m, const TW* __restrict__ linv, const int* __restrict__ perm,
+                                   const TV* __restrict__ b, TW* __restrict__ y) {
     const int lane = threadIdx.x & 31;
     const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     if (w >= (long long)n * m) return;
     const int i = (int)(w / m), c = (int)(w % m);
-    TV acc = VT<TV>::zero();
-    for (int j = lane; j <= i; j += 32) acc = acc + linv[(size_t)i * n + j] * b[(size_t)perm[j] * m + c];
+    TW acc = VT<TW>::zero();
+    for (int j = lane; j <= i; j += 32) acc = acc + linv[(size_t)i * n + j] * widen(b[(size_t)perm[j] * m + c]);
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) acc = acc + shfl_xor_(acc, s);
     if (lane == 0) y[(size_t)i * m + c] = acc;
 }
 
 // x[i*m+c] = sum_{j>=i} Uinv[i][j] * y[j*m+c]
-template <typename TV>
-__global__ void upper_apply_kernel(int n, int m, const TV* __restrict__ uinv, const TV* __restrict__ y,
+template <typename TW, typename TV>
+__global__ void upper_apply_kernel(int n, int m, const TW* __restrict__ uinv, const TW* __restrict__ y,
                                    TV* __restrict__ x) {
     const int lane = threadIdx.x & 31;
     const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     if (w >= (long long)n * m) return;
     const int i = (int)(w / m), c = (int)(w % m);
-    TV acc = VT<TV>::zero();
+    TW acc = VT<TW>::zero();
     for (int j = i + lane; j < n; j += 32) acc = acc + uinv[(size_t)i * n + j] * y[(size_t)j * m + c];
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) acc = acc + shfl_xor_(acc, s);
-    if (lane == 0) x[(size_t)i * m + c] = acc;
+    if (lane == 0) narrow(acc, x[(size_t)i * m + c]);
 }
 
 }  // namespace mgb200

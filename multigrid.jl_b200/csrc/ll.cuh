@@ -47,6 +47,29 @@ struct LL<cplx> {
     }
 };
 
+template <>
+struct LL<float> {
+    static constexpr int W = 1;
+    __device__ static __forceinline__ void put(unsigned long long* dst, float v, unsigned flag) {
+        st_ll(dst, __float_as_uint(v), flag);
+    }
+    __device__ static __forceinline__ float get(const unsigned long long* src, unsigned flag) {
+        return __uint_as_float(ld_ll(src, flag));
+    }
+};
+template <>
+struct LL<cplxf> {
+    static constexpr int W = 2;
+    __device__ static __forceinline__ void put(unsigned long long* dst, cplxf v, unsigned flag) {
+        st_ll(dst, __float_as_uint(v.x), flag);
+        st_ll(dst + 1, __float_as_uint(v.y), flag);
+    }
+    __device__ static __forceinline__ cplxf get(const unsigned long long* src, unsigned flag) {
+        const unsigned a = ld_ll(src, flag), b = ld_ll(src + 1, flag);
+        return make_cplxf(__uint_as_float(a), __uint_as_float(b));
+    }
+};
+
 // Fused put: the rows of a level vector that the slab neighbours need (for a z-slab: the first plane goes to the lower
 // neighbour, the last plane to the upper one) are stored as LL words by the kernel that COMPUTES them, so the
 // transfer rides under the rest of that kernel and the exchange kernel that follows only has to poll and unpack.

@@ -41,13 +41,21 @@ static void dispatch(mgb200_handle h, F&& f) {
         auto* H = static_cast<Hierarchy<double>*>(h->impl);
         MGB_CUDA(cudaSetDevice(H->ctx.device));
         f(H);
-    } else {
+    } else if (h->val_type == MGB200_CFP64) {
         auto* H = static_cast<Hierarchy<cplx>*>(h->impl);
+        MGB_CUDA(cudaSetDevice(H->ctx.device));
+        f(H);
+    } else if (h->val_type == MGB200_FP32) {
+        auto* H = static_cast<Hierarchy<float>*>(h->impl);
+        MGB_CUDA(cudaSetDevice(H->ctx.device));
+        f(H);
+    } else {
+        auto* H = static_cast<Hierarchy<cplxf>*>(h->impl);
         MGB_CUDA(cudaSetDevice(H->ctx.device));
         f(H);
     }
 }
-// generic body for both value types; `H` is the typed hierarchy pointer
+// generic body for all value types; `H` is the typed hierarchy pointer
 #define MGB_BOTH(h, ...) dispatch(h, [&](auto* H) { __VA_ARGS__; })
 
 template <typename TV>
@@ -96,6 +104,39 @@ static void spmatmul_impl(Hierarchy<TV>* H, int level, int which, double alpha, 
     }
 }
 
+// outer (double-precision, Krylov only) handle over a single-precision hierarchy
+template <typename TD, typename TS>
+static HierarchyBase* make_mixed(Hierarchy<TS>* in) {
+    MGB_CUDA(cudaSetDevice(in->ctx.device));
+    MGB_CHECK(!in->comm.active(), "mixed precision over a row-partitioned hierarchy is not supported");
+    MGB_CHECK(in->L[0].n > 0, "upload the single-precision hierarchy first");
+    const int64_t one[1] = {1};
+    auto* out = new Hierarchy<TD>(1, in->m, in->cycle_type, 0, one, one, in->ctx.device);
+    out->krylov_only = true;
+    out->L[0].n = in->L[0].n;
+    out->L[0].nalloc = in->L[0].n;
+    for (auto& e : out->mix_ev) MGB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    out->ext_prec = [out, in](const TD* r) -> TD* {
+        MGB_CHECK(in->m == out->m, "nrhs of the two mixed-precision handles differ (mgb200_adjust_nrhs on both)");
+        in->ensure_work();
+        const long long nm = in->L[0].n * in->m;
+        cudaStream_t si = in->ctx.stream, so = out->ctx.stream;
+        MGB_CUDA(cudaEventRecord(out->mix_ev[0], so));
+        MGB_CUDA(cudaStreamWaitEvent(si, out->mix_ev[0], 0));
+        const long long l0 = in->ctx.launches;
+        convert_kernel<TD, TS><<<in->ctx.ew_blocks(nm), 256, 0, si>>>(nm, r, in->L[0].b);      // bl[:] .= b
+        MGB_LAUNCH_CHECK();
+        TS* z = in->precondition(in->L[0].b);                                                   // z .= 0; cycle
+        convert_kernel<TS, TD><<<in->ctx.ew_blocks(nm), 256, 0, si>>>(nm, z, out->L[0].x0);    // z2[:] .= z
+        MGB_LAUNCH_CHECK();
+        MGB_CUDA(cudaEventRecord(out->mix_ev[1], si));
+        MGB_CUDA(cudaStreamWaitEvent(so, out->mix_ev[1], 0));
+        out->ctx.launches += 2 + (in->ctx.launches - l0);
+        return out->L[0].x0;
+    };
+    return out;
+}
+
 extern "C" {
 
 const char* mgb200_last_error(void) { return g_last_error.c_str(); }
@@ -105,7 +146,7 @@ int mgb200_create(mgb200_handle* h, int val_type, int levels, int nrhs, char cyc
                   const int64_t* relax_pre, const int64_t* relax_post, int device) {
     MGB_TRY
     MGB_CHECK(h != nullptr, "null handle pointer");
-    MGB_CHECK(val_type == MGB200_FP64 || val_type == MGB200_CFP64, "val_type must be MGB200_FP64 or MGB200_CFP64");
+    MGB_CHECK(val_type >= MGB200_FP64 && val_type <= MGB200_CFP32, "val_type must be MGB200_FP64, _CFP64, _FP32 or _CFP32");
     MGB_CHECK(relax_kind == 0 || relax_kind == 1, "relax_kind must be 0 (diagonal) or 1 (Jac-GMRES)");
     MGB_CHECK(relax_pre && relax_post, "relax_pre / relax_post required");
     int ndev = 0;
@@ -120,14 +161,42 @@ int mgb200_create(mgb200_handle* h, int val_type, int levels, int nrhs, char cyc
     try {
         if (val_type == MGB200_FP64)
             hh->impl = new Hierarchy<double>(levels, nrhs, cycle_type, relax_kind, relax_pre, relax_post, device);
-        else
+        else if (val_type == MGB200_CFP64)
             hh->impl = new Hierarchy<cplx>(levels, nrhs, cycle_type, relax_kind, relax_pre, relax_post, device);
+        else if (val_type == MGB200_FP32)
+            hh->impl = new Hierarchy<float>(levels, nrhs, cycle_type, relax_kind, relax_pre, relax_post, device);
+        else
+            hh->impl = new Hierarchy<cplxf>(levels, nrhs, cycle_type, relax_kind, relax_pre, relax_post, device);
     } catch (...) {
         delete hh;
         throw;
     }
     hh->impl->val_type = val_type;
     *h = hh;
+    MGB_CATCH
+}
+
+int mgb200_create_mixed(mgb200_handle* outer, mgb200_handle inner) {
+    MGB_TRY
+    MGB_CHECK(outer && inner && inner->impl, "null handle");
+    MGB_CHECK(inner->val_type == MGB200_FP32 || inner->val_type == MGB200_CFP32,
+              "mgb200_create_mixed: the inner hierarchy must be MGB200_FP32 or MGB200_CFP32");
+    mgb200_hierarchy* hh = new mgb200_hierarchy;
+    hh->impl = nullptr;
+    try {
+        if (inner->val_type == MGB200_FP32) {
+            hh->val_type = MGB200_FP64;
+            hh->impl = make_mixed<double, float>(static_cast<Hierarchy<float>*>(inner->impl));
+        } else {
+            hh->val_type = MGB200_CFP64;
+            hh->impl = make_mixed<cplx, cplxf>(static_cast<Hierarchy<cplxf>*>(inner->impl));
+        }
+    } catch (...) {
+        delete hh;
+        throw;
+    }
+    hh->impl->val_type = hh->val_type;
+    *outer = hh;
     MGB_CATCH
 }
 
@@ -142,8 +211,8 @@ int mgb200_destroy(mgb200_handle h) {
 
 int mgb200_upload_level(mgb200_handle h, int level, int64_t n, int64_t nc, const int64_t* a_colptr,
                         const int64_t* a_rowval, const void* a_nzval, const int64_t* p_colptr,
-                        const int64_t* p_rowval, const double* p_nzval, const int64_t* r_colptr,
-                        const int64_t* r_rowval, const double* r_nzval, const void* d, int index_base) {
+                        const int64_t* p_rowval, const void* p_nzval, const int64_t* r_colptr,
+                        const int64_t* r_rowval, const void* r_nzval, const void* d, int index_base) {
     MGB_TRY
     MGB_BOTH(h, H->upload_level(level, n, nc, a_colptr, a_rowval, a_nzval, p_colptr, p_rowval, p_nzval,
                                 r_colptr, r_rowval, r_nzval, d, index_base));
@@ -193,8 +262,8 @@ int mgb200_dist_init(mgb200_handle h, int rank, int world, const char* unique_id
 int mgb200_dist_upload_level(mgb200_handle h, int level, int64_t n_global, const int64_t* row_offsets,
                              int64_t nc_global, const int64_t* coarse_row_offsets, const int64_t* a_colptr,
                              const int64_t* a_rowval, const void* a_nzval, const int64_t* p_colptr,
-                             const int64_t* p_rowval, const double* p_nzval, const int64_t* r_colptr,
-                             const int64_t* r_rowval, const double* r_nzval, const void* d, int index_base) {
+                             const int64_t* p_rowval, const void* p_nzval, const int64_t* r_colptr,
+                             const int64_t* r_rowval, const void* r_nzval, const void* d, int index_base) {
     MGB_TRY
     MGB_CHECK(row_offsets && coarse_row_offsets && a_colptr && a_rowval && a_nzval && p_colptr && p_rowval &&
                   p_nzval && r_colptr && r_rowval && r_nzval && d, "null argument");

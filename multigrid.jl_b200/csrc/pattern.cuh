@@ -67,8 +67,8 @@ static inline uint64_t pat_mix(uint64_t h, uint64_t v) {
 template <typename TA>
 static bool build_patterns_mode(long long n_rows, const int64_t* cp, const int64_t* rv, const TA* nz, int base,
                                 bool conjugate, bool rowrel, int max_pat, int max_ent, HostPatterns<TA>& out) {
-    static_assert(sizeof(TA) % 8 == 0, "value type is made of doubles");
-    constexpr int W = sizeof(TA) / 8;
+    static_assert(sizeof(TA) % 4 == 0, "value type is made of 4-byte words");
+    constexpr int W = sizeof(TA) / 4;
     int T = (int)std::thread::hardware_concurrency();
     T = std::max(1, std::min(T, 16));
     if (n_rows < 4096) T = 1;
@@ -100,7 +100,7 @@ static bool build_patterns_mode(long long n_rows, const int64_t* cp, const int64
             const long long k0 = cp[row] - base, k1 = cp[row + 1] - base;
             const long long ref = ref_of(row, k0, k1 - k0);
             uint64_t h = pat_mix(0x1234567ull, (uint64_t)(k1 - k0));
-            const uint64_t* vb = reinterpret_cast<const uint64_t*>(nz + k0);
+            const uint32_t* vb = reinterpret_cast<const uint32_t*>(nz + k0);
             for (long long k = k0; k < k1; ++k) {
                 h = pat_mix(h, (uint64_t)(rv[k] - base - ref));
                 for (int w = 0; w < W; ++w) h = pat_mix(h, vb[(k - k0) * W + w]);
@@ -352,7 +352,8 @@ static void upload_patterns(PatDict<TA>& D, const HostPatterns<TA>& H, long long
     std::vector<int> soff;
     int max_len = 0;
     for (int p = 0; p < D.npat; ++p) max_len = std::max(max_len, H.pat_off[p + 1] - H.pat_off[p]);
-    if (max_len < (1 << 11) && build_tma_plan<TA>(H, TmaTile<TA>::NT, D.plan, soff)) {
+    // (4-byte values would need the copies rounded to 4 elements: Float32 matrices keep the one-pass kernel)
+    if (sizeof(TA) >= 8 && max_len < (1 << 11) && build_tma_plan<TA>(H, TmaTile<TA>::NT, D.plan, soff)) {
         std::vector<int> hdr(D.npat);
         for (int p = 0; p < D.npat; ++p) hdr[p] = H.pat_off[p] | ((H.pat_off[p + 1] - H.pat_off[p]) << 20);
         MGB_CUDA(cudaMalloc(&D.hdr, D.npat * sizeof(int)));
@@ -377,6 +378,21 @@ __device__ __forceinline__ PatEntry<cplx> ldg_ent(const PatEntry<cplx>* p) {
     PatEntry<cplx> e;
     e.v = make_cplx(a.x, a.y);
     e.delta = q.x;
+    return e;
+}
+
+__device__ __forceinline__ PatEntry<float> ldg_ent(const PatEntry<float>* p) {
+    const int2 q = __ldg(reinterpret_cast<const int2*>(p));
+    PatEntry<float> e;
+    e.v = __int_as_float(q.x);
+    e.delta = q.y;
+    return e;
+}
+__device__ __forceinline__ PatEntry<cplxf> ldg_ent(const PatEntry<cplxf>* p) {
+    const int4 q = __ldg(reinterpret_cast<const int4*>(p));
+    PatEntry<cplxf> e;
+    e.v = make_cplxf(__int_as_float(q.x), __int_as_float(q.y));
+    e.delta = q.z;
     return e;
 }
 

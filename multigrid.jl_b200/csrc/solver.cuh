@@ -41,7 +41,8 @@ template <typename TV>
 struct Level {
     long long n = 0;
     Csr<TV> A;
-    Csr<double> P, R;
+    typedef typename VT<TV>::real_t RT;   // P and R are real (SA-AMG.jl:9-10, MGsetup.jl:80-81)
+    Csr<RT> P, R;
     TV* d = nullptr;
     TV* dpat = nullptr;            // d as a function of A's pattern id, when it is one (pattern.cuh)
     TV *b = nullptr, *r = nullptr, *x0 = nullptr, *x1 = nullptr;  // CYCLEmem + ping-pong partner of x
@@ -50,7 +51,7 @@ struct Level {
     long long nalloc = 0;          // rows allocated per vector: owned + ghost (== n when not distributed)
     DistSpace sp;                  // vector space of this level
     HostRows<TV> hA;               // staged owned rows with global columns (until finalisation)
-    HostRows<double> hP, hR;
+    HostRows<RT> hP, hR;
     std::vector<TV> hd;
     std::vector<long long> coarse_row_offsets;  // row partition of level l+1 (R output / P input)
     long long nc_global = 0;
@@ -73,10 +74,11 @@ template <typename TV>
 struct Coarsest {
     int n = 0;
     int kind = 0;     // 0: dense LU (default branch of defineCoarsestAinv), 1: "GMRES" (MGsetup.jl:333-334)
-    TV* linv = nullptr;
-    TV* uinv = nullptr;
+    typedef typename Wide<TV>::type TW;   // the factors of a single-precision hierarchy are double precision (common.cuh)
+    TW* linv = nullptr;
+    TW* uinv = nullptr;
     int* perm = nullptr;
-    TV* y = nullptr;  // n*m scratch
+    TW* y = nullptr;  // n*m scratch
     // coarseSolveType "GMRES": param.LU = conj(relaxParam ./ diag(AT)) and the FGMRES(10) workspace
     TV *d = nullptr, *r = nullptr, *w = nullptr, *t = nullptr, *V = nullptr, *dv = nullptr;
     void release() {
@@ -95,6 +97,7 @@ struct HierarchyBase {
 
 template <typename TV>
 struct Hierarchy : HierarchyBase {
+    typedef typename VT<TV>::real_t RT;
     int levels = 0;
     int m = 1;  // nrhs
     char cycle_type = 'V';
@@ -119,6 +122,11 @@ struct Hierarchy : HierarchyBase {
     std::vector<const TV*> put_done;
     int use_fused_put = 1;
     bool dist_finalized = true;
+    // mixed precision (mgb200_create_mixed): a handle without levels of its own whose preconditioner is one cycle of
+    // a single-precision hierarchy (getMultigridPreconditioner with VAL != eltype(B), SolveFuncs.jl:52-60)
+    bool krylov_only = false;
+    std::function<TV*(const TV*)> ext_prec;
+    cudaEvent_t mix_ev[2] = {nullptr, nullptr};
     // V/F/W cycles have no host synchronisation: each (buffers, x-is-zero, type) variant is captured
     // once into a CUDA graph and replayed, which removes the launch gaps of the coarse levels
     struct GraphEntry {
@@ -162,6 +170,8 @@ struct Hierarchy : HierarchyBase {
         dev_free(kq);
         if (comm.comm) nccl().CommDestroy(comm.comm);
         comm.comm = nullptr;
+        for (auto& e : mix_ev)
+            if (e) cudaEventDestroy(e);
         ctx.destroy();
     }
     void set_cycle(char ct, const int64_t* rpre, const int64_t* rpost) {
@@ -185,16 +195,16 @@ struct Hierarchy : HierarchyBase {
 
     // ---- upload ---------------------------------------------------------------------------
     void upload_level(int level, long long n, long long nc, const int64_t* acp, const int64_t* arv,
-                      const void* anz, const int64_t* pcp, const int64_t* prv, const double* pnz,
-                      const int64_t* rcp, const int64_t* rrv, const double* rnz, const void* d, int base) {
+                      const void* anz, const int64_t* pcp, const int64_t* prv, const void* pnz,
+                      const int64_t* rcp, const int64_t* rrv, const void* rnz, const void* d, int base) {
         MGB_CHECK(level >= 1 && level < levels, "upload_level: level must be in 1..levels-1");
         MGB_CHECK(base == 0 || base == 1, "index_base must be 0 or 1");
         MGB_CUDA(cudaSetDevice(ctx.device));
         Level<TV>& lv = L[level - 1];
         lv.n = n;
         upload_csr<TV>(ctx, lv.A, n, n, acp, arv, static_cast<const TV*>(anz), base, true);
-        upload_csr<double>(ctx, lv.P, n, nc, pcp, prv, pnz, base, false);
-        upload_csr<double>(ctx, lv.R, nc, n, rcp, rrv, rnz, base, false);
+        upload_csr<RT>(ctx, lv.P, n, nc, pcp, prv, static_cast<const RT*>(pnz), base, false);
+        upload_csr<RT>(ctx, lv.R, nc, n, rcp, rrv, static_cast<const RT*>(rnz), base, false);
         dev_free(lv.d);
         lv.d = dev_alloc<TV>(n + 4);   // slack for the even-rounded tile copies of the TMA kernel
         MGB_CUDA(cudaMemcpy(lv.d, d, n * sizeof(TV), cudaMemcpyHostToDevice));
@@ -246,19 +256,20 @@ struct Hierarchy : HierarchyBase {
         coarse.release();
         coarse.n = (int)n;
         const int N = (int)n;
-        TV* a = dev_alloc<TV>((size_t)N * N);
-        MGB_CUDA(cudaMemsetAsync(a, 0, (size_t)N * N * sizeof(TV), ctx.stream));
-        densify_kernel<TV><<<cdiv(N, 128), 128, 0, ctx.stream>>>(N, lv.A.rowptr, lv.A.colind, lv.A.val, a);
+        typedef typename Wide<TV>::type TW;
+        TW* a = dev_alloc<TW>((size_t)N * N);
+        MGB_CUDA(cudaMemsetAsync(a, 0, (size_t)N * N * sizeof(TW), ctx.stream));
+        densify_kernel<TV, TW><<<cdiv(N, 128), 128, 0, ctx.stream>>>(N, lv.A.rowptr, lv.A.colind, lv.A.val, a);
         MGB_LAUNCH_CHECK();
         int* piv = dev_alloc<int>(N + 1);
         int* info = piv + N;
         MGB_CUDA(cudaMemsetAsync(info, 0, sizeof(int), ctx.stream));
         for (int k = 0; k < N; ++k) {
-            lu_pivot_kernel<TV><<<1, 256, 0, ctx.stream>>>(a, N, k, piv, info);
+            lu_pivot_kernel<TW><<<1, 256, 0, ctx.stream>>>(a, N, k, piv, info);
             const int rem = N - k - 1;
             if (rem > 0) {
                 dim3 blk(32, 8), grd(cdiv(rem, 32), cdiv(rem, 8));
-                lu_update_kernel<TV><<<grd, blk, 0, ctx.stream>>>(a, N, k);
+                lu_update_kernel<TW><<<grd, blk, 0, ctx.stream>>>(a, N, k);
             }
         }
         MGB_LAUNCH_CHECK();
@@ -271,10 +282,10 @@ struct Hierarchy : HierarchyBase {
         for (int k = 0; k < N; ++k) std::swap(perm[k], perm[hpiv[k]]);
         coarse.perm = dev_alloc<int>(N);
         MGB_CUDA(cudaMemcpy(coarse.perm, perm.data(), N * sizeof(int), cudaMemcpyHostToDevice));
-        coarse.linv = dev_alloc<TV>((size_t)N * N);
-        coarse.uinv = dev_alloc<TV>((size_t)N * N);
-        lower_inverse_kernel<TV><<<cdiv(N, 64), 64, 0, ctx.stream>>>(a, N, coarse.linv);
-        upper_inverse_kernel<TV><<<cdiv(N, 64), 64, 0, ctx.stream>>>(a, N, coarse.uinv);
+        coarse.linv = dev_alloc<TW>((size_t)N * N);
+        coarse.uinv = dev_alloc<TW>((size_t)N * N);
+        lower_inverse_kernel<TW><<<cdiv(N, 64), 64, 0, ctx.stream>>>(a, N, coarse.linv);
+        upper_inverse_kernel<TW><<<cdiv(N, 64), 64, 0, ctx.stream>>>(a, N, coarse.uinv);
         MGB_LAUNCH_CHECK();
         ctx.sync();
         dev_free(a);
@@ -344,8 +355,8 @@ struct Hierarchy : HierarchyBase {
     }
     void dist_upload_level(int level, long long n_global, const int64_t* row_offsets, long long nc_global,
                            const int64_t* coarse_row_offsets, const int64_t* acp, const int64_t* arv,
-                           const void* anz, const int64_t* pcp, const int64_t* prv, const double* pnz,
-                           const int64_t* rcp, const int64_t* rrv, const double* rnz, const void* d, int base) {
+                           const void* anz, const int64_t* pcp, const int64_t* prv, const void* pnz,
+                           const int64_t* rcp, const int64_t* rrv, const void* rnz, const void* d, int base) {
         MGB_CHECK(level >= 1 && level < levels, "dist_upload_level: level must be in 1..levels-1");
         MGB_CHECK(base == 0 || base == 1, "index_base must be 0 or 1");
         Level<TV>& lv = L[level - 1];
@@ -361,8 +372,8 @@ struct Hierarchy : HierarchyBase {
         lv.coarse_row_offsets.assign(coarse_row_offsets, coarse_row_offsets + w + 1);
         const long long nc_owned = coarse_row_offsets[r + 1] - coarse_row_offsets[r];
         stage_rows<TV>(lv.hA, lv.n, acp, arv, static_cast<const TV*>(anz), base, true);
-        stage_rows<double>(lv.hP, lv.n, pcp, prv, pnz, base, false);
-        stage_rows<double>(lv.hR, nc_owned, rcp, rrv, rnz, base, false);
+        stage_rows<RT>(lv.hP, lv.n, pcp, prv, static_cast<const RT*>(pnz), base, false);
+        stage_rows<RT>(lv.hR, nc_owned, rcp, rrv, static_cast<const RT*>(rnz), base, false);
         lv.hd.assign(static_cast<const TV*>(d), static_cast<const TV*>(d) + lv.n);
         dist_finalized = false;
         work_ready = false;
@@ -459,8 +470,8 @@ struct Hierarchy : HierarchyBase {
                 if (lc.nalloc < lc.n) lc.nalloc = lc.n;
             }
             upload_csr<TV>(ctx, lv.A, lv.hA.n_rows, lv.nalloc, lv.hA.rowptr.data(), lv.hA.col.data(), lv.hA.val.data(), 0, false);
-            upload_csr<double>(ctx, lv.P, lv.hP.n_rows, pcols, lv.hP.rowptr.data(), lv.hP.col.data(), lv.hP.val.data(), 0, false);
-            upload_csr<double>(ctx, lv.R, lv.hR.n_rows, lv.nalloc, lv.hR.rowptr.data(), lv.hR.col.data(), lv.hR.val.data(), 0, false);
+            upload_csr<RT>(ctx, lv.P, lv.hP.n_rows, pcols, lv.hP.rowptr.data(), lv.hP.col.data(), lv.hP.val.data(), 0, false);
+            upload_csr<RT>(ctx, lv.R, lv.hR.n_rows, lv.nalloc, lv.hR.rowptr.data(), lv.hR.col.data(), lv.hR.val.data(), 0, false);
             // rows that read no ghost row of their input vector (they may run beside the halo exchange, apply_x)
             interior_rows(lv.hA, sp.n_owned, lv.A.int_lo, lv.A.int_hi);
             interior_rows(lv.hR, sp.n_owned, lv.R.int_lo, lv.R.int_hi);
@@ -520,9 +531,10 @@ struct Hierarchy : HierarchyBase {
             // for level l (1-based l+1 >= 2) and used when the parent recurses into it.
             if (cycle_type == 'K' && l >= 1 && l < levels - 1) alloc_fgmres(lv.memK, nm, 2, pad);
         }
-        MGB_CHECK(coarse.n == (int)L[levels - 1].n, "coarsest factorisation missing (mgb200_upload_coarsest)");
+        MGB_CHECK(krylov_only || coarse.n == (int)L[levels - 1].n, "coarsest factorisation missing (mgb200_upload_coarsest)");
+        MGB_CHECK(!krylov_only || Akry.present(), "mixed-precision handle without its Krylov matrix (mgb200_set_krylov_matrix)");
         dev_free(coarse.y);
-        coarse.y = dev_alloc<TV>((size_t)coarse.n * m);
+        coarse.y = dev_alloc<typename Wide<TV>::type>((size_t)coarse.n * m);
         free_krylov();
         dev_free(hstage);
         hstage_n = 0;
@@ -963,10 +975,11 @@ struct Hierarchy : HierarchyBase {
             fgmres_core(L[levels - 1].A, levels, n, b, x, 10, false, 0.01, 1, m2, ws, &flag, nullptr, &nres);
             return;
         }
-        Launch La(ctx, K_COARSE, levels, (double)n * n * sizeof(TV));
+        typedef typename Wide<TV>::type TW;
+        Launch La(ctx, K_COARSE, levels, (double)n * n * sizeof(TW));
         const int grid = cdiv((long long)n * m * 32, 256);
-        lower_apply_kernel<TV><<<grid, 256, 0, ctx.stream>>>(n, m, coarse.linv, coarse.perm, b, coarse.y);
-        upper_apply_kernel<TV><<<grid, 256, 0, ctx.stream>>>(n, m, coarse.uinv, coarse.y, x);
+        lower_apply_kernel<TW, TV><<<grid, 256, 0, ctx.stream>>>(n, m, coarse.linv, coarse.perm, b, coarse.y);
+        upper_apply_kernel<TW, TV><<<grid, 256, 0, ctx.stream>>>(n, m, coarse.uinv, coarse.y, x);
         MGB_LAUNCH_CHECK();
     }
 
@@ -1047,11 +1060,11 @@ struct Hierarchy : HierarchyBase {
         residual(lv.A, b, x, lv.r, l + 1, relax_kind == 0 ? l : -1);                // :58-60; r is exchanged for R
         if (lv.sp.dist && !lc.sp.dist) {
             // last distributed level: each rank restricts its own coarse rows, then the pieces are gathered
-            apply_x<double>(l, lv.R, MODE_SPMV, lv.r, nullptr, nullptr,
+            apply_x<RT>(l, lv.R, MODE_SPMV, lv.r, nullptr, nullptr,
                             lc.b + (size_t)lv.coarse_row_offsets[comm.rank] * m, K_RESTRICT, l + 1);
             allgather_rows(l + 1, lc.b, lv.coarse_row_offsets);
         } else {
-            apply_x<double>(l, lv.R, MODE_SPMV, lv.r, nullptr, nullptr, lc.b, K_RESTRICT, l + 1);  // :66
+            apply_x<RT>(l, lv.R, MODE_SPMV, lv.r, nullptr, nullptr, lc.b, K_RESTRICT, l + 1);  // :66
         }
         if (l + 1 == levels - 1) {
             solve_coarsest(lc.b, lc.x0);                                           // :67-69
@@ -1073,7 +1086,7 @@ struct Hierarchy : HierarchyBase {
             }
         }
         // the corrected x is exchanged by the first post-sweep
-        apply_x<double>(l + 1, lv.P, MODE_ADD, xc_cur, nullptr, nullptr, x, K_PROLONG, l + 1, nullptr,
+        apply_x<RT>(l + 1, lv.P, MODE_ADD, xc_cur, nullptr, nullptr, x, K_PROLONG, l + 1, nullptr,
                         relax_kind == 0 ? l : -1);                                  // :90
         // ---- post-relaxation (:92-103) ----
         if (relax_kind == 1) {
@@ -1148,6 +1161,7 @@ struct Hierarchy : HierarchyBase {
 
     // one cycle on the caller's buffers (b in L[0].b, x in ucur); the result pointer is returned
     TV* cycle_top(bool xzero) {
+        MGB_CHECK(!krylov_only, "a mixed-precision handle has no cycle of its own: call the single-precision handle");
         ensure_work();
         TV* other = (ucur == ux0) ? ux1 : ux0;
         ucur = cycle_fine(L[0].b, ucur, other, xzero, cycle_type);
@@ -1156,6 +1170,7 @@ struct Hierarchy : HierarchyBase {
 
     // ---- solveMG (SolveFuncs.jl:3-39) on the device buffers L[0].b / xcur ---------------------
     int solveMG(double tol, int max_iter, double* resvec) {
+        MGB_CHECK(!krylov_only, "solveMG on a mixed-precision handle: call the single-precision handle");
         ensure_work();
         Level<TV>& lv = L[0];
         const long long nm = lv.n * m;
@@ -1186,6 +1201,7 @@ struct Hierarchy : HierarchyBase {
 
     // getMultigridPreconditioner (SolveFuncs.jl:43-63): z .= 0; recursiveCycle(param,r,z,1); z
     TV* precondition(const TV* r) {
+        if (ext_prec) return ext_prec(r);
         Level<TV>& lv = L[0];
         return cycle_fine(r, lv.x0, lv.x1, true, cycle_type);
     }

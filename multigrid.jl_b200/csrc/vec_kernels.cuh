@@ -368,4 +368,16 @@ __global__ void cg_direction_kernel(long long n, const double* __restrict__ gamm
         p[i] = z[i] + beta * p[i];
 }
 
+// precision change of a vector block (mixed-precision preconditioner, SolveFuncs.jl:57: bl[:] .= b ... z2[:] .= z)
+__device__ __forceinline__ void convert_val(double a, float& o) { o = (float)a; }
+__device__ __forceinline__ void convert_val(float a, double& o) { o = (double)a; }
+__device__ __forceinline__ void convert_val(cplx a, cplxf& o) { o = make_cplxf((float)a.x, (float)a.y); }
+__device__ __forceinline__ void convert_val(cplxf a, cplx& o) { o = make_cplx((double)a.x, (double)a.y); }
+template <typename TS, typename TD>
+__global__ void convert_kernel(long long n, const TS* __restrict__ src, TD* __restrict__ dst) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) convert_val(src[i], dst[i]);
+}
+
 }  // namespace mgb200

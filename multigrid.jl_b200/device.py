@@ -19,7 +19,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmgb200.so")
 _LIB = None
 
-MGB200_FP64, MGB200_CFP64 = 0, 1
+MGB200_FP64, MGB200_CFP64, MGB200_FP32, MGB200_CFP32 = 0, 1, 2, 3
+_VT_CODE = {np.dtype(np.float64): MGB200_FP64, np.dtype(np.complex128): MGB200_CFP64,
+            np.dtype(np.float32): MGB200_FP32, np.dtype(np.complex64): MGB200_CFP32}
+
+
+def _real_dtype(VAL):
+    """real(VAL): the value type of Ps / Rs (SA-AMG.jl:9-10, MGsetup.jl:80-81)."""
+    return np.dtype(np.float32) if np.dtype(VAL) in (np.dtype(np.float32), np.dtype(np.complex64)) else np.dtype(np.float64)
 KIND_NAMES = ["sweep", "resid", "spmv", "restrict", "prolong", "diag", "coarse", "reduce", "vector", "copy"]
 
 _c_i64p = ctypes.POINTER(ctypes.c_int64)
@@ -72,13 +79,9 @@ class DeviceHierarchy:
     def __init__(self, param, device: int = 0):
         L = lib()
         VAL = np.dtype(param.VAL)
-        if VAL == np.float64:
-            vt = MGB200_FP64
-        elif VAL == np.complex128:
-            vt = MGB200_CFP64
-        else:
-            raise MGB200Error("only Float64 and ComplexF64 hierarchies are supported on the device "
-                              "(single precision is a 'next' row, SURVEY.md section 8(f))")
+        if VAL not in _VT_CODE:
+            raise MGB200Error(f"value type {VAL} is not one of Float64, ComplexF64, Float32, ComplexF32")
+        vt = _VT_CODE[VAL]
         if param.relaxType in ("Jac", "SPAI"):
             rk = 0
         elif param.relaxType == "Jac-GMRES":
@@ -96,7 +99,7 @@ class DeviceHierarchy:
         self.h = _vp()
         _check(L.mgb200_create(ctypes.byref(self.h), vt, self.levels, self.nrhs,
                                ctypes.c_char(param.cycleType.encode()), rk, _ptr(pre), _ptr(post), device))
-        rVAL = np.float64
+        rVAL = _real_dtype(VAL)
         try:
             for l in range(self.levels - 1):
                 acp, arv, anz = _csc_arrays(param.As[l], VAL)
@@ -120,6 +123,29 @@ class DeviceHierarchy:
         except Exception:
             self.destroy()
             raise
+
+    # -- mixed precision ------------------------------------------------------------------------
+    @classmethod
+    def mixed_over(cls, inner: "DeviceHierarchy", AT):
+        """Double-precision Krylov handle over the single-precision hierarchy ``inner``
+        (getMultigridPreconditioner with VAL != eltype(B), SolveFuncs.jl:52-60); AT is the matrix the
+        Krylov method multiplies with (getAfun(AT,...), SolveFuncs.jl:65-71), stored in double precision."""
+        if inner.VAL not in (np.dtype(np.float32), np.dtype(np.complex64)):
+            raise MGB200Error("mixed precision needs a Float32 / ComplexF32 hierarchy")
+        self = cls.__new__(cls)
+        self.VAL = np.dtype(np.float64) if inner.VAL == np.dtype(np.float32) else np.dtype(np.complex128)
+        self.levels = 1
+        self.n = inner.n
+        self.nrhs = inner.nrhs
+        self.inner = inner
+        self.h = _vp()
+        _check(lib().mgb200_create_mixed(ctypes.byref(self.h), inner.h))
+        try:
+            self.set_krylov_matrix(AT)
+        except Exception:
+            self.destroy()
+            raise
+        return self
 
     # -- multi-GPU ------------------------------------------------------------------------------
     @staticmethod
@@ -196,8 +222,12 @@ class DeviceHierarchy:
     def adjust_nrhs(self, nrhs: int):
         _check(lib().mgb200_adjust_nrhs(self.h, int(nrhs)))
         self.nrhs = int(nrhs)
+        if getattr(self, "inner", None) is not None:
+            self.inner.adjust_nrhs(nrhs)
 
     def set_cycle(self, param):
+        if getattr(self, "inner", None) is not None:
+            return self.inner.set_cycle(param)
         pre = np.array([param.relaxPre(l + 1) for l in range(self.levels)], dtype=np.int64)
         post = np.array([param.relaxPost(l + 1) for l in range(self.levels)], dtype=np.int64)
         _check(lib().mgb200_set_cycle(self.h, ctypes.c_char(param.cycleType.encode()), _ptr(pre), _ptr(post)))

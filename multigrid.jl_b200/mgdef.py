@@ -68,6 +68,8 @@ class MGparam:
         self.singlePrecision = self.VAL in (np.float32, np.complex64)
         self.nrhs = 0          # nrhs the device workspaces are sized for
         self.device = None     # uploaded hierarchy (multigrid_jl_b200.device.DeviceHierarchy)
+        self._mixed_device = None  # double-precision Krylov handle over a single-precision hierarchy
+        self._mixed_key = None
         self.aggregates = []   # SA-AMG integer maps per level (kept for parity checks)
 
 
@@ -106,6 +108,9 @@ def clear(param: MGparam):
     param.aggregates = []
     param.LU = []
     param.nrhs = 0
+    if getattr(param, "_mixed_device", None) is not None:
+        param._mixed_device.destroy()   # before the hierarchy it preconditions with
+        param._mixed_device = None
     if param.device is not None:
         param.device.destroy()
         param.device = None

@@ -146,6 +146,9 @@ def MGsetup(ATf, Mesh: RegularMesh, param: MGparam, nrhs: int = 1, verbose: bool
 
 
 def _invalidate_device(param: MGparam):
+    if getattr(param, "_mixed_device", None) is not None:
+        param._mixed_device.destroy()   # before the hierarchy it preconditions with
+        param._mixed_device = None
     if param.device is not None:
         param.device.destroy()
         param.device = None

@@ -26,6 +26,33 @@ def _device(param: MGparam, b):
     return dev
 
 
+def _is_single(dt) -> bool:
+    return np.dtype(dt) in (np.dtype(np.float32), np.dtype(np.complex64))
+
+
+def _krylov_device(param: MGparam, AT, b):
+    """Device handle the Krylov drivers run on.  A single-precision hierarchy under double-precision b / x0 is the
+    reference's mixed-precision mode (getMultigridPreconditioner, SolveFuncs.jl:52-60: the cycle runs in single
+    precision on a rounded copy of the residual, the Krylov method and its matrix stay in double precision)."""
+    dev = _device(param, b)
+    if not (_is_single(param.VAL) and not _is_single(np.asarray(b).dtype)):
+        _krylov_matrix(dev, AT, param)
+        return dev
+    import scipy.sparse as sp
+    key = None if AT is None else id(AT)
+    mixed = getattr(param, "_mixed_device", None)
+    if mixed is None or mixed.inner is not dev or getattr(param, "_mixed_key", None) != key:
+        if mixed is not None:
+            mixed.destroy()
+        Ak = param.As[0] if AT is None else AT
+        kd = np.complex128 if np.iscomplexobj(Ak.data) or np.dtype(param.VAL).kind == "c" else np.float64
+        mixed = type(dev).mixed_over(dev, sp.csc_matrix(Ak).astype(kd))
+        param._mixed_device, param._mixed_key = mixed, key
+    if mixed.nrhs != _nrhs(b):
+        mixed.adjust_nrhs(_nrhs(b))
+    return mixed
+
+
 def solveMG(param: MGparam, b, x, verbose: bool = False):
     """solveMG(param,b,x,verbose) -> (x, param, iter)   (SolveFuncs.jl:3-39).
     ``param.last_resvec`` holds [res_init, res_1, ...] (the per-cycle residual norms)."""
@@ -59,8 +86,7 @@ def _krylov_matrix(dev, AT, param):
 def solveCG_MG(AT, param: MGparam, b, x0, verbose: bool = False):
     """solveCG_MG(AT,param,b,x0,verbose) -> (x, param, iter)   (SolveFuncs.jl:77-79,103-116).
     AT is the (adjoint-stored) matrix the Krylov method multiplies with."""
-    dev = _device(param, b)
-    _krylov_matrix(dev, AT, param)
+    dev = _krylov_device(param, AT, b)
     xx, it, flag, res = dev.solveCG(b, x0, param.relativeTol, param.maxOuterIter)
     param.last_resvec, param.last_flag = res, flag
     x0[...] = xx.reshape(x0.shape)
@@ -70,8 +96,7 @@ def solveCG_MG(AT, param: MGparam, b, x0, verbose: bool = False):
 def solveBiCGSTAB_MG(AT, param: MGparam, b, x0, verbose: bool = False):
     """solveBiCGSTAB_MG(AT,param,b,x0,verbose) -> (x, param, iter, nprec)   (SolveFuncs.jl:73-75,85-99);
     an n x nrhs block b runs KrylovMethods.blockBiCGSTB (SolveFuncs.jl:95)."""
-    dev = _device(param, b)
-    _krylov_matrix(dev, AT, param)
+    dev = _krylov_device(param, AT, b)
     xx, it, flag, res, nprec = dev.solveBiCGSTAB(b, x0, param.relativeTol, param.maxOuterIter)
     param.last_resvec, param.last_flag = res, flag
     x0[...] = xx.reshape(x0.shape)
@@ -81,8 +106,7 @@ def solveBiCGSTAB_MG(AT, param: MGparam, b, x0, verbose: bool = False):
 def solveGMRES_MG(AT, param: MGparam, b, x0, flexible: bool, inner: int, verbose: bool = False):
     """solveGMRES_MG(AT,param,b,x0,flexible,inner,verbose) -> (x, param, iter, resvec)
     (SolveFuncs.jl:80-82,120-132)."""
-    dev = _device(param, b)
-    _krylov_matrix(dev, AT, param)
+    dev = _krylov_device(param, AT, b)
     xx, it, flag, res = dev.solveFGMRES(b, x0, inner, flexible, param.relativeTol, param.maxOuterIter)
     param.last_resvec, param.last_flag = res, flag
     x0[...] = xx.reshape(x0.shape)
