@@ -42,14 +42,18 @@ static PaddedRegistry& padded_registry() {
     static PaddedRegistry r;
     return r;
 }
-// Every vector carries 4 elements of zeroed slack and starts on a 16-byte boundary (pad rounded up to an even
-// element count), so that the bulk copies of the TMA kernels may round their ranges outwards to even elements.
-static inline size_t even_pad(size_t pad) { return (pad + 1) & ~(size_t)1; }
+// Every vector carries 4 elements of zeroed slack and starts on a 16-byte boundary (pad rounded up to a multiple of
+// tma_align<T>() elements: 2 for the 8- and 16-byte value types, 4 for Float32), so that the bulk copies of the TMA
+// kernels may round their ranges outwards to that granularity.
+template <typename T>
+constexpr int tma_align() { return sizeof(T) >= 8 ? 2 : 4; }
+template <typename T>
+static inline size_t align_pad(size_t pad) { return (pad + tma_align<T>() - 1) & ~(size_t)(tma_align<T>() - 1); }
 template <typename T>
 static T* vec_alloc(size_t total, size_t pad, cudaStream_t stream) {
     T* b = dev_alloc<T>(total + 4);
     MGB_CUDA(cudaMemsetAsync(b, 0, (total + 4) * sizeof(T), stream));
-    pad = even_pad(pad);
+    pad = align_pad<T>(pad);
     if (pad == 0) return b;
     PaddedRegistry& r = padded_registry();
     std::lock_guard<std::mutex> g(r.mu);
@@ -328,7 +332,7 @@ static void upload_csr(Context& ctx, Csr<TA>& M, long long n_rows, long long n_c
         if (build_patterns<TA>(n_rows, colptr, rowval, nzval, base, conjugate, PAT_MAX_PATTERNS, PAT_MAX_ENTRIES, hp)) {
             upload_patterns<TA>(M.pat, hp, n_rows);
             M.pat.xlo = 0;                               // input vectors hold n_cols elements (+ slack, vec_alloc)
-            M.pat.xhi = (n_cols + 1) & ~1LL;
+            M.pat.xhi = (long long)align_pad<TA>((size_t)n_cols);
         }
     }
 }

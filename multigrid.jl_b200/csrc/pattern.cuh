@@ -218,8 +218,8 @@ constexpr int TMA_MAX_WIN = 16;
 constexpr int TMA_MAX_ENT = 1024;   // dictionary entries / patterns that fit the shared-memory copy
 constexpr int TMA_MAX_PAT = 256;
 struct TmaWin {
-    int lo_even;   // lowest offset of the window rounded down to an even element (16-byte aligned copies)
-    int len;       // elements copied (even)
+    int lo_even;   // lowest offset of the window rounded down to 16 bytes (2 elements, 4 for Float32)
+    int len;       // elements copied (a multiple of the same granularity)
     int sbase;     // first element of the window in the stage buffer
 };
 struct TmaPlan {
@@ -281,9 +281,10 @@ static bool build_tma_plan(const HostPatterns<TA>& H, int tile, TmaPlan& P, std:
     std::memset(&P, 0, sizeof(P));
     int nw = 0, sb = 0;
     auto close = [&](int lo, int hi) {
-        const int lo_even = lo & ~1;
+        constexpr int AL = sizeof(TA) >= 8 ? 2 : 4;          // elements per 16 bytes (at least 2): tma_align, hierarchy.cuh
+        const int lo_even = lo & ~(AL - 1);
         int len = (hi - lo_even) + tile;
-        len = (len + 1) & ~1;
+        len = (len + AL - 1) & ~(AL - 1);
         P.w[nw].lo_even = lo_even;
         P.w[nw].len = len;
         P.w[nw].sbase = sb;
@@ -352,8 +353,7 @@ static void upload_patterns(PatDict<TA>& D, const HostPatterns<TA>& H, long long
     std::vector<int> soff;
     int max_len = 0;
     for (int p = 0; p < D.npat; ++p) max_len = std::max(max_len, H.pat_off[p + 1] - H.pat_off[p]);
-    // (4-byte values would need the copies rounded to 4 elements: Float32 matrices keep the one-pass kernel)
-    if (sizeof(TA) >= 8 && max_len < (1 << 11) && build_tma_plan<TA>(H, TmaTile<TA>::NT, D.plan, soff)) {
+    if (max_len < (1 << 11) && build_tma_plan<TA>(H, TmaTile<TA>::NT, D.plan, soff)) {
         std::vector<int> hdr(D.npat);
         for (int p = 0; p < D.npat; ++p) hdr[p] = H.pat_off[p] | ((H.pat_off[p + 1] - H.pat_off[p]) << 20);
         MGB_CUDA(cudaMalloc(&D.hdr, D.npat * sizeof(int)));
@@ -484,7 +484,8 @@ pat_tma_kernel(const __grid_constant__ TmaPlan P, const __grid_constant__ PutPla
         TV* sd = sb + (NEED_B ? NT : 0);
         uint16_t* sp = reinterpret_cast<uint16_t*>(sx + elems);
         const long long row0 = (long long)tile * NT;
-        const long long rend = min(row0 + NT, (long long)((n_rows + 1) & ~1));   // vectors carry 2 elements of slack
+        constexpr int AL = sizeof(TV) >= 8 ? 2 : 4;
+        const long long rend = min(row0 + NT, (long long)((n_rows + AL - 1) & ~(AL - 1)));   // vectors carry 4 elements of slack
         const long long pend = min(row0 + NT, (long long)((n_rows + 7) & ~7));
         uint32_t bytes = (uint32_t)(pend - row0) * 2u;
         for (int g = 0; g < P.nwin; ++g) {

@@ -481,8 +481,8 @@ struct Hierarchy : HierarchyBase {
             MGB_CUDA(cudaMemcpy(lv.d, lv.hd.data(), lv.n * sizeof(TV), cudaMemcpyHostToDevice));
             fold_d(lv, lv.hd.data());
             // input vectors of A_l are laid out [ghosts below | owned | ghosts above] around the vector pointer
-            lv.A.pat.xlo = -(long long)even_pad((size_t)sp.n_lo);
-            lv.A.pat.xhi = (sp.n_owned + (sp.n_ghost - sp.n_lo) + 1) & ~1LL;
+            lv.A.pat.xlo = -(long long)align_pad<TV>((size_t)sp.n_lo);
+            lv.A.pat.xhi = (long long)align_pad<TV>((size_t)(sp.n_owned + (sp.n_ghost - sp.n_lo)));
         }
         for (int l = 0; l < levels - 1; ++l) {
             L[l].hA.clear();
@@ -548,7 +548,7 @@ struct Hierarchy : HierarchyBase {
         work_ready = true;
     }
     // elements in front of the first owned row of a level-l vector (lower ghost rows, dist.cuh)
-    size_t vec_pad(int l) const { return L[l].sp.dist ? even_pad((size_t)L[l].sp.n_lo * m) : 0; }
+    size_t vec_pad(int l) const { return L[l].sp.dist ? align_pad<TV>((size_t)L[l].sp.n_lo * m) : 0; }
     void alloc_fgmres(FgmresMem<TV>& mem, size_t nm, int inner, size_t pad) {
         mem.release();
         mem.inner = inner;
