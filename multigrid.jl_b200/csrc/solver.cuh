@@ -176,6 +176,13 @@ struct Hierarchy : HierarchyBase {
     }
     void set_cycle(char ct, const int64_t* rpre, const int64_t* rpost) {
         MGB_CHECK(ct == 'V' || ct == 'F' || ct == 'W' || ct == 'K', "cycle_type must be V, F, W or K");
+        // the front ends set the cycle before every solve: unchanged parameters keep the workspaces and graphs
+        if (ct == cycle_type && (int)pre.size() == levels && (int)post.size() == levels) {
+            bool same = true;
+            if (rpre && rpost)
+                for (int l = 0; l < levels && same; ++l) same = (pre[l] == (int)rpre[l] && post[l] == (int)rpost[l]);
+            if (same) return;
+        }
         cycle_type = ct;
         invalidate_graphs();
         if (rpre && rpost) {
