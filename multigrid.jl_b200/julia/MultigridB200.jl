@@ -15,8 +15,12 @@ const libmgb200 = joinpath(dirname(pathof(Multigrid)), "..", "deps", "builds", "
 
 const MGB200_FP64  = Cint(0)
 const MGB200_CFP64 = Cint(1)
+const MGB200_FP32  = Cint(2)   # getMGparam(Float32, ...) / getMGparam(ComplexF32, ...): `singlePrecision`
+const MGB200_CFP32 = Cint(3)   # hierarchies (MGdef.jl:119,151; MGsetup.jl:31-33,79-82,108-110)
 valtype_code(::Type{Float64})    = MGB200_FP64
 valtype_code(::Type{ComplexF64}) = MGB200_CFP64
+valtype_code(::Type{Float32})    = MGB200_FP32
+valtype_code(::Type{ComplexF32}) = MGB200_CFP32
 
 check(status::Cint) = status == 0 ? nothing :
     error("mgb200 status $status: ", unsafe_string(ccall((:mgb200_last_error, libmgb200), Cstring, ())))
@@ -48,8 +52,8 @@ function uploadHierarchy(param::MGparam{VAL,Int64}; device::Integer=0) where {VA
         check(ccall((:mgb200_upload_level, libmgb200), Cint,
                     (Ptr{Cvoid}, Cint, Int64, Int64,
                      Ptr{Int64}, Ptr{Int64}, Ptr{VAL},
-                     Ptr{Int64}, Ptr{Int64}, Ptr{Float64},
-                     Ptr{Int64}, Ptr{Int64}, Ptr{Float64},
+                     Ptr{Int64}, Ptr{Int64}, Ptr{real(VAL)},      # Ps, Rs hold real(VAL) values
+                     Ptr{Int64}, Ptr{Int64}, Ptr{real(VAL)},
                      Ptr{VAL}, Cint),
                     h[], l, size(AT, 2), size(param.As[l+1], 2),
                     AT.colptr, AT.rowval, AT.nzval,
@@ -104,6 +108,35 @@ function solveCG_MG(AT::SparseMatrixCSC{VAL,Int64}, param::MGparam{VAL,Int64}, d
     check(ccall((:mgb200_solveCG, libmgb200), Cint,
                 (Ptr{Cvoid}, Ptr{VAL}, Ptr{VAL}, Cdouble, Cint, Ref{Cint}, Ref{Cint}, Ptr{Cdouble}),
                 dev.handle, b, x0, param.relativeTol, param.maxOuterIter, iter, flag, resvec))
+    return x0, param, Int(iter[])
+end
+
+# ---- mixed precision (SolveFuncs.jl:52-60: VAL != eltype(B)) --------------------------------------
+# A Float32 / ComplexF32 hierarchy under Float64 / ComplexF64 Krylov vectors: the outer handle holds only the Krylov
+# matrix AT (double precision) and the Krylov vectors, its preconditioner is one cycle of `dev` on a rounded copy of
+# the residual.  The Krylov front ends below are then called with the outer handle and double-precision b, x0:
+#     dev32 = uploadHierarchy(param32);  outer = mixedPrecisionHandle(dev32, AT64)
+#     solveCG_MG(AT64, param32, outer, b64, x64)        # dispatches on eltype(b), like the reference
+function mixedPrecisionHandle(dev::DeviceHierarchy, AT::SparseMatrixCSC{VALD,Int64}) where {VALD<:Union{Float64,ComplexF64}}
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:mgb200_create_mixed, libmgb200), Cint, (Ref{Ptr{Cvoid}}, Ptr{Cvoid}), h, dev.handle))
+    check(ccall((:mgb200_set_krylov_matrix, libmgb200), Cint,
+                (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{VALD}, Cint),
+                h[], size(AT, 2), AT.colptr, AT.rowval, AT.nzval, 1))
+    outer = DeviceHierarchy(h[])
+    finalizer(d -> ccall((:mgb200_destroy, libmgb200), Cint, (Ptr{Cvoid},), d.handle), outer)
+    return outer     # `dev` must outlive it
+end
+function solveCG_MG(AT::SparseMatrixCSC{VALD,Int64}, param::MGparam{VAL,Int64}, outer::DeviceHierarchy,
+                    inner::DeviceHierarchy, b::Array{VALD}, x0::Array{VALD}) where {VAL<:Union{Float32,ComplexF32},VALD<:Union{Float64,ComplexF64}}
+    for h in (inner.handle, outer.handle)
+        check(ccall((:mgb200_adjust_nrhs, libmgb200), Cint, (Ptr{Cvoid}, Cint), h, size(b, 2)))
+    end
+    iter = Ref{Cint}(0); flag = Ref{Cint}(0)
+    resvec = zeros(param.maxOuterIter * size(b, 2))
+    check(ccall((:mgb200_solveCG, libmgb200), Cint,
+                (Ptr{Cvoid}, Ptr{VALD}, Ptr{VALD}, Cdouble, Cint, Ref{Cint}, Ref{Cint}, Ptr{Cdouble}),
+                outer.handle, b, x0, param.relativeTol, param.maxOuterIter, iter, flag, resvec))
     return x0, param, Int(iter[])
 end
 
