@@ -219,6 +219,16 @@ int mgb200_pattern_info(mgb200_handle h, int level, int which, int64_t* out);
  * "split_test" (rows: single-GPU test hook that forces the split launch sequence of the overlap path). */
 int mgb200_set_option(mgb200_handle h, const char* key, int64_t value);
 
+/* Host-only (no GPU): the window plan of the TMA-staged dictionary kernel for a row-relative matrix, exported for the
+ * CPU test-suite.  Input as mgb200_host_build_patterns; `tile` rows per tile, elem_bytes 4, 8 or 16 (copies are rounded
+ * outwards to 16 bytes).  info[0] = 1 if a plan exists (row-relative dictionary, few enough windows), info[1] = windows,
+ * info[2] = elements per stage, info[3] = stage offset of the centre x[row], info[4] = dictionary entries.
+ * win[3*g .. 3*g+2] = (lowest offset, elements copied, first element in the stage buffer) of window g (<= 16 windows);
+ * delta[k] / soff[k] = column offset and stage offset of dictionary entry k (caller-allocated, max_entries). */
+int mgb200_host_tma_plan(int64_t n_rows, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+                         int index_base, int tile, int elem_bytes, int max_patterns, int max_entries, int64_t* info,
+                         int32_t* win, int32_t* delta, int32_t* soff);
+
 /* Host-only (no GPU): the row deduplication behind the stencil dictionary, exported for the CPU test-suite.
  * Input: CSR arrays (row pointers colptr[n_rows+1], Int64 columns, Float64 values).  info[0] = 1 if the matrix
  * deduplicates within max_patterns / max_entries, info[1] = row-relative, info[2] = patterns, info[3] = entries.

@@ -137,6 +137,34 @@ static HierarchyBase* make_mixed(Hierarchy<TS>* in) {
     return out;
 }
 
+template <typename TA>
+static void host_tma_plan_impl(const HostPatterns<double>& hp, int tile, int64_t* info, int32_t* win, int32_t* delta,
+                               int32_t* soff) {
+    // the plan depends on the offsets and on the element size only: re-type the dictionary
+    HostPatterns<TA> h;
+    h.ok = hp.ok;
+    h.rowrel = hp.rowrel;
+    h.pat_off = hp.pat_off;
+    h.delta = hp.delta;
+    h.val.resize(hp.val.size());
+    TmaPlan P;
+    std::vector<int> so;
+    if (!build_tma_plan<TA>(h, tile, P, so)) return;
+    info[0] = 1;
+    info[1] = P.nwin;
+    info[2] = P.total;
+    info[3] = P.centre;
+    for (int g = 0; g < P.nwin; ++g) {
+        win[3 * g] = P.w[g].lo_even;
+        win[3 * g + 1] = P.w[g].len;
+        win[3 * g + 2] = P.w[g].sbase;
+    }
+    for (size_t k = 0; k < so.size(); ++k) {
+        delta[k] = hp.delta[k];
+        soff[k] = so[k];
+    }
+}
+
 extern "C" {
 
 const char* mgb200_last_error(void) { return g_last_error.c_str(); }
@@ -517,6 +545,25 @@ int mgb200_host_build_patterns(int64_t n_rows, const int64_t* colptr, const int6
         std::memcpy(pat_off, hp.pat_off.data(), hp.pat_off.size() * sizeof(int32_t));
         std::memcpy(delta, hp.delta.data(), hp.delta.size() * sizeof(int32_t));
         std::memcpy(val, hp.val.data(), hp.val.size() * sizeof(double));
+    }
+    MGB_CATCH
+}
+
+int mgb200_host_tma_plan(int64_t n_rows, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+                         int index_base, int tile, int elem_bytes, int max_patterns, int max_entries, int64_t* info,
+                         int32_t* win, int32_t* delta, int32_t* soff) {
+    MGB_TRY
+    MGB_CHECK(colptr && rowval && nzval && info && win && delta && soff && tile > 0, "bad argument");
+    MGB_CHECK(elem_bytes == 4 || elem_bytes == 8 || elem_bytes == 16, "elem_bytes must be 4, 8 or 16");
+    HostPatterns<double> hp;
+    const bool ok = build_patterns<double>(n_rows, colptr, rowval, nzval, index_base, false, max_patterns,
+                                           max_entries, hp);
+    info[0] = info[1] = info[2] = info[3] = 0;
+    info[4] = ok ? (int64_t)hp.delta.size() : 0;
+    if (ok && hp.rowrel) {
+        if (elem_bytes == 4) host_tma_plan_impl<float>(hp, tile, info, win, delta, soff);
+        else if (elem_bytes == 8) host_tma_plan_impl<double>(hp, tile, info, win, delta, soff);
+        else host_tma_plan_impl<cplx>(hp, tile, info, win, delta, soff);
     }
     MGB_CATCH
 }

@@ -404,6 +404,28 @@ def host_build_patterns(M, max_patterns=4096, max_entries=1 << 16):
                 val=va[:nent])
 
 
+def host_tma_plan(M, tile=1024, elem_bytes=8, max_patterns=4096, max_entries=1 << 16):
+    """Host-only window plan of the TMA-staged dictionary kernel (csrc/pattern.cuh::build_tma_plan) for the CSC
+    arrays of ``M`` read as CSR.  Returns None when the matrix has no row-relative dictionary or needs too many
+    windows; else dict(windows=[(lo, len, sbase), ...], total, centre, delta, soff)."""
+    M = sp.csc_matrix(M)
+    if not M.has_sorted_indices:
+        M.sort_indices()
+    n = M.shape[1]
+    cp, rv, nz = _i64(M.indptr), _i64(M.indices), np.ascontiguousarray(M.data, dtype=np.float64)
+    info = np.zeros(5, dtype=np.int64)
+    win = np.zeros(3 * 16, dtype=np.int32)
+    de = np.zeros(max_entries, dtype=np.int32)
+    so = np.zeros(max_entries, dtype=np.int32)
+    _check(lib().mgb200_host_tma_plan(ctypes.c_int64(n), _ptr(cp), _ptr(rv), _ptr(nz), 0, int(tile), int(elem_bytes),
+                                      int(max_patterns), int(max_entries), _ptr(info), _ptr(win), _ptr(de), _ptr(so)))
+    if not info[0]:
+        return None
+    nw, nent = int(info[1]), int(info[4])
+    return dict(windows=[tuple(int(v) for v in win[3 * g:3 * g + 3]) for g in range(nw)], total=int(info[2]),
+                centre=int(info[3]), delta=de[:nent].copy(), soff=so[:nent].copy())
+
+
 def uploadHierarchy(param, device: int = 0):
     """Upload (or reuse) the device copy of ``param``'s hierarchy."""
     if len(param.As) == 0:

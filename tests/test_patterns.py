@@ -72,6 +72,59 @@ def test_host_patterns_empty_rows_and_caps():
     assert device.host_build_patterns(M, max_patterns=1) is None
 
 
+def _check_plan(plan, tile, al):
+    """Every dictionary offset lies in exactly the window its stage offset points into; windows are 16-byte
+    granular, disjoint in the stage buffer and long enough for a whole tile."""
+    wins = plan["windows"]
+    assert plan["total"] == sum(w[1] for w in wins)
+    sb = 0
+    for lo, ln, base in wins:
+        assert lo % al == 0 and ln % al == 0 and base == sb
+        sb += ln
+    for d, so in zip(list(plan["delta"]) + [0], list(plan["soff"]) + [plan["centre"]]):
+        hit = [(lo, ln, base) for lo, ln, base in wins if base <= so < base + ln]
+        assert len(hit) == 1
+        lo, ln, base = hit[0]
+        assert so - base == d - lo                     # x[row + d] of thread t sits at stage[so + t]
+        assert 0 <= so - base and (so - base) + tile <= ln   # ... for every t < tile
+
+
+@pytest.mark.parametrize("elem_bytes,al", [(8, 2), (4, 4), (16, 2)])
+def test_tma_plan_merges_windows_of_a_3d_stencil(elem_bytes, al, monkeypatch):
+    """7-point and 27-point operators on a 41^3-node grid, tile 256: the y-neighbour lines (gap 41-2 < tile) share the
+    window of the centre line, the z-planes (gap 41^2 - ... > tile) keep their own: 3 windows.  With the round-1
+    threshold (gap 32) the same matrices need 5 and 9."""
+    import multigrid_jl_b200 as mg
+    from multigrid_jl_b200 import device
+    monkeypatch.delenv("MGB200_TMA_GAP", raising=False)
+    M = mg.getRegularMesh([0, 1, 0, 1, 0, 1], [40, 40, 40])
+    A = mg.poisson_shifted(M, 1e-4)
+    p = mg.getMGparam(np.float64, np.int64, 2, 8, 5, 1e-8, "Jac", 0.8, 2, 2, 'V')
+    mg.MGsetup(A, M, p, 1)
+    tile = 256
+    for mat, n1, old in ((p.As[0], 41, 5), (p.As[1], 21, 9)):
+        monkeypatch.delenv("MGB200_TMA_GAP", raising=False)
+        plan = device.host_tma_plan(mat, tile=tile, elem_bytes=elem_bytes)
+        assert plan is not None and len(plan["windows"]) == 3
+        _check_plan(plan, tile, al)
+        # the middle window spans the three lines of the own plane
+        lo, ln, _ = plan["windows"][1]
+        assert lo <= -(n1 + 1) and lo + ln - tile >= n1 + 1
+        monkeypatch.setenv("MGB200_TMA_GAP", "8")
+        plan_old = device.host_tma_plan(mat, tile=tile, elem_bytes=elem_bytes)
+        assert len(plan_old["windows"]) == old
+        _check_plan(plan_old, tile, al)
+        assert plan["total"] < plan_old["total"]        # fewer elements copied per tile
+
+
+def test_tma_plan_absent_for_transfer_operators():
+    """P and R take their offsets from the first stored column, not from the row: no TMA plan."""
+    from multigrid_jl_b200 import device
+    A, AT, M, p, b = _cpu_problem([16, 16], 3)
+    assert device.host_tma_plan(p.Ps[0]) is None
+    assert device.host_tma_plan(p.As[0], tile=64) is not None
+
+
 def _cpu_problem(n, levels):
     import multigrid_jl_b200 as mg
     dom = [0.0, 1.0] * len(n)
