@@ -243,10 +243,13 @@ def run_reference(args):
         "steps": len(times), "warmup": 1, "ms_per_step": tmax * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"cfg2: 3D Poisson {cells}^3 cells ({cells + 1}^3 nodes), geometric MG Galerkin "
-                               f"{p.levels} levels, damped Jacobi 0.8, one V(2,2) cycle from x=0 per step"},
+                               f"{p.levels} levels, damped Jacobi 0.8, one V(2,2) cycle from x=0 per step",
+                   "rows": N, "parallelism": f"host CPU, {cores} OpenMP threads"},
         "cpu_baseline": {"value": val, "unit": "DOF/s", "cores": cores, "kind": "port",
-                         "sample": f"{len(times)} full V(2,2) cycles of the same hierarchy (unfused reference order, "
-                                   f"OpenMP row-parallel SpMV, Int64 indices)",
+                         "sample": f"{len(times)} full V(2,2) cycles of the {cells + 1}^3 hierarchy (unfused reference "
+                                   f"order, OpenMP row-parallel SpMV, Int64 indices)"
+                                   + ("" if args.gpus == 1 else f"; bounded sample of the {args.gpus}-GPU weak-scaled "
+                                      f"workload: DOF/s of the memory-bound CPU path does not depend on the grid size"),
                          "effective_gbs": nbytes / tmax / 1e9},
         "e2e": {"value": val, "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
