@@ -192,6 +192,7 @@ def SA_AMGsetup(AT, param: MGparam, symm: bool = True, nrhs: int = 1, verbose: b
     if np.iscomplexobj(np.zeros(0, dtype=VAL)):
         raise TypeError("SA-AMG is real-only in the reference (SURVEY appendix F)")
     norm = _op_norm if opnorm else _entry_norm
+    rVAL = np.zeros(0, dtype=VAL).real.dtype
     As, Ps, Rs, relaxPrecs, aggregates = [_csc(AT, dtype=VAL)], [], [], [], []
     levels = param.levels
     for l in range(levels - 1):
@@ -210,7 +211,12 @@ def SA_AMGsetup(AT, param: MGparam, symm: bool = True, nrhs: int = 1, verbose: b
         aggregates.append(agg)
         DAT = _csc(ATl @ sp.diags(d))
         rhoDAT = min(norm(DAT, 1), norm(DAT, np.inf))
-        PT = sparse_add_dropzeros(P0T, -(((1.33 / rhoDAT) * P0T) @ DAT))
+        # Julia: 1.33/rhoDAT is Float64 also for a Float32 hierarchy, PT is formed in the wider type and rounded to
+        # real(VAL) when it is stored into Ps / Rs (typed arrays, SA-AMG.jl:9-10,41-42); the Galerkin product then
+        # runs in VAL
+        PT = sparse_add_dropzeros(P0T, -(((1.33 / float(rhoDAT)) * P0T) @ DAT))
+        if PT.dtype != rVAL:
+            PT = _csc(PT, dtype=rVAL)
         Rs.append(_csc(PT.T))
         Ps.append(PT)
         As.append(_csc(galerkin(Ps[l], ATl, Rs[l]), dtype=VAL))

@@ -35,6 +35,32 @@ def test_single_precision_setup_types(kind, n):
     assert all(d.dtype == p.VAL for d in p.relaxPrecs)
 
 
+def test_sa_amg_setup_single_precision_types():
+    """SA_AMGsetup with a Float32 param: Ps / Rs are stored as real(VAL) (typed arrays, SA-AMG.jl:9-10), the Galerkin
+    products are formed from those rounded operators, the aggregates are those of the double-precision setup."""
+    import multigrid_jl_b200 as mg
+    M = mg.getRegularMesh([0, 1, 0, 1], [24, 24])
+    rng = np.random.default_rng(0)
+    w = mg.edge_weights_from_cells(M, np.exp(rng.standard_normal(24 * 24)))
+    A = mg.nodal_stencil_matrix(M, w, 1e-3)
+    p32 = mg.getMGparam(np.float32, np.int64, 3, 8, 5, 1e-6, "SPAI", 1.0, 1, 1, 'W')
+    p64 = mg.getMGparam(np.float64, np.int64, 3, 8, 5, 1e-6, "SPAI", 1.0, 1, 1, 'W')
+    mg.SA_AMGsetup(A, p32, True, 1)
+    mg.SA_AMGsetup(A, p64, True, 1)
+    assert all(m.dtype == np.float32 for m in p32.As + p32.Ps + p32.Rs)
+    assert all(d.dtype == np.float32 for d in p32.relaxPrecs)
+    assert [a.shape for a in p32.As] == [a.shape for a in p64.As]
+    for a32, a64 in zip(p32.aggregates, p64.aggregates):
+        assert np.array_equal(a32, a64)
+    for P32, P64 in zip(p32.Ps, p64.Ps):
+        assert np.array_equal(P32.indices, P64.indices)
+        np.testing.assert_allclose(P32.data, P64.data, rtol=1e-4, atol=1e-5)   # entries are O(1), some by cancellation
+    import scipy.sparse as sp
+    G = sp.csc_matrix((p32.Ps[0] @ p32.As[0]) @ p32.Rs[0])
+    G.sort_indices()
+    assert G.dtype == np.float32 and np.array_equal(G.data, p32.As[1].data)
+
+
 def test_oracle32_cycle_converges_to_single_precision_floor():
     from oracle import cycle as oc, cycle32 as o32
     import multigrid_jl_b200 as mg
