@@ -14,8 +14,11 @@
 //   gpurun_out/microbench_lines              # 7-point 257^3 and 27-point 129^3 on the GPU, all variants, bit-compare
 //   gpurun_out/microbench_lines --host-check # no GPU: runs the per-thread function on the CPU for 9^3 .. 12x9x7 grids
 //
-// NOT part of the library; not yet run on a B200 (written in a session whose GPU budget was spent; the host check
-// passes).
+// Two forms: (a) x straight from global memory (L1 / L2), (b) x staged in shared memory by bulk copies, one per plane of
+// the stencil, in a two-stage pipeline of persistent CTAs - the production kernel's scheme with another thread-to-row map.
+//
+// NOT part of the library; not yet run on a B200 (written in a session whose GPU budget was spent; the host check,
+// which also replays the staged form with host buffers filled like the bulk copies fill shared memory, passes).
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdint>
@@ -48,22 +51,41 @@ __global__ void __launch_bounds__(256) k_reference(Grid G, const uint16_t* __res
     if (row < G.n) y[row] = row_reference(G, row, pid, pat, ent, dp, x, b);
 }
 
-// one thread: column i of the R lines [y0, y0+R) of plane z.  x must be readable S2 + S + 1 elements beyond both ends.
+// Where a thread finds its data.  rel = row - T0 for a reference row T0 (0 for the global-memory form, the first row of
+// the tile for the staged form).  xs[dz+1][rel] == x[T0 + dz*S2 + rel] for every rel the thread may touch.
+struct View {
+    const double* xs[3];
+    const double* b;        // b[rel]
+    const uint16_t* pid;    // pid[rel]
+};
+
+// fallback: one row, dictionary walked entry by entry, x through the view (delta = dx + S*dy + S2*dz)
+__host__ __device__ inline double row_view(const Grid& G, const View& V, long long rel, const Pat* pat, const Ent* ent,
+                                           const double* dp) {
+    const int p = V.pid[rel];
+    const Pat P = pat[p];
+    double acc = 0.0;
+    for (int k = P.k0; k < P.k0 + P.len; ++k) {
+        const int d = ent[k].delta;
+        const int dz = (2 * d > G.S2) ? 1 : ((2 * d < -G.S2) ? -1 : 0);
+        const double* xb = dz > 0 ? V.xs[2] : (dz < 0 ? V.xs[0] : V.xs[1]);      // no dynamic index into the view
+        acc = acc + ent[k].v * xb[rel + (d - dz * G.S2)];
+    }
+    return V.xs[1][rel] + dp[p] * (V.b[rel] - acc);
+}
+
+// one thread: column i of the R lines [y0, y0+R) of plane z; rel0 = rel of its first row, row0 = that row's global index
 template <int R>
-__host__ __device__ inline void lines_thread(const Grid& G, int i, int y0, int z, const uint16_t* pid, const Pat* pat,
-                                             const Ent* ent, const double* dp, const double* x, const double* b, double* y) {
-    const long long row0 = (long long)z * G.S2 + (long long)y0 * G.S + i;
+__host__ __device__ inline void lines_thread(const Grid& G, const View& V, long long rel0, long long row0, int y0,
+                                             const Pat* pat, const Ent* ent, const double* dp, double* y) {
     const int nr = (G.n2 - y0 < R) ? (G.n2 - y0) : R;          // lines left in this plane
-    int p0 = pid[row0];
+    const int p0 = V.pid[rel0];
     bool same = (nr == R);
 #pragma unroll
     for (int j = 1; j < R; ++j)
-        if (j < nr) same = same && (pid[row0 + (long long)j * G.S] == p0);
+        if (j < nr) same = same && (V.pid[rel0 + (long long)j * G.S] == p0);
     if (!same) {                                                  // mixed patterns or a short group: row by row
-        for (int j = 0; j < nr; ++j) {
-            const long long row = row0 + (long long)j * G.S;
-            y[row] = row_reference(G, row, pid, pat, ent, dp, x, b);
-        }
+        for (int j = 0; j < nr; ++j) y[row0 + (long long)j * G.S] = row_view(G, V, rel0 + (long long)j * G.S, pat, ent, dp);
         return;
     }
     const Pat P = pat[p0];
@@ -76,15 +98,15 @@ __host__ __device__ inline void lines_thread(const Grid& G, int i, int y0, int z
     for (int dz = -1; dz <= 1; ++dz) {
         const int mz = (P.mask >> ((dz + 1) * 9)) & 0x1FF;
         if (mz == 0) continue;
-        const double* xp = x + row0 + (long long)dz * G.S2;
+        const double* xp = V.xs[dz + 1] + rel0;
         // which columns / lines of this plane does the pattern touch?
         const bool col_m = (mz & 0x049) != 0, col_0 = (mz & 0x092) != 0, col_p = (mz & 0x124) != 0;   // dx = -1, 0, +1
         const bool lin_m = (mz & 0x007) != 0, lin_p = (mz & 0x1C0) != 0;                               // dy = -1, +1
         double X[3][R + 2];
 #pragma unroll
         for (int l = 0; l < R + 2; ++l) {
-            const bool need = (l == 0) ? lin_m : (l == R + 1 ? lin_p : true);
             // dy = 0 entries use l = 1..R; dy = -1 uses 0..R-1; dy = +1 uses 2..R+1
+            const bool need = (l == 0) ? lin_m : (l == R + 1 ? lin_p : true);
             const double* q = xp + (long long)(l - 1) * G.S;
             X[0][l] = (need && col_m) ? q[-1] : 0.0;
             X[1][l] = (need && col_0) ? q[0] : 0.0;
@@ -111,14 +133,22 @@ __host__ __device__ inline void lines_thread(const Grid& G, int i, int y0, int z
     const double d = dp[p0];
 #pragma unroll
     for (int j = 0; j < R; ++j) {
-        const long long row = row0 + (long long)j * G.S;
-        if (!have_c) xc[j] = x[row];
-        y[row] = xc[j] + d * (b[row] - acc[j]);
+        const long long rel = rel0 + (long long)j * G.S;
+        if (!have_c) xc[j] = V.xs[1][rel];
+        y[row0 + (long long)j * G.S] = xc[j] + d * (V.b[rel] - acc[j]);
     }
 }
 
-// persistent grid-stride over the flattened (group, column) index; groups ordered plane by plane so that the three
-// planes a group reads stay L2 resident
+__host__ __device__ inline View global_view(const Grid& G, const uint16_t* pid, const double* x, const double* b) {
+    View V;
+    V.xs[0] = x - G.S2; V.xs[1] = x; V.xs[2] = x + G.S2;
+    V.b = b; V.pid = pid;
+    return V;
+}
+
+// (a) straight from global memory: persistent grid-stride over the flattened (group, column) index; groups ordered plane
+// by plane so that the three planes a group reads stay L2 resident.  x must be addressable S2 elements beyond both ends
+// (only the pointer arithmetic goes there, no load does).
 template <int R>
 __global__ void __launch_bounds__(256) k_lines(Grid G, const uint16_t* __restrict__ pid, const Pat* __restrict__ pat,
                                                const Ent* __restrict__ ent, const double* __restrict__ dp,
@@ -126,13 +156,146 @@ __global__ void __launch_bounds__(256) k_lines(Grid G, const uint16_t* __restric
                                                double* __restrict__ y) {
     const int gpp = (G.n2 + R - 1) / R;                       // line groups per plane
     const long long total = (long long)G.n3 * gpp * G.S;
+    const View V = global_view(G, pid, x, b);
     for (long long f = blockIdx.x * (long long)blockDim.x + threadIdx.x; f < total; f += (long long)gridDim.x * blockDim.x) {
         const long long g = f / G.S;
         const int i = (int)(f - g * G.S);
         const int z = (int)(g / gpp), q = (int)(g - (long long)z * gpp);
-        lines_thread<R>(G, i, q * R, z, pid, pat, ent, dp, x, b, y);
+        const long long row0 = (long long)z * G.S2 + (long long)q * R * G.S + i;
+        lines_thread<R>(G, V, row0, row0, q * R, pat, ent, dp, y);
     }
 }
+
+// (b) staged: a tile is Q line groups of one plane (Q*R lines = Q*R*S consecutive rows).  Its x comes as three
+// contiguous ranges, one per plane of the stencil, each ONE bulk copy (the merged windows of csrc/pattern.cuh with a
+// tile of Q*R*S rows), plus the b and pid tiles.  Ranges are clipped to the vector and rounded outwards to 16 bytes.
+struct TilePlan {
+    long long T0;            // first row of the tile
+    int lines;               // lines in the tile (<= Q*R)
+    long long xa[3], xe[3];  // copy range of x per stencil plane, [xa, xe), even; xe <= xa: plane absent
+    long long ba, be;        // copy range of b (even)
+    long long pa, pe;        // copy range of pid (multiples of 8)
+};
+__host__ __device__ inline TilePlan plan_tile(const Grid& G, int R, int Q, long long tile) {
+    const int gpp = (G.n2 + R - 1) / R, tpp = (gpp + Q - 1) / Q;
+    const int z = (int)(tile / tpp), q0 = (int)(tile - (long long)z * tpp) * Q;
+    TilePlan T;
+    T.T0 = (long long)z * G.S2 + (long long)q0 * R * G.S;
+    const int left = G.n2 - q0 * R;
+    T.lines = left < Q * R ? left : Q * R;
+    const long long T1 = T.T0 + (long long)T.lines * G.S, nev = (G.n + 1) & ~1LL, n8 = (G.n + 7) & ~7LL;
+#pragma unroll
+    for (int dz = -1; dz <= 1; ++dz) {
+        if (z + dz < 0 || z + dz >= G.n3) { T.xa[dz + 1] = T.xe[dz + 1] = 0; continue; }
+        long long a = T.T0 + (long long)dz * G.S2 - G.S - 1, e = T1 + (long long)dz * G.S2 + G.S + 1;
+        a = a < 0 ? 0 : a;
+        e = e > nev ? nev : e;
+        T.xa[dz + 1] = a & ~1LL;
+        T.xe[dz + 1] = (e + 1) & ~1LL;
+    }
+    T.ba = T.T0 & ~1LL;
+    T.be = ((T1 + 1) & ~1LL) > nev ? nev : ((T1 + 1) & ~1LL);
+    T.pa = T.T0 & ~7LL;
+    T.pe = ((T1 + 7) & ~7LL) > n8 ? n8 : ((T1 + 7) & ~7LL);
+    return T;
+}
+// elements a stage must hold (same for every tile): 3 x-ranges, b, pid
+__host__ __device__ inline void stage_layout(const Grid& G, int R, int Q, int& xcap, int& bcap, int& pcap) {
+    xcap = (Q * R + 2) * G.S + 6;          // + 2 (the +-1 columns) + rounding
+    bcap = Q * R * G.S + 4;
+    pcap = Q * R * G.S + 16;
+    xcap = (xcap + 1) & ~1; bcap = (bcap + 1) & ~1; pcap = (pcap + 7) & ~7;
+}
+__host__ __device__ inline View stage_view(const Grid& G, const TilePlan& T, const double* sx, int xcap, const double* sb,
+                                           const uint16_t* sp) {
+    View V;
+    // xs[d][rel] = stage_d[(T0 + (d-1)*S2 + rel) - xa[d]]
+#pragma unroll
+    for (int d = 0; d < 3; ++d) V.xs[d] = sx + (long long)d * xcap + ((T.T0 + (long long)(d - 1) * G.S2) - T.xa[d]);
+    V.b = sb + (T.T0 - T.ba);
+    V.pid = sp + (T.T0 - T.pa);
+    return V;
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const uint32_t a = smem_u32(bar);
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+// persistent CTAs of ceil32(Q*S) threads, two stages; x, b, pid need 16-byte aligned bases and (for x) an allocation that
+// covers the even-rounded end of the vector
+template <int R, int NTMAX>
+__global__ void __launch_bounds__(NTMAX) k_lines_tma(Grid G, int Q, long long ntiles, const uint16_t* __restrict__ pid,
+                                                    const Pat* __restrict__ pat, const Ent* __restrict__ ent,
+                                                    const double* __restrict__ dp, const double* __restrict__ x,
+                                                    const double* __restrict__ b, double* __restrict__ y) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+    int xcap, bcap, pcap;
+    stage_layout(G, R, Q, xcap, bcap, pcap);
+    const size_t stage_bytes = (((size_t)(3 * xcap + bcap) * 8 + (size_t)pcap * 2) + 127) / 128 * 128;
+    unsigned char* stage0 = smem_raw + 128;
+    const int t = threadIdx.x;
+    if (t == 0) {
+        mbar_init(full, 1);
+        mbar_init(full + 1, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    auto issue = [&](long long tile, int s) {
+        const TilePlan T = plan_tile(G, R, Q, tile);
+        double* sx = reinterpret_cast<double*>(stage0 + (size_t)s * stage_bytes);
+        double* sb = sx + 3 * (size_t)xcap;
+        uint16_t* sp = reinterpret_cast<uint16_t*>(sb + bcap);
+        uint32_t bytes = (uint32_t)(T.be - T.ba) * 8u + (uint32_t)(T.pe - T.pa) * 2u;
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+            if (T.xe[d] > T.xa[d]) bytes += (uint32_t)(T.xe[d] - T.xa[d]) * 8u;
+        mbar_expect_tx(full + s, bytes);
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+            if (T.xe[d] > T.xa[d]) bulk_g2s(sx + (size_t)d * xcap, x + T.xa[d], (uint32_t)(T.xe[d] - T.xa[d]) * 8u, full + s);
+        bulk_g2s(sb, b + T.ba, (uint32_t)(T.be - T.ba) * 8u, full + s);
+        bulk_g2s(sp, pid + T.pa, (uint32_t)(T.pe - T.pa) * 2u, full + s);
+    };
+    if (t == 0 && blockIdx.x < ntiles) issue(blockIdx.x, 0);
+    const int grp = t / G.S, i = t - grp * G.S;
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int s = it & 1;
+        if (t == 0 && tile + gridDim.x < ntiles) issue(tile + gridDim.x, s ^ 1);
+        mbar_wait(full + s, (it >> 1) & 1);
+        const TilePlan T = plan_tile(G, R, Q, tile);
+        const double* sx = reinterpret_cast<const double*>(stage0 + (size_t)s * stage_bytes);
+        const double* sb = sx + 3 * (size_t)xcap;
+        const uint16_t* sp = reinterpret_cast<const uint16_t*>(sb + bcap);
+        if (grp < Q && grp * R < T.lines) {
+            const View V = stage_view(G, T, sx, xcap, sb, sp);
+            const long long rel0 = (long long)grp * R * G.S + i;
+            const int y0 = (int)((T.T0 % G.S2) / G.S) + grp * R;
+            lines_thread<R>(G, V, rel0, T.T0 + rel0, y0, pat, ent, dp, y);
+        }
+        __syncthreads();
+    }
+}
+#endif
 
 // pure streaming floor with the same vector traffic
 __global__ void __launch_bounds__(256) k_stream(long long n, const uint16_t* __restrict__ pid, const double* __restrict__ dp,
@@ -185,19 +348,58 @@ template <int R>
 static bool host_check_one(const Grid& G, int pts) {
     std::vector<uint16_t> pid; std::vector<Pat> pat; std::vector<Ent> ent; std::vector<double> dp;
     build(G, pts, pid, pat, ent, dp);
+    pid.resize(G.n + 16, 0xFFFF);
     const long long pad = G.S2 + G.S + 1;
-    std::vector<double> xbuf(G.n + 2 * pad, 1e300), b(G.n), yref(G.n), y(G.n, -1.0);   // poison in the padding
+    std::vector<double> xbuf(G.n + 2 * pad, 1e300), b(G.n + 2, 1e300), yref(G.n), y(G.n, -1.0), y2(G.n, -1.0);   // poison in the padding
     double* x = xbuf.data() + pad;
     srand(7);
     for (long long i = 0; i < G.n; ++i) { x[i] = rand() / (double)RAND_MAX; b[i] = rand() / (double)RAND_MAX; }
     for (long long r = 0; r < G.n; ++r) yref[r] = row_reference(G, r, pid.data(), pat.data(), ent.data(), dp.data(), x, b.data());
+    // (a) global-memory form
     const int gpp = (G.n2 + R - 1) / R;
+    const View Vg = global_view(G, pid.data(), x, b.data());
     for (int z = 0; z < G.n3; ++z)
         for (int q = 0; q < gpp; ++q)
-            for (int i = 0; i < G.n1; ++i)
-                lines_thread<R>(G, i, q * R, z, pid.data(), pat.data(), ent.data(), dp.data(), x, b.data(), y.data());
-    const bool ok = memcmp(y.data(), yref.data(), G.n * sizeof(double)) == 0;
-    printf("host check %2d-point %dx%dx%d R=%d: %s\n", pts, G.n1, G.n2, G.n3, R, ok ? "bit-identical" : "MISMATCH");
+            for (int i = 0; i < G.n1; ++i) {
+                const long long row0 = (long long)z * G.S2 + (long long)q * R * G.S + i;
+                lines_thread<R>(G, Vg, row0, row0, q * R, pat.data(), ent.data(), dp.data(), y.data());
+            }
+    bool ok = memcmp(y.data(), yref.data(), G.n * sizeof(double)) == 0;
+    // (b) staged form: the stage is a host buffer filled exactly as the kernel's bulk copies fill shared memory
+    for (int Q = 1; Q <= 3; ++Q) {
+        std::fill(y2.begin(), y2.end(), -1.0);
+        int xcap, bcap, pcap;
+        stage_layout(G, R, Q, xcap, bcap, pcap);
+        const int tpp = (gpp + Q - 1) / Q;
+        const long long ntiles = (long long)G.n3 * tpp;
+        std::vector<double> sx(3 * (size_t)xcap), sb(bcap);
+        std::vector<uint16_t> sp(pcap);
+        for (long long tile = 0; tile < ntiles; ++tile) {
+            const TilePlan T = plan_tile(G, R, Q, tile);
+            std::fill(sx.begin(), sx.end(), 1e300);
+            std::fill(sb.begin(), sb.end(), 1e300);
+            std::fill(sp.begin(), sp.end(), (uint16_t)0xFFFF);
+            for (int d = 0; d < 3; ++d) {
+                if (T.xe[d] - T.xa[d] > xcap) { printf("x range exceeds the stage\n"); return false; }
+                for (long long g = T.xa[d]; g < T.xe[d]; ++g) sx[(size_t)d * xcap + (g - T.xa[d])] = x[g];   // x[n] (even rounding) is padding
+            }
+            if (T.be - T.ba > bcap || T.pe - T.pa > pcap) { printf("b / pid range exceeds the stage\n"); return false; }
+            for (long long g = T.ba; g < T.be; ++g) sb[g - T.ba] = b[g];
+            for (long long g = T.pa; g < T.pe; ++g) sp[g - T.pa] = pid[g];
+            const View V = stage_view(G, T, sx.data(), xcap, sb.data(), sp.data());
+            const int nthreads = ((Q * G.S + 31) / 32) * 32;
+            for (int t = 0; t < nthreads; ++t) {
+                const int grp = t / G.S, i = t - grp * G.S;
+                if (!(grp < Q && grp * R < T.lines)) continue;
+                const long long rel0 = (long long)grp * R * G.S + i;
+                const int y0 = (int)((T.T0 % G.S2) / G.S) + grp * R;
+                lines_thread<R>(G, V, rel0, T.T0 + rel0, y0, pat.data(), ent.data(), dp.data(), y2.data());
+            }
+        }
+        ok = ok && memcmp(y2.data(), yref.data(), G.n * sizeof(double)) == 0;
+    }
+    printf("host check %2d-point %dx%dx%d R=%d (global form, staged form Q=1..3): %s\n", pts, G.n1, G.n2, G.n3, R,
+           ok ? "bit-identical" : "MISMATCH");
     return ok;
 }
 
@@ -222,7 +424,7 @@ int main(int argc, char** argv) {
     for (int cfg = 0; cfg < 2; ++cfg) {
         const int N = cfg == 0 ? 257 : 129, pts = cfg == 0 ? 7 : 27;
         const Grid G = make_grid(N, N, N);
-        const long long n = G.n, pad = G.S2 + G.S + 1;
+        const long long n = G.n, pad = (G.S2 + G.S + 2) & ~1LL;   // even: x[0] stays 16-byte aligned
         std::vector<uint16_t> pid; std::vector<Pat> pat; std::vector<Ent> ent; std::vector<double> dp;
         build(G, pts, pid, pat, ent, dp);
         std::vector<double> hx(n), hb(n), href(n), hy(n);
@@ -243,8 +445,26 @@ int main(int argc, char** argv) {
         CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
         const int grid1 = (int)((n + 255) / 256);
         const char* names[] = {"reference 1 row/thread", "stream floor", "lines R=2 x4 CTAs/SM", "lines R=2 x8 CTAs/SM", "lines R=4 x3 CTAs/SM",
-                               "lines R=4 x6 CTAs/SM", "lines R=8 x2 CTAs/SM", "lines R=8 x4 CTAs/SM"};
-        for (int v = 0; v < 8; ++v) {
+                               "lines R=4 x6 CTAs/SM", "lines R=8 x2 CTAs/SM", "lines R=8 x4 CTAs/SM", "lines TMA R=2 Q=1", "lines TMA R=2 Q=2",
+                               "lines TMA R=4 Q=1", "lines TMA R=4 Q=2", "lines TMA R=8 Q=1"};
+        // staged form: Q groups per tile, ceil32(Q*S) threads, 2 stages; as many CTAs per SM as shared memory allows
+        auto tma_launch = [&](int R, int Q) {
+            int xcap, bcap, pcap;
+            stage_layout(G, R, Q, xcap, bcap, pcap);
+            const size_t stage = (((size_t)(3 * xcap + bcap) * 8 + (size_t)pcap * 2) + 127) / 128 * 128, smem = 128 + 2 * stage;
+            const int nt = ((Q * G.S + 31) / 32) * 32;
+            const int gpp = (G.n2 + R - 1) / R, tpp = (gpp + Q - 1) / Q;
+            const long long ntiles = (long long)G.n3 * tpp;
+            if (smem > 227 * 1024 || nt > 544) { printf("  (R=%d Q=%d skipped: %zu B shared memory, %d threads)\n", R, Q, smem, nt); return; }
+            int per = (int)std::min<size_t>((size_t)(2048 / nt), (228 * 1024) / (smem + 1024));
+            if (per < 1) per = 1;
+            const int grid = (int)std::min<long long>(ntiles, (long long)nsm * per);
+#define TL(R_) { static bool once = false; if (!once) { CK(cudaFuncSetAttribute(k_lines_tma<R_, 544>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); once = true; } \
+                 k_lines_tma<R_, 544><<<grid, nt, smem>>>(G, Q, ntiles, dpid, dpat, dent, ddp, dx, db, dy); }
+            if (R == 2) TL(2) else if (R == 4) TL(4) else TL(8)
+#undef TL
+        };
+        for (int v = 0; v < 13; ++v) {
             auto launch = [&]() {
                 switch (v) {
                     case 0: k_reference<<<grid1, 256>>>(G, dpid, dpat, dent, ddp, dx, db, dy); break;
@@ -255,6 +475,11 @@ int main(int argc, char** argv) {
                     case 5: k_lines<4><<<nsm * 6, 256>>>(G, dpid, dpat, dent, ddp, dx, db, dy); break;
                     case 6: k_lines<8><<<nsm * 2, 256>>>(G, dpid, dpat, dent, ddp, dx, db, dy); break;
                     case 7: k_lines<8><<<nsm * 4, 256>>>(G, dpid, dpat, dent, ddp, dx, db, dy); break;
+                    case 8: tma_launch(2, 1); break;
+                    case 9: tma_launch(2, 2); break;
+                    case 10: tma_launch(4, 1); break;
+                    case 11: tma_launch(4, 2); break;
+                    case 12: tma_launch(8, 1); break;
                 }
             };
             CK(cudaMemset(dy, 0, n * 8));
