@@ -99,18 +99,20 @@ __host__ __device__ inline void lines_thread(const Grid& G, const View& V, long 
         const int mz = (P.mask >> ((dz + 1) * 9)) & 0x1FF;
         if (mz == 0) continue;
         const double* xp = V.xs[dz + 1] + rel0;
-        // which columns / lines of this plane does the pattern touch?
-        const bool col_m = (mz & 0x049) != 0, col_0 = (mz & 0x092) != 0, col_p = (mz & 0x124) != 0;   // dx = -1, 0, +1
-        const bool lin_m = (mz & 0x007) != 0, lin_p = (mz & 0x1C0) != 0;                               // dy = -1, +1
+        // X[dx][l] is loaded iff some row of the group multiplies it: row j uses line l = j + 1 + dy, so dy = -1 reaches
+        // l <= R-1, dy = 0 the lines 1..R and dy = +1 l >= 2.  Every load is then an address some row's entry names,
+        // hence inside the vector - the kernel assumes nothing about the grid beyond the offsets dz*S2 + dy*S + dx.
+        const bool col_0 = (mz & 0x092) != 0;
         double X[3][R + 2];
 #pragma unroll
         for (int l = 0; l < R + 2; ++l) {
-            // dy = 0 entries use l = 1..R; dy = -1 uses 0..R-1; dy = +1 uses 2..R+1
-            const bool need = (l == 0) ? lin_m : (l == R + 1 ? lin_p : true);
             const double* q = xp + (long long)(l - 1) * G.S;
-            X[0][l] = (need && col_m) ? q[-1] : 0.0;
-            X[1][l] = (need && col_0) ? q[0] : 0.0;
-            X[2][l] = (need && col_p) ? q[1] : 0.0;
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const bool need = ((l <= R - 1) && (mz & (1 << (0 + dx + 1)))) || ((l >= 1 && l <= R) && (mz & (1 << (3 + dx + 1)))) ||
+                                  ((l >= 2) && (mz & (1 << (6 + dx + 1))));
+                X[dx + 1][l] = need ? q[dx] : 0.0;
+            }
         }
         if (dz == 0 && col_0) {
             have_c = true;

@@ -82,17 +82,19 @@ __host__ __device__ inline void restrict_thread(const Geo& g, int I, int J0, int
     for (int dz = -1; dz <= 1; ++dz) {
         const int mz = (P.mask >> ((dz + 1) * 9)) & 0x1FF;
         if (mz == 0) continue;
-        const bool col_m = (mz & 0x049) != 0, col_0 = (mz & 0x092) != 0, col_p = (mz & 0x124) != 0;
-        const bool lin_m = (mz & 0x007) != 0, lin_0 = (mz & 0x038) != 0, lin_p = (mz & 0x1C0) != 0;
         const double* xp = rf + f0 + (long long)dz * S2 - S;        // fine line 2 J0 - 1
         double X[3][2 * R + 1];                                     // l = fine line - (2 J0 - 1)
+        // coarse row j uses fine line l = 2j + 1 + dy: a value is loaded iff some row multiplies it, so every load is an
+        // address some row's entry names
 #pragma unroll
         for (int l = 0; l < 2 * R + 1; ++l) {
-            const bool need = (l & 1) ? lin_0 : (l == 0 ? lin_m : (l == 2 * R ? lin_p : (lin_m || lin_p)));
             const double* q = xp + (long long)l * S;
-            X[0][l] = (need && col_m) ? q[-1] : 0.0;
-            X[1][l] = (need && col_0) ? q[0] : 0.0;
-            X[2][l] = (need && col_p) ? q[1] : 0.0;
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const bool need = (l & 1) ? (mz & (1 << (3 + dx + 1))) != 0
+                                          : (((l <= 2 * R - 2) && (mz & (1 << (0 + dx + 1)))) || ((l >= 2) && (mz & (1 << (6 + dx + 1)))));
+                X[dx + 1][l] = need ? q[dx] : 0.0;
+            }
         }
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy) {
