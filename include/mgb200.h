@@ -219,6 +219,13 @@ int mgb200_pattern_info(mgb200_handle h, int level, int which, int64_t* out);
  * "split_test" (rows: single-GPU test hook that forces the split launch sequence of the overlap path). */
 int mgb200_set_option(mgb200_handle h, const char* key, int64_t value);
 
+/* Host-only (no GPU): box structure of a row-relative dictionary (csrc/pattern.cuh::detect_box) - every column offset
+ * is dz*S2 + dy*S + dx with dx, dy, dz in {-1,0,1}.  Input as mgb200_host_build_patterns.  info[0] = 1 if the matrix
+ * has it, info[1] = S (line length, 0: 1-D), info[2] = S2 (plane length, 0: 2-D), info[3] = patterns;
+ * mask[p] = presence bits (dz+1)*9 + (dy+1)*3 + (dx+1) of pattern p (caller-allocated, max_patterns). */
+int mgb200_host_detect_box(int64_t n_rows, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+                           int index_base, int max_patterns, int max_entries, int64_t* info, int32_t* mask);
+
 /* Host-only (no GPU): the window plan of the TMA-staged dictionary kernel for a row-relative matrix, exported for the
  * CPU test-suite.  Input as mgb200_host_build_patterns; `tile` rows per tile, elem_bytes 4, 8 or 16 (copies are rounded
  * outwards to 16 bytes).  info[0] = 1 if a plan exists (row-relative dictionary, few enough windows), info[1] = windows,

@@ -568,6 +568,27 @@ int mgb200_host_tma_plan(int64_t n_rows, const int64_t* colptr, const int64_t* r
     MGB_CATCH
 }
 
+int mgb200_host_detect_box(int64_t n_rows, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+                           int index_base, int max_patterns, int max_entries, int64_t* info, int32_t* mask) {
+    MGB_TRY
+    MGB_CHECK(colptr && rowval && nzval && info && mask, "null argument");
+    HostPatterns<double> hp;
+    const bool ok = build_patterns<double>(n_rows, colptr, rowval, nzval, index_base, false, max_patterns,
+                                           max_entries, hp);
+    info[0] = info[1] = info[2] = info[3] = 0;
+    if (ok) {
+        const BoxInfo B = detect_box<double>(hp, n_rows);
+        if (B.ok) {
+            info[0] = 1;
+            info[1] = B.S;
+            info[2] = B.S2;
+            info[3] = hp.npat();
+            for (int p = 0; p < hp.npat(); ++p) mask[p] = B.mask[p];
+        }
+    }
+    MGB_CATCH
+}
+
 int mgb200_profile_enable(mgb200_handle h, int on) {
     MGB_TRY
     MGB_BOTH(h, {

@@ -210,6 +210,101 @@ static bool build_patterns(long long n_rows, const int64_t* cp, const int64_t* r
     return build_patterns_mode<TA>(n_rows, cp, rv, nz, base, conjugate, false, max_pat, max_ent, out);
 }
 
+// Box structure of a row-relative dictionary: every column offset is dz*S2 + dy*S + dx with dx, dy, dz in {-1,0,1}
+// (S = line length, S2 = plane length of a lexicographic grid; S2 = 0: no entry leaves the plane, S = 0: none leaves
+// the line).  A pattern is then a 27-bit presence mask, bit (dz+1)*9 + (dy+1)*3 + (dx+1), and its entries in stored
+// (ascending column) order are its set bits in ascending order.  This is what a line-blocked kernel needs
+// (tools/microbench_lines.cu); nothing else about the grid is assumed.
+struct BoxInfo {
+    bool ok = false;
+    int S = 0, S2 = 0;
+    std::vector<int> mask;   // per pattern
+};
+static inline bool box_decompose(long long d, int S, int S2, int& dx, int& dy, int& dz) {
+    dz = 0;
+    if (S2 > 0) {
+        dz = (2 * d > S2) ? 1 : ((2 * d < -(long long)S2) ? -1 : 0);
+        d -= (long long)dz * S2;
+    }
+    dy = 0;
+    if (S > 0) {
+        dy = (2 * d > S) ? 1 : ((2 * d < -(long long)S) ? -1 : 0);
+        d -= (long long)dy * S;
+    }
+    if (d < -1 || d > 1) return false;
+    dx = (int)d;
+    return true;
+}
+template <typename TA>
+static BoxInfo detect_box(const HostPatterns<TA>& H, long long n_rows) {
+    BoxInfo B;
+    if (!H.ok || !H.rowrel || H.delta.empty()) return B;
+    std::vector<long long> pos;
+    for (int d : H.delta)
+        if (d != 0) pos.push_back(d < 0 ? -(long long)d : d);
+    std::sort(pos.begin(), pos.end());
+    pos.erase(std::unique(pos.begin(), pos.end()), pos.end());
+    auto valid = [&](int S, int S2) {
+        if (S > 0 && S < 3) return false;
+        if (S2 > 0 && (S == 0 || S2 < 3 * S)) return false;
+        for (int d : H.delta) {
+            int dx, dy, dz;
+            if (!box_decompose(d, S, S2, dx, dy, dz)) return false;
+            if ((long long)dz * S2 + (long long)dy * S + dx != d) return false;
+        }
+        return true;
+    };
+    auto finish = [&](int S, int S2) {
+        B.S = S;
+        B.S2 = S2;
+        B.mask.assign(H.npat(), 0);
+        for (int p = 0; p < H.npat(); ++p) {
+            int last = -1;
+            for (int k = H.pat_off[p]; k < H.pat_off[p + 1]; ++k) {
+                int dx, dy, dz;
+                box_decompose(H.delta[k], S, S2, dx, dy, dz);
+                const int bit = (dz + 1) * 9 + (dy + 1) * 3 + (dx + 1);
+                if (bit <= last) return;        // stored order is not (dz,dy,dx) order, or a duplicate offset
+                last = bit;
+                B.mask[p] |= 1 << bit;
+            }
+        }
+        B.ok = true;
+    };
+    // candidates: the smallest offset beyond 1 is S-1, S or S+1; the smallest beyond S+1 is S2 + dy*S + dx
+    std::vector<long long> big;
+    for (long long d : pos)
+        if (d > 1) big.push_back(d);
+    if (big.empty()) {            // offsets within {-1, 0, 1}: a 1-D stencil
+        if (valid(0, 0)) finish(0, 0);
+        return B;
+    }
+    int best_S = -1, best_S2 = -1, best_score = -1;
+    for (int a = -1; a <= 1; ++a) {
+        const long long S = big[0] + a;
+        if (S < 3 || S > 0x3fffffff) continue;
+        std::vector<long long> bigger;
+        for (long long d : big)
+            if (d > S + 1) bigger.push_back(d);
+        std::vector<long long> cand2;
+        if (bigger.empty()) cand2.push_back(0);
+        else
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) cand2.push_back(bigger[0] - dy * S - dx);
+        for (long long S2 : cand2) {
+            if (S2 < 0 || S2 > 0x3fffffff) continue;
+            if (!valid((int)S, (int)S2)) continue;
+            // several decompositions can fit a sparse offset set: prefer the one that tiles the matrix
+            int score = 0;
+            if (S2 > 0 && S2 % S == 0) score += 2;
+            if (n_rows % (S2 > 0 ? S2 : S) == 0) score += 1;
+            if (score > best_score) { best_score = score; best_S = (int)S; best_S2 = (int)S2; }
+        }
+    }
+    if (best_score >= 0) finish(best_S, best_S2);
+    return B;
+}
+
 // device side ---------------------------------------------------------------------------------
 // Plan of the TMA-staged variant of the kernel (pat_tma_kernel): the column offsets of the whole dictionary are
 // clustered into windows [lo, hi]; a CTA that owns a tile of `tile` consecutive rows needs

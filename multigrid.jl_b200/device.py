@@ -426,6 +426,23 @@ def host_tma_plan(M, tile=1024, elem_bytes=8, max_patterns=4096, max_entries=1 <
                 centre=int(info[3]), delta=de[:nent].copy(), soff=so[:nent].copy())
 
 
+def host_detect_box(M, max_patterns=4096, max_entries=1 << 16):
+    """Host-only: box structure of the row-relative dictionary of ``M`` (csrc/pattern.cuh::detect_box): every
+    column offset is dz*S2 + dy*S + dx with dx, dy, dz in {-1,0,1}.  None, or dict(S, S2, masks)."""
+    M = sp.csc_matrix(M)
+    if not M.has_sorted_indices:
+        M.sort_indices()
+    n = M.shape[1]
+    cp, rv, nz = _i64(M.indptr), _i64(M.indices), np.ascontiguousarray(M.data, dtype=np.float64)
+    info = np.zeros(4, dtype=np.int64)
+    mask = np.zeros(max_patterns, dtype=np.int32)
+    _check(lib().mgb200_host_detect_box(ctypes.c_int64(n), _ptr(cp), _ptr(rv), _ptr(nz), 0, int(max_patterns),
+                                        int(max_entries), _ptr(info), _ptr(mask)))
+    if not info[0]:
+        return None
+    return dict(S=int(info[1]), S2=int(info[2]), masks=mask[:int(info[3])].copy())
+
+
 def uploadHierarchy(param, device: int = 0):
     """Upload (or reuse) the device copy of ``param``'s hierarchy."""
     if len(param.As) == 0:

@@ -125,6 +125,44 @@ def test_tma_plan_absent_for_transfer_operators():
     assert device.host_tma_plan(p.As[0], tile=64) is not None
 
 
+@pytest.mark.parametrize("n,S,S2", [([24, 20, 12], 25, 525), ([32, 32], 33, 0), ([18, 40, 10], 19, 779)])
+def test_box_structure_detected(n, S, S2):
+    """The line length and the plane length come out of the dictionary offsets alone (7- / 5-point fine level, 27- /
+    9-point Galerkin level); a pattern's mask has one bit per stored entry."""
+    from multigrid_jl_b200 import device
+    A, AT, M, p, b = _cpu_problem(n, 2)
+    for l, (s1, s2) in enumerate([(S, S2), (n[0] // 2 + 1, (n[0] // 2 + 1) * (n[1] // 2 + 1) if len(n) == 3 else 0)]):
+        mat = sp.csc_matrix(p.As[l])
+        box = device.host_detect_box(mat)
+        pat = device.host_build_patterns(mat)
+        assert box is not None and (box["S"], box["S2"]) == (s1, s2), (l, box)
+        lens = np.diff(pat["pat_off"])
+        assert [bin(m).count("1") for m in box["masks"]] == list(lens)
+        # the centre bit (dz = dy = dx = 0) is set in every pattern of these operators
+        assert all(m & (1 << 13) for m in box["masks"])
+        # interior pattern: all 27 (9 in 2-D) neighbours on the Galerkin level, 7 (5) on the fine level
+        full = max(bin(m).count("1") for m in box["masks"])
+        assert full == ((27 if len(n) == 3 else 9) if l == 1 else (7 if len(n) == 3 else 5))
+
+
+def test_box_structure_rejected():
+    from multigrid_jl_b200 import device
+    A, AT, M, p, b = _cpu_problem([16, 16], 3)
+    assert device.host_detect_box(p.Ps[0]) is None            # not row-relative
+    n = 400
+    # a pentadiagonal matrix IS a box stencil for lines of 3 (+-2 = +-3 -+ 1): the structure is about offsets only
+    T = sp.diags([np.ones(n - 2), np.ones(n - 1), 4 * np.ones(n), np.ones(n - 1), np.ones(n - 2)], [-2, -1, 0, 1, 2], format="csc")
+    box = device.host_detect_box(T)
+    assert box is not None and (box["S"], box["S2"]) == (3, 0)
+    # balanced base-S digits represent many offset sets; {0, +-1, +-3, +-6, +-9, +-30} fits no (S, S2)
+    offs = [-30, -9, -6, -3, -1, 0, 1, 3, 6, 9, 30]
+    T = sp.diags([np.ones(n - abs(o)) * (4.0 if o == 0 else 1.0) for o in offs], offs, format="csc")
+    assert device.host_detect_box(T) is None
+    T3 = sp.diags([np.ones(n - 1), 4 * np.ones(n), np.ones(n - 1)], [-1, 0, 1], format="csc")
+    box = device.host_detect_box(T3)
+    assert box is not None and (box["S"], box["S2"]) == (0, 0)
+
+
 def _cpu_problem(n, levels):
     import multigrid_jl_b200 as mg
     dom = [0.0, 1.0] * len(n)
