@@ -226,6 +226,17 @@ int mgb200_set_option(mgb200_handle h, const char* key, int64_t value);
 int mgb200_host_detect_box(int64_t n_rows, const int64_t* colptr, const int64_t* rowval, const double* nzval,
                            int index_base, int max_patterns, int max_entries, int64_t* info, int32_t* mask);
 
+/* Host-only (no GPU): runs the per-thread function of the line-blocked dictionary kernel (csrc/pattern.cuh::
+ * pat_lines_thread, __host__ __device__) on the CPU for every thread of a launch - the exact code the GPU executes -
+ * for a Float64 matrix given as in mgb200_host_build_patterns.  mode: 0 y = A x, 2 y = b - A x, 3 y = x + d.*(b - A x);
+ * rows_per_thread R in {2, 4}, or 0 for the one-row-per-thread dictionary walk (the reference the kernel must match
+ * bit for bit); fold_d != 0: d is read per pattern (first row that carries the pattern).  info[0] = 1 if the matrix has
+ * the box structure the kernel needs (y is then written), info[1] = S, info[2] = S2, info[3] = groups that took the
+ * row-by-row path. */
+int mgb200_host_lines_apply(int64_t n_rows, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+                            int index_base, int mode, int rows_per_thread, int fold_d, const double* x, const double* b,
+                            const double* d, double* y, int64_t* info);
+
 /* Host-only (no GPU): the window plan of the TMA-staged dictionary kernel for a row-relative matrix, exported for the
  * CPU test-suite.  Input as mgb200_host_build_patterns; `tile` rows per tile, elem_bytes 4, 8 or 16 (copies are rounded
  * outwards to 16 bytes).  info[0] = 1 if a plan exists (row-relative dictionary, few enough windows), info[1] = windows,

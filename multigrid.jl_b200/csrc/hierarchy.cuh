@@ -125,6 +125,8 @@ struct Context {
     int use_patterns = 1;          // 0: always stream CSR (MGB200_PATTERNS / mgb200_set_option)
     int use_graphs = 1;            // 0: never replay cycles from CUDA graphs
     int use_tma = 1;               // 0: never use the TMA-staged dictionary kernel (MGB200_TMA)
+    int lines = 0;                 // > 0: line-blocked dictionary kernel with that many rows per thread (2 or 4); off by default
+    int lines_min_rows = 50000;
     int tma_min_rows = 200000;     // smaller matrices keep the one-pass kernel (too few tiles per SM)
     int split_test = 0;            // > 0: every dictionary pass runs as interior + both ends (test hook)
     int use_overlap = 0;           // multi-GPU: halo exchange beside the interior rows (MGB200_OVERLAP=1; measured
@@ -156,6 +158,8 @@ struct Context {
         use_graphs = env_int("MGB200_GRAPHS", 1);
         use_tma = env_int("MGB200_TMA", 1);
         tma_min_rows = env_int("MGB200_TMA_MIN_ROWS", 200000);
+        lines = env_int("MGB200_LINES", 0);
+        lines_min_rows = env_int("MGB200_LINES_MIN_ROWS", 50000);
         use_overlap = env_int("MGB200_OVERLAP", 0);
         split_test = env_int("MGB200_SPLIT_TEST", 0);
         int prio_lo = 0, prio_hi = 0;

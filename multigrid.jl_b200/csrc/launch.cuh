@@ -146,6 +146,35 @@ static bool launch_pattern_tma(Context& ctx, const Csr<TA>& M, int mode, const T
     return true;
 }
 
+// line-blocked variant (pat_lines_kernel): box-structured square operators, SPMV / RESID / SWEEP, whole matrix,
+// no fused put; off unless the option "lines" (MGB200_LINES) holds the rows per thread (2 or 4)
+template <typename TA, typename TV>
+static bool launch_pattern_lines(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d,
+                                 const TV* dpat, TV* y) {
+    return false;
+}
+template <typename TV>
+static bool launch_pattern_lines(Context& ctx, const Csr<TV>& M, int mode, const TV* x, const TV* b, const TV* d,
+                                 const TV* dpat, TV* y) {
+    const PatDict<TV>& D = M.pat;
+    const int R = ctx.lines;
+    if ((R != 2 && R != 4) || !D.box_ok || !D.rowrel || mode == MODE_ADD || x == y) return false;
+    if (M.n_rows < ctx.lines_min_rows) return false;
+    const long long S = D.S, nlines = (M.n_rows + S - 1) / S, total = ((nlines + R - 1) / R) * S;
+    const int grid = (int)std::min<long long>((total + 255) / 256, (long long)ctx.sm_count * (R == 2 ? 6 : 3));
+#define MGB_LL(MODE, DP, RR) \
+    pat_lines_kernel<TV, TV, MODE, DP, RR><<<grid, 256, 0, ctx.stream>>>(S, (long long)D.S2, (long long)M.n_rows, total, D.pid, D.pat_off, D.ent, D.box_mask, dpat, x, b, d, y)
+#define MGB_LR(MODE, DP) { if (R == 2) MGB_LL(MODE, DP, 2); else MGB_LL(MODE, DP, 4); }
+    if (mode == MODE_SPMV) MGB_LR(MODE_SPMV, false)
+    else if (mode == MODE_RESID) MGB_LR(MODE_RESID, false)
+    else if (dpat) MGB_LR(MODE_SWEEP, true)
+    else MGB_LR(MODE_SWEEP, false)
+#undef MGB_LR
+#undef MGB_LL
+    MGB_LAUNCH_CHECK();
+    return true;
+}
+
 // one-pass dictionary kernel over the rows [rA, rA + nA) and [rB, rB + nB)
 template <typename TA, typename TV>
 static void launch_pattern_rows(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d,
@@ -179,6 +208,7 @@ static void launch_pattern_rows(Context& ctx, const Csr<TA>& M, int mode, const 
 template <typename TA, typename TV>
 static void launch_pattern_mode(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d,
                                 const TV* dpat, TV* y, const PutPlan& pp = no_put()) {
+    if (!pp.on && ctx.lines > 0 && launch_pattern_lines(ctx, M, mode, x, b, d, dpat, y)) return;
     if (M.pat.rowrel && launch_pattern_tma<TA, TV>(ctx, M, mode, x, b, d, dpat, y, 0, -1, 0, pp)) return;
     launch_pattern_rows<TA, TV>(ctx, M, mode, x, b, d, dpat, y, 0, M.n_rows, 0, 0, pp);
 }

@@ -165,6 +165,35 @@ static void host_tma_plan_impl(const HostPatterns<double>& hp, int tile, int64_t
     }
 }
 
+template <int MODE, bool DPAT>
+static long long host_lines_run(const HostPatterns<double>& hp, const BoxInfo& B, long long n_rows, int R,
+                                const std::vector<PatEntry<double>>& ent, const double* dpat, const double* x,
+                                const double* b, const double* d, double* y) {
+    const long long S = B.S, S2 = B.S2;
+    long long slow = 0;
+    if (R == 0) {
+        for (long long row = 0; row < n_rows; ++row)
+            y[row] = pat_row_walk<double, double, MODE, DPAT>(row, hp.pid.data(), hp.pat_off.data(), ent.data(), dpat, x, b, d);
+        return 0;
+    }
+    const long long nlines = (n_rows + S - 1) / S, groups = (nlines + R - 1) / R;
+    for (long long q = 0; q < groups; ++q)
+        for (long long i = 0; i < S; ++i) {
+            const long long row0 = q * R * S + i;
+            if (row0 >= n_rows) continue;
+            bool same = row0 + (long long)(R - 1) * S < n_rows;
+            for (int j = 1; j < R && same; ++j) same = hp.pid[row0 + j * S] == hp.pid[row0];
+            slow += same ? 0 : 1;
+            if (R == 2)
+                pat_lines_thread<double, double, MODE, DPAT, 2>(S, S2, n_rows, q, i, hp.pid.data(), hp.pat_off.data(), ent.data(),
+                                                                B.mask.data(), dpat, x, b, d, y);
+            else
+                pat_lines_thread<double, double, MODE, DPAT, 4>(S, S2, n_rows, q, i, hp.pid.data(), hp.pat_off.data(), ent.data(),
+                                                                B.mask.data(), dpat, x, b, d, y);
+        }
+    return slow;
+}
+
 extern "C" {
 
 const char* mgb200_last_error(void) { return g_last_error.c_str(); }
@@ -517,6 +546,8 @@ int mgb200_set_option(mgb200_handle h, const char* key, int64_t value) {
         else if (k == "smem_budget") H->ctx.smem_budget = (int)value;
         else if (k == "tma") H->ctx.use_tma = (int)value;
         else if (k == "tma_min_rows") H->ctx.tma_min_rows = (int)value;
+        else if (k == "lines") H->ctx.lines = (int)value;
+        else if (k == "lines_min_rows") H->ctx.lines_min_rows = (int)value;
         else if (k == "split_test") H->ctx.split_test = (int)value;
         else if (k == "overlap") H->ctx.use_overlap = (int)value;
         else if (k == "fused_put") H->use_fused_put = (int)value;
@@ -586,6 +617,41 @@ int mgb200_host_detect_box(int64_t n_rows, const int64_t* colptr, const int64_t*
             for (int p = 0; p < hp.npat(); ++p) mask[p] = B.mask[p];
         }
     }
+    MGB_CATCH
+}
+
+int mgb200_host_lines_apply(int64_t n_rows, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+                            int index_base, int mode, int rows_per_thread, int fold_d, const double* x, const double* b,
+                            const double* d, double* y, int64_t* info) {
+    MGB_TRY
+    MGB_CHECK(colptr && rowval && nzval && x && y && info, "null argument");
+    MGB_CHECK(mode == 0 || mode == 2 || mode == 3, "mode must be 0, 2 or 3");
+    MGB_CHECK(rows_per_thread == 0 || rows_per_thread == 2 || rows_per_thread == 4, "rows_per_thread must be 0, 2 or 4");
+    MGB_CHECK(mode == 0 || b, "b required");
+    MGB_CHECK(mode != 3 || d, "d required");
+    info[0] = info[1] = info[2] = info[3] = 0;
+    HostPatterns<double> hp;
+    if (!build_patterns<double>(n_rows, colptr, rowval, nzval, index_base, false, PAT_MAX_PATTERNS, PAT_MAX_ENTRIES, hp)) return 0;
+    const BoxInfo B = detect_box<double>(hp, n_rows);
+    if (!B.ok || B.S < 3) return 0;
+    std::vector<PatEntry<double>> ent(hp.delta.size());
+    for (size_t k = 0; k < ent.size(); ++k) {
+        ent[k].v = hp.val[k];
+        ent[k].delta = hp.delta[k];
+    }
+    std::vector<double> dpat(hp.npat(), 0.0);
+    if (mode == 3 && fold_d)
+        for (int p = 0; p < hp.npat(); ++p) dpat[p] = d[hp.rep_row[p]];
+    long long slow = 0;
+    const bool dp = (mode == 3 && fold_d);
+    if (mode == 0) slow = host_lines_run<0, false>(hp, B, n_rows, rows_per_thread, ent, nullptr, x, b, d, y);
+    else if (mode == 2) slow = host_lines_run<2, false>(hp, B, n_rows, rows_per_thread, ent, nullptr, x, b, d, y);
+    else if (dp) slow = host_lines_run<3, true>(hp, B, n_rows, rows_per_thread, ent, dpat.data(), x, b, d, y);
+    else slow = host_lines_run<3, false>(hp, B, n_rows, rows_per_thread, ent, nullptr, x, b, d, y);
+    info[0] = 1;
+    info[1] = B.S;
+    info[2] = B.S2;
+    info[3] = slow;
     MGB_CATCH
 }
 

@@ -338,7 +338,15 @@ struct PatDict {
     int* pat_off = nullptr;
     PatEntry<TA>* ent = nullptr;
     std::vector<uint16_t> host_pid;  // kept for the d-folding check at upload
+    // box structure (detect_box): offsets are dz*S2 + dy*S + dx; box_mask[p] = presence bits of pattern p (device)
+    bool box_ok = false;
+    int S = 0, S2 = 0;
+    int* box_mask = nullptr;
     void release() {
+        if (box_mask) cudaFree(box_mask);
+        box_mask = nullptr;
+        box_ok = false;
+        S = S2 = 0;
         if (pid) cudaFree(pid);
         if (c0) cudaFree(c0);
         if (pat_off) cudaFree(pat_off);
@@ -444,6 +452,16 @@ static void upload_patterns(PatDict<TA>& D, const HostPatterns<TA>& H, long long
     MGB_CUDA(cudaMemcpy(D.ent, e.data(), e.size() * sizeof(PatEntry<TA>), cudaMemcpyHostToDevice));
     D.host_pid = H.pid;
     D.present = true;
+    {
+        const BoxInfo B = detect_box<TA>(H, n_rows);
+        if (B.ok && B.S >= 3) {   // the line-blocked kernel (pat_lines_kernel) needs lines
+            MGB_CUDA(cudaMalloc(&D.box_mask, D.npat * sizeof(int)));
+            MGB_CUDA(cudaMemcpy(D.box_mask, B.mask.data(), D.npat * sizeof(int), cudaMemcpyHostToDevice));
+            D.box_ok = true;
+            D.S = B.S;
+            D.S2 = B.S2;
+        }
+    }
     // ---- TMA variant ----
     std::vector<int> soff;
     int max_len = 0;
@@ -534,6 +552,145 @@ pat_kernel(const __grid_constant__ PutPlan pp, int rA, int nA, int rB, int nB, c
     }
     y[row] = out;
     if (pp.on) ll_put_edge<TV>(pp, row, out);
+}
+
+// ---- line-blocked variant (off by default: option "lines" / MGB200_LINES = R) --------------------------------------
+// For dictionaries with box structure (detect_box): a thread owns R rows that are S apart - the same column of R
+// consecutive lines of a lexicographic grid; lanes are consecutive columns, so every load of a warp is contiguous.  Per
+// plane dz of the stencil it loads x[dx][l], l = -1..R, once for the 9 R products of that plane and every dictionary
+// value once for R rows; the offsets are not read at all (a pattern is a presence mask).  Stored order is (dz,dy,dx)
+// order, so every row still accumulates its products in stored order: bit-identical to pat_kernel.  A value is loaded
+// only if some row of the group multiplies it, i.e. only addresses that entries name: nothing is assumed about the
+// grid beyond the offsets.  Groups whose R rows do not share one pattern walk the dictionary row by row.
+// The per-thread function is __host__ __device__: mgb200_host_lines_apply runs exactly this code on the CPU
+// (tests/test_patterns.py).  First measurements are due in the next round (tools/microbench_lines.cu).
+template <typename T>
+__host__ __device__ __forceinline__ T ld_ro(const T* p) {
+#ifdef __CUDA_ARCH__
+    return ldg_(p);
+#else
+    return *p;
+#endif
+}
+__host__ __device__ __forceinline__ int ld_pid(const uint16_t* p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(reinterpret_cast<const unsigned short*>(p));
+#else
+    return *p;
+#endif
+}
+template <int MODE, typename TV>
+__host__ __device__ __forceinline__ TV pat_epilogue(TV acc, TV xval, TV bval, TV dval) {
+    if (MODE == 0) return acc;
+    if (MODE == 2) return bval - acc;
+    const TV r = bval - acc;
+    return xval + dval * r;
+}
+// one row, dictionary walked entry by entry (what pat_kernel<..., ROWREL = true> computes)
+template <typename TA, typename TV, int MODE, bool DPAT>
+__host__ __device__ inline TV pat_row_walk(long long row, const uint16_t* pid, const int* pat_off, const PatEntry<TA>* ent,
+                                           const TV* dpat, const TV* x, const TV* b, const TV* d) {
+    const int p = ld_pid(pid + row);
+    const int k0 = ld_ro(pat_off + p), k1 = ld_ro(pat_off + p + 1);
+    TV acc = VT<TV>::zero();
+    for (int k = k0; k < k1; ++k) acc = acc + ent[k].v * ld_ro(x + (row + ent[k].delta));
+    TV bval = VT<TV>::zero(), dval = VT<TV>::zero(), xval = VT<TV>::zero();
+    if (MODE == 2 || MODE == 3) bval = b[row];
+    if (MODE == 3) {
+        dval = DPAT ? ld_ro(dpat + p) : d[row];
+        xval = x[row];
+    }
+    return pat_epilogue<MODE, TV>(acc, xval, bval, dval);
+}
+template <typename TA, typename TV, int MODE, bool DPAT, int R>
+__host__ __device__ inline void pat_lines_thread(long long S, long long S2, long long n_rows, long long q, long long i,
+                                                 const uint16_t* pid, const int* pat_off, const PatEntry<TA>* ent,
+                                                 const int* mask, const TV* dpat, const TV* x, const TV* b, const TV* d,
+                                                 TV* y) {
+    const long long row0 = q * R * S + i;
+    if (row0 >= n_rows) return;
+    int nr = R;
+    while (row0 + (long long)(nr - 1) * S >= n_rows) --nr;        // rows of the group that exist (nr >= 1)
+    const int p0 = ld_pid(pid + row0);
+    bool same = (nr == R);
+#pragma unroll
+    for (int j = 1; j < R; ++j)
+        if (j < nr) same = same && (ld_pid(pid + row0 + j * S) == p0);
+    if (!same) {
+        for (int j = 0; j < nr; ++j) {
+            const long long row = row0 + j * S;
+            y[row] = pat_row_walk<TA, TV, MODE, DPAT>(row, pid, pat_off, ent, dpat, x, b, d);
+        }
+        return;
+    }
+    const int m = ld_ro(mask + p0);
+    const PatEntry<TA>* e = ent + ld_ro(pat_off + p0);
+    TV acc[R], xc[R];
+    bool have_c = false;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        acc[j] = VT<TV>::zero();
+        xc[j] = VT<TV>::zero();
+    }
+#pragma unroll
+    for (int dz = -1; dz <= 1; ++dz) {
+        const int mz = (m >> ((dz + 1) * 9)) & 0x1FF;
+        if (mz == 0) continue;
+        const TV* xp = x + (row0 + dz * S2);
+        TV X[3][R + 2];
+#pragma unroll
+        for (int l = 0; l < R + 2; ++l) {
+            const TV* ql = xp + (l - 1) * S;
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                // row j multiplies line l = j + 1 + dy: dy = -1 reaches l <= R-1, dy = 0 the lines 1..R, dy = +1 l >= 2
+                const bool need = ((l <= R - 1) && (mz & (1 << (0 + dx + 1)))) || ((l >= 1 && l <= R) && (mz & (1 << (3 + dx + 1)))) ||
+                                  ((l >= 2) && (mz & (1 << (6 + dx + 1))));
+                X[dx + 1][l] = need ? ld_ro(ql + dx) : VT<TV>::zero();
+            }
+        }
+        if (MODE == 3 && dz == 0 && (mz & (1 << 4))) {
+            have_c = true;
+#pragma unroll
+            for (int j = 0; j < R; ++j) xc[j] = X[1][j + 1];
+        }
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                if (mz & (1 << ((dy + 1) * 3 + (dx + 1)))) {
+                    const TA v = e->v;
+                    ++e;
+#pragma unroll
+                    for (int j = 0; j < R; ++j) acc[j] = acc[j] + v * X[dx + 1][j + 1 + dy];
+                }
+            }
+        }
+    }
+    const TV dp = (MODE == 3 && DPAT) ? ld_ro(dpat + p0) : VT<TV>::zero();
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        const long long row = row0 + j * S;
+        TV bval = VT<TV>::zero(), dval = dp, xval = xc[j];
+        if (MODE == 2 || MODE == 3) bval = b[row];
+        if (MODE == 3) {
+            if (!DPAT) dval = d[row];
+            if (!have_c) xval = x[row];
+        }
+        y[row] = pat_epilogue<MODE, TV>(acc[j], xval, bval, dval);
+    }
+}
+// persistent grid-stride over the flattened (group, column) index
+template <typename TA, typename TV, int MODE, bool DPAT, int R>
+__global__ void __launch_bounds__(256)
+pat_lines_kernel(long long S, long long S2, long long n_rows, long long total, const uint16_t* __restrict__ pid,
+                 const int* __restrict__ pat_off, const PatEntry<TA>* __restrict__ ent, const int* __restrict__ mask,
+                 const TV* __restrict__ dpat, const TV* __restrict__ x, const TV* __restrict__ b, const TV* __restrict__ d,
+                 TV* __restrict__ y) {
+    for (long long f = blockIdx.x * (long long)blockDim.x + threadIdx.x; f < total; f += (long long)gridDim.x * blockDim.x) {
+        const long long q = f / S;
+        pat_lines_thread<TA, TV, MODE, DPAT, R>(S, S2, n_rows, q, f - q * S, pid, pat_off, ent, mask, dpat, x, b, d, y);
+    }
 }
 
 // ---- TMA-staged variant ----------------------------------------------------------------------------------

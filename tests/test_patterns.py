@@ -163,6 +163,35 @@ def test_box_structure_rejected():
     assert box is not None and (box["S"], box["S2"]) == (0, 0)
 
 
+@pytest.mark.parametrize("n", [[24, 20, 12], [32, 32], [18, 40, 10], [22, 10, 14]])
+@pytest.mark.parametrize("R", [2, 4])
+def test_line_blocked_kernel_code_on_the_cpu(n, R):
+    """csrc/pattern.cuh::pat_lines_thread is __host__ __device__: run on the CPU for every thread of a launch it must
+    reproduce the one-row-per-thread dictionary walk bit for bit in all three modes (fine 7- / 5-point level and
+    27- / 9-point Galerkin level; line counts R does and does not divide), and that walk must agree with scipy."""
+    from multigrid_jl_b200 import device
+    A, AT, M, p, b0 = _cpu_problem(n, 2)
+    rng = np.random.default_rng(11)
+    for l in range(2):
+        mat = sp.csc_matrix(p.As[l])
+        N = mat.shape[0]
+        x, b = rng.standard_normal(N), rng.standard_normal(N)
+        d = np.ascontiguousarray(p.relaxPrecs[l]) if l < len(p.relaxPrecs) else 0.8 / mat.diagonal()
+        Aop = sp.csr_matrix(mat.T)
+        for mode, fold in ((0, False), (2, False), (3, False), (3, True)):
+            ref = device.host_lines_apply(mat, mode, 0, x, b, d, fold)
+            got = device.host_lines_apply(mat, mode, R, x, b, d, fold)
+            assert ref is not None and got is not None
+            assert np.array_equal(ref[0].view(np.int64), got[0].view(np.int64)), (l, mode, fold)
+            # the blocked path is really taken on the fine level (a 6-line coarse plane may have no R = 4 group with
+            # one pattern: everything then goes row by row, still bit-identical)
+            lines = -(-N // got[1]["S"])
+            if l == 0:
+                assert got[1]["slow_groups"] < 0.7 * (-(-lines // R)) * got[1]["S"]
+            want = {0: Aop @ x, 2: b - Aop @ x, 3: x + d * (b - Aop @ x)}[mode]
+            np.testing.assert_allclose(ref[0], want, rtol=1e-12, atol=1e-12)
+
+
 def _cpu_problem(n, levels):
     import multigrid_jl_b200 as mg
     dom = [0.0, 1.0] * len(n)
@@ -267,3 +296,19 @@ def test_split_launches_bit_identical(kind, n, cycle, tma):
     for rows in ("7", "1500"):
         x1, r1, it1, _ = _solve(kind, n, 3, cycle, dict(base, MGB200_SPLIT_TEST=rows))
         assert it0 == it1 and np.array_equal(r0, r1) and np.array_equal(x0, x1)
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="pat_lines_kernel (off by default) was written after the GPU budget of round 1 was "
+                                        "spent: its per-thread code is bit-identical on the CPU "
+                                        "(test_line_blocked_kernel_code_on_the_cpu); first GPU run pending")
+@pytest.mark.parametrize("kind,n,cycle", [("poisson", [40, 36, 28], 'V'), ("helmholtz", [33, 31, 17], 'W'),
+                                          ("poisson", [300, 200], 'F')])
+@pytest.mark.parametrize("R", ["2", "4"])
+def test_line_blocked_kernel_bit_identical(kind, n, cycle, R):
+    """Option "lines" (MGB200_LINES): the line-blocked dictionary kernel on every box-structured level instead of the
+    one-pass / TMA-staged kernels: results must not change by a bit (Float64 and ComplexF64, 2-D and 3-D)."""
+    base = {"MGB200_PATTERNS": "1", "MGB200_GRAPHS": "1", "MGB200_TMA": "1", "MGB200_TMA_MIN_ROWS": "0"}
+    x0, r0, it0, _ = _solve(kind, n, 3, cycle, dict(base, MGB200_LINES="0"))
+    x1, r1, it1, _ = _solve(kind, n, 3, cycle, dict(base, MGB200_LINES=R, MGB200_LINES_MIN_ROWS="0"))
+    assert it0 == it1 and np.array_equal(r0, r1) and np.array_equal(x0, x1)
