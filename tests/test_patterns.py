@@ -299,9 +299,11 @@ def test_split_launches_bit_identical(kind, n, cycle, tma):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="pat_lines_kernel (off by default) was written after the GPU budget of round 1 was "
-                                        "spent: its per-thread code is bit-identical on the CPU "
-                                        "(test_line_blocked_kernel_code_on_the_cpu); first GPU run pending")
+@pytest.mark.skipif(os.environ.get("MGB200_TEST_LINES", "0") != "1",
+                    reason="pat_lines_kernel (off by default) was written after the GPU budget of round 1 was spent: its "
+                           "per-thread code is bit-identical on the CPU (test_line_blocked_kernel_code_on_the_cpu); set "
+                           "MGB200_TEST_LINES=1 for its first GPU run (a faulting kernel would poison the CUDA context "
+                           "of the tests that follow, so it does not run unasked)")
 @pytest.mark.parametrize("kind,n,cycle", [("poisson", [40, 36, 28], 'V'), ("helmholtz", [33, 31, 17], 'W'),
                                           ("poisson", [300, 200], 'F')])
 @pytest.mark.parametrize("R", ["2", "4"])

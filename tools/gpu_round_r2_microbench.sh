@@ -8,3 +8,10 @@ for t in microbench_lines microbench_transfer; do
   timeout 120 gpurun_out/$t > gpurun_out/$t.log 2>&1; echo "$t exit $?"
   cat gpurun_out/$t.log
 done
+# then the library form of the line-blocked kernel: bit-identity on the GPU, and the bench with it
+MGB200_TEST_LINES=1 timeout 300 python -m pytest tests/test_patterns.py -m gpu -q -k line_blocked 2>&1 | tail -3
+for R in 2 4; do
+  MGB200_LINES=$R timeout 300 python bench.py --no-cpu > gpurun_out/bench_n1_lines$R.json 2> gpurun_out/bench_n1_lines$R.log; echo "bench lines=$R exit $?"
+  cut -c1-200 gpurun_out/bench_n1_lines$R.json
+  grep "per-kernel" gpurun_out/bench_n1_lines$R.log | cut -c1-900
+done
