@@ -25,8 +25,10 @@ def _wide(dt):
 
 class OracleMG32:
     def __init__(self, param):
+        # written for the single-precision types; it is type-generic, and tests/test_oracle.py also runs it in double
+        # precision as an independent (scipy / numpy) cross-check of oracle/cycle.py + mg_kernels.c
         self.VAL = np.dtype(param.VAL)
-        assert self.VAL in (np.dtype(np.float32), np.dtype(np.complex64))
+        assert self.VAL in (np.dtype(np.float32), np.dtype(np.complex64), np.dtype(np.float64), np.dtype(np.complex128))
         self.relaxPre, self.relaxPost = param.relaxPre, param.relaxPost
         self.cycleType = param.cycleType
         self.maxOuterIter, self.relativeTol = param.maxOuterIter, param.relativeTol

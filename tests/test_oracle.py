@@ -236,3 +236,19 @@ def test_block_krylov_solves_all_columns(kind, nrhs):
                                                 M1=Mfun, x=np.zeros_like(b))
     assert flag in (0, -3) and np.linalg.norm(b - Aw @ X) <= 1.5e-9 * nb
     assert abs(res[-1] - np.linalg.norm(b - Aw @ X) / nb) <= 1e-10
+
+
+@pytest.mark.parametrize("kind,n,levels,cycle,relax", [("poisson", [32, 32], 3, 'V', "Jac"), ("poisson", [12, 12, 12], 3, 'W', "Jac"),
+                                                       ("diffusion", [24, 24], 3, 'F', "SPAI"), ("helmholtz", [24, 24], 3, 'V', "Jac"),
+                                                       ("helmholtz", [10, 10, 10], 3, 'W', "SPAI")])
+def test_two_independent_restatements_agree(kind, n, levels, cycle, relax):
+    """oracle/cycle.py (control flow + the C kernels of mg_kernels.c) and oracle/cycle32.py (plain scipy / numpy passes,
+    written separately) restate the same lines of MGcycle.jl / SolveFuncs.jl: in double precision their per-cycle
+    residual norms agree to rounding (different accumulation code, same operation order)."""
+    from conftest import make_problem
+    from oracle import cycle as oc, cycle32 as o32
+    A, AT, M, p, b = make_problem(kind, n, levels, cycle=cycle, relax=relax, omega=0.8 if relax == "Jac" else 1.0, maxit=5)
+    _, it_c, res_c = oc.solveMG(oc.OracleMG(p), b, np.zeros_like(b))
+    _, it_n, res_n = o32.solveMG(o32.OracleMG32(p), b, np.zeros_like(b))
+    assert it_c == it_n
+    np.testing.assert_allclose(res_n, res_c, rtol=1e-11)
