@@ -14,8 +14,10 @@
 //   gpurun_out/microbench_lines              # 7-point 257^3 and 27-point 129^3 on the GPU, all variants, bit-compare
 //   gpurun_out/microbench_lines --host-check # no GPU: runs the per-thread function on the CPU for 9^3 .. 12x9x7 grids
 //
-// Two forms: (a) x straight from global memory (L1 / L2), (b) x staged in shared memory by bulk copies, one per plane of
-// the stencil, in a two-stage pipeline of persistent CTAs - the production kernel's scheme with another thread-to-row map.
+// Three forms: (a) x straight from global memory (L1 / L2), (b) x staged in shared memory by bulk copies, one per plane of
+// the stencil, in a two-stage pipeline of persistent CTAs - the production kernel's scheme with another thread-to-row map,
+// (c) marching: a CTA walks a column of line groups plane by plane with a ring of four plane slabs, so every x element
+// enters shared memory once per column instead of once per stencil plane (2.5-D blocking).
 //
 // NOT part of the library; not yet run on a B200 (written in a session whose GPU budget was spent; the host check,
 // which also replays the staged form with host buffers filled like the bulk copies fill shared memory, passes).
@@ -219,6 +221,53 @@ __host__ __device__ inline View stage_view(const Grid& G, const TilePlan& T, con
     return V;
 }
 
+// (c) marching: a CTA owns a column of Q line groups and walks it plane by plane (2.5-D blocking).  Slot zz % 4 of a
+// ring holds, for plane zz, the x slab [first line - 1, last line + 1] of the column (one bulk copy) and - for planes
+// the CTA computes - the b and pid tiles.  Computing plane z reads the slabs of z-1, z, z+1 while z+2 is in flight:
+// every x element enters shared memory ONCE per column (plus the two halo lines), not once per stencil plane.
+struct SlabPlan {
+    long long T0;            // first row of the column in this plane
+    int lines;
+    long long xa, xe;        // x slab [xa, xe), even; xe <= xa: plane outside the grid
+    long long ba, be, pa, pe;
+};
+__host__ __device__ inline SlabPlan plan_slab(const Grid& G, int R, int Q, int col, int zz) {
+    SlabPlan T;
+    const int q0 = col * Q;
+    T.T0 = (long long)zz * G.S2 + (long long)q0 * R * G.S;
+    const int left = G.n2 - q0 * R;
+    T.lines = left < Q * R ? left : Q * R;
+    const long long T1 = T.T0 + (long long)T.lines * G.S, nev = (G.n + 1) & ~1LL, n8 = (G.n + 7) & ~7LL;
+    if (zz < 0 || zz >= G.n3) { T.xa = T.xe = T.ba = T.be = T.pa = T.pe = 0; return T; }
+    long long a = T.T0 - G.S - 1, e = T1 + G.S + 1;
+    a = a < 0 ? 0 : a;
+    e = e > nev ? nev : e;
+    T.xa = a & ~1LL;
+    T.xe = (e + 1) & ~1LL;
+    T.ba = T.T0 & ~1LL;
+    T.be = ((T1 + 1) & ~1LL) > nev ? nev : ((T1 + 1) & ~1LL);
+    T.pa = T.T0 & ~7LL;
+    T.pe = ((T1 + 7) & ~7LL) > n8 ? n8 : ((T1 + 7) & ~7LL);
+    return T;
+}
+// the view of plane z of a column from the ring: slot(zz) = zz & 3; slot layout [x: xcap][b: bcap][pid: pcap]
+__host__ __device__ inline View march_view(const Grid& G, int R, int Q, int col, int z, const unsigned char* ring,
+                                           size_t slot_bytes, int xcap, int bcap) {
+    View V;
+    const SlabPlan C = plan_slab(G, R, Q, col, z);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const int zz = z + d - 1;
+        const SlabPlan P = plan_slab(G, R, Q, col, zz);
+        const double* sx = reinterpret_cast<const double*>(ring + (size_t)(zz & 3) * slot_bytes);
+        V.xs[d] = sx + (P.T0 - P.xa);   // xs[d][rel] = slab_zz[(T0(zz) + rel) - xa(zz)], T0(zz) = T0(z) + (d-1)*S2
+    }
+    const double* sc = reinterpret_cast<const double*>(ring + (size_t)(z & 3) * slot_bytes);
+    V.b = sc + xcap + (C.T0 - C.ba);
+    V.pid = reinterpret_cast<const uint16_t*>(sc + xcap + bcap) + (C.T0 - C.pa);
+    return V;
+}
+
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -295,6 +344,70 @@ __global__ void __launch_bounds__(NTMAX) k_lines_tma(Grid G, int Q, long long nt
             lines_thread<R>(G, V, rel0, T.T0 + rel0, y0, pat, ent, dp, y);
         }
         __syncthreads();
+    }
+}
+// work item = (column, z-chunk); ceil32(Q*S) threads
+template <int R, int NTMAX>
+__global__ void __launch_bounds__(NTMAX) k_lines_march(Grid G, int Q, int ncols, int zc, int nitems, const uint16_t* __restrict__ pid,
+                                                       const Pat* __restrict__ pat, const Ent* __restrict__ ent,
+                                                       const double* __restrict__ dp, const double* __restrict__ x,
+                                                       const double* __restrict__ b, double* __restrict__ y) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+    int xcap, bcap, pcap;
+    stage_layout(G, R, Q, xcap, bcap, pcap);
+    const size_t slot_bytes = (((size_t)(xcap + bcap) * 8 + (size_t)pcap * 2) + 127) / 128 * 128;
+    unsigned char* ring = smem_raw + 128;
+    const int t = threadIdx.x;
+    if (t == 0) {
+        for (int k = 0; k < 4; ++k) mbar_init(full + k, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    uint32_t phase = 0;                                            // bit k: parity the next wait on slot k expects
+    const int grp = t / G.S, i = t - grp * G.S;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int col = item % ncols, chunk = item / ncols;
+        const int z0 = chunk * zc, z1 = min(z0 + zc, G.n3);
+        const int first = max(z0 - 1, 0), last = min(z1, G.n3 - 1);
+        auto issue = [&](int zz) {
+            const SlabPlan P = plan_slab(G, R, Q, col, zz);
+            const int k = zz & 3;
+            double* sx = reinterpret_cast<double*>(ring + (size_t)k * slot_bytes);
+            const bool own = (zz >= z0 && zz < z1);                // planes this item computes also need b and pid
+            uint32_t bytes = (uint32_t)(P.xe - P.xa) * 8u;
+            if (own) bytes += (uint32_t)(P.be - P.ba) * 8u + (uint32_t)(P.pe - P.pa) * 2u;
+            mbar_expect_tx(full + k, bytes);
+            bulk_g2s(sx, x + P.xa, (uint32_t)(P.xe - P.xa) * 8u, full + k);
+            if (own) {
+                bulk_g2s(sx + xcap, b + P.ba, (uint32_t)(P.be - P.ba) * 8u, full + k);
+                bulk_g2s(reinterpret_cast<uint16_t*>(sx + xcap + bcap), pid + P.pa, (uint32_t)(P.pe - P.pa) * 2u, full + k);
+            }
+        };
+        int issued = first - 1, waited = first - 1;
+        if (t == 0)
+            for (int zz = first; zz <= min(first + 2, last); ++zz) issue(zz);
+        issued = min(first + 2, last);
+        for (int z = z0; z < z1; ++z) {
+            if (z + 2 <= last && z + 2 > issued) {                  // slot (z+2)&3 held plane z-2: free since the last barrier
+                if (t == 0) issue(z + 2);
+                issued = z + 2;
+            }
+            const int need = min(z + 1, last);
+            while (waited < need) {
+                ++waited;
+                const int k = waited & 3;
+                mbar_wait(full + k, (phase >> k) & 1);
+                phase ^= 1u << k;
+            }
+            const SlabPlan C = plan_slab(G, R, Q, col, z);
+            if (grp < Q && grp * R < C.lines) {
+                const View V = march_view(G, R, Q, col, z, ring, slot_bytes, xcap, bcap);
+                const long long rel0 = (long long)grp * R * G.S + i;
+                lines_thread<R>(G, V, rel0, C.T0 + rel0, col * Q * R + grp * R, pat, ent, dp, y);
+            }
+            __syncthreads();
+        }
     }
 }
 #endif
@@ -400,7 +513,51 @@ static bool host_check_one(const Grid& G, int pts) {
         }
         ok = ok && memcmp(y2.data(), yref.data(), G.n * sizeof(double)) == 0;
     }
-    printf("host check %2d-point %dx%dx%d R=%d (global form, staged form Q=1..3): %s\n", pts, G.n1, G.n2, G.n3, R,
+    // (c) marching form: the ring of four slots is replayed literally - a slot is poisoned and refilled exactly when the
+    // kernel would issue its copies, so a wrong schedule (a slab overwritten while still needed) shows as a mismatch
+    for (int Q = 1; Q <= 2; ++Q)
+        for (int zc : {1, 3, G.n3}) {
+            std::fill(y2.begin(), y2.end(), -1.0);
+            int xcap, bcap, pcap;
+            stage_layout(G, R, Q, xcap, bcap, pcap);
+            const size_t slot_bytes = (((size_t)(xcap + bcap) * 8 + (size_t)pcap * 2) + 127) / 128 * 128;
+            std::vector<unsigned char> ringv(4 * slot_bytes + 16);
+            unsigned char* ring = ringv.data() + (16 - ((uintptr_t)ringv.data() & 15)) % 16;
+            const int ncols = (gpp + Q - 1) / Q, nchunks = (G.n3 + zc - 1) / zc;
+            for (int item = 0; item < ncols * nchunks; ++item) {
+                const int col = item % ncols, chunk = item / ncols;
+                const int z0 = chunk * zc, z1 = std::min(z0 + zc, G.n3);
+                const int first = std::max(z0 - 1, 0), last = std::min(z1, G.n3 - 1);
+                auto issue = [&](int zz) {
+                    const SlabPlan P = plan_slab(G, R, Q, col, zz);
+                    double* sx = reinterpret_cast<double*>(ring + (size_t)(zz & 3) * slot_bytes);
+                    for (size_t k = 0; k < slot_bytes / 8; ++k) sx[k] = 1e300;
+                    if (P.xe - P.xa > xcap || P.be - P.ba > bcap || P.pe - P.pa > pcap) { printf("slab exceeds the slot\n"); exit(1); }
+                    for (long long g = P.xa; g < P.xe; ++g) sx[g - P.xa] = x[g];
+                    if (zz >= z0 && zz < z1) {
+                        for (long long g = P.ba; g < P.be; ++g) sx[xcap + (g - P.ba)] = b[g];
+                        uint16_t* sp = reinterpret_cast<uint16_t*>(sx + xcap + bcap);
+                        for (long long g = P.pa; g < P.pe; ++g) sp[g - P.pa] = pid[g];
+                    }
+                };
+                int issued = std::min(first + 2, last);
+                for (int zz = first; zz <= issued; ++zz) issue(zz);
+                for (int z = z0; z < z1; ++z) {
+                    if (z + 2 <= last && z + 2 > issued) { issue(z + 2); issued = z + 2; }
+                    const SlabPlan C = plan_slab(G, R, Q, col, z);
+                    const int nthreads = ((Q * G.S + 31) / 32) * 32;
+                    for (int t = 0; t < nthreads; ++t) {
+                        const int grp = t / G.S, i = t - grp * G.S;
+                        if (!(grp < Q && grp * R < C.lines)) continue;
+                        const View V = march_view(G, R, Q, col, z, ring, slot_bytes, xcap, bcap);
+                        const long long rel0 = (long long)grp * R * G.S + i;
+                        lines_thread<R>(G, V, rel0, C.T0 + rel0, col * Q * R + grp * R, pat.data(), ent.data(), dp.data(), y2.data());
+                    }
+                }
+            }
+            ok = ok && memcmp(y2.data(), yref.data(), G.n * sizeof(double)) == 0;
+        }
+    printf("host check %2d-point %dx%dx%d R=%d (global form, staged form Q=1..3, marching form): %s\n", pts, G.n1, G.n2, G.n3, R,
            ok ? "bit-identical" : "MISMATCH");
     return ok;
 }
@@ -448,7 +605,8 @@ int main(int argc, char** argv) {
         const int grid1 = (int)((n + 255) / 256);
         const char* names[] = {"reference 1 row/thread", "stream floor", "lines R=2 x4 CTAs/SM", "lines R=2 x8 CTAs/SM", "lines R=4 x3 CTAs/SM",
                                "lines R=4 x6 CTAs/SM", "lines R=8 x2 CTAs/SM", "lines R=8 x4 CTAs/SM", "lines TMA R=2 Q=1", "lines TMA R=2 Q=2",
-                               "lines TMA R=4 Q=1", "lines TMA R=4 Q=2", "lines TMA R=8 Q=1"};
+                               "lines TMA R=4 Q=1", "lines TMA R=4 Q=2", "lines TMA R=8 Q=1", "march R=2 Q=1", "march R=4 Q=1", "march R=4 Q=2",
+                               "march R=8 Q=1"};
         // staged form: Q groups per tile, ceil32(Q*S) threads, 2 stages; as many CTAs per SM as shared memory allows
         auto tma_launch = [&](int R, int Q) {
             int xcap, bcap, pcap;
@@ -466,7 +624,26 @@ int main(int argc, char** argv) {
             if (R == 2) TL(2) else if (R == 4) TL(4) else TL(8)
 #undef TL
         };
-        for (int v = 0; v < 13; ++v) {
+        // marching form: items = columns x z-chunks, chunks sized so that about 3 items per resident CTA exist
+        auto march_launch = [&](int R, int Q) {
+            int xcap, bcap, pcap;
+            stage_layout(G, R, Q, xcap, bcap, pcap);
+            const size_t slot = (((size_t)(xcap + bcap) * 8 + (size_t)pcap * 2) + 127) / 128 * 128, smem = 128 + 4 * slot;
+            const int nt = ((Q * G.S + 31) / 32) * 32;
+            if (smem > 227 * 1024 || nt > 544) { printf("  (march R=%d Q=%d skipped: %zu B shared memory, %d threads)\n", R, Q, smem, nt); return; }
+            int per = (int)std::min<size_t>((size_t)(2048 / nt), (228 * 1024) / (smem + 1024));
+            if (per < 1) per = 1;
+            const int gpp = (G.n2 + R - 1) / R, ncols = (gpp + Q - 1) / Q;
+            int nchunks = std::max(1, (3 * nsm * per + ncols - 1) / ncols);
+            int zc = std::max(8, (G.n3 + nchunks - 1) / nchunks);
+            nchunks = (G.n3 + zc - 1) / zc;
+            const int nitems = ncols * nchunks, grid = std::min(nitems, nsm * per);
+#define ML(R_) { static bool once = false; if (!once) { CK(cudaFuncSetAttribute(k_lines_march<R_, 544>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); once = true; } \
+                 k_lines_march<R_, 544><<<grid, nt, smem>>>(G, Q, ncols, zc, nitems, dpid, dpat, dent, ddp, dx, db, dy); }
+            if (R == 2) ML(2) else if (R == 4) ML(4) else ML(8)
+#undef ML
+        };
+        for (int v = 0; v < 17; ++v) {
             auto launch = [&]() {
                 switch (v) {
                     case 0: k_reference<<<grid1, 256>>>(G, dpid, dpat, dent, ddp, dx, db, dy); break;
@@ -482,6 +659,10 @@ int main(int argc, char** argv) {
                     case 10: tma_launch(4, 1); break;
                     case 11: tma_launch(4, 2); break;
                     case 12: tma_launch(8, 1); break;
+                    case 13: march_launch(2, 1); break;
+                    case 14: march_launch(4, 1); break;
+                    case 15: march_launch(4, 2); break;
+                    case 16: march_launch(8, 1); break;
                 }
             };
             CK(cudaMemset(dy, 0, n * 8));
