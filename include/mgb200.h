@@ -215,6 +215,9 @@ int mgb200_pattern_info(mgb200_handle h, int level, int which, int64_t* out);
  * building it), "graphs" (1/0: replay V/F/W cycles from CUDA graphs), "smem_budget" (bytes per CTA used when
  * choosing the rows per CTA of the CSR-stream kernel at upload), "tma" (1/0: TMA-staged persistent variant of the
  * dictionary kernel for square stencil operators), "tma_min_rows" (matrices with fewer rows keep the one-pass kernel),
+ * "lines" (0 = off, the default; 2 or 4: line-blocked dictionary kernel with that many rows per thread on levels whose
+ * dictionary has box structure and at least "lines_min_rows" rows - not yet run on a GPU),
+ * "fused_put" (1/0: multi-GPU, the producing kernel stores the slab-end rows to the neighbours itself),
  * "overlap" (1/0: multi-GPU, run the halo exchange of an operator's input beside the rows that read no ghost),
  * "split_test" (rows: single-GPU test hook that forces the split launch sequence of the overlap path). */
 int mgb200_set_option(mgb200_handle h, const char* key, int64_t value);
