@@ -65,6 +65,14 @@ int mgb200_upload_level(mgb200_handle h, int level, int64_t n, int64_t nc,
                         const int64_t* r_colptr, const int64_t* r_rowval, const void* r_nzval,
                         const void* d, int index_base);
 
+/* Optional grid hint for the transfer operators of level l, BEFORE mgb200_upload_level(l): the nodes per dimension of
+ * the meshes of level l and l+1 (param.Meshes[l].n .+ 1, param.Meshes[l+1].n .+ 1; dim = 1, 2 or 3).  If the uploaded
+ * Ps[l] / Rs[l] are exactly the operators those grids imply (full-weighting pair of GeometricTransferOperators.jl on
+ * nodal grids, every dimension coarsened; checked row by row at upload, the values are taken from the matrices) and
+ * the option "grid_transfers" is on, restriction and prolongation run kernels that read no matrix stream at all
+ * (csrc/grid_xfer.cuh); otherwise the hint is ignored.  Results are bit-identical either way. */
+int mgb200_set_level_grid(mgb200_handle h, int level, int dim, const int64_t* n_fine_nodes, const int64_t* n_coarse_nodes);
+
 /* defineCoarsestAinv (MGsetup.jl:323-355, default branch): As[end] = A_L^H in CSC; densified,
  * LU-factorised with partial pivoting and prepared for solves on the device. */
 int mgb200_upload_coarsest(mgb200_handle h, int64_t n, const int64_t* colptr, const int64_t* rowval,
@@ -217,6 +225,8 @@ int mgb200_pattern_info(mgb200_handle h, int level, int which, int64_t* out);
  * dictionary kernel for square stencil operators), "tma_min_rows" (matrices with fewer rows keep the one-pass kernel),
  * "lines" (0 = off, the default; 2 or 4: line-blocked dictionary kernel with that many rows per thread on levels whose
  * dictionary has box structure and at least "lines_min_rows" rows - not yet run on a GPU),
+ * "grid_transfers" (0 = off, the default; 1, 2 or 4: grid-hinted transfer kernels with that many coarse lines per thread
+ * on levels whose hint was verified, mgb200_set_level_grid - not yet run on a GPU),
  * "fused_put" (1/0: multi-GPU, the producing kernel stores the slab-end rows to the neighbours itself),
  * "overlap" (1/0: multi-GPU, run the halo exchange of an operator's input beside the rows that read no ghost),
  * "split_test" (rows: single-GPU test hook that forces the split launch sequence of the overlap path). */
@@ -239,6 +249,15 @@ int mgb200_host_detect_box(int64_t n_rows, const int64_t* colptr, const int64_t*
 int mgb200_host_lines_apply(int64_t n_rows, const int64_t* colptr, const int64_t* rowval, const double* nzval,
                             int index_base, int mode, int rows_per_thread, int fold_d, const double* x, const double* b,
                             const double* d, double* y, int64_t* info);
+
+/* Host-only (no GPU): the grid-hinted transfer kernels' per-thread functions (csrc/grid_xfer.cuh, __host__ __device__) run
+ * on the CPU for every thread of a launch, for a real Float64 transfer matrix given by its CSC-of-the-transpose arrays
+ * as uploaded (kind 1: Ps[l], y += P x with x coarse, y fine; kind 2: Rs[l], y = R x with x fine, y coarse).
+ * lines_per_thread in {1, 2, 4}, or 0 for the dictionary walk (the reference the kernels must match bit for bit).
+ * info[0] = 1 if the hint matches the matrix (y is then written / updated), else 0 and y is untouched. */
+int mgb200_host_grid_transfer(int kind, int dim, const int64_t* n_fine_nodes, const int64_t* n_coarse_nodes, int64_t n_rows,
+                              const int64_t* colptr, const int64_t* rowval, const double* nzval, int index_base,
+                              int lines_per_thread, const double* x, double* y, int64_t* info);
 
 /* Host-only (no GPU): the window plan of the TMA-staged dictionary kernel for a row-relative matrix, exported for the
  * CPU test-suite.  Input as mgb200_host_build_patterns; `tile` rows per tile, elem_bytes 4, 8 or 16 (copies are rounded

@@ -12,6 +12,7 @@
 #include "csr_kernels.cuh"
 #include "dense_lu.cuh"
 #include "pattern.cuh"
+#include "grid_xfer.cuh"
 #include "vec_kernels.cuh"
 
 namespace mgb200 {
@@ -96,9 +97,11 @@ struct Csr {
     size_t smem = 0;
     PatDict<TA> pat;    // stencil-dictionary form (pattern.cuh), when the rows deduplicate
     int int_lo = 0, int_hi = 0;  // row-partitioned levels: rows [int_lo, int_hi) read no ghost row of the input vector
+    GridXfer gx{};      // grid hint of a transfer operator (grid_xfer.cuh), ok = 0 unless verified at upload
     bool present() const { return rowptr != nullptr; }
     void release() {
         pat.release();
+        gx = no_grid();
         int_lo = int_hi = 0;
         dev_free(rowptr);
         dev_free(colind);
@@ -125,6 +128,7 @@ struct Context {
     int use_patterns = 1;          // 0: always stream CSR (MGB200_PATTERNS / mgb200_set_option)
     int use_graphs = 1;            // 0: never replay cycles from CUDA graphs
     int use_tma = 1;               // 0: never use the TMA-staged dictionary kernel (MGB200_TMA)
+    int grid_transfers = 0;        // > 0: grid-hinted transfer kernels (grid_xfer.cuh) with that many coarse lines per thread (1, 2, 4); off by default
     int lines = 0;                 // > 0: line-blocked dictionary kernel with that many rows per thread (2 or 4); off by default
     int lines_min_rows = 50000;
     int tma_min_rows = 200000;     // smaller matrices keep the one-pass kernel (too few tiles per SM)
@@ -159,6 +163,7 @@ struct Context {
         use_tma = env_int("MGB200_TMA", 1);
         tma_min_rows = env_int("MGB200_TMA_MIN_ROWS", 200000);
         lines = env_int("MGB200_LINES", 0);
+        grid_transfers = env_int("MGB200_GRID_TRANSFERS", 0);
         lines_min_rows = env_int("MGB200_LINES_MIN_ROWS", 50000);
         use_overlap = env_int("MGB200_OVERLAP", 0);
         split_test = env_int("MGB200_SPLIT_TEST", 0);
@@ -252,7 +257,7 @@ struct Launch {
 template <typename TA>
 static void upload_csr(Context& ctx, Csr<TA>& M, long long n_rows, long long n_cols, const int64_t* colptr,
                        const int64_t* rowval, const TA* nzval, int base, bool conjugate,
-                       bool want_patterns = true) {
+                       bool want_patterns = true, HostPatterns<TA>* keep = nullptr) {
     MGB_CHECK(n_rows > 0 && n_rows < (1LL << 31) - 8, "matrix rows out of range");
     MGB_CHECK(colptr && rowval && nzval, "null matrix array");
     const long long nnz = colptr[n_rows] - base;
@@ -337,6 +342,7 @@ static void upload_csr(Context& ctx, Csr<TA>& M, long long n_rows, long long n_c
             upload_patterns<TA>(M.pat, hp, n_rows);
             M.pat.xlo = 0;                               // input vectors hold n_cols elements (+ slack, vec_alloc)
             M.pat.xhi = (long long)align_pad<TA>((size_t)n_cols);
+            if (keep) *keep = std::move(hp);      // the caller checks a grid hint against the dictionary
         }
     }
 }

@@ -194,6 +194,17 @@ static long long host_lines_run(const HostPatterns<double>& hp, const BoxInfo& B
     return slow;
 }
 
+template <int R>
+static void host_gx_run(const GridXfer& X, const std::vector<PatEntry<double>>& ent, const double* x, double* y) {
+    const int gpp = (X.N[1] + R - 1) / R;
+    for (int K = 0; K < X.N[2]; ++K)
+        for (int q = 0; q < gpp; ++q)
+            for (int I = 0; I < X.N[0]; ++I) {
+                if (X.kind == 2) gx_restrict_thread<double, double, R>(X, I, q * R, K, ent.data(), x, y);
+                else gx_prolong_thread<double, double, R>(X, I, q * R, K, ent.data(), x, y);
+            }
+}
+
 extern "C" {
 
 const char* mgb200_last_error(void) { return g_last_error.c_str(); }
@@ -273,6 +284,12 @@ int mgb200_upload_level(mgb200_handle h, int level, int64_t n, int64_t nc, const
     MGB_TRY
     MGB_BOTH(h, H->upload_level(level, n, nc, a_colptr, a_rowval, a_nzval, p_colptr, p_rowval, p_nzval,
                                 r_colptr, r_rowval, r_nzval, d, index_base));
+    MGB_CATCH
+}
+
+int mgb200_set_level_grid(mgb200_handle h, int level, int dim, const int64_t* n_fine_nodes, const int64_t* n_coarse_nodes) {
+    MGB_TRY
+    MGB_BOTH(h, H->set_level_grid(level, dim, n_fine_nodes, n_coarse_nodes));
     MGB_CATCH
 }
 
@@ -547,6 +564,7 @@ int mgb200_set_option(mgb200_handle h, const char* key, int64_t value) {
         else if (k == "tma") H->ctx.use_tma = (int)value;
         else if (k == "tma_min_rows") H->ctx.tma_min_rows = (int)value;
         else if (k == "lines") H->ctx.lines = (int)value;
+        else if (k == "grid_transfers") H->ctx.grid_transfers = (int)value;
         else if (k == "lines_min_rows") H->ctx.lines_min_rows = (int)value;
         else if (k == "split_test") H->ctx.split_test = (int)value;
         else if (k == "overlap") H->ctx.use_overlap = (int)value;
@@ -652,6 +670,45 @@ int mgb200_host_lines_apply(int64_t n_rows, const int64_t* colptr, const int64_t
     info[1] = B.S;
     info[2] = B.S2;
     info[3] = slow;
+    MGB_CATCH
+}
+
+int mgb200_host_grid_transfer(int kind, int dim, const int64_t* n_fine_nodes, const int64_t* n_coarse_nodes, int64_t n_rows,
+                              const int64_t* colptr, const int64_t* rowval, const double* nzval, int index_base,
+                              int lines_per_thread, const double* x, double* y, int64_t* info) {
+    MGB_TRY
+    MGB_CHECK(colptr && rowval && nzval && x && y && info && n_fine_nodes && n_coarse_nodes, "null argument");
+    MGB_CHECK(kind == 1 || kind == 2, "kind must be 1 (prolongation) or 2 (restriction)");
+    MGB_CHECK(dim >= 1 && dim <= 3, "dim must be 1, 2 or 3");
+    MGB_CHECK(lines_per_thread == 0 || lines_per_thread == 1 || lines_per_thread == 2 || lines_per_thread == 4,
+              "lines_per_thread must be 0, 1, 2 or 4");
+    info[0] = 0;
+    HostPatterns<double> hp;
+    if (!build_patterns<double>(n_rows, colptr, rowval, nzval, index_base, false, PAT_MAX_PATTERNS, PAT_MAX_ENTRIES, hp)) return 0;
+    int n[3], N[3];
+    for (int d = 0; d < 3; ++d) {
+        n[d] = d < dim ? (int)n_fine_nodes[d] : 1;
+        N[d] = d < dim ? (int)n_coarse_nodes[d] : 1;
+    }
+    GridXfer X;
+    const bool ok = kind == 1 ? gx_verify_prolongation<double>(hp, n_rows, n, N, X) : gx_verify_restriction<double>(hp, n_rows, n, N, X);
+    if (!ok) return 0;
+    std::vector<PatEntry<double>> ent(hp.delta.size());
+    for (size_t k = 0; k < ent.size(); ++k) {
+        ent[k].v = hp.val[k];
+        ent[k].delta = hp.delta[k];
+    }
+    if (lines_per_thread == 0) {           // dictionary walk, one row at a time: column = c0[row] + delta
+        for (long long row = 0; row < n_rows; ++row) {
+            const int p = hp.pid[row];
+            double acc = 0.0;
+            for (int k = hp.pat_off[p]; k < hp.pat_off[p + 1]; ++k) acc = acc + hp.val[k] * x[hp.c0[row] + hp.delta[k]];
+            y[row] = kind == 1 ? y[row] + acc : acc;
+        }
+    } else if (lines_per_thread == 1) host_gx_run<1>(X, ent, x, y);
+    else if (lines_per_thread == 2) host_gx_run<2>(X, ent, x, y);
+    else host_gx_run<4>(X, ent, x, y);
+    info[0] = 1;
     MGB_CATCH
 }
 

@@ -45,6 +45,8 @@ struct Level {
     Csr<RT> P, R;
     TV* d = nullptr;
     TV* dpat = nullptr;            // d as a function of A's pattern id, when it is one (pattern.cuh)
+    int gn[3] = {0, 0, 0}, gN[3] = {0, 0, 0};   // grid hint (mgb200_set_level_grid): fine / coarse nodes per dimension
+    bool ghint = false;
     TV *b = nullptr, *r = nullptr, *x0 = nullptr, *x1 = nullptr;  // CYCLEmem + ping-pong partner of x
     FgmresMem<TV> memRelax, memK;
     // ---- multi-GPU row partition (dist.cuh) ----
@@ -210,8 +212,18 @@ struct Hierarchy : HierarchyBase {
         Level<TV>& lv = L[level - 1];
         lv.n = n;
         upload_csr<TV>(ctx, lv.A, n, n, acp, arv, static_cast<const TV*>(anz), base, true);
-        upload_csr<RT>(ctx, lv.P, n, nc, pcp, prv, static_cast<const RT*>(pnz), base, false);
-        upload_csr<RT>(ctx, lv.R, nc, n, rcp, rrv, static_cast<const RT*>(rnz), base, false);
+        if (lv.ghint) {
+            // the hint is only kept for the operator it describes exactly (grid_xfer.cuh); otherwise nothing changes
+            HostPatterns<RT> hp;
+            upload_csr<RT>(ctx, lv.P, n, nc, pcp, prv, static_cast<const RT*>(pnz), base, false, true, &hp);
+            if (lv.P.pat.present) gx_verify_prolongation<RT>(hp, n, lv.gn, lv.gN, lv.P.gx);
+            hp = HostPatterns<RT>();
+            upload_csr<RT>(ctx, lv.R, nc, n, rcp, rrv, static_cast<const RT*>(rnz), base, false, true, &hp);
+            if (lv.R.pat.present) gx_verify_restriction<RT>(hp, nc, lv.gn, lv.gN, lv.R.gx);
+        } else {
+            upload_csr<RT>(ctx, lv.P, n, nc, pcp, prv, static_cast<const RT*>(pnz), base, false);
+            upload_csr<RT>(ctx, lv.R, nc, n, rcp, rrv, static_cast<const RT*>(rnz), base, false);
+        }
         dev_free(lv.d);
         lv.d = dev_alloc<TV>(n + 4);   // slack for the even-rounded tile copies of the TMA kernel
         MGB_CUDA(cudaMemcpy(lv.d, d, n * sizeof(TV), cudaMemcpyHostToDevice));
@@ -221,6 +233,18 @@ struct Hierarchy : HierarchyBase {
         L[level].n = nc;
         L[level].nalloc = nc;
         work_ready = false;
+    }
+
+    // the meshes of level l and l+1 (param.Meshes[l].n + 1 nodes per dimension), BEFORE upload_level(level)
+    void set_level_grid(int level, int dim, const int64_t* nf, const int64_t* nc) {
+        MGB_CHECK(level >= 1 && level < levels, "set_level_grid: level must be in 1..levels-1");
+        MGB_CHECK(dim >= 1 && dim <= 3 && nf && nc, "set_level_grid: dim must be 1, 2 or 3");
+        Level<TV>& lv = L[level - 1];
+        for (int d = 0; d < 3; ++d) {
+            lv.gn[d] = d < dim ? (int)nf[d] : 1;
+            lv.gN[d] = d < dim ? (int)nc[d] : 1;
+        }
+        lv.ghint = true;
     }
 
     // relaxPrecs[l] as a function of A_l's pattern id: d folds into the dictionary when every row of

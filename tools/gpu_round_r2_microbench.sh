@@ -15,3 +15,10 @@ for R in 2 4; do
   cut -c1-200 gpurun_out/bench_n1_lines$R.json
   grep "per-kernel" gpurun_out/bench_n1_lines$R.log | cut -c1-900
 done
+# the grid-hinted transfer kernels: bit-identity on the GPU, and the bench with them
+MGB200_TEST_GRID_TRANSFERS=1 timeout 300 python -m pytest tests/test_patterns.py -m gpu -q -k grid_hinted 2>&1 | tail -3
+for R in 1 2 4; do
+  MGB200_GRID_TRANSFERS=$R timeout 300 python bench.py --no-cpu > gpurun_out/bench_n1_gx$R.json 2> gpurun_out/bench_n1_gx$R.log; echo "bench grid_transfers=$R exit $?"
+  cut -c1-200 gpurun_out/bench_n1_gx$R.json
+  grep "per-kernel" gpurun_out/bench_n1_gx$R.log | cut -c1-900
+done
