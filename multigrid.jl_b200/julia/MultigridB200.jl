@@ -48,6 +48,11 @@ function uploadHierarchy(param::MGparam{VAL,Int64}; device::Integer=0) where {VA
                 h, valtype_code(VAL), levels, nrhs, Cchar(param.cycleType), relaxKind, pre, post, device))
     for l = 1:levels-1
         AT, PT, RT = param.As[l], param.Ps[l], param.Rs[l]
+        if length(param.Meshes) > l      # geometric hierarchy: the meshes are a hint for the transfer kernels (optional)
+            nf = Int64.(param.Meshes[l].n .+ 1); nc = Int64.(param.Meshes[l+1].n .+ 1)
+            check(ccall((:mgb200_set_level_grid, libmgb200), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Int64}, Ptr{Int64}),
+                        h[], l, length(nf), nf, nc))
+        end
         d = convert(Vector{VAL}, param.relaxPrecs[l])
         check(ccall((:mgb200_upload_level, libmgb200), Cint,
                     (Ptr{Cvoid}, Cint, Int64, Int64,
