@@ -224,7 +224,8 @@ int mgb200_pattern_info(mgb200_handle h, int level, int which, int64_t* out);
  * choosing the rows per CTA of the CSR-stream kernel at upload), "tma" (1/0: TMA-staged persistent variant of the
  * dictionary kernel for square stencil operators), "tma_min_rows" (matrices with fewer rows keep the one-pass kernel),
  * "lines" (0 = off, the default; 2 or 4: line-blocked dictionary kernel with that many rows per thread on levels whose
- * dictionary has box structure and at least "lines_min_rows" rows - not yet run on a GPU),
+ * dictionary has box structure and at least "lines_min_rows" rows; "lines_staged" 1: its TMA-staged form where the
+ * lines are short enough, else the global-memory form - not yet run on a GPU),
  * "grid_transfers" (0 = off, the default; 1, 2 or 4: grid-hinted transfer kernels with that many coarse lines per thread
  * on levels whose hint was verified, mgb200_set_level_grid - not yet run on a GPU),
  * "fused_put" (1/0: multi-GPU, the producing kernel stores the slab-end rows to the neighbours itself),
@@ -243,12 +244,13 @@ int mgb200_host_detect_box(int64_t n_rows, const int64_t* colptr, const int64_t*
  * pat_lines_thread, __host__ __device__) on the CPU for every thread of a launch - the exact code the GPU executes -
  * for a Float64 matrix given as in mgb200_host_build_patterns.  mode: 0 y = A x, 2 y = b - A x, 3 y = x + d.*(b - A x);
  * rows_per_thread R in {2, 4}, or 0 for the one-row-per-thread dictionary walk (the reference the kernel must match
- * bit for bit); fold_d != 0: d is read per pattern (first row that carries the pattern).  info[0] = 1 if the matrix has
+ * bit for bit); groups_per_tile 0: global-memory form, Q > 0: staged form with tiles of Q groups, the stage being a
+ * host buffer filled exactly as the kernel's bulk copies fill shared memory; fold_d != 0: d is read per pattern (first row that carries the pattern).  info[0] = 1 if the matrix has
  * the box structure the kernel needs (y is then written), info[1] = S, info[2] = S2, info[3] = groups that took the
  * row-by-row path. */
 int mgb200_host_lines_apply(int64_t n_rows, const int64_t* colptr, const int64_t* rowval, const double* nzval,
-                            int index_base, int mode, int rows_per_thread, int fold_d, const double* x, const double* b,
-                            const double* d, double* y, int64_t* info);
+                            int index_base, int mode, int rows_per_thread, int groups_per_tile, int fold_d, const double* x,
+                            const double* b, const double* d, double* y, int64_t* info);
 
 /* Host-only (no GPU): the grid-hinted transfer kernels' per-thread functions (csrc/grid_xfer.cuh, __host__ __device__) run
  * on the CPU for every thread of a launch, for a real Float64 transfer matrix given by its CSC-of-the-transpose arrays

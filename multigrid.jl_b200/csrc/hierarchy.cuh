@@ -131,6 +131,7 @@ struct Context {
     int grid_transfers = 0;        // > 0: grid-hinted transfer kernels (grid_xfer.cuh) with that many coarse lines per thread (1, 2, 4); off by default
     int lines = 0;                 // > 0: line-blocked dictionary kernel with that many rows per thread (2 or 4); off by default
     int lines_min_rows = 50000;
+    int lines_staged = 1;          // 1: TMA-staged form of the line-blocked kernel where the lines fit a CTA, 0: global-memory form
     int tma_min_rows = 200000;     // smaller matrices keep the one-pass kernel (too few tiles per SM)
     int split_test = 0;            // > 0: every dictionary pass runs as interior + both ends (test hook)
     int use_overlap = 0;           // multi-GPU: halo exchange beside the interior rows (MGB200_OVERLAP=1; measured
@@ -165,6 +166,7 @@ struct Context {
         lines = env_int("MGB200_LINES", 0);
         grid_transfers = env_int("MGB200_GRID_TRANSFERS", 0);
         lines_min_rows = env_int("MGB200_LINES_MIN_ROWS", 50000);
+        lines_staged = env_int("MGB200_LINES_STAGED", 1);
         use_overlap = env_int("MGB200_OVERLAP", 0);
         split_test = env_int("MGB200_SPLIT_TEST", 0);
         int prio_lo = 0, prio_hi = 0;

@@ -160,7 +160,47 @@ static bool launch_pattern_lines(Context& ctx, const Csr<TV>& M, int mode, const
     const int R = ctx.lines;
     if ((R != 2 && R != 4) || !D.box_ok || !D.rowrel || mode == MODE_ADD || x == y) return false;
     if (M.n_rows < ctx.lines_min_rows) return false;
-    const long long S = D.S, nlines = (M.n_rows + S - 1) / S, total = ((nlines + R - 1) / R) * S;
+    const long long S = D.S, nlines = (M.n_rows + S - 1) / S, groups = (nlines + R - 1) / R, total = groups * S;
+    // (b) staged form: tiles of Q groups, ceil32(Q*S) <= 544 threads, two stages in shared memory
+    if (ctx.lines_staged && S <= 544 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (!b || (reinterpret_cast<uintptr_t>(b) & 15) == 0) &&
+        (!d || (reinterpret_cast<uintptr_t>(d) & 15) == 0)) {
+        constexpr int AL = sizeof(TV) >= 8 ? 2 : 4;
+        const bool need_b = (mode == MODE_RESID || mode == MODE_SWEEP), need_d = (mode == MODE_SWEEP && !dpat);
+        int Q = (int)std::max<long long>(1, 512 / S);
+        size_t smem = 0;
+        int nt = 0;
+        for (; Q >= 1; --Q) {
+            int xcap, vcap, pcap;
+            lines_stage_layout(S, R, Q, AL, xcap, vcap, pcap);
+            const size_t stage = (((size_t)(3 * xcap + (need_b ? vcap : 0) + (need_d ? vcap : 0)) * sizeof(TV) + (size_t)pcap * 2) + 127) / 128 * 128;
+            smem = 128 + 2 * stage;
+            nt = (int)(((long long)Q * S + 31) / 32 * 32);
+            if (smem <= (size_t)ctx.max_smem_optin / 2 - 1024 || Q == 1) break;     // two CTAs per SM when possible
+        }
+        if (nt <= 544 && smem <= (size_t)ctx.max_smem_optin - 1024) {
+            const long long ntiles = (groups + Q - 1) / Q;
+            int per = (int)std::min<size_t>((size_t)(2048 / nt), ((size_t)ctx.max_smem_optin + 1024) / (smem + 1024));
+            per = std::max(per, 1);
+            const int grid = (int)std::min<long long>(ntiles, (long long)ctx.sm_count * per);
+#define MGB_LT(MODE, DP, RR)                                                                                          \
+    {                                                                                                                 \
+        auto kern = pat_lines_tma_kernel<TV, TV, MODE, DP, RR, 544>;                                                  \
+        MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx.max_smem_optin));        \
+        kern<<<grid, nt, smem, ctx.stream>>>(S, (long long)D.S2, (long long)M.n_rows, Q, ntiles, D.xlo, D.xhi, D.pid, D.pat_off, \
+                                             D.ent, D.box_mask, dpat, x, b, d, y);                                     \
+    }
+#define MGB_LTR(MODE, DP) { if (R == 2) MGB_LT(MODE, DP, 2) else MGB_LT(MODE, DP, 4) }
+            if (mode == MODE_SPMV) MGB_LTR(MODE_SPMV, false)
+            else if (mode == MODE_RESID) MGB_LTR(MODE_RESID, false)
+            else if (dpat) MGB_LTR(MODE_SWEEP, true)
+            else MGB_LTR(MODE_SWEEP, false)
+#undef MGB_LTR
+#undef MGB_LT
+            MGB_LAUNCH_CHECK();
+            return true;
+        }
+    }
+    // (a) global-memory form
     const int grid = (int)std::min<long long>((total + 255) / 256, (long long)ctx.sm_count * (R == 2 ? 6 : 3));
 #define MGB_LL(MODE, DP, RR) \
     pat_lines_kernel<TV, TV, MODE, DP, RR><<<grid, 256, 0, ctx.stream>>>(S, (long long)D.S2, (long long)M.n_rows, total, D.pid, D.pat_off, D.ent, D.box_mask, dpat, x, b, d, y)

@@ -183,6 +183,10 @@ def test_line_blocked_kernel_code_on_the_cpu(n, R):
             got = device.host_lines_apply(mat, mode, R, x, b, d, fold)
             assert ref is not None and got is not None
             assert np.array_equal(ref[0].view(np.int64), got[0].view(np.int64)), (l, mode, fold)
+            # staged (TMA) form: tiles of Q groups, the stage replayed with host buffers filled like the bulk copies
+            for Q in (1, 3):
+                st = device.host_lines_apply(mat, mode, R, x, b, d, fold, groups_per_tile=Q)
+                assert st is not None and np.array_equal(ref[0].view(np.int64), st[0].view(np.int64)), (l, mode, fold, Q)
             # the blocked path is really taken on the fine level (a 6-line coarse plane may have no R = 4 group with
             # one pattern: everything then goes row by row, still bit-identical)
             lines = -(-N // got[1]["S"])

@@ -10,11 +10,12 @@ for t in microbench_lines microbench_transfer; do
 done
 # then the library form of the line-blocked kernel: bit-identity on the GPU, and the bench with it
 MGB200_TEST_LINES=1 timeout 300 python -m pytest tests/test_patterns.py -m gpu -q -k line_blocked 2>&1 | tail -3
-for R in 2 4; do
-  MGB200_LINES=$R timeout 300 python bench.py --no-cpu > gpurun_out/bench_n1_lines$R.json 2> gpurun_out/bench_n1_lines$R.log; echo "bench lines=$R exit $?"
-  cut -c1-200 gpurun_out/bench_n1_lines$R.json
-  grep "per-kernel" gpurun_out/bench_n1_lines$R.log | cut -c1-900
-done
+MGB200_TEST_LINES=1 MGB200_LINES_STAGED=0 timeout 300 python -m pytest tests/test_patterns.py -m gpu -q -k line_blocked 2>&1 | tail -3
+for ST in 1 0; do for R in 2 4; do
+  MGB200_LINES=$R MGB200_LINES_STAGED=$ST timeout 300 python bench.py --no-cpu > gpurun_out/bench_n1_lines${R}_st$ST.json 2> gpurun_out/bench_n1_lines${R}_st$ST.log; echo "bench lines=$R staged=$ST exit $?"
+  cut -c1-200 gpurun_out/bench_n1_lines${R}_st$ST.json
+  grep "per-kernel" gpurun_out/bench_n1_lines${R}_st$ST.log | cut -c1-900
+done; done
 # the grid-hinted transfer kernels: bit-identity on the GPU, and the bench with them
 MGB200_TEST_GRID_TRANSFERS=1 timeout 300 python -m pytest tests/test_patterns.py -m gpu -q -k grid_hinted 2>&1 | tail -3
 for R in 1 2 4; do
