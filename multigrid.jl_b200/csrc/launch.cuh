@@ -219,6 +219,9 @@ static bool launch_pattern_lines(Context& ctx, const Csr<TV>& M, int mode, const
 // option "grid_transfers" (MGB200_GRID_TRANSFERS) holds the coarse lines per thread (1, 2 or 4)
 template <typename TA, typename TV>
 static bool launch_grid_xfer(Context& ctx, const Csr<TA>& M, int mode, const TV* x, TV* y) {
+    if constexpr (VT<TA>::is_complex) {
+        return false;     // P and R are real (SA-AMG.jl:9-10, MGsetup.jl:80-81): no complex instantiation
+    } else {
     const GridXfer& X = M.gx;
     const int R = ctx.grid_transfers;
     if (!X.ok || !M.pat.present || (R != 1 && R != 2 && R != 4) || x == y) return false;
@@ -233,6 +236,7 @@ static bool launch_grid_xfer(Context& ctx, const Csr<TA>& M, int mode, const TV*
 #undef MGB_GX
     MGB_LAUNCH_CHECK();
     return true;
+    }
 }
 
 // one-pass dictionary kernel over the rows [rA, rA + nA) and [rB, rB + nB)
