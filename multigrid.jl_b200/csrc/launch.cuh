@@ -146,16 +146,16 @@ static bool launch_pattern_tma(Context& ctx, const Csr<TA>& M, int mode, const T
     return true;
 }
 
-// line-blocked variant (pat_lines_kernel): box-structured square operators, SPMV / RESID / SWEEP, whole matrix,
-// no fused put; off unless the option "lines" (MGB200_LINES) holds the rows per thread (2 or 4)
+// line-blocked variant (pat_lines_kernel / pat_lines_tma_kernel): box-structured square operators, SPMV / RESID /
+// SWEEP, whole matrix, with the fused put of row-partitioned levels; off unless the option "lines" (MGB200_LINES) holds the rows per thread (2 or 4)
 template <typename TA, typename TV>
 static bool launch_pattern_lines(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d,
-                                 const TV* dpat, TV* y) {
+                                 const TV* dpat, TV* y, const PutPlan& pp) {
     return false;
 }
 template <typename TV>
 static bool launch_pattern_lines(Context& ctx, const Csr<TV>& M, int mode, const TV* x, const TV* b, const TV* d,
-                                 const TV* dpat, TV* y) {
+                                 const TV* dpat, TV* y, const PutPlan& pp) {
     const PatDict<TV>& D = M.pat;
     const int R = ctx.lines;
     if ((R != 2 && R != 4) || !D.box_ok || !D.rowrel || mode == MODE_ADD || x == y) return false;
@@ -186,7 +186,7 @@ static bool launch_pattern_lines(Context& ctx, const Csr<TV>& M, int mode, const
     {                                                                                                                 \
         auto kern = pat_lines_tma_kernel<TV, TV, MODE, DP, RR, 544>;                                                  \
         MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx.max_smem_optin));        \
-        kern<<<grid, nt, smem, ctx.stream>>>(S, (long long)D.S2, (long long)M.n_rows, Q, ntiles, D.xlo, D.xhi, D.pid, D.pat_off, \
+        kern<<<grid, nt, smem, ctx.stream>>>(pp, S, (long long)D.S2, (long long)M.n_rows, Q, ntiles, D.xlo, D.xhi, D.pid, D.pat_off, \
                                              D.ent, D.box_mask, dpat, x, b, d, y);                                     \
     }
 #define MGB_LTR(MODE, DP) { if (R == 2) MGB_LT(MODE, DP, 2) else MGB_LT(MODE, DP, 4) }
@@ -203,7 +203,7 @@ static bool launch_pattern_lines(Context& ctx, const Csr<TV>& M, int mode, const
     // (a) global-memory form
     const int grid = (int)std::min<long long>((total + 255) / 256, (long long)ctx.sm_count * (R == 2 ? 6 : 3));
 #define MGB_LL(MODE, DP, RR) \
-    pat_lines_kernel<TV, TV, MODE, DP, RR><<<grid, 256, 0, ctx.stream>>>(S, (long long)D.S2, (long long)M.n_rows, total, D.pid, D.pat_off, D.ent, D.box_mask, dpat, x, b, d, y)
+    pat_lines_kernel<TV, TV, MODE, DP, RR><<<grid, 256, 0, ctx.stream>>>(pp, S, (long long)D.S2, (long long)M.n_rows, total, D.pid, D.pat_off, D.ent, D.box_mask, dpat, x, b, d, y)
 #define MGB_LR(MODE, DP) { if (R == 2) MGB_LL(MODE, DP, 2); else MGB_LL(MODE, DP, 4); }
     if (mode == MODE_SPMV) MGB_LR(MODE_SPMV, false)
     else if (mode == MODE_RESID) MGB_LR(MODE_RESID, false)
@@ -272,7 +272,7 @@ static void launch_pattern_rows(Context& ctx, const Csr<TA>& M, int mode, const 
 template <typename TA, typename TV>
 static void launch_pattern_mode(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d,
                                 const TV* dpat, TV* y, const PutPlan& pp = no_put()) {
-    if (!pp.on && ctx.lines > 0 && launch_pattern_lines(ctx, M, mode, x, b, d, dpat, y)) return;
+    if (ctx.lines > 0 && launch_pattern_lines(ctx, M, mode, x, b, d, dpat, y, pp)) return;
     if (M.pat.rowrel && launch_pattern_tma<TA, TV>(ctx, M, mode, x, b, d, dpat, y, 0, -1, 0, pp)) return;
     launch_pattern_rows<TA, TV>(ctx, M, mode, x, b, d, dpat, y, 0, M.n_rows, 0, 0, pp);
 }

@@ -586,6 +586,14 @@ __host__ __device__ __forceinline__ TV pat_epilogue(TV acc, TV xval, TV bval, TV
     const TV r = bval - acc;
     return xval + dval * r;
 }
+// result store of the line-blocked kernels: on the device also the fused put of a row-partitioned level (ll.cuh)
+template <typename TV>
+__host__ __device__ __forceinline__ void lines_store(TV* y, long long row, TV out, const PutPlan* pp) {
+    y[row] = out;
+#ifdef __CUDA_ARCH__
+    if (pp && pp->on) ll_put_edge<TV>(*pp, row, out);
+#endif
+}
 // Where a thread of the line-blocked kernel finds its data.  rel = row - T0 for a reference row T0 (0 for the
 // global-memory form, the first row of the tile for the staged form): xs[dz+1][rel] == x[T0 + dz*S2 + rel] for every rel
 // the thread touches; b, d, pid likewise.
@@ -621,7 +629,8 @@ __host__ __device__ inline TV pat_row_walk(long long S2, const LinesView<TV>& V,
 template <typename TA, typename TV, int MODE, bool DPAT, int R>
 __host__ __device__ inline void pat_lines_thread(long long S, long long S2, long long n_rows, const LinesView<TV>& V,
                                                  long long rel0, long long row0, const int* pat_off,
-                                                 const PatEntry<TA>* ent, const int* mask, const TV* dpat, TV* y) {
+                                                 const PatEntry<TA>* ent, const int* mask, const TV* dpat, TV* y,
+                                                 const PutPlan* pp = nullptr) {
     if (row0 >= n_rows) return;
     int nr = R;
     while (row0 + (long long)(nr - 1) * S >= n_rows) --nr;        // rows of the group that exist (nr >= 1)
@@ -632,7 +641,7 @@ __host__ __device__ inline void pat_lines_thread(long long S, long long S2, long
         if (j < nr) same = same && (ld_pid(V.pid + rel0 + j * S) == p0);
     if (!same) {
         for (int j = 0; j < nr; ++j)
-            y[row0 + j * S] = pat_row_walk<TA, TV, MODE, DPAT>(S2, V, rel0 + j * S, pat_off, ent, dpat);
+            lines_store<TV>(y, row0 + j * S, pat_row_walk<TA, TV, MODE, DPAT>(S2, V, rel0 + j * S, pat_off, ent, dpat), pp);
         return;
     }
     const int m = ld_ro(mask + p0);
@@ -689,7 +698,7 @@ __host__ __device__ inline void pat_lines_thread(long long S, long long S2, long
             if (!DPAT) dval = V.d[rel];
             if (!have_c) xval = V.xs[1][rel];
         }
-        y[row0 + j * S] = pat_epilogue<MODE, TV>(acc[j], xval, bval, dval);
+        lines_store<TV>(y, row0 + j * S, pat_epilogue<MODE, TV>(acc[j], xval, bval, dval), pp);
     }
 }
 template <typename TV>
@@ -707,7 +716,7 @@ __host__ __device__ __forceinline__ LinesView<TV> lines_global_view(long long S2
 // (a) global-memory form: persistent grid-stride over the flattened (group, column) index
 template <typename TA, typename TV, int MODE, bool DPAT, int R>
 __global__ void __launch_bounds__(256)
-pat_lines_kernel(long long S, long long S2, long long n_rows, long long total, const uint16_t* __restrict__ pid,
+pat_lines_kernel(const __grid_constant__ PutPlan pp, long long S, long long S2, long long n_rows, long long total, const uint16_t* __restrict__ pid,
                  const int* __restrict__ pat_off, const PatEntry<TA>* __restrict__ ent, const int* __restrict__ mask,
                  const TV* __restrict__ dpat, const TV* __restrict__ x, const TV* __restrict__ b, const TV* __restrict__ d,
                  TV* __restrict__ y) {
@@ -715,7 +724,7 @@ pat_lines_kernel(long long S, long long S2, long long n_rows, long long total, c
     for (long long f = blockIdx.x * (long long)blockDim.x + threadIdx.x; f < total; f += (long long)gridDim.x * blockDim.x) {
         const long long q = f / S;
         const long long row0 = q * R * S + (f - q * S);
-        pat_lines_thread<TA, TV, MODE, DPAT, R>(S, S2, n_rows, V, row0, row0, pat_off, ent, mask, dpat, y);
+        pat_lines_thread<TA, TV, MODE, DPAT, R>(S, S2, n_rows, V, row0, row0, pat_off, ent, mask, dpat, y, &pp);
     }
 }
 
@@ -774,7 +783,7 @@ __host__ __device__ inline LinesView<TV> lines_stage_view(long long S2, const Li
 }
 template <typename TA, typename TV, int MODE, bool DPAT, int R, int NTMAX>
 __global__ void __launch_bounds__(NTMAX)
-pat_lines_tma_kernel(long long S, long long S2, long long n_rows, int Q, long long ntiles, long long xlo, long long xhi,
+pat_lines_tma_kernel(const __grid_constant__ PutPlan pp, long long S, long long S2, long long n_rows, int Q, long long ntiles, long long xlo, long long xhi,
                      const uint16_t* __restrict__ pid, const int* __restrict__ pat_off, const PatEntry<TA>* __restrict__ ent,
                      const int* __restrict__ mask, const TV* __restrict__ dpat, const TV* __restrict__ x,
                      const TV* __restrict__ b, const TV* __restrict__ d, TV* __restrict__ y) {
@@ -829,7 +838,7 @@ pat_lines_tma_kernel(long long S, long long S2, long long n_rows, int Q, long lo
         if (grp < Q) {
             const LinesView<TV> V = lines_stage_view<TV>(S2, T, sx, xcap, sb, sd, sp);
             const long long rel0 = grp * R * S + col;
-            pat_lines_thread<TA, TV, MODE, DPAT, R>(S, S2, n_rows, V, rel0, T.T0 + rel0, pat_off, ent, mask, dpat, y);
+            pat_lines_thread<TA, TV, MODE, DPAT, R>(S, S2, n_rows, V, rel0, T.T0 + rel0, pat_off, ent, mask, dpat, y, &pp);
         }
         __syncthreads();
     }
