@@ -454,6 +454,9 @@ def run_ours(args):
                                       "put+poll kernel per exchange); cycle incl. exchanges replayed from a CUDA graph"
                                       if dinfo["p2p"] else "ncclSend/ncclRecv"))},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "spmv": spmv,
+        "kernel_options": {k: os.environ[k] for k in ("MGB200_LINES", "MGB200_LINES_STAGED", "MGB200_GRID_TRANSFERS",
+                                                      "MGB200_TMA", "MGB200_TMA_GAP", "MGB200_PATTERNS", "MGB200_GRAPHS",
+                                                      "MGB200_FUSED_PUT", "MGB200_OVERLAP") if k in os.environ},
         "kernels": kern[:10],
     }
     if rank == 0 and world == 1 and not args.no_cpu:

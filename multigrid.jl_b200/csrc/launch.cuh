@@ -218,7 +218,7 @@ static bool launch_pattern_lines(Context& ctx, const Csr<TV>& M, int mode, const
 // grid-hinted transfer kernels (grid_xfer.cuh): P in mode ADD, R in mode SPMV, one right-hand side; off unless the
 // option "grid_transfers" (MGB200_GRID_TRANSFERS) holds the coarse lines per thread (1, 2 or 4)
 template <typename TA, typename TV>
-static bool launch_grid_xfer(Context& ctx, const Csr<TA>& M, int mode, const TV* x, TV* y) {
+static bool launch_grid_xfer(Context& ctx, const Csr<TA>& M, int mode, const TV* x, TV* y, bool dry = false) {
     if constexpr (VT<TA>::is_complex) {
         return false;     // P and R are real (SA-AMG.jl:9-10, MGsetup.jl:80-81): no complex instantiation
     } else {
@@ -226,6 +226,7 @@ static bool launch_grid_xfer(Context& ctx, const Csr<TA>& M, int mode, const TV*
     const int R = ctx.grid_transfers;
     if (!X.ok || !M.pat.present || (R != 1 && R != 2 && R != 4) || x == y) return false;
     if (!((X.kind == 1 && mode == MODE_ADD) || (X.kind == 2 && mode == MODE_SPMV))) return false;
+    if (dry) return true;      // the caller only asks whether this kernel will run (byte accounting)
     const long long total = (long long)X.N[2] * ((X.N[1] + R - 1) / R) * X.N[0];
     const int grid = (int)std::min<long long>((total + 255) / 256, (long long)ctx.sm_count * (R == 4 ? 3 : 6));
 #define MGB_GX(KIND, RR) gx_kernel<TA, TV, KIND, RR><<<grid, 256, 0, ctx.stream>>>(X, total, M.pat.ent, x, y)
@@ -309,9 +310,12 @@ static void csr_apply(Context& ctx, const Csr<TA>& M, int mode, const TV* x, con
     MGB_CHECK(M.present(), "matrix not uploaded");
     const bool use_pat = M.pat.present && m == 1 && ctx.use_patterns;
     MGB_CHECK(!pp.on || use_pat, "fused put needs the stencil-dictionary format");
-    const double fmt = use_pat ? M.pat.matrix_bytes(M.n_rows) + vec_bytes<TA, TV>(M, mode, m, dpat != nullptr) : -1.0;
+    const bool use_gx = use_pat && !pp.on && ctx.grid_transfers > 0 && launch_grid_xfer<TA, TV>(ctx, M, mode, x, y, true);
+    // bytes the device format really streams: the grid-hinted transfer kernels read no matrix stream at all
+    const double fmt = use_gx ? vec_bytes<TA, TV>(M, mode, m, false)
+                              : (use_pat ? M.pat.matrix_bytes(M.n_rows) + vec_bytes<TA, TV>(M, mode, m, dpat != nullptr) : -1.0);
     Launch L(ctx, kind, level, csr_bytes<TA, TV>(M, mode, m), fmt);
-    if (use_pat && !pp.on && ctx.grid_transfers > 0 && launch_grid_xfer<TA, TV>(ctx, M, mode, x, y)) return;
+    if (use_gx && launch_grid_xfer<TA, TV>(ctx, M, mode, x, y)) return;
     if (use_pat && ctx.split_test > 0 && M.n_rows > 2 * ctx.split_test) {
         // test hook (mgb200_set_option "split_test"): the split launch sequence of the multi-GPU overlap path
         pattern_apply_split<TA, TV>(ctx, M, mode, x, b, d, dpat, y, ctx.split_test, M.n_rows - ctx.split_test, 16384, [] {}, pp);
