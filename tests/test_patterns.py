@@ -374,3 +374,47 @@ def test_grid_hinted_transfers_bit_identical(kind, n, cycle, R):
     x0, r0, it0, _ = _solve(kind, n, 3, cycle, dict(base, MGB200_GRID_TRANSFERS="0"))
     x1, r1, it1, _ = _solve(kind, n, 3, cycle, dict(base, MGB200_GRID_TRANSFERS=R))
     assert it0 == it1 and np.array_equal(r0, r1) and np.array_equal(x0, x1)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_line_blocked_kernel_code_fuzz(seed):
+    """Random box stencils - arbitrary subsets of the 27 offsets (upwind-like one-sided ones, stencils without a centre
+    entry, different ones near the boundaries), random grid sizes with tiny dimensions: the line-blocked kernel code
+    (global and staged form) must equal the dictionary walk bit for bit whenever the box structure is detected."""
+    from multigrid_jl_b200 import device
+    rng = np.random.default_rng(1000 + seed)
+    dim = 3 if seed % 3 else 2
+    n = [int(rng.integers(4, 14)) for _ in range(dim)] + [1] * (3 - dim)
+    n[0] = int(rng.integers(5, 40))
+    N = n[0] * n[1] * n[2]
+    S, S2 = n[0], n[0] * n[1]
+    offs = [(dz, dy, dx) for dz in ((-1, 0, 1) if dim == 3 else (0,)) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+    keep = [o for o in offs if rng.random() < 0.6]
+    if not any(o[2] != 0 for o in keep):
+        keep.append((0, 0, 1))
+    if not any(o[1] != 0 for o in keep):
+        keep.append((0, 1, 0))
+    vals = {o: float(rng.standard_normal()) for o in keep}
+    rows, cols, data = [], [], []
+    idx = np.arange(N)
+    i, j, k = idx % n[0], (idx // n[0]) % n[1], idx // S2
+    for (dz, dy, dx) in keep:
+        ok = (i + dx >= 0) & (i + dx < n[0]) & (j + dy >= 0) & (j + dy < n[1]) & (k + dz >= 0) & (k + dz < n[2])
+        # a second value on the first plane / line makes more patterns than the pure boundary classes
+        v = np.where((j == 0) | (k == 0), vals[(dz, dy, dx)] * 1.5, vals[(dz, dy, dx)])
+        rows.append(idx[ok]); cols.append(idx[ok] + dx + S * dy + S2 * dz); data.append(v[ok])
+    A = sp.csr_matrix((np.concatenate(data), (np.concatenate(rows), np.concatenate(cols))), shape=(N, N))
+    A.sort_indices()
+    mat = sp.csc_matrix(A.T)          # the hierarchy stores the transpose (CSC arrays = CSR arrays of the operator)
+    x, b, d = rng.standard_normal(N), rng.standard_normal(N), rng.standard_normal(N)
+    ref = device.host_lines_apply(mat, 3, 0, x, b, d, False)
+    if ref is None:
+        # no dictionary (too few rows per pattern) or an offset set that fits no (S, S2): nothing to compare
+        return
+    np.testing.assert_allclose(ref[0], x + d * (b - A @ x), rtol=1e-12, atol=1e-12)
+    for R in (2, 4):
+        for Q in (0, 1, 2):
+            for mode in (0, 2, 3):
+                r0 = device.host_lines_apply(mat, mode, 0, x, b, d, False)
+                got = device.host_lines_apply(mat, mode, R, x, b, d, False, groups_per_tile=Q)
+                assert got is not None and np.array_equal(r0[0].view(np.int64), got[0].view(np.int64)), (n, keep, R, Q, mode)
