@@ -23,3 +23,7 @@ for R in 1 2 4; do
   cut -c1-200 gpurun_out/bench_n1_gx$R.json
   grep "per-kernel" gpurun_out/bench_n1_gx$R.log | cut -c1-900
 done
+# full ncu capture of the new kernels inside the bench (edit the options to the winners of the runs above)
+MGB200_LINES=4 MGB200_GRID_TRANSFERS=2 timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off \
+    -k regex:'pat_lines|gx_kernel' -c 12 -f -o gpurun_out/lines_gx_full python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/bench_ncu_lines.log 2>&1
+echo "ncu exit $?"
