@@ -93,7 +93,9 @@ int mgb200_upload_coarsest_gmres(mgb200_handle h, int64_t n, const int64_t* colp
 int mgb200_create_mixed(mgb200_handle* outer, mgb200_handle inner);
 
 /* Optional: the matrix the Krylov drivers multiply with when it is not As[1]
- * (solveCG_MG(AT,param,...) takes AT separately, SolveFuncs.jl:77-82).  CSC of A^H. */
+ * (solveCG_MG(AT,param,...) takes AT separately, SolveFuncs.jl:77-82).  CSC of A^H.
+ * colptr == NULL (or n == 0) releases it: the drivers multiply with As[1] again.  The reference builds Afun from the
+ * AT of EVERY call (getAfun, SolveFuncs.jl:65-82), so a front end calls this at the start of every Krylov solve. */
 int mgb200_set_krylov_matrix(mgb200_handle h, int64_t n, const int64_t* colptr, const int64_t* rowval,
                              const void* nzval, int index_base);
 
@@ -239,6 +241,15 @@ int mgb200_set_option(mgb200_handle h, const char* key, int64_t value);
  * mask[p] = presence bits (dz+1)*9 + (dy+1)*3 + (dx+1) of pattern p (caller-allocated, max_patterns). */
 int mgb200_host_detect_box(int64_t n_rows, const int64_t* colptr, const int64_t* rowval, const double* nzval,
                            int index_base, int max_patterns, int max_entries, int64_t* info, int32_t* mask);
+
+/* CPU replay of one launch of the box-stencil kernel (csrc/box.cuh) on a matrix given in the upload format: the
+ * kernel's own tile plan, copy list and per-thread function run on the host, the stages being host buffers filled where
+ * the bulk copies fill shared memory.  Test hook (tests/test_patterns.py); no GPU is used.  x, b, d must carry the 4
+ * elements of slack device vectors have.  info[0] = 1 if the matrix qualifies (else y is untouched), info[1] = stencil
+ * shape (7 or 27), info[2] = patterns, info[3] = rows computed on the constant-coefficient fast path. */
+int mgb200_host_box_apply(int64_t n_rows, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+                          int index_base, int mode, int rows_per_thread, int base_rows, int ctas, int fold_d,
+                          const double* x, const double* b, const double* d, double* y, int64_t* info);
 
 /* Host-only (no GPU): runs the per-thread function of the line-blocked dictionary kernel (csrc/pattern.cuh::
  * pat_lines_thread, __host__ __device__) on the CPU for every thread of a launch - the exact code the GPU executes -

@@ -1,0 +1,440 @@
+// Box-stencil kernel: the fused sweep / residual / product of a square operator whose stencil dictionary has box
+// structure on a lexicographic 3-D grid (detect_box, pattern.cuh: every column offset is dz*S2 + dy*S + dx with
+// dx, dy, dz in {-1, 0, 1}).  The geometric hierarchies of the reference (MGsetup.jl:94-111: 7-point fine operators,
+// 27-point Galerkin products, or rediscretised 7-point operators on every level) are exactly that.
+//
+// Why another kernel: the dictionary walk of pat_tma_kernel (pattern.cuh) spends ~145 warp instructions per 32 rows of
+// the 7-point level - header, loop, entry loads with their offsets - and is bound by issue slots and shared-memory
+// wavefronts, not by DRAM (profiles/r01i_ncu_full_dictionary_kernels_summary.txt).  Here the stencil SHAPE is a
+// compile-time constant (the 7-point star or the full 27-point box), so the product chain is fully unrolled with
+// immediate offsets, and the dictionary becomes a DENSE coefficient table coef[k][pattern] with zeros where a
+// boundary pattern has no entry.  Adding 0 * x[..] leaves a sum unchanged bit for bit (the skipped neighbour of a
+// boundary row is a finite element of the staged window), so one thread still accumulates one row in stored
+// (dz, dy, dx) order and the results are bit-identical to pat_kernel and to the CPU oracle.
+//  * Warps whose rows all carry the dominant (interior) pattern take the coefficients from the kernel parameter, i.e.
+//    straight from the constant bank as instruction operands: no coefficient loads at all.
+//  * A thread owns RZ rows that are one plane apart (rows r, r + S2, ...): the x values of a plane are loaded once
+//    for the (up to) three rows that multiply them, and a tile needs RZ + 2 plane windows for RZ planes of rows
+//    instead of 3 for 1.  Planes are visited in ascending order, which IS stored order for every row.
+// Staging is as in pat_tma_kernel: one bulk copy (cp.async.bulk + mbarrier) per plane window, plus the b / d / pattern
+// id tiles; persistent CTAs, STAGES = 2 (copies of tile i+1 fly while tile i is computed) or 1 (several CTAs per SM
+// cover each other's copies).
+// The per-thread function and the tile plan are __host__ __device__: mgb200_host_box_apply replays a launch on the CPU
+// against host buffers filled exactly where the bulk copies would fill shared memory (tests/test_patterns.py).
+#pragma once
+#include "pattern.cuh"
+
+namespace mgb200 {
+
+constexpr int BOX_MAX_RZ = 4;
+constexpr int BOX_MAX_PAT = 64;      // patterns of a dense coefficient table (27 boundary classes on a box grid)
+
+// stencil shapes: 7 = star (centre, +-1 in each direction), 27 = full box.  Entry index k of (dz,dy,dx) in stored order.
+template <int SHAPE>
+__host__ __device__ constexpr bool box_has(int dz, int dy, int dx) {
+    return SHAPE == 27 ? true : ((dz != 0) + (dy != 0) + (dx != 0) <= 1);
+}
+template <int SHAPE>
+__host__ __device__ constexpr int box_k(int dz, int dy, int dx) {
+    if (SHAPE == 27) return (dz + 1) * 9 + (dy + 1) * 3 + (dx + 1);
+    // star, ascending column order: (-1,0,0) (0,-1,0) (0,0,-1) (0,0,0) (0,0,1) (0,1,0) (1,0,0)
+    return dz < 0 ? 0 : (dz > 0 ? 6 : (dy < 0 ? 1 : (dy > 0 ? 5 : 3 + dx)));
+}
+constexpr int BOX_STAR_MASK = (1 << 4) | (1 << 10) | (1 << 12) | (1 << 13) | (1 << 14) | (1 << 16) | (1 << 22);
+
+// coefficients of the dominant pattern: a kernel parameter, so the fast path reads them from the constant bank
+template <typename TV>
+struct BoxCoef {
+    TV c[27];
+    TV d0;       // folded relaxation weight of the dominant pattern (DPAT)
+};
+
+// (32-bit on purpose: the issuing warp plans every tile with these; the launcher checks that n_rows + 2 S2 fits)
+struct BoxPlan {
+    int n_rows;
+    int S, S2;              // line / plane length of the grid
+    int plane;              // rows per plane of the tiling: S2, or n_rows when a thread owns one row (RZ == 1)
+    int nplanes;            // planes of the tiling: n_rows / S2, or 1
+    int xlo, xhi;           // elements of an input vector that may be copied: [xlo, xhi), multiples of the copy granule
+    int ntiles;
+    int nchunk;             // chunks of NB base rows per plane
+    int npat, NP, p0;       // patterns, leading dimension of the coefficient table, dominant pattern
+    int wlo[BOX_MAX_RZ + 2], whi[BOX_MAX_RZ + 2];   // window w holds offsets [wlo, NB - 1 + whi] around its centre rows
+    int sbase[BOX_MAX_RZ + 2];                      // first element of window w in a stage
+    int xtotal;             // elements of all windows of a stage
+};
+
+template <typename TV>
+__host__ __device__ constexpr int box_al() { return sizeof(TV) >= 8 ? 2 : 4; }   // elements per 16 bytes (tma_align)
+
+// host: windows of a tile for SHAPE / RZ / NB
+template <typename TV>
+static inline void box_make_plan(BoxPlan& P, int shape, int RZ, int NB, long long n_rows, long long S, long long S2,
+                                 long long xlo, long long xhi, int npat, int p0) {
+    constexpr int AL = box_al<TV>();
+    std::memset(&P, 0, sizeof(P));
+    P.n_rows = (int)n_rows;
+    P.S = (int)S;
+    P.S2 = (int)S2;
+    P.plane = (int)(RZ == 1 ? n_rows : S2);
+    P.xlo = (int)xlo;
+    P.xhi = (int)xhi;
+    P.nchunk = (P.plane + NB - 1) / NB;
+    P.nplanes = (int)((n_rows + P.plane - 1) / P.plane);
+    const long long nt = (long long)((P.nplanes + RZ - 1) / RZ) * P.nchunk;
+    P.ntiles = nt < (1LL << 31) ? (int)nt : 0;
+    P.npat = npat;
+    P.NP = (npat + 1) & ~1;
+    P.p0 = p0;
+    int sb = 0;
+    for (int w = 0; w < RZ + 2; ++w) {
+        const bool inner = (w >= 1 && w <= RZ);
+        const int span = (shape == 27 || inner) ? (int)(S + 1) : 0;
+        P.wlo[w] = -span;
+        P.whi[w] = span;
+        P.sbase[w] = sb;
+        sb += (NB + 2 * span + 2 * AL + AL - 1) / AL * AL;
+    }
+    P.xtotal = sb;
+}
+template <typename TV>
+__host__ __device__ inline size_t box_stage_bytes(const BoxPlan& P, int RZ, int NB, bool need_b, bool need_d) {
+    constexpr int AL = box_al<TV>();
+    const size_t bcap = NB + 2 * AL, pcap = NB + 16;
+    const size_t bytes = ((size_t)P.xtotal + (need_b ? RZ * bcap : 0) + (need_d ? RZ * bcap : 0)) * sizeof(TV) + RZ * pcap * 2;
+    return 128 /* BOX_DESC_BYTES */ + (bytes + 127) / 128 * 128;
+}
+template <typename TV>
+__host__ __device__ inline size_t box_head_bytes(const BoxPlan& P, int nk) {
+    return ((64 + ((size_t)nk * P.NP + P.NP) * sizeof(TV)) + 127) / 128 * 128;
+}
+
+// One copy of a tile: `bytes` from global element `src` (of array `what`: 0 x, 1 b, 2 d, 3 pid) to byte offset `dst`
+// of the stage's data part; bytes == 0: nothing to copy.  `off` is the element index (within its region of the stage)
+// of thread 0's element: xoff[w] for a window, boff[j] / poff[j] for the row tiles.
+struct BoxCopy {
+    int src;
+    unsigned dst, bytes;
+    int what, off;
+};
+__host__ __device__ inline int box_floor(int a, int al) { return a & ~(al - 1); }
+__host__ __device__ inline int box_ceil(int a, int al) { return (a + al - 1) & ~(al - 1); }
+__host__ __device__ constexpr int box_ncopies(int RZ, bool need_b, bool need_d) {
+    return RZ + 2 + RZ * (1 + (need_b ? 1 : 0) + (need_d ? 1 : 0));
+}
+// geometry of tile (plane group g, chunk c): first row, base rows, row-planes that exist
+__host__ __device__ inline void box_tile_rows(const BoxPlan& P, int RZ, int NB, int g, int c, int& r0, int& nb, int& nrp) {
+    const int c0 = c * NB;
+    r0 = g * RZ * P.plane + c0;
+    nb = P.plane - c0 < NB ? P.plane - c0 : NB;
+    const int left = P.nplanes - g * RZ;               // RZ > 1: n_rows is a multiple of S2 (launcher)
+    nrp = left < RZ ? left : RZ;
+}
+// Copy number i of the tile, i < box_ncopies: the windows 0 .. RZ+1 first, then per row-plane j the b tile, the d tile
+// and the pattern ids.  Every lane of the issuing warp computes one of them.
+template <typename TV>
+__host__ __device__ inline BoxCopy box_one_copy(const BoxPlan& P, int RZ, int NB, bool need_b, bool need_d, int r0, int nb,
+                                                int nrp, int i) {
+    constexpr int AL = box_al<TV>();
+    BoxCopy C;
+    C.bytes = 0;
+    C.src = 0;
+    C.dst = 0;
+    const int bcap = NB + 2 * AL, pcap = NB + 16;
+    if (i < RZ + 2) {
+        const int w = i;
+        C.what = 0;
+        const int centre = r0 + (w - 1) * P.S2;
+        const int a0 = box_floor(centre + P.wlo[w], AL);
+        C.off = P.sbase[w] + (centre - a0);
+        if (w - 2 >= nrp) return C;            // none of the window's (up to three) row-planes exists
+        int a = a0, e = box_ceil(centre + nb + P.whi[w], AL);
+        if (a < P.xlo) a = P.xlo;
+        if (e > P.xhi) e = P.xhi;
+        if (e <= a) return C;
+        C.src = a;
+        C.dst = (unsigned)((P.sbase[w] + (a - a0)) * sizeof(TV));
+        C.bytes = (unsigned)((e - a) * sizeof(TV));
+        return C;
+    }
+    const int per = 1 + (need_b ? 1 : 0) + (need_d ? 1 : 0);
+    const int j = (i - (RZ + 2)) / per, k = (i - (RZ + 2)) - j * per;     // k: 0 pid, then b, then d
+    const int r = r0 + j * P.S2;
+    const size_t boff_bytes = (size_t)P.xtotal * sizeof(TV);
+    const size_t doff_bytes = boff_bytes + (need_b ? (size_t)RZ * bcap * sizeof(TV) : 0);
+    const size_t poff_bytes = doff_bytes + (need_d ? (size_t)RZ * bcap * sizeof(TV) : 0);
+    if (k == 0) {
+        const int a8 = box_floor(r, 8);
+        C.what = 3;
+        C.off = j * pcap + (r - a8);
+        if (j >= nrp) return C;
+        int e8 = box_ceil(r + nb, 8);
+        const int n8 = box_ceil(P.n_rows, 8);
+        if (e8 > n8) e8 = n8;
+        C.src = a8;
+        C.dst = (unsigned)(poff_bytes + (size_t)j * pcap * 2);
+        C.bytes = (unsigned)((e8 - a8) * 2);
+        return C;
+    }
+    const bool is_b = need_b && k == 1;
+    const int a = box_floor(r, AL);
+    C.what = is_b ? 1 : 2;
+    C.off = j * bcap + (r - a);
+    if (j >= nrp) return C;
+    int e = box_ceil(r + nb, AL);
+    const int nal = box_ceil(P.n_rows, AL);
+    if (e > nal) e = nal;
+    C.src = a;
+    C.dst = (unsigned)((is_b ? boff_bytes : doff_bytes) + (size_t)j * bcap * sizeof(TV));
+    C.bytes = (unsigned)((e - a) * sizeof(TV));
+    return C;
+}
+
+// One thread: RZ rows one plane apart.  xc[w]: the thread's centre element of window w; coefficients from C0 (FAST: every
+// row of the warp carries the dominant pattern) or from the dense table ctab[k * NP + pattern].
+template <typename TV, int SHAPE, int MODE, bool DPAT, int RZ, bool FAST>
+__host__ __device__ __forceinline__ void box_thread(const BoxCoef<TV>& C0, const TV* ctab, const TV* dtab, int NP, int S,
+                                                    const TV* const* xc, const TV* const* bp, const TV* const* dp,
+                                                    const int* pat, TV* out) {
+    TV acc[RZ], xcen[RZ];
+#pragma unroll
+    for (int j = 0; j < RZ; ++j) {
+        acc[j] = VT<TV>::zero();
+        xcen[j] = VT<TV>::zero();
+    }
+#pragma unroll
+    for (int w = 0; w < RZ + 2; ++w) {
+        const bool inner = (w >= 1 && w <= RZ);
+        const TV* q = xc[w];
+        TV X[3][3];
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const bool need = SHAPE == 27 || (dy == 0 && dx == 0) || (inner && (dy == 0 || dx == 0));
+                if (need) X[dy + 1][dx + 1] = q[dy * S + dx];
+            }
+#pragma unroll
+        for (int j = 0; j < RZ; ++j) {
+            const int dz = w - 1 - j;
+            if (dz < -1 || dz > 1) continue;
+            if (dz == 0) xcen[j] = X[1][1];
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                for (int dx = -1; dx <= 1; ++dx) {
+                    if (!box_has<SHAPE>(dz, dy, dx)) continue;
+                    const int k = box_k<SHAPE>(dz, dy, dx);
+                    const TV cf = FAST ? C0.c[k] : ctab[k * NP + pat[j]];
+                    acc[j] = acc[j] + cf * X[dy + 1][dx + 1];
+                }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < RZ; ++j) {
+        TV bval = VT<TV>::zero(), dval = VT<TV>::zero();
+        if (MODE == 2 || MODE == 3) bval = *bp[j];
+        if (MODE == 3) dval = DPAT ? (FAST ? C0.d0 : dtab[pat[j]]) : *dp[j];
+        out[j] = pat_epilogue<MODE, TV>(acc[j], xcen[j], bval, dval);
+    }
+}
+
+// Stage layout: [descriptor, 128 bytes][x windows][b tiles][d tiles][pattern ids].  The descriptor is written by the
+// issuing warp before it arms the mbarrier and holds what every thread needs of the tile's geometry.
+constexpr int BOX_DESC_BYTES = 128;
+struct BoxDesc {
+    int r0, pad_;
+    int nb, nrp;
+    int xoff[BOX_MAX_RZ + 2];
+    int boff[BOX_MAX_RZ];
+    int poff[BOX_MAX_RZ];
+};
+static_assert(sizeof(BoxDesc) <= BOX_DESC_BYTES, "descriptor does not fit its slot");
+
+template <typename TV, int SHAPE, int MODE, bool DPAT, int RZ, int NB, int STAGES>
+__global__ void __launch_bounds__(NB)
+box_kernel(const __grid_constant__ BoxPlan P, const __grid_constant__ BoxCoef<TV> C0, const __grid_constant__ PutPlan pp,
+           const uint16_t* __restrict__ pid, const TV* __restrict__ ctab_g, const TV* __restrict__ dtab_g,
+           const TV* __restrict__ x, const TV* __restrict__ b, const TV* __restrict__ d, TV* __restrict__ y) {
+    constexpr bool NEED_B = (MODE == 2 || MODE == 3);
+    constexpr bool NEED_D = (MODE == 3 && !DPAT);
+    constexpr int NK = SHAPE == 27 ? 27 : 7;
+    constexpr int AL = box_al<TV>();
+    constexpr int BCAP = NB + 2 * AL;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+    TV* ctab = reinterpret_cast<TV*>(smem_raw + 64);
+    TV* dtab = ctab + (size_t)NK * P.NP;
+    unsigned char* stage0 = smem_raw + box_head_bytes<TV>(P, NK);
+    const unsigned stage_bytes = (unsigned)box_stage_bytes<TV>(P, RZ, NB, NEED_B, NEED_D);
+    const int t = threadIdx.x;
+    if (t == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(full + s, 1);
+        fence_mbar_init();
+    }
+    for (int i = t; i < NK * P.NP; i += NB) ctab[i] = ctab_g[i];
+    for (int i = t; i < P.NP; i += NB) dtab[i] = (MODE == 3 && DPAT) ? dtab_g[i] : VT<TV>::zero();
+    // elements of a window that no copy fills (beyond the ends of the vector) are multiplied by zero coefficients:
+    // they must be finite, so the stages start out as zeros
+    {
+        uint4* z = reinterpret_cast<uint4*>(stage0);
+        const unsigned nz = (unsigned)STAGES * stage_bytes / 16;
+        for (unsigned i = t; i < nz; i += NB) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    const int ntiles = P.ntiles;
+    // Warp 0 issues the copies of a tile: every lane plans ONE copy (a window, or a b / d / pattern-id tile) and writes
+    // its entry of the stage's descriptor, lane 0 arms the mbarrier with the byte total, then the lanes issue their
+    // copies (a copy that completes before the barrier is armed only makes the transaction count negative for a
+    // moment: the phase cannot complete before lane 0 has arrived).  The warp walks (plane group, chunk) of its tiles
+    // without dividing.
+    constexpr int NCP = box_ncopies(RZ, NEED_B, NEED_D);
+    constexpr int PER = NCP - (RZ + 2) > 0 ? (NCP - (RZ + 2)) / RZ : 1;
+    static_assert(NCP <= 32, "one copy per lane of the issuing warp");
+    int ig = 0, ic = 0;
+    auto advance = [&](int by) {
+        ic += by;
+        while (ic >= P.nchunk) {
+            ic -= P.nchunk;
+            ++ig;
+        }
+    };
+    auto issue = [&](int s) {            // all lanes of warp 0
+        unsigned char* st = stage0 + (size_t)s * stage_bytes;
+        BoxDesc* D = reinterpret_cast<BoxDesc*>(st);
+        int r0, nb, nrp;
+        box_tile_rows(P, RZ, NB, ig, ic, r0, nb, nrp);
+        BoxCopy C;
+        C.bytes = 0;
+        C.what = -1;
+        if (t < NCP) {
+            C = box_one_copy<TV>(P, RZ, NB, NEED_B, NEED_D, r0, nb, nrp, t);
+            if (C.what == 0) D->xoff[t] = C.off;
+            else if (C.what == 3) D->poff[(t - (RZ + 2)) / PER] = C.off;
+            else if (C.what == 1 || (!NEED_B && C.what == 2)) D->boff[(t - (RZ + 2)) / PER] = C.off;
+        }
+        if (!NEED_B && !NEED_D && t < RZ) D->boff[t] = 0;
+        if (t == 0) {
+            D->r0 = r0;
+            D->nb = nb;
+            D->nrp = nrp;
+        }
+        unsigned total = C.bytes;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+        __syncwarp();
+        if (t == 0) mbar_expect_tx(full + s, total);
+        __syncwarp();
+        if (C.bytes) {
+            const void* src = C.what == 0 ? static_cast<const void*>(x + C.src)
+                              : (C.what == 1 ? static_cast<const void*>(b + C.src)
+                                             : (C.what == 2 ? static_cast<const void*>(d + C.src) : static_cast<const void*>(pid + C.src)));
+            bulk_g2s(st + BOX_DESC_BYTES + C.dst, src, C.bytes, full + s);
+        }
+    };
+    const bool issuer = t < 32;
+    if (issuer) {
+        advance(blockIdx.x);
+        if ((int)blockIdx.x < ntiles) issue(0);
+    }
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int s = STAGES == 2 ? (it & 1) : 0;
+        if (STAGES == 2 && issuer && tile + (int)gridDim.x < ntiles) {
+            advance(gridDim.x);
+            issue(s ^ 1);
+        }
+        const unsigned char* st = stage0 + (size_t)s * stage_bytes;
+        const BoxDesc* D = reinterpret_cast<const BoxDesc*>(st);
+        const TV* sx = reinterpret_cast<const TV*>(st + BOX_DESC_BYTES);
+        const TV* sb = sx + P.xtotal;
+        const TV* sd = sb + (NEED_B ? RZ * BCAP : 0);
+        const uint16_t* sp = reinterpret_cast<const uint16_t*>(sd + (NEED_D ? RZ * BCAP : 0));
+        mbar_wait(full + s, STAGES == 2 ? ((it >> 1) & 1) : (it & 1));
+        const int nb = D->nb, nrp = D->nrp;
+        const TV* xc[RZ + 2];
+        const TV* bp[RZ];
+        const TV* dp[RZ];
+        int pat[RZ];
+        bool mine_fast = true;
+#pragma unroll
+        for (int w = 0; w < RZ + 2; ++w) xc[w] = sx + D->xoff[w] + t;
+#pragma unroll
+        for (int j = 0; j < RZ; ++j) {
+            bp[j] = sb + D->boff[j] + t;
+            dp[j] = sd + D->boff[j] + t;
+            const bool ex = t < nb && j < nrp;
+            pat[j] = ex ? (int)sp[D->poff[j] + t] : P.p0;
+            mine_fast = mine_fast && (pat[j] == P.p0);
+        }
+        const bool fast = __all_sync(0xffffffffu, mine_fast);
+        if (t < nb) {
+            TV out[RZ];
+            if (fast) box_thread<TV, SHAPE, MODE, DPAT, RZ, true>(C0, ctab, dtab, P.NP, P.S, xc, bp, dp, pat, out);
+            else box_thread<TV, SHAPE, MODE, DPAT, RZ, false>(C0, ctab, dtab, P.NP, P.S, xc, bp, dp, pat, out);
+            const int row0 = D->r0 + t;
+#pragma unroll
+            for (int j = 0; j < RZ; ++j)
+                if (j < nrp) {
+                    const int row = row0 + j * P.S2;
+                    y[row] = out[j];
+                    if (pp.on) ll_put_edge<TV>(pp, row, out[j]);
+                }
+        }
+        __syncthreads();
+        if (STAGES == 1 && issuer && tile + (int)gridDim.x < ntiles) {
+            advance(gridDim.x);
+            issue(0);
+        }
+    }
+}
+
+// ---- host side: dense tables ---------------------------------------------------------------------------------------
+template <typename TV>
+struct BoxDict {
+    bool ok = false;
+    int shape = 0;                 // 7 or 27
+    int npat = 0, NP = 0, p0 = 0;
+    BoxCoef<TV> c0;
+    TV* ctab = nullptr;            // device: coef[k * NP + p]
+    TV* dtab = nullptr;            // device: folded relaxation weights per pattern (set by fold_d), NP elements
+    std::vector<TV> h_ctab;        // host copies (the CPU replay, tests)
+    void release() {
+        if (ctab) cudaFree(ctab);
+        if (dtab) cudaFree(dtab);
+        ctab = dtab = nullptr;
+        ok = false;
+        h_ctab.clear();
+    }
+};
+// dense table of a box-structured dictionary; false when the shape is not one the kernel is instantiated for
+template <typename TV>
+static bool box_build_tables(const HostPatterns<TV>& H, const BoxInfo& B, long long n_rows, int& shape, int& NP, int& p0,
+                             std::vector<TV>& tab, BoxCoef<TV>& c0) {
+    if (!B.ok || B.S < 3 || B.S2 < 3 * B.S || H.npat() > BOX_MAX_PAT) return false;
+    int U = 0;
+    for (int m : B.mask) U |= m;
+    shape = (U & ~BOX_STAR_MASK) == 0 ? 7 : 27;
+    const int nk = shape;
+    NP = (H.npat() + 1) & ~1;
+    tab.assign((size_t)nk * NP, VT<TV>::zero());
+    for (int p = 0; p < H.npat(); ++p) {
+        int e = H.pat_off[p];
+        for (int bit = 0; bit < 27; ++bit) {
+            if (!(B.mask[p] & (1 << bit))) continue;
+            const int dz = bit / 9 - 1, dy = (bit / 3) % 3 - 1, dx = bit % 3 - 1;
+            const int k = shape == 27 ? box_k<27>(dz, dy, dx) : box_k<7>(dz, dy, dx);
+            tab[(size_t)k * NP + p] = H.val[e++];
+        }
+        if (e != H.pat_off[p + 1]) return false;
+    }
+    std::vector<long long> cnt(H.npat(), 0);
+    for (long long r = 0; r < n_rows; ++r) cnt[H.pid[r]]++;
+    p0 = (int)(std::max_element(cnt.begin(), cnt.end()) - cnt.begin());
+    std::memset(static_cast<void*>(&c0), 0, sizeof(c0));
+    for (int k = 0; k < nk; ++k) c0.c[k] = tab[(size_t)k * NP + p0];
+    return true;
+}
+
+}  // namespace mgb200

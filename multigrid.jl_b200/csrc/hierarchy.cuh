@@ -12,6 +12,7 @@
 #include "csr_kernels.cuh"
 #include "dense_lu.cuh"
 #include "pattern.cuh"
+#include "box.cuh"
 #include "grid_xfer.cuh"
 #include "vec_kernels.cuh"
 
@@ -98,9 +99,11 @@ struct Csr {
     PatDict<TA> pat;    // stencil-dictionary form (pattern.cuh), when the rows deduplicate
     int int_lo = 0, int_hi = 0;  // row-partitioned levels: rows [int_lo, int_hi) read no ghost row of the input vector
     GridXfer gx{};      // grid hint of a transfer operator (grid_xfer.cuh), ok = 0 unless verified at upload
+    BoxDict<TA> box;    // dense coefficient tables of a box-structured dictionary (box.cuh)
     bool present() const { return rowptr != nullptr; }
     void release() {
         pat.release();
+        box.release();
         gx = no_grid();
         int_lo = int_hi = 0;
         dev_free(rowptr);
@@ -133,6 +136,9 @@ struct Context {
     int lines_min_rows = 50000;
     int lines_staged = 1;          // 1: TMA-staged form of the line-blocked kernel where the lines fit a CTA, 0: global-memory form
     int tma_min_rows = 200000;     // smaller matrices keep the one-pass kernel (too few tiles per SM)
+    int use_box = 1;               // box-stencil kernel (box.cuh) for box-structured square operators (MGB200_BOX)
+    int box_variant = 0;           // (rows per thread, base rows per tile, stages): see launch_box (MGB200_BOX_VARIANT)
+    int box_min_rows = 100000;
     int split_test = 0;            // > 0: every dictionary pass runs as interior + both ends (test hook)
     int use_overlap = 0;           // multi-GPU: halo exchange beside the interior rows (MGB200_OVERLAP=1; measured
                                    // slower than the serial exchange at N = 2, profiles/r01e_bench_n2_*: default off)
@@ -163,6 +169,9 @@ struct Context {
         use_graphs = env_int("MGB200_GRAPHS", 1);
         use_tma = env_int("MGB200_TMA", 1);
         tma_min_rows = env_int("MGB200_TMA_MIN_ROWS", 200000);
+        use_box = env_int("MGB200_BOX", 1);
+        box_variant = env_int("MGB200_BOX_VARIANT", 0);
+        box_min_rows = env_int("MGB200_BOX_MIN_ROWS", 100000);
         lines = env_int("MGB200_LINES", 0);
         grid_transfers = env_int("MGB200_GRID_TRANSFERS", 0);
         lines_min_rows = env_int("MGB200_LINES_MIN_ROWS", 50000);
@@ -344,6 +353,18 @@ static void upload_csr(Context& ctx, Csr<TA>& M, long long n_rows, long long n_c
             upload_patterns<TA>(M.pat, hp, n_rows);
             M.pat.xlo = 0;                               // input vectors hold n_cols elements (+ slack, vec_alloc)
             M.pat.xhi = (long long)align_pad<TA>((size_t)n_cols);
+            if (hp.rowrel && ctx.use_box) {     // box-stencil kernel (box.cuh): dense tables
+                const BoxInfo B = detect_box<TA>(hp, n_rows);
+                BoxDict<TA>& X = M.box;
+                if (box_build_tables<TA>(hp, B, n_rows, X.shape, X.NP, X.p0, X.h_ctab, X.c0)) {
+                    X.npat = hp.npat();
+                    X.ctab = dev_alloc<TA>(X.h_ctab.size());
+                    MGB_CUDA(cudaMemcpy(X.ctab, X.h_ctab.data(), X.h_ctab.size() * sizeof(TA), cudaMemcpyHostToDevice));
+                    X.dtab = dev_alloc<TA>(X.NP);
+                    MGB_CUDA(cudaMemset(X.dtab, 0, X.NP * sizeof(TA)));
+                    X.ok = true;
+                }
+            }
             if (keep) *keep = std::move(hp);      // the caller checks a grid hint against the dictionary
         }
     }

@@ -1,6 +1,8 @@
 // Launch wrappers: pick the kernel instantiation chosen at upload and account the
 // algorithmic bytes of SURVEY.md section 8(d) for every launch.
 #pragma once
+#include <type_traits>
+
 #include "hierarchy.cuh"
 
 namespace mgb200 {
@@ -240,6 +242,64 @@ static bool launch_grid_xfer(Context& ctx, const Csr<TA>& M, int mode, const TV*
     }
 }
 
+// box-stencil kernel (box.cuh): box-structured square operators on a 3-D grid, SPMV / RESID / SWEEP, one right-hand
+// side, double and complex double.  Variants (rows per thread RZ, base rows per tile NB, stages): ctx.box_variant.
+template <typename TV, int RZ, int NB, int STAGES>
+static bool launch_box_variant(Context& ctx, const Csr<TV>& M, int mode, const TV* x, const TV* b, const TV* d,
+                               const TV* dpat, TV* y, const PutPlan& pp) {
+    const BoxDict<TV>& X = M.box;
+    const PatDict<TV>& D = M.pat;
+    BoxPlan P;
+    box_make_plan<TV>(P, X.shape, RZ, NB, M.n_rows, D.S, D.S2, D.xlo, D.xhi, X.npat, X.p0);
+    P.NP = X.NP;
+    if (P.ntiles <= 0 || (long long)M.n_rows + 2LL * D.S2 + NB >= (1LL << 31) || (RZ > 1 && M.n_rows % D.S2 != 0)) return false;
+    const bool need_b = (mode == MODE_RESID || mode == MODE_SWEEP), need_d = (mode == MODE_SWEEP && !dpat);
+    const size_t smem = box_head_bytes<TV>(P, X.shape) + STAGES * box_stage_bytes<TV>(P, RZ, NB, need_b, need_d);
+    if (smem > (size_t)ctx.max_smem_optin) return false;
+#define MGB_BX(SHAPE, MODE, DP)                                                                                      \
+    {                                                                                                                 \
+        auto kern = box_kernel<TV, SHAPE, MODE, DP, RZ, NB, STAGES>;                                                  \
+        MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx.max_smem_optin));        \
+        int per = 0;                                                                                                  \
+        MGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, NB, smem));                                \
+        if (per < 1) return false;                                                                                    \
+        const int grid = (int)std::min<long long>(P.ntiles, (long long)ctx.sm_count * per);                           \
+        kern<<<grid, NB, smem, ctx.stream>>>(P, X.c0, pp, D.pid, X.ctab, X.dtab, x, b, d, y);                         \
+    }
+#define MGB_BXS(MODE, DP) { if (X.shape == 7) MGB_BX(7, MODE, DP) else MGB_BX(27, MODE, DP) }
+    if (mode == MODE_SPMV) MGB_BXS(MODE_SPMV, false)
+    else if (mode == MODE_RESID) MGB_BXS(MODE_RESID, false)
+    else if (dpat) MGB_BXS(MODE_SWEEP, true)
+    else MGB_BXS(MODE_SWEEP, false)
+#undef MGB_BXS
+#undef MGB_BX
+    MGB_LAUNCH_CHECK();
+    return true;
+}
+template <typename TA, typename TV>
+static bool launch_box(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d, const TV* dpat,
+                       TV* y, const PutPlan& pp) {
+    if constexpr (std::is_same<TA, TV>::value && (std::is_same<TV, double>::value || std::is_same<TV, cplx>::value)) {
+        if (!M.box.ok || !ctx.use_box || mode == MODE_ADD || x == y || M.n_rows < ctx.box_min_rows) return false;
+        if ((reinterpret_cast<uintptr_t>(x) & 15) || (b && (reinterpret_cast<uintptr_t>(b) & 15)) ||
+            (d && (reinterpret_cast<uintptr_t>(d) & 15)))
+            return false;
+        constexpr int F = sizeof(TV) / 8;      // complex tiles hold half the rows
+        switch (ctx.box_variant) {
+            case 1: return launch_box_variant<TV, 2, 512 / F, 2>(ctx, M, mode, x, b, d, dpat, y, pp);
+            case 2: return launch_box_variant<TV, 2, 512 / F, 1>(ctx, M, mode, x, b, d, dpat, y, pp);
+            case 3: return launch_box_variant<TV, 4, 256 / F, 1>(ctx, M, mode, x, b, d, dpat, y, pp);
+            case 4: return launch_box_variant<TV, 4, 256 / F, 2>(ctx, M, mode, x, b, d, dpat, y, pp);
+            case 5: return launch_box_variant<TV, 1, 512 / F, 1>(ctx, M, mode, x, b, d, dpat, y, pp);
+            case 6: return launch_box_variant<TV, 2, 1024 / F, 1>(ctx, M, mode, x, b, d, dpat, y, pp);
+            case 7: return launch_box_variant<TV, 1, 1024 / F, 1>(ctx, M, mode, x, b, d, dpat, y, pp);
+            default: return launch_box_variant<TV, 1, 1024 / F, 2>(ctx, M, mode, x, b, d, dpat, y, pp);
+        }
+    } else {
+        return false;
+    }
+}
+
 // one-pass dictionary kernel over the rows [rA, rA + nA) and [rB, rB + nB)
 template <typename TA, typename TV>
 static void launch_pattern_rows(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d,
@@ -273,6 +333,7 @@ static void launch_pattern_rows(Context& ctx, const Csr<TA>& M, int mode, const 
 template <typename TA, typename TV>
 static void launch_pattern_mode(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d,
                                 const TV* dpat, TV* y, const PutPlan& pp = no_put()) {
+    if (launch_box<TA, TV>(ctx, M, mode, x, b, d, dpat, y, pp)) return;
     if (ctx.lines > 0 && launch_pattern_lines(ctx, M, mode, x, b, d, dpat, y, pp)) return;
     if (M.pat.rowrel && launch_pattern_tma<TA, TV>(ctx, M, mode, x, b, d, dpat, y, 0, -1, 0, pp)) return;
     launch_pattern_rows<TA, TV>(ctx, M, mode, x, b, d, dpat, y, 0, M.n_rows, 0, 0, pp);

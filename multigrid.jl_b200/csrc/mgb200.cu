@@ -165,6 +165,66 @@ static void host_tma_plan_impl(const HostPatterns<double>& hp, int tile, int64_t
     }
 }
 
+// CPU replay of a box_kernel launch (box.cuh): the tile plan, the copies and the per-thread function are the
+// kernel's own __host__ __device__ code; the stages are host buffers that persist from tile to tile like shared memory.
+template <int SHAPE, int MODE, bool DPAT, int RZ>
+static void host_box_run(const BoxPlan& P, const BoxCoef<double>& C0, const std::vector<double>& ctab, const std::vector<double>& dtab,
+                         int NB, int ctas, const uint16_t* pid, const double* x, const double* b, const double* d, double* y,
+                         long long* fast_rows) {
+    constexpr bool NEED_B = (MODE == 2 || MODE == 3), NEED_D = (MODE == 3 && !DPAT);
+    const size_t stage_bytes = box_stage_bytes<double>(P, RZ, NB, NEED_B, NEED_D) - BOX_DESC_BYTES;
+    const int bcap = NB + 4;
+    for (int cta = 0; cta < ctas; ++cta) {
+        std::vector<unsigned char> stage(stage_bytes, 0);
+        for (long long tile = cta; tile < P.ntiles; tile += ctas) {
+            int r0, nb, nrp;
+            box_tile_rows(P, RZ, NB, (int)(tile / P.nchunk), (int)(tile % P.nchunk), r0, nb, nrp);
+            struct { int r0; int nb, nrp; int xoff[RZ + 2], boff[RZ], poff[RZ]; } T;
+            T.r0 = r0; T.nb = nb; T.nrp = nrp;
+            for (int j = 0; j < RZ; ++j) T.boff[j] = 0;
+            constexpr int NCP = box_ncopies(RZ, NEED_B, NEED_D);
+            constexpr int PER = (NCP - (RZ + 2)) / RZ;
+            for (int i = 0; i < NCP; ++i) {
+                const BoxCopy C = box_one_copy<double>(P, RZ, NB, NEED_B, NEED_D, r0, nb, nrp, i);
+                if (C.what == 0) T.xoff[i] = C.off;
+                else if (C.what == 3) T.poff[(i - (RZ + 2)) / PER] = C.off;
+                else T.boff[(i - (RZ + 2)) / PER] = C.off;
+                if (!C.bytes) continue;
+                MGB_CHECK((size_t)C.dst + C.bytes <= stage_bytes && C.dst % 16 == 0 && C.bytes % 16 == 0, "copy outside the stage or unaligned");
+                const unsigned char* src = C.what == 0 ? reinterpret_cast<const unsigned char*>(x + C.src)
+                                           : (C.what == 1 ? reinterpret_cast<const unsigned char*>(b + C.src)
+                                                          : (C.what == 2 ? reinterpret_cast<const unsigned char*>(d + C.src)
+                                                                         : reinterpret_cast<const unsigned char*>(pid + C.src)));
+                MGB_CHECK((C.what == 3 ? C.src % 8 : C.src % 2) == 0, "unaligned source of a bulk copy");
+                std::memcpy(stage.data() + C.dst, src, C.bytes);
+            }
+            const double* sx = reinterpret_cast<const double*>(stage.data());
+            const double* sb = sx + P.xtotal;
+            const double* sd = sb + (NEED_B ? RZ * bcap : 0);
+            const uint16_t* sp = reinterpret_cast<const uint16_t*>(sd + (NEED_D ? RZ * bcap : 0));
+            for (int t = 0; t < T.nb; ++t) {
+                const double* xc[RZ + 2];
+                const double* bp[RZ];
+                const double* dp[RZ];
+                int pat[RZ];
+                bool fast = true;
+                for (int w = 0; w < RZ + 2; ++w) xc[w] = sx + T.xoff[w] + t;
+                for (int j = 0; j < RZ; ++j) {
+                    bp[j] = sb + T.boff[j] + t;
+                    dp[j] = sd + T.boff[j] + t;
+                    pat[j] = j < T.nrp ? (int)sp[T.poff[j] + t] : P.p0;
+                    fast = fast && pat[j] == P.p0;
+                }
+                double out[RZ];
+                if (fast) box_thread<double, SHAPE, MODE, DPAT, RZ, true>(C0, ctab.data(), dtab.data(), P.NP, P.S, xc, bp, dp, pat, out);
+                else box_thread<double, SHAPE, MODE, DPAT, RZ, false>(C0, ctab.data(), dtab.data(), P.NP, P.S, xc, bp, dp, pat, out);
+                if (fast) *fast_rows += T.nrp;
+                for (int j = 0; j < T.nrp; ++j) y[T.r0 + t + (long long)j * P.S2] = out[j];
+            }
+        }
+    }
+}
+
 template <int MODE, bool DPAT>
 static long long host_lines_run(const HostPatterns<double>& hp, const BoxInfo& B, long long n_rows, int R, int Q,
                                 const std::vector<PatEntry<double>>& ent, const double* dpat, const double* x,
@@ -599,6 +659,9 @@ int mgb200_set_option(mgb200_handle h, const char* key, int64_t value) {
         else if (k == "smem_budget") H->ctx.smem_budget = (int)value;
         else if (k == "tma") H->ctx.use_tma = (int)value;
         else if (k == "tma_min_rows") H->ctx.tma_min_rows = (int)value;
+        else if (k == "box") H->ctx.use_box = (int)value;
+        else if (k == "box_variant") H->ctx.box_variant = (int)value;
+        else if (k == "box_min_rows") H->ctx.box_min_rows = (int)value;
         else if (k == "lines") H->ctx.lines = (int)value;
         else if (k == "lines_staged") H->ctx.lines_staged = (int)value;
         else if (k == "grid_transfers") H->ctx.grid_transfers = (int)value;
@@ -672,6 +735,55 @@ int mgb200_host_detect_box(int64_t n_rows, const int64_t* colptr, const int64_t*
             for (int p = 0; p < hp.npat(); ++p) mask[p] = B.mask[p];
         }
     }
+    MGB_CATCH
+}
+
+int mgb200_host_box_apply(int64_t n_rows, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+                          int index_base, int mode, int rows_per_thread, int base_rows, int ctas, int fold_d, const double* x,
+                          const double* b, const double* d, double* y, int64_t* info) {
+    MGB_TRY
+    MGB_CHECK(colptr && rowval && nzval && x && y && info, "null argument");
+    MGB_CHECK(mode == 0 || mode == 2 || mode == 3, "mode must be 0, 2 or 3");
+    MGB_CHECK(rows_per_thread == 1 || rows_per_thread == 2 || rows_per_thread == 4, "rows_per_thread must be 1, 2 or 4");
+    MGB_CHECK(base_rows >= 8 && base_rows % 8 == 0 && ctas >= 1, "base_rows must be a multiple of 8");
+    MGB_CHECK(mode == 0 || b, "b required");
+    MGB_CHECK(mode != 3 || d, "d required");
+    info[0] = info[1] = info[2] = info[3] = 0;
+    HostPatterns<double> hp;
+    if (!build_patterns<double>(n_rows, colptr, rowval, nzval, index_base, false, PAT_MAX_PATTERNS, PAT_MAX_ENTRIES, hp)) return 0;
+    if (!hp.rowrel) return 0;
+    const BoxInfo B = detect_box<double>(hp, n_rows);
+    int shape = 0, NP = 0, p0 = 0;
+    std::vector<double> ctab;
+    BoxCoef<double> C0;
+    if (!box_build_tables<double>(hp, B, n_rows, shape, NP, p0, ctab, C0)) return 0;
+    const int RZ = rows_per_thread;
+    if (RZ > 1 && n_rows % B.S2 != 0) return 0;
+    std::vector<double> dtab(NP, 0.0);
+    bool dp = false;
+    if (mode == 3 && fold_d) {
+        dp = true;
+        for (int p = 0; p < hp.npat(); ++p) dtab[p] = d[hp.rep_row[p]];
+        C0.d0 = dtab[p0];
+    }
+    BoxPlan P;
+    box_make_plan<double>(P, shape, RZ, base_rows, n_rows, B.S, B.S2, 0, (n_rows + 1) & ~1LL, hp.npat(), p0);
+    long long fast_rows = 0;
+#define MGB_HB(SHAPE, RR)                                                                                                   \
+    {                                                                                                                       \
+        if (mode == 0) host_box_run<SHAPE, 0, false, RR>(P, C0, ctab, dtab, base_rows, ctas, hp.pid.data(), x, b, d, y, &fast_rows);      \
+        else if (mode == 2) host_box_run<SHAPE, 2, false, RR>(P, C0, ctab, dtab, base_rows, ctas, hp.pid.data(), x, b, d, y, &fast_rows); \
+        else if (dp) host_box_run<SHAPE, 3, true, RR>(P, C0, ctab, dtab, base_rows, ctas, hp.pid.data(), x, b, d, y, &fast_rows);         \
+        else host_box_run<SHAPE, 3, false, RR>(P, C0, ctab, dtab, base_rows, ctas, hp.pid.data(), x, b, d, y, &fast_rows);                \
+    }
+#define MGB_HBR(SHAPE) { if (RZ == 1) MGB_HB(SHAPE, 1) else if (RZ == 2) MGB_HB(SHAPE, 2) else MGB_HB(SHAPE, 4) }
+    if (shape == 7) MGB_HBR(7) else MGB_HBR(27)
+#undef MGB_HBR
+#undef MGB_HB
+    info[0] = 1;
+    info[1] = shape;
+    info[2] = hp.npat();
+    info[3] = fast_rows;
     MGB_CATCH
 }
 

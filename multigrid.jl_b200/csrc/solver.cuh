@@ -275,6 +275,11 @@ struct Hierarchy : HierarchyBase {
         if (!ok) return;
         lv.dpat = dev_alloc<TV>(D.npat);
         MGB_CUDA(cudaMemcpy(lv.dpat, dp.data(), D.npat * sizeof(TV), cudaMemcpyHostToDevice));
+        BoxDict<TV>& X = lv.A.box;
+        if (X.ok) {      // the box-stencil kernel keeps its own (padded) copy and the dominant pattern's weight
+            MGB_CUDA(cudaMemcpy(X.dtab, dp.data(), D.npat * sizeof(TV), cudaMemcpyHostToDevice));
+            X.c0.d0 = dp[X.p0];
+        }
     }
 
     void upload_coarsest(long long n, const int64_t* cp, const int64_t* rv, const void* nz, int base) {
@@ -350,6 +355,10 @@ struct Hierarchy : HierarchyBase {
 
     void set_krylov_matrix(long long n, const int64_t* cp, const int64_t* rv, const void* nz, int base) {
         MGB_CUDA(cudaSetDevice(ctx.device));
+        if (cp == nullptr || n == 0) {   // back to the hierarchy's own fine matrix (getAfun(AT) with AT === As[1])
+            Akry.release();
+            return;
+        }
         MGB_CHECK(n == L[0].n, "Krylov matrix size differs from the fine level");
         upload_csr<TV>(ctx, Akry, n, n, cp, rv, static_cast<const TV*>(nz), base, true);
     }

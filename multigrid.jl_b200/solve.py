@@ -74,11 +74,12 @@ def _same_storage(a, b):
 
 def _krylov_matrix(dev, AT, param):
     """The AT argument of solveCG_MG / solveGMRES_MG (SolveFuncs.jl:77-82): uploaded separately only
-    when it is not the matrix the hierarchy was built from."""
-    if AT is None or AT is param.As[0]:
-        return
+    when it is not the matrix the hierarchy was built from.  The reference builds Afun from the AT of every call
+    (getAfun, SolveFuncs.jl:65-82), so a matrix left behind by an earlier solve is released here."""
     import scipy.sparse as sp
-    if sp.issparse(AT) and AT.format == "csc" and _same_storage(AT, param.As[0]):
+    if (AT is None or AT is param.As[0]
+            or (sp.issparse(AT) and AT.format == "csc" and _same_storage(AT, param.As[0]))):
+        dev.set_krylov_matrix(None)
         return
     dev.set_krylov_matrix(AT)
 

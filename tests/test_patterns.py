@@ -163,6 +163,42 @@ def test_box_structure_rejected():
     assert box is not None and (box["S"], box["S2"]) == (0, 0)
 
 
+@pytest.mark.parametrize("n", [[24, 20, 12], [18, 40, 10], [8, 8, 8], [7, 9, 5]])
+@pytest.mark.parametrize("RZ,NB", [(1, 256), (1, 64), (2, 128), (2, 40), (4, 64), (4, 512)])
+def test_box_kernel_code_on_the_cpu(n, RZ, NB):
+    """csrc/box.cuh: the box-stencil kernel's tile plan, copy list and per-thread function are __host__ __device__.
+    Replayed on the CPU for every tile of a launch (stages = host buffers filled where the bulk copies fill shared
+    memory, zero elsewhere) they must reproduce the one-row-per-thread dictionary walk bit for bit in all modes, on the
+    7-point fine level and the 27-point Galerkin level, for tiles that do and do not divide the planes."""
+    from multigrid_jl_b200 import device
+    A, AT, M, p, b0 = _cpu_problem(n, 2)
+    rng = np.random.default_rng(13)
+    for l in range(2):
+        mat = sp.csc_matrix(p.As[l])
+        N = mat.shape[0]
+        x, b = rng.standard_normal(N), rng.standard_normal(N)
+        d = np.ascontiguousarray(p.relaxPrecs[l]) if l < len(p.relaxPrecs) else 0.8 / mat.diagonal()
+        for mode, fold in ((0, False), (2, False), (3, False), (3, True)):
+            ref = device.host_lines_apply(mat, mode, 0, x, b, d, fold)
+            got = device.host_box_apply(mat, mode, RZ, NB, x, b, d, fold)
+            if ref is None:          # tiny coarse levels are not worth a dictionary
+                assert got is None and N < 8 * 27
+                continue
+            assert got is not None, (l, mode)
+            assert got[1]["shape"] == (7 if l == 0 else 27)
+            assert np.array_equal(ref[0].view(np.int64), got[0].view(np.int64)), (l, mode, fold)
+        if min(n) >= 8 and l == 0 and got is not None:
+            assert got[1]["fast_rows"] > 0.2 * N       # interior rows take the constant-coefficient path
+
+
+def test_box_kernel_rejects_what_it_cannot_do():
+    from multigrid_jl_b200 import device
+    A, AT, M, p, b0 = _cpu_problem([32, 32], 2)          # 2-D: no planes
+    x = np.ones(A.shape[0])
+    assert device.host_box_apply(sp.csc_matrix(p.As[0]), 0, 1, 64, x) is None
+    assert device.host_box_apply(sp.csc_matrix(p.Ps[0]), 0, 1, 64, np.ones(p.Ps[0].shape[1])) is None
+
+
 @pytest.mark.parametrize("n", [[24, 20, 12], [32, 32], [18, 40, 10], [22, 10, 14]])
 @pytest.mark.parametrize("R", [2, 4])
 def test_line_blocked_kernel_code_on_the_cpu(n, R):
@@ -338,6 +374,22 @@ def test_split_launches_bit_identical(kind, n, cycle, tma):
     for rows in ("7", "1500"):
         x1, r1, it1, _ = _solve(kind, n, 3, cycle, dict(base, MGB200_SPLIT_TEST=rows))
         assert it0 == it1 and np.array_equal(r0, r1) and np.array_equal(x0, x1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,n,cycle", [("poisson", [40, 36, 28], 'V'), ("helmholtz", [33, 31, 17], 'W'),
+                                          ("poisson", [64, 64, 64], 'F')])
+@pytest.mark.parametrize("variant", ["0", "1", "2", "3", "4", "5", "6", "7"])
+def test_box_kernel_bit_identical(kind, n, cycle, variant):
+    """csrc/box.cuh: the box-stencil kernel (dense coefficient tables, unrolled 7- / 27-point chains, RZ rows per
+    thread one plane apart) on every box-structured 3-D level instead of the dictionary walk: results must not change
+    by a bit (Float64 and ComplexF64; planes the tiles do and do not divide; d folded and as a vector)."""
+    base = {"MGB200_PATTERNS": "1", "MGB200_GRAPHS": "1", "MGB200_TMA": "1", "MGB200_TMA_MIN_ROWS": "0"}
+    x0, r0, it0, _ = _solve(kind, n, 3, cycle, dict(base, MGB200_BOX="0"))
+    for fold in ("1", "0"):
+        x1, r1, it1, _ = _solve(kind, n, 3, cycle, dict(base, MGB200_BOX="1", MGB200_BOX_MIN_ROWS="0",
+                                                        MGB200_BOX_VARIANT=variant, MGB200_FOLD_D=fold))
+        assert it0 == it1 and np.array_equal(r0, r1) and np.array_equal(x0, x1), fold
 
 
 @pytest.mark.gpu
