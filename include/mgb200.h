@@ -110,6 +110,10 @@ int mgb200_set_cycle(mgb200_handle h, char cycle_type, const int64_t* relax_pre,
 /* x = recursiveCycle(param,b,x,1) (MGcycle.jl:1-118); x is read and overwritten. */
 int mgb200_cycle(mgb200_handle h, const void* b, void* x);
 
+/* The closure getMultigridPreconditioner returns (SolveFuncs.jl:43-63):  z .= 0; recursiveCycle(param,r,z,1); z.
+ * Host buffers like mgb200_cycle, but z is only written: the zero initial guess is not copied to the device. */
+int mgb200_precondition(mgb200_handle h, const void* r, void* z);
+
 /* solveMG (SolveFuncs.jl:3-39).  resvec must hold max_iter+1 doubles: resvec[0] = res_init,
  * resvec[k] = ||b - A x_k|| after cycle k.  *iter = cycles done. */
 int mgb200_solveMG(mgb200_handle h, const void* b, void* x, double tol, int max_iter, int* iter,
@@ -266,7 +270,7 @@ int mgb200_host_lines_apply(int64_t n_rows, const int64_t* colptr, const int64_t
 /* Host-only (no GPU): the grid-hinted transfer kernels' per-thread functions (csrc/grid_xfer.cuh, __host__ __device__) run
  * on the CPU for every thread of a launch, for a real Float64 transfer matrix given by its CSC-of-the-transpose arrays
  * as uploaded (kind 1: Ps[l], y += P x with x coarse, y fine; kind 2: Rs[l], y = R x with x fine, y coarse).
- * lines_per_thread in {1, 2, 4}, or 0 for the dictionary walk (the reference the kernels must match bit for bit).
+ * lines_per_thread != 0: the per-row functions of the kernels; 0: the dictionary walk (the reference they must match bit for bit).
  * info[0] = 1 if the hint matches the matrix (y is then written / updated), else 0 and y is untouched. */
 int mgb200_host_grid_transfer(int kind, int dim, const int64_t* n_fine_nodes, const int64_t* n_coarse_nodes, int64_t n_rows,
                               const int64_t* colptr, const int64_t* rowval, const double* nzval, int index_base,

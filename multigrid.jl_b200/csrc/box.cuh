@@ -18,7 +18,11 @@
 //    instead of 3 for 1.  Planes are visited in ascending order, which IS stored order for every row.
 // Staging is as in pat_tma_kernel: one bulk copy (cp.async.bulk + mbarrier) per plane window, plus the b / d / pattern
 // id tiles; persistent CTAs, STAGES = 2 (copies of tile i+1 fly while tile i is computed) or 1 (several CTAs per SM
-// cover each other's copies).
+// cover each other's copies).  The copy list of every tile is planned ON THE HOST once per (matrix, variant) and kept
+// in device memory as one record per tile (BoxRec: the copies + a descriptor of the tile's geometry): the issuing warp
+// loads one 16-byte copy entry per lane and fires - planning a tile in the kernel (alignment of odd plane lengths,
+// clamping at the ends of the vector) put ~200 dependent instructions in front of every tile's copies and made
+// the issuing warp the critical path (profiles/r02_box_variants.log).
 // The per-thread function and the tile plan are __host__ __device__: mgb200_host_box_apply replays a launch on the CPU
 // against host buffers filled exactly where the bulk copies would fill shared memory (tests/test_patterns.py).
 #pragma once
@@ -102,92 +106,101 @@ __host__ __device__ inline size_t box_stage_bytes(const BoxPlan& P, int RZ, int 
     constexpr int AL = box_al<TV>();
     const size_t bcap = NB + 2 * AL, pcap = NB + 16;
     const size_t bytes = ((size_t)P.xtotal + (need_b ? RZ * bcap : 0) + (need_d ? RZ * bcap : 0)) * sizeof(TV) + RZ * pcap * 2;
-    return 128 /* BOX_DESC_BYTES */ + (bytes + 127) / 128 * 128;
+    return 128 /* BOX_DESC_BYTES */ + (bytes + 127) / 128 * 128;      // [descriptor][x windows][pattern ids][b][d]
 }
 template <typename TV>
 __host__ __device__ inline size_t box_head_bytes(const BoxPlan& P, int nk) {
     return ((64 + ((size_t)nk * P.NP + P.NP) * sizeof(TV)) + 127) / 128 * 128;
 }
 
-// One copy of a tile: `bytes` from global element `src` (of array `what`: 0 x, 1 b, 2 d, 3 pid) to byte offset `dst`
-// of the stage's data part; bytes == 0: nothing to copy.  `off` is the element index (within its region of the stage)
-// of thread 0's element: xoff[w] for a window, boff[j] / poff[j] for the row tiles.
-struct BoxCopy {
+// One copy of a tile: `bytes` from global element `src` (of array `what`: 0 x, 1 b, 2 d, 3 pid, 4 the tile's own
+// descriptor) to byte offset `dst` of the stage; bytes == 0: nothing to copy.
+struct __align__(16) BoxCopy {
     int src;
     unsigned dst, bytes;
-    int what, off;
+    int what;
 };
 __host__ __device__ inline int box_floor(int a, int al) { return a & ~(al - 1); }
 __host__ __device__ inline int box_ceil(int a, int al) { return (a + al - 1) & ~(al - 1); }
-__host__ __device__ constexpr int box_ncopies(int RZ, bool need_b, bool need_d) {
-    return RZ + 2 + RZ * (1 + (need_b ? 1 : 0) + (need_d ? 1 : 0));
-}
+// copies of a tile: the windows 0 .. RZ+1, then per row-plane j the pattern ids, the b tile and the d tile
+__host__ __device__ constexpr int box_ncopies(int RZ) { return RZ + 2 + 3 * RZ; }
+// Stage layout: [descriptor, 128 bytes][x windows][pattern ids][b tiles][d tiles] (b, d only in the modes that read them).
+constexpr int BOX_DESC_BYTES = 128;
+struct BoxDesc {           // what every thread needs of a tile's geometry: element indices of thread 0's elements
+    int r0, nb, nrp, pad_;
+    int xoff[BOX_MAX_RZ + 2];   // centre element of window w, from the start of the x region
+    int boff[BOX_MAX_RZ];       // row of row-plane j, from the start of the b (or d) region
+    int poff[BOX_MAX_RZ];       // same for the pattern ids
+};
+static_assert(sizeof(BoxDesc) <= BOX_DESC_BYTES, "descriptor does not fit its slot");
+// One record per tile in device memory: the descriptor (copied into the stage like the data) and the copy list.
+__host__ __device__ constexpr int box_rec_bytes(int RZ) { return BOX_DESC_BYTES + box_ncopies(RZ) * (int)sizeof(BoxCopy); }
+
 // geometry of tile (plane group g, chunk c): first row, base rows, row-planes that exist
-__host__ __device__ inline void box_tile_rows(const BoxPlan& P, int RZ, int NB, int g, int c, int& r0, int& nb, int& nrp) {
+inline void box_tile_rows(const BoxPlan& P, int RZ, int NB, int g, int c, int& r0, int& nb, int& nrp) {
     const int c0 = c * NB;
     r0 = g * RZ * P.plane + c0;
     nb = P.plane - c0 < NB ? P.plane - c0 : NB;
     const int left = P.nplanes - g * RZ;               // RZ > 1: n_rows is a multiple of S2 (launcher)
     nrp = left < RZ ? left : RZ;
 }
-// Copy number i of the tile, i < box_ncopies: the windows 0 .. RZ+1 first, then per row-plane j the b tile, the d tile
-// and the pattern ids.  Every lane of the issuing warp computes one of them.
+// host: the record of one tile (rec: box_rec_bytes(RZ) bytes)
 template <typename TV>
-__host__ __device__ inline BoxCopy box_one_copy(const BoxPlan& P, int RZ, int NB, bool need_b, bool need_d, int r0, int nb,
-                                                int nrp, int i) {
+inline void box_plan_tile(const BoxPlan& P, int RZ, int NB, int tile, unsigned char* rec) {
     constexpr int AL = box_al<TV>();
-    BoxCopy C;
-    C.bytes = 0;
-    C.src = 0;
-    C.dst = 0;
+    std::memset(rec, 0, box_rec_bytes(RZ));
+    BoxDesc* D = reinterpret_cast<BoxDesc*>(rec);
+    BoxCopy* cp = reinterpret_cast<BoxCopy*>(rec + BOX_DESC_BYTES);
+    int r0, nb, nrp;
+    box_tile_rows(P, RZ, NB, tile / P.nchunk, tile % P.nchunk, r0, nb, nrp);
+    D->r0 = r0;
+    D->nb = nb;
+    D->nrp = nrp;
     const int bcap = NB + 2 * AL, pcap = NB + 16;
-    if (i < RZ + 2) {
-        const int w = i;
+    const size_t x_bytes = BOX_DESC_BYTES;
+    const size_t p_bytes = x_bytes + (size_t)P.xtotal * sizeof(TV);
+    const size_t b_bytes = p_bytes + (size_t)RZ * pcap * 2;
+    const size_t d_bytes = b_bytes + (size_t)RZ * bcap * sizeof(TV);
+    int n = 0;
+    for (int w = 0; w < RZ + 2; ++w, ++n) {
+        BoxCopy& C = cp[n];
         C.what = 0;
         const int centre = r0 + (w - 1) * P.S2;
         const int a0 = box_floor(centre + P.wlo[w], AL);
-        C.off = P.sbase[w] + (centre - a0);
-        if (w - 2 >= nrp) return C;            // none of the window's (up to three) row-planes exists
+        D->xoff[w] = P.sbase[w] + (centre - a0);
+        if (w - 2 >= nrp) continue;            // none of the window's (up to three) row-planes exists
         int a = a0, e = box_ceil(centre + nb + P.whi[w], AL);
         if (a < P.xlo) a = P.xlo;
         if (e > P.xhi) e = P.xhi;
-        if (e <= a) return C;
+        if (e <= a) continue;
         C.src = a;
-        C.dst = (unsigned)((P.sbase[w] + (a - a0)) * sizeof(TV));
+        C.dst = (unsigned)(x_bytes + (size_t)(P.sbase[w] + (a - a0)) * sizeof(TV));
         C.bytes = (unsigned)((e - a) * sizeof(TV));
-        return C;
     }
-    const int per = 1 + (need_b ? 1 : 0) + (need_d ? 1 : 0);
-    const int j = (i - (RZ + 2)) / per, k = (i - (RZ + 2)) - j * per;     // k: 0 pid, then b, then d
-    const int r = r0 + j * P.S2;
-    const size_t boff_bytes = (size_t)P.xtotal * sizeof(TV);
-    const size_t doff_bytes = boff_bytes + (need_b ? (size_t)RZ * bcap * sizeof(TV) : 0);
-    const size_t poff_bytes = doff_bytes + (need_d ? (size_t)RZ * bcap * sizeof(TV) : 0);
-    if (k == 0) {
-        const int a8 = box_floor(r, 8);
-        C.what = 3;
-        C.off = j * pcap + (r - a8);
-        if (j >= nrp) return C;
-        int e8 = box_ceil(r + nb, 8);
-        const int n8 = box_ceil(P.n_rows, 8);
+    const int nal = box_ceil(P.n_rows, AL), n8 = box_ceil(P.n_rows, 8);
+    for (int j = 0; j < RZ; ++j) {
+        const int r = r0 + j * P.S2;
+        const int a = box_floor(r, AL), a8 = box_floor(r, 8);
+        D->boff[j] = j * bcap + (r - a);
+        D->poff[j] = j * pcap + (r - a8);
+        BoxCopy& Cp = cp[n++];
+        BoxCopy& Cb = cp[n++];
+        BoxCopy& Cd = cp[n++];
+        Cp.what = 3;
+        Cb.what = 1;
+        Cd.what = 2;
+        if (j >= nrp) continue;
+        int e = box_ceil(r + nb, AL), e8 = box_ceil(r + nb, 8);
+        if (e > nal) e = nal;
         if (e8 > n8) e8 = n8;
-        C.src = a8;
-        C.dst = (unsigned)(poff_bytes + (size_t)j * pcap * 2);
-        C.bytes = (unsigned)((e8 - a8) * 2);
-        return C;
+        Cp.src = a8;
+        Cp.dst = (unsigned)(p_bytes + (size_t)j * pcap * 2);
+        Cp.bytes = (unsigned)((e8 - a8) * 2);
+        Cb.src = Cd.src = a;
+        Cb.dst = (unsigned)(b_bytes + (size_t)j * bcap * sizeof(TV));
+        Cd.dst = (unsigned)(d_bytes + (size_t)j * bcap * sizeof(TV));
+        Cb.bytes = Cd.bytes = (unsigned)((e - a) * sizeof(TV));
     }
-    const bool is_b = need_b && k == 1;
-    const int a = box_floor(r, AL);
-    C.what = is_b ? 1 : 2;
-    C.off = j * bcap + (r - a);
-    if (j >= nrp) return C;
-    int e = box_ceil(r + nb, AL);
-    const int nal = box_ceil(P.n_rows, AL);
-    if (e > nal) e = nal;
-    C.src = a;
-    C.dst = (unsigned)((is_b ? boff_bytes : doff_bytes) + (size_t)j * bcap * sizeof(TV));
-    C.bytes = (unsigned)((e - a) * sizeof(TV));
-    return C;
 }
 
 // One thread: RZ rows one plane apart.  xc[w]: the thread's centre element of window w; coefficients from C0 (FAST: every
@@ -239,28 +252,19 @@ __host__ __device__ __forceinline__ void box_thread(const BoxCoef<TV>& C0, const
     }
 }
 
-// Stage layout: [descriptor, 128 bytes][x windows][b tiles][d tiles][pattern ids].  The descriptor is written by the
-// issuing warp before it arms the mbarrier and holds what every thread needs of the tile's geometry.
-constexpr int BOX_DESC_BYTES = 128;
-struct BoxDesc {
-    int r0, pad_;
-    int nb, nrp;
-    int xoff[BOX_MAX_RZ + 2];
-    int boff[BOX_MAX_RZ];
-    int poff[BOX_MAX_RZ];
-};
-static_assert(sizeof(BoxDesc) <= BOX_DESC_BYTES, "descriptor does not fit its slot");
-
 template <typename TV, int SHAPE, int MODE, bool DPAT, int RZ, int NB, int STAGES>
 __global__ void __launch_bounds__(NB)
 box_kernel(const __grid_constant__ BoxPlan P, const __grid_constant__ BoxCoef<TV> C0, const __grid_constant__ PutPlan pp,
-           const uint16_t* __restrict__ pid, const TV* __restrict__ ctab_g, const TV* __restrict__ dtab_g,
-           const TV* __restrict__ x, const TV* __restrict__ b, const TV* __restrict__ d, TV* __restrict__ y) {
+           const unsigned char* __restrict__ recs, const uint16_t* __restrict__ pid, const TV* __restrict__ ctab_g,
+           const TV* __restrict__ dtab_g, const TV* __restrict__ x, const TV* __restrict__ b, const TV* __restrict__ d,
+           TV* __restrict__ y) {
     constexpr bool NEED_B = (MODE == 2 || MODE == 3);
     constexpr bool NEED_D = (MODE == 3 && !DPAT);
     constexpr int NK = SHAPE == 27 ? 27 : 7;
     constexpr int AL = box_al<TV>();
-    constexpr int BCAP = NB + 2 * AL;
+    constexpr int BCAP = NB + 2 * AL, PCAP = NB + 16;
+    constexpr int NCP = box_ncopies(RZ), REC = box_rec_bytes(RZ);
+    static_assert(NCP < 32, "one copy per lane of the issuing warp, plus the descriptor");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
     TV* ctab = reinterpret_cast<TV*>(smem_raw + 64);
@@ -284,73 +288,51 @@ box_kernel(const __grid_constant__ BoxPlan P, const __grid_constant__ BoxCoef<TV
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     const int ntiles = P.ntiles;
-    // Warp 0 issues the copies of a tile: every lane plans ONE copy (a window, or a b / d / pattern-id tile) and writes
-    // its entry of the stage's descriptor, lane 0 arms the mbarrier with the byte total, then the lanes issue their
-    // copies (a copy that completes before the barrier is armed only makes the transaction count negative for a
-    // moment: the phase cannot complete before lane 0 has arrived).  The warp walks (plane group, chunk) of its tiles
-    // without dividing.
-    constexpr int NCP = box_ncopies(RZ, NEED_B, NEED_D);
-    constexpr int PER = NCP - (RZ + 2) > 0 ? (NCP - (RZ + 2)) / RZ : 1;
-    static_assert(NCP <= 32, "one copy per lane of the issuing warp");
-    int ig = 0, ic = 0;
-    auto advance = [&](int by) {
-        ic += by;
-        while (ic >= P.nchunk) {
-            ic -= P.nchunk;
-            ++ig;
-        }
-    };
-    auto issue = [&](int s) {            // all lanes of warp 0
+    // Warp 0 issues the copies of a tile: lane i loads entry i of the tile's record and fires it, lane NCP copies the
+    // record's descriptor into the stage; lane 0 arms the mbarrier with the byte total first.
+    auto issue = [&](int tile, int s) {            // all lanes of warp 0
         unsigned char* st = stage0 + (size_t)s * stage_bytes;
-        BoxDesc* D = reinterpret_cast<BoxDesc*>(st);
-        int r0, nb, nrp;
-        box_tile_rows(P, RZ, NB, ig, ic, r0, nb, nrp);
+        const unsigned char* rec = recs + (size_t)tile * REC;
         BoxCopy C;
         C.bytes = 0;
         C.what = -1;
         if (t < NCP) {
-            C = box_one_copy<TV>(P, RZ, NB, NEED_B, NEED_D, r0, nb, nrp, t);
-            if (C.what == 0) D->xoff[t] = C.off;
-            else if (C.what == 3) D->poff[(t - (RZ + 2)) / PER] = C.off;
-            else if (C.what == 1 || (!NEED_B && C.what == 2)) D->boff[(t - (RZ + 2)) / PER] = C.off;
-        }
-        if (!NEED_B && !NEED_D && t < RZ) D->boff[t] = 0;
-        if (t == 0) {
-            D->r0 = r0;
-            D->nb = nb;
-            D->nrp = nrp;
+            const int4 q = __ldg(reinterpret_cast<const int4*>(rec + BOX_DESC_BYTES) + t);
+            C.src = q.x;
+            C.dst = (unsigned)q.y;
+            C.bytes = (unsigned)q.z;
+            C.what = q.w;
+            if ((C.what == 1 && !NEED_B) || (C.what == 2 && !NEED_D)) C.bytes = 0;
+        } else if (t == NCP) {
+            C.what = 4;
+            C.dst = 0;
+            C.bytes = BOX_DESC_BYTES;
         }
         unsigned total = C.bytes;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-        __syncwarp();
         if (t == 0) mbar_expect_tx(full + s, total);
         __syncwarp();
         if (C.bytes) {
             const void* src = C.what == 0 ? static_cast<const void*>(x + C.src)
                               : (C.what == 1 ? static_cast<const void*>(b + C.src)
-                                             : (C.what == 2 ? static_cast<const void*>(d + C.src) : static_cast<const void*>(pid + C.src)));
-            bulk_g2s(st + BOX_DESC_BYTES + C.dst, src, C.bytes, full + s);
+                                             : (C.what == 2 ? static_cast<const void*>(d + C.src)
+                                                            : (C.what == 3 ? static_cast<const void*>(pid + C.src) : static_cast<const void*>(rec))));
+            bulk_g2s(st + C.dst, src, C.bytes, full + s);
         }
     };
     const bool issuer = t < 32;
-    if (issuer) {
-        advance(blockIdx.x);
-        if ((int)blockIdx.x < ntiles) issue(0);
-    }
+    if (issuer && (int)blockIdx.x < ntiles) issue(blockIdx.x, 0);
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int s = STAGES == 2 ? (it & 1) : 0;
-        if (STAGES == 2 && issuer && tile + (int)gridDim.x < ntiles) {
-            advance(gridDim.x);
-            issue(s ^ 1);
-        }
+        if (STAGES == 2 && issuer && tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x, s ^ 1);
         const unsigned char* st = stage0 + (size_t)s * stage_bytes;
         const BoxDesc* D = reinterpret_cast<const BoxDesc*>(st);
         const TV* sx = reinterpret_cast<const TV*>(st + BOX_DESC_BYTES);
-        const TV* sb = sx + P.xtotal;
-        const TV* sd = sb + (NEED_B ? RZ * BCAP : 0);
-        const uint16_t* sp = reinterpret_cast<const uint16_t*>(sd + (NEED_D ? RZ * BCAP : 0));
+        const uint16_t* sp = reinterpret_cast<const uint16_t*>(sx + P.xtotal);
+        const TV* sb = reinterpret_cast<const TV*>(sp + RZ * PCAP);
+        const TV* sd = sb + RZ * BCAP;
         mbar_wait(full + s, STAGES == 2 ? ((it >> 1) & 1) : (it & 1));
         const int nb = D->nb, nrp = D->nrp;
         const TV* xc[RZ + 2];
@@ -383,10 +365,7 @@ box_kernel(const __grid_constant__ BoxPlan P, const __grid_constant__ BoxCoef<TV
                 }
         }
         __syncthreads();
-        if (STAGES == 1 && issuer && tile + (int)gridDim.x < ntiles) {
-            advance(gridDim.x);
-            issue(0);
-        }
+        if (STAGES == 1 && issuer && tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x, 0);
     }
 }
 
@@ -400,12 +379,37 @@ struct BoxDict {
     TV* ctab = nullptr;            // device: coef[k * NP + p]
     TV* dtab = nullptr;            // device: folded relaxation weights per pattern (set by fold_d), NP elements
     std::vector<TV> h_ctab;        // host copies (the CPU replay, tests)
+    // tile records of the variant in use (box_plan_tile), planned at the first launch and whenever the variant or the
+    // copyable range of the input vectors changes
+    unsigned char* recs = nullptr;
+    int rec_RZ = 0, rec_NB = 0, rec_xlo = 0, rec_xhi = 0;
     void release() {
         if (ctab) cudaFree(ctab);
         if (dtab) cudaFree(dtab);
+        if (recs) cudaFree(recs);
         ctab = dtab = nullptr;
+        recs = nullptr;
+        rec_RZ = rec_NB = 0;
         ok = false;
         h_ctab.clear();
+    }
+    bool has_records(const BoxPlan& P, int RZ, int NB) const {
+        return recs && rec_RZ == RZ && rec_NB == NB && rec_xlo == P.xlo && rec_xhi == P.xhi;
+    }
+    const unsigned char* records(const BoxPlan& P, int RZ, int NB) {
+        if (has_records(P, RZ, NB)) return recs;
+        if (recs) cudaFree(recs);
+        recs = nullptr;
+        const size_t rb = box_rec_bytes(RZ);
+        std::vector<unsigned char> h((size_t)P.ntiles * rb);
+        for (int tile = 0; tile < P.ntiles; ++tile) box_plan_tile<TV>(P, RZ, NB, tile, h.data() + (size_t)tile * rb);
+        MGB_CUDA(cudaMalloc(&recs, std::max<size_t>(h.size(), 16)));
+        MGB_CUDA(cudaMemcpy(recs, h.data(), h.size(), cudaMemcpyHostToDevice));
+        rec_RZ = RZ;
+        rec_NB = NB;
+        rec_xlo = P.xlo;
+        rec_xhi = P.xhi;
+        return recs;
     }
 };
 // dense table of a box-structured dictionary; false when the shape is not one the kernel is instantiated for

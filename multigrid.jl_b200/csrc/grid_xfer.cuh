@@ -1,19 +1,22 @@
-// Transfer operators of the geometric hierarchy with a GRID HINT (off by default: option "grid_transfers").
+// Transfer operators of the geometric hierarchy with a GRID HINT (option "grid_transfers", on by default).
 //
 // P = kron of 1-D linear interpolations on nodal grids, R = 2^-dim P^T (src/Multigrid/GeometricTransferOperators.jl:5-46,
 // MGsetup.jl:53-62 of the reference).  In stencil-dictionary form (pattern.cuh) their rows are copies of 8 (P: one per
 // parity class of the fine node) or 27 (R: first / interior / last per dimension) patterns, but the dictionary kernel
-// still reads 6 bytes per row (pattern id + first column) and walks the entries per lane.  The reference's setup knows
-// the meshes (param.Meshes[l].n); when the host passes them (mgb200_set_level_grid) and the uploaded P / R are exactly
-// what those grids imply - verified row by row at upload, values untouched - the pattern and the columns of a row are
-// functions of its grid coordinates: the kernels below read NO matrix stream at all, only the dictionary VALUES (so a
-// P with other weights still works), and block R coarse lines per thread:
-//   restriction:  a thread owns coarse column I of R coarse lines; per fine plane it loads the 3 x (2R+1) fine values
-//                 around its coarse nodes once for 27 R products;
-//   prolongation: it loads the 2 x (R+1) x 2 coarse corner values once and updates the 8 R fine nodes of its cells.
-// Entries are multiplied in stored order ((dz,dy,dx) ascending), so results are bit-identical to the dictionary walk.
-// The per-thread functions are __host__ __device__: mgb200_host_grid_transfer runs them on the CPU
-// (tests/test_patterns.py).  NOT yet run on a GPU (written after the GPU budget of round 1 was spent).
+// still reads 6 bytes per row (pattern id + first column) and walks the entries per lane with 1 ... 8 trips inside a
+// warp (prolongation) or with a 16-byte entry load per product (restriction).  The reference's setup knows the meshes
+// (param.Meshes[l].n); when the host passes them (mgb200_set_level_grid) and the uploaded P / R are exactly what those
+// grids imply - verified row by row at upload, values untouched - the pattern and the columns of a row are functions
+// of its grid coordinates.  The kernels below then read NO matrix stream at all, only dense tables of the dictionary
+// VALUES (so a P with other weights still works):
+//   prolongation: a CTA walks fine lines; a thread owns fine node i of the line (coalesced read-modify-write of x_f); the
+//                 parities of the line (b, c) are CTA-uniform, the products of a row run in stored order (dz', dy', dx');
+//   restriction:  a CTA walks coarse lines; a thread owns coarse node I; 27 predicated products in stored order with the
+//                 coefficients of the line's boundary class in shared memory.
+// One thread = one row and stored order, so results are bit-identical to the dictionary walk.  The per-row functions
+// are __host__ __device__: mgb200_host_grid_transfer runs them on the CPU (tests/test_patterns.py).
+// (Round 1 had a coarse-column-per-thread form with R lines per thread; measured on the B200 it gained little -
+// profiles/r02a_microbench_lines_transfer.log - and was replaced by the kernels below.)
 #pragma once
 #include "pattern.cuh"
 
@@ -24,7 +27,10 @@ struct GridXfer {
     int kind;          // 1: prolongation (rows = fine nodes), 2: restriction (rows = coarse nodes)
     int n[3], N[3];    // fine / coarse nodes per dimension (unused dimensions: 1); n = 2N - 1 where N > 1
     int cls_k0[27];    // first dictionary entry of the pattern of each class (-1: class does not occur)
+    void* tab;         // device: dense value table (gx_dense_table), released with the matrix
 };
+constexpr int GXP_TAB = 8 * 8;      // prolongation: class a + 2b + 4c, up to 8 values in stored order (zeros beyond)
+constexpr int GXR_TAB = 27 * 27;    // restriction: class cx + 3cy + 9cz, coefficient of offset (dz+1)*9 + (dy+1)*3 + (dx+1)
 static inline GridXfer no_grid() {
     GridXfer X;
     std::memset(&X, 0, sizeof(X));
@@ -119,122 +125,128 @@ static bool gx_verify_restriction(const HostPatterns<TA>& H, long long n_rows, c
     return true;
 }
 
-// ---- restriction: r_c = R r_f, thread = coarse column I of the coarse lines [J0, J0+R) of coarse plane K ------------------
-template <typename TA, typename TV, int R>
-__host__ __device__ inline void gx_restrict_thread(const GridXfer& X, int I, int J0, int K, const PatEntry<TA>* ent,
-                                                   const TV* rf, TV* rc) {
-    const int N1 = X.N[0], N2 = X.N[1];
-    const int nr = (N2 - J0 < R) ? (N2 - J0) : R;
-    // one pattern for the R rows: all of them interior lines (or R == 1)
-    const bool uniform = (R == 1) ? (nr == 1) : (nr == R && J0 >= 1 && J0 + R - 1 <= N2 - 2);
-    if (!uniform) {
-        for (int j = 0; j < nr; ++j) gx_restrict_thread<TA, TV, 1>(X, I, J0 + j, K, ent, rf, rc);
-        return;
+// dense value table of a verified hint, from the dictionary values (host)
+template <typename TA>
+static std::vector<TA> gx_dense_table(const GridXfer& X, const std::vector<TA>& val) {
+    std::vector<TA> t(X.kind == 1 ? GXP_TAB : GXR_TAB, TA());
+    if (X.kind == 1) {
+        for (int cls = 0; cls < 8; ++cls) {
+            if (X.cls_k0[cls] < 0) continue;
+            const int a = cls & 1, b = (cls >> 1) & 1, c = (cls >> 2) & 1;
+            for (int k = 0; k < (1 << (a + b + c)); ++k) t[cls * 8 + k] = val[X.cls_k0[cls] + k];
+        }
+    } else {
+        for (int cls = 0; cls < 27; ++cls) {
+            if (X.cls_k0[cls] < 0) continue;
+            const int ax = gx_allowed(cls % 3, X.N[0]), ay = gx_allowed((cls / 3) % 3, X.N[1]), az = gx_allowed(cls / 9, X.N[2]);
+            int q = X.cls_k0[cls];
+            for (int dz = -1; dz <= 1; ++dz)
+                for (int dy = -1; dy <= 1; ++dy)
+                    for (int dx = -1; dx <= 1; ++dx)
+                        if (((az >> (dz + 1)) & 1) && ((ay >> (dy + 1)) & 1) && ((ax >> (dx + 1)) & 1))
+                            t[cls * 27 + (dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)] = val[q++];
+        }
     }
-    const int cx = gx_class(I, N1), cy = (R == 1) ? gx_class(J0, N2) : 1, cz = gx_class(K, X.N[2]);
-    const int ax = gx_allowed(cx, N1), ay = gx_allowed(cy, N2), az = gx_allowed(cz, X.N[2]);
-    const PatEntry<TA>* e = ent + X.cls_k0[cx + 3 * cy + 9 * cz];
-    const long long S = X.n[0], S2 = (long long)X.n[0] * X.n[1];
-    const long long f0 = S2 * (2LL * K) + S * (2LL * J0) + 2LL * I;       // fine node under the first coarse node
-    const long long crow0 = ((long long)K * N2 + J0) * N1 + I;
-    TV acc[R];
+    return t;
+}
+
+template <typename T>
+__host__ __device__ __forceinline__ T gx_ld(const T* p) {
+#ifdef __CUDA_ARCH__
+    return ldg_(p);
+#else
+    return *p;
+#endif
+}
+
+// ---- prolongation: x_f[i] += sum of P's row, fine node (i, j, k); b = j & 1, c = k & 1; q = coarse node (0, j/2, k/2) ----
+// tab: the 8 x 8 dense table.  Products in stored order (dz', dy', dx').
+template <typename TA, typename TV>
+__host__ __device__ __forceinline__ TV gxp_row(const TA* tab, const TV* q, int N0, long long cs2, int i, int b, int c, TV xf) {
+    const int a = i & 1;
+    const TA* tv = tab + (a + 2 * b + 4 * c) * 8;
+    const TV* p0 = q + (i >> 1);
+    TV acc = VT<TV>::zero();
+    int idx = 0;
 #pragma unroll
-    for (int j = 0; j < R; ++j) acc[j] = VT<TV>::zero();
+    for (int dz = 0; dz < 2; ++dz) {
+        if (dz > c) break;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+            if (dy > b) break;
+            const TV* p = p0 + dy * N0 + dz * cs2;
+            acc = acc + tv[idx] * gx_ld(p);
+            ++idx;
+            if (a) {
+                acc = acc + tv[idx] * gx_ld(p + 1);
+                ++idx;
+            }
+        }
+    }
+    return xf + acc;
+}
+// ---- restriction: coarse node (I, J, K) = 27 predicated products around fine node (2I, 2J, 2K) in stored order -------------
+// tv: the 27 coefficients of the node's class; ax / ay / az: allowed offsets per dimension (gx_allowed)
+template <typename TA, typename TV>
+__host__ __device__ __forceinline__ TV gxr_row(const TA* tv, const TV* f, long long S, long long S2, int ax, int ay, int az) {
+    TV acc = VT<TV>::zero();
 #pragma unroll
     for (int dz = -1; dz <= 1; ++dz) {
         if (!((az >> (dz + 1)) & 1)) continue;
-        const TV* xp = rf + (f0 + dz * S2 - S);                            // fine line 2 J0 - 1
-        TV Xv[3][2 * R + 1];                                               // l = fine line - (2 J0 - 1)
-#pragma unroll
-        for (int l = 0; l < 2 * R + 1; ++l) {
-            // coarse row j multiplies fine line l = 2j + 1 + dy: a value is loaded iff some row multiplies it
-            const bool lneed = (l & 1) ? ((ay >> 1) & 1) : (((l <= 2 * R - 2) && (ay & 1)) || ((l >= 2) && ((ay >> 2) & 1)));
-            const TV* q = xp + l * S;
-#pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) Xv[dx + 1][l] = (lneed && ((ax >> (dx + 1)) & 1)) ? ld_ro(q + dx) : VT<TV>::zero();
-        }
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy) {
+            if (!((ay >> (dy + 1)) & 1)) continue;
+            const TV* p = f + dz * S2 + dy * S;
 #pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-                if (((ay >> (dy + 1)) & 1) && ((ax >> (dx + 1)) & 1)) {
-                    const TA v = e->v;
-                    ++e;
-#pragma unroll
-                    for (int j = 0; j < R; ++j) acc[j] = acc[j] + v * Xv[dx + 1][2 * j + 1 + dy];
-                }
-            }
+            for (int dx = -1; dx <= 1; ++dx)
+                if ((ax >> (dx + 1)) & 1) acc = acc + tv[(dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)] * gx_ld(p + dx);
         }
     }
-#pragma unroll
-    for (int j = 0; j < R; ++j) rc[crow0 + (long long)j * N1] = acc[j];
+    return acc;
 }
 
-// ---- prolongation: x_f += P x_c, thread = coarse column I of the coarse lines [J0, J0+R) of coarse plane K; it owns the
-// fine nodes (2I+a, 2J+b, 2K+c), a, b, c in {0,1}, of those coarse nodes -------------------------------------------------
-template <typename TA, typename TV, int R>
-__host__ __device__ inline void gx_prolong_thread(const GridXfer& X, int I, int J0, int K, const PatEntry<TA>* ent,
-                                                  const TV* xc, TV* xf) {
-    const int N1 = X.N[0], N2 = X.N[1], N3 = X.N[2];
-    const long long S = X.n[0], S2 = (long long)X.n[0] * X.n[1], CS = N1, CS2 = (long long)N1 * N2;
-    const long long crow0 = ((long long)K * N2 + J0) * N1 + I;
-    const bool hasI = I + 1 < N1, hasK = K + 1 < N3;
-    TV XC[2][R + 1][2];
-#pragma unroll
-    for (int dz = 0; dz < 2; ++dz)
-#pragma unroll
-        for (int l = 0; l < R + 1; ++l) {
-            const bool in = (J0 + l < N2) && (dz == 0 || hasK);
-            const TV* q = xc + (crow0 + dz * CS2 + l * CS);
-            XC[dz][l][0] = in ? ld_ro(q) : VT<TV>::zero();
-            XC[dz][l][1] = (in && hasI) ? ld_ro(q + 1) : VT<TV>::zero();
-        }
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-#pragma unroll
-            for (int a = 0; a < 2; ++a) {
-                if ((c == 0 || hasK) && (a == 0 || hasI)) {
-                    const int k0 = X.cls_k0[a + 2 * b + 4 * c];
-                    if (k0 >= 0) {
-                        // the values of this parity class in stored order (dz', dy', dx'): 2^(a+b+c) of them
-                        TA v[8];
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) v[k] = (k < (1 << (a + b + c))) ? ent[k0 + k].v : TA();
-#pragma unroll
-                        for (int j = 0; j < R; ++j) {
-                            if (J0 + j < N2 && (b == 0 || J0 + j + 1 < N2)) {
-                                const long long row = S2 * (2LL * K + c) + S * (2LL * (J0 + j) + b) + 2LL * I + a;
-                                TV acc = VT<TV>::zero();
-#pragma unroll
-                                for (int dz = 0; dz <= c; ++dz)
-#pragma unroll
-                                    for (int dy = 0; dy <= b; ++dy)
-#pragma unroll
-                                        for (int dx = 0; dx <= a; ++dx)
-                                            acc = acc + v[(dz * (b + 1) + dy) * (a + 1) + dx] * XC[dz][j + dy][dx];
-                                xf[row] = xf[row] + acc;
-                            }
-                        }
-                    }
-                }
-            }
-        }
+// persistent CTAs over the fine lines (j, k); threads over i
+template <typename TA, typename TV>
+__global__ void __launch_bounds__(1024) gxp_kernel(const __grid_constant__ GridXfer X, const TA* __restrict__ tabg,
+                                                   const TV* __restrict__ xc, TV* __restrict__ xf) {
+    __shared__ TA tab[GXP_TAB];
+    for (int i = threadIdx.x; i < GXP_TAB; i += blockDim.x) tab[i] = tabg[i];
+    __syncthreads();
+    const int n0 = X.n[0], n1 = X.n[1], N0 = X.N[0], N1 = X.N[1];
+    const long long cs2 = (long long)N0 * N1;
+    const int nlines = n1 * X.n[2];
+    for (int line = blockIdx.x; line < nlines; line += gridDim.x) {
+        const int k = line / n1, j = line - k * n1;
+        const TV* q = xc + ((long long)(k >> 1) * N1 + (j >> 1)) * N0;
+        TV* xl = xf + (long long)line * n0;
+        for (int i = threadIdx.x; i < n0; i += blockDim.x) xl[i] = gxp_row<TA, TV>(tab, q, N0, cs2, i, j & 1, k & 1, xl[i]);
     }
 }
-
-// persistent grid-stride over the flattened (plane, line group, column) index of the COARSE grid
-template <typename TA, typename TV, int KIND, int R>
-__global__ void __launch_bounds__(256) gx_kernel(const __grid_constant__ GridXfer X, long long total,
-                                                 const PatEntry<TA>* __restrict__ ent, const TV* __restrict__ in,
-                                                 TV* __restrict__ out) {
-    const int N1 = X.N[0], gpp = (X.N[1] + R - 1) / R;
-    for (long long f = blockIdx.x * (long long)blockDim.x + threadIdx.x; f < total; f += (long long)gridDim.x * blockDim.x) {
-        const long long grp = f / N1;
-        const int I = (int)(f - grp * N1), K = (int)(grp / gpp), q = (int)(grp - (long long)K * gpp);
-        if (KIND == 2) gx_restrict_thread<TA, TV, R>(X, I, q * R, K, ent, in, out);
-        else gx_prolong_thread<TA, TV, R>(X, I, q * R, K, ent, in, out);
+// persistent CTAs over the coarse lines (J, K); threads over I
+template <typename TA, typename TV>
+__global__ void __launch_bounds__(1024) gxr_kernel(const __grid_constant__ GridXfer X, const TA* __restrict__ tabg,
+                                                   const TV* __restrict__ rf, TV* __restrict__ rc) {
+    __shared__ TA tab[3 * 27];
+    const int N0 = X.N[0], N1 = X.N[1], N2 = X.N[2];
+    const long long S = X.n[0], S2 = (long long)X.n[0] * X.n[1];
+    const int nlines = N1 * N2;
+    int cur = -1;
+    for (int line = blockIdx.x; line < nlines; line += gridDim.x) {
+        const int K = line / N1, J = line - K * N1;
+        const int cy = gx_class(J, N1), cz = gx_class(K, N2);
+        if (3 * cy + 9 * cz != cur) {          // CTA-uniform: the three x classes of this line's (y, z) class
+            __syncthreads();
+            cur = 3 * cy + 9 * cz;
+            for (int i = threadIdx.x; i < 81; i += blockDim.x) tab[i] = tabg[(cur + i / 27) * 27 + i % 27];
+            __syncthreads();
+        }
+        const int ay = gx_allowed(cy, N1), az = gx_allowed(cz, N2);
+        const TV* f0 = rf + S2 * (2LL * K) + S * (2LL * J);
+        TV* out = rc + (long long)line * N0;
+        for (int I = threadIdx.x; I < N0; I += blockDim.x) {
+            const int cx = gx_class(I, N0);
+            out[I] = gxr_row<TA, TV>(tab + cx * 27, f0 + 2 * I, S, S2, gx_allowed(cx, N0), ay, az);
+        }
     }
 }
 

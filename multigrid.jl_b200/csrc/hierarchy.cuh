@@ -104,6 +104,7 @@ struct Csr {
     void release() {
         pat.release();
         box.release();
+        if (gx.tab) cudaFree(gx.tab);
         gx = no_grid();
         int_lo = int_hi = 0;
         dev_free(rowptr);
@@ -131,7 +132,7 @@ struct Context {
     int use_patterns = 1;          // 0: always stream CSR (MGB200_PATTERNS / mgb200_set_option)
     int use_graphs = 1;            // 0: never replay cycles from CUDA graphs
     int use_tma = 1;               // 0: never use the TMA-staged dictionary kernel (MGB200_TMA)
-    int grid_transfers = 0;        // > 0: grid-hinted transfer kernels (grid_xfer.cuh) with that many coarse lines per thread (1, 2, 4); off by default
+    int grid_transfers = 1;        // > 0: grid-hinted transfer kernels (grid_xfer.cuh) where a hint was given and verified
     int lines = 0;                 // > 0: line-blocked dictionary kernel with that many rows per thread (2 or 4); off by default
     int lines_min_rows = 50000;
     int lines_staged = 1;          // 1: TMA-staged form of the line-blocked kernel where the lines fit a CTA, 0: global-memory form
@@ -173,7 +174,7 @@ struct Context {
         box_variant = env_int("MGB200_BOX_VARIANT", 0);
         box_min_rows = env_int("MGB200_BOX_MIN_ROWS", 100000);
         lines = env_int("MGB200_LINES", 0);
-        grid_transfers = env_int("MGB200_GRID_TRANSFERS", 0);
+        grid_transfers = env_int("MGB200_GRID_TRANSFERS", 1);
         lines_min_rows = env_int("MGB200_LINES_MIN_ROWS", 50000);
         lines_staged = env_int("MGB200_LINES_STAGED", 1);
         use_overlap = env_int("MGB200_OVERLAP", 0);

@@ -217,26 +217,23 @@ static bool launch_pattern_lines(Context& ctx, const Csr<TV>& M, int mode, const
     return true;
 }
 
-// grid-hinted transfer kernels (grid_xfer.cuh): P in mode ADD, R in mode SPMV, one right-hand side; off unless the
-// option "grid_transfers" (MGB200_GRID_TRANSFERS) holds the coarse lines per thread (1, 2 or 4)
+// grid-hinted transfer kernels (grid_xfer.cuh): P in mode ADD, R in mode SPMV, one right-hand side; option
+// "grid_transfers" (MGB200_GRID_TRANSFERS, default 1) and a hint that was verified at upload
 template <typename TA, typename TV>
 static bool launch_grid_xfer(Context& ctx, const Csr<TA>& M, int mode, const TV* x, TV* y, bool dry = false) {
     if constexpr (VT<TA>::is_complex) {
         return false;     // P and R are real (SA-AMG.jl:9-10, MGsetup.jl:80-81): no complex instantiation
     } else {
     const GridXfer& X = M.gx;
-    const int R = ctx.grid_transfers;
-    if (!X.ok || !M.pat.present || (R != 1 && R != 2 && R != 4) || x == y) return false;
+    if (!X.ok || !X.tab || !M.pat.present || ctx.grid_transfers <= 0 || x == y) return false;
     if (!((X.kind == 1 && mode == MODE_ADD) || (X.kind == 2 && mode == MODE_SPMV))) return false;
     if (dry) return true;      // the caller only asks whether this kernel will run (byte accounting)
-    const long long total = (long long)X.N[2] * ((X.N[1] + R - 1) / R) * X.N[0];
-    const int grid = (int)std::min<long long>((total + 255) / 256, (long long)ctx.sm_count * (R == 4 ? 3 : 6));
-#define MGB_GX(KIND, RR) gx_kernel<TA, TV, KIND, RR><<<grid, 256, 0, ctx.stream>>>(X, total, M.pat.ent, x, y)
-#define MGB_GR(KIND) { if (R == 1) MGB_GX(KIND, 1); else if (R == 2) MGB_GX(KIND, 2); else MGB_GX(KIND, 4); }
-    if (X.kind == 1) MGB_GR(1)
-    else MGB_GR(2)
-#undef MGB_GR
-#undef MGB_GX
+    const int width = X.kind == 1 ? X.n[0] : X.N[0];
+    const long long nlines = X.kind == 1 ? (long long)X.n[1] * X.n[2] : (long long)X.N[1] * X.N[2];
+    const int nt = std::min(1024, (width + 31) / 32 * 32);
+    const int grid = (int)std::min<long long>(nlines, (long long)ctx.sm_count * std::max(1, 2048 / nt) * 4);
+    if (X.kind == 1) gxp_kernel<TA, TV><<<grid, nt, 0, ctx.stream>>>(X, static_cast<const TA*>(X.tab), x, y);
+    else gxr_kernel<TA, TV><<<grid, nt, 0, ctx.stream>>>(X, static_cast<const TA*>(X.tab), x, y);
     MGB_LAUNCH_CHECK();
     return true;
     }
@@ -246,8 +243,8 @@ static bool launch_grid_xfer(Context& ctx, const Csr<TA>& M, int mode, const TV*
 // side, double and complex double.  Variants (rows per thread RZ, base rows per tile NB, stages): ctx.box_variant.
 template <typename TV, int RZ, int NB, int STAGES>
 static bool launch_box_variant(Context& ctx, const Csr<TV>& M, int mode, const TV* x, const TV* b, const TV* d,
-                               const TV* dpat, TV* y, const PutPlan& pp) {
-    const BoxDict<TV>& X = M.box;
+                               const TV* dpat, TV* y, const PutPlan& pp, bool prepare_only) {
+    BoxDict<TV>& X = const_cast<BoxDict<TV>&>(M.box);      // the record cache is filled on first use
     const PatDict<TV>& D = M.pat;
     BoxPlan P;
     box_make_plan<TV>(P, X.shape, RZ, NB, M.n_rows, D.S, D.S2, D.xlo, D.xhi, X.npat, X.p0);
@@ -256,6 +253,14 @@ static bool launch_box_variant(Context& ctx, const Csr<TV>& M, int mode, const T
     const bool need_b = (mode == MODE_RESID || mode == MODE_SWEEP), need_d = (mode == MODE_SWEEP && !dpat);
     const size_t smem = box_head_bytes<TV>(P, X.shape) + STAGES * box_stage_bytes<TV>(P, RZ, NB, need_b, need_d);
     if (smem > (size_t)ctx.max_smem_optin) return false;
+    // the tile records are planned outside stream capture (box_prepare, called before a cycle graph is captured)
+    if (!prepare_only && !X.has_records(P, RZ, NB)) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        MGB_CUDA(cudaStreamIsCapturing(ctx.stream, &cs));
+        if (cs != cudaStreamCaptureStatusNone) return false;
+    }
+    const unsigned char* recs = X.records(P, RZ, NB);
+    if (prepare_only) return true;
 #define MGB_BX(SHAPE, MODE, DP)                                                                                      \
     {                                                                                                                 \
         auto kern = box_kernel<TV, SHAPE, MODE, DP, RZ, NB, STAGES>;                                                  \
@@ -264,7 +269,7 @@ static bool launch_box_variant(Context& ctx, const Csr<TV>& M, int mode, const T
         MGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, NB, smem));                                \
         if (per < 1) return false;                                                                                    \
         const int grid = (int)std::min<long long>(P.ntiles, (long long)ctx.sm_count * per);                           \
-        kern<<<grid, NB, smem, ctx.stream>>>(P, X.c0, pp, D.pid, X.ctab, X.dtab, x, b, d, y);                         \
+        kern<<<grid, NB, smem, ctx.stream>>>(P, X.c0, pp, recs, D.pid, X.ctab, X.dtab, x, b, d, y);                         \
     }
 #define MGB_BXS(MODE, DP) { if (X.shape == 7) MGB_BX(7, MODE, DP) else MGB_BX(27, MODE, DP) }
     if (mode == MODE_SPMV) MGB_BXS(MODE_SPMV, false)
@@ -278,26 +283,35 @@ static bool launch_box_variant(Context& ctx, const Csr<TV>& M, int mode, const T
 }
 template <typename TA, typename TV>
 static bool launch_box(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d, const TV* dpat,
-                       TV* y, const PutPlan& pp) {
+                       TV* y, const PutPlan& pp, bool prepare_only = false) {
     if constexpr (std::is_same<TA, TV>::value && (std::is_same<TV, double>::value || std::is_same<TV, cplx>::value)) {
-        if (!M.box.ok || !ctx.use_box || mode == MODE_ADD || x == y || M.n_rows < ctx.box_min_rows) return false;
-        if ((reinterpret_cast<uintptr_t>(x) & 15) || (b && (reinterpret_cast<uintptr_t>(b) & 15)) ||
-            (d && (reinterpret_cast<uintptr_t>(d) & 15)))
-            return false;
+        if (!M.box.ok || !ctx.use_box || M.n_rows < ctx.box_min_rows) return false;
+        if (!prepare_only) {
+            if (mode == MODE_ADD || x == y) return false;
+            if ((reinterpret_cast<uintptr_t>(x) & 15) || (b && (reinterpret_cast<uintptr_t>(b) & 15)) ||
+                (d && (reinterpret_cast<uintptr_t>(d) & 15)))
+                return false;
+        }
         constexpr int F = sizeof(TV) / 8;      // complex tiles hold half the rows
         switch (ctx.box_variant) {
-            case 1: return launch_box_variant<TV, 2, 512 / F, 2>(ctx, M, mode, x, b, d, dpat, y, pp);
-            case 2: return launch_box_variant<TV, 2, 512 / F, 1>(ctx, M, mode, x, b, d, dpat, y, pp);
-            case 3: return launch_box_variant<TV, 4, 256 / F, 1>(ctx, M, mode, x, b, d, dpat, y, pp);
-            case 4: return launch_box_variant<TV, 4, 256 / F, 2>(ctx, M, mode, x, b, d, dpat, y, pp);
-            case 5: return launch_box_variant<TV, 1, 512 / F, 1>(ctx, M, mode, x, b, d, dpat, y, pp);
-            case 6: return launch_box_variant<TV, 2, 1024 / F, 1>(ctx, M, mode, x, b, d, dpat, y, pp);
-            case 7: return launch_box_variant<TV, 1, 1024 / F, 1>(ctx, M, mode, x, b, d, dpat, y, pp);
-            default: return launch_box_variant<TV, 1, 1024 / F, 2>(ctx, M, mode, x, b, d, dpat, y, pp);
+            case 1: return launch_box_variant<TV, 2, 512 / F, 2>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only);
+            case 2: return launch_box_variant<TV, 2, 512 / F, 1>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only);
+            case 3: return launch_box_variant<TV, 4, 256 / F, 1>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only);
+            case 4: return launch_box_variant<TV, 4, 256 / F, 2>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only);
+            case 5: return launch_box_variant<TV, 1, 512 / F, 1>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only);
+            case 6: return launch_box_variant<TV, 2, 1024 / F, 1>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only);
+            case 7: return launch_box_variant<TV, 1, 1024 / F, 1>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only);
+            default: return launch_box_variant<TV, 1, 1024 / F, 2>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only);
         }
     } else {
         return false;
     }
+}
+
+// plan the tile records of the box-stencil kernel for the variant in use (allocates: never inside stream capture)
+template <typename TA>
+static void box_prepare(Context& ctx, const Csr<TA>& M) {
+    launch_box<TA, TA>(ctx, M, MODE_SPMV, nullptr, nullptr, nullptr, nullptr, nullptr, no_put(), true);
 }
 
 // one-pass dictionary kernel over the rows [rA, rA + nA) and [rB, rB + nB)

@@ -172,24 +172,19 @@ static void host_box_run(const BoxPlan& P, const BoxCoef<double>& C0, const std:
                          int NB, int ctas, const uint16_t* pid, const double* x, const double* b, const double* d, double* y,
                          long long* fast_rows) {
     constexpr bool NEED_B = (MODE == 2 || MODE == 3), NEED_D = (MODE == 3 && !DPAT);
-    const size_t stage_bytes = box_stage_bytes<double>(P, RZ, NB, NEED_B, NEED_D) - BOX_DESC_BYTES;
-    const int bcap = NB + 4;
+    const size_t stage_bytes = box_stage_bytes<double>(P, RZ, NB, NEED_B, NEED_D);
+    const int bcap = NB + 4, pcap = NB + 16;
+    const size_t rb = box_rec_bytes(RZ);
+    std::vector<unsigned char> rec(rb);
     for (int cta = 0; cta < ctas; ++cta) {
         std::vector<unsigned char> stage(stage_bytes, 0);
         for (long long tile = cta; tile < P.ntiles; tile += ctas) {
-            int r0, nb, nrp;
-            box_tile_rows(P, RZ, NB, (int)(tile / P.nchunk), (int)(tile % P.nchunk), r0, nb, nrp);
-            struct { int r0; int nb, nrp; int xoff[RZ + 2], boff[RZ], poff[RZ]; } T;
-            T.r0 = r0; T.nb = nb; T.nrp = nrp;
-            for (int j = 0; j < RZ; ++j) T.boff[j] = 0;
-            constexpr int NCP = box_ncopies(RZ, NEED_B, NEED_D);
-            constexpr int PER = (NCP - (RZ + 2)) / RZ;
-            for (int i = 0; i < NCP; ++i) {
-                const BoxCopy C = box_one_copy<double>(P, RZ, NB, NEED_B, NEED_D, r0, nb, nrp, i);
-                if (C.what == 0) T.xoff[i] = C.off;
-                else if (C.what == 3) T.poff[(i - (RZ + 2)) / PER] = C.off;
-                else T.boff[(i - (RZ + 2)) / PER] = C.off;
-                if (!C.bytes) continue;
+            box_plan_tile<double>(P, RZ, NB, (int)tile, rec.data());
+            const BoxCopy* cp = reinterpret_cast<const BoxCopy*>(rec.data() + BOX_DESC_BYTES);
+            std::memcpy(stage.data(), rec.data(), BOX_DESC_BYTES);
+            for (int i = 0; i < box_ncopies(RZ); ++i) {
+                const BoxCopy& C = cp[i];
+                if (!C.bytes || (C.what == 1 && !NEED_B) || (C.what == 2 && !NEED_D)) continue;
                 MGB_CHECK((size_t)C.dst + C.bytes <= stage_bytes && C.dst % 16 == 0 && C.bytes % 16 == 0, "copy outside the stage or unaligned");
                 const unsigned char* src = C.what == 0 ? reinterpret_cast<const unsigned char*>(x + C.src)
                                            : (C.what == 1 ? reinterpret_cast<const unsigned char*>(b + C.src)
@@ -198,10 +193,11 @@ static void host_box_run(const BoxPlan& P, const BoxCoef<double>& C0, const std:
                 MGB_CHECK((C.what == 3 ? C.src % 8 : C.src % 2) == 0, "unaligned source of a bulk copy");
                 std::memcpy(stage.data() + C.dst, src, C.bytes);
             }
-            const double* sx = reinterpret_cast<const double*>(stage.data());
-            const double* sb = sx + P.xtotal;
-            const double* sd = sb + (NEED_B ? RZ * bcap : 0);
-            const uint16_t* sp = reinterpret_cast<const uint16_t*>(sd + (NEED_D ? RZ * bcap : 0));
+            const BoxDesc& T = *reinterpret_cast<const BoxDesc*>(stage.data());
+            const double* sx = reinterpret_cast<const double*>(stage.data() + BOX_DESC_BYTES);
+            const uint16_t* sp = reinterpret_cast<const uint16_t*>(sx + P.xtotal);
+            const double* sb = reinterpret_cast<const double*>(sp + RZ * pcap);
+            const double* sd = sb + RZ * bcap;
             for (int t = 0; t < T.nb; ++t) {
                 const double* xc[RZ + 2];
                 const double* bp[RZ];
@@ -290,15 +286,29 @@ static long long host_lines_run(const HostPatterns<double>& hp, const BoxInfo& B
     return slow;
 }
 
-template <int R>
-static void host_gx_run(const GridXfer& X, const std::vector<PatEntry<double>>& ent, const double* x, double* y) {
-    const int gpp = (X.N[1] + R - 1) / R;
-    for (int K = 0; K < X.N[2]; ++K)
-        for (int q = 0; q < gpp; ++q)
-            for (int I = 0; I < X.N[0]; ++I) {
-                if (X.kind == 2) gx_restrict_thread<double, double, R>(X, I, q * R, K, ent.data(), x, y);
-                else gx_prolong_thread<double, double, R>(X, I, q * R, K, ent.data(), x, y);
+// CPU replay of the grid-hinted transfer kernels (grid_xfer.cuh): their per-row functions, row by row
+static void host_gx_run(const GridXfer& X, const std::vector<double>& tab, const double* x, double* y) {
+    if (X.kind == 1) {
+        const long long cs2 = (long long)X.N[0] * X.N[1];
+        for (int k = 0; k < X.n[2]; ++k)
+            for (int j = 0; j < X.n[1]; ++j) {
+                const double* q = x + ((long long)(k >> 1) * X.N[1] + (j >> 1)) * X.N[0];
+                double* xl = y + ((long long)k * X.n[1] + j) * X.n[0];
+                for (int i = 0; i < X.n[0]; ++i) xl[i] = gxp_row<double, double>(tab.data(), q, X.N[0], cs2, i, j & 1, k & 1, xl[i]);
             }
+    } else {
+        const long long S = X.n[0], S2 = (long long)X.n[0] * X.n[1];
+        for (int K = 0; K < X.N[2]; ++K)
+            for (int J = 0; J < X.N[1]; ++J) {
+                const int cy = gx_class(J, X.N[1]), cz = gx_class(K, X.N[2]);
+                for (int I = 0; I < X.N[0]; ++I) {
+                    const int cx = gx_class(I, X.N[0]);
+                    y[((long long)K * X.N[1] + J) * X.N[0] + I] =
+                        gxr_row<double, double>(tab.data() + (cx + 3 * cy + 9 * cz) * 27, x + S2 * (2LL * K) + S * (2LL * J) + 2 * I, S, S2,
+                                                gx_allowed(cx, X.N[0]), gx_allowed(cy, X.N[1]), gx_allowed(cz, X.N[2]));
+                }
+            }
+    }
 }
 
 extern "C" {
@@ -494,6 +504,19 @@ int mgb200_cycle(mgb200_handle h, const void* b, void* x) {
         const bool xzero = (H->norm(n * H->m, H->ucur) == 0.0);  // `if norm(x)>0.0` (MGcycle.jl:29)
         H->cycle_top(xzero);
         H->d2h_vec(H->ucur, x, n);
+    });
+    MGB_CATCH
+}
+
+int mgb200_precondition(mgb200_handle h, const void* r, void* z) {
+    MGB_TRY
+    MGB_CHECK(r && z, "null vector");
+    MGB_BOTH(h, {
+        H->ensure_work();
+        const long long n = H->L[0].n;
+        H->h2d_vec(r, H->L[0].b, n);
+        H->cycle_top(true);      // z .= 0 is a flag, not a copy: the first sweep from zero is x = d .* b
+        H->d2h_vec(H->ucur, z, n);
     });
     MGB_CATCH
 }
@@ -855,9 +878,9 @@ int mgb200_host_grid_transfer(int kind, int dim, const int64_t* n_fine_nodes, co
             for (int k = hp.pat_off[p]; k < hp.pat_off[p + 1]; ++k) acc = acc + hp.val[k] * x[hp.c0[row] + hp.delta[k]];
             y[row] = kind == 1 ? y[row] + acc : acc;
         }
-    } else if (lines_per_thread == 1) host_gx_run<1>(X, ent, x, y);
-    else if (lines_per_thread == 2) host_gx_run<2>(X, ent, x, y);
-    else host_gx_run<4>(X, ent, x, y);
+    } else {
+        host_gx_run(X, gx_dense_table<double>(X, hp.val), x, y);
+    }
     info[0] = 1;
     MGB_CATCH
 }

@@ -216,10 +216,17 @@ struct Hierarchy : HierarchyBase {
             // the hint is only kept for the operator it describes exactly (grid_xfer.cuh); otherwise nothing changes
             HostPatterns<RT> hp;
             upload_csr<RT>(ctx, lv.P, n, nc, pcp, prv, static_cast<const RT*>(pnz), base, false, true, &hp);
-            if (lv.P.pat.present) gx_verify_prolongation<RT>(hp, n, lv.gn, lv.gN, lv.P.gx);
+            auto dense = [&](Csr<RT>& M) {      // dense value table of a verified hint (grid_xfer.cuh)
+                if (!M.gx.ok) return;
+                const std::vector<RT> t = gx_dense_table<RT>(M.gx, hp.val);
+                RT* dt = dev_alloc<RT>(t.size());
+                MGB_CUDA(cudaMemcpy(dt, t.data(), t.size() * sizeof(RT), cudaMemcpyHostToDevice));
+                M.gx.tab = dt;
+            };
+            if (lv.P.pat.present && gx_verify_prolongation<RT>(hp, n, lv.gn, lv.gN, lv.P.gx)) dense(lv.P);
             hp = HostPatterns<RT>();
             upload_csr<RT>(ctx, lv.R, nc, n, rcp, rrv, static_cast<const RT*>(rnz), base, false, true, &hp);
-            if (lv.R.pat.present) gx_verify_restriction<RT>(hp, nc, lv.gn, lv.gN, lv.R.gx);
+            if (lv.R.pat.present && gx_verify_restriction<RT>(hp, nc, lv.gn, lv.gN, lv.R.gx)) dense(lv.R);
         } else {
             upload_csr<RT>(ctx, lv.P, n, nc, pcp, prv, static_cast<const RT*>(pnz), base, false);
             upload_csr<RT>(ctx, lv.R, nc, n, rcp, rrv, static_cast<const RT*>(rnz), base, false);
@@ -1172,6 +1179,7 @@ struct Hierarchy : HierarchyBase {
         const auto key = std::make_tuple(b, x, scratch, xzero, ctype);
         auto it = graphs.find(key);
         if (it == graphs.end()) {
+            for (int l = 0; l < levels - 1; ++l) box_prepare<TV>(ctx, L[l].A);    // allocations stay outside the capture
             const long long l0 = ctx.launches;
             MGB_CUDA(cudaStreamBeginCapture(ctx.stream, cudaStreamCaptureModeThreadLocal));
             TV* res = nullptr;

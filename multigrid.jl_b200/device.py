@@ -113,8 +113,9 @@ class DeviceHierarchy:
                 n = param.As[l].shape[1]
                 nc = param.As[l + 1].shape[1]
                 assert param.Ps[l].shape == (nc, n) and param.Rs[l].shape == (n, nc)
-                if os.environ.get("MGB200_GRID_TRANSFERS", "0") != "0" and len(param.Meshes) > l + 1:
-                    # grid hint for the transfer operators (csrc/grid_xfer.cuh; off by default, not yet run on a GPU)
+                if len(getattr(param, "Meshes", []) or []) > l + 1:
+                    # grid hint for the transfer operators (csrc/grid_xfer.cuh): the meshes MGsetup keeps anyway
+                    # (param.Meshes, MGsetup.jl:94-98); verified against Ps[l] / Rs[l] at upload, ignored if it does not hold
                     nf_, nc_ = _i64(np.asarray(param.Meshes[l].n) + 1), _i64(np.asarray(param.Meshes[l + 1].n) + 1)
                     _check(L.mgb200_set_level_grid(self.h, l + 1, len(nf_), _ptr(nf_), _ptr(nc_)))
                 _check(L.mgb200_upload_level(self.h, l + 1, ctypes.c_int64(n), ctypes.c_int64(nc),
@@ -265,6 +266,13 @@ class DeviceHierarchy:
         xx = self._vec(x, "x").copy(order="F")
         _check(lib().mgb200_cycle(self.h, _ptr(b), _ptr(xx)))
         return xx
+
+    def precondition(self, r, out=None):
+        """z = M^-1 r: one cycle from a zero initial guess (the closure of getMultigridPreconditioner)."""
+        r = self._vec(r, "r")
+        z = np.empty_like(r, order="F") if out is None else out
+        _check(lib().mgb200_precondition(self.h, _ptr(r), _ptr(z)))
+        return z
 
     def solveMG(self, b, x, tol, max_iter):
         b = self._vec(b, "b")

@@ -111,10 +111,13 @@ def _window(own_lo, own_hi, n_planes, margin, align):
 
 
 def setup_slab_hierarchy(window_operator, domain, n_cells, param, rank, world, replicate_below=200000,
-                         gather=None, verbose=False):
-    """Distributed twin of ``MGsetup`` (Galerkin path, MGsetup.jl:7-138) for rank ``rank``.
+                         gather=None, verbose=False, rediscretise=False):
+    """Distributed twin of ``MGsetup`` (MGsetup.jl:7-138) for rank ``rank``.
 
-    window_operator(level_cells, plane_lo, plane_hi) -> principal sub-matrix of the fine operator.
+    window_operator(level_cells, plane_lo, plane_hi) -> principal sub-matrix of the operator on the mesh with
+    ``level_cells`` cells.  Galerkin path (default): only the fine level uses it, coarser operators are windowed
+    products R A P.  rediscretise=True: the multilevelOperatorConstructor path (MGsetup.jl:28,105-106 with a
+    parameter-free PDE, restrictParams = identity): EVERY level's operator is window_operator on that level's mesh.
     gather(obj) -> list of obj from all ranks (host all-gather; identity list for world == 1).
     Returns a DistHierarchy; ``param`` supplies levels / relaxType / relaxParam / VAL."""
     n_cells = np.asarray(n_cells, dtype=np.int64)
@@ -143,6 +146,9 @@ def setup_slab_hierarchy(window_operator, domain, n_cells, param, rank, world, r
     if world == 1:
         k = min(k, L - 1)
     nd = k                      # number of distributed levels: 0..k-1
+    if rediscretise:
+        return _setup_slab_rediscretised(window_operator, domain, n_cells, param, rank, world, gather, verbose,
+                                         cells, nrows, nd, L)
     # ---- owned planes per level and the fine window -------------------------------------------
     own = [slab_planes(int(cells[l][2]), world) for l in range(nd + 1)]
     # Fine window.  Only the plane at a cut end of a window holds inexact rows, on EVERY level: the fine window is a
@@ -228,6 +234,79 @@ def setup_slab_hierarchy(window_operator, domain, n_cells, param, rank, world, r
                      param.coarseSolveType)
     Mk = getRegularMesh(domain, cells[nd])
     MGsetup(A_k_T, Mk, rep, 1)
+    out.replicated = rep
+    out.nd = nd
+    out.cells = cells
+    return out
+
+
+def _setup_slab_rediscretised(window_operator, domain, n_cells, param, rank, world, gather, verbose, cells, nrows, nd, L):
+    """Rediscretised hierarchy, rank's rows only: level l's owned rows come from the operator on the window of owned
+    planes plus one plane on either side (a principal sub-matrix whose owned rows are complete); P from the 1-D
+    interpolations restricted to the owned fine planes, R to the owned coarse planes."""
+    VAL = param.VAL
+    rVAL = np.float64
+    relaxParam = param.relaxParam
+    own = [slab_planes(int(cells[l][2]), world) for l in range(nd + 1)]
+    out = DistHierarchy(rank=rank, world=world, n_cells=n_cells, levels=L)
+
+    def lift(Mcsc, row_shift, n_rows_global):
+        Mcsc = sp.csc_matrix(Mcsc)
+        return sp.csc_matrix((Mcsc.data, Mcsc.indices.astype(np.int64) + row_shift, Mcsc.indptr),
+                             shape=(n_rows_global, Mcsc.shape[1]))
+    for l in range(nd):
+        nn = cells[l] + 1
+        ncn = cells[l + 1] + 1
+        plane_f, plane_c = int(nn[0] * nn[1]), int(ncn[0] * ncn[1])
+        n_glob, nc_glob = nrows[l], nrows[l + 1]
+        olo, ohi = own[l][rank]
+        c_olo, c_ohi = own[l + 1][rank]
+        # ---- A: window = owned planes + one on either side -----------------------------------------------------
+        wlo, whi = max(0, olo - 1), min(int(nn[2]), ohi + 1)
+        A = sp.csc_matrix(window_operator(cells[l], wlo, whi))
+        if A.dtype != VAL:
+            A = sp.csc_matrix(A, dtype=VAL)
+        AT = _csc(A.conj().T) if np.iscomplexobj(A.data) else _csc(A.T)
+        d_win = getRelaxPrec(AT, param.relaxType, relaxParam if not isinstance(relaxParam, (list, tuple, np.ndarray))
+                             else relaxParam[l], VAL)
+        r0, r1 = (olo - wlo) * plane_f, (ohi - wlo) * plane_f
+        AT_own = lift(AT[:, r0:r1], wlo * plane_f, n_glob)
+        # ---- P rows of the owned fine planes, R rows of the owned coarse planes ---------------------------------
+        P1, _ = get1DFWInterp(int(nn[0]), False)
+        P2, _ = get1DFWInterp(int(nn[1]), False)
+        P3g = sp.csr_matrix(get1DFWInterp(int(nn[2]), False)[0])
+        P12 = sp.kron(P2, P1, format="csc")
+        # fine planes olo..ohi-1 interpolate from coarse planes olo//2 .. (ohi-1+1)//2
+        cp_lo, cp_hi = olo // 2, min(int(ncn[2]), (ohi - 1 + 1) // 2 + 1)
+        Pown = sp.kron(sp.csc_matrix(P3g[olo:ohi, cp_lo:cp_hi]), P12, format="csc")      # (owned fine rows) x (coarse window)
+        PT_own = lift(_csc(Pown.T, dtype=rVAL), cp_lo * plane_c, nc_glob)
+        # coarse planes c_olo..c_ohi-1 restrict from fine planes 2c-1 .. 2c+1
+        fp_lo, fp_hi = max(0, 2 * c_olo - 1), min(int(nn[2]), 2 * (c_ohi - 1) + 2)
+        Pcw = sp.kron(sp.csc_matrix(P3g[fp_lo:fp_hi, c_olo:c_ohi]), P12, format="csc")    # (fine window) x (owned coarse)
+        RT_own = _csc(Pcw, dtype=rVAL)
+        RT_own.data *= 0.5 ** 3
+        RT_own = lift(RT_own, fp_lo * plane_f, n_glob)
+        roff = np.array([o[0] * plane_f for o in own[l]] + [n_glob], dtype=np.int64)
+        croff = np.array([o[0] * plane_c for o in own[l + 1]] + [nc_glob], dtype=np.int64)
+        out.dist_levels.append(DistLevel(n_global=n_glob, row_offsets=roff, AT=AT_own, PT=PT_own, RT=RT_own,
+                                         d=np.ascontiguousarray(d_win[r0:r1]), nc_global=nc_glob,
+                                         coarse_row_offsets=croff))
+        if verbose:
+            print(f"[rank {rank}] level {l + 1} (rediscretised): owned planes {(olo, ohi)}, rows {r1 - r0}, nnz {AT_own.nnz}")
+    # ---- replicated levels: the ordinary rediscretised setup from level nd on -------------------------------------
+    from .mgdef import getMGparam, getMultilevelOperatorConstructor
+    from .mgsetup import MGsetup
+    rep = getMGparam(VAL, np.int64, L - nd, param.numCores, param.maxOuterIter, param.relativeTol,
+                     param.relaxType, relaxParam if not isinstance(relaxParam, (list, tuple, np.ndarray))
+                     else list(relaxParam[nd:]), param.relaxPre, param.relaxPost, param.cycleType,
+                     param.coarseSolveType)
+    Mk = getRegularMesh(domain, cells[nd])
+
+    def full_operator(mesh, _):
+        c = np.asarray(mesh.n, dtype=np.int64)
+        return window_operator(c, 0, int(c[2]) + 1)
+    ctor = getMultilevelOperatorConstructor(None, full_operator, lambda mf, mc, pf, level: pf)
+    MGsetup(ctor, Mk, rep, 1)
     out.replicated = rep
     out.nd = nd
     out.cells = cells

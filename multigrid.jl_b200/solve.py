@@ -119,10 +119,9 @@ def getMultigridPreconditioner(param: MGparam, B, verbose: bool = False):
     if not hierarchyExists(param):
         print("You have to do a setup first.")
     dev = _device(param, B)
-    zero = np.zeros(np.asarray(B).shape, dtype=param.VAL, order="F")
 
     def MMG(r):
-        return dev.cycle(r, zero)
+        return dev.precondition(r)
     return MMG
 
 

@@ -81,3 +81,37 @@ def test_windowed_galerkin_equals_global_rows(n, world, nd_expected):
         assert np.array_equal(np.concatenate([dh.dist_levels[l].d for dh in dhs]), pg.relaxPrecs[l])
     for j, a in enumerate(dhs[0].replicated.As):
         assert (a != pg.As[nd + j]).nnz == 0
+
+
+@pytest.mark.parametrize("n,world", [([8, 8, 64], 4), ([8, 16, 48], 3), ([4, 4, 96], 8), ([8, 8, 32], 2), ([8, 8, 16], 1)])
+def test_rediscretised_slabs_equal_global_rows(n, world):
+    """cfg5's hierarchy (ComplexF64 shifted Laplacian, rediscretised on every level: the multilevelOperatorConstructor
+    path, MGsetup.jl:28,105-106): every rank's owned rows of A, P, R and d equal the global MGsetup bit for bit, and
+    the replicated coarse part equals the global coarse levels."""
+    import scipy.sparse as sp
+    import multigrid_jl_b200 as mg
+    dom = [0, 1, 0, n[1] / n[0], 0, n[2] / n[0]]
+    kappa2 = (2 * np.pi / (10 * (1.0 / n[0])) * 0.35) ** 2
+    op = mg.poisson_window_operator(dom, n, kappa2=kappa2, gamma=0.5)
+    M = mg.getRegularMesh(dom, n)
+    ctor = mg.getMultilevelOperatorConstructor(kappa2, lambda mesh, k2: op(np.asarray(mesh.n), 0, int(mesh.n[2]) + 1),
+                                               lambda mf, mc, pf, level: pf)
+    pg = mg.getMGparam(np.complex128, np.int64, 5, 8, 5, 1e-8, 'Jac', 0.8, 2, 2, 'V')
+    mg.MGsetup(ctor, M, pg, 1)
+    dhs = []
+    for r in range(world):
+        p = mg.getMGparam(np.complex128, np.int64, 5, 8, 5, 1e-8, 'Jac', 0.8, 2, 2, 'V')
+        dhs.append(mg.setup_slab_hierarchy(op, dom, n, p, r, world, replicate_below=100, gather=lambda o: [o],
+                                           rediscretise=True))
+    nd = dhs[0].nd
+    assert nd >= 1 or world == 1
+    for l in range(nd):
+        for name, ref in (("AT", pg.As[l]), ("PT", pg.Ps[l]), ("RT", pg.Rs[l])):
+            glob = sp.hstack([getattr(dh.dist_levels[l], name) for dh in dhs]).tocsc()
+            assert glob.shape == ref.shape and (glob != ref).nnz == 0, (l, name)
+        d = np.concatenate([dh.dist_levels[l].d for dh in dhs])
+        assert np.array_equal(d, pg.relaxPrecs[l])
+    rep = dhs[0].replicated
+    assert len(rep.As) == len(pg.As) - nd
+    for j in range(len(rep.As)):
+        assert (rep.As[j] != pg.As[nd + j]).nnz == 0

@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""Cycle time and per-kernel times (CUDA events) of the bench workload for option sets given on the command line:
+    python tools/tune.py [--cells 256 --levels 6] box=0 box=1,box_variant=1 grid_transfers=0 ...
+Every set is applied with mgb200_set_option on top of the defaults; results must not change by a bit."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import multigrid_jl_b200 as mg  # noqa: E402
+from bench import build_problem  # noqa: E402
+
+
+def timeit(dev, steps=20, top=40):
+    for _ in range(5):
+        dev.cycle_device(True)
+    dev.synchronize()
+    dev.event_record(0)
+    for _ in range(steps):
+        dev.cycle_device(True)
+    dev.event_record(1)
+    ms = dev.event_elapsed_ms(0, 1) / steps
+    dev.profile_enable(True)
+    for _ in range(steps):
+        dev.cycle_device(True)
+    prof = dev.profile_report()
+    dev.profile_enable(False)
+    kern = {f"{r['kind']}{r['level']}": round(1e3 * r["total_ms"] / r["launches"], 1)
+            for r in sorted(prof, key=lambda r: -r["total_ms"])[:top]}
+    return ms, kern
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cells", type=int, default=256)
+    ap.add_argument("--levels", type=int, default=6)
+    ap.add_argument("sets", nargs="*")
+    args = ap.parse_args()
+    A, M, p, b = build_problem(args.cells, args.levels)
+    dev = mg.DeviceHierarchy(p, device=0)
+    x = np.zeros_like(b)
+    _, _, res0 = dev.solveMG(b, x, 0.0, 2)
+    defaults = {}
+    for spec in [""] + list(args.sets):
+        opts = dict(kv.split("=") for kv in spec.split(",") if kv)
+        for k, v in defaults.items():
+            dev.set_option(k, v)
+        for k, v in opts.items():
+            defaults.setdefault(k, {"box": 1, "box_variant": 1, "box_min_rows": 100000, "grid_transfers": 1, "tma": 1,
+                                    "graphs": 1}.get(k, 0))
+            dev.set_option(k, int(v))
+        _, _, res = dev.solveMG(b, x, 0.0, 2)
+        ms, kern = timeit(dev)
+        print(json.dumps({"options": opts or "defaults", "bit_identical": bool(np.array_equal(res, res0)),
+                          "cycle_ms": round(ms, 4), "kernels_us": kern}), flush=True)
+    dev.destroy()
+
+
+if __name__ == "__main__":
+    main()
