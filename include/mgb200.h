@@ -249,7 +249,8 @@ int mgb200_host_detect_box(int64_t n_rows, const int64_t* colptr, const int64_t*
 /* CPU replay of one launch of the box-stencil kernel (csrc/box.cuh) on a matrix given in the upload format: the
  * kernel's own tile plan, copy list and per-thread function run on the host, the stages being host buffers filled where
  * the bulk copies fill shared memory.  Test hook (tests/test_patterns.py); no GPU is used.  x, b, d must carry the 4
- * elements of slack device vectors have.  info[0] = 1 if the matrix qualifies (else y is untouched), info[1] = stencil
+ * elements of slack device vectors have.  mode 0: A x, 2: b - A x, 3: x + d.*(b - A x), 4: the first two sweeps from
+ * zero in one pass, x1 = 0 + d.*x, y = x1 + d.*(x - A x1) with the right-hand side in `x` and d constant per pattern.  info[0] = 1 if the matrix qualifies (else y is untouched), info[1] = stencil
  * shape (7 or 27), info[2] = patterns, info[3] = rows computed on the constant-coefficient fast path. */
 int mgb200_host_box_apply(int64_t n_rows, const int64_t* colptr, const int64_t* rowval, const double* nzval,
                           int index_base, int mode, int rows_per_thread, int base_rows, int ctas, int fold_d,

@@ -66,7 +66,14 @@ struct BoxPlan {
     int wlo[BOX_MAX_RZ + 2], whi[BOX_MAX_RZ + 2];   // window w holds offsets [wlo, NB - 1 + whi] around its centre rows
     int sbase[BOX_MAX_RZ + 2];                      // first element of window w in a stage
     int xtotal;             // elements of all windows of a stage
+    int pbase[BOX_MAX_RZ + 2];                      // first pattern id of the id window w (MODE 4 only)
+    int ptotal;             // pattern ids of all id windows
 };
+// MODE 4 of the box kernel: the first TWO sweeps of a relaxation that starts from x = 0 (MGcycle.jl:128-135 with the
+// reference's `x .= 0` start), x1 = 0 + d.*b, x2 = x1 + d.*(b - A x1), in one pass: the staged windows hold b and the
+// pattern ids of the neighbours, and x1 of a neighbour is recomputed where it is needed.  Needs d folded into the
+// dictionary (d = dtab[pattern id]).
+constexpr int MODE_SWEEP2_FROM_ZERO = 4;
 
 template <typename TV>
 __host__ __device__ constexpr int box_al() { return sizeof(TV) >= 8 ? 2 : 4; }   // elements per 16 bytes (tma_align)
@@ -100,13 +107,21 @@ static inline void box_make_plan(BoxPlan& P, int shape, int RZ, int NB, long lon
         sb += (NB + 2 * span + 2 * AL + AL - 1) / AL * AL;
     }
     P.xtotal = sb;
+    int pb = 0;
+    for (int w = 0; w < RZ + 2; ++w) {
+        P.pbase[w] = pb;
+        pb += (NB + P.whi[w] - P.wlo[w] + 16 + 7) / 8 * 8;
+    }
+    P.ptotal = pb;
 }
 template <typename TV>
-__host__ __device__ inline size_t box_stage_bytes(const BoxPlan& P, int RZ, int NB, bool need_b, bool need_d) {
+__host__ __device__ inline size_t box_stage_bytes(const BoxPlan& P, int RZ, int NB, bool need_b, bool need_d, bool need_pw = false) {
     constexpr int AL = box_al<TV>();
     const size_t bcap = NB + 2 * AL, pcap = NB + 16;
-    const size_t bytes = ((size_t)P.xtotal + (need_b ? RZ * bcap : 0) + (need_d ? RZ * bcap : 0)) * sizeof(TV) + RZ * pcap * 2;
-    return 128 /* BOX_DESC_BYTES */ + (bytes + 127) / 128 * 128;      // [descriptor][x windows][pattern ids][b][d]
+    const size_t bytes = ((size_t)P.xtotal + (need_b ? RZ * bcap : 0) + (need_d ? RZ * bcap : 0)) * sizeof(TV) + RZ * pcap * 2 +
+                         (need_pw ? (size_t)P.ptotal * 2 : 0);
+    // [descriptor][x windows][pattern ids][b][d], or in MODE 4 [descriptor][b windows][pattern ids][id windows]
+    return 128 /* BOX_DESC_BYTES */ + (bytes + 127) / 128 * 128;
 }
 template <typename TV>
 __host__ __device__ inline size_t box_head_bytes(const BoxPlan& P, int nk) {
@@ -122,8 +137,9 @@ struct __align__(16) BoxCopy {
 };
 __host__ __device__ inline int box_floor(int a, int al) { return a & ~(al - 1); }
 __host__ __device__ inline int box_ceil(int a, int al) { return (a + al - 1) & ~(al - 1); }
-// copies of a tile: the windows 0 .. RZ+1, then per row-plane j the pattern ids, the b tile and the d tile
-__host__ __device__ constexpr int box_ncopies(int RZ) { return RZ + 2 + 3 * RZ; }
+// copies of a tile: the windows 0 .. RZ+1, then per row-plane j the pattern ids, the b tile and the d tile, then the
+// pattern-id windows (what = 5, MODE 4 only)
+__host__ __device__ constexpr int box_ncopies(int RZ) { return RZ + 2 + 3 * RZ + RZ + 2; }
 // Stage layout: [descriptor, 128 bytes][x windows][pattern ids][b tiles][d tiles] (b, d only in the modes that read them).
 constexpr int BOX_DESC_BYTES = 128;
 struct BoxDesc {           // what every thread needs of a tile's geometry: element indices of thread 0's elements
@@ -131,6 +147,7 @@ struct BoxDesc {           // what every thread needs of a tile's geometry: elem
     int xoff[BOX_MAX_RZ + 2];   // centre element of window w, from the start of the x region
     int boff[BOX_MAX_RZ];       // row of row-plane j, from the start of the b (or d) region
     int poff[BOX_MAX_RZ];       // same for the pattern ids
+    int pwoff[BOX_MAX_RZ + 2];  // centre element of id window w, from the start of the id-window region (MODE 4)
 };
 static_assert(sizeof(BoxDesc) <= BOX_DESC_BYTES, "descriptor does not fit its slot");
 // One record per tile in device memory: the descriptor (copied into the stage like the data) and the copy list.
@@ -201,6 +218,23 @@ inline void box_plan_tile(const BoxPlan& P, int RZ, int NB, int tile, unsigned c
         Cd.dst = (unsigned)(d_bytes + (size_t)j * bcap * sizeof(TV));
         Cb.bytes = Cd.bytes = (unsigned)((e - a) * sizeof(TV));
     }
+    // pattern-id windows (MODE 4: no b / d tiles in the stage, the id windows follow the id tiles)
+    const size_t pw_bytes = b_bytes;
+    for (int w = 0; w < RZ + 2; ++w, ++n) {
+        BoxCopy& C = cp[n];
+        C.what = 5;
+        const int centre = r0 + (w - 1) * P.S2;
+        const int a0 = box_floor(centre + P.wlo[w], 8);
+        D->pwoff[w] = P.pbase[w] + (centre - a0);
+        if (w - 2 >= nrp) continue;
+        int a = a0, e = box_ceil(centre + nb + P.whi[w], 8);
+        if (a < 0) a = 0;
+        if (e > n8) e = n8;
+        if (e <= a) continue;
+        C.src = a;
+        C.dst = (unsigned)(pw_bytes + (size_t)(P.pbase[w] + (a - a0)) * 2);
+        C.bytes = (unsigned)((e - a) * 2);
+    }
 }
 
 // One thread: RZ rows one plane apart.  xc[w]: the thread's centre element of window w; coefficients from C0 (FAST: every
@@ -208,12 +242,13 @@ inline void box_plan_tile(const BoxPlan& P, int RZ, int NB, int tile, unsigned c
 template <typename TV, int SHAPE, int MODE, bool DPAT, int RZ, bool FAST>
 __host__ __device__ __forceinline__ void box_thread(const BoxCoef<TV>& C0, const TV* ctab, const TV* dtab, int NP, int S,
                                                     const TV* const* xc, const TV* const* bp, const TV* const* dp,
-                                                    const int* pat, TV* out) {
-    TV acc[RZ], xcen[RZ];
+                                                    const int* pat, TV* out, const uint16_t* const* pw = nullptr) {
+    TV acc[RZ], xcen[RZ], bcen[RZ];
 #pragma unroll
     for (int j = 0; j < RZ; ++j) {
         acc[j] = VT<TV>::zero();
         xcen[j] = VT<TV>::zero();
+        bcen[j] = VT<TV>::zero();
     }
 #pragma unroll
     for (int w = 0; w < RZ + 2; ++w) {
@@ -225,7 +260,15 @@ __host__ __device__ __forceinline__ void box_thread(const BoxCoef<TV>& C0, const
 #pragma unroll
             for (int dx = -1; dx <= 1; ++dx) {
                 const bool need = SHAPE == 27 || (dy == 0 && dx == 0) || (inner && (dy == 0 || dx == 0));
-                if (need) X[dy + 1][dx + 1] = q[dy * S + dx];
+                if (need) {
+                    if (MODE == 4) {      // the window holds b: x1 = 0 + d .* b, exactly as diag_scale_pat_kernel computes it
+                        const TV bv = q[dy * S + dx];
+                        if (inner && dy == 0 && dx == 0) bcen[inner ? w - 1 : 0] = bv;
+                        X[dy + 1][dx + 1] = VT<TV>::zero() + dtab[pw[w][dy * S + dx]] * bv;
+                    } else {
+                        X[dy + 1][dx + 1] = q[dy * S + dx];
+                    }
+                }
             }
 #pragma unroll
         for (int j = 0; j < RZ; ++j) {
@@ -247,8 +290,10 @@ __host__ __device__ __forceinline__ void box_thread(const BoxCoef<TV>& C0, const
     for (int j = 0; j < RZ; ++j) {
         TV bval = VT<TV>::zero(), dval = VT<TV>::zero();
         if (MODE == 2 || MODE == 3) bval = *bp[j];
+        if (MODE == 4) bval = bcen[j];
         if (MODE == 3) dval = DPAT ? (FAST ? C0.d0 : dtab[pat[j]]) : *dp[j];
-        out[j] = pat_epilogue<MODE, TV>(acc[j], xcen[j], bval, dval);
+        if (MODE == 4) dval = FAST ? C0.d0 : dtab[pat[j]];
+        out[j] = pat_epilogue<(MODE == 4 ? 3 : MODE), TV>(acc[j], xcen[j], bval, dval);
     }
 }
 
@@ -260,6 +305,7 @@ box_kernel(const __grid_constant__ BoxPlan P, const __grid_constant__ BoxCoef<TV
            TV* __restrict__ y) {
     constexpr bool NEED_B = (MODE == 2 || MODE == 3);
     constexpr bool NEED_D = (MODE == 3 && !DPAT);
+    constexpr bool NEED_PW = (MODE == 4);
     constexpr int NK = SHAPE == 27 ? 27 : 7;
     constexpr int AL = box_al<TV>();
     constexpr int BCAP = NB + 2 * AL, PCAP = NB + 16;
@@ -270,14 +316,14 @@ box_kernel(const __grid_constant__ BoxPlan P, const __grid_constant__ BoxCoef<TV
     TV* ctab = reinterpret_cast<TV*>(smem_raw + 64);
     TV* dtab = ctab + (size_t)NK * P.NP;
     unsigned char* stage0 = smem_raw + box_head_bytes<TV>(P, NK);
-    const unsigned stage_bytes = (unsigned)box_stage_bytes<TV>(P, RZ, NB, NEED_B, NEED_D);
+    const unsigned stage_bytes = (unsigned)box_stage_bytes<TV>(P, RZ, NB, NEED_B, NEED_D, NEED_PW);
     const int t = threadIdx.x;
     if (t == 0) {
         for (int s = 0; s < STAGES; ++s) mbar_init(full + s, 1);
         fence_mbar_init();
     }
     for (int i = t; i < NK * P.NP; i += NB) ctab[i] = ctab_g[i];
-    for (int i = t; i < P.NP; i += NB) dtab[i] = (MODE == 3 && DPAT) ? dtab_g[i] : VT<TV>::zero();
+    for (int i = t; i < P.NP; i += NB) dtab[i] = ((MODE == 3 && DPAT) || MODE == 4) ? dtab_g[i] : VT<TV>::zero();
     // elements of a window that no copy fills (beyond the ends of the vector) are multiplied by zero coefficients:
     // they must be finite, so the stages start out as zeros
     {
@@ -302,7 +348,7 @@ box_kernel(const __grid_constant__ BoxPlan P, const __grid_constant__ BoxCoef<TV
             C.dst = (unsigned)q.y;
             C.bytes = (unsigned)q.z;
             C.what = q.w;
-            if ((C.what == 1 && !NEED_B) || (C.what == 2 && !NEED_D)) C.bytes = 0;
+            if ((C.what == 1 && !NEED_B) || (C.what == 2 && !NEED_D) || (C.what == 5 && !NEED_PW)) C.bytes = 0;
         } else if (t == NCP) {
             C.what = 4;
             C.dst = 0;
@@ -317,7 +363,8 @@ box_kernel(const __grid_constant__ BoxPlan P, const __grid_constant__ BoxCoef<TV
             const void* src = C.what == 0 ? static_cast<const void*>(x + C.src)
                               : (C.what == 1 ? static_cast<const void*>(b + C.src)
                                              : (C.what == 2 ? static_cast<const void*>(d + C.src)
-                                                            : (C.what == 3 ? static_cast<const void*>(pid + C.src) : static_cast<const void*>(rec))));
+                                                            : ((C.what == 3 || C.what == 5) ? static_cast<const void*>(pid + C.src)
+                                                                                            : static_cast<const void*>(rec))));
             bulk_g2s(st + C.dst, src, C.bytes, full + s);
         }
     };
@@ -333,15 +380,20 @@ box_kernel(const __grid_constant__ BoxPlan P, const __grid_constant__ BoxCoef<TV
         const uint16_t* sp = reinterpret_cast<const uint16_t*>(sx + P.xtotal);
         const TV* sb = reinterpret_cast<const TV*>(sp + RZ * PCAP);
         const TV* sd = sb + RZ * BCAP;
+        const uint16_t* spw = sp + RZ * PCAP;          // MODE 4: the id windows take the place of the b / d tiles
         mbar_wait(full + s, STAGES == 2 ? ((it >> 1) & 1) : (it & 1));
         const int nb = D->nb, nrp = D->nrp;
         const TV* xc[RZ + 2];
+        const uint16_t* pwc[RZ + 2];
         const TV* bp[RZ];
         const TV* dp[RZ];
         int pat[RZ];
         bool mine_fast = true;
 #pragma unroll
-        for (int w = 0; w < RZ + 2; ++w) xc[w] = sx + D->xoff[w] + t;
+        for (int w = 0; w < RZ + 2; ++w) {
+            xc[w] = sx + D->xoff[w] + t;
+            pwc[w] = spw + (NEED_PW ? D->pwoff[w] : 0) + t;
+        }
 #pragma unroll
         for (int j = 0; j < RZ; ++j) {
             bp[j] = sb + D->boff[j] + t;
@@ -353,8 +405,8 @@ box_kernel(const __grid_constant__ BoxPlan P, const __grid_constant__ BoxCoef<TV
         const bool fast = __all_sync(0xffffffffu, mine_fast);
         if (t < nb) {
             TV out[RZ];
-            if (fast) box_thread<TV, SHAPE, MODE, DPAT, RZ, true>(C0, ctab, dtab, P.NP, P.S, xc, bp, dp, pat, out);
-            else box_thread<TV, SHAPE, MODE, DPAT, RZ, false>(C0, ctab, dtab, P.NP, P.S, xc, bp, dp, pat, out);
+            if (fast) box_thread<TV, SHAPE, MODE, DPAT, RZ, true>(C0, ctab, dtab, P.NP, P.S, xc, bp, dp, pat, out, pwc);
+            else box_thread<TV, SHAPE, MODE, DPAT, RZ, false>(C0, ctab, dtab, P.NP, P.S, xc, bp, dp, pat, out, pwc);
             const int row0 = D->r0 + t;
 #pragma unroll
             for (int j = 0; j < RZ; ++j)
@@ -366,6 +418,89 @@ box_kernel(const __grid_constant__ BoxPlan P, const __grid_constant__ BoxCoef<TV
         }
         __syncthreads();
         if (STAGES == 1 && issuer && tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x, 0);
+    }
+}
+
+// ---- direct form: no staging at all ----------------------------------------------------------------------------------
+// The same unrolled chains with x read straight from global memory through the read-only path: every load of a warp is
+// a contiguous 256-byte segment, the +-1 and +-S neighbours hit L1, the +-S2 planes hit L2, and nothing synchronises -
+// 64 independent warps per SM with 7 ... 27 loads in flight each hide the latency that the staged form has to hide
+// with its two-stage pipeline and a CTA barrier per tile (profiles/r02e_ncu_box_v0_raw.csv: barrier stall 13.7 cycles
+// per issue, no pipe above 47 %).  Rows whose zero-coefficient neighbours would lie outside the input vector (the first
+// and the last plane) walk the dictionary entry by entry instead, like pat_kernel.
+template <typename TV, int SHAPE, int MODE, bool DPAT, int RZ, int NT>
+__global__ void __launch_bounds__(NT)
+box_direct_kernel(const __grid_constant__ BoxPlan P, const __grid_constant__ BoxCoef<TV> C0, const __grid_constant__ PutPlan pp,
+                  const uint16_t* __restrict__ pid, const TV* __restrict__ ctab_g, const TV* __restrict__ dtab_g,
+                  const int* __restrict__ pat_off, const PatEntry<TV>* __restrict__ ent, const TV* __restrict__ x,
+                  const TV* __restrict__ b, const TV* __restrict__ d, TV* __restrict__ y) {
+    constexpr int NK = SHAPE == 27 ? 27 : 7;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TV* ctab = reinterpret_cast<TV*>(smem_raw);
+    TV* dtab = ctab + (size_t)NK * P.NP;
+    const int t = threadIdx.x;
+    for (int i = t; i < NK * P.NP; i += NT) ctab[i] = ctab_g[i];
+    for (int i = t; i < P.NP; i += NT) dtab[i] = (MODE == 3 && DPAT) ? dtab_g[i] : VT<TV>::zero();
+    __syncthreads();
+    // plane groups of RZ planes in blockIdx.y (RZ == 1: one "plane" of n_rows), chunks of the plane in blockIdx.x
+    const int g = blockIdx.y;
+    const int nrp = P.nplanes - g * RZ < RZ ? P.nplanes - g * RZ : RZ;
+    const int gbase = g * RZ * P.plane;
+    for (int c0 = blockIdx.x * NT; c0 < P.plane; c0 += gridDim.x * NT) {       // warp-uniform trip count
+        const int c = c0 + t;
+        const bool act = c < P.plane;
+        const int r0 = gbase + (act ? c : 0);
+        int pat[RZ];
+        bool mine_fast = true;
+#pragma unroll
+        for (int j = 0; j < RZ; ++j) {
+            pat[j] = (act && j < nrp) ? (int)__ldg(reinterpret_cast<const unsigned short*>(pid) + r0 + j * P.S2) : P.p0;
+            mine_fast = mine_fast && (pat[j] == P.p0);
+        }
+        // every address of the unrolled chain inside the input vector?  (windows 0 .. RZ+1, offsets up to +-(S+1))
+        const bool safe = nrp == RZ && r0 - P.S2 - P.S - 1 >= P.xlo && r0 + RZ * P.S2 + P.S + 1 < P.xhi;
+        const bool fast = __all_sync(0xffffffffu, mine_fast && (safe || !act));
+        if (!act) continue;
+        if (safe) {
+            const TV* xc[RZ + 2];
+            const TV* bp[RZ];
+            const TV* dp[RZ];
+#pragma unroll
+            for (int w = 0; w < RZ + 2; ++w) xc[w] = x + r0 + (w - 1) * P.S2;
+#pragma unroll
+            for (int j = 0; j < RZ; ++j) {
+                bp[j] = b + r0 + j * P.S2;
+                dp[j] = d + r0 + j * P.S2;
+            }
+            TV out[RZ];
+            if (fast) box_thread<TV, SHAPE, MODE, DPAT, RZ, true>(C0, ctab, dtab, P.NP, P.S, xc, bp, dp, pat, out);
+            else box_thread<TV, SHAPE, MODE, DPAT, RZ, false>(C0, ctab, dtab, P.NP, P.S, xc, bp, dp, pat, out);
+#pragma unroll
+            for (int j = 0; j < RZ; ++j) {
+                const int row = r0 + j * P.S2;
+                y[row] = out[j];
+                if (pp.on) ll_put_edge<TV>(pp, row, out[j]);
+            }
+        } else {
+            for (int j = 0; j < nrp; ++j) {          // exact walk: only the entries the row has
+                const int row = r0 + j * P.S2;
+                const int k0 = __ldg(pat_off + pat[j]), k1 = __ldg(pat_off + pat[j] + 1);
+                TV acc = VT<TV>::zero();
+                for (int k = k0; k < k1; ++k) {
+                    const PatEntry<TV> e = ldg_ent(ent + k);
+                    acc = acc + e.v * ldg_(x + (row + e.delta));
+                }
+                TV bval = VT<TV>::zero(), dval = VT<TV>::zero(), xval = VT<TV>::zero();
+                if (MODE == 2 || MODE == 3) bval = b[row];
+                if (MODE == 3) {
+                    dval = DPAT ? dtab[pat[j]] : d[row];
+                    xval = x[row];
+                }
+                const TV out = pat_epilogue<MODE, TV>(acc, xval, bval, dval);
+                y[row] = out;
+                if (pp.on) ll_put_edge<TV>(pp, row, out);
+            }
+        }
     }
 }
 

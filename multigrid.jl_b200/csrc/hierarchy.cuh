@@ -20,7 +20,8 @@ namespace mgb200 {
 
 enum Kind {
     K_SWEEP = 0, K_RESID = 1, K_SPMV = 2, K_RESTRICT = 3, K_PROLONG = 4, K_DIAG = 5, K_COARSE = 6,
-    K_REDUCE = 7, K_VECTOR = 8, K_COPY = 9, K_NKINDS = 10
+    K_REDUCE = 7, K_VECTOR = 8, K_COPY = 9, K_FIRST2 = 10 /* first two sweeps from x = 0, fused */, K_TAIL = 11 /* coarse levels in one kernel */,
+    K_NKINDS = 12
 };
 
 static inline int env_int(const char* name, int dflt) {
@@ -138,8 +139,11 @@ struct Context {
     int lines_staged = 1;          // 1: TMA-staged form of the line-blocked kernel where the lines fit a CTA, 0: global-memory form
     int tma_min_rows = 200000;     // smaller matrices keep the one-pass kernel (too few tiles per SM)
     int use_box = 1;               // box-stencil kernel (box.cuh) for box-structured square operators (MGB200_BOX)
-    int box_variant = 0;           // (rows per thread, base rows per tile, stages): see launch_box (MGB200_BOX_VARIANT)
+    int box_variant = 1;           // (rows per thread, base rows per tile, stages): see launch_box (MGB200_BOX_VARIANT)
+    int box_variant27 = -1;        // >= 0: another variant for the 27-point levels (MGB200_BOX_VARIANT27)
     int box_min_rows = 100000;
+    int gxp_lines = 1;             // fine lines per thread of the grid-hinted prolongation (1, 2, 4)
+    int fuse_first_sweeps = 1;     // first two sweeps from x = 0 in one pass of the box kernel (MGB200_FUSE_FIRST)
     int split_test = 0;            // > 0: every dictionary pass runs as interior + both ends (test hook)
     int use_overlap = 0;           // multi-GPU: halo exchange beside the interior rows (MGB200_OVERLAP=1; measured
                                    // slower than the serial exchange at N = 2, profiles/r01e_bench_n2_*: default off)
@@ -171,8 +175,11 @@ struct Context {
         use_tma = env_int("MGB200_TMA", 1);
         tma_min_rows = env_int("MGB200_TMA_MIN_ROWS", 200000);
         use_box = env_int("MGB200_BOX", 1);
-        box_variant = env_int("MGB200_BOX_VARIANT", 0);
+        box_variant = env_int("MGB200_BOX_VARIANT", 1);
+        box_variant27 = env_int("MGB200_BOX_VARIANT27", -1);
         box_min_rows = env_int("MGB200_BOX_MIN_ROWS", 100000);
+        fuse_first_sweeps = env_int("MGB200_FUSE_FIRST", 1);
+        gxp_lines = env_int("MGB200_GXP_LINES", 1);
         lines = env_int("MGB200_LINES", 0);
         grid_transfers = env_int("MGB200_GRID_TRANSFERS", 1);
         lines_min_rows = env_int("MGB200_LINES_MIN_ROWS", 50000);
@@ -252,6 +259,14 @@ struct Launch {
             r.e1 = c.get_event();
             cudaEventRecord(r.e0, c.stream);
         }
+    }
+    void cancel() {          // nothing was launched under this bracket after all
+        c.launches--;
+        if (rec) {
+            c.ev_pool.push_back(r.e0);
+            c.ev_pool.push_back(r.e1);
+        }
+        rec = false;
     }
     ~Launch() {
         if (rec) {

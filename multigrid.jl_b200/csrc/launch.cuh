@@ -229,10 +229,13 @@ static bool launch_grid_xfer(Context& ctx, const Csr<TA>& M, int mode, const TV*
     if (!((X.kind == 1 && mode == MODE_ADD) || (X.kind == 2 && mode == MODE_SPMV))) return false;
     if (dry) return true;      // the caller only asks whether this kernel will run (byte accounting)
     const int width = X.kind == 1 ? X.n[0] : X.N[0];
-    const long long nlines = X.kind == 1 ? (long long)X.n[1] * X.n[2] : (long long)X.N[1] * X.N[2];
+    const int lpt = ctx.gxp_lines == 2 || ctx.gxp_lines == 4 ? ctx.gxp_lines : 1;
+    const long long nlines = X.kind == 1 ? (long long)((X.n[1] + lpt - 1) / lpt) * X.n[2] : (long long)X.N[1] * X.N[2];
     const int nt = std::min(1024, (width + 31) / 32 * 32);
     const int grid = (int)std::min<long long>(nlines, (long long)ctx.sm_count * std::max(1, 2048 / nt) * 4);
-    if (X.kind == 1) gxp_kernel<TA, TV><<<grid, nt, 0, ctx.stream>>>(X, static_cast<const TA*>(X.tab), x, y);
+    if (X.kind == 1 && lpt == 1) gxp_kernel<TA, TV, 1><<<grid, nt, 0, ctx.stream>>>(X, static_cast<const TA*>(X.tab), x, y);
+    else if (X.kind == 1 && lpt == 2) gxp_kernel<TA, TV, 2><<<grid, nt, 0, ctx.stream>>>(X, static_cast<const TA*>(X.tab), x, y);
+    else if (X.kind == 1) gxp_kernel<TA, TV, 4><<<grid, nt, 0, ctx.stream>>>(X, static_cast<const TA*>(X.tab), x, y);
     else gxr_kernel<TA, TV><<<grid, nt, 0, ctx.stream>>>(X, static_cast<const TA*>(X.tab), x, y);
     MGB_LAUNCH_CHECK();
     return true;
@@ -251,7 +254,8 @@ static bool launch_box_variant(Context& ctx, const Csr<TV>& M, int mode, const T
     P.NP = X.NP;
     if (P.ntiles <= 0 || (long long)M.n_rows + 2LL * D.S2 + NB >= (1LL << 31) || (RZ > 1 && M.n_rows % D.S2 != 0)) return false;
     const bool need_b = (mode == MODE_RESID || mode == MODE_SWEEP), need_d = (mode == MODE_SWEEP && !dpat);
-    const size_t smem = box_head_bytes<TV>(P, X.shape) + STAGES * box_stage_bytes<TV>(P, RZ, NB, need_b, need_d);
+    const bool need_pw = (mode == MODE_SWEEP2_FROM_ZERO);
+    const size_t smem = box_head_bytes<TV>(P, X.shape) + STAGES * box_stage_bytes<TV>(P, RZ, NB, need_b, need_d, need_pw);
     if (smem > (size_t)ctx.max_smem_optin) return false;
     // the tile records are planned outside stream capture (box_prepare, called before a cycle graph is captured)
     if (!prepare_only && !X.has_records(P, RZ, NB)) {
@@ -274,10 +278,41 @@ static bool launch_box_variant(Context& ctx, const Csr<TV>& M, int mode, const T
 #define MGB_BXS(MODE, DP) { if (X.shape == 7) MGB_BX(7, MODE, DP) else MGB_BX(27, MODE, DP) }
     if (mode == MODE_SPMV) MGB_BXS(MODE_SPMV, false)
     else if (mode == MODE_RESID) MGB_BXS(MODE_RESID, false)
+    else if (mode == MODE_SWEEP2_FROM_ZERO) MGB_BXS(MODE_SWEEP2_FROM_ZERO, true)
     else if (dpat) MGB_BXS(MODE_SWEEP, true)
     else MGB_BXS(MODE_SWEEP, false)
 #undef MGB_BXS
 #undef MGB_BX
+    MGB_LAUNCH_CHECK();
+    return true;
+}
+// direct form (box_direct_kernel): no staging, RZ rows per thread one plane apart
+template <typename TV, int RZ>
+static bool launch_box_direct(Context& ctx, const Csr<TV>& M, int mode, const TV* x, const TV* b, const TV* d,
+                              const TV* dpat, TV* y, const PutPlan& pp, bool prepare_only) {
+    const BoxDict<TV>& X = M.box;
+    const PatDict<TV>& D = M.pat;
+    constexpr int NT = 256;
+    BoxPlan P;
+    box_make_plan<TV>(P, X.shape, RZ, NT, M.n_rows, D.S, D.S2, D.xlo, D.xhi, X.npat, X.p0);
+    P.NP = X.NP;
+    if ((long long)M.n_rows + 2LL * D.S2 + NT >= (1LL << 31) || (RZ > 1 && M.n_rows % D.S2 != 0)) return false;
+    const int ngroups = (P.nplanes + RZ - 1) / RZ;
+    if (ngroups > 65535) return false;
+    if (prepare_only) return true;
+    const size_t smem = ((size_t)X.shape * P.NP + P.NP) * sizeof(TV);
+    const int chunks = (P.plane + NT - 1) / NT;
+    const int gx = std::max(1, std::min(chunks, ctx.sm_count * 32 / ngroups + 1));
+    const dim3 grid(gx, ngroups);
+#define MGB_BD(SHAPE, MODE, DP) \
+    box_direct_kernel<TV, SHAPE, MODE, DP, RZ, NT><<<grid, NT, smem, ctx.stream>>>(P, X.c0, pp, D.pid, X.ctab, X.dtab, D.pat_off, D.ent, x, b, d, y)
+#define MGB_BDS(MODE, DP) { if (X.shape == 7) MGB_BD(7, MODE, DP); else MGB_BD(27, MODE, DP); }
+    if (mode == MODE_SPMV) MGB_BDS(MODE_SPMV, false)
+    else if (mode == MODE_RESID) MGB_BDS(MODE_RESID, false)
+    else if (dpat) MGB_BDS(MODE_SWEEP, true)
+    else MGB_BDS(MODE_SWEEP, false)
+#undef MGB_BDS
+#undef MGB_BD
     MGB_LAUNCH_CHECK();
     return true;
 }
@@ -286,21 +321,22 @@ static bool launch_box(Context& ctx, const Csr<TA>& M, int mode, const TV* x, co
                        TV* y, const PutPlan& pp, bool prepare_only = false) {
     if constexpr (std::is_same<TA, TV>::value && (std::is_same<TV, double>::value || std::is_same<TV, cplx>::value)) {
         if (!M.box.ok || !ctx.use_box || M.n_rows < ctx.box_min_rows) return false;
+        const int variant = (M.box.shape == 27 && ctx.box_variant27 >= 0) ? ctx.box_variant27 : ctx.box_variant;
         if (!prepare_only) {
             if (mode == MODE_ADD || x == y) return false;
+            // the fused first two sweeps: b is the staged vector, d must be folded, no ghost rows, staged variants only
+            if (mode == MODE_SWEEP2_FROM_ZERO && (!dpat || pp.on || M.pat.xlo != 0 || M.n_rows != M.n_cols || (variant >= 8 && variant <= 10)))
+                return false;
             if ((reinterpret_cast<uintptr_t>(x) & 15) || (b && (reinterpret_cast<uintptr_t>(b) & 15)) ||
                 (d && (reinterpret_cast<uintptr_t>(d) & 15)))
                 return false;
         }
         constexpr int F = sizeof(TV) / 8;      // complex tiles hold half the rows
-        switch (ctx.box_variant) {
+        switch (variant) {
             case 1: return launch_box_variant<TV, 2, 512 / F, 2>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only);
-            case 2: return launch_box_variant<TV, 2, 512 / F, 1>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only);
             case 3: return launch_box_variant<TV, 4, 256 / F, 1>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only);
-            case 4: return launch_box_variant<TV, 4, 256 / F, 2>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only);
-            case 5: return launch_box_variant<TV, 1, 512 / F, 1>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only);
-            case 6: return launch_box_variant<TV, 2, 1024 / F, 1>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only);
-            case 7: return launch_box_variant<TV, 1, 1024 / F, 1>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only);
+            case 11: return launch_box_variant<TV, 4, 1024 / F, 2>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only);
+            case 9: return launch_box_direct<TV, 2>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only);
             default: return launch_box_variant<TV, 1, 1024 / F, 2>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only);
         }
     } else {

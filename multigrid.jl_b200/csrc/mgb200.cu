@@ -171,8 +171,8 @@ template <int SHAPE, int MODE, bool DPAT, int RZ>
 static void host_box_run(const BoxPlan& P, const BoxCoef<double>& C0, const std::vector<double>& ctab, const std::vector<double>& dtab,
                          int NB, int ctas, const uint16_t* pid, const double* x, const double* b, const double* d, double* y,
                          long long* fast_rows) {
-    constexpr bool NEED_B = (MODE == 2 || MODE == 3), NEED_D = (MODE == 3 && !DPAT);
-    const size_t stage_bytes = box_stage_bytes<double>(P, RZ, NB, NEED_B, NEED_D);
+    constexpr bool NEED_B = (MODE == 2 || MODE == 3), NEED_D = (MODE == 3 && !DPAT), NEED_PW = (MODE == 4);
+    const size_t stage_bytes = box_stage_bytes<double>(P, RZ, NB, NEED_B, NEED_D, NEED_PW);
     const int bcap = NB + 4, pcap = NB + 16;
     const size_t rb = box_rec_bytes(RZ);
     std::vector<unsigned char> rec(rb);
@@ -184,13 +184,13 @@ static void host_box_run(const BoxPlan& P, const BoxCoef<double>& C0, const std:
             std::memcpy(stage.data(), rec.data(), BOX_DESC_BYTES);
             for (int i = 0; i < box_ncopies(RZ); ++i) {
                 const BoxCopy& C = cp[i];
-                if (!C.bytes || (C.what == 1 && !NEED_B) || (C.what == 2 && !NEED_D)) continue;
+                if (!C.bytes || (C.what == 1 && !NEED_B) || (C.what == 2 && !NEED_D) || (C.what == 5 && !NEED_PW)) continue;
                 MGB_CHECK((size_t)C.dst + C.bytes <= stage_bytes && C.dst % 16 == 0 && C.bytes % 16 == 0, "copy outside the stage or unaligned");
                 const unsigned char* src = C.what == 0 ? reinterpret_cast<const unsigned char*>(x + C.src)
                                            : (C.what == 1 ? reinterpret_cast<const unsigned char*>(b + C.src)
                                                           : (C.what == 2 ? reinterpret_cast<const unsigned char*>(d + C.src)
                                                                          : reinterpret_cast<const unsigned char*>(pid + C.src)));
-                MGB_CHECK((C.what == 3 ? C.src % 8 : C.src % 2) == 0, "unaligned source of a bulk copy");
+                MGB_CHECK(((C.what == 3 || C.what == 5) ? C.src % 8 : C.src % 2) == 0, "unaligned source of a bulk copy");
                 std::memcpy(stage.data() + C.dst, src, C.bytes);
             }
             const BoxDesc& T = *reinterpret_cast<const BoxDesc*>(stage.data());
@@ -200,11 +200,15 @@ static void host_box_run(const BoxPlan& P, const BoxCoef<double>& C0, const std:
             const double* sd = sb + RZ * bcap;
             for (int t = 0; t < T.nb; ++t) {
                 const double* xc[RZ + 2];
+                const uint16_t* pwc[RZ + 2];
                 const double* bp[RZ];
                 const double* dp[RZ];
                 int pat[RZ];
                 bool fast = true;
-                for (int w = 0; w < RZ + 2; ++w) xc[w] = sx + T.xoff[w] + t;
+                for (int w = 0; w < RZ + 2; ++w) {
+                    xc[w] = sx + T.xoff[w] + t;
+                    pwc[w] = sp + RZ * pcap + (NEED_PW ? T.pwoff[w] : 0) + t;
+                }
                 for (int j = 0; j < RZ; ++j) {
                     bp[j] = sb + T.boff[j] + t;
                     dp[j] = sd + T.boff[j] + t;
@@ -212,8 +216,8 @@ static void host_box_run(const BoxPlan& P, const BoxCoef<double>& C0, const std:
                     fast = fast && pat[j] == P.p0;
                 }
                 double out[RZ];
-                if (fast) box_thread<double, SHAPE, MODE, DPAT, RZ, true>(C0, ctab.data(), dtab.data(), P.NP, P.S, xc, bp, dp, pat, out);
-                else box_thread<double, SHAPE, MODE, DPAT, RZ, false>(C0, ctab.data(), dtab.data(), P.NP, P.S, xc, bp, dp, pat, out);
+                if (fast) box_thread<double, SHAPE, MODE, DPAT, RZ, true>(C0, ctab.data(), dtab.data(), P.NP, P.S, xc, bp, dp, pat, out, pwc);
+                else box_thread<double, SHAPE, MODE, DPAT, RZ, false>(C0, ctab.data(), dtab.data(), P.NP, P.S, xc, bp, dp, pat, out, pwc);
                 if (fast) *fast_rows += T.nrp;
                 for (int j = 0; j < T.nrp; ++j) y[T.r0 + t + (long long)j * P.S2] = out[j];
             }
@@ -684,6 +688,9 @@ int mgb200_set_option(mgb200_handle h, const char* key, int64_t value) {
         else if (k == "tma_min_rows") H->ctx.tma_min_rows = (int)value;
         else if (k == "box") H->ctx.use_box = (int)value;
         else if (k == "box_variant") H->ctx.box_variant = (int)value;
+        else if (k == "box_variant27") H->ctx.box_variant27 = (int)value;
+        else if (k == "fuse_first") H->ctx.fuse_first_sweeps = (int)value;
+        else if (k == "gxp_lines") H->ctx.gxp_lines = (int)value;
         else if (k == "box_min_rows") H->ctx.box_min_rows = (int)value;
         else if (k == "lines") H->ctx.lines = (int)value;
         else if (k == "lines_staged") H->ctx.lines_staged = (int)value;
@@ -766,7 +773,7 @@ int mgb200_host_box_apply(int64_t n_rows, const int64_t* colptr, const int64_t* 
                           const double* b, const double* d, double* y, int64_t* info) {
     MGB_TRY
     MGB_CHECK(colptr && rowval && nzval && x && y && info, "null argument");
-    MGB_CHECK(mode == 0 || mode == 2 || mode == 3, "mode must be 0, 2 or 3");
+    MGB_CHECK(mode == 0 || mode == 2 || mode == 3 || mode == 4, "mode must be 0, 2, 3 or 4");
     MGB_CHECK(rows_per_thread == 1 || rows_per_thread == 2 || rows_per_thread == 4, "rows_per_thread must be 1, 2 or 4");
     MGB_CHECK(base_rows >= 8 && base_rows % 8 == 0 && ctas >= 1, "base_rows must be a multiple of 8");
     MGB_CHECK(mode == 0 || b, "b required");
@@ -784,7 +791,7 @@ int mgb200_host_box_apply(int64_t n_rows, const int64_t* colptr, const int64_t* 
     if (RZ > 1 && n_rows % B.S2 != 0) return 0;
     std::vector<double> dtab(NP, 0.0);
     bool dp = false;
-    if (mode == 3 && fold_d) {
+    if ((mode == 3 && fold_d) || mode == 4) {
         dp = true;
         for (int p = 0; p < hp.npat(); ++p) dtab[p] = d[hp.rep_row[p]];
         C0.d0 = dtab[p0];
@@ -792,12 +799,15 @@ int mgb200_host_box_apply(int64_t n_rows, const int64_t* colptr, const int64_t* 
     BoxPlan P;
     box_make_plan<double>(P, shape, RZ, base_rows, n_rows, B.S, B.S2, 0, (n_rows + 1) & ~1LL, hp.npat(), p0);
     long long fast_rows = 0;
+    std::vector<uint16_t> pidp(hp.pid.size() + 16, 0);       // the device array carries 16 zeroed ids of slack
+    std::copy(hp.pid.begin(), hp.pid.end(), pidp.begin());
 #define MGB_HB(SHAPE, RR)                                                                                                   \
     {                                                                                                                       \
-        if (mode == 0) host_box_run<SHAPE, 0, false, RR>(P, C0, ctab, dtab, base_rows, ctas, hp.pid.data(), x, b, d, y, &fast_rows);      \
-        else if (mode == 2) host_box_run<SHAPE, 2, false, RR>(P, C0, ctab, dtab, base_rows, ctas, hp.pid.data(), x, b, d, y, &fast_rows); \
-        else if (dp) host_box_run<SHAPE, 3, true, RR>(P, C0, ctab, dtab, base_rows, ctas, hp.pid.data(), x, b, d, y, &fast_rows);         \
-        else host_box_run<SHAPE, 3, false, RR>(P, C0, ctab, dtab, base_rows, ctas, hp.pid.data(), x, b, d, y, &fast_rows);                \
+        if (mode == 0) host_box_run<SHAPE, 0, false, RR>(P, C0, ctab, dtab, base_rows, ctas, pidp.data(), x, b, d, y, &fast_rows);      \
+        else if (mode == 2) host_box_run<SHAPE, 2, false, RR>(P, C0, ctab, dtab, base_rows, ctas, pidp.data(), x, b, d, y, &fast_rows); \
+        else if (mode == 4) host_box_run<SHAPE, 4, true, RR>(P, C0, ctab, dtab, base_rows, ctas, pidp.data(), x, b, d, y, &fast_rows);  \
+        else if (dp) host_box_run<SHAPE, 3, true, RR>(P, C0, ctab, dtab, base_rows, ctas, pidp.data(), x, b, d, y, &fast_rows);         \
+        else host_box_run<SHAPE, 3, false, RR>(P, C0, ctab, dtab, base_rows, ctas, pidp.data(), x, b, d, y, &fast_rows);                \
     }
 #define MGB_HBR(SHAPE) { if (RZ == 1) MGB_HB(SHAPE, 1) else if (RZ == 2) MGB_HB(SHAPE, 2) else MGB_HB(SHAPE, 4) }
     if (shape == 7) MGB_HBR(7) else MGB_HBR(27)

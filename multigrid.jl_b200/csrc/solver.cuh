@@ -307,15 +307,38 @@ struct Hierarchy : HierarchyBase {
         int* piv = dev_alloc<int>(N + 1);
         int* info = piv + N;
         MGB_CUDA(cudaMemsetAsync(info, 0, sizeof(int), ctx.stream));
-        for (int k = 0; k < N; ++k) {
-            lu_pivot_kernel<TW><<<1, 256, 0, ctx.stream>>>(a, N, k, piv, info);
-            const int rem = N - k - 1;
-            if (rem > 0) {
-                dim3 blk(32, 8), grd(cdiv(rem, 32), cdiv(rem, 8));
-                lu_update_kernel<TW><<<grd, blk, 0, ctx.stream>>>(a, N, k);
+        // blocked right-looking LU (dense_lu.cuh): per panel of LU_NB columns one cooperative panel kernel, the row
+        // interchanges outside the panel, the triangular solve for U12 and the trailing update as a tiled product
+        {
+            int per_sm = 0;
+            MGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lu_panel_kernel<TW>, 256, 0));
+            MGB_CHECK(per_sm >= 1, "LU panel kernel does not fit an SM");
+            const int pg = std::max(1, std::min(ctx.sm_count * std::min(per_sm, 2), cdiv(N, 256)));
+            LuPivot* cand = dev_alloc<LuPivot>(pg);
+            unsigned* counter = dev_alloc<unsigned>(1);
+            MGB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), ctx.stream));
+            unsigned epoch = 0;
+            for (int k0 = 0; k0 < N; k0 += LU_NB) {
+                int nb = std::min(LU_NB, N - k0);
+                TW* ap = a;
+                int nn = N, kk = k0;
+                void* args[] = {&ap, &nn, &kk, &nb, &piv, &info, &cand, &counter, &epoch};
+                MGB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(lu_panel_kernel<TW>), dim3(pg), dim3(256), args, 0,
+                                                     ctx.stream));
+                epoch += 3u * (unsigned)nb * (unsigned)pg;          // three grid barriers per column
+                if (N > nb) lu_swap_kernel<TW><<<cdiv(N - nb, 256), 256, 0, ctx.stream>>>(a, N, k0, nb, piv);
+                const int rem = N - k0 - nb;
+                if (rem > 0) {
+                    lu_trsm_kernel<TW><<<cdiv(rem, 128), 128, 0, ctx.stream>>>(a, N, k0, nb);
+                    dim3 grd(cdiv(rem, LuTile<TW>::T), cdiv(rem, LuTile<TW>::T));
+                    lu_gemm_kernel<TW><<<grd, 256, 0, ctx.stream>>>(a, N, k0, nb);
+                }
             }
+            MGB_LAUNCH_CHECK();
+            ctx.sync();
+            dev_free(cand);
+            dev_free(counter);
         }
-        MGB_LAUNCH_CHECK();
         std::vector<int> hpiv(N + 1);
         MGB_CUDA(cudaMemcpyAsync(hpiv.data(), piv, (N + 1) * sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
         ctx.sync();
@@ -327,8 +350,21 @@ struct Hierarchy : HierarchyBase {
         MGB_CUDA(cudaMemcpy(coarse.perm, perm.data(), N * sizeof(int), cudaMemcpyHostToDevice));
         coarse.linv = dev_alloc<TW>((size_t)N * N);
         coarse.uinv = dev_alloc<TW>((size_t)N * N);
-        lower_inverse_kernel<TW><<<cdiv(N, 64), 64, 0, ctx.stream>>>(a, N, coarse.linv);
-        upper_inverse_kernel<TW><<<cdiv(N, 64), 64, 0, ctx.stream>>>(a, N, coarse.uinv);
+        MGB_CUDA(cudaMemsetAsync(coarse.linv, 0, (size_t)N * N * sizeof(TW), ctx.stream));
+        MGB_CUDA(cudaMemsetAsync(coarse.uinv, 0, (size_t)N * N * sizeof(TW), ctx.stream));
+        // blocked inversion of the two factors: block rows in dependency order (L top-down, U bottom-up)
+        const int nblk = cdiv(N, TI_NB);
+        for (int bi = 0; bi < nblk; ++bi) {
+            const int r0 = bi * TI_NB, nbk = std::min(TI_NB, N - r0);
+            tri_diag_inv_kernel<TW, false><<<1, TI_NB, 0, ctx.stream>>>(a, N, r0, nbk, coarse.linv);
+            if (r0 > 0) tri_inv_row_kernel<TW, false><<<cdiv(r0, LuTile<TW>::T), 256, 0, ctx.stream>>>(a, N, r0, nbk, coarse.linv);
+        }
+        for (int bi = nblk - 1; bi >= 0; --bi) {
+            const int r0 = bi * TI_NB, nbk = std::min(TI_NB, N - r0);
+            tri_diag_inv_kernel<TW, true><<<1, TI_NB, 0, ctx.stream>>>(a, N, r0, nbk, coarse.uinv);
+            const int right = N - r0 - nbk;
+            if (right > 0) tri_inv_row_kernel<TW, true><<<cdiv(right, LuTile<TW>::T), 256, 0, ctx.stream>>>(a, N, r0, nbk, coarse.uinv);
+        }
         MGB_LAUNCH_CHECK();
         ctx.sync();
         dev_free(a);
@@ -981,6 +1017,19 @@ struct Hierarchy : HierarchyBase {
         Level<TV>& lv = L[l];
         int sweeps = std::max(numit, 1);  // numit = 0 still does one update (MGcycle.jl:134)
         const TV* dpat = (lv.dpat && m == 1 && ctx.use_patterns) ? lv.dpat : nullptr;
+        if (xzero && dpat && sweeps >= 2 && ctx.fuse_first_sweeps && !lv.sp.dist) {
+            // x1 = d .* b and x2 = x1 + d .* (b - A x1) in one pass of the box-stencil kernel (box.cuh, MODE 4)
+            const double bytes = 3.0 * lv.n * sizeof(TV) + csr_bytes<TV, TV>(lv.A, MODE_SWEEP, 1);
+            const double fmt = lv.n * (2.0 * sizeof(TV) + 2.0);
+            Launch La(ctx, K_FIRST2, l + 1, bytes, fmt);
+            if (launch_box<TV, TV>(ctx, lv.A, MODE_SWEEP2_FROM_ZERO, b, nullptr, nullptr, dpat, scratch, no_put())) {
+                std::swap(x, scratch);
+                sweeps -= 2;
+                xzero = false;
+            } else {
+                La.cancel();
+            }
+        }
         if (xzero) {
             if (dpat) {
                 const PutPlan pp = (sweeps > 1 || last_exchanged) ? make_put(l) : no_put();
@@ -1024,7 +1073,7 @@ struct Hierarchy : HierarchyBase {
         }
         typedef typename Wide<TV>::type TW;
         Launch La(ctx, K_COARSE, levels, (double)n * n * sizeof(TW));
-        const int grid = cdiv((long long)n * m * 32, 256);
+        const int grid = cdiv((long long)n * cdiv(m, AP_MC) * 32, 256);
         lower_apply_kernel<TW, TV><<<grid, 256, 0, ctx.stream>>>(n, m, coarse.linv, coarse.perm, b, coarse.y);
         upper_apply_kernel<TW, TV><<<grid, 256, 0, ctx.stream>>>(n, m, coarse.uinv, coarse.y, x);
         MGB_LAUNCH_CHECK();

@@ -27,7 +27,8 @@ _VT_CODE = {np.dtype(np.float64): MGB200_FP64, np.dtype(np.complex128): MGB200_C
 def _real_dtype(VAL):
     """real(VAL): the value type of Ps / Rs (SA-AMG.jl:9-10, MGsetup.jl:80-81)."""
     return np.dtype(np.float32) if np.dtype(VAL) in (np.dtype(np.float32), np.dtype(np.complex64)) else np.dtype(np.float64)
-KIND_NAMES = ["sweep", "resid", "spmv", "restrict", "prolong", "diag", "coarse", "reduce", "vector", "copy"]
+KIND_NAMES = ["sweep", "resid", "spmv", "restrict", "prolong", "diag", "coarse", "reduce", "vector", "copy", "first2sweeps",
+              "coarse_tail"]
 
 _c_i64p = ctypes.POINTER(ctypes.c_int64)
 _vp = ctypes.c_void_p
@@ -491,17 +492,18 @@ def host_lines_apply(M, mode, rows_per_thread, x, b=None, d=None, fold_d=False, 
 def host_box_apply(M, mode, rows_per_thread, base_rows, x, b=None, d=None, fold_d=False, ctas=3):
     """Host-only: CPU replay of one launch of the box-stencil kernel (csrc/box.cuh) - its tile plan, copy list and
     per-thread function - for the operator M^T given by the CSC arrays of ``M``.  mode 0: A x, 2: b - A x,
-    3: x + d.*(b - A x).  Returns (y, info) or None when the matrix does not qualify."""
+    3: x + d.*(b - A x), 4: the fused first two sweeps from zero (x holds the right-hand side).
+    Returns (y, info) or None when the matrix does not qualify."""
     M = sp.csc_matrix(M)
     if not M.has_sorted_indices:
         M.sort_indices()
     n = M.shape[1]
     cp, rv, nz = _i64(M.indptr), _i64(M.indices), np.ascontiguousarray(M.data, dtype=np.float64)
 
-    def slack(v):       # device vectors carry 4 elements of zeroed slack (vec_alloc)
+    def slack(v):       # device vectors carry 4 elements of zeroed slack (vec_alloc), pattern ids 16
         if v is None:
             return None
-        out = np.zeros(n + 4)
+        out = np.zeros(n + 16)
         out[:n] = v
         return out
     xx, bb, dd = slack(x), slack(b), slack(d)

@@ -286,3 +286,34 @@ def test_preconditioner_closure_and_cycle():
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()
+
+
+@pytest.mark.parametrize("VAL,n,nrhs", [(np.float64, 777, 1), (np.complex128, 333, 1), (np.float64, 1100, 5), (np.float64, 40, 1)])
+def test_coarsest_dense_lu_with_pivoting(VAL, n, nrhs):
+    """defineCoarsestAinv / solveCoarsest (MGsetup.jl:350, MGcycle.jl:176-179) on its own: a one-level hierarchy
+    (recursiveCycle with levels == 1 is the coarsest solve, MGcycle.jl:13-18) whose matrix NEEDS row interchanges (zero
+    and tiny diagonal entries), sizes that are no multiple of the panel width; the blocked device LU + blocked
+    triangular inversions must solve it like LAPACK."""
+    import scipy.sparse as sp
+    import multigrid_jl_b200 as mg
+    rng = np.random.default_rng(n)
+    A = sp.random(n, n, density=min(1.0, 12.0 / n), random_state=rng, format="lil", dtype=np.float64)
+    A = A + sp.diags(np.where(rng.random(n) < 0.3, 0.0, rng.standard_normal(n))) + sp.eye(n, k=1) * 0.5 - sp.eye(n, k=-2) * 0.25
+    A = sp.csc_matrix(A).astype(VAL)
+    if VAL == np.complex128:
+        A = A + 1j * sp.csc_matrix(sp.random(n, n, density=min(1.0, 6.0 / n), random_state=rng))
+    Ad = A.toarray()
+    assert np.linalg.cond(Ad) < 1e10
+    p = mg.getMGparam(VAL, np.int64, 1, 8, 1, 1e-12, "Jac", 0.8, 2, 2, 'V')
+    p.As = [sp.csc_matrix(A.conj().T)]          # the hierarchy stores adjoints
+    p.Ps, p.Rs, p.relaxPrecs, p.levels, p.nrhs = [], [], [], 1, nrhs
+    shape = (n,) if nrhs == 1 else (n, nrhs)
+    b = rng.standard_normal(shape).astype(VAL)
+    if VAL == np.complex128:
+        b = b + 1j * rng.standard_normal(shape)
+    dev = mg.DeviceHierarchy(p)
+    x = dev.cycle(np.asfortranarray(b), np.zeros_like(np.asfortranarray(b)))
+    ref = np.linalg.solve(Ad, b)
+    assert np.linalg.norm(x - ref) <= 1e-9 * np.linalg.norm(ref)
+    assert np.linalg.norm(Ad @ x - b) <= 1e-10 * np.linalg.norm(b) * np.linalg.cond(Ad) ** 0.5
+    dev.destroy()

@@ -187,6 +187,13 @@ def test_box_kernel_code_on_the_cpu(n, RZ, NB):
             assert got is not None, (l, mode)
             assert got[1]["shape"] == (7 if l == 0 else 27)
             assert np.array_equal(ref[0].view(np.int64), got[0].view(np.int64)), (l, mode, fold)
+        if ref is not None:
+            # MODE 4: the first two sweeps from x = 0 in one pass == diag_scale followed by one sweep, bit for bit
+            dfold = device.host_lines_apply(mat, 3, 0, np.zeros(N), b, d, True)     # x1 = 0 + d .* (b - A 0): folded d
+            x1 = 0.0 + (dfold[0] / np.where(b != 0, b, 1.0)) * b                      # = dpat[pid] .* b
+            two = device.host_lines_apply(mat, 3, 0, x1, b, d, True)
+            got4 = device.host_box_apply(mat, 4, RZ, NB, b, b, d, True)
+            assert got4 is not None and np.array_equal(two[0].view(np.int64), got4[0].view(np.int64)), l
         if min(n) >= 8 and l == 0 and got is not None:
             assert got[1]["fast_rows"] > 0.2 * N       # interior rows take the constant-coefficient path
 
@@ -379,7 +386,7 @@ def test_split_launches_bit_identical(kind, n, cycle, tma):
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind,n,cycle", [("poisson", [40, 36, 28], 'V'), ("helmholtz", [33, 31, 17], 'W'),
                                           ("poisson", [64, 64, 64], 'F')])
-@pytest.mark.parametrize("variant", ["0", "1", "2", "3", "4", "5", "6", "7"])
+@pytest.mark.parametrize("variant", ["0", "1", "3", "9", "11"])
 def test_box_kernel_bit_identical(kind, n, cycle, variant):
     """csrc/box.cuh: the box-stencil kernel (dense coefficient tables, unrolled 7- / 27-point chains, RZ rows per
     thread one plane apart) on every box-structured 3-D level instead of the dictionary walk: results must not change
