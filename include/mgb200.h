@@ -256,17 +256,14 @@ int mgb200_host_box_apply(int64_t n_rows, const int64_t* colptr, const int64_t* 
                           int index_base, int mode, int rows_per_thread, int base_rows, int ctas, int fold_d,
                           const double* x, const double* b, const double* d, double* y, int64_t* info);
 
-/* Host-only (no GPU): runs the per-thread function of the line-blocked dictionary kernel (csrc/pattern.cuh::
- * pat_lines_thread, __host__ __device__) on the CPU for every thread of a launch - the exact code the GPU executes -
- * for a Float64 matrix given as in mgb200_host_build_patterns.  mode: 0 y = A x, 2 y = b - A x, 3 y = x + d.*(b - A x);
- * rows_per_thread R in {2, 4}, or 0 for the one-row-per-thread dictionary walk (the reference the kernel must match
- * bit for bit); groups_per_tile 0: global-memory form, Q > 0: staged form with tiles of Q groups, the stage being a
- * host buffer filled exactly as the kernel's bulk copies fill shared memory; fold_d != 0: d is read per pattern (first row that carries the pattern).  info[0] = 1 if the matrix has
- * the box structure the kernel needs (y is then written), info[1] = S, info[2] = S2, info[3] = groups that took the
- * row-by-row path. */
-int mgb200_host_lines_apply(int64_t n_rows, const int64_t* colptr, const int64_t* rowval, const double* nzval,
-                            int index_base, int mode, int rows_per_thread, int groups_per_tile, int fold_d, const double* x,
-                            const double* b, const double* d, double* y, int64_t* info);
+/* Host-only (no GPU): the one-row-per-thread dictionary walk of pat_kernel (csrc/pattern.cuh) on the CPU for a square
+ * row-relative matrix given in the upload format - the reference every other kernel form must match bit for bit
+ * (tests/test_patterns.py).  mode 0: y = A x, 2: y = b - A x, 3: y = x + d.*(b - A x); fold_d: d taken per pattern.
+ * info[0] = 1 if the matrix has a row-relative dictionary (else y is untouched), info[1], info[2] = line / plane length
+ * when the offsets have box structure. */
+int mgb200_host_pattern_apply(int64_t n_rows, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+                              int index_base, int mode, int fold_d, const double* x, const double* b, const double* d,
+                              double* y, int64_t* info);
 
 /* Host-only (no GPU): the grid-hinted transfer kernels' per-thread functions (csrc/grid_xfer.cuh, __host__ __device__) run
  * on the CPU for every thread of a launch, for a real Float64 transfer matrix given by its CSC-of-the-transpose arrays

@@ -317,27 +317,27 @@ __global__ void __launch_bounds__(256) tri_inv_row_kernel(const TW* __restrict__
 // y[i*m+c] = sum_{j<=i} Linv[i][j] * b[perm[j]*m+c]      (one warp per row and chunk of up to AP_MC right-hand sides:
 // the factor row is read once per chunk, not once per right-hand side)
 constexpr int AP_MC = 8;
-template <typename TW, typename TV>
+template <typename TW, typename TV, int MC>
 __global__ void lower_apply_kernel(int n, int m, const TW* __restrict__ linv, const int* __restrict__ perm,
                                    const TV* __restrict__ b, TW* __restrict__ y) {
     const int lane = threadIdx.x & 31;
-    const int nch = (m + AP_MC - 1) / AP_MC;
+    const int nch = (m + MC - 1) / MC;
     const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     if (w >= (long long)n * nch) return;
-    const int i = (int)(w / nch), c0 = (int)(w % nch) * AP_MC;
-    const int mc = m - c0 < AP_MC ? m - c0 : AP_MC;
-    TW acc[AP_MC];
+    const int i = (int)(w / nch), c0 = (int)(w % nch) * MC;
+    const int mc = m - c0 < MC ? m - c0 : MC;
+    TW acc[MC];
 #pragma unroll
-    for (int c = 0; c < AP_MC; ++c) acc[c] = VT<TW>::zero();
+    for (int c = 0; c < MC; ++c) acc[c] = VT<TW>::zero();
     for (int j = lane; j <= i; j += 32) {
         const TW l = linv[(size_t)i * n + j];
         const TV* bj = b + (size_t)perm[j] * m + c0;
 #pragma unroll
-        for (int c = 0; c < AP_MC; ++c)
+        for (int c = 0; c < MC; ++c)
             if (c < mc) acc[c] = acc[c] + l * widen(bj[c]);
     }
 #pragma unroll
-    for (int c = 0; c < AP_MC; ++c) {
+    for (int c = 0; c < MC; ++c) {
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) acc[c] = acc[c] + shfl_xor_(acc[c], s);
         if (lane == 0 && c < mc) y[(size_t)i * m + c0 + c] = acc[c];
@@ -345,27 +345,27 @@ __global__ void lower_apply_kernel(int n, int m, const TW* __restrict__ linv, co
 }
 
 // x[i*m+c] = sum_{j>=i} Uinv[i][j] * y[j*m+c]
-template <typename TW, typename TV>
+template <typename TW, typename TV, int MC>
 __global__ void upper_apply_kernel(int n, int m, const TW* __restrict__ uinv, const TW* __restrict__ y,
                                    TV* __restrict__ x) {
     const int lane = threadIdx.x & 31;
-    const int nch = (m + AP_MC - 1) / AP_MC;
+    const int nch = (m + MC - 1) / MC;
     const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     if (w >= (long long)n * nch) return;
-    const int i = (int)(w / nch), c0 = (int)(w % nch) * AP_MC;
-    const int mc = m - c0 < AP_MC ? m - c0 : AP_MC;
-    TW acc[AP_MC];
+    const int i = (int)(w / nch), c0 = (int)(w % nch) * MC;
+    const int mc = m - c0 < MC ? m - c0 : MC;
+    TW acc[MC];
 #pragma unroll
-    for (int c = 0; c < AP_MC; ++c) acc[c] = VT<TW>::zero();
+    for (int c = 0; c < MC; ++c) acc[c] = VT<TW>::zero();
     for (int j = i + lane; j < n; j += 32) {
         const TW u = uinv[(size_t)i * n + j];
         const TW* yj = y + (size_t)j * m + c0;
 #pragma unroll
-        for (int c = 0; c < AP_MC; ++c)
+        for (int c = 0; c < MC; ++c)
             if (c < mc) acc[c] = acc[c] + u * yj[c];
     }
 #pragma unroll
-    for (int c = 0; c < AP_MC; ++c) {
+    for (int c = 0; c < MC; ++c) {
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) acc[c] = acc[c] + shfl_xor_(acc[c], s);
         if (lane == 0 && c < mc) narrow(acc[c], x[(size_t)i * m + c0 + c]);

@@ -205,10 +205,9 @@ __host__ __device__ __forceinline__ TV gxr_row(const TA* tv, const TV* f, long l
     return acc;
 }
 
-// persistent CTAs over groups of LPT fine lines (same k); threads over i.  A thread updates its node of every line of the
-// group: the LPT reads of x_f (the DRAM stream of this kernel: 8 bytes per thread are far too little in flight to cover
-// the latency) are issued first, then the independent chains, then the stores.
-template <typename TA, typename TV, int LPT>
+// persistent CTAs over the fine lines (j, k); threads over i.  (Two or four lines per thread with the x_f reads issued
+// up front measured slower on the B200: 107 / 107 against 99 us at 257^3, profiles/r02_tune_log.txt.)
+template <typename TA, typename TV>
 __global__ void __launch_bounds__(1024) gxp_kernel(const __grid_constant__ GridXfer X, const TA* __restrict__ tabg,
                                                    const TV* __restrict__ xc, TV* __restrict__ xf) {
     __shared__ TA tab[GXP_TAB];
@@ -216,23 +215,12 @@ __global__ void __launch_bounds__(1024) gxp_kernel(const __grid_constant__ GridX
     __syncthreads();
     const int n0 = X.n[0], n1 = X.n[1], N0 = X.N[0], N1 = X.N[1];
     const long long cs2 = (long long)N0 * N1;
-    const int gpl = (n1 + LPT - 1) / LPT;          // groups per plane
-    const int ngroups = gpl * X.n[2];
-    for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
-        const int k = grp / gpl, j0 = (grp - k * gpl) * LPT;
-        const TV* qk = xc + (long long)(k >> 1) * cs2;
-        TV* xl0 = xf + ((long long)k * n1 + j0) * n0;
-        for (int i = threadIdx.x; i < n0; i += blockDim.x) {
-            TV v[LPT];
-#pragma unroll
-            for (int q = 0; q < LPT; ++q) v[q] = (j0 + q < n1) ? xl0[(long long)q * n0 + i] : VT<TV>::zero();
-#pragma unroll
-            for (int q = 0; q < LPT; ++q)
-                if (j0 + q < n1) v[q] = gxp_row<TA, TV>(tab, qk + (long long)((j0 + q) >> 1) * N0, N0, cs2, i, (j0 + q) & 1, k & 1, v[q]);
-#pragma unroll
-            for (int q = 0; q < LPT; ++q)
-                if (j0 + q < n1) xl0[(long long)q * n0 + i] = v[q];
-        }
+    const int nlines = n1 * X.n[2];
+    for (int line = blockIdx.x; line < nlines; line += gridDim.x) {
+        const int k = line / n1, j = line - k * n1;
+        const TV* q = xc + ((long long)(k >> 1) * N1 + (j >> 1)) * N0;
+        TV* xl = xf + (long long)line * n0;
+        for (int i = threadIdx.x; i < n0; i += blockDim.x) xl[i] = gxp_row<TA, TV>(tab, q, N0, cs2, i, j & 1, k & 1, xl[i]);
     }
 }
 // persistent CTAs over the coarse lines (J, K); threads over I

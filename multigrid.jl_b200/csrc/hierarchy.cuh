@@ -134,15 +134,11 @@ struct Context {
     int use_graphs = 1;            // 0: never replay cycles from CUDA graphs
     int use_tma = 1;               // 0: never use the TMA-staged dictionary kernel (MGB200_TMA)
     int grid_transfers = 1;        // > 0: grid-hinted transfer kernels (grid_xfer.cuh) where a hint was given and verified
-    int lines = 0;                 // > 0: line-blocked dictionary kernel with that many rows per thread (2 or 4); off by default
-    int lines_min_rows = 50000;
-    int lines_staged = 1;          // 1: TMA-staged form of the line-blocked kernel where the lines fit a CTA, 0: global-memory form
     int tma_min_rows = 200000;     // smaller matrices keep the one-pass kernel (too few tiles per SM)
     int use_box = 1;               // box-stencil kernel (box.cuh) for box-structured square operators (MGB200_BOX)
     int box_variant = 1;           // (rows per thread, base rows per tile, stages): see launch_box (MGB200_BOX_VARIANT)
     int box_variant27 = -1;        // >= 0: another variant for the 27-point levels (MGB200_BOX_VARIANT27)
     int box_min_rows = 100000;
-    int gxp_lines = 1;             // fine lines per thread of the grid-hinted prolongation (1, 2, 4)
     int fuse_first_sweeps = 1;     // first two sweeps from x = 0 in one pass of the box kernel (MGB200_FUSE_FIRST)
     int split_test = 0;            // > 0: every dictionary pass runs as interior + both ends (test hook)
     int use_overlap = 0;           // multi-GPU: halo exchange beside the interior rows (MGB200_OVERLAP=1; measured
@@ -179,11 +175,7 @@ struct Context {
         box_variant27 = env_int("MGB200_BOX_VARIANT27", -1);
         box_min_rows = env_int("MGB200_BOX_MIN_ROWS", 100000);
         fuse_first_sweeps = env_int("MGB200_FUSE_FIRST", 1);
-        gxp_lines = env_int("MGB200_GXP_LINES", 1);
-        lines = env_int("MGB200_LINES", 0);
         grid_transfers = env_int("MGB200_GRID_TRANSFERS", 1);
-        lines_min_rows = env_int("MGB200_LINES_MIN_ROWS", 50000);
-        lines_staged = env_int("MGB200_LINES_STAGED", 1);
         use_overlap = env_int("MGB200_OVERLAP", 0);
         split_test = env_int("MGB200_SPLIT_TEST", 0);
         int prio_lo = 0, prio_hi = 0;

@@ -148,75 +148,6 @@ static bool launch_pattern_tma(Context& ctx, const Csr<TA>& M, int mode, const T
     return true;
 }
 
-// line-blocked variant (pat_lines_kernel / pat_lines_tma_kernel): box-structured square operators, SPMV / RESID /
-// SWEEP, whole matrix, with the fused put of row-partitioned levels; off unless the option "lines" (MGB200_LINES) holds the rows per thread (2 or 4)
-template <typename TA, typename TV>
-static bool launch_pattern_lines(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d,
-                                 const TV* dpat, TV* y, const PutPlan& pp) {
-    return false;
-}
-template <typename TV>
-static bool launch_pattern_lines(Context& ctx, const Csr<TV>& M, int mode, const TV* x, const TV* b, const TV* d,
-                                 const TV* dpat, TV* y, const PutPlan& pp) {
-    const PatDict<TV>& D = M.pat;
-    const int R = ctx.lines;
-    if ((R != 2 && R != 4) || !D.box_ok || !D.rowrel || mode == MODE_ADD || x == y) return false;
-    if (M.n_rows < ctx.lines_min_rows) return false;
-    const long long S = D.S, nlines = (M.n_rows + S - 1) / S, groups = (nlines + R - 1) / R, total = groups * S;
-    // (b) staged form: tiles of Q groups, ceil32(Q*S) <= 544 threads, two stages in shared memory
-    if (ctx.lines_staged && S <= 544 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (!b || (reinterpret_cast<uintptr_t>(b) & 15) == 0) &&
-        (!d || (reinterpret_cast<uintptr_t>(d) & 15) == 0)) {
-        constexpr int AL = sizeof(TV) >= 8 ? 2 : 4;
-        const bool need_b = (mode == MODE_RESID || mode == MODE_SWEEP), need_d = (mode == MODE_SWEEP && !dpat);
-        int Q = (int)std::max<long long>(1, 512 / S);
-        size_t smem = 0;
-        int nt = 0;
-        for (; Q >= 1; --Q) {
-            int xcap, vcap, pcap;
-            lines_stage_layout(S, R, Q, AL, xcap, vcap, pcap);
-            const size_t stage = (((size_t)(3 * xcap + (need_b ? vcap : 0) + (need_d ? vcap : 0)) * sizeof(TV) + (size_t)pcap * 2) + 127) / 128 * 128;
-            smem = 128 + 2 * stage;
-            nt = (int)(((long long)Q * S + 31) / 32 * 32);
-            if (smem <= (size_t)ctx.max_smem_optin / 2 - 1024 || Q == 1) break;     // two CTAs per SM when possible
-        }
-        if (nt <= 544 && smem <= (size_t)ctx.max_smem_optin - 1024) {
-            const long long ntiles = (groups + Q - 1) / Q;
-            int per = (int)std::min<size_t>((size_t)(2048 / nt), ((size_t)ctx.max_smem_optin + 1024) / (smem + 1024));
-            per = std::max(per, 1);
-            const int grid = (int)std::min<long long>(ntiles, (long long)ctx.sm_count * per);
-#define MGB_LT(MODE, DP, RR)                                                                                          \
-    {                                                                                                                 \
-        auto kern = pat_lines_tma_kernel<TV, TV, MODE, DP, RR, 544>;                                                  \
-        MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx.max_smem_optin));        \
-        kern<<<grid, nt, smem, ctx.stream>>>(pp, S, (long long)D.S2, (long long)M.n_rows, Q, ntiles, D.xlo, D.xhi, D.pid, D.pat_off, \
-                                             D.ent, D.box_mask, dpat, x, b, d, y);                                     \
-    }
-#define MGB_LTR(MODE, DP) { if (R == 2) MGB_LT(MODE, DP, 2) else MGB_LT(MODE, DP, 4) }
-            if (mode == MODE_SPMV) MGB_LTR(MODE_SPMV, false)
-            else if (mode == MODE_RESID) MGB_LTR(MODE_RESID, false)
-            else if (dpat) MGB_LTR(MODE_SWEEP, true)
-            else MGB_LTR(MODE_SWEEP, false)
-#undef MGB_LTR
-#undef MGB_LT
-            MGB_LAUNCH_CHECK();
-            return true;
-        }
-    }
-    // (a) global-memory form
-    const int grid = (int)std::min<long long>((total + 255) / 256, (long long)ctx.sm_count * (R == 2 ? 6 : 3));
-#define MGB_LL(MODE, DP, RR) \
-    pat_lines_kernel<TV, TV, MODE, DP, RR><<<grid, 256, 0, ctx.stream>>>(pp, S, (long long)D.S2, (long long)M.n_rows, total, D.pid, D.pat_off, D.ent, D.box_mask, dpat, x, b, d, y)
-#define MGB_LR(MODE, DP) { if (R == 2) MGB_LL(MODE, DP, 2); else MGB_LL(MODE, DP, 4); }
-    if (mode == MODE_SPMV) MGB_LR(MODE_SPMV, false)
-    else if (mode == MODE_RESID) MGB_LR(MODE_RESID, false)
-    else if (dpat) MGB_LR(MODE_SWEEP, true)
-    else MGB_LR(MODE_SWEEP, false)
-#undef MGB_LR
-#undef MGB_LL
-    MGB_LAUNCH_CHECK();
-    return true;
-}
-
 // grid-hinted transfer kernels (grid_xfer.cuh): P in mode ADD, R in mode SPMV, one right-hand side; option
 // "grid_transfers" (MGB200_GRID_TRANSFERS, default 1) and a hint that was verified at upload
 template <typename TA, typename TV>
@@ -229,13 +160,10 @@ static bool launch_grid_xfer(Context& ctx, const Csr<TA>& M, int mode, const TV*
     if (!((X.kind == 1 && mode == MODE_ADD) || (X.kind == 2 && mode == MODE_SPMV))) return false;
     if (dry) return true;      // the caller only asks whether this kernel will run (byte accounting)
     const int width = X.kind == 1 ? X.n[0] : X.N[0];
-    const int lpt = ctx.gxp_lines == 2 || ctx.gxp_lines == 4 ? ctx.gxp_lines : 1;
-    const long long nlines = X.kind == 1 ? (long long)((X.n[1] + lpt - 1) / lpt) * X.n[2] : (long long)X.N[1] * X.N[2];
+    const long long nlines = X.kind == 1 ? (long long)X.n[1] * X.n[2] : (long long)X.N[1] * X.N[2];
     const int nt = std::min(1024, (width + 31) / 32 * 32);
     const int grid = (int)std::min<long long>(nlines, (long long)ctx.sm_count * std::max(1, 2048 / nt) * 4);
-    if (X.kind == 1 && lpt == 1) gxp_kernel<TA, TV, 1><<<grid, nt, 0, ctx.stream>>>(X, static_cast<const TA*>(X.tab), x, y);
-    else if (X.kind == 1 && lpt == 2) gxp_kernel<TA, TV, 2><<<grid, nt, 0, ctx.stream>>>(X, static_cast<const TA*>(X.tab), x, y);
-    else if (X.kind == 1) gxp_kernel<TA, TV, 4><<<grid, nt, 0, ctx.stream>>>(X, static_cast<const TA*>(X.tab), x, y);
+    if (X.kind == 1) gxp_kernel<TA, TV><<<grid, nt, 0, ctx.stream>>>(X, static_cast<const TA*>(X.tab), x, y);
     else gxr_kernel<TA, TV><<<grid, nt, 0, ctx.stream>>>(X, static_cast<const TA*>(X.tab), x, y);
     MGB_LAUNCH_CHECK();
     return true;
@@ -384,7 +312,6 @@ template <typename TA, typename TV>
 static void launch_pattern_mode(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d,
                                 const TV* dpat, TV* y, const PutPlan& pp = no_put()) {
     if (launch_box<TA, TV>(ctx, M, mode, x, b, d, dpat, y, pp)) return;
-    if (ctx.lines > 0 && launch_pattern_lines(ctx, M, mode, x, b, d, dpat, y, pp)) return;
     if (M.pat.rowrel && launch_pattern_tma<TA, TV>(ctx, M, mode, x, b, d, dpat, y, 0, -1, 0, pp)) return;
     launch_pattern_rows<TA, TV>(ctx, M, mode, x, b, d, dpat, y, 0, M.n_rows, 0, 0, pp);
 }

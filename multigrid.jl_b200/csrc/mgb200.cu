@@ -225,69 +225,13 @@ static void host_box_run(const BoxPlan& P, const BoxCoef<double>& C0, const std:
     }
 }
 
+// the one-row-per-thread dictionary walk of pat_kernel on the CPU: the reference every other kernel form must match bit for bit
 template <int MODE, bool DPAT>
-static long long host_lines_run(const HostPatterns<double>& hp, const BoxInfo& B, long long n_rows, int R, int Q,
-                                const std::vector<PatEntry<double>>& ent, const double* dpat, const double* x,
-                                const double* b, const double* d, double* y) {
-    const long long S = B.S, S2 = B.S2;
-    long long slow = 0;
+static void host_pattern_walk(const HostPatterns<double>& hp, long long S2, long long n_rows, const std::vector<PatEntry<double>>& ent,
+                              const double* dpat, const double* x, const double* b, const double* d, double* y) {
     const LinesView<double> Vg = lines_global_view<double>(S2, hp.pid.data(), x, b, d);
-    if (R == 0) {
-        for (long long row = 0; row < n_rows; ++row)
-            y[row] = pat_row_walk<double, double, MODE, DPAT>(S2, Vg, row, hp.pat_off.data(), ent.data(), dpat);
-        return 0;
-    }
-    auto thread = [&](const LinesView<double>& V, long long rel0, long long row0) {
-        if (R == 2) pat_lines_thread<double, double, MODE, DPAT, 2>(S, S2, n_rows, V, rel0, row0, hp.pat_off.data(), ent.data(), B.mask.data(), dpat, y);
-        else pat_lines_thread<double, double, MODE, DPAT, 4>(S, S2, n_rows, V, rel0, row0, hp.pat_off.data(), ent.data(), B.mask.data(), dpat, y);
-    };
-    const long long nlines = (n_rows + S - 1) / S, groups = (nlines + R - 1) / R;
-    if (Q == 0) {            // (a) global-memory form
-        for (long long q = 0; q < groups; ++q)
-            for (long long i = 0; i < S; ++i) {
-                const long long row0 = q * R * S + i;
-                if (row0 >= n_rows) continue;
-                bool same = row0 + (long long)(R - 1) * S < n_rows;
-                for (int j = 1; j < R && same; ++j) same = hp.pid[row0 + j * S] == hp.pid[row0];
-                slow += same ? 0 : 1;
-                thread(Vg, row0, row0);
-            }
-        return slow;
-    }
-    // (b) staged form: the stage is a host buffer filled exactly as the kernel's bulk copies fill shared memory (poison
-    // elsewhere); x, b, d carry the slack of device vectors in the caller's buffers
-    constexpr int AL = 2;
-    int xcap, vcap, pcap;
-    lines_stage_layout(S, R, Q, AL, xcap, vcap, pcap);
-    const long long ntiles = (groups + Q - 1) / Q, xlo = 0, xhi = (n_rows + AL - 1) / AL * AL;
-    std::vector<double> sx(3 * (size_t)xcap), sb(vcap), sd(vcap);
-    std::vector<uint16_t> sp(pcap);
-    for (long long tile = 0; tile < ntiles; ++tile) {
-        const LinesTile T = lines_plan_tile(S, S2, n_rows, R, Q, tile, xlo, xhi, AL);
-        std::fill(sx.begin(), sx.end(), 1e300);
-        std::fill(sb.begin(), sb.end(), 1e300);
-        std::fill(sd.begin(), sd.end(), 1e300);
-        std::fill(sp.begin(), sp.end(), (uint16_t)0xFFFF);
-        for (int k = 0; k < 3; ++k) {
-            MGB_CHECK(T.xe[k] - T.xa[k] <= xcap, "x range exceeds the stage");
-            for (long long g = T.xa[k]; g < T.xe[k]; ++g) sx[(size_t)k * xcap + (g - T.xa[k])] = g < n_rows ? x[g] : 0.0;
-        }
-        MGB_CHECK(T.ve - T.va <= vcap && T.pe - T.pa <= pcap, "row tile exceeds the stage");
-        for (long long g = T.va; g < T.ve; ++g) {
-            if (b) sb[g - T.va] = g < n_rows ? b[g] : 0.0;
-            if (d) sd[g - T.va] = g < n_rows ? d[g] : 0.0;
-        }
-        for (long long g = T.pa; g < T.pe; ++g) sp[g - T.pa] = g < n_rows ? hp.pid[g] : (uint16_t)0;
-        const LinesView<double> V = lines_stage_view<double>(S2, T, sx.data(), xcap, sb.data(), sd.data(), sp.data());
-        const long long nthreads = ((Q * S + 31) / 32) * 32;
-        for (long long t = 0; t < nthreads; ++t) {
-            const long long grp = t / S, col = t - grp * S;
-            if (grp >= Q) continue;
-            const long long rel0 = grp * R * S + col;
-            thread(V, rel0, T.T0 + rel0);
-        }
-    }
-    return slow;
+    for (long long row = 0; row < n_rows; ++row)
+        y[row] = pat_row_walk<double, double, MODE, DPAT>(S2, Vg, row, hp.pat_off.data(), ent.data(), dpat);
 }
 
 // CPU replay of the grid-hinted transfer kernels (grid_xfer.cuh): their per-row functions, row by row
@@ -690,12 +634,8 @@ int mgb200_set_option(mgb200_handle h, const char* key, int64_t value) {
         else if (k == "box_variant") H->ctx.box_variant = (int)value;
         else if (k == "box_variant27") H->ctx.box_variant27 = (int)value;
         else if (k == "fuse_first") H->ctx.fuse_first_sweeps = (int)value;
-        else if (k == "gxp_lines") H->ctx.gxp_lines = (int)value;
         else if (k == "box_min_rows") H->ctx.box_min_rows = (int)value;
-        else if (k == "lines") H->ctx.lines = (int)value;
-        else if (k == "lines_staged") H->ctx.lines_staged = (int)value;
         else if (k == "grid_transfers") H->ctx.grid_transfers = (int)value;
-        else if (k == "lines_min_rows") H->ctx.lines_min_rows = (int)value;
         else if (k == "split_test") H->ctx.split_test = (int)value;
         else if (k == "overlap") H->ctx.use_overlap = (int)value;
         else if (k == "fused_put") H->use_fused_put = (int)value;
@@ -820,39 +760,36 @@ int mgb200_host_box_apply(int64_t n_rows, const int64_t* colptr, const int64_t* 
     MGB_CATCH
 }
 
-int mgb200_host_lines_apply(int64_t n_rows, const int64_t* colptr, const int64_t* rowval, const double* nzval,
-                            int index_base, int mode, int rows_per_thread, int groups_per_tile, int fold_d, const double* x,
-                            const double* b, const double* d, double* y, int64_t* info) {
+int mgb200_host_pattern_apply(int64_t n_rows, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+                              int index_base, int mode, int fold_d, const double* x, const double* b, const double* d,
+                              double* y, int64_t* info) {
     MGB_TRY
     MGB_CHECK(colptr && rowval && nzval && x && y && info, "null argument");
     MGB_CHECK(mode == 0 || mode == 2 || mode == 3, "mode must be 0, 2 or 3");
-    MGB_CHECK(rows_per_thread == 0 || rows_per_thread == 2 || rows_per_thread == 4, "rows_per_thread must be 0, 2 or 4");
     MGB_CHECK(mode == 0 || b, "b required");
     MGB_CHECK(mode != 3 || d, "d required");
-    MGB_CHECK(groups_per_tile >= 0 && groups_per_tile <= 64, "groups_per_tile out of range");
     info[0] = info[1] = info[2] = info[3] = 0;
     HostPatterns<double> hp;
     if (!build_patterns<double>(n_rows, colptr, rowval, nzval, index_base, false, PAT_MAX_PATTERNS, PAT_MAX_ENTRIES, hp)) return 0;
-    const BoxInfo B = detect_box<double>(hp, n_rows);
-    if (!B.ok || B.S < 3) return 0;
+    if (!hp.rowrel) return 0;
+    const BoxInfo B = detect_box<double>(hp, n_rows);      // S2 only steers which of the three x pointers a walk uses
     std::vector<PatEntry<double>> ent(hp.delta.size());
     for (size_t k = 0; k < ent.size(); ++k) {
         ent[k].v = hp.val[k];
         ent[k].delta = hp.delta[k];
     }
     std::vector<double> dpat(hp.npat(), 0.0);
-    if (mode == 3 && fold_d)
-        for (int p = 0; p < hp.npat(); ++p) dpat[p] = d[hp.rep_row[p]];
-    long long slow = 0;
     const bool dp = (mode == 3 && fold_d);
-    if (mode == 0) slow = host_lines_run<0, false>(hp, B, n_rows, rows_per_thread, groups_per_tile, ent, nullptr, x, b, d, y);
-    else if (mode == 2) slow = host_lines_run<2, false>(hp, B, n_rows, rows_per_thread, groups_per_tile, ent, nullptr, x, b, d, y);
-    else if (dp) slow = host_lines_run<3, true>(hp, B, n_rows, rows_per_thread, groups_per_tile, ent, dpat.data(), x, b, d, y);
-    else slow = host_lines_run<3, false>(hp, B, n_rows, rows_per_thread, groups_per_tile, ent, nullptr, x, b, d, y);
+    if (dp)
+        for (int p = 0; p < hp.npat(); ++p) dpat[p] = d[hp.rep_row[p]];
+    const long long S2 = B.ok ? B.S2 : 0;
+    if (mode == 0) host_pattern_walk<0, false>(hp, S2, n_rows, ent, nullptr, x, b, d, y);
+    else if (mode == 2) host_pattern_walk<2, false>(hp, S2, n_rows, ent, nullptr, x, b, d, y);
+    else if (dp) host_pattern_walk<3, true>(hp, S2, n_rows, ent, dpat.data(), x, b, d, y);
+    else host_pattern_walk<3, false>(hp, S2, n_rows, ent, nullptr, x, b, d, y);
     info[0] = 1;
-    info[1] = B.S;
-    info[2] = B.S2;
-    info[3] = slow;
+    info[1] = B.ok ? B.S : 0;
+    info[2] = S2;
     MGB_CATCH
 }
 

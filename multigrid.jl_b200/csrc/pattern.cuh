@@ -454,7 +454,7 @@ static void upload_patterns(PatDict<TA>& D, const HostPatterns<TA>& H, long long
     D.present = true;
     {
         const BoxInfo B = detect_box<TA>(H, n_rows);
-        if (B.ok && B.S >= 3) {   // the line-blocked kernel (pat_lines_kernel) needs lines
+        if (B.ok && B.S >= 3) {   // kept for the box-stencil kernel (box.cuh) and mgb200_host_detect_box
             MGB_CUDA(cudaMalloc(&D.box_mask, D.npat * sizeof(int)));
             MGB_CUDA(cudaMemcpy(D.box_mask, B.mask.data(), D.npat * sizeof(int), cudaMemcpyHostToDevice));
             D.box_ok = true;
@@ -554,16 +554,7 @@ pat_kernel(const __grid_constant__ PutPlan pp, int rA, int nA, int rB, int nB, c
     if (pp.on) ll_put_edge<TV>(pp, row, out);
 }
 
-// ---- line-blocked variant (off by default: option "lines" / MGB200_LINES = R) --------------------------------------
-// For dictionaries with box structure (detect_box): a thread owns R rows that are S apart - the same column of R
-// consecutive lines of a lexicographic grid; lanes are consecutive columns, so every load of a warp is contiguous.  Per
-// plane dz of the stencil it loads x[dx][l], l = -1..R, once for the 9 R products of that plane and every dictionary
-// value once for R rows; the offsets are not read at all (a pattern is a presence mask).  Stored order is (dz,dy,dx)
-// order, so every row still accumulates its products in stored order: bit-identical to pat_kernel.  A value is loaded
-// only if some row of the group multiplies it, i.e. only addresses that entries name: nothing is assumed about the
-// grid beyond the offsets.  Groups whose R rows do not share one pattern walk the dictionary row by row.
-// The per-thread function is __host__ __device__: mgb200_host_lines_apply runs exactly this code on the CPU
-// (tests/test_patterns.py).  First measurements are due in the next round (tools/microbench_lines.cu).
+// ---- host / device helpers shared with box.cuh and with the CPU replays (mgb200_host_pattern_apply) -----------------------
 template <typename T>
 __host__ __device__ __forceinline__ T ld_ro(const T* p) {
 #ifdef __CUDA_ARCH__
@@ -586,17 +577,7 @@ __host__ __device__ __forceinline__ TV pat_epilogue(TV acc, TV xval, TV bval, TV
     const TV r = bval - acc;
     return xval + dval * r;
 }
-// result store of the line-blocked kernels: on the device also the fused put of a row-partitioned level (ll.cuh)
-template <typename TV>
-__host__ __device__ __forceinline__ void lines_store(TV* y, long long row, TV out, const PutPlan* pp) {
-    y[row] = out;
-#ifdef __CUDA_ARCH__
-    if (pp && pp->on) ll_put_edge<TV>(*pp, row, out);
-#endif
-}
-// Where a thread of the line-blocked kernel finds its data.  rel = row - T0 for a reference row T0 (0 for the
-// global-memory form, the first row of the tile for the staged form): xs[dz+1][rel] == x[T0 + dz*S2 + rel] for every rel
-// the thread touches; b, d, pid likewise.
+// View of the vectors for the one-row dictionary walk below: xs[dz+1][row] == x[dz*S2 + row]; b, d, pid by row.
 template <typename TV>
 struct LinesView {
     const TV* xs[3];
@@ -625,82 +606,6 @@ __host__ __device__ inline TV pat_row_walk(long long S2, const LinesView<TV>& V,
     }
     return pat_epilogue<MODE, TV>(acc, xval, bval, dval);
 }
-// one thread: R rows S apart, the first one at rel0 (view) / row0 (global)
-template <typename TA, typename TV, int MODE, bool DPAT, int R>
-__host__ __device__ inline void pat_lines_thread(long long S, long long S2, long long n_rows, const LinesView<TV>& V,
-                                                 long long rel0, long long row0, const int* pat_off,
-                                                 const PatEntry<TA>* ent, const int* mask, const TV* dpat, TV* y,
-                                                 const PutPlan* pp = nullptr) {
-    if (row0 >= n_rows) return;
-    int nr = R;
-    while (row0 + (long long)(nr - 1) * S >= n_rows) --nr;        // rows of the group that exist (nr >= 1)
-    const int p0 = ld_pid(V.pid + rel0);
-    bool same = (nr == R);
-#pragma unroll
-    for (int j = 1; j < R; ++j)
-        if (j < nr) same = same && (ld_pid(V.pid + rel0 + j * S) == p0);
-    if (!same) {
-        for (int j = 0; j < nr; ++j)
-            lines_store<TV>(y, row0 + j * S, pat_row_walk<TA, TV, MODE, DPAT>(S2, V, rel0 + j * S, pat_off, ent, dpat), pp);
-        return;
-    }
-    const int m = ld_ro(mask + p0);
-    const PatEntry<TA>* e = ent + ld_ro(pat_off + p0);
-    TV acc[R], xc[R];
-    bool have_c = false;
-#pragma unroll
-    for (int j = 0; j < R; ++j) {
-        acc[j] = VT<TV>::zero();
-        xc[j] = VT<TV>::zero();
-    }
-#pragma unroll
-    for (int dz = -1; dz <= 1; ++dz) {
-        const int mz = (m >> ((dz + 1) * 9)) & 0x1FF;
-        if (mz == 0) continue;
-        const TV* xp = V.xs[dz + 1] + rel0;
-        TV X[3][R + 2];
-#pragma unroll
-        for (int l = 0; l < R + 2; ++l) {
-            const TV* ql = xp + (l - 1) * S;
-#pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-                // row j multiplies line l = j + 1 + dy: dy = -1 reaches l <= R-1, dy = 0 the lines 1..R, dy = +1 l >= 2
-                const bool need = ((l <= R - 1) && (mz & (1 << (0 + dx + 1)))) || ((l >= 1 && l <= R) && (mz & (1 << (3 + dx + 1)))) ||
-                                  ((l >= 2) && (mz & (1 << (6 + dx + 1))));
-                X[dx + 1][l] = need ? ld_ro(ql + dx) : VT<TV>::zero();
-            }
-        }
-        if (MODE == 3 && dz == 0 && (mz & (1 << 4))) {
-            have_c = true;
-#pragma unroll
-            for (int j = 0; j < R; ++j) xc[j] = X[1][j + 1];
-        }
-#pragma unroll
-        for (int dy = -1; dy <= 1; ++dy) {
-#pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-                if (mz & (1 << ((dy + 1) * 3 + (dx + 1)))) {
-                    const TA v = e->v;
-                    ++e;
-#pragma unroll
-                    for (int j = 0; j < R; ++j) acc[j] = acc[j] + v * X[dx + 1][j + 1 + dy];
-                }
-            }
-        }
-    }
-    const TV dp = (MODE == 3 && DPAT) ? ld_ro(dpat + p0) : VT<TV>::zero();
-#pragma unroll
-    for (int j = 0; j < R; ++j) {
-        const long long rel = rel0 + j * S;
-        TV bval = VT<TV>::zero(), dval = dp, xval = xc[j];
-        if (MODE == 2 || MODE == 3) bval = V.b[rel];
-        if (MODE == 3) {
-            if (!DPAT) dval = V.d[rel];
-            if (!have_c) xval = V.xs[1][rel];
-        }
-        lines_store<TV>(y, row0 + j * S, pat_epilogue<MODE, TV>(acc[j], xval, bval, dval), pp);
-    }
-}
 template <typename TV>
 __host__ __device__ __forceinline__ LinesView<TV> lines_global_view(long long S2, const uint16_t* pid, const TV* x, const TV* b,
                                                                     const TV* d) {
@@ -713,137 +618,6 @@ __host__ __device__ __forceinline__ LinesView<TV> lines_global_view(long long S2
     V.pid = pid;
     return V;
 }
-// (a) global-memory form: persistent grid-stride over the flattened (group, column) index
-template <typename TA, typename TV, int MODE, bool DPAT, int R>
-__global__ void __launch_bounds__(256)
-pat_lines_kernel(const __grid_constant__ PutPlan pp, long long S, long long S2, long long n_rows, long long total, const uint16_t* __restrict__ pid,
-                 const int* __restrict__ pat_off, const PatEntry<TA>* __restrict__ ent, const int* __restrict__ mask,
-                 const TV* __restrict__ dpat, const TV* __restrict__ x, const TV* __restrict__ b, const TV* __restrict__ d,
-                 TV* __restrict__ y) {
-    const LinesView<TV> V = lines_global_view<TV>(S2, pid, x, b, d);
-    for (long long f = blockIdx.x * (long long)blockDim.x + threadIdx.x; f < total; f += (long long)gridDim.x * blockDim.x) {
-        const long long q = f / S;
-        const long long row0 = q * R * S + (f - q * S);
-        pat_lines_thread<TA, TV, MODE, DPAT, R>(S, S2, n_rows, V, row0, row0, pat_off, ent, mask, dpat, y, &pp);
-    }
-}
-
-// (b) staged form: a tile is Q groups of R lines = Q*R*S consecutive rows; its x arrives as (up to) three contiguous
-// ranges, one per plane of the stencil, each ONE bulk copy (the merged windows of the TMA kernel below with a tile of
-// Q*R*S rows), plus the b, d and pid tiles; two stages, persistent CTAs of ceil32(Q*S) threads.
-struct LinesTile {
-    long long T0, T1;          // rows of the tile
-    long long xa[3], xe[3];    // copy range of x per stencil plane, [xa, xe); xe <= xa: nothing to copy
-    long long va, ve;          // copy range of the row tiles b, d (aligned like x)
-    long long pa, pe;          // copy range of pid (multiples of 8)
-};
-// AL = elements per 16 bytes (tma_align); [xlo, xhi) = elements of the input vector that may be copied (PatDict)
-__host__ __device__ inline LinesTile lines_plan_tile(long long S, long long S2, long long n_rows, int R, int Q, long long tile,
-                                                     long long xlo, long long xhi, int AL) {
-    LinesTile T;
-    T.T0 = tile * Q * R * S;
-    T.T1 = T.T0 + (long long)Q * R * S;
-    if (T.T1 > n_rows) T.T1 = n_rows;
-    const long long nal = (n_rows + AL - 1) / AL * AL, n8 = (n_rows + 7) & ~7LL;
-#pragma unroll
-    for (int dz = -1; dz <= 1; ++dz) {
-        if (dz != 0 && S2 == 0) { T.xa[dz + 1] = T.xe[dz + 1] = 0; continue; }
-        long long a = T.T0 + dz * S2 - S - 1, e = T.T1 + dz * S2 + S + 1;
-        a = a < xlo ? xlo : a;
-        e = e > xhi ? xhi : e;
-        if (e <= a) { T.xa[dz + 1] = T.xe[dz + 1] = 0; continue; }
-        // round outwards; xlo and xhi are multiples of AL, so the rounded range stays inside [xlo, xhi)
-        T.xa[dz + 1] = (a >= 0 ? a / AL : -((-a + AL - 1) / AL)) * AL;
-        T.xe[dz + 1] = (e >= 0 ? (e + AL - 1) / AL : -((-e) / AL)) * AL;
-    }
-    T.va = T.T0 / AL * AL;
-    T.ve = (T.T1 + AL - 1) / AL * AL;
-    if (T.ve > nal) T.ve = nal;
-    T.pa = T.T0 & ~7LL;
-    T.pe = (T.T1 + 7) & ~7LL;
-    if (T.pe > n8) T.pe = n8;
-    return T;
-}
-// elements a stage holds: three x ranges of xcap each, the row tiles of vcap each, pcap pattern ids
-__host__ __device__ inline void lines_stage_layout(long long S, int R, int Q, int AL, int& xcap, int& vcap, int& pcap) {
-    xcap = (int)(((long long)(Q * R + 2) * S + 2 + 2 * AL + AL - 1) / AL * AL);
-    vcap = (int)(((long long)Q * R * S + 2 * AL + AL - 1) / AL * AL);
-    pcap = (int)((((long long)Q * R * S + 16) + 7) & ~7LL);
-}
-template <typename TV>
-__host__ __device__ inline LinesView<TV> lines_stage_view(long long S2, const LinesTile& T, const TV* sx, int xcap, const TV* sb,
-                                                          const TV* sd, const uint16_t* sp) {
-    LinesView<TV> V;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) V.xs[k] = sx + (long long)k * xcap + ((T.T0 + (long long)(k - 1) * S2) - T.xa[k]);
-    V.b = sb + (T.T0 - T.va);
-    V.d = sd + (T.T0 - T.va);
-    V.pid = sp + (T.T0 - T.pa);
-    return V;
-}
-template <typename TA, typename TV, int MODE, bool DPAT, int R, int NTMAX>
-__global__ void __launch_bounds__(NTMAX)
-pat_lines_tma_kernel(const __grid_constant__ PutPlan pp, long long S, long long S2, long long n_rows, int Q, long long ntiles, long long xlo, long long xhi,
-                     const uint16_t* __restrict__ pid, const int* __restrict__ pat_off, const PatEntry<TA>* __restrict__ ent,
-                     const int* __restrict__ mask, const TV* __restrict__ dpat, const TV* __restrict__ x,
-                     const TV* __restrict__ b, const TV* __restrict__ d, TV* __restrict__ y) {
-    constexpr int AL = sizeof(TV) >= 8 ? 2 : 4;
-    constexpr bool NEED_B = (MODE == 2 || MODE == 3);
-    constexpr bool NEED_D = (MODE == 3 && !DPAT);
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
-    int xcap, vcap, pcap;
-    lines_stage_layout(S, R, Q, AL, xcap, vcap, pcap);
-    const size_t stage_bytes = (((size_t)(3 * xcap + (NEED_B ? vcap : 0) + (NEED_D ? vcap : 0)) * sizeof(TV) + (size_t)pcap * 2) + 127) / 128 * 128;
-    unsigned char* stage0 = smem_raw + 128;
-    const int t = threadIdx.x;
-    if (t == 0) {
-        mbar_init(full, 1);
-        mbar_init(full + 1, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    auto issue = [&](long long tile, int s) {
-        const LinesTile T = lines_plan_tile(S, S2, n_rows, R, Q, tile, xlo, xhi, AL);
-        TV* sx = reinterpret_cast<TV*>(stage0 + (size_t)s * stage_bytes);
-        TV* sb = sx + 3 * (size_t)xcap;
-        TV* sd = sb + (NEED_B ? vcap : 0);
-        uint16_t* sp = reinterpret_cast<uint16_t*>(sd + (NEED_D ? vcap : 0));
-        uint32_t bytes = (uint32_t)(T.pe - T.pa) * 2u;
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-            if (T.xe[k] > T.xa[k]) bytes += (uint32_t)(T.xe[k] - T.xa[k]) * (uint32_t)sizeof(TV);
-        if (NEED_B) bytes += (uint32_t)(T.ve - T.va) * (uint32_t)sizeof(TV);
-        if (NEED_D) bytes += (uint32_t)(T.ve - T.va) * (uint32_t)sizeof(TV);
-        mbar_expect_tx(full + s, bytes);
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-            if (T.xe[k] > T.xa[k]) bulk_g2s(sx + (size_t)k * xcap, x + T.xa[k], (uint32_t)(T.xe[k] - T.xa[k]) * (uint32_t)sizeof(TV), full + s);
-        if (NEED_B) bulk_g2s(sb, b + T.va, (uint32_t)(T.ve - T.va) * (uint32_t)sizeof(TV), full + s);
-        if (NEED_D) bulk_g2s(sd, d + T.va, (uint32_t)(T.ve - T.va) * (uint32_t)sizeof(TV), full + s);
-        bulk_g2s(sp, pid + T.pa, (uint32_t)(T.pe - T.pa) * 2u, full + s);
-    };
-    if (t == 0 && blockIdx.x < ntiles) issue(blockIdx.x, 0);
-    const long long grp = t / S, col = t - grp * S;
-    int it = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const int s = it & 1;
-        if (t == 0 && tile + gridDim.x < ntiles) issue(tile + gridDim.x, s ^ 1);
-        mbar_wait(full + s, (it >> 1) & 1);
-        const LinesTile T = lines_plan_tile(S, S2, n_rows, R, Q, tile, xlo, xhi, AL);
-        const TV* sx = reinterpret_cast<const TV*>(stage0 + (size_t)s * stage_bytes);
-        const TV* sb = sx + 3 * (size_t)xcap;
-        const TV* sd = sb + (NEED_B ? vcap : 0);
-        const uint16_t* sp = reinterpret_cast<const uint16_t*>(sd + (NEED_D ? vcap : 0));
-        if (grp < Q) {
-            const LinesView<TV> V = lines_stage_view<TV>(S2, T, sx, xcap, sb, sd, sp);
-            const long long rel0 = grp * R * S + col;
-            pat_lines_thread<TA, TV, MODE, DPAT, R>(S, S2, n_rows, V, rel0, T.T0 + rel0, pat_off, ent, mask, dpat, y, &pp);
-        }
-        __syncthreads();
-    }
-}
-
 // ---- TMA-staged variant ----------------------------------------------------------------------------------
 // Persistent CTAs of NT threads walk tiles of NT consecutive rows with a two-stage pipeline: while the CTA computes
 // tile i, the bulk copies of tile i+1 (the x windows, the b / d tiles and the pattern ids, issued by one thread,

@@ -1073,9 +1073,15 @@ struct Hierarchy : HierarchyBase {
         }
         typedef typename Wide<TV>::type TW;
         Launch La(ctx, K_COARSE, levels, (double)n * n * sizeof(TW));
-        const int grid = cdiv((long long)n * cdiv(m, AP_MC) * 32, 256);
-        lower_apply_kernel<TW, TV><<<grid, 256, 0, ctx.stream>>>(n, m, coarse.linv, coarse.perm, b, coarse.y);
-        upper_apply_kernel<TW, TV><<<grid, 256, 0, ctx.stream>>>(n, m, coarse.uinv, coarse.y, x);
+        if (m == 1) {
+            const int grid = cdiv((long long)n * 32, 256);
+            lower_apply_kernel<TW, TV, 1><<<grid, 256, 0, ctx.stream>>>(n, m, coarse.linv, coarse.perm, b, coarse.y);
+            upper_apply_kernel<TW, TV, 1><<<grid, 256, 0, ctx.stream>>>(n, m, coarse.uinv, coarse.y, x);
+        } else {
+            const int grid = cdiv((long long)n * cdiv(m, AP_MC) * 32, 256);
+            lower_apply_kernel<TW, TV, AP_MC><<<grid, 256, 0, ctx.stream>>>(n, m, coarse.linv, coarse.perm, b, coarse.y);
+            upper_apply_kernel<TW, TV, AP_MC><<<grid, 256, 0, ctx.stream>>>(n, m, coarse.uinv, coarse.y, x);
+        }
         MGB_LAUNCH_CHECK();
     }
 

@@ -465,12 +465,10 @@ def host_detect_box(M, max_patterns=4096, max_entries=1 << 16):
     return dict(S=int(info[1]), S2=int(info[2]), masks=mask[:int(info[3])].copy())
 
 
-def host_lines_apply(M, mode, rows_per_thread, x, b=None, d=None, fold_d=False, groups_per_tile=0):
-    """Host-only: the per-thread function of the line-blocked dictionary kernel (csrc/pattern.cuh::pat_lines_thread)
-    run on the CPU for every thread of a launch, for the operator M^T given by the CSC arrays of ``M``.
-    mode 0: A x, 2: b - A x, 3: x + d.*(b - A x); rows_per_thread 0 is the one-row-per-thread dictionary walk;
-    groups_per_tile Q > 0 replays the staged (TMA) form with host buffers as the stage.
-    Returns (y, info) or None when the matrix has no box structure."""
+def host_pattern_apply(M, mode, x, b=None, d=None, fold_d=False):
+    """Host-only: the one-row-per-thread dictionary walk (csrc/pattern.cuh::pat_row_walk) on the CPU for the operator
+    M^T given by the CSC arrays of ``M``.  mode 0: A x, 2: b - A x, 3: x + d.*(b - A x).
+    Returns (y, info) or None when the matrix has no row-relative dictionary."""
     M = sp.csc_matrix(M)
     if not M.has_sorted_indices:
         M.sort_indices()
@@ -481,12 +479,12 @@ def host_lines_apply(M, mode, rows_per_thread, x, b=None, d=None, fold_d=False, 
     dd = None if d is None else np.ascontiguousarray(d, dtype=np.float64)
     y = np.full(n, np.nan)
     info = np.zeros(4, dtype=np.int64)
-    _check(lib().mgb200_host_lines_apply(ctypes.c_int64(n), _ptr(cp), _ptr(rv), _ptr(nz), 0, int(mode), int(rows_per_thread),
-                                         int(groups_per_tile), int(bool(fold_d)), _ptr(x), None if bb is None else _ptr(bb),
-                                         None if dd is None else _ptr(dd), _ptr(y), _ptr(info)))
+    _check(lib().mgb200_host_pattern_apply(ctypes.c_int64(n), _ptr(cp), _ptr(rv), _ptr(nz), 0, int(mode), int(bool(fold_d)),
+                                           _ptr(x), None if bb is None else _ptr(bb), None if dd is None else _ptr(dd),
+                                           _ptr(y), _ptr(info)))
     if not info[0]:
         return None
-    return y, dict(S=int(info[1]), S2=int(info[2]), slow_groups=int(info[3]))
+    return y, dict(S=int(info[1]), S2=int(info[2]))
 
 
 def host_box_apply(M, mode, rows_per_thread, base_rows, x, b=None, d=None, fold_d=False, ctas=3):

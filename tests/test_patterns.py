@@ -179,7 +179,7 @@ def test_box_kernel_code_on_the_cpu(n, RZ, NB):
         x, b = rng.standard_normal(N), rng.standard_normal(N)
         d = np.ascontiguousarray(p.relaxPrecs[l]) if l < len(p.relaxPrecs) else 0.8 / mat.diagonal()
         for mode, fold in ((0, False), (2, False), (3, False), (3, True)):
-            ref = device.host_lines_apply(mat, mode, 0, x, b, d, fold)
+            ref = device.host_pattern_apply(mat, mode, x, b, d, fold)
             got = device.host_box_apply(mat, mode, RZ, NB, x, b, d, fold)
             if ref is None:          # tiny coarse levels are not worth a dictionary
                 assert got is None and N < 8 * 27
@@ -189,9 +189,9 @@ def test_box_kernel_code_on_the_cpu(n, RZ, NB):
             assert np.array_equal(ref[0].view(np.int64), got[0].view(np.int64)), (l, mode, fold)
         if ref is not None:
             # MODE 4: the first two sweeps from x = 0 in one pass == diag_scale followed by one sweep, bit for bit
-            dfold = device.host_lines_apply(mat, 3, 0, np.zeros(N), b, d, True)     # x1 = 0 + d .* (b - A 0): folded d
+            dfold = device.host_pattern_apply(mat, 3, np.zeros(N), b, d, True)     # x1 = 0 + d .* (b - A 0): folded d
             x1 = 0.0 + (dfold[0] / np.where(b != 0, b, 1.0)) * b                      # = dpat[pid] .* b
-            two = device.host_lines_apply(mat, 3, 0, x1, b, d, True)
+            two = device.host_pattern_apply(mat, 3, x1, b, d, True)
             got4 = device.host_box_apply(mat, 4, RZ, NB, b, b, d, True)
             assert got4 is not None and np.array_equal(two[0].view(np.int64), got4[0].view(np.int64)), l
         if min(n) >= 8 and l == 0 and got is not None:
@@ -204,39 +204,6 @@ def test_box_kernel_rejects_what_it_cannot_do():
     x = np.ones(A.shape[0])
     assert device.host_box_apply(sp.csc_matrix(p.As[0]), 0, 1, 64, x) is None
     assert device.host_box_apply(sp.csc_matrix(p.Ps[0]), 0, 1, 64, np.ones(p.Ps[0].shape[1])) is None
-
-
-@pytest.mark.parametrize("n", [[24, 20, 12], [32, 32], [18, 40, 10], [22, 10, 14]])
-@pytest.mark.parametrize("R", [2, 4])
-def test_line_blocked_kernel_code_on_the_cpu(n, R):
-    """csrc/pattern.cuh::pat_lines_thread is __host__ __device__: run on the CPU for every thread of a launch it must
-    reproduce the one-row-per-thread dictionary walk bit for bit in all three modes (fine 7- / 5-point level and
-    27- / 9-point Galerkin level; line counts R does and does not divide), and that walk must agree with scipy."""
-    from multigrid_jl_b200 import device
-    A, AT, M, p, b0 = _cpu_problem(n, 2)
-    rng = np.random.default_rng(11)
-    for l in range(2):
-        mat = sp.csc_matrix(p.As[l])
-        N = mat.shape[0]
-        x, b = rng.standard_normal(N), rng.standard_normal(N)
-        d = np.ascontiguousarray(p.relaxPrecs[l]) if l < len(p.relaxPrecs) else 0.8 / mat.diagonal()
-        Aop = sp.csr_matrix(mat.T)
-        for mode, fold in ((0, False), (2, False), (3, False), (3, True)):
-            ref = device.host_lines_apply(mat, mode, 0, x, b, d, fold)
-            got = device.host_lines_apply(mat, mode, R, x, b, d, fold)
-            assert ref is not None and got is not None
-            assert np.array_equal(ref[0].view(np.int64), got[0].view(np.int64)), (l, mode, fold)
-            # staged (TMA) form: tiles of Q groups, the stage replayed with host buffers filled like the bulk copies
-            for Q in (1, 3):
-                st = device.host_lines_apply(mat, mode, R, x, b, d, fold, groups_per_tile=Q)
-                assert st is not None and np.array_equal(ref[0].view(np.int64), st[0].view(np.int64)), (l, mode, fold, Q)
-            # the blocked path is really taken on the fine level (a 6-line coarse plane may have no R = 4 group with
-            # one pattern: everything then goes row by row, still bit-identical)
-            lines = -(-N // got[1]["S"])
-            if l == 0:
-                assert got[1]["slow_groups"] < 0.7 * (-(-lines // R)) * got[1]["S"]
-            want = {0: Aop @ x, 2: b - Aop @ x, 3: x + d * (b - Aop @ x)}[mode]
-            np.testing.assert_allclose(ref[0], want, rtol=1e-12, atol=1e-12)
 
 
 @pytest.mark.parametrize("n", [[24, 20, 12], [32, 32], [18, 40, 10], [14, 10, 8]])
@@ -400,24 +367,6 @@ def test_box_kernel_bit_identical(kind, n, cycle, variant):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("MGB200_TEST_LINES", "0") != "1",
-                    reason="pat_lines_kernel (off by default) was written after the GPU budget of round 1 was spent: its "
-                           "per-thread code is bit-identical on the CPU (test_line_blocked_kernel_code_on_the_cpu); set "
-                           "MGB200_TEST_LINES=1 for its first GPU run (a faulting kernel would poison the CUDA context "
-                           "of the tests that follow, so it does not run unasked)")
-@pytest.mark.parametrize("kind,n,cycle", [("poisson", [40, 36, 28], 'V'), ("helmholtz", [33, 31, 17], 'W'),
-                                          ("poisson", [300, 200], 'F')])
-@pytest.mark.parametrize("R", ["2", "4"])
-def test_line_blocked_kernel_bit_identical(kind, n, cycle, R):
-    """Option "lines" (MGB200_LINES): the line-blocked dictionary kernel on every box-structured level instead of the
-    one-pass / TMA-staged kernels: results must not change by a bit (Float64 and ComplexF64, 2-D and 3-D)."""
-    base = {"MGB200_PATTERNS": "1", "MGB200_GRAPHS": "1", "MGB200_TMA": "1", "MGB200_TMA_MIN_ROWS": "0"}
-    x0, r0, it0, _ = _solve(kind, n, 3, cycle, dict(base, MGB200_LINES="0"))
-    x1, r1, it1, _ = _solve(kind, n, 3, cycle, dict(base, MGB200_LINES=R, MGB200_LINES_MIN_ROWS="0"))
-    assert it0 == it1 and np.array_equal(r0, r1) and np.array_equal(x0, x1)
-
-
-@pytest.mark.gpu
 @pytest.mark.parametrize("kind,n,cycle", [("poisson", [40, 36, 28], 'V'), ("helmholtz", [32, 24, 16], 'W'),
                                           ("poisson", [300, 200], 'F'), ("poisson", [64, 64, 64], 'V')])
 @pytest.mark.parametrize("R", ["1"])
@@ -431,10 +380,10 @@ def test_grid_hinted_transfers_bit_identical(kind, n, cycle, R):
 
 
 @pytest.mark.parametrize("seed", range(12))
-def test_line_blocked_kernel_code_fuzz(seed):
+def test_box_kernel_code_fuzz(seed):
     """Random box stencils - arbitrary subsets of the 27 offsets (upwind-like one-sided ones, stencils without a centre
-    entry, different ones near the boundaries), random grid sizes with tiny dimensions: the line-blocked kernel code
-    (global and staged form) must equal the dictionary walk bit for bit whenever the box structure is detected."""
+    entry, different ones near the boundaries), random grid sizes with tiny dimensions: the box-stencil kernel code
+    (csrc/box.cuh, replayed on the CPU) must equal the dictionary walk bit for bit whenever the matrix qualifies."""
     from multigrid_jl_b200 import device
     rng = np.random.default_rng(1000 + seed)
     dim = 3 if seed % 3 else 2
@@ -461,14 +410,16 @@ def test_line_blocked_kernel_code_fuzz(seed):
     A.sort_indices()
     mat = sp.csc_matrix(A.T)          # the hierarchy stores the transpose (CSC arrays = CSR arrays of the operator)
     x, b, d = rng.standard_normal(N), rng.standard_normal(N), rng.standard_normal(N)
-    ref = device.host_lines_apply(mat, 3, 0, x, b, d, False)
+    ref = device.host_pattern_apply(mat, 3, x, b, d, False)
     if ref is None:
         # no dictionary (too few rows per pattern) or an offset set that fits no (S, S2): nothing to compare
         return
     np.testing.assert_allclose(ref[0], x + d * (b - A @ x), rtol=1e-12, atol=1e-12)
-    for R in (2, 4):
-        for Q in (0, 1, 2):
-            for mode in (0, 2, 3):
-                r0 = device.host_lines_apply(mat, mode, 0, x, b, d, False)
-                got = device.host_lines_apply(mat, mode, R, x, b, d, False, groups_per_tile=Q)
-                assert got is not None and np.array_equal(r0[0].view(np.int64), got[0].view(np.int64)), (n, keep, R, Q, mode)
+    for RZ, NB in ((1, 64), (2, 40), (4, 128)):
+        for mode in (0, 2, 3):
+            r0 = device.host_pattern_apply(mat, mode, x, b, d, False)
+            got = device.host_box_apply(mat, mode, RZ, NB, x, b, d, False)
+            if got is None:          # 2-D grids, or a box the kernel is not built for
+                assert dim == 2 or device.host_detect_box(mat) is None or device.host_detect_box(mat)["S2"] < 3 * device.host_detect_box(mat)["S"]
+                continue
+            assert np.array_equal(r0[0].view(np.int64), got[0].view(np.int64)), (n, keep, RZ, NB, mode)
