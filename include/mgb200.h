@@ -185,6 +185,43 @@ int mgb200_dist_upload_level(mgb200_handle h, int level, int64_t n_global, const
                              const int64_t* r_colptr, const int64_t* r_rowval, const void* r_nzval,
                              const void* d, int index_base);
 
+/* ---- multi-GPU, single process: ONE handle drives G devices (SURVEY.md 8(b) "Threading": a single ccall from one Julia
+ * task is enough; no mpirun / torchrun / Distributed workers on the product path) ------------------------------------------
+ * The entry points take GLOBAL arrays exactly as the reference holds them and slice the contiguous row ranges of the
+ * z-slab partition themselves; every device runs its part on its own host thread inside the call, ghost planes travel
+ * over NVLink peer memory (plain peer access between devices of one process).
+ *   mgb200_multi_create         getMGparam + the device part of MGsetup on devices[0 .. n_devices-1] (NULL: 0, 1, ...)
+ *   mgb200_multi_upload_level   As[l], Ps[l], Rs[l], relaxPrecs[l] (global CSC arrays as for mgb200_upload_level).
+ *                               row_offsets / coarse_row_offsets (n_devices + 1 entries, first 0, last n / nc): the rows of
+ *                               level l / l+1 each device owns - for the reference's box partition with NumCells = [1,1,G]
+ *                               (getOriginalBoundingBoxCells, DDIndices.jl:41-47) device g owns node planes g*c .. (g+1)*c-1,
+ *                               the last one also the final plane.  row_offsets == NULL: the level is replicated on every
+ *                               device (the coarse levels below the agglomeration threshold); all levels after the first
+ *                               replicated one must be replicated too.
+ *   mgb200_multi_upload_coarsest  As[end] on every device
+ *   mgb200_multi_solveMG / solveCG / solveFGMRES / precondition  as the single-device calls, with the GLOBAL b and x
+ *   mgb200_multi_info           as mgb200_dist_info (of device 0) */
+typedef struct mgb200_multi* mgb200_multi_handle;
+int mgb200_multi_create(mgb200_multi_handle* mh, int n_devices, const int* devices, int val_type, int levels, int nrhs,
+                        char cycle_type, int relax_kind, const int64_t* relax_pre, const int64_t* relax_post);
+int mgb200_multi_destroy(mgb200_multi_handle mh);
+int mgb200_multi_upload_level(mgb200_multi_handle mh, int level, int64_t n, int64_t nc, const int64_t* row_offsets,
+                              const int64_t* coarse_row_offsets, const int64_t* a_colptr, const int64_t* a_rowval,
+                              const void* a_nzval, const int64_t* p_colptr, const int64_t* p_rowval, const void* p_nzval,
+                              const int64_t* r_colptr, const int64_t* r_rowval, const void* r_nzval, const void* d,
+                              int index_base);
+int mgb200_multi_set_level_grid(mgb200_multi_handle mh, int level, int dim, const int64_t* n_fine_nodes,
+                                const int64_t* n_coarse_nodes);      /* as mgb200_set_level_grid, GLOBAL grids */
+int mgb200_multi_upload_coarsest(mgb200_multi_handle mh, int64_t n, const int64_t* colptr, const int64_t* rowval,
+                                 const void* nzval, int index_base);
+int mgb200_multi_solveMG(mgb200_multi_handle mh, const void* b, void* x, double tol, int max_iter, int* iter, double* resvec);
+int mgb200_multi_solveCG(mgb200_multi_handle mh, const void* b, void* x, double tol, int max_iter, int* iter, int* flag,
+                         double* resvec);
+int mgb200_multi_solveFGMRES(mgb200_multi_handle mh, const void* b, void* x, int inner, int flexible, double tol, int max_iter,
+                             int* iter, int* flag, double* resvec, int* nres);
+int mgb200_multi_precondition(mgb200_multi_handle mh, const void* r, void* z);
+int mgb200_multi_info(mgb200_multi_handle mh, int64_t* out);
+
 /* out[0] = world, out[1] = rank, out[2] = 1 if halo exchange and coarse gather run over NVLink peer memory
  * (CUDA IPC, csrc/p2p.cuh; 0: NCCL send/recv, e.g. when MGB200_P2P=0 or the peers are not IPC reachable),
  * out[3] = number of row-partitioned levels.  Collective on first use (it finalises the distributed setup). */

@@ -18,7 +18,7 @@ from .mgsetup import (MGsetup, getRelaxPrec, getSPAIprec, adjustMemoryForNumRHS,
                       replaceMatrixInHierarchy, transposeHierarchy, defineCoarsestAinv)
 from .sa_amg import (SA_AMGsetup, getAggregation, getStrengthMatrix, neighborhoodAggregationNew,
                      aggrArray2P)
-from .device import DeviceHierarchy, uploadHierarchy, MGB200Error, LIB_PATH
+from .device import DeviceHierarchy, MultiDeviceHierarchy, uploadHierarchy, MGB200Error, LIB_PATH
 from .solve import (solveMG, solveCG_MG, solveGMRES_MG, solveBiCGSTAB_MG, getMultigridPreconditioner, recursiveCycle,
                     SpMatMul)
 from .dist_setup import (slab_planes, setup_slab_hierarchy, poisson_window_operator, DistHierarchy, DistLevel)

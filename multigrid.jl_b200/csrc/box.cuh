@@ -68,7 +68,22 @@ struct BoxPlan {
     int xtotal;             // elements of all windows of a stage
     int pbase[BOX_MAX_RZ + 2];                      // first pattern id of the id window w (MODE 4 only)
     int ptotal;             // pattern ids of all id windows
+    int first_ghost_tile;   // records from this one on read ghost rows of the input vector (they are sorted last)
 };
+// A consumer that runs beside the halo exchange of its input vector (row-partitioned levels): tiles that read ghost rows
+// wait inside the kernel until the exchange kernel has published exchange number *consumed + 1 (p2p.cuh).
+struct BoxWait {
+    const unsigned long long* epoch;    // null: no waiting
+    unsigned long long* consumed;
+    unsigned* ticket;
+};
+static inline BoxWait no_wait() {
+    BoxWait w;
+    w.epoch = nullptr;
+    w.consumed = nullptr;
+    w.ticket = nullptr;
+    return w;
+}
 // MODE 4 of the box kernel: the first TWO sweeps of a relaxation that starts from x = 0 (MGcycle.jl:128-135 with the
 // reference's `x .= 0` start), x1 = 0 + d.*b, x2 = x1 + d.*(b - A x1), in one pass: the staged windows hold b and the
 // pattern ids of the neighbours, and x1 of a neighbour is recomputed where it is needed.  Needs d folded into the
@@ -300,7 +315,8 @@ __host__ __device__ __forceinline__ void box_thread(const BoxCoef<TV>& C0, const
 template <typename TV, int SHAPE, int MODE, bool DPAT, int RZ, int NB, int STAGES>
 __global__ void __launch_bounds__(NB)
 box_kernel(const __grid_constant__ BoxPlan P, const __grid_constant__ BoxCoef<TV> C0, const __grid_constant__ PutPlan pp,
-           const unsigned char* __restrict__ recs, const uint16_t* __restrict__ pid, const TV* __restrict__ ctab_g,
+           const __grid_constant__ BoxWait bw, const unsigned char* __restrict__ recs, const uint16_t* __restrict__ pid,
+           const TV* __restrict__ ctab_g,
            const TV* __restrict__ dtab_g, const TV* __restrict__ x, const TV* __restrict__ b, const TV* __restrict__ d,
            TV* __restrict__ y) {
     constexpr bool NEED_B = (MODE == 2 || MODE == 3);
@@ -336,7 +352,19 @@ box_kernel(const __grid_constant__ BoxPlan P, const __grid_constant__ BoxCoef<TV
     const int ntiles = P.ntiles;
     // Warp 0 issues the copies of a tile: lane i loads entry i of the tile's record and fires it, lane NCP copies the
     // record's descriptor into the stage; lane 0 arms the mbarrier with the byte total first.
+    // exchange number this kernel's ghost tiles wait for (read before anything else can advance `consumed`)
+    const unsigned long long want = (bw.epoch && t == 0) ? *bw.consumed + 1 : 0;
+    bool ghosts_ready = bw.epoch == nullptr;
     auto issue = [&](int tile, int s) {            // all lanes of warp 0
+        if (!ghosts_ready && tile >= P.first_ghost_tile) {
+            if (t == 0) {
+                while (*reinterpret_cast<const volatile unsigned long long*>(bw.epoch) < want) {}
+                __threadfence();
+            }
+            __syncwarp();
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+            ghosts_ready = true;
+        }
         unsigned char* st = stage0 + (size_t)s * stage_bytes;
         const unsigned char* rec = recs + (size_t)tile * REC;
         BoxCopy C;
@@ -418,6 +446,10 @@ box_kernel(const __grid_constant__ BoxPlan P, const __grid_constant__ BoxCoef<TV
         }
         __syncthreads();
         if (STAGES == 1 && issuer && tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x, 0);
+    }
+    if (bw.epoch) {          // the last CTA to finish marks the exchange as consumed
+        __syncthreads();
+        if (t == 0 && atomicInc(bw.ticket, gridDim.x - 1) == gridDim.x - 1) *bw.consumed = want;
     }
 }
 
@@ -531,13 +563,30 @@ struct BoxDict {
     bool has_records(const BoxPlan& P, int RZ, int NB) const {
         return recs && rec_RZ == RZ && rec_NB == NB && rec_xlo == P.xlo && rec_xhi == P.xhi;
     }
+    int first_ghost_tile = 0;
     const unsigned char* records(const BoxPlan& P, int RZ, int NB) {
         if (has_records(P, RZ, NB)) return recs;
         if (recs) cudaFree(recs);
         recs = nullptr;
         const size_t rb = box_rec_bytes(RZ);
-        std::vector<unsigned char> h((size_t)P.ntiles * rb);
-        for (int tile = 0; tile < P.ntiles; ++tile) box_plan_tile<TV>(P, RZ, NB, tile, h.data() + (size_t)tile * rb);
+        std::vector<unsigned char> h((size_t)P.ntiles * rb), one(rb);
+        // tiles that read ghost rows of the input vector (rows outside [0, n_rows)) go last: on a row-partitioned level
+        // they may have to wait for the halo exchange that runs beside the kernel
+        constexpr int AL = box_al<TV>();
+        const int nal = box_ceil(P.n_rows, AL);
+        std::vector<int> ghost_tiles;
+        int n_int = 0;
+        for (int tile = 0; tile < P.ntiles; ++tile) {
+            box_plan_tile<TV>(P, RZ, NB, tile, one.data());
+            const BoxCopy* cp = reinterpret_cast<const BoxCopy*>(one.data() + BOX_DESC_BYTES);
+            bool ghost = false;
+            for (int i = 0; i < RZ + 2; ++i)
+                if (cp[i].bytes && (cp[i].src < 0 || cp[i].src + (int)(cp[i].bytes / sizeof(TV)) > nal)) ghost = true;
+            if (ghost) ghost_tiles.push_back(tile);
+            else std::memcpy(h.data() + (size_t)(n_int++) * rb, one.data(), rb);
+        }
+        first_ghost_tile = n_int;
+        for (int tile : ghost_tiles) box_plan_tile<TV>(P, RZ, NB, tile, h.data() + (size_t)(n_int++) * rb);
         MGB_CUDA(cudaMalloc(&recs, std::max<size_t>(h.size(), 16)));
         MGB_CUDA(cudaMemcpy(recs, h.data(), h.size(), cudaMemcpyHostToDevice));
         rec_RZ = RZ;

@@ -14,6 +14,7 @@
 // carry no NCCL dependency.
 #pragma once
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nccl.h>
 
 #include <algorithm>

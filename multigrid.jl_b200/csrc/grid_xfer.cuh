@@ -19,6 +19,7 @@
 // profiles/r02a_microbench_lines_transfer.log - and was replaced by the kernels below.)
 #pragma once
 #include "pattern.cuh"
+#include "ll.cuh"
 
 namespace mgb200 {
 
@@ -28,6 +29,10 @@ struct GridXfer {
     int n[3], N[3];    // fine / coarse nodes per dimension (unused dimensions: 1); n = 2N - 1 where N > 1
     int cls_k0[27];    // first dictionary entry of the pattern of each class (-1: class does not occur)
     void* tab;         // device: dense value table (gx_dense_table), released with the matrix
+    // z-slab of a row-partitioned level: the matrix holds the rows of the planes [k0, k0 + nk) of the ROW grid (fine
+    // planes for P, coarse planes for R); its column indices are global indices of the column grid minus `shift`
+    int k0, nk;
+    long long shift;
 };
 constexpr int GXP_TAB = 8 * 8;      // prolongation: class a + 2b + 4c, up to 8 values in stored order (zeros beyond)
 constexpr int GXR_TAB = 27 * 27;    // restriction: class cx + 3cy + 9cz, coefficient of offset (dz+1)*9 + (dy+1)*3 + (dx+1)
@@ -43,7 +48,8 @@ __host__ __device__ __forceinline__ int gx_class(int I, int N) { return I == 0 ?
 
 // ---- upload-time verification (host) ---------------------------------------------------------------------------------
 template <typename TA>
-static bool gx_verify_prolongation(const HostPatterns<TA>& H, long long n_rows, const int n[3], const int N[3], GridXfer& X) {
+static bool gx_verify_prolongation(const HostPatterns<TA>& H, long long n_rows, const int n[3], const int N[3], GridXfer& X,
+                                   int k0 = 0, int nk = -1, long long shift = 0) {
     X = no_grid();
     if (!H.ok || H.rowrel) return false;
     for (int d = 0; d < 3; ++d) {
@@ -51,17 +57,21 @@ static bool gx_verify_prolongation(const HostPatterns<TA>& H, long long n_rows, 
         X.n[d] = n[d];
         X.N[d] = N[d];
     }
-    if ((long long)n[0] * n[1] * n[2] != n_rows) return false;
+    if (nk < 0) nk = n[2];
+    if (k0 < 0 || k0 + nk > n[2] || (long long)n[0] * n[1] * nk != n_rows) return false;
+    X.k0 = k0;
+    X.nk = nk;
+    X.shift = shift;
     int cls_pat[8];
     for (int c = 0; c < 8; ++c) cls_pat[c] = -1;
     for (int c = 0; c < 27; ++c) X.cls_k0[c] = -1;
     const long long N1 = N[0], N12 = (long long)N[0] * N[1];
     long long row = 0;
-    for (int k = 0; k < n[2]; ++k)
+    for (int k = k0; k < k0 + nk; ++k)
         for (int j = 0; j < n[1]; ++j)
             for (int i = 0; i < n[0]; ++i, ++row) {
                 const int a = i & 1, b = j & 1, c = k & 1, cls = a + 2 * b + 4 * c, p = H.pid[row];
-                if (H.c0[row] != (i >> 1) + N1 * (j >> 1) + N12 * (k >> 1)) return false;
+                if (H.c0[row] != (i >> 1) + N1 * (j >> 1) + N12 * (k >> 1) - shift) return false;
                 if (cls_pat[cls] == p) continue;
                 if (cls_pat[cls] != -1) return false;
                 int q = H.pat_off[p];
@@ -78,7 +88,8 @@ static bool gx_verify_prolongation(const HostPatterns<TA>& H, long long n_rows, 
     return true;
 }
 template <typename TA>
-static bool gx_verify_restriction(const HostPatterns<TA>& H, long long n_rows, const int n[3], const int N[3], GridXfer& X) {
+static bool gx_verify_restriction(const HostPatterns<TA>& H, long long n_rows, const int n[3], const int N[3], GridXfer& X,
+                                  int k0 = 0, int nk = -1, long long shift = 0) {
     X = no_grid();
     if (!H.ok || H.rowrel) return false;
     for (int d = 0; d < 3; ++d) {
@@ -86,7 +97,11 @@ static bool gx_verify_restriction(const HostPatterns<TA>& H, long long n_rows, c
         X.n[d] = n[d];
         X.N[d] = N[d];
     }
-    if ((long long)N[0] * N[1] * N[2] != n_rows) return false;
+    if (nk < 0) nk = N[2];
+    if (k0 < 0 || k0 + nk > N[2] || (long long)N[0] * N[1] * nk != n_rows) return false;
+    X.k0 = k0;
+    X.nk = nk;
+    X.shift = shift;
     int cls_pat[27];
     for (int c = 0; c < 27; ++c) {
         cls_pat[c] = -1;
@@ -94,7 +109,7 @@ static bool gx_verify_restriction(const HostPatterns<TA>& H, long long n_rows, c
     }
     const long long S = n[0], S2 = (long long)n[0] * n[1];
     long long row = 0;
-    for (int K = 0; K < N[2]; ++K)
+    for (int K = k0; K < k0 + nk; ++K)
         for (int J = 0; J < N[1]; ++J)
             for (int I = 0; I < N[0]; ++I, ++row) {
                 const int cx = gx_class(I, N[0]), cy = gx_class(J, N[1]), cz = gx_class(K, N[2]), cls = cx + 3 * cy + 9 * cz;
@@ -104,7 +119,7 @@ static bool gx_verify_restriction(const HostPatterns<TA>& H, long long n_rows, c
                 // first entry = smallest allowed offset in every dimension
                 const int fx = (ax & 1) ? -1 : 0, fy = (ay & 1) ? -1 : 0, fz = (az & 1) ? -1 : 0;
                 const long long first = fx + S * fy + S2 * fz;
-                if (H.c0[row] != anchor + first) return false;
+                if (H.c0[row] != anchor + first - shift) return false;
                 if (cls_pat[cls] == p) continue;
                 if (cls_pat[cls] != -1) return false;
                 int q = H.pat_off[p];
@@ -208,19 +223,23 @@ __host__ __device__ __forceinline__ TV gxr_row(const TA* tv, const TV* f, long l
 // persistent CTAs over the fine lines (j, k); threads over i.  (Two or four lines per thread with the x_f reads issued
 // up front measured slower on the B200: 107 / 107 against 99 us at 257^3, profiles/r02_tune_log.txt.)
 template <typename TA, typename TV>
-__global__ void __launch_bounds__(1024) gxp_kernel(const __grid_constant__ GridXfer X, const TA* __restrict__ tabg,
-                                                   const TV* __restrict__ xc, TV* __restrict__ xf) {
+__global__ void __launch_bounds__(1024) gxp_kernel(const __grid_constant__ GridXfer X, const __grid_constant__ PutPlan pp,
+                                                   const TA* __restrict__ tabg, const TV* __restrict__ xc, TV* __restrict__ xf) {
     __shared__ TA tab[GXP_TAB];
     for (int i = threadIdx.x; i < GXP_TAB; i += blockDim.x) tab[i] = tabg[i];
     __syncthreads();
     const int n0 = X.n[0], n1 = X.n[1], N0 = X.N[0], N1 = X.N[1];
     const long long cs2 = (long long)N0 * N1;
-    const int nlines = n1 * X.n[2];
+    const int nlines = n1 * X.nk;                         // the rows of this matrix: fine planes k0 .. k0 + nk - 1
     for (int line = blockIdx.x; line < nlines; line += gridDim.x) {
-        const int k = line / n1, j = line - k * n1;
-        const TV* q = xc + ((long long)(k >> 1) * N1 + (j >> 1)) * N0;
+        const int kl = line / n1, j = line - kl * n1, k = X.k0 + kl;
+        const TV* q = xc + (((long long)(k >> 1) * N1 + (j >> 1)) * N0 - X.shift);
         TV* xl = xf + (long long)line * n0;
-        for (int i = threadIdx.x; i < n0; i += blockDim.x) xl[i] = gxp_row<TA, TV>(tab, q, N0, cs2, i, j & 1, k & 1, xl[i]);
+        for (int i = threadIdx.x; i < n0; i += blockDim.x) {
+            const TV v = gxp_row<TA, TV>(tab, q, N0, cs2, i, j & 1, k & 1, xl[i]);
+            xl[i] = v;
+            if (pp.on) ll_put_edge<TV>(pp, (long long)line * n0 + i, v);
+        }
     }
 }
 // persistent CTAs over the coarse lines (J, K); threads over I
@@ -230,10 +249,10 @@ __global__ void __launch_bounds__(1024) gxr_kernel(const __grid_constant__ GridX
     __shared__ TA tab[3 * 27];
     const int N0 = X.N[0], N1 = X.N[1], N2 = X.N[2];
     const long long S = X.n[0], S2 = (long long)X.n[0] * X.n[1];
-    const int nlines = N1 * N2;
+    const int nlines = N1 * X.nk;                         // the rows of this matrix: coarse planes k0 .. k0 + nk - 1
     int cur = -1;
     for (int line = blockIdx.x; line < nlines; line += gridDim.x) {
-        const int K = line / N1, J = line - K * N1;
+        const int Kl = line / N1, J = line - Kl * N1, K = X.k0 + Kl;
         const int cy = gx_class(J, N1), cz = gx_class(K, N2);
         if (3 * cy + 9 * cz != cur) {          // CTA-uniform: the three x classes of this line's (y, z) class
             __syncthreads();
@@ -242,7 +261,7 @@ __global__ void __launch_bounds__(1024) gxr_kernel(const __grid_constant__ GridX
             __syncthreads();
         }
         const int ay = gx_allowed(cy, N1), az = gx_allowed(cz, N2);
-        const TV* f0 = rf + S2 * (2LL * K) + S * (2LL * J);
+        const TV* f0 = rf + (S2 * (2LL * K) + S * (2LL * J) - X.shift);
         TV* out = rc + (long long)line * N0;
         const bool inner_line = ay == 7 && az == 7;          // CTA-uniform
         for (int I0 = 0; I0 < N0; I0 += blockDim.x) {

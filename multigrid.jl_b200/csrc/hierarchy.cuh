@@ -138,7 +138,10 @@ struct Context {
     int use_box = 1;               // box-stencil kernel (box.cuh) for box-structured square operators (MGB200_BOX)
     int box_variant = 1;           // (rows per thread, base rows per tile, stages): see launch_box (MGB200_BOX_VARIANT)
     int box_variant27 = -1;        // >= 0: another variant for the 27-point levels (MGB200_BOX_VARIANT27)
+    int box_variant_c = -1;        // >= 0: another variant for ComplexF64 hierarchies (MGB200_BOX_VARIANT_C)
     int box_min_rows = 100000;
+    int overlap_box = 1;           // row-partitioned levels: the box kernel runs beside the halo exchange of its input
+                                   // vector and waits for the ghost rows inside the kernel (MGB200_OVERLAP_BOX)
     int fuse_first_sweeps = 1;     // first two sweeps from x = 0 in one pass of the box kernel (MGB200_FUSE_FIRST)
     int split_test = 0;            // > 0: every dictionary pass runs as interior + both ends (test hook)
     int use_overlap = 0;           // multi-GPU: halo exchange beside the interior rows (MGB200_OVERLAP=1; measured
@@ -173,8 +176,10 @@ struct Context {
         use_box = env_int("MGB200_BOX", 1);
         box_variant = env_int("MGB200_BOX_VARIANT", 1);
         box_variant27 = env_int("MGB200_BOX_VARIANT27", -1);
+        box_variant_c = env_int("MGB200_BOX_VARIANT_C", -1);
         box_min_rows = env_int("MGB200_BOX_MIN_ROWS", 100000);
         fuse_first_sweeps = env_int("MGB200_FUSE_FIRST", 1);
+        overlap_box = env_int("MGB200_OVERLAP_BOX", 1);
         grid_transfers = env_int("MGB200_GRID_TRANSFERS", 1);
         use_overlap = env_int("MGB200_OVERLAP", 0);
         split_test = env_int("MGB200_SPLIT_TEST", 0);

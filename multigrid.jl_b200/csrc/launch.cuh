@@ -151,7 +151,8 @@ static bool launch_pattern_tma(Context& ctx, const Csr<TA>& M, int mode, const T
 // grid-hinted transfer kernels (grid_xfer.cuh): P in mode ADD, R in mode SPMV, one right-hand side; option
 // "grid_transfers" (MGB200_GRID_TRANSFERS, default 1) and a hint that was verified at upload
 template <typename TA, typename TV>
-static bool launch_grid_xfer(Context& ctx, const Csr<TA>& M, int mode, const TV* x, TV* y, bool dry = false) {
+static bool launch_grid_xfer(Context& ctx, const Csr<TA>& M, int mode, const TV* x, TV* y, bool dry = false,
+                             const PutPlan& pp = no_put()) {
     if constexpr (VT<TA>::is_complex) {
         return false;     // P and R are real (SA-AMG.jl:9-10, MGsetup.jl:80-81): no complex instantiation
     } else {
@@ -160,10 +161,11 @@ static bool launch_grid_xfer(Context& ctx, const Csr<TA>& M, int mode, const TV*
     if (!((X.kind == 1 && mode == MODE_ADD) || (X.kind == 2 && mode == MODE_SPMV))) return false;
     if (dry) return true;      // the caller only asks whether this kernel will run (byte accounting)
     const int width = X.kind == 1 ? X.n[0] : X.N[0];
-    const long long nlines = X.kind == 1 ? (long long)X.n[1] * X.n[2] : (long long)X.N[1] * X.N[2];
+    if (pp.on && X.kind != 1) return false;
+    const long long nlines = X.kind == 1 ? (long long)X.n[1] * X.nk : (long long)X.N[1] * X.nk;
     const int nt = std::min(1024, (width + 31) / 32 * 32);
     const int grid = (int)std::min<long long>(nlines, (long long)ctx.sm_count * std::max(1, 2048 / nt) * 4);
-    if (X.kind == 1) gxp_kernel<TA, TV><<<grid, nt, 0, ctx.stream>>>(X, static_cast<const TA*>(X.tab), x, y);
+    if (X.kind == 1) gxp_kernel<TA, TV><<<grid, nt, 0, ctx.stream>>>(X, pp, static_cast<const TA*>(X.tab), x, y);
     else gxr_kernel<TA, TV><<<grid, nt, 0, ctx.stream>>>(X, static_cast<const TA*>(X.tab), x, y);
     MGB_LAUNCH_CHECK();
     return true;
@@ -174,7 +176,7 @@ static bool launch_grid_xfer(Context& ctx, const Csr<TA>& M, int mode, const TV*
 // side, double and complex double.  Variants (rows per thread RZ, base rows per tile NB, stages): ctx.box_variant.
 template <typename TV, int RZ, int NB, int STAGES>
 static bool launch_box_variant(Context& ctx, const Csr<TV>& M, int mode, const TV* x, const TV* b, const TV* d,
-                               const TV* dpat, TV* y, const PutPlan& pp, bool prepare_only) {
+                               const TV* dpat, TV* y, const PutPlan& pp, bool prepare_only, const BoxWait& bw) {
     BoxDict<TV>& X = const_cast<BoxDict<TV>&>(M.box);      // the record cache is filled on first use
     const PatDict<TV>& D = M.pat;
     BoxPlan P;
@@ -192,6 +194,7 @@ static bool launch_box_variant(Context& ctx, const Csr<TV>& M, int mode, const T
         if (cs != cudaStreamCaptureStatusNone) return false;
     }
     const unsigned char* recs = X.records(P, RZ, NB);
+    P.first_ghost_tile = X.first_ghost_tile;
     if (prepare_only) return true;
 #define MGB_BX(SHAPE, MODE, DP)                                                                                      \
     {                                                                                                                 \
@@ -200,8 +203,10 @@ static bool launch_box_variant(Context& ctx, const Csr<TV>& M, int mode, const T
         int per = 0;                                                                                                  \
         MGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, NB, smem));                                \
         if (per < 1) return false;                                                                                    \
+        /* a kernel that waits for the exchange beside it must leave that kernel room on every SM */                  \
+        if (bw.epoch && per * NB > 1536) return false;                                                                \
         const int grid = (int)std::min<long long>(P.ntiles, (long long)ctx.sm_count * per);                           \
-        kern<<<grid, NB, smem, ctx.stream>>>(P, X.c0, pp, recs, D.pid, X.ctab, X.dtab, x, b, d, y);                         \
+        kern<<<grid, NB, smem, ctx.stream>>>(P, X.c0, pp, bw, recs, D.pid, X.ctab, X.dtab, x, b, d, y);                     \
     }
 #define MGB_BXS(MODE, DP) { if (X.shape == 7) MGB_BX(7, MODE, DP) else MGB_BX(27, MODE, DP) }
     if (mode == MODE_SPMV) MGB_BXS(MODE_SPMV, false)
@@ -246,10 +251,11 @@ static bool launch_box_direct(Context& ctx, const Csr<TV>& M, int mode, const TV
 }
 template <typename TA, typename TV>
 static bool launch_box(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d, const TV* dpat,
-                       TV* y, const PutPlan& pp, bool prepare_only = false) {
+                       TV* y, const PutPlan& pp, bool prepare_only = false, const BoxWait& bw = no_wait()) {
     if constexpr (std::is_same<TA, TV>::value && (std::is_same<TV, double>::value || std::is_same<TV, cplx>::value)) {
         if (!M.box.ok || !ctx.use_box || M.n_rows < ctx.box_min_rows) return false;
-        const int variant = (M.box.shape == 27 && ctx.box_variant27 >= 0) ? ctx.box_variant27 : ctx.box_variant;
+        int variant = (M.box.shape == 27 && ctx.box_variant27 >= 0) ? ctx.box_variant27 : ctx.box_variant;
+        if (sizeof(TV) == 16 && ctx.box_variant_c >= 0) variant = ctx.box_variant_c;      // complex double: its own choice
         if (!prepare_only) {
             if (mode == MODE_ADD || x == y) return false;
             // the fused first two sweeps: b is the staged vector, d must be folded, no ghost rows, staged variants only
@@ -261,11 +267,15 @@ static bool launch_box(Context& ctx, const Csr<TA>& M, int mode, const TV* x, co
         }
         constexpr int F = sizeof(TV) / 8;      // complex tiles hold half the rows
         switch (variant) {
-            case 1: return launch_box_variant<TV, 2, 512 / F, 2>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only);
-            case 3: return launch_box_variant<TV, 4, 256 / F, 1>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only);
-            case 11: return launch_box_variant<TV, 4, 1024 / F, 2>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only);
-            case 9: return launch_box_direct<TV, 2>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only);
-            default: return launch_box_variant<TV, 1, 1024 / F, 2>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only);
+            case 1: return launch_box_variant<TV, 2, 512 / F, 2>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only, bw);
+            case 3: return launch_box_variant<TV, 4, 256 / F, 1>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only, bw);
+            case 11: return launch_box_variant<TV, 4, 1024 / F, 2>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only, bw);
+            // the same tile sizes for both value types (the variants above halve NB for complex values)
+            case 20: return launch_box_variant<TV, 2, 512, 1>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only, bw);
+            case 21: return launch_box_variant<TV, 1, 512, 2>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only, bw);
+            case 22: return launch_box_variant<TV, 2, 512, 2>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only, bw);
+            case 9: return bw.epoch ? false : launch_box_direct<TV, 2>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only);
+            default: return launch_box_variant<TV, 1, 1024 / F, 2>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only, bw);
         }
     } else {
         return false;
@@ -348,12 +358,12 @@ static void csr_apply(Context& ctx, const Csr<TA>& M, int mode, const TV* x, con
     MGB_CHECK(M.present(), "matrix not uploaded");
     const bool use_pat = M.pat.present && m == 1 && ctx.use_patterns;
     MGB_CHECK(!pp.on || use_pat, "fused put needs the stencil-dictionary format");
-    const bool use_gx = use_pat && !pp.on && ctx.grid_transfers > 0 && launch_grid_xfer<TA, TV>(ctx, M, mode, x, y, true);
+    const bool use_gx = use_pat && ctx.grid_transfers > 0 && launch_grid_xfer<TA, TV>(ctx, M, mode, x, y, true, pp);
     // bytes the device format really streams: the grid-hinted transfer kernels read no matrix stream at all
     const double fmt = use_gx ? vec_bytes<TA, TV>(M, mode, m, false)
                               : (use_pat ? M.pat.matrix_bytes(M.n_rows) + vec_bytes<TA, TV>(M, mode, m, dpat != nullptr) : -1.0);
     Launch L(ctx, kind, level, csr_bytes<TA, TV>(M, mode, m), fmt);
-    if (use_gx && launch_grid_xfer<TA, TV>(ctx, M, mode, x, y)) return;
+    if (use_gx && launch_grid_xfer<TA, TV>(ctx, M, mode, x, y, false, pp)) return;
     if (use_pat && ctx.split_test > 0 && M.n_rows > 2 * ctx.split_test) {
         // test hook (mgb200_set_option "split_test"): the split launch sequence of the multi-GPU overlap path
         pattern_apply_split<TA, TV>(ctx, M, mode, x, b, d, dpat, y, ctx.split_test, M.n_rows - ctx.split_test, 16384, [] {}, pp);

@@ -259,6 +259,8 @@ static void host_gx_run(const GridXfer& X, const std::vector<double>& tab, const
     }
 }
 
+#include "multi.cuh"
+
 extern "C" {
 
 const char* mgb200_last_error(void) { return g_last_error.c_str(); }
@@ -633,7 +635,9 @@ int mgb200_set_option(mgb200_handle h, const char* key, int64_t value) {
         else if (k == "box") H->ctx.use_box = (int)value;
         else if (k == "box_variant") H->ctx.box_variant = (int)value;
         else if (k == "box_variant27") H->ctx.box_variant27 = (int)value;
+        else if (k == "box_variant_c") H->ctx.box_variant_c = (int)value;
         else if (k == "fuse_first") H->ctx.fuse_first_sweeps = (int)value;
+        else if (k == "overlap_box") H->ctx.overlap_box = (int)value;
         else if (k == "box_min_rows") H->ctx.box_min_rows = (int)value;
         else if (k == "grid_transfers") H->ctx.grid_transfers = (int)value;
         else if (k == "split_test") H->ctx.split_test = (int)value;
@@ -1036,6 +1040,225 @@ int mgb200_host_interior_rows(int64_t n_rows, const int64_t* rowptr, const int64
     interior_rows(H, n_in_owned, lo, hi);
     out[0] = lo;
     out[1] = hi;
+    MGB_CATCH
+}
+
+
+/* ---- single-process multi-GPU entry (multi.cuh) ---------------------------------------------------------------------- */
+static size_t mgb_val_bytes(int val_type, bool real_part) {
+    switch (val_type) {
+        case MGB200_FP64: return 8;
+        case MGB200_CFP64: return real_part ? 8 : 16;
+        case MGB200_FP32: return 4;
+        default: return real_part ? 4 : 8;
+    }
+}
+
+int mgb200_multi_create(mgb200_multi_handle* out, int n_devices, const int* devices, int val_type, int levels, int nrhs,
+                        char cycle_type, int relax_kind, const int64_t* relax_pre, const int64_t* relax_post) {
+    MGB_TRY
+    MGB_CHECK(out && n_devices >= 1 && n_devices <= 64, "bad device count");
+    int have = 0;
+    MGB_CUDA(cudaGetDeviceCount(&have));
+    std::unique_ptr<MultiHandle> M(new MultiHandle());
+    M->G = n_devices;
+    M->val_type = val_type;
+    M->levels = levels;
+    M->nrhs = nrhs;
+    for (int g = 0; g < n_devices; ++g) {
+        const int dev = devices ? devices[g] : g;
+        MGB_CHECK(dev >= 0 && dev < have, "device index out of range");
+        M->devices.push_back(dev);
+    }
+    M->h.assign(n_devices, nullptr);
+    char id[128];
+    if (n_devices > 1) {
+        const int st = mgb200_dist_unique_id(id);
+        if (st != 0) return st;
+    }
+    MultiHandle* Mp = M.get();
+    const int st = multi_run(Mp, [&](int g) {
+        int s = mgb200_create(&Mp->h[g], val_type, levels, nrhs, cycle_type, relax_kind, relax_pre, relax_post, Mp->devices[g]);
+        if (s == 0) s = mgb200_dist_init(Mp->h[g], g, Mp->G, Mp->G > 1 ? id : nullptr);
+        return s;
+    });
+    if (st != 0) {
+        g_last_error = Mp->error;
+        for (auto h : Mp->h)
+            if (h) mgb200_destroy(h);
+        return st;
+    }
+    *out = reinterpret_cast<mgb200_multi_handle>(M.release());
+    MGB_CATCH
+}
+
+int mgb200_multi_destroy(mgb200_multi_handle mh) {
+    MGB_TRY
+    MultiHandle* M = reinterpret_cast<MultiHandle*>(mh);
+    if (!M) return 0;
+    multi_run(M, [&](int g) { return M->h[g] ? mgb200_destroy(M->h[g]) : 0; });
+    delete M;
+    MGB_CATCH
+}
+
+int mgb200_multi_upload_level(mgb200_multi_handle mh, int level, int64_t n, int64_t nc, const int64_t* row_offsets,
+                              const int64_t* coarse_row_offsets, const int64_t* a_colptr, const int64_t* a_rowval,
+                              const void* a_nzval, const int64_t* p_colptr, const int64_t* p_rowval, const void* p_nzval,
+                              const int64_t* r_colptr, const int64_t* r_rowval, const void* r_nzval, const void* d, int index_base) {
+    MGB_TRY
+    MultiHandle* M = reinterpret_cast<MultiHandle*>(mh);
+    MGB_CHECK(M, "null handle");
+    MGB_CHECK(a_colptr && a_rowval && a_nzval && p_colptr && p_rowval && p_nzval && r_colptr && r_rowval && r_nzval && d, "null array");
+    int st;
+    if (!row_offsets || M->G == 1) {
+        // replicated level (or one device): every rank holds the global matrices
+        st = multi_run(M, [&](int g) {
+            return mgb200_upload_level(M->h[g], level, n, nc, a_colptr, a_rowval, a_nzval, p_colptr, p_rowval, p_nzval, r_colptr,
+                                       r_rowval, r_nzval, d, index_base);
+        });
+        if (level == 1) {
+            M->fine_offsets.assign(M->G + 1, 0);
+            M->fine_offsets[M->G] = n;          // every rank works on the whole vector (G == 1, or nothing is partitioned)
+        }
+    } else {
+        MGB_CHECK(coarse_row_offsets, "coarse_row_offsets required for a row-partitioned level");
+        MGB_CHECK(row_offsets[0] == 0 && row_offsets[M->G] == n && coarse_row_offsets[0] == 0 && coarse_row_offsets[M->G] == nc,
+                  "row offsets must cover [0, n] and [0, nc]");
+        const size_t va = mgb_val_bytes(M->val_type, false), vr = mgb_val_bytes(M->val_type, true);
+        if (level == 1) M->fine_offsets.assign(row_offsets, row_offsets + M->G + 1);
+        st = multi_run(M, [&](int g) {
+            const int64_t lo = row_offsets[g], hi = row_offsets[g + 1], clo = coarse_row_offsets[g], chi = coarse_row_offsets[g + 1];
+            const CscSlice A = csc_columns(a_colptr, a_rowval, a_nzval, va, lo, hi, index_base);
+            const CscSlice P = csc_columns(p_colptr, p_rowval, p_nzval, vr, lo, hi, index_base);
+            const CscSlice R = csc_columns(r_colptr, r_rowval, r_nzval, vr, clo, chi, index_base);
+            return mgb200_dist_upload_level(M->h[g], level, n, row_offsets, nc, coarse_row_offsets, A.colptr.data(), A.rowval, A.nzval,
+                                            P.colptr.data(), P.rowval, P.nzval, R.colptr.data(), R.rowval, R.nzval,
+                                            static_cast<const unsigned char*>(d) + (size_t)lo * va, index_base);
+        });
+    }
+    if (st != 0) g_last_error = M->error;
+    return st;
+    MGB_CATCH
+}
+
+int mgb200_multi_set_level_grid(mgb200_multi_handle mh, int level, int dim, const int64_t* n_fine_nodes, const int64_t* n_coarse_nodes) {
+    MGB_TRY
+    MultiHandle* M = reinterpret_cast<MultiHandle*>(mh);
+    MGB_CHECK(M, "null handle");
+    for (int g = 0; g < M->G; ++g) {
+        const int st = mgb200_set_level_grid(M->h[g], level, dim, n_fine_nodes, n_coarse_nodes);
+        if (st != 0) return st;
+    }
+    MGB_CATCH
+}
+
+int mgb200_multi_upload_coarsest(mgb200_multi_handle mh, int64_t n, const int64_t* colptr, const int64_t* rowval, const void* nzval,
+                                 int index_base) {
+    MGB_TRY
+    MultiHandle* M = reinterpret_cast<MultiHandle*>(mh);
+    MGB_CHECK(M, "null handle");
+    const int st = multi_run(M, [&](int g) { return mgb200_upload_coarsest(M->h[g], n, colptr, rowval, nzval, index_base); });
+    if (st != 0) g_last_error = M->error;
+    return st;
+    MGB_CATCH
+}
+
+/* the solve entry points: every rank gets its rows of b and x (nrhs = 1: contiguous slices of the global vectors) */
+static int multi_solve(mgb200_multi_handle mh, const void* b, void* x, const std::function<int(int, const void*, void*)>& call) {
+    MultiHandle* M = reinterpret_cast<MultiHandle*>(mh);
+    if (!M) {
+        g_last_error = "mgb200: null handle";
+        return -1;
+    }
+    if (M->fine_offsets.size() != (size_t)M->G + 1 || !b || !x) {
+        g_last_error = "mgb200: level 1 not uploaded, or null vector";
+        return -1;
+    }
+    if (M->nrhs != 1 && M->G > 1) {
+        g_last_error = "mgb200_multi_*: the row-partitioned path takes one right-hand side";
+        return -1;
+    }
+    const size_t va = mgb_val_bytes(M->val_type, false);
+    const int st = multi_run(M, [&](int g) {
+        const int64_t lo = (M->fine_offsets[g + 1] == M->fine_offsets[M->G] && M->fine_offsets[g] == 0 && g > 0) ? 0 : M->fine_offsets[g];
+        return call(g, static_cast<const unsigned char*>(b) + (size_t)lo * va, static_cast<unsigned char*>(x) + (size_t)lo * va);
+    });
+    if (st != 0) g_last_error = M->error;
+    return st;
+}
+
+int mgb200_multi_solveMG(mgb200_multi_handle mh, const void* b, void* x, double tol, int max_iter, int* iter, double* resvec) {
+    MGB_TRY
+    MGB_CHECK(iter && resvec, "null argument");
+    MultiHandle* M = reinterpret_cast<MultiHandle*>(mh);
+    MGB_CHECK(M, "null handle");
+    std::vector<int> its(M->G, 0);
+    std::vector<std::vector<double>> rv(M->G, std::vector<double>(max_iter + 1, 0.0));
+    const int st = multi_solve(mh, b, x, [&](int g, const void* bg, void* xg) {
+        return mgb200_solveMG(M->h[g], bg, xg, tol, max_iter, &its[g], rv[g].data());
+    });
+    if (st != 0) return st;
+    *iter = its[0];
+    std::copy(rv[0].begin(), rv[0].end(), resvec);
+    MGB_CATCH
+}
+
+int mgb200_multi_solveCG(mgb200_multi_handle mh, const void* b, void* x, double tol, int max_iter, int* iter, int* flag,
+                         double* resvec) {
+    MGB_TRY
+    MGB_CHECK(iter && flag && resvec, "null argument");
+    MultiHandle* M = reinterpret_cast<MultiHandle*>(mh);
+    MGB_CHECK(M, "null handle");
+    std::vector<int> its(M->G, 0), fl(M->G, 0);
+    std::vector<std::vector<double>> rv(M->G, std::vector<double>(std::max(max_iter, 1), 0.0));
+    const int st = multi_solve(mh, b, x, [&](int g, const void* bg, void* xg) {
+        return mgb200_solveCG(M->h[g], bg, xg, tol, max_iter, &its[g], &fl[g], rv[g].data());
+    });
+    if (st != 0) return st;
+    *iter = its[0];
+    *flag = fl[0];
+    std::copy(rv[0].begin(), rv[0].end(), resvec);
+    MGB_CATCH
+}
+
+int mgb200_multi_solveFGMRES(mgb200_multi_handle mh, const void* b, void* x, int inner, int flexible, double tol, int max_iter,
+                             int* iter, int* flag, double* resvec, int* nres) {
+    MGB_TRY
+    MGB_CHECK(iter && flag && resvec && nres, "null argument");
+    MultiHandle* M = reinterpret_cast<MultiHandle*>(mh);
+    MGB_CHECK(M, "null handle");
+    std::vector<int> its(M->G, 0), fl(M->G, 0), nr(M->G, 0);
+    std::vector<std::vector<double>> rv(M->G, std::vector<double>(std::max(inner * max_iter, 1), 0.0));
+    const int st = multi_solve(mh, b, x, [&](int g, const void* bg, void* xg) {
+        return mgb200_solveFGMRES(M->h[g], bg, xg, inner, flexible, tol, max_iter, &its[g], &fl[g], rv[g].data(), &nr[g]);
+    });
+    if (st != 0) return st;
+    *iter = its[0];
+    *flag = fl[0];
+    *nres = nr[0];
+    std::copy(rv[0].begin(), rv[0].begin() + nr[0], resvec);
+    MGB_CATCH
+}
+
+int mgb200_multi_precondition(mgb200_multi_handle mh, const void* r, void* z) {
+    MGB_TRY
+    MultiHandle* M = reinterpret_cast<MultiHandle*>(mh);
+    MGB_CHECK(M, "null handle");
+    return multi_solve(mh, r, z, [&](int g, const void* rg, void* zg) { return mgb200_precondition(M->h[g], rg, zg); });
+    MGB_CATCH
+}
+
+int mgb200_multi_info(mgb200_multi_handle mh, int64_t* out) {
+    MGB_TRY
+    MultiHandle* M = reinterpret_cast<MultiHandle*>(mh);
+    MGB_CHECK(M && out, "null argument");
+    std::vector<std::vector<int64_t>> o(M->G, std::vector<int64_t>(4, 0));
+    const int st = multi_run(M, [&](int g) { return mgb200_dist_info(M->h[g], o[g].data()); });
+    if (st != 0) {
+        g_last_error = M->error;
+        return st;
+    }
+    for (int k = 0; k < 4; ++k) out[k] = o[0][k];
     MGB_CATCH
 }
 

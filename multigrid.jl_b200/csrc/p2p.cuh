@@ -55,10 +55,18 @@ struct ChanDev {
     int world, rank;
 };
 
-// The exchange number is advanced by the last CTA to finish (every CTA has read it by then).
-__device__ __forceinline__ void p2p_advance(unsigned long long e, unsigned long long* epoch, unsigned* ticket) {
+// The exchange number is advanced by the last CTA to finish (every CTA has read it by then).  `consumed` (may be
+// null) counts the exchanges whose consumer has passed: a consumer that runs BESIDE the exchange kernel and waits for
+// the ghost rows inside the kernel (box.cuh) advances it itself; in the serial form the exchange kernel does.
+__device__ __forceinline__ void p2p_advance(unsigned long long e, unsigned long long* epoch, unsigned* ticket,
+                                            unsigned long long* consumed = nullptr) {
+    __threadfence();          // the ghost rows written above are visible before the exchange number is
     __syncthreads();
-    if (threadIdx.x == 0 && atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1) *epoch = e;
+    if (threadIdx.x == 0 && atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1) {
+        if (consumed) *consumed = e;
+        __threadfence();
+        *reinterpret_cast<volatile unsigned long long*>(epoch) = e;
+    }
 }
 
 // Halo exchange in one kernel: gather the owned rows the peers asked for and store them as LL words straight into
@@ -68,7 +76,7 @@ template <typename TV>
 __global__ void p2p_halo_kernel(const ChanDev<TV>* __restrict__ cd, TV* __restrict__ v,
                                 const int* __restrict__ send_idx, int n_send, long long n_ghost, long long n_lo,
                                 long long n_owned, int m, unsigned long long* epoch, unsigned* ticket,
-                                unsigned long long* trace, int skip_put) {
+                                unsigned long long* trace, int skip_put, unsigned long long* consumed) {
     constexpr int W = LL<TV>::W;
     const unsigned long long e = *epoch + 1;
     const int par = (int)(e & 1);
@@ -96,8 +104,11 @@ __global__ void p2p_halo_kernel(const ChanDev<TV>* __restrict__ cd, TV* __restri
         v[pos * m + j] = LL<TV>::get(rb + t * W, flag);
     }
     if (tr) trow[2] = trow[3] = globaltimer_ns();
-    p2p_advance(e, epoch, ticket);
+    p2p_advance(e, epoch, ticket, consumed);
 }
+
+// the exchange that ran beside a consumer which, after all, did not wait for it in the kernel
+static __global__ void p2p_mark_consumed_kernel(const unsigned long long* epoch, unsigned long long* consumed) { *consumed = *epoch; }
 
 // Gather of a replicated vector in one kernel: my piece v[off .. off+cnt) (element units) goes to the same place
 // of every peer's buffer; the pieces of the other ranks are polled out of my buffer (same layout as v).
@@ -139,8 +150,11 @@ struct P2P {
     unsigned char* block = nullptr;          // my IPC-exported block: flag words, then the receive buffers
     size_t block_bytes = 0;
     std::vector<unsigned char*> peer;        // mapped blocks of the peers (peer[rank] == block)
+    std::vector<char> same_process;          // peer q is a device of this process (plain peer access, no IPC mapping)
     std::vector<ChanHost> chan;              // levels halo channels + 1 gather channel
     unsigned long long* epoch = nullptr;     // per channel, device
+    unsigned long long* consumed = nullptr;  // per channel, device: exchanges whose consumer has passed (see p2p_advance)
+    unsigned* ticket2 = nullptr;             // per channel, device: CTA counter of a consumer that waits in-kernel
     unsigned* ticket = nullptr;              // per channel, device
     int gather_level = -1;                   // level index (0-based) of the first replicated level
     unsigned long long* trace = nullptr;     // per halo channel P2P_TRACE_ROWS x 4 timestamps (MGB200_P2P_TRACE=1)

@@ -52,8 +52,10 @@ static inline void jacobi_eig_sym(int N, std::vector<double>& A, std::vector<dou
 // t = pinv(H) * xi for Hermitian H (n x n, row-major).  Singular values <= eps*n*max are
 // dropped, the rule of Julia's LinearAlgebra.pinv default (rtol = eps*min(size)).
 // A complex Hermitian H = A + iB is embedded as the real symmetric [[A,-B],[B,A]].
+// eps: machine epsilon of the hierarchy's value type (the reference's H is Float32 / ComplexF32 for single-precision
+// hierarchies, so its pinv drops singular values below eps(Float32) * n * max).
 static inline void hermitian_pinv_apply(int n, const std::vector<zc>& H, const std::vector<zc>& xi,
-                                        std::vector<zc>& t) {
+                                        std::vector<zc>& t, double eps = std::numeric_limits<double>::epsilon()) {
     const int N = 2 * n;
     std::vector<double> M((size_t)N * N), V;
     for (int i = 0; i < n; ++i)
@@ -67,7 +69,7 @@ static inline void hermitian_pinv_apply(int n, const std::vector<zc>& H, const s
     jacobi_eig_sym(N, M, V);
     double smax = 0.0;
     for (int i = 0; i < N; ++i) smax = std::max(smax, std::fabs(M[(size_t)i * N + i]));
-    const double tol = std::numeric_limits<double>::epsilon() * n * smax;
+    const double tol = eps * n * smax;
     std::vector<double> rhs(N), out(N, 0.0);
     for (int i = 0; i < n; ++i) {
         rhs[i] = xi[i].real();

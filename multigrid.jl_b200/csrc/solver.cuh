@@ -216,17 +216,10 @@ struct Hierarchy : HierarchyBase {
             // the hint is only kept for the operator it describes exactly (grid_xfer.cuh); otherwise nothing changes
             HostPatterns<RT> hp;
             upload_csr<RT>(ctx, lv.P, n, nc, pcp, prv, static_cast<const RT*>(pnz), base, false, true, &hp);
-            auto dense = [&](Csr<RT>& M) {      // dense value table of a verified hint (grid_xfer.cuh)
-                if (!M.gx.ok) return;
-                const std::vector<RT> t = gx_dense_table<RT>(M.gx, hp.val);
-                RT* dt = dev_alloc<RT>(t.size());
-                MGB_CUDA(cudaMemcpy(dt, t.data(), t.size() * sizeof(RT), cudaMemcpyHostToDevice));
-                M.gx.tab = dt;
-            };
-            if (lv.P.pat.present && gx_verify_prolongation<RT>(hp, n, lv.gn, lv.gN, lv.P.gx)) dense(lv.P);
+            if (lv.P.pat.present && gx_verify_prolongation<RT>(hp, n, lv.gn, lv.gN, lv.P.gx)) gx_attach_table(lv.P, hp);
             hp = HostPatterns<RT>();
             upload_csr<RT>(ctx, lv.R, nc, n, rcp, rrv, static_cast<const RT*>(rnz), base, false, true, &hp);
-            if (lv.R.pat.present && gx_verify_restriction<RT>(hp, nc, lv.gn, lv.gN, lv.R.gx)) dense(lv.R);
+            if (lv.R.pat.present && gx_verify_restriction<RT>(hp, nc, lv.gn, lv.gN, lv.R.gx)) gx_attach_table(lv.R, hp);
         } else {
             upload_csr<RT>(ctx, lv.P, n, nc, pcp, prv, static_cast<const RT*>(pnz), base, false);
             upload_csr<RT>(ctx, lv.R, nc, n, rcp, rrv, static_cast<const RT*>(rnz), base, false);
@@ -240,6 +233,15 @@ struct Hierarchy : HierarchyBase {
         L[level].n = nc;
         L[level].nalloc = nc;
         work_ready = false;
+    }
+
+    // dense value table of a verified grid hint (grid_xfer.cuh)
+    void gx_attach_table(Csr<RT>& M, const HostPatterns<RT>& hp) {
+        if (!M.gx.ok) return;
+        const std::vector<RT> t = gx_dense_table<RT>(M.gx, hp.val);
+        RT* dt = dev_alloc<RT>(t.size());
+        MGB_CUDA(cudaMemcpy(dt, t.data(), t.size() * sizeof(RT), cudaMemcpyHostToDevice));
+        M.gx.tab = dt;
     }
 
     // the meshes of level l and l+1 (param.Meshes[l].n + 1 nodes per dimension), BEFORE upload_level(level)
@@ -553,8 +555,26 @@ struct Hierarchy : HierarchyBase {
                 if (lc.nalloc < lc.n) lc.nalloc = lc.n;
             }
             upload_csr<TV>(ctx, lv.A, lv.hA.n_rows, lv.nalloc, lv.hA.rowptr.data(), lv.hA.col.data(), lv.hA.val.data(), 0, false);
-            upload_csr<RT>(ctx, lv.P, lv.hP.n_rows, pcols, lv.hP.rowptr.data(), lv.hP.col.data(), lv.hP.val.data(), 0, false);
-            upload_csr<RT>(ctx, lv.R, lv.hR.n_rows, lv.nalloc, lv.hR.rowptr.data(), lv.hR.col.data(), lv.hR.val.data(), 0, false);
+            if (lv.ghint && lv.gn[2] > 1) {
+                // grid hint on a z-slab (grid_xfer.cuh): the rows are whole planes of the global grids, the local column
+                // indices are the global ones minus the first owned row of the column space - checked row by row
+                const long long pf = (long long)lv.gn[0] * lv.gn[1], pc = (long long)lv.gN[0] * lv.gN[1];
+                const long long clo = lv.coarse_row_offsets[comm.rank], chi = lv.coarse_row_offsets[comm.rank + 1];
+                HostPatterns<RT> hp;
+                upload_csr<RT>(ctx, lv.P, lv.hP.n_rows, pcols, lv.hP.rowptr.data(), lv.hP.col.data(), lv.hP.val.data(), 0, false, true, &hp);
+                if (lv.P.pat.present && sp.lo % pf == 0 && sp.n_owned % pf == 0 &&
+                    gx_verify_prolongation<RT>(hp, lv.hP.n_rows, lv.gn, lv.gN, lv.P.gx, (int)(sp.lo / pf), (int)(sp.n_owned / pf),
+                                               lc.sp.dist ? lc.sp.lo : 0))
+                    gx_attach_table(lv.P, hp);
+                hp = HostPatterns<RT>();
+                upload_csr<RT>(ctx, lv.R, lv.hR.n_rows, lv.nalloc, lv.hR.rowptr.data(), lv.hR.col.data(), lv.hR.val.data(), 0, false, true, &hp);
+                if (lv.R.pat.present && clo % pc == 0 && (chi - clo) % pc == 0 &&
+                    gx_verify_restriction<RT>(hp, lv.hR.n_rows, lv.gn, lv.gN, lv.R.gx, (int)(clo / pc), (int)((chi - clo) / pc), sp.lo))
+                    gx_attach_table(lv.R, hp);
+            } else {
+                upload_csr<RT>(ctx, lv.P, lv.hP.n_rows, pcols, lv.hP.rowptr.data(), lv.hP.col.data(), lv.hP.val.data(), 0, false);
+                upload_csr<RT>(ctx, lv.R, lv.hR.n_rows, lv.nalloc, lv.hR.rowptr.data(), lv.hR.col.data(), lv.hR.val.data(), 0, false);
+            }
             // rows that read no ghost row of their input vector (they may run beside the halo exchange, apply_x)
             interior_rows(lv.hA, sp.n_owned, lv.A.int_lo, lv.A.int_hi);
             interior_rows(lv.hR, sp.n_owned, lv.R.int_lo, lv.R.int_hi);
@@ -695,6 +715,36 @@ struct Hierarchy : HierarchyBase {
         const bool need = comm.active() && lin >= 0 && lin < levels && L[lin].sp.dist;
         const bool split = need && p2p.on && ctx.use_overlap && !ctx.profiling && pattern_in_use(ctx, M, m) &&
                            2LL * (M.int_hi - M.int_lo) >= M.n_rows;
+        if constexpr (std::is_same<TA, TV>::value) {
+            // box-stencil kernel beside the exchange of its input vector: the kernel starts at once, its tiles that read
+            // ghost rows come last and wait in the kernel for the exchange number (box.cuh, BoxWait)
+            if (need && p2p.on && ctx.overlap_box && !ctx.profiling && m == 1 && M.box.ok && pattern_in_use(ctx, M, m) &&
+                ctx.split_test == 0 && ctx.use_box && M.n_rows >= ctx.box_min_rows && mode != MODE_ADD && v != y) {
+                MGB_CUDA(cudaEventRecord(ctx.ev_fork, ctx.stream));
+                MGB_CUDA(cudaStreamWaitEvent(ctx.side, ctx.ev_fork, 0));
+                exchange(lin, v, ctx.side, 0, true);
+                MGB_CUDA(cudaEventRecord(ctx.ev_join, ctx.side));
+                BoxWait bw;
+                bw.epoch = p2p.epoch + lin;
+                bw.consumed = p2p.consumed + lin;
+                bw.ticket = p2p.ticket2 + lin;
+                bool ran;
+                {
+                    const double fmt = M.pat.matrix_bytes(M.n_rows) + vec_bytes<TA, TV>(M, mode, m, dpat != nullptr);
+                    Launch La(ctx, kind, level, csr_bytes<TA, TV>(M, mode, m), fmt);
+                    ran = launch_box<TA, TV>(ctx, M, mode, v, b, d, dpat, y, pp, false, bw);
+                    if (!ran) La.cancel();
+                }
+                MGB_CUDA(cudaStreamWaitEvent(ctx.stream, ctx.ev_join, 0));
+                if (!ran) {      // the box kernel declined: mark the exchange consumed and run the ordinary pass
+                    p2p_mark_consumed_kernel<<<1, 1, 0, ctx.stream>>>(p2p.epoch + lin, p2p.consumed + lin);
+                    MGB_LAUNCH_CHECK();
+                    csr_apply<TA, TV>(ctx, M, mode, v, b, d, y, m, kind, level, dpat, pp);
+                }
+                note_put(put_level, pp, y);
+                return;
+            }
+        }
         if (!split) {
             if (need) exchange(lin, v);
             csr_apply<TA, TV>(ctx, M, mode, v, b, d, y, m, kind, level, dpat, pp);
@@ -731,7 +781,7 @@ struct Hierarchy : HierarchyBase {
     }
 
     // halo exchange of a level-l vector laid out [ghosts below | owned | ghosts above], v at the first owned row
-    void exchange(int l, TV* v, cudaStream_t stream = nullptr, int max_ctas = 0) {
+    void exchange(int l, TV* v, cudaStream_t stream = nullptr, int max_ctas = 0, bool consumer_waits = false) {
         if (!comm.active() || l < 0 || l >= levels || !L[l].sp.dist) return;
         DistSpace& sp = L[l].sp;
         if (!stream) stream = ctx.stream;
@@ -754,7 +804,7 @@ struct Hierarchy : HierarchyBase {
             p2p_halo_kernel<TV><<<g, 256, 0, stream>>>(cd, v, sp.d_send_idx, sp.n_send, sp.n_ghost, sp.n_lo,
                                                             sp.n_owned, m, p2p.epoch + l, p2p.ticket + l,
                                                             p2p.trace ? p2p.trace + (size_t)l * P2P_TRACE_ROWS * 4 : nullptr,
-                                                            skip_put);
+                                                            skip_put, consumer_waits ? nullptr : p2p.consumed + l);
             MGB_LAUNCH_CHECK();
             return;
         }
@@ -802,8 +852,10 @@ struct Hierarchy : HierarchyBase {
         if (ctx.stream) cudaStreamSynchronize(ctx.stream);
         p2p_trace_report();
         for (int q = 0; q < (int)p2p.peer.size(); ++q)
-            if (q != comm.rank && p2p.peer[q]) cudaIpcCloseMemHandle(p2p.peer[q]);
+            if (q != comm.rank && p2p.peer[q] && !(q < (int)p2p.same_process.size() && p2p.same_process[q]))
+                cudaIpcCloseMemHandle(p2p.peer[q]);
         p2p.peer.clear();
+        p2p.same_process.clear();
         for (auto& c : p2p.chan) {
             if (c.dev) cudaFree(c.dev);
             c.dev = nullptr;
@@ -816,6 +868,8 @@ struct Hierarchy : HierarchyBase {
         p2p.block_bytes = 0;
         dev_free(p2p.epoch);
         dev_free(p2p.ticket);
+        dev_free(p2p.consumed);
+        dev_free(p2p.ticket2);
         p2p.on = false;
         p2p.gather_level = -1;
     }
@@ -890,14 +944,17 @@ struct Hierarchy : HierarchyBase {
             if (cudaIpcGetMemHandle(&mine, p2p.block) != cudaSuccess) ok = 0;
         }
         cudaGetLastError();
-        // table: handle | ok | per channel {buf_off[2], recv_off[w]}
+        // table: handle | ok | process id | device | block address | per channel {buf_off[2], recv_off[w]}
         const size_t per_chan = 2 + (size_t)w;
-        std::vector<long long> tab(8 + 1 + per_chan * nchan, 0);
+        std::vector<long long> tab(8 + 4 + per_chan * nchan, 0);
         static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
         std::memcpy(tab.data(), &mine, 64);
         tab[8] = ok;
+        tab[9] = (long long)getpid();
+        tab[10] = ctx.device;
+        tab[11] = (long long)reinterpret_cast<uintptr_t>(p2p.block);
         for (int c = 0; c < nchan; ++c) {
-            long long* t = tab.data() + 9 + per_chan * c;
+            long long* t = tab.data() + 12 + per_chan * c;
             t[0] = (long long)p2p.chan[c].buf_off[0];
             t[1] = (long long)p2p.chan[c].buf_off[1];
             if (c < levels && p2p.chan[c].used)
@@ -909,10 +966,27 @@ struct Hierarchy : HierarchyBase {
         auto T = [&](int q) { return all + (size_t)q * tab.size(); };
         for (int q = 0; q < w; ++q) ok = ok && (int)T(q)[8];
         p2p.peer.assign(w, nullptr);
+        p2p.same_process.assign(w, 0);
         if (ok) {
             p2p.peer[r] = p2p.block;
             for (int q = 0; q < w && ok; ++q) {
                 if (q == r) continue;
+                if (T(q)[9] == (long long)getpid()) {
+                    // a device driven by another thread of this process (mgb200_multi_*): plain peer access
+                    int can = 0;
+                    const int dq = (int)T(q)[10];
+                    if (cudaDeviceCanAccessPeer(&can, ctx.device, dq) != cudaSuccess || !can) {
+                        ok = 0;
+                        cudaGetLastError();
+                    } else {
+                        const cudaError_t e = cudaDeviceEnablePeerAccess(dq, 0);
+                        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = 0;
+                        cudaGetLastError();
+                        p2p.peer[q] = reinterpret_cast<unsigned char*>((uintptr_t)T(q)[11]);
+                        p2p.same_process[q] = 1;
+                    }
+                    continue;
+                }
                 cudaIpcMemHandle_t hq;
                 std::memcpy(&hq, T(q), 64);
                 void* ptr = nullptr;
@@ -949,7 +1023,7 @@ struct Hierarchy : HierarchyBase {
             for (int par = 0; par < 2; ++par) cd.rbuf[par] = reinterpret_cast<const TV*>(p2p.block + ch.buf_off[par]);
             cd.send_off[0] = 0;
             for (int q = 0; q < w; ++q) {
-                const long long* tq = T(q) + 9 + per_chan * c;
+                const long long* tq = T(q) + 12 + per_chan * c;
                 const long long land = gather ? lg.coarse_row_offsets[r] : tq[2 + r];
                 for (int par = 0; par < 2; ++par)   // landing zone in LL words (2 x sizeof(TV) bytes per element)
                     cd.dst[par][q] = reinterpret_cast<TV*>(p2p.peer[q] + tq[par] + (size_t)land * m * sizeof(TV) * 2);
@@ -1001,8 +1075,12 @@ struct Hierarchy : HierarchyBase {
         }
         p2p.epoch = dev_alloc<unsigned long long>(nchan);
         p2p.ticket = dev_alloc<unsigned>(nchan);
+        p2p.consumed = dev_alloc<unsigned long long>(nchan);
+        p2p.ticket2 = dev_alloc<unsigned>(nchan);
         MGB_CUDA(cudaMemset(p2p.epoch, 0, nchan * sizeof(unsigned long long)));
         MGB_CUDA(cudaMemset(p2p.ticket, 0, nchan * sizeof(unsigned)));
+        MGB_CUDA(cudaMemset(p2p.consumed, 0, nchan * sizeof(unsigned long long)));
+        MGB_CUDA(cudaMemset(p2p.ticket2, 0, nchan * sizeof(unsigned)));
         for (int c = 0; c < levels; ++c) p2p.chan[c].put.epoch = p2p.epoch + c;
         put_done.assign(levels, nullptr);
         p2p.on = true;
@@ -1120,7 +1198,8 @@ struct Hierarchy : HierarchyBase {
                 for (int c = 0; c < inner; ++c)
                     Hs[(size_t)a * inner + c] = 0.5 * H[(size_t)a * inner + c] + 0.5 * std::conj(H[(size_t)c * inner + a]);
             H = Hs;
-            hermitian_pinv_apply(inner, H, xi, t);
+            hermitian_pinv_apply(inner, H, xi, t, sizeof(typename VT<TV>::real_t) == 4 ? (double)std::numeric_limits<float>::epsilon()
+                                                                                       : std::numeric_limits<double>::epsilon());
             zc tHt(0, 0), txi(0, 0);
             for (int a = 0; a < inner; ++a) {
                 zc Ht(0, 0);
@@ -1205,7 +1284,10 @@ struct Hierarchy : HierarchyBase {
     void jac_gmres(int l, const TV* r, TV* x, int inner) {
         Level<TV>& lv = L[l];
         FgmresMem<TV>& mem = lv.memRelax;
-        if (mem.inner != inner) alloc_fgmres(mem, (size_t)lv.nalloc * m, inner, vec_pad(l));
+        // adjustMemoryForNumRHS sizes memRelax[l] for max(relaxPre(l), relaxPost(l)) (MGsetup.jl:209-211) and
+        // FGMRES_relaxation raises an error when `inner` differs from that size (FGMRES.jl:60-62): same here
+        const int maxRelax = std::max(std::max(pre[l], post[l]), 1);
+        if (mem.inner != maxRelax) alloc_fgmres(mem, (size_t)lv.nalloc * m, maxRelax, vec_pad(l));
         PrecFn mm = [&, this](const TV* v) -> TV* {
             // y = D .* v  (0 + d*v is exact)
             Launch La(ctx, K_DIAG, l + 1, (2.0 * m + 1.0) * lv.n * sizeof(TV));

@@ -9,6 +9,10 @@ from conftest import make_problem
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-10
+# coarseSolveType "GMRES": the coarsest solve is one restart of GMRES(10) stopped at 1e-2 - an inexact, data-dependent
+# projection whose Gram-Schmidt coefficients differ between the two implementations in the last bits (different summation
+# order of the dots) and are amplified by the ill-conditioned 10 x 10 least-squares problem
+COARSE_GMRES_RTOL = 1e-10
 
 
 def _oracle(p):
@@ -128,7 +132,7 @@ def test_coarsest_gmres_option(VAL, n, cycle):
     x = np.zeros_like(b)
     _, _, it = mg.solveMG(p, b, x)
     assert it == it_ref
-    np.testing.assert_allclose(p.last_resvec, res_ref, rtol=1e-8)
+    np.testing.assert_allclose(p.last_resvec, res_ref, rtol=COARSE_GMRES_RTOL)
     assert res_ref[-1] < 0.2 * res_ref[0]
 
 
@@ -139,7 +143,16 @@ def test_jac_gmres_smoother():
     _, it_ref, res_ref = oc.solveMG(o, b, np.zeros_like(b))
     x = np.zeros_like(b)
     mg.solveMG(p, b, x)
-    np.testing.assert_allclose(p.last_resvec, res_ref, rtol=1e-8)
+    np.testing.assert_allclose(p.last_resvec, res_ref, rtol=RTOL)
+
+
+def test_jac_gmres_with_different_pre_and_post_counts_is_an_error():
+    """adjustMemoryForNumRHS sizes memRelax for max(relaxPre, relaxPost) and FGMRES_relaxation raises
+    "size of Krylov subspace is different than inner" for the other count (MGsetup.jl:209-211, FGMRES.jl:60-62)."""
+    import multigrid_jl_b200 as mg
+    A, AT, M, p, b = make_problem("poisson", [32, 32], 3, relax="Jac-GMRES", omega=0.75, pre=2, post=1, maxit=2)
+    with pytest.raises(mg.MGB200Error, match="size of Krylov subspace"):
+        mg.solveMG(p, b, np.zeros_like(b))
 
 
 @pytest.mark.parametrize("kind,n,levels", [("poisson", [128, 128], 4), ("poisson", [32, 32, 32], 4),

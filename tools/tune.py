@@ -39,9 +39,21 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cells", type=int, default=256)
     ap.add_argument("--levels", type=int, default=6)
+    ap.add_argument("--helmholtz", action="store_true", help="cfg5's family: ComplexF64 shifted Laplacian, rediscretised")
     ap.add_argument("sets", nargs="*")
     args = ap.parse_args()
-    A, M, p, b = build_problem(args.cells, args.levels)
+    if args.helmholtz:
+        M = mg.getRegularMesh([0, 1, 0, 1, 0, 1], [args.cells] * 3)
+        kappa2 = (2 * np.pi / (10 * (1.0 / args.cells))) ** 2
+        ctor = mg.getMultilevelOperatorConstructor(kappa2, lambda mesh, k2: mg.helmholtz_shifted(mesh, k2, 0.5),
+                                                   lambda mf, mc, pf, level: pf)
+        p = mg.getMGparam(np.complex128, np.int64, args.levels, 8, 20, 1e-6, "Jac", 0.8, 2, 2, 'V')
+        mg.MGsetup(ctor, M, p, 1)
+        rng = np.random.default_rng(0)
+        b = rng.random(p.As[0].shape[0]) + 1j * rng.random(p.As[0].shape[0])
+        b /= np.linalg.norm(b)
+    else:
+        A, M, p, b = build_problem(args.cells, args.levels)
     dev = mg.DeviceHierarchy(p, device=0)
     x = np.zeros_like(b)
     _, _, res0 = dev.solveMG(b, x, 0.0, 2)
@@ -51,8 +63,8 @@ def main():
         for k, v in defaults.items():
             dev.set_option(k, v)
         for k, v in opts.items():
-            defaults.setdefault(k, {"box": 1, "box_variant": 1, "box_min_rows": 100000, "grid_transfers": 1, "tma": 1,
-                                    "graphs": 1}.get(k, 0))
+            defaults.setdefault(k, {"box": 1, "box_variant": 1, "box_variant27": -1, "box_variant_c": -1, "box_min_rows": 100000,
+                                    "grid_transfers": 1, "tma": 1, "graphs": 1, "fuse_first": 1}.get(k, 0))
             dev.set_option(k, int(v))
         _, _, res = dev.solveMG(b, x, 0.0, 2)
         ms, kern = timeit(dev)
