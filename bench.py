@@ -383,7 +383,7 @@ def run_ours(args):
         kern.append({"kind": r["kind"], "level": r["level"], "launches": r["launches"],
                      "avg_us": 1e3 * r["total_ms"] / r["launches"], "gbs": gbs, "format_gbs": fgbs,
                      "share": r["total_ms"] / tot_ms})
-    log("[bench] per-kernel (events): " + json.dumps(kern[:8]))
+    log(f"[bench rank {rank}] per-kernel (events): " + json.dumps(kern[:8]))
     achieved = dom["bytes"] / (dom["total_ms"] * 1e-3) / 1e9
     fmt_achieved = dom["format_bytes"] / (dom["total_ms"] * 1e-3) / 1e9
     fmt_cycle = sum(r["format_bytes"] for r in prof) / args.steps

@@ -536,6 +536,68 @@ box_direct_kernel(const __grid_constant__ BoxPlan P, const __grid_constant__ Box
     }
 }
 
+// ---- block variant (nrhs > 1): the same unrolled chains over a block of right-hand sides ------------------------------------
+// Blocks are stored RHS-fastest (x[row * m + j], solver.cuh), so the m values of a row are one contiguous segment: a
+// group of MP = min(32, pow2(m)) lanes owns one row, lane j its right-hand side j (+ MP, + 2 MP ... when m > 32), and every
+// load of a group is one coalesced segment (256 bytes for m = 32).  The matrix is not streamed at all - pattern id per
+// row, coefficients from the constant bank (groups of a warp that all carry the dominant pattern) or from the dense
+// table - where csr_stream_mrhs_kernel reads 12 bytes per non-zero.  Products run in stored order per (row, j):
+// bit-identical to the CSR kernel and to the oracle's column-by-column SpMatMul.
+template <typename TV, int SHAPE, int MODE, bool DPAT, int NT>
+__global__ void __launch_bounds__(NT)
+box_mrhs_kernel(const __grid_constant__ BoxPlan P, const __grid_constant__ BoxCoef<TV> C0, int m, int mp,
+                const uint16_t* __restrict__ pid, const TV* __restrict__ ctab_g, const TV* __restrict__ dtab_g,
+                const int* __restrict__ pat_off, const PatEntry<TV>* __restrict__ ent, const TV* __restrict__ x,
+                const TV* __restrict__ b, const TV* __restrict__ d, TV* __restrict__ y) {
+    constexpr int NK = SHAPE == 27 ? 27 : 7;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TV* ctab = reinterpret_cast<TV*>(smem_raw);
+    TV* dtab = ctab + (size_t)NK * P.NP;
+    const int t = threadIdx.x;
+    for (int i = t; i < NK * P.NP; i += NT) ctab[i] = ctab_g[i];
+    for (int i = t; i < P.NP; i += NT) dtab[i] = (MODE == 3 && DPAT) ? dtab_g[i] : VT<TV>::zero();
+    __syncthreads();
+    const int rpb = NT / mp;                       // rows per CTA pass
+    const int rloc = t / mp, j0 = t - rloc * mp;
+    const long long S = P.S, S2 = P.S2;
+    for (int base = blockIdx.x * rpb; base < P.n_rows; base += gridDim.x * rpb) {       // warp-uniform trip count
+        const int row = base + rloc;
+        const bool act = row < P.n_rows;
+        const int pat = act ? (int)__ldg(reinterpret_cast<const unsigned short*>(pid) + row) : P.p0;
+        const bool safe = row - S2 - S - 1 >= P.xlo && row + S2 + S + 1 < P.xhi;
+        const bool fast = __all_sync(0xffffffffu, !act || (pat == P.p0 && safe));
+        if (!act) continue;
+        const TV dval = (MODE == 3) ? (DPAT ? dtab[pat] : d[row]) : VT<TV>::zero();
+        for (int j = j0; j < m; j += mp) {
+            const TV* xr = x + (long long)row * m + j;
+            TV acc = VT<TV>::zero();
+            if (safe) {
+#pragma unroll
+                for (int dz = -1; dz <= 1; ++dz)
+#pragma unroll
+                    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            if (!box_has<SHAPE>(dz, dy, dx)) continue;
+                            const int k = box_k<SHAPE>(dz, dy, dx);
+                            const TV cf = fast ? C0.c[k] : ctab[k * P.NP + pat];
+                            acc = acc + cf * ldg_(xr + (dz * S2 + dy * S + dx) * m);
+                        }
+            } else {                                // rows next to the ends of the vector: only the entries the row has
+                const int k0 = __ldg(pat_off + pat), k1 = __ldg(pat_off + pat + 1);
+                for (int k = k0; k < k1; ++k) {
+                    const PatEntry<TV> e = ldg_ent(ent + k);
+                    acc = acc + e.v * ldg_(xr + (long long)e.delta * m);
+                }
+            }
+            TV bval = VT<TV>::zero(), xval = VT<TV>::zero();
+            if (MODE == 2 || MODE == 3) bval = b[(long long)row * m + j];
+            if (MODE == 3) xval = *xr;
+            y[(long long)row * m + j] = pat_epilogue<MODE, TV>(acc, xval, bval, dval);
+        }
+    }
+}
+
 // ---- host side: dense tables ---------------------------------------------------------------------------------------
 template <typename TV>
 struct BoxDict {

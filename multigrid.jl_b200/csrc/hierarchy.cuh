@@ -50,12 +50,16 @@ static PaddedRegistry& padded_registry() {
 // kernels may round their ranges outwards to that granularity.
 template <typename T>
 constexpr int tma_align() { return sizeof(T) >= 8 ? 2 : 4; }
+// The pad in front of the owned rows (the lower ghost rows of a row-partitioned level) is rounded up to 16 elements, so
+// that the owned rows start on a 128-byte boundary like the vectors of a single-GPU run: with a pad that was only
+// 16-byte aligned the rank with lower ghosts ran its level-1 sweeps at 150 us against 96 us on the rank without
+// (profiles/r02l_bench_n2.log: every 256-byte row segment of a warp straddled three 128-byte lines instead of two).
 template <typename T>
-static inline size_t align_pad(size_t pad) { return (pad + tma_align<T>() - 1) & ~(size_t)(tma_align<T>() - 1); }
+static inline size_t align_pad(size_t pad) { return (pad + 15) & ~(size_t)15; }
 template <typename T>
 static T* vec_alloc(size_t total, size_t pad, cudaStream_t stream) {
-    T* b = dev_alloc<T>(total + 4);
-    MGB_CUDA(cudaMemsetAsync(b, 0, (total + 4) * sizeof(T), stream));
+    T* b = dev_alloc<T>(total + 4 + 16);
+    MGB_CUDA(cudaMemsetAsync(b, 0, (total + 4 + 16) * sizeof(T), stream));
     pad = align_pad<T>(pad);
     if (pad == 0) return b;
     PaddedRegistry& r = padded_registry();
@@ -142,6 +146,7 @@ struct Context {
     int box_min_rows = 100000;
     int overlap_box = 1;           // row-partitioned levels: the box kernel runs beside the halo exchange of its input
                                    // vector and waits for the ghost rows inside the kernel (MGB200_OVERLAP_BOX)
+    int mrhs_dpat = 0;             // the block kernels take d as a vector (the cycle passes dpat only for one RHS)
     int fuse_first_sweeps = 1;     // first two sweeps from x = 0 in one pass of the box kernel (MGB200_FUSE_FIRST)
     int split_test = 0;            // > 0: every dictionary pass runs as interior + both ends (test hook)
     int use_overlap = 0;           // multi-GPU: halo exchange beside the interior rows (MGB200_OVERLAP=1; measured

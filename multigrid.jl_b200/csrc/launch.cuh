@@ -249,6 +249,40 @@ static bool launch_box_direct(Context& ctx, const Csr<TV>& M, int mode, const TV
     MGB_LAUNCH_CHECK();
     return true;
 }
+// block variant of the box-stencil kernel (box_mrhs_kernel): nrhs > 1, blocks stored RHS-fastest
+template <typename TA, typename TV>
+static bool launch_box_mrhs(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d, const TV* dpat,
+                            TV* y, int m) {
+    if constexpr (std::is_same<TA, TV>::value && (std::is_same<TV, double>::value || std::is_same<TV, cplx>::value)) {
+        const BoxDict<TV>& X = M.box;
+        const PatDict<TV>& D = M.pat;
+        if (!X.ok || !ctx.use_box || !ctx.use_patterns || mode == MODE_ADD || x == y || m < 2) return false;
+        if ((long long)M.n_rows + 2LL * D.S2 + 2048 >= (1LL << 31)) return false;
+        constexpr int NT = 256;
+        BoxPlan P;
+        box_make_plan<TV>(P, X.shape, 1, NT, M.n_rows, D.S, D.S2, D.xlo, D.xhi, X.npat, X.p0);
+        P.NP = X.NP;
+        int mp = 1;
+        while (mp < m && mp < 32) mp *= 2;
+        const size_t smem = ((size_t)X.shape * P.NP + P.NP) * sizeof(TV);
+        const int rpb = NT / mp;
+        const int grid = (int)std::min<long long>(((long long)M.n_rows + rpb - 1) / rpb, (long long)ctx.sm_count * 32);
+#define MGB_BM(SHAPE, MODE, DP) \
+    box_mrhs_kernel<TV, SHAPE, MODE, DP, NT><<<grid, NT, smem, ctx.stream>>>(P, X.c0, m, mp, D.pid, X.ctab, X.dtab, D.pat_off, D.ent, x, b, d, y)
+#define MGB_BMS(MODE, DP) { if (X.shape == 7) MGB_BM(7, MODE, DP); else MGB_BM(27, MODE, DP); }
+        if (mode == MODE_SPMV) MGB_BMS(MODE_SPMV, false)
+        else if (mode == MODE_RESID) MGB_BMS(MODE_RESID, false)
+        else if (dpat) MGB_BMS(MODE_SWEEP, true)
+        else MGB_BMS(MODE_SWEEP, false)
+#undef MGB_BMS
+#undef MGB_BM
+        MGB_LAUNCH_CHECK();
+        return true;
+    } else {
+        return false;
+    }
+}
+
 template <typename TA, typename TV>
 static bool launch_box(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d, const TV* dpat,
                        TV* y, const PutPlan& pp, bool prepare_only = false, const BoxWait& bw = no_wait()) {
@@ -321,7 +355,15 @@ static void launch_pattern_rows(Context& ctx, const Csr<TA>& M, int mode, const 
 template <typename TA, typename TV>
 static void launch_pattern_mode(Context& ctx, const Csr<TA>& M, int mode, const TV* x, const TV* b, const TV* d,
                                 const TV* dpat, TV* y, const PutPlan& pp = no_put()) {
-    if (launch_box<TA, TV>(ctx, M, mode, x, b, d, dpat, y, pp)) return;
+    static const bool dbg = env_int("MGB200_DEBUG_KERNELS", 0) != 0;
+    if (launch_box<TA, TV>(ctx, M, mode, x, b, d, dpat, y, pp)) {
+        if (dbg) std::fprintf(stderr, "[mgb200 dev %d] rows %d mode %d: box kernel (shape %d)\n", ctx.device, M.n_rows, mode, M.box.shape);
+        return;
+    }
+    if (dbg)
+        std::fprintf(stderr, "[mgb200 dev %d] rows %d mode %d: dictionary walk (box ok %d, S %d, S2 %d, npat %d, rows %% S2 = %d, x align %d)\n",
+                     ctx.device, M.n_rows, mode, (int)M.box.ok, M.pat.S, M.pat.S2, M.pat.npat,
+                     M.pat.S2 > 0 ? (int)(M.n_rows % M.pat.S2) : -1, (int)(reinterpret_cast<uintptr_t>(x) & 127));
     if (M.pat.rowrel && launch_pattern_tma<TA, TV>(ctx, M, mode, x, b, d, dpat, y, 0, -1, 0, pp)) return;
     launch_pattern_rows<TA, TV>(ctx, M, mode, x, b, d, dpat, y, 0, M.n_rows, 0, 0, pp);
 }
@@ -372,7 +414,9 @@ static void csr_apply(Context& ctx, const Csr<TA>& M, int mode, const TV* x, con
     } else if (!M.staged) {
         launch_rowwarp_mode<TA, TV>(ctx, M, mode, x, b, d, y, m);
     } else if (m > 1) {
-        launch_mrhs_mode<TA, TV>(ctx, M, mode, x, b, d, y, m);
+        // blocks of right-hand sides: the box-stencil kernel when the matrix has that structure, else the CSR stream
+        if (!launch_box_mrhs<TA, TV>(ctx, M, mode, x, b, d, ctx.mrhs_dpat ? dpat : nullptr, y, m))
+            launch_mrhs_mode<TA, TV>(ctx, M, mode, x, b, d, y, m);
     } else {
         switch (M.tpr) {
             case 1: launch_stream_mode<TA, TV, 1>(ctx, M, mode, x, b, d, y); break;

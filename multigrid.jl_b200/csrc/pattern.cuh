@@ -279,7 +279,24 @@ static BoxInfo detect_box(const HostPatterns<TA>& H, long long n_rows) {
         if (valid(0, 0)) finish(0, 0);
         return B;
     }
+    // Several (S, S2) can decompose a sparse offset set (a 7-point stencil on planes of 257 x 257 also reads as lines
+    // of 256 with offsets (dy,dx) = (1,1) and (dz,dy,dx) = (1,1,1), and a z-slab of 256 such planes even tiles that
+    // way).  Take the simplest reading - the smallest sum of |dz| + |dy| + |dx| over the offsets - and among equals the
+    // one that tiles the matrix.
     int best_S = -1, best_S2 = -1, best_score = -1;
+    long long best_cost = -1;
+    auto cost_of = [&](int S, int S2) {
+        std::vector<int> ds(H.delta);
+        std::sort(ds.begin(), ds.end());
+        ds.erase(std::unique(ds.begin(), ds.end()), ds.end());
+        long long c = 0;
+        for (int d : ds) {
+            int dx, dy, dz;
+            box_decompose(d, S, S2, dx, dy, dz);
+            c += std::abs(dx) + std::abs(dy) + std::abs(dz);
+        }
+        return c;
+    };
     for (int a = -1; a <= 1; ++a) {
         const long long S = big[0] + a;
         if (S < 3 || S > 0x3fffffff) continue;
@@ -298,10 +315,16 @@ static BoxInfo detect_box(const HostPatterns<TA>& H, long long n_rows) {
             int score = 0;
             if (S2 > 0 && S2 % S == 0) score += 2;
             if (n_rows % (S2 > 0 ? S2 : S) == 0) score += 1;
-            if (score > best_score) { best_score = score; best_S = (int)S; best_S2 = (int)S2; }
+            const long long cost = cost_of((int)S, (int)S2);
+            if (best_cost < 0 || cost < best_cost || (cost == best_cost && score > best_score)) {
+                best_cost = cost;
+                best_score = score;
+                best_S = (int)S;
+                best_S2 = (int)S2;
+            }
         }
     }
-    if (best_score >= 0) finish(best_S, best_S2);
+    if (best_cost >= 0) finish(best_S, best_S2);
     return B;
 }
 

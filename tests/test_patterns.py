@@ -423,3 +423,21 @@ def test_box_kernel_code_fuzz(seed):
                 assert dim == 2 or device.host_detect_box(mat) is None or device.host_detect_box(mat)["S2"] < 3 * device.host_detect_box(mat)["S"]
                 continue
             assert np.array_equal(r0[0].view(np.int64), got[0].view(np.int64)), (n, keep, RZ, NB, mode)
+
+
+def test_box_structure_of_a_z_slab_is_read_the_simple_way():
+    """A z-slab of 16 planes of 17 x 17 nodes (rank 0 of a row-partitioned level) tiles as lines of 16 as well:
+    offsets +-17 = (dy,dx) = (1,1), +-289 = (dz,dy,dx) = (1,1,1) with S2 = 272, and 16 * 289 = 17 * 272 rows.  The
+    detection must still read the 7-point stencil as a star (S = 17, S2 = 289): the other reading runs the 27-point
+    kernel on it (found on the B200: 150 us against 97 us per level-1 sweep on rank 0, profiles/r02o_*)."""
+    from multigrid_jl_b200 import device
+    import multigrid_jl_b200 as mg
+    n, dom = [16, 16, 32], [0, 1, 0, 1, 0, 2]
+    A = mg.poisson_shifted(mg.getRegularMesh(dom, n), 1e-4).tocsr()
+    plane = 17 * 17
+    rows = A[:16 * plane, :].tocoo()
+    loc = sp.csr_matrix((rows.data, (rows.row, rows.col)), shape=(16 * plane, 17 * plane))     # owned rows | ghost plane above
+    box = device.host_detect_box(sp.csc_matrix(loc.T))
+    assert box is not None and (box["S"], box["S2"]) == (17, 289)
+    star = (1 << 4) | (1 << 10) | (1 << 12) | (1 << 13) | (1 << 14) | (1 << 16) | (1 << 22)
+    assert all((int(m) & ~star) == 0 for m in box["masks"])
