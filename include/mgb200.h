@@ -84,6 +84,23 @@ int mgb200_upload_coarsest(mgb200_handle h, int64_t n, const int64_t* colptr, co
 int mgb200_upload_coarsest_gmres(mgb200_handle h, int64_t n, const int64_t* colptr, const int64_t* rowval,
                                  const void* nzval, const void* d, int index_base);
 
+/* replaceMatrixInHierarchy (MGsetup.jl:226-270) on the device: the fine matrix changes, Ps / Rs stay.  The new
+ * As[1] = A^H comes in CSC like in mgb200_upload_level; per level the relaxation weights (getRelaxPrec, MGsetup.jl:142-160:
+ * relax_type 0 = "Jac" / "Jac-GMRES", 1 = "SPAI"; relax_param[l] = relaxParam of level l + 1, `levels` entries, NULL = 1.0),
+ * the Galerkin product Ps[l]*AT*Rs[l] (numeric only: into the sparsity the first setup produced, csrc/galerkin.cuh) and
+ * the coarsest factorisation (defineCoarsestAinv) are redone on the device.  *done = 1: the hierarchy now belongs to
+ * the new matrix.  *done = 0: the device path does not apply (the new matrix has another sparsity than the resident
+ * one, the hierarchy is row-partitioned, or SPAI on a structurally unsymmetric operator) - nothing was changed and the
+ * caller redoes the setup on the host and uploads again. */
+int mgb200_replace_matrix(mgb200_handle h, int64_t n, const int64_t* colptr, const int64_t* rowval, const void* nzval,
+                          int index_base, int relax_type, const double* relax_param, int* done);
+
+/* Values of a resident matrix back to the host, in the caller's convention (nzval of the stored CSC array of level
+ * `level`: which = 0 As[level], 1 Ps[level], 2 Rs[level]; nnz must match) - after mgb200_replace_matrix this is how
+ * param.As[2:end] are refreshed on the host when somebody needs them - and relaxPrecs[level]. */
+int mgb200_download_values(mgb200_handle h, int level, int which, void* nzval, int64_t nnz);
+int mgb200_download_relax_prec(mgb200_handle h, int level, void* d);
+
 /* Mixed precision (getMultigridPreconditioner with VAL != eltype(B), SolveFuncs.jl:52-60): a double-precision handle
  * that holds no hierarchy of its own, only the Krylov matrix (mgb200_set_krylov_matrix, mandatory) and the Krylov
  * vectors; its preconditioner is one cycle of the single-precision hierarchy `inner` (MGB200_FP32 -> an MGB200_FP64

@@ -598,6 +598,131 @@ box_mrhs_kernel(const __grid_constant__ BoxPlan P, const __grid_constant__ BoxCo
     }
 }
 
+// ---- block variant, marching form ------------------------------------------------------------------------------------------
+// box_mrhs_kernel above reads every neighbour of a row from global memory, and the CTAs that run together are spread over
+// a whole plane of the grid: nothing is reused in L1, each block row of x is read 7 (27) times from L2, and the kernel
+// runs at the L2's pace (cfg4, profiles/r02o_cfg4.json: level-1 sweep 612 us for 1.65 GB of vectors, 8 TB/s through
+// L2).  Here a CTA owns a tile of TX x TY grid columns and marches through a range of planes (2.5-D blocking): a node's
+// m values (256 bytes for m = 32) enter shared memory once per CTA - four rotating plane buffers of (TX + 2) x (TY + 2)
+// nodes - and all 7 / 27 neighbours are read from there; one warp = one node at a time, lane j = right-hand side j,
+// every shared-memory access a conflict-free 256-byte row, one barrier per plane, and the global loads of plane k + 2
+// fly while plane k is computed.  Nodes outside the grid are zeros in the buffers (their coefficients are zero in the
+// dense table, box_kernel's argument).  Products run in stored (dz, dy, dx) order per (row, j): bit-identical to
+// box_mrhs_kernel, the CSR block kernel and the oracle's column-by-column SpMatMul.
+constexpr int MARCH_TX = 8, MARCH_TY = 8, MARCH_NW = 16;       // tile columns, warps per CTA
+constexpr int MARCH_HX = MARCH_TX + 2, MARCH_HY = MARCH_TY + 2, MARCH_NODES = MARCH_HX * MARCH_HY;
+constexpr int MARCH_HALO = MARCH_NODES - MARCH_TX * MARCH_TY;   // 36 nodes around the tile
+template <typename TV>
+static inline size_t march_smem_bytes(int shape, int NP) {
+    return ((size_t)shape * NP + NP) * sizeof(TV) + 4 * (size_t)MARCH_NODES * 32 * sizeof(TV);
+}
+template <typename TV, int SHAPE, int MODE, bool DPAT>
+__global__ void __launch_bounds__(MARCH_NW * 32, 2)
+box_mrhs_march_kernel(const __grid_constant__ BoxCoef<TV> C0, int NP, int p0, int m, int n0, int n1, int nz, int zchunk,
+                      const uint16_t* __restrict__ pid, const TV* __restrict__ ctab_g, const TV* __restrict__ dtab_g,
+                      const TV* __restrict__ x, const TV* __restrict__ b, const TV* __restrict__ d, TV* __restrict__ y) {
+    constexpr int NK = SHAPE == 27 ? 27 : 7;
+    constexpr int TX = MARCH_TX, TY = MARCH_TY, HX = MARCH_HX, NODES = MARCH_NODES, NW = MARCH_NW;
+    constexpr int CPW = TX * TY / NW;                 // columns per warp (consecutive in x)
+    constexpr int HPW = (MARCH_HALO + NW - 1) / NW;   // halo nodes per warp
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TV* ctab = reinterpret_cast<TV*>(smem_raw);
+    TV* dtab = ctab + (size_t)NK * NP;
+    TV* buf = dtab + NP;                              // [4][NODES][32]
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    for (int i = t; i < NK * NP; i += NW * 32) ctab[i] = ctab_g[i];
+    for (int i = t; i < NP; i += NW * 32) dtab[i] = (MODE == 3 && DPAT) ? dtab_g[i] : VT<TV>::zero();
+    const int tiles_x = (n0 + TX - 1) / TX;
+    const int tx0 = ((int)blockIdx.x % tiles_x) * TX, ty0 = ((int)blockIdx.x / tiles_x) * TY;
+    const int kz0 = (int)blockIdx.y * zchunk, kz1 = min(nz, kz0 + zchunk);
+    const int j = (int)blockIdx.z * 32 + lane;
+    const bool jl = j < m;
+    const long long S2 = (long long)n0 * n1;
+    // the nodes this warp moves into the plane buffers: CPW tile columns and up to HPW halo nodes
+    int node[CPW + HPW];          // index in a plane buffer, -1: none
+    int col[CPW + HPW];           // gy * S + gx, -1: outside the grid
+#pragma unroll
+    for (int q = 0; q < CPW; ++q) {
+        const int c = w * CPW + q, lx = c % TX, ly = c / TX, gx = tx0 + lx, gy = ty0 + ly;
+        node[q] = (ly + 1) * HX + (lx + 1);
+        col[q] = (gx < n0 && gy < n1) ? gy * n0 + gx : -1;
+    }
+#pragma unroll
+    for (int q = 0; q < HPW; ++q) {
+        const int h = w + q * NW;
+        int hx, hy;
+        if (h < HX) { hy = -1; hx = h - 1; }
+        else if (h < 2 * HX) { hy = TY; hx = h - HX - 1; }
+        else if (h < 2 * HX + TY) { hx = -1; hy = h - 2 * HX; }
+        else { hx = TX; hy = h - 2 * HX - TY; }
+        const int gx = tx0 + hx, gy = ty0 + hy;
+        node[CPW + q] = h < MARCH_HALO ? (hy + 1) * HX + (hx + 1) : -1;
+        col[CPW + q] = (h < MARCH_HALO && gx >= 0 && gx < n0 && gy >= 0 && gy < n1) ? gy * n0 + gx : -1;
+    }
+    TV nx[CPW + HPW];
+    auto load_plane = [&](int kk) {
+#pragma unroll
+        for (int q = 0; q < CPW + HPW; ++q) {
+            nx[q] = VT<TV>::zero();
+            if (kk >= 0 && kk < nz && col[q] >= 0 && jl) nx[q] = ldg_(x + ((kk * S2 + col[q]) * m + j));
+        }
+    };
+    auto store_plane = [&](int kk) {
+        TV* pb = buf + (size_t)(kk & 3) * NODES * 32;
+#pragma unroll
+        for (int q = 0; q < CPW + HPW; ++q)
+            if (node[q] >= 0) pb[node[q] * 32 + lane] = nx[q];
+    };
+    load_plane(kz0 - 1);
+    store_plane(kz0 - 1);
+    load_plane(kz0);
+    store_plane(kz0);
+    load_plane(kz0 + 1);
+    for (int k = kz0; k < kz1; ++k) {
+        store_plane(k + 1);
+        __syncthreads();
+        load_plane(k + 2);                       // in flight while plane k is computed
+        const TV* pz[3] = {buf + (size_t)((k - 1) & 3) * NODES * 32 + lane, buf + (size_t)(k & 3) * NODES * 32 + lane,
+                           buf + (size_t)((k + 1) & 3) * NODES * 32 + lane};
+        TV bv[CPW];
+        int pat[CPW];
+#pragma unroll
+        for (int q = 0; q < CPW; ++q) {
+            bv[q] = VT<TV>::zero();
+            pat[q] = p0;
+            if (col[q] >= 0) {
+                const long long row = k * S2 + col[q];
+                pat[q] = (int)__ldg(reinterpret_cast<const unsigned short*>(pid) + row);
+                if ((MODE == 2 || MODE == 3) && jl) bv[q] = b[row * m + j];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < CPW; ++q) {
+            if (col[q] < 0) continue;              // warp-uniform
+            const long long row = k * S2 + col[q];
+            const bool fast = pat[q] == p0;        // warp-uniform
+            TV acc = VT<TV>::zero();
+#pragma unroll
+            for (int dz = -1; dz <= 1; ++dz)
+#pragma unroll
+                for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        if (!box_has<SHAPE>(dz, dy, dx)) continue;
+                        const int kk = box_k<SHAPE>(dz, dy, dx);
+                        const TV cf = fast ? C0.c[kk] : ctab[kk * NP + pat[q]];
+                        acc = acc + cf * pz[dz + 1][(node[q] + dy * HX + dx) * 32];
+                    }
+            TV dval = VT<TV>::zero(), xval = VT<TV>::zero();
+            if (MODE == 3) {
+                dval = DPAT ? (fast ? C0.d0 : dtab[pat[q]]) : d[row];
+                xval = pz[1][node[q] * 32];
+            }
+            if (jl) y[row * m + j] = pat_epilogue<MODE, TV>(acc, xval, bv[q], dval);
+        }
+    }
+}
+
 // ---- host side: dense tables ---------------------------------------------------------------------------------------
 template <typename TV>
 struct BoxDict {
@@ -608,6 +733,7 @@ struct BoxDict {
     TV* ctab = nullptr;            // device: coef[k * NP + p]
     TV* dtab = nullptr;            // device: folded relaxation weights per pattern (set by fold_d), NP elements
     std::vector<TV> h_ctab;        // host copies (the CPU replay, tests)
+    std::vector<int> h_mask, h_pat_off;   // presence bits and entry offsets of the patterns (refill)
     // tile records of the variant in use (box_plan_tile), planned at the first launch and whenever the variant or the
     // copyable range of the input vectors changes
     unsigned char* recs = nullptr;
@@ -621,6 +747,25 @@ struct BoxDict {
         rec_RZ = rec_NB = 0;
         ok = false;
         h_ctab.clear();
+        h_mask.clear();
+        h_pat_off.clear();
+    }
+    // the same tables from new dictionary values (replace_matrix: the patterns kept their shape, galerkin.cuh)
+    bool refill(const std::vector<TV>& val) {
+        if (!ok || h_mask.empty() || (int)h_pat_off.size() != npat + 1) return false;
+        std::fill(h_ctab.begin(), h_ctab.end(), VT<TV>::zero());
+        for (int p = 0; p < npat; ++p) {
+            int e = h_pat_off[p];
+            for (int bit = 0; bit < 27; ++bit) {
+                if (!(h_mask[p] & (1 << bit))) continue;
+                const int dz = bit / 9 - 1, dy = (bit / 3) % 3 - 1, dx = bit % 3 - 1;
+                const int k = shape == 27 ? box_k<27>(dz, dy, dx) : box_k<7>(dz, dy, dx);
+                h_ctab[(size_t)k * NP + p] = val[e++];
+            }
+            if (e != h_pat_off[p + 1]) return false;
+        }
+        for (int k = 0; k < shape; ++k) c0.c[k] = h_ctab[(size_t)k * NP + p0];
+        return true;
     }
     bool has_records(const BoxPlan& P, int RZ, int NB) const {
         return recs && rec_RZ == RZ && rec_NB == NB && rec_xlo == P.xlo && rec_xhi == P.xhi;

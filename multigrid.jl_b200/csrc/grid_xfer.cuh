@@ -242,7 +242,113 @@ __global__ void __launch_bounds__(1024) gxp_kernel(const __grid_constant__ GridX
         }
     }
 }
-// persistent CTAs over the coarse lines (J, K); threads over I
+// ---- prolongation, quad form (the default) ----------------------------------------------------------------------------------
+// The line form above is latency-bound (profiles/r02q_ncu_gxp_summary.txt: 144 us at 257^3, DRAM 20 %, ~143 warp
+// instructions per 32 rows, one x_f load in flight per thread, the coarse loads behind parity branches).  Here a thread
+// owns fine column i of the (up to) FOUR fine lines (2J + b, 2K + c) of one coarse cell row (J, K): the 4 ... 8 coarse
+// values those lines interpolate from and the four x_f values are loaded first, unconditionally (line and plane
+// existence is uniform over the thread's y-row; only the `a` parity is per lane), and the index arithmetic is paid
+// once per four rows.  Each row is still the sum of its products in stored order (dz', dy', dx') starting from zero and
+// added to x_f last - gxp_row above - so the result does not change by a bit.  blockDim.y cell rows per CTA pass keep
+// narrow (coarse) levels from running one-warp CTAs.
+template <typename TA, typename TV>
+__device__ __forceinline__ TV gxp_quad_row(const TA* tab, const TV (&v)[2][2][2], int a, int b, int c, TV xf) {
+    // compact table of class a + 2b + 4c: entry ((dz (b + 1) + dy) << a) + dx
+    const TA* tv = tab + (a + 2 * b + 4 * c) * 8;
+    TV acc = VT<TV>::zero();
+#pragma unroll
+    for (int dz = 0; dz < 2; ++dz) {
+        if (dz > c) break;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+            if (dy > b) break;
+            const int e = (dz * (b + 1) + dy) << a;
+            acc = acc + tv[e] * v[dz][dy][0];
+            if (a) acc = acc + tv[e + 1] * v[dz][dy][1];
+        }
+    }
+    return xf + acc;
+}
+template <typename TA, typename TV, int MINB>
+__global__ void __launch_bounds__(512, MINB) gxp_quad_kernel(const __grid_constant__ GridXfer X, const __grid_constant__ PutPlan pp,
+                                                        const TA* __restrict__ tabg, const TV* __restrict__ xc,
+                                                        TV* __restrict__ xf) {
+    __shared__ TA tab[GXP_TAB];
+    for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < GXP_TAB; i += blockDim.x * blockDim.y) tab[i] = tabg[i];
+    __syncthreads();
+    const int n0 = X.n[0], n1 = X.n[1], N0 = X.N[0], N1 = X.N[1];
+    const long long cs2 = (long long)N0 * N1, fs2 = (long long)n0 * n1;
+    const int k_end = X.k0 + X.nk;                         // the rows of this matrix: fine planes k0 .. k_end - 1
+    const int K_first = X.k0 >> 1, nK = ((k_end - 1) >> 1) - K_first + 1;
+    const int ngroups = N1 * nK;
+    for (int g = blockIdx.x * blockDim.y + threadIdx.y; g < ngroups; g += gridDim.x * blockDim.y) {
+        const int Kl = g / N1, J = g - Kl * N1, K = K_first + Kl;
+        const int j0 = 2 * J, kk = 2 * K;
+        const bool eb = j0 + 1 < n1;                                     // the lines with b = 1 exist
+        const bool e0 = kk >= X.k0, e1 = kk + 1 < k_end;                 // the planes with c = 0 / c = 1 are rows of this matrix
+        const TV* q00 = xc + (((long long)K * N1 + J) * N0 - X.shift);
+        const TV* q10 = q00 + N0;
+        const TV* q01 = q00 + cs2;
+        const TV* q11 = q01 + N0;
+        const long long r00 = ((long long)(kk - X.k0) * n1 + j0) * n0;   // first row of line (b, c) = (0, 0); negative if !e0
+        for (int i = threadIdx.x; i < n0; i += blockDim.x) {
+            const int a = i & 1, I = i >> 1;
+            TV v[2][2][2];
+#pragma unroll
+            for (int z = 0; z < 8; ++z) v[z >> 2][(z >> 1) & 1][z & 1] = VT<TV>::zero();
+            TV f00 = VT<TV>::zero(), f10 = f00, f01 = f00, f11 = f00;
+            // all loads first
+            v[0][0][0] = ldg_(q00 + I);
+            if (a) v[0][0][1] = ldg_(q00 + I + 1);
+            if (eb) {
+                v[0][1][0] = ldg_(q10 + I);
+                if (a) v[0][1][1] = ldg_(q10 + I + 1);
+            }
+            if (e1) {
+                v[1][0][0] = ldg_(q01 + I);
+                if (a) v[1][0][1] = ldg_(q01 + I + 1);
+                if (eb) {
+                    v[1][1][0] = ldg_(q11 + I);
+                    if (a) v[1][1][1] = ldg_(q11 + I + 1);
+                }
+            }
+            const long long r = r00 + i;
+            if (e0) {
+                f00 = xf[r];
+                if (eb) f10 = xf[r + n0];
+            }
+            if (e1) {
+                f01 = xf[r + fs2];
+                if (eb) f11 = xf[r + fs2 + n0];
+            }
+            if (e0) {
+                const TV o = gxp_quad_row<TA, TV>(tab, v, a, 0, 0, f00);
+                xf[r] = o;
+                if (pp.on) ll_put_edge<TV>(pp, r, o);
+                if (eb) {
+                    const TV o1 = gxp_quad_row<TA, TV>(tab, v, a, 1, 0, f10);
+                    xf[r + n0] = o1;
+                    if (pp.on) ll_put_edge<TV>(pp, r + n0, o1);
+                }
+            }
+            if (e1) {
+                const TV o = gxp_quad_row<TA, TV>(tab, v, a, 0, 1, f01);
+                xf[r + fs2] = o;
+                if (pp.on) ll_put_edge<TV>(pp, r + fs2, o);
+                if (eb) {
+                    const TV o1 = gxp_quad_row<TA, TV>(tab, v, a, 1, 1, f11);
+                    xf[r + fs2 + n0] = o1;
+                    if (pp.on) ll_put_edge<TV>(pp, r + fs2 + n0, o1);
+                }
+            }
+        }
+    }
+}
+
+// persistent CTAs over the coarse lines (J, K); threads over I.
+// (Measured and rejected, profiles/r02r_*: 16-byte loads of the aligned (even, odd) fine pair with all 18 loads of a row
+// issued up front need 80 registers; at 160-thread CTAs that left 11 warps per SM and the kernel ran at 107 us against
+// 55 us for this form at 257^3.)
 template <typename TA, typename TV>
 __global__ void __launch_bounds__(1024) gxr_kernel(const __grid_constant__ GridXfer X, const TA* __restrict__ tabg,
                                                    const TV* __restrict__ rf, TV* __restrict__ rc) {

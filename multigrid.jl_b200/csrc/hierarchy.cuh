@@ -14,6 +14,7 @@
 #include "pattern.cuh"
 #include "box.cuh"
 #include "grid_xfer.cuh"
+#include "galerkin.cuh"
 #include "vec_kernels.cuh"
 
 namespace mgb200 {
@@ -138,6 +139,8 @@ struct Context {
     int use_graphs = 1;            // 0: never replay cycles from CUDA graphs
     int use_tma = 1;               // 0: never use the TMA-staged dictionary kernel (MGB200_TMA)
     int grid_transfers = 1;        // > 0: grid-hinted transfer kernels (grid_xfer.cuh) where a hint was given and verified
+    int gxp_quad = 1;              // prolongation: quad form (four fine lines per thread; 1 / 2 / 3: register budget 64 / 40 / 32)
+                                   // instead of the line form (MGB200_GXP_QUAD)
     int tma_min_rows = 200000;     // smaller matrices keep the one-pass kernel (too few tiles per SM)
     int use_box = 1;               // box-stencil kernel (box.cuh) for box-structured square operators (MGB200_BOX)
     int box_variant = 1;           // (rows per thread, base rows per tile, stages): see launch_box (MGB200_BOX_VARIANT)
@@ -146,6 +149,7 @@ struct Context {
     int box_min_rows = 100000;
     int overlap_box = 1;           // row-partitioned levels: the box kernel runs beside the halo exchange of its input
                                    // vector and waits for the ghost rows inside the kernel (MGB200_OVERLAP_BOX)
+    int mrhs_march = 1;            // block variant of the box kernel: marching (2.5-D) form (MGB200_MRHS_MARCH)
     int mrhs_dpat = 0;             // the block kernels take d as a vector (the cycle passes dpat only for one RHS)
     int fuse_first_sweeps = 1;     // first two sweeps from x = 0 in one pass of the box kernel (MGB200_FUSE_FIRST)
     int split_test = 0;            // > 0: every dictionary pass runs as interior + both ends (test hook)
@@ -186,6 +190,8 @@ struct Context {
         fuse_first_sweeps = env_int("MGB200_FUSE_FIRST", 1);
         overlap_box = env_int("MGB200_OVERLAP_BOX", 1);
         grid_transfers = env_int("MGB200_GRID_TRANSFERS", 1);
+        gxp_quad = env_int("MGB200_GXP_QUAD", 1);
+        mrhs_march = env_int("MGB200_MRHS_MARCH", 1);
         use_overlap = env_int("MGB200_OVERLAP", 0);
         split_test = env_int("MGB200_SPLIT_TEST", 0);
         int prio_lo = 0, prio_hi = 0;
@@ -376,6 +382,8 @@ static void upload_csr(Context& ctx, Csr<TA>& M, long long n_rows, long long n_c
                 BoxDict<TA>& X = M.box;
                 if (box_build_tables<TA>(hp, B, n_rows, X.shape, X.NP, X.p0, X.h_ctab, X.c0)) {
                     X.npat = hp.npat();
+                    X.h_mask = B.mask;
+                    X.h_pat_off = hp.pat_off;
                     X.ctab = dev_alloc<TA>(X.h_ctab.size());
                     MGB_CUDA(cudaMemcpy(X.ctab, X.h_ctab.data(), X.h_ctab.size() * sizeof(TA), cudaMemcpyHostToDevice));
                     X.dtab = dev_alloc<TA>(X.NP);

@@ -165,7 +165,17 @@ static bool launch_grid_xfer(Context& ctx, const Csr<TA>& M, int mode, const TV*
     const long long nlines = X.kind == 1 ? (long long)X.n[1] * X.nk : (long long)X.N[1] * X.nk;
     const int nt = std::min(1024, (width + 31) / 32 * 32);
     const int grid = (int)std::min<long long>(nlines, (long long)ctx.sm_count * std::max(1, 2048 / nt) * 4);
-    if (X.kind == 1) gxp_kernel<TA, TV><<<grid, nt, 0, ctx.stream>>>(X, pp, static_cast<const TA*>(X.tab), x, y);
+    if (X.kind == 1 && ctx.gxp_quad) {
+        // quad form: coarse cell rows (J, K) of the planes this matrix touches; ny cell rows per CTA pass
+        const int ntx = std::min(512, (width + 31) / 32 * 32), ny = std::max(1, 256 / ntx);
+        const long long nK = ((X.k0 + X.nk - 1) >> 1) - (X.k0 >> 1) + 1, ngroups = (long long)X.N[1] * nK;
+        const int g2 = (int)std::min<long long>((ngroups + ny - 1) / ny, (long long)ctx.sm_count * std::max(1, 2048 / (ntx * ny)) * 2);
+        const TA* tab = static_cast<const TA*>(X.tab);
+        // register budget per thread: 64 (2 CTAs of 512 threads per SM), 40 (3) or 32 (4) - option gxp_quad = 1, 2, 3
+        if (ctx.gxp_quad == 2) gxp_quad_kernel<TA, TV, 3><<<g2, dim3(ntx, ny), 0, ctx.stream>>>(X, pp, tab, x, y);
+        else if (ctx.gxp_quad == 3) gxp_quad_kernel<TA, TV, 4><<<g2, dim3(ntx, ny), 0, ctx.stream>>>(X, pp, tab, x, y);
+        else gxp_quad_kernel<TA, TV, 2><<<g2, dim3(ntx, ny), 0, ctx.stream>>>(X, pp, tab, x, y);
+    } else if (X.kind == 1) gxp_kernel<TA, TV><<<grid, nt, 0, ctx.stream>>>(X, pp, static_cast<const TA*>(X.tab), x, y);
     else gxr_kernel<TA, TV><<<grid, nt, 0, ctx.stream>>>(X, static_cast<const TA*>(X.tab), x, y);
     MGB_LAUNCH_CHECK();
     return true;
@@ -258,6 +268,33 @@ static bool launch_box_mrhs(Context& ctx, const Csr<TA>& M, int mode, const TV* 
         const PatDict<TV>& D = M.pat;
         if (!X.ok || !ctx.use_box || !ctx.use_patterns || mode == MODE_ADD || x == y || m < 2) return false;
         if ((long long)M.n_rows + 2LL * D.S2 + 2048 >= (1LL << 31)) return false;
+        // marching form (2.5-D tiles through shared memory): whole grids, Float64, at least 8 right-hand sides (a ComplexF64
+        // block needs 205 KB of plane buffers and spills at 64 registers: it keeps the direct form)
+        if (std::is_same<TV, double>::value && ctx.mrhs_march && m >= 8 && D.xlo == 0 && M.n_rows == M.n_cols && D.S >= 3 && D.S2 >= 3 * D.S && D.S2 % D.S == 0 &&
+            M.n_rows % D.S2 == 0 && march_smem_bytes<TV>(X.shape, X.NP) <= (size_t)ctx.max_smem_optin) {
+            const int n0 = D.S, n1 = D.S2 / D.S, nz = M.n_rows / D.S2;
+            const int tiles = cdiv(n0, MARCH_TX) * cdiv(n1, MARCH_TY);
+            const int want = std::max(1, cdiv(4 * ctx.sm_count, tiles));              // z-chunks for ~4 CTAs per SM
+            const int nzc = std::max(1, std::min(want, std::max(1, nz / 4)));
+            const int zchunk = cdiv(nz, nzc);
+            const size_t smem = march_smem_bytes<TV>(X.shape, X.NP);
+            const dim3 grd(tiles, cdiv(nz, zchunk), cdiv(m, 32));
+#define MGB_MM(SHAPE, MODE, DP)                                                                                               \
+    {                                                                                                                         \
+        auto kern = box_mrhs_march_kernel<TV, SHAPE, MODE, DP>;                                                               \
+        MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx.max_smem_optin));                \
+        kern<<<grd, MARCH_NW * 32, smem, ctx.stream>>>(X.c0, X.NP, X.p0, m, n0, n1, nz, zchunk, D.pid, X.ctab, X.dtab, x, b, d, y); \
+    }
+#define MGB_MMS(MODE, DP) { if (X.shape == 7) MGB_MM(7, MODE, DP) else MGB_MM(27, MODE, DP) }
+            if (mode == MODE_SPMV) MGB_MMS(MODE_SPMV, false)
+            else if (mode == MODE_RESID) MGB_MMS(MODE_RESID, false)
+            else if (dpat) MGB_MMS(MODE_SWEEP, true)
+            else MGB_MMS(MODE_SWEEP, false)
+#undef MGB_MMS
+#undef MGB_MM
+            MGB_LAUNCH_CHECK();
+            return true;
+        }
         constexpr int NT = 256;
         BoxPlan P;
         box_make_plan<TV>(P, X.shape, 1, NT, M.n_rows, D.S, D.S2, D.xlo, D.xhi, X.npat, X.p0);
@@ -308,6 +345,11 @@ static bool launch_box(Context& ctx, const Csr<TA>& M, int mode, const TV* x, co
             case 20: return launch_box_variant<TV, 2, 512, 1>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only, bw);
             case 21: return launch_box_variant<TV, 1, 512, 2>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only, bw);
             case 22: return launch_box_variant<TV, 2, 512, 2>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only, bw);
+            // long lines (S >= 512: the y-halo of a window, 2 (S + 1) elements, must not dwarf the tile): 1024 base rows
+            case 30: return launch_box_variant<TV, 1, 1024, 2>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only, bw);
+            case 31: return launch_box_variant<TV, 2, 1024, 2>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only, bw);
+            case 32: return launch_box_variant<TV, 2, 1024, 1>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only, bw);
+            case 33: return launch_box_variant<TV, 4, 1024, 1>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only, bw);
             case 9: return bw.epoch ? false : launch_box_direct<TV, 2>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only);
             default: return launch_box_variant<TV, 1, 1024 / F, 2>(ctx, M, mode, x, b, d, dpat, y, pp, prepare_only, bw);
         }

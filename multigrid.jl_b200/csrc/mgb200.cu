@@ -356,6 +356,29 @@ int mgb200_upload_coarsest(mgb200_handle h, int64_t n, const int64_t* colptr, co
     MGB_CATCH
 }
 
+int mgb200_replace_matrix(mgb200_handle h, int64_t n, const int64_t* colptr, const int64_t* rowval, const void* nzval,
+                          int index_base, int relax_type, const double* relax_param, int* done) {
+    MGB_TRY
+    MGB_CHECK(colptr && rowval && nzval && done, "null argument");
+    *done = 0;
+    MGB_BOTH(h, *done = H->replace_matrix(n, colptr, rowval, nzval, index_base, relax_type, relax_param) ? 1 : 0);
+    MGB_CATCH
+}
+
+int mgb200_download_values(mgb200_handle h, int level, int which, void* nzval, int64_t nnz) {
+    MGB_TRY
+    MGB_CHECK(nzval && which >= 0 && which <= 2, "bad argument");
+    MGB_BOTH(h, H->download_values(level, which, nzval, nnz));
+    MGB_CATCH
+}
+
+int mgb200_download_relax_prec(mgb200_handle h, int level, void* d) {
+    MGB_TRY
+    MGB_CHECK(d, "null argument");
+    MGB_BOTH(h, H->download_relax_prec(level, d));
+    MGB_CATCH
+}
+
 int mgb200_upload_coarsest_gmres(mgb200_handle h, int64_t n, const int64_t* colptr, const int64_t* rowval,
                                  const void* nzval, const void* d, int index_base) {
     MGB_TRY
@@ -640,6 +663,8 @@ int mgb200_set_option(mgb200_handle h, const char* key, int64_t value) {
         else if (k == "overlap_box") H->ctx.overlap_box = (int)value;
         else if (k == "box_min_rows") H->ctx.box_min_rows = (int)value;
         else if (k == "grid_transfers") H->ctx.grid_transfers = (int)value;
+        else if (k == "gxp_quad") H->ctx.gxp_quad = (int)value;
+        else if (k == "mrhs_march") H->ctx.mrhs_march = (int)value;
         else if (k == "split_test") H->ctx.split_test = (int)value;
         else if (k == "overlap") H->ctx.use_overlap = (int)value;
         else if (k == "fused_put") H->use_fused_put = (int)value;

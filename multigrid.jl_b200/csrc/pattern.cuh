@@ -360,6 +360,7 @@ struct PatDict {
     int* c0 = nullptr;
     int* pat_off = nullptr;
     PatEntry<TA>* ent = nullptr;
+    int* rep = nullptr;               // representative row of each pattern (replace_matrix, galerkin.cuh)
     std::vector<uint16_t> host_pid;  // kept for the d-folding check at upload
     // box structure (detect_box): offsets are dz*S2 + dy*S + dx; box_mask[p] = presence bits of pattern p (device)
     bool box_ok = false;
@@ -374,6 +375,8 @@ struct PatDict {
         if (c0) cudaFree(c0);
         if (pat_off) cudaFree(pat_off);
         if (ent) cudaFree(ent);
+        if (rep) cudaFree(rep);
+        rep = nullptr;
         if (hdr) cudaFree(hdr);
         if (ent_s) cudaFree(ent_s);
         hdr = nullptr;
@@ -473,6 +476,11 @@ static void upload_patterns(PatDict<TA>& D, const HostPatterns<TA>& H, long long
     }
     MGB_CUDA(cudaMalloc(&D.ent, e.size() * sizeof(PatEntry<TA>)));
     MGB_CUDA(cudaMemcpy(D.ent, e.data(), e.size() * sizeof(PatEntry<TA>), cudaMemcpyHostToDevice));
+    if ((int)H.rep_row.size() == D.npat) {
+        std::vector<int> rr(H.rep_row.begin(), H.rep_row.end());
+        MGB_CUDA(cudaMalloc(&D.rep, std::max(D.npat, 1) * sizeof(int)));
+        MGB_CUDA(cudaMemcpy(D.rep, rr.data(), D.npat * sizeof(int), cudaMemcpyHostToDevice));
+    }
     D.host_pid = H.pid;
     D.present = true;
     {

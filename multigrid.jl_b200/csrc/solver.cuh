@@ -256,6 +256,218 @@ struct Hierarchy : HierarchyBase {
         lv.ghint = true;
     }
 
+    // ---- replaceMatrixInHierarchy on the device (galerkin.cuh; MGsetup.jl:226-270) -------------------------------------------
+    // The new fine matrix (same sparsity as the resident one) comes from the host; relaxation weights, Galerkin products
+    // and the coarsest factorisation are redone on the device with the resident Ps / Rs.  Returns false (nothing
+    // changed) when the device path does not apply - another sparsity, a row-partitioned hierarchy, SPAI on a
+    // structurally unsymmetric operator - and the caller redoes the setup on the host.
+    // relax_type: 0 "Jac" / "Jac-GMRES", 1 "SPAI"; omega[l]: relaxParam of level l + 1.
+    bool replace_matrix(long long n, const int64_t* cp, const int64_t* rv, const void* nz, int base, int relax_type,
+                        const double* omega) {
+        MGB_CHECK(levels >= 1 && n == L[0].n, "replace_matrix: size differs from the fine level");
+        MGB_CHECK(base == 0 || base == 1, "index_base must be 0 or 1");
+        MGB_CHECK(relax_type == 0 || relax_type == 1, "replace_matrix: relax_type must be 0 (Jac) or 1 (SPAI)");
+        MGB_CUDA(cudaSetDevice(ctx.device));
+        for (int l = 0; l < levels; ++l)
+            if (L[l].sp.dist) return false;
+        if (levels > 1 && !L[0].A.present()) return false;
+        int* flag = dev_alloc<int>(1);
+        auto read_flag = [&]() {
+            int h = 0;
+            MGB_CUDA(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+            ctx.sync();
+            MGB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx.stream));
+            return h;
+        };
+        MGB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx.stream));
+        // (1) the new fine matrix: a full upload (dictionary, box tables) next to the old one, kept only if the sparsity agrees
+        Csr<TV> Anew;
+        if (levels == 1) {
+            upload_csr<TV>(ctx, L[0].A, n, n, cp, rv, static_cast<const TV*>(nz), base, true, false);
+            factor_or_refresh_coarsest(omega ? omega[0] : 1.0);
+            dev_free(flag);
+            invalidate_graphs();
+            return true;
+        }
+        upload_csr<TV>(ctx, Anew, n, n, cp, rv, static_cast<const TV*>(nz), base, true);
+        Csr<TV>& A1 = L[0].A;
+        bool same = Anew.nnz == A1.nnz;
+        if (same) {
+            csr_same_structure_kernel<<<ctx.ew_blocks(n + 1), 256, 0, ctx.stream>>>(n + 1, Anew.rowptr, A1.rowptr, flag);
+            csr_same_structure_kernel<<<ctx.ew_blocks(A1.nnz), 256, 0, ctx.stream>>>(A1.nnz, Anew.colind, A1.colind, flag);
+            MGB_LAUNCH_CHECK();
+            same = read_flag() == 0;
+        }
+        if (!same) {
+            Anew.release();
+            dev_free(flag);
+            return false;
+        }
+        // SPAI needs the columns of A through a symmetric structure: test on every level before anything is changed
+        std::vector<TV*> dnew(levels - 1, nullptr);
+        auto fail = [&]() {
+            for (auto& q : dnew) dev_free(q);
+            Anew.release();
+            dev_free(flag);
+            return false;
+        };
+        // (2) level by level: weights of A_l, then A_{l+1} = R_l A_l P_l into the resident structure
+        std::swap(A1, Anew);                  // A1 is the new matrix from here on; Anew holds the old one
+        for (int l = 0; l + 1 < levels; ++l) {
+            Level<TV>& lv = L[l];
+            Csr<TV>& A = lv.A;
+            dnew[l] = dev_alloc<TV>(lv.n + 4);
+            MGB_CUDA(cudaMemsetAsync(dnew[l] + lv.n, 0, 4 * sizeof(TV), ctx.stream));
+            relax_prec_kernel<TV><<<ctx.ew_blocks(lv.n), 256, 0, ctx.stream>>>((int)lv.n, A.rowptr, A.colind, A.val, relax_type,
+                                                                                omega ? omega[l] : 1.0, dnew[l], flag);
+            MGB_LAUNCH_CHECK();
+            if (read_flag() != 0) {
+                // restore: the old fine matrix goes back, coarse values already overwritten are recomputed from it
+                std::swap(A1, Anew);
+                for (int q = 0; q < l; ++q) galerkin_level(q);
+                return fail();
+            }
+            galerkin_level(l);
+        }
+        Anew.release();
+        // (3) commit: weights, dictionaries of the coarse operators, coarsest factorisation
+        for (int l = 0; l + 1 < levels; ++l) {
+            Level<TV>& lv = L[l];
+            dev_free(lv.d);
+            lv.d = dnew[l];
+            if (l > 0) refresh_dictionary(lv.A, flag);
+            fold_d_device(lv, flag);
+        }
+        factor_or_refresh_coarsest(omega ? omega[levels - 1] : 1.0);
+        dev_free(flag);
+        invalidate_graphs();
+        return true;
+    }
+    void galerkin_level(int l) {
+        Level<TV>& lv = L[l];
+        Csr<TV>& C = L[l + 1].A;
+        MGB_CHECK(C.present() && lv.R.present() && lv.P.present(), "replace_matrix: level not uploaded");
+        const int nc = C.n_rows;
+        const int grid = std::min(cdiv(nc, 8), ctx.sm_count * 8 * 4);
+        galerkin_kernel<TV, RT><<<grid, 256, 0, ctx.stream>>>(nc, lv.R.rowptr, lv.R.colind, lv.R.val, lv.A.rowptr, lv.A.colind,
+                                                               lv.A.val, lv.P.rowptr, lv.P.colind, lv.P.val, C.rowptr, C.colind, C.val);
+        MGB_LAUNCH_CHECK();
+    }
+    // dictionary / box tables of a matrix whose CSR values changed: kept when every row still equals its pattern's
+    // representative row, dropped (CSR-stream kernels from then on) otherwise
+    void refresh_dictionary(Csr<TV>& M, int* flag) {
+        PatDict<TV>& D = M.pat;
+        if (!D.present) return;
+        bool ok = D.rep != nullptr;
+        if (ok) {
+            pat_verify_values_kernel<TV><<<ctx.ew_blocks(M.n_rows), 256, 0, ctx.stream>>>(M.n_rows, M.rowptr, M.val, D.pid, D.rep, flag);
+            MGB_LAUNCH_CHECK();
+            int h = 0;
+            MGB_CUDA(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+            ctx.sync();
+            MGB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx.stream));
+            ok = h == 0;
+        }
+        if (!ok) {
+            D.release();
+            M.box.release();
+            return;
+        }
+        TV* vals = dev_alloc<TV>(std::max(D.nent, 1));
+        pat_refresh_values_kernel<TV><<<D.npat, 32, 0, ctx.stream>>>(D.npat, D.pat_off, D.rep, M.rowptr, M.val, D.ent, D.ent_s, vals);
+        MGB_LAUNCH_CHECK();
+        BoxDict<TV>& X = M.box;
+        if (X.ok) {
+            std::vector<TV> hv(std::max(D.nent, 1));
+            MGB_CUDA(cudaMemcpyAsync(hv.data(), vals, (size_t)D.nent * sizeof(TV), cudaMemcpyDeviceToHost, ctx.stream));
+            ctx.sync();
+            if (!X.refill(hv)) {
+                X.release();
+            } else {
+                MGB_CUDA(cudaMemcpy(X.ctab, X.h_ctab.data(), X.h_ctab.size() * sizeof(TV), cudaMemcpyHostToDevice));
+            }
+        }
+        ctx.sync();
+        dev_free(vals);
+    }
+    // fold_d from the resident d (no host copy): d[rep[p]] per pattern, verified against every row
+    void fold_d_device(Level<TV>& lv, int* flag) {
+        dev_free(lv.dpat);
+        PatDict<TV>& D = lv.A.pat;
+        D.host_pid.clear();
+        D.host_pid.shrink_to_fit();
+        if (!D.present || !D.rep || env_int("MGB200_FOLD_D", 1) == 0) return;
+        TV* dp = dev_alloc<TV>(D.npat);
+        pat_gather_d_kernel<TV><<<cdiv(D.npat, 64), 64, 0, ctx.stream>>>(D.npat, D.rep, lv.d, dp);
+        pat_verify_d_kernel<TV><<<ctx.ew_blocks(lv.n), 256, 0, ctx.stream>>>((int)lv.n, D.pid, dp, lv.d, flag);
+        MGB_LAUNCH_CHECK();
+        int h = 0;
+        MGB_CUDA(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+        ctx.sync();
+        MGB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx.stream));
+        if (h != 0) {
+            dev_free(dp);
+            return;
+        }
+        lv.dpat = dp;
+        BoxDict<TV>& X = lv.A.box;
+        if (X.ok) {
+            std::vector<TV> hd(D.npat);
+            MGB_CUDA(cudaMemcpy(hd.data(), dp, D.npat * sizeof(TV), cudaMemcpyDeviceToHost));
+            MGB_CUDA(cudaMemcpy(X.dtab, hd.data(), D.npat * sizeof(TV), cudaMemcpyHostToDevice));
+            X.c0.d0 = hd[X.p0];
+        }
+    }
+    // coarsest solver of the resident As[end]: dense LU again, or (coarseSolveType "GMRES") the Jacobi weights
+    void factor_or_refresh_coarsest(double omega) {
+        if (coarse.kind == 1) {
+            Level<TV>& lv = L[levels - 1];
+            int* flag = dev_alloc<int>(1);
+            MGB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx.stream));
+            relax_prec_kernel<TV><<<ctx.ew_blocks(lv.n), 256, 0, ctx.stream>>>((int)lv.n, lv.A.rowptr, lv.A.colind, lv.A.val, 0, omega,
+                                                                                coarse.d, flag);
+            MGB_LAUNCH_CHECK();
+            ctx.sync();
+            dev_free(flag);
+            refresh_dictionary(lv.A, nullptr_flag());
+        } else {
+            factor_coarsest();
+        }
+    }
+    int* scratch_flag = nullptr;
+    int* nullptr_flag() {
+        if (!scratch_flag) {
+            scratch_flag = dev_alloc<int>(1);
+            MGB_CUDA(cudaMemset(scratch_flag, 0, sizeof(int)));
+        }
+        return scratch_flag;
+    }
+    // values of a resident matrix back in the caller's convention (nzval of the stored adjoint: conjugated for A)
+    void download_values(int level, int which, void* out, long long nnz) {
+        MGB_CHECK(level >= 1 && level <= levels, "download_values: level out of range");
+        MGB_CUDA(cudaSetDevice(ctx.device));
+        Level<TV>& lv = L[level - 1];
+        ctx.sync();
+        if (which == 0) {
+            MGB_CHECK(lv.A.present() && lv.A.nnz == nnz, "download_values: nnz differs from the resident matrix");
+            std::vector<TV> h((size_t)nnz);
+            MGB_CUDA(cudaMemcpy(h.data(), lv.A.val, (size_t)nnz * sizeof(TV), cudaMemcpyDeviceToHost));
+            TV* o = static_cast<TV*>(out);
+            for (long long k = 0; k < nnz; ++k) o[k] = conj_(h[k]);
+        } else {
+            Csr<RT>& M = which == 1 ? lv.P : lv.R;
+            MGB_CHECK(M.present() && M.nnz == nnz, "download_values: nnz differs from the resident matrix");
+            MGB_CUDA(cudaMemcpy(out, M.val, (size_t)nnz * sizeof(RT), cudaMemcpyDeviceToHost));
+        }
+    }
+    void download_relax_prec(int level, void* out) {
+        MGB_CHECK(level >= 1 && level < levels, "download_relax_prec: level must be in 1..levels-1");
+        MGB_CUDA(cudaSetDevice(ctx.device));
+        ctx.sync();
+        MGB_CHECK(L[level - 1].d, "download_relax_prec: level not uploaded");
+        MGB_CUDA(cudaMemcpy(out, L[level - 1].d, (size_t)L[level - 1].n * sizeof(TV), cudaMemcpyDeviceToHost));
+    }
+
     // relaxPrecs[l] as a function of A_l's pattern id: d folds into the dictionary when every row of
     // a pattern carries bit-identical d (constant-coefficient stencils)
     void fold_d(Level<TV>& lv, const TV* d) {
@@ -298,6 +510,12 @@ struct Hierarchy : HierarchyBase {
         lv.n = n;
         lv.nalloc = n;
         upload_csr<TV>(ctx, lv.A, n, n, cp, rv, static_cast<const TV*>(nz), base, true, false);
+        factor_coarsest();
+    }
+    // dense LU of the resident As[end] (also after replace_matrix put new values into it)
+    void factor_coarsest() {
+        Level<TV>& lv = L[levels - 1];
+        const long long n = lv.n;
         coarse.release();
         coarse.n = (int)n;
         const int N = (int)n;

@@ -258,6 +258,35 @@ class DeviceHierarchy:
         _check(lib().mgb200_set_krylov_matrix(self.h, ctypes.c_int64(AT.shape[1]), _ptr(cp), _ptr(rv), _ptr(nz),
                                               int(index_base)))
 
+    # -- replaceMatrixInHierarchy on the device (MGsetup.jl:226-270; csrc/galerkin.cuh) ------------------------
+    def replace_matrix(self, AT, relaxType="Jac", relaxParam=1.0, index_base: int = 0) -> bool:
+        """New fine matrix AT (= A^H, same sparsity as the resident As[1]): relaxation weights, Galerkin products with
+        the resident Ps / Rs and the coarsest factorisation are redone on the device.  False: the device path does not
+        apply and nothing was changed (redo the setup on the host and upload again)."""
+        if getattr(self, "inner", None) is not None:
+            raise MGB200Error("replace_matrix: not available on a mixed-precision handle")
+        if relaxType not in ("Jac", "Jac-GMRES", "SPAI"):
+            raise MGB200Error(f"relaxType {relaxType!r} is out of scope for the device path")
+        rp = np.ascontiguousarray(np.broadcast_to(np.asarray(relaxParam, dtype=np.float64), (self.levels,)) if
+                                  np.ndim(relaxParam) == 0 else np.asarray(relaxParam, dtype=np.float64)[:self.levels])
+        cp, rv, nz = _csc_arrays(AT, self.VAL, int(index_base))
+        done = ctypes.c_int(0)
+        _check(lib().mgb200_replace_matrix(self.h, ctypes.c_int64(AT.shape[1]), _ptr(cp), _ptr(rv), _ptr(nz), int(index_base),
+                                           1 if relaxType == "SPAI" else 0, _ptr(rp), ctypes.byref(done)))
+        return bool(done.value)
+
+    def download_values(self, level: int, which: int, nnz: int):
+        """nzval of As[level] (which = 0), Ps[level] (1) or Rs[level] (2) as the device holds it now, in the stored
+        (adjoint CSC) convention; level is 1-based."""
+        out = np.empty(int(nnz), dtype=self.VAL if which == 0 else _real_dtype(self.VAL))
+        _check(lib().mgb200_download_values(self.h, int(level), int(which), _ptr(out), ctypes.c_int64(int(nnz))))
+        return out
+
+    def download_relax_prec(self, level: int, n: int):
+        out = np.empty(int(n), dtype=self.VAL)
+        _check(lib().mgb200_download_relax_prec(self.h, int(level), _ptr(out)))
+        return out
+
     # -- helpers ----------------------------------------------------------------------------
     def _vec(self, a, name):
         a = np.asarray(a)

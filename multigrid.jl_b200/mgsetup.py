@@ -166,10 +166,33 @@ def adjustMemoryForNumRHS(param: MGparam, nrhs: int = 1, verbose: bool = False):
     return param
 
 
-def replaceMatrixInHierarchy(param: MGparam, AT, verbose: bool = False):
+def replaceMatrixInHierarchy(param: MGparam, AT, verbose: bool = False, device: bool = True):
     """MGsetup.jl:226-270: keep Ps/Rs, redo the Galerkin products, the
-    relaxation diagonals and the coarsest factorisation."""
+    relaxation diagonals and the coarsest factorisation.
+
+    With a resident device hierarchy (``param.device``) and ``device=True`` the products run on the device
+    (``mgb200_replace_matrix``, csrc/galerkin.cuh): only ``As[1]`` travels; ``param.As[2:]`` and ``param.relaxPrecs`` on
+    the host are then refreshed from the device (values only - the sparsity is the one of the first setup).  When
+    the device path does not apply (another sparsity, row-partitioned hierarchy) the host path below runs and the
+    device hierarchy is dropped for re-upload, as before."""
     relaxParamArr = _relax_param_array(param)
+    dev = getattr(param, "device", None)
+    if (device and dev is not None and hasattr(dev, "replace_matrix") and getattr(param, "_mixed_device", None) is None
+            and param.coarseSolveType not in ("MUMPS", "VankaFaces")):
+        ATc = _csc(AT, dtype=param.VAL)
+        rp = np.array([float(np.real(v)) for v in relaxParamArr], dtype=np.float64)
+        if dev.replace_matrix(ATc, param.relaxType, rp):
+            param.As[0] = ATc
+            for l in range(param.levels - 1):
+                param.relaxPrecs[l] = dev.download_relax_prec(l + 1, param.As[l].shape[1])
+                nxt = sp.csc_matrix(param.As[l + 1], copy=True)
+                if not nxt.has_sorted_indices:
+                    nxt.sort_indices()
+                nxt.data[:] = dev.download_values(l + 2, 0, nxt.nnz)
+                param.As[l + 1] = nxt
+            defineCoarsestAinv(param, param.As[-1])
+            param.doTranspose = 0
+            return
     param.As[0] = _csc(AT, dtype=param.VAL)
     for l in range(param.levels - 1):
         ATl = param.As[l]

@@ -40,6 +40,8 @@ def main():
     ap.add_argument("--cells", type=int, default=256)
     ap.add_argument("--levels", type=int, default=6)
     ap.add_argument("--helmholtz", action="store_true", help="cfg5's family: ComplexF64 shifted Laplacian, rediscretised")
+    ap.add_argument("--grid", default="", help="Float64 Poisson on n1,n2,n3 cells instead of a cube (long lines: 512,512,64)")
+    ap.add_argument("--nrhs", type=int, default=1, help="block variant: nrhs right-hand sides (cfg4: --cells 128 --levels 5 --nrhs 32)")
     ap.add_argument("sets", nargs="*")
     args = ap.parse_args()
     if args.helmholtz:
@@ -52,8 +54,16 @@ def main():
         rng = np.random.default_rng(0)
         b = rng.random(p.As[0].shape[0]) + 1j * rng.random(p.As[0].shape[0])
         b /= np.linalg.norm(b)
+    elif args.grid:
+        n = [int(v) for v in args.grid.split(",")]
+        M = mg.getRegularMesh([0, n[0] / max(n), 0, n[1] / max(n), 0, n[2] / max(n)], n)
+        A = mg.poisson_shifted(M, 1e-4)
+        p = mg.getMGparam(np.float64, np.int64, args.levels, 8, 20, 1e-8, "Jac", 0.8, 2, 2, 'V')
+        mg.MGsetup(A, M, p, 1)
+        b = A @ np.random.default_rng(0).random(A.shape[0])
+        b /= np.linalg.norm(b)
     else:
-        A, M, p, b = build_problem(args.cells, args.levels)
+        A, M, p, b = build_problem(args.cells, args.levels, nrhs=args.nrhs)
     dev = mg.DeviceHierarchy(p, device=0)
     x = np.zeros_like(b)
     _, _, res0 = dev.solveMG(b, x, 0.0, 2)
