@@ -530,6 +530,65 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_config5(args, g):
+    """cfg5 (BASELINE.json configs[4]) behind the same command line: our arm = tools/bench_cfg5.py (513^3 nodes, one
+    global grid for every N); reference arm = the CPU oracle's V(2,2) cycle on a BOUNDED SAMPLE of the same family
+    (129^3 nodes, same operator, wavelength per cell and smoother: DOF/s of the memory-bound CPU path does not depend on
+    the grid size), all host cores, rank 0 only."""
+    cells, levels = args.cfg5_cells, args.cfg5_levels
+    if args.impl != "reference":
+        if not os.path.exists(g.LIB):
+            g.build_cuda()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_cfg5
+        sys.argv = ["bench_cfg5.py", "--cells", str(cells), "--levels", str(levels), "--steps", str(args.steps),
+                    "--warmup", str(args.warmup)]
+        # cross-N parity at the full size (the CPU oracle does not fit the time budget at 513^3): the per-cycle residual
+        # norms and the FGMRES step count of the committed one-GPU run
+        ref = os.path.join(ROOT, "profiles", "r02_cfg5_n1_norms.json")
+        if cells == 512 and levels == 7 and int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.path.exists(ref):
+            sys.argv += ["--norms-ref", ref]
+        bench_cfg5.main()
+        return
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    g.build_oracle()
+    import multigrid_jl_b200 as mg
+    from oracle import cycle as oc
+    sc, sl = 128, 5
+    dom, n = [0.0, 1.0] * 3, [sc] * 3
+    kappa2 = (2 * np.pi / (10.0 * (1.0 / sc))) ** 2
+    p = mg.getMGparam(np.complex128, np.int64, sl, 8, 20, 1e-6, "Jac", 0.8, 2, 2, 'V')
+    ctor = mg.getMultilevelOperatorConstructor(kappa2, lambda mesh, k2: mg.helmholtz_shifted(mesh, k2, 0.5),
+                                               lambda mf, mc, pf, level: pf)
+    mg.MGsetup(ctor, mg.getRegularMesh(dom, n), p, 1)
+    N = p.As[0].shape[0]
+    rng = np.random.default_rng(0)
+    b = rng.random(N) + 1j * rng.random(N)
+    b /= np.linalg.norm(b)
+    cores = host_cores()
+    o = oc.OracleMG(p, numCores=cores)
+    MMG = oc.getMultigridPreconditioner(o, b)
+    MMG(b)
+    times = []
+    for _ in range(max(args.steps, 1) + max(args.warmup - 1, 0)):
+        t0 = time.perf_counter()
+        MMG(b)
+        times.append(time.perf_counter() - t0)
+    times = times[max(args.warmup - 1, 0):]
+    tm = float(np.mean(times))
+    val = N / tm
+    sample = (f"{len(times)} V(2,2) cycles of the cfg5 family at {sc + 1}^3 nodes (ComplexF64 shifted Laplacian, 10 points per "
+              f"wavelength, rediscretised, {sl} levels): BOUNDED SAMPLE of the {cells + 1}^3 workload")
+    out = {"impl": "reference", "metric": "vcycle_dof_per_s", "value": val, "unit": "DOF/s", "n_gpus": args.gpus,
+           "steps": len(times), "warmup": max(args.warmup, 1), "ms_per_step": tm * 1e3, "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+           "config": {"workload": "cfg5: " + sample, "rows": N, "parallelism": f"host CPU, {cores} OpenMP threads (set explicitly)"},
+           "cpu_baseline": {"value": val, "unit": "DOF/s", "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -544,8 +603,16 @@ def main():
     ap.add_argument("--grid", default="", help="N > 1: explicit cells per dimension n1,n2,n3 (development runs)")
     ap.add_argument("--layout", default="cube", choices=["cube", "stack"],
                     help="N > 1 weak-scaling grid: doubling dimensions up to 512^3 at N=8 (cube) or stacked in z")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 5],
+                    help="BASELINE.json config: 2 (default, the metric's config: Float64 Poisson 256^3, weak-scaled for N > 1) or "
+                         "5 (ComplexF64 Helmholtz 512^3 rediscretised, STRONG-scaled over N GPUs: tools/bench_cfg5.py)")
+    ap.add_argument("--cfg5-cells", type=int, default=512)
+    ap.add_argument("--cfg5-levels", type=int, default=7)
     args = ap.parse_args()
     import __graft_entry__ as g
+    if args.config == 5:
+        run_config5(args, g)
+        return
     if args.impl == "reference":
         g.build_oracle()
         run_reference(args)

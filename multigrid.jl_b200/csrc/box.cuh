@@ -609,6 +609,8 @@ box_mrhs_kernel(const __grid_constant__ BoxPlan P, const __grid_constant__ BoxCo
 // fly while plane k is computed.  Nodes outside the grid are zeros in the buffers (their coefficients are zero in the
 // dense table, box_kernel's argument).  Products run in stored (dz, dy, dx) order per (row, j): bit-identical to
 // box_mrhs_kernel, the CSR block kernel and the oracle's column-by-column SpMatMul.
+// (A form that also carried b and the pattern ids one plane ahead and issued all loads before the barrier measured
+// twice as slow - 1219 against 598 us on the level-1 sweep of cfg4, profiles/r02u_tune_cfg4.log - and was dropped.)
 constexpr int MARCH_TX = 8, MARCH_TY = 8, MARCH_NW = 16;       // tile columns, warps per CTA
 constexpr int MARCH_HX = MARCH_TX + 2, MARCH_HY = MARCH_TY + 2, MARCH_NODES = MARCH_HX * MARCH_HY;
 constexpr int MARCH_HALO = MARCH_NODES - MARCH_TX * MARCH_TY;   // 36 nodes around the tile
@@ -734,17 +736,20 @@ struct BoxDict {
     TV* dtab = nullptr;            // device: folded relaxation weights per pattern (set by fold_d), NP elements
     std::vector<TV> h_ctab;        // host copies (the CPU replay, tests)
     std::vector<int> h_mask, h_pat_off;   // presence bits and entry offsets of the patterns (refill)
-    // tile records of the variant in use (box_plan_tile), planned at the first launch and whenever the variant or the
-    // copyable range of the input vectors changes
-    unsigned char* recs = nullptr;
-    int rec_RZ = 0, rec_NB = 0, rec_xlo = 0, rec_xhi = 0;
+    // tile records (box_plan_tile) per kernel variant in use - the fused first two sweeps may run another variant than the
+    // other modes - planned at the first launch of a variant and whenever the copyable range of the input vectors changes
+    struct RecSet {
+        unsigned char* recs = nullptr;
+        int RZ = 0, NB = 0, xlo = 0, xhi = 0, first_ghost_tile = 0;
+    };
+    std::vector<RecSet> sets;
     void release() {
         if (ctab) cudaFree(ctab);
         if (dtab) cudaFree(dtab);
-        if (recs) cudaFree(recs);
+        for (auto& r : sets)
+            if (r.recs) cudaFree(r.recs);
+        sets.clear();
         ctab = dtab = nullptr;
-        recs = nullptr;
-        rec_RZ = rec_NB = 0;
         ok = false;
         h_ctab.clear();
         h_mask.clear();
@@ -767,14 +772,24 @@ struct BoxDict {
         for (int k = 0; k < shape; ++k) c0.c[k] = h_ctab[(size_t)k * NP + p0];
         return true;
     }
-    bool has_records(const BoxPlan& P, int RZ, int NB) const {
-        return recs && rec_RZ == RZ && rec_NB == NB && rec_xlo == P.xlo && rec_xhi == P.xhi;
+    const RecSet* find_records(const BoxPlan& P, int RZ, int NB) const {
+        for (const auto& r : sets)
+            if (r.recs && r.RZ == RZ && r.NB == NB && r.xlo == P.xlo && r.xhi == P.xhi) return &r;
+        return nullptr;
     }
-    int first_ghost_tile = 0;
+    bool has_records(const BoxPlan& P, int RZ, int NB) const { return find_records(P, RZ, NB) != nullptr; }
+    int first_ghost_tile = 0;          // of the set records() returned last
     const unsigned char* records(const BoxPlan& P, int RZ, int NB) {
-        if (has_records(P, RZ, NB)) return recs;
-        if (recs) cudaFree(recs);
-        recs = nullptr;
+        if (const RecSet* r = find_records(P, RZ, NB)) {
+            first_ghost_tile = r->first_ghost_tile;
+            return r->recs;
+        }
+        // a set planned for another range of the same variant is stale: drop it
+        for (auto& r : sets)
+            if (r.recs && r.RZ == RZ && r.NB == NB) {
+                cudaFree(r.recs);
+                r.recs = nullptr;
+            }
         const size_t rb = box_rec_bytes(RZ);
         std::vector<unsigned char> h((size_t)P.ntiles * rb), one(rb);
         // tiles that read ghost rows of the input vector (rows outside [0, n_rows)) go last: on a row-partitioned level
@@ -792,15 +807,25 @@ struct BoxDict {
             if (ghost) ghost_tiles.push_back(tile);
             else std::memcpy(h.data() + (size_t)(n_int++) * rb, one.data(), rb);
         }
-        first_ghost_tile = n_int;
+        RecSet R;
+        R.first_ghost_tile = n_int;
         for (int tile : ghost_tiles) box_plan_tile<TV>(P, RZ, NB, tile, h.data() + (size_t)(n_int++) * rb);
-        MGB_CUDA(cudaMalloc(&recs, std::max<size_t>(h.size(), 16)));
-        MGB_CUDA(cudaMemcpy(recs, h.data(), h.size(), cudaMemcpyHostToDevice));
-        rec_RZ = RZ;
-        rec_NB = NB;
-        rec_xlo = P.xlo;
-        rec_xhi = P.xhi;
-        return recs;
+        MGB_CUDA(cudaMalloc(&R.recs, std::max<size_t>(h.size(), 16)));
+        MGB_CUDA(cudaMemcpy(R.recs, h.data(), h.size(), cudaMemcpyHostToDevice));
+        R.RZ = RZ;
+        R.NB = NB;
+        R.xlo = P.xlo;
+        R.xhi = P.xhi;
+        bool placed = false;
+        for (auto& r : sets)
+            if (!r.recs) {
+                r = R;
+                placed = true;
+                break;
+            }
+        if (!placed) sets.push_back(R);
+        first_ghost_tile = R.first_ghost_tile;
+        return R.recs;
     }
 };
 // dense table of a box-structured dictionary; false when the shape is not one the kernel is instantiated for

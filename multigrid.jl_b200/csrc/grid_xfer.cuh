@@ -384,4 +384,89 @@ __global__ void __launch_bounds__(1024) gxr_kernel(const __grid_constant__ GridX
     }
 }
 
+// ---- block variants (nrhs > 1): blocks are stored RHS-fastest, a node is one contiguous segment of m values ---------------------
+// One warp = one row at a time, lane j = right-hand side j (+ 32, ... when m > 32): every access is a coalesced segment
+// (256 bytes for m = 32 Float64), the class tables sit in shared memory, no matrix stream.  The CSR block kernel these
+// replace reads 12 bytes per non-zero and gathers through L2 (cfg4: restriction 445 us, prolongation 372 us,
+// profiles/r02o_cfg4.json).  Products in stored order per (row, j): bit-identical to csr_stream_mrhs_kernel.
+template <typename TA, typename TV>
+__global__ void __launch_bounds__(256, 3) gxp_mrhs_kernel(const __grid_constant__ GridXfer X, int m, const TA* __restrict__ tabg,
+                                                       const TV* __restrict__ xc, TV* __restrict__ xf) {
+    __shared__ TA tab[GXP_TAB];
+    for (int i = threadIdx.x; i < GXP_TAB; i += blockDim.x) tab[i] = tabg[i];
+    __syncthreads();
+    const int n0 = X.n[0], n1 = X.n[1], N0 = X.N[0], N1 = X.N[1];
+    const long long cs2 = (long long)N0 * N1;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int nlines = n1 * X.nk;
+    for (int line = blockIdx.x; line < nlines; line += gridDim.x) {
+        const int kl = line / n1, jj = line - kl * n1, k = X.k0 + kl, b = jj & 1, c = k & 1;
+        const long long q = ((long long)(k >> 1) * N1 + (jj >> 1)) * N0 - X.shift;        // coarse node (0, j/2, k/2)
+        for (int i = w; i < n0; i += nw) {
+            const int a = i & 1;
+            const TA* tv = tab + (a + 2 * b + 4 * c) * 8;
+            const long long row = (long long)line * n0 + i, p0 = q + (i >> 1);
+            for (int j = lane; j < m; j += 32) {
+                TV acc = VT<TV>::zero();
+                int idx = 0;
+#pragma unroll
+                for (int dz = 0; dz < 2; ++dz) {
+                    if (dz > c) break;
+#pragma unroll
+                    for (int dy = 0; dy < 2; ++dy) {
+                        if (dy > b) break;
+                        const long long p = p0 + dy * N0 + dz * cs2;
+                        acc = acc + tv[idx] * ldg_(xc + (p * m + j));
+                        ++idx;
+                        if (a) {
+                            acc = acc + tv[idx] * ldg_(xc + ((p + 1) * m + j));
+                            ++idx;
+                        }
+                    }
+                }
+                xf[row * m + j] = xf[row * m + j] + acc;
+            }
+        }
+    }
+}
+template <typename TA, typename TV>
+__global__ void __launch_bounds__(256, 3) gxr_mrhs_kernel(const __grid_constant__ GridXfer X, int m, const TA* __restrict__ tabg,
+                                                       const TV* __restrict__ rf, TV* __restrict__ rc) {
+    __shared__ TA tab[GXR_TAB];
+    for (int i = threadIdx.x; i < GXR_TAB; i += blockDim.x) tab[i] = tabg[i];
+    __syncthreads();
+    const int N0 = X.N[0], N1 = X.N[1], N2 = X.N[2];
+    const long long S = X.n[0], S2 = (long long)X.n[0] * X.n[1];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int nlines = N1 * X.nk;
+    for (int line = blockIdx.x; line < nlines; line += gridDim.x) {
+        const int Kl = line / N1, J = line - Kl * N1, K = X.k0 + Kl;
+        const int cy = gx_class(J, N1), cz = gx_class(K, N2);
+        const int ay = gx_allowed(cy, N1), az = gx_allowed(cz, N2);
+        const long long f0 = S2 * (2LL * K) + S * (2LL * J) - X.shift;
+        for (int I = w; I < N0; I += nw) {
+            const int cx = gx_class(I, N0), ax = gx_allowed(cx, N0);
+            const TA* tv = tab + (cx + 3 * cy + 9 * cz) * 27;
+            const long long f = f0 + 2 * I, row = (long long)line * N0 + I;
+            const bool plain = ax == 7 && ay == 7 && az == 7;      // warp-uniform: interior node, all 27 products
+            for (int j = lane; j < m; j += 32) {
+                TV acc = VT<TV>::zero();
+                if (plain) {
+#pragma unroll
+                    for (int e = 0; e < 27; ++e)
+                        acc = acc + tv[e] * ldg_(rf + ((f + (e / 9 - 1) * S2 + ((e / 3) % 3 - 1) * S + (e % 3 - 1)) * m + j));
+                } else {
+#pragma unroll 1
+                    for (int e = 0; e < 27; ++e) {
+                        const int dz = e / 9 - 1, dy = (e / 3) % 3 - 1, dx = e % 3 - 1;
+                        if (((az >> (dz + 1)) & 1) && ((ay >> (dy + 1)) & 1) && ((ax >> (dx + 1)) & 1))
+                            acc = acc + tv[e] * ldg_(rf + ((f + dz * S2 + dy * S + dx) * m + j));
+                    }
+                }
+                rc[row * m + j] = acc;
+            }
+        }
+    }
+}
+
 }  // namespace mgb200

@@ -143,7 +143,7 @@ struct Context {
                                    // instead of the line form (MGB200_GXP_QUAD)
     int tma_min_rows = 200000;     // smaller matrices keep the one-pass kernel (too few tiles per SM)
     int use_box = 1;               // box-stencil kernel (box.cuh) for box-structured square operators (MGB200_BOX)
-    int box_variant = 1;           // (rows per thread, base rows per tile, stages): see launch_box (MGB200_BOX_VARIANT)
+    int box_variant = -1;          // >= 0: (rows per thread, base rows per tile, stages) instead of launch_box's own choice (MGB200_BOX_VARIANT)
     int box_variant27 = -1;        // >= 0: another variant for the 27-point levels (MGB200_BOX_VARIANT27)
     int box_variant_c = -1;        // >= 0: another variant for ComplexF64 hierarchies (MGB200_BOX_VARIANT_C)
     int box_min_rows = 100000;
@@ -183,7 +183,7 @@ struct Context {
         use_tma = env_int("MGB200_TMA", 1);
         tma_min_rows = env_int("MGB200_TMA_MIN_ROWS", 200000);
         use_box = env_int("MGB200_BOX", 1);
-        box_variant = env_int("MGB200_BOX_VARIANT", 1);
+        box_variant = env_int("MGB200_BOX_VARIANT", -1);
         box_variant27 = env_int("MGB200_BOX_VARIANT27", -1);
         box_variant_c = env_int("MGB200_BOX_VARIANT_C", -1);
         box_min_rows = env_int("MGB200_BOX_MIN_ROWS", 100000);

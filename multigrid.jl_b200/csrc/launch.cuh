@@ -182,6 +182,27 @@ static bool launch_grid_xfer(Context& ctx, const Csr<TA>& M, int mode, const TV*
     }
 }
 
+// block variants of the grid-hinted transfer kernels (nrhs > 1, whole grids)
+template <typename TA, typename TV>
+static bool launch_grid_xfer_mrhs(Context& ctx, const Csr<TA>& M, int mode, const TV* x, TV* y, int m) {
+    if constexpr (VT<TA>::is_complex) {
+        return false;
+    } else {
+        const GridXfer& X = M.gx;
+        if (!X.ok || !X.tab || ctx.grid_transfers <= 0 || !ctx.use_patterns || x == y || m < 2) return false;
+        if (!((X.kind == 1 && mode == MODE_ADD) || (X.kind == 2 && mode == MODE_SPMV))) return false;
+        // measured on cfg4 (profiles/r02u_tune_cfg4.log): the restriction gains on every level (706 -> 551 us per cycle),
+        // the prolongation loses against the CSR block kernel (500 -> 874 us): option grid_transfers >= 2 switches it on
+        if (X.kind == 1 && ctx.grid_transfers < 2) return false;
+        const long long nlines = X.kind == 1 ? (long long)X.n[1] * X.nk : (long long)X.N[1] * X.nk;
+        const int grid = (int)std::min<long long>(nlines, (long long)ctx.sm_count * 8 * 4);
+        if (X.kind == 1) gxp_mrhs_kernel<TA, TV><<<grid, 256, 0, ctx.stream>>>(X, m, static_cast<const TA*>(X.tab), x, y);
+        else gxr_mrhs_kernel<TA, TV><<<grid, 256, 0, ctx.stream>>>(X, m, static_cast<const TA*>(X.tab), x, y);
+        MGB_LAUNCH_CHECK();
+        return true;
+    }
+}
+
 // box-stencil kernel (box.cuh): box-structured square operators on a 3-D grid, SPMV / RESID / SWEEP, one right-hand
 // side, double and complex double.  Variants (rows per thread RZ, base rows per tile NB, stages): ctx.box_variant.
 template <typename TV, int RZ, int NB, int STAGES>
@@ -325,7 +346,19 @@ static bool launch_box(Context& ctx, const Csr<TA>& M, int mode, const TV* x, co
                        TV* y, const PutPlan& pp, bool prepare_only = false, const BoxWait& bw = no_wait()) {
     if constexpr (std::is_same<TA, TV>::value && (std::is_same<TV, double>::value || std::is_same<TV, cplx>::value)) {
         if (!M.box.ok || !ctx.use_box || M.n_rows < ctx.box_min_rows) return false;
-        int variant = (M.box.shape == 27 && ctx.box_variant27 >= 0) ? ctx.box_variant27 : ctx.box_variant;
+        // Variant (rows per thread RZ, base rows per tile NB, stages).  Measured choices (profiles/r02_box_variants.log,
+        // r02t_*): a window carries a y-halo of 2 (S + 1) elements, so long lines need long tiles.
+        //   Float64 7-point: (2, 512, 2); lines of >= 400 nodes (the z-slabs of the 512^3 grid) and the fused first two
+        //   sweeps (126 -> 95 us at 257^3: fewer neighbours are recomputed per row): (4, 1024, 2)
+        //   Float64 27-point: (2, 512, 2)
+        //   ComplexF64 7-point: (1, 512, 2); lines of >= 400 nodes (cfg5, 513^3): (2, 1024, 2), the fused first two sweeps
+        //   (whose stage also holds the pattern-id windows) (2, 512, 2)
+        // Options box_variant / box_variant27 / box_variant_c >= 0 override (tools/tune.py).
+        int variant = 1;
+        if (sizeof(TV) == 8 && M.box.shape == 7 && (M.pat.S >= 400 || mode == MODE_SWEEP2_FROM_ZERO)) variant = 11;
+        if (sizeof(TV) == 16 && M.box.shape == 7) variant = M.pat.S >= 400 ? (mode == MODE_SWEEP2_FROM_ZERO ? 22 : 31) : 21;
+        if (ctx.box_variant >= 0) variant = ctx.box_variant;
+        if (M.box.shape == 27 && ctx.box_variant27 >= 0) variant = ctx.box_variant27;
         if (sizeof(TV) == 16 && ctx.box_variant_c >= 0) variant = ctx.box_variant_c;      // complex double: its own choice
         if (!prepare_only) {
             if (mode == MODE_ADD || x == y) return false;
@@ -362,6 +395,7 @@ static bool launch_box(Context& ctx, const Csr<TA>& M, int mode, const TV* x, co
 template <typename TA>
 static void box_prepare(Context& ctx, const Csr<TA>& M) {
     launch_box<TA, TA>(ctx, M, MODE_SPMV, nullptr, nullptr, nullptr, nullptr, nullptr, no_put(), true);
+    launch_box<TA, TA>(ctx, M, MODE_SWEEP2_FROM_ZERO, nullptr, nullptr, nullptr, nullptr, nullptr, no_put(), true);   // may run another variant
 }
 
 // one-pass dictionary kernel over the rows [rA, rA + nA) and [rB, rB + nB)
@@ -457,7 +491,8 @@ static void csr_apply(Context& ctx, const Csr<TA>& M, int mode, const TV* x, con
         launch_rowwarp_mode<TA, TV>(ctx, M, mode, x, b, d, y, m);
     } else if (m > 1) {
         // blocks of right-hand sides: the box-stencil kernel when the matrix has that structure, else the CSR stream
-        if (!launch_box_mrhs<TA, TV>(ctx, M, mode, x, b, d, ctx.mrhs_dpat ? dpat : nullptr, y, m))
+        if (!launch_grid_xfer_mrhs<TA, TV>(ctx, M, mode, x, y, m) &&
+            !launch_box_mrhs<TA, TV>(ctx, M, mode, x, b, d, ctx.mrhs_dpat ? dpat : nullptr, y, m))
             launch_mrhs_mode<TA, TV>(ctx, M, mode, x, b, d, y, m);
     } else {
         switch (M.tpr) {

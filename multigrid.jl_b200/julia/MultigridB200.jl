@@ -300,4 +300,34 @@ function solveCG_MG(AT::SparseMatrixCSC{VALD,Int64}, param::MGparam{VAL,Int64}, 
     return x0, param, Int(iter[])
 end
 
+# replaceMatrixInHierarchy (MGsetup.jl:226-270) with a resident device hierarchy: only the new As[1] travels; relaxation
+# weights, Galerkin products and the coarsest factorisation are redone on the device (csrc/galerkin.cuh), then
+# param.As[2:end] and param.relaxPrecs are refreshed from the device (values only: the sparsity is that of the first
+# setup).  When the device path does not apply (another sparsity, row-partitioned hierarchy) the reference's host
+# function runs and the device hierarchy is dropped for re-upload.
+function replaceMatrixInHierarchy(param::MGparam{VAL,Int64}, AT::SparseMatrixCSC{VAL,Int64}, verbose::Bool=false) where {VAL}
+    dev = get(_devices, param, nothing)
+    if dev === nothing || dev.multi || !(param.relaxType in ("Jac", "Jac-GMRES", "SPAI"))
+        clearDevice!(param)
+        return Multigrid.replaceMatrixInHierarchy(param, AT, verbose)
+    end
+    omega = isa(param.relaxParam, Array) ? Float64.(real.(param.relaxParam)) : fill(Float64(real(param.relaxParam)), param.levels)
+    done = Ref{Cint}(0)
+    check(ccall((:mgb200_replace_matrix, libmgb200), Cint,
+                (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{VAL}, Cint, Cint, Ptr{Float64}, Ref{Cint}),
+                dev.handle, size(AT, 2), AT.colptr, AT.rowval, AT.nzval, 1, param.relaxType == "SPAI" ? 1 : 0, omega, done))
+    if done[] == 0
+        clearDevice!(param)
+        return Multigrid.replaceMatrixInHierarchy(param, AT, verbose)
+    end
+    param.As[1] = AT
+    for l = 1:(param.levels - 1)
+        check(ccall((:mgb200_download_relax_prec, libmgb200), Cint, (Ptr{Cvoid}, Cint, Ptr{VAL}), dev.handle, l, param.relaxPrecs[l]))
+        check(ccall((:mgb200_download_values, libmgb200), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{VAL}, Int64),
+                    dev.handle, l + 1, 0, param.As[l+1].nzval, nnz(param.As[l+1])))
+    end
+    param.doTranspose = 0
+    return
+end
+
 end # module

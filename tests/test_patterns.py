@@ -379,6 +379,45 @@ def test_grid_hinted_transfers_bit_identical(kind, n, cycle, R):
     assert it0 == it1 and np.array_equal(r0, r1) and np.array_equal(x0, x1)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,nrhs", [([24, 20, 18], 32), ([17, 9, 33], 8), ([40, 12, 12], 13), ([16, 16, 16], 40)])
+@pytest.mark.parametrize("variant", ["quad_prolongation", "long_lines_30", "long_lines_31", "long_lines_32", "long_lines_33"])
+def test_round2_kernel_options_bit_identical(n, nrhs, variant):
+    """Marching block kernel (csrc/box.cuh, box_mrhs_march_kernel: tiles that do not divide the grid, nrhs below / at /
+    above one warp) against the direct block kernel, and the box variants for long lines / the line-form prolongation
+    against the defaults, on one right-hand side: nothing may change by a bit."""
+    import multigrid_jl_b200 as mg
+
+    def run(env, m):
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            A, AT, M, p, b = make_problem("poisson", n, 3, nrhs=m, maxit=3)
+            x, _, it = mg.solveMG(p, b, np.zeros_like(b))
+            res = p.last_resvec.copy()
+            p.device.destroy()
+            return x, res
+        finally:
+            for k, v in old.items():
+                os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
+    base = {"MGB200_BOX_MIN_ROWS": "0"}
+    if variant == "quad_prolongation":
+        x0, r0 = run(dict(base, MGB200_MRHS_MARCH="0"), nrhs)
+        x1, r1 = run(dict(base, MGB200_MRHS_MARCH="1"), nrhs)
+        assert np.array_equal(r0, r1) and np.array_equal(x0, x1)
+        for gt in ("0", "2"):      # block transfers: CSR stream (0), grid-hinted restriction (default), + prolongation (2)
+            x1, r1 = run(dict(base, MGB200_GRID_TRANSFERS=gt), nrhs)
+            assert np.array_equal(r0, r1) and np.array_equal(x0, x1), gt
+        x0, r0 = run(dict(base, MGB200_GXP_QUAD="0"), 1)
+        for q in ("1", "2", "3"):
+            x1, r1 = run(dict(base, MGB200_GXP_QUAD=q), 1)
+            assert np.array_equal(r0, r1) and np.array_equal(x0, x1), q
+    else:
+        x0, r0 = run(dict(base, MGB200_BOX="0"), 1)
+        x1, r1 = run(dict(base, MGB200_BOX_VARIANT=variant.split("_")[-1]), 1)
+        assert np.array_equal(r0, r1) and np.array_equal(x0, x1)
+
+
 @pytest.mark.parametrize("seed", range(12))
 def test_box_kernel_code_fuzz(seed):
     """Random box stencils - arbitrary subsets of the 27 offsets (upwind-like one-sided ones, stencils without a centre

@@ -73,7 +73,7 @@ def main():
         for k, v in defaults.items():
             dev.set_option(k, v)
         for k, v in opts.items():
-            defaults.setdefault(k, {"box": 1, "box_variant": 1, "box_variant27": -1, "box_variant_c": -1, "box_min_rows": 100000,
+            defaults.setdefault(k, {"box": 1, "box_variant": -1, "box_variant27": -1, "box_variant_c": -1, "box_min_rows": 100000,
                                     "grid_transfers": 1, "tma": 1, "graphs": 1, "fuse_first": 1}.get(k, 0))
             dev.set_option(k, int(v))
         _, _, res = dev.solveMG(b, x, 0.0, 2)
