@@ -395,8 +395,12 @@ def run_ours(args):
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "peak_source": peak_src,
                 "traffic": ncu_traffic(cells, dom, "pattern" if pinfo["in_use"] else "csr"),
+                "traffic_source": "constant from the committed ncu --set full capture of this kernel (profiles/ncu_traffic.json "
+                                  "names the file); not measured by this run",
+                "kernel_impl": "box_kernel (csrc/box.cuh: dense coefficient tables, TMA-staged plane windows, host-planned tile "
+                               "records) on box-structured levels, else pat_tma_kernel / pat_kernel (csrc/pattern.cuh)",
                 "share_of_step": dom["total_ms"] / tot_ms,
-                "device_format": ("stencil dictionary (csrc/pattern.cuh): 16-bit pattern id per row, "
+                "device_format": ("stencil dictionary (csrc/pattern.cuh, csrc/box.cuh): 16-bit pattern id per row, "
                                   f"{pinfo['patterns']} patterns / {pinfo['entries']} entries for A_1, d folded: "
                                   f"{pinfo['d_folded']}") if pinfo["in_use"] else "CSR (Int32 indices), TMA-staged",
                 "format_bytes_per_launch": dom["format_bytes"] / dom["launches"],
@@ -491,9 +495,7 @@ def run_ours(args):
                                       "put+poll kernel per exchange); cycle incl. exchanges replayed from a CUDA graph"
                                       if dinfo["p2p"] else "ncclSend/ncclRecv"))},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "spmv": spmv,
-        "kernel_options": {k: os.environ[k] for k in ("MGB200_LINES", "MGB200_LINES_STAGED", "MGB200_GRID_TRANSFERS",
-                                                      "MGB200_TMA", "MGB200_TMA_GAP", "MGB200_PATTERNS", "MGB200_GRAPHS",
-                                                      "MGB200_FUSED_PUT", "MGB200_OVERLAP") if k in os.environ},
+        "kernel_options": {k: v for k, v in os.environ.items() if k.startswith("MGB200_")},
         "kernels": kern[:10],
     }
     if rank == 0 and world == 1 and not args.no_cpu:

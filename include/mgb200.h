@@ -279,18 +279,21 @@ int mgb200_kernel_config(mgb200_handle h, int level, int which, int64_t* out);
  * out[3] = dictionary entries, out[4] = 1 if relaxPrecs[level] is folded into the dictionary (which = 0). */
 int mgb200_pattern_info(mgb200_handle h, int level, int which, int64_t* out);
 
-/* Runtime options: "patterns" (1/0: use the stencil dictionary where available; set before upload to skip
- * building it), "graphs" (1/0: replay V/F/W cycles from CUDA graphs), "smem_budget" (bytes per CTA used when
- * choosing the rows per CTA of the CSR-stream kernel at upload), "tma" (1/0: TMA-staged persistent variant of the
- * dictionary kernel for square stencil operators), "tma_min_rows" (matrices with fewer rows keep the one-pass kernel),
- * "lines" (0 = off, the default; 2 or 4: line-blocked dictionary kernel with that many rows per thread on levels whose
- * dictionary has box structure and at least "lines_min_rows" rows; "lines_staged" 1: its TMA-staged form where the
- * lines are short enough, else the global-memory form - not yet run on a GPU),
- * "grid_transfers" (0 = off, the default; 1, 2 or 4: grid-hinted transfer kernels with that many coarse lines per thread
- * on levels whose hint was verified, mgb200_set_level_grid - not yet run on a GPU),
- * "fused_put" (1/0: multi-GPU, the producing kernel stores the slab-end rows to the neighbours itself),
- * "overlap" (1/0: multi-GPU, run the halo exchange of an operator's input beside the rows that read no ghost),
- * "split_test" (rows: single-GPU test hook that forces the split launch sequence of the overlap path). */
+/* Runtime options (every MGB200_<KEY> environment variable sets the same default at mgb200_create; results never change
+ * by a bit, only the kernels that produce them - tests/test_patterns.py):
+ *  "patterns" (1/0: stencil dictionary where the rows deduplicate; set before upload to skip building it),
+ *  "graphs" (1/0: replay V/F/W cycles from CUDA graphs), "smem_budget" (bytes per CTA when choosing the rows per CTA of the
+ *  CSR-stream kernel at upload), "tma" (1/0: TMA-staged variant of the dictionary kernel), "tma_min_rows",
+ *  "box" (1/0: box-stencil kernel on box-structured square operators, csrc/box.cuh), "box_min_rows",
+ *  "box_variant" / "box_variant27" / "box_variant_c" (-1 = the library's choice; else the tile
+ *  variant for all / 27-point / ComplexF64 levels), "fuse_first" (1/0: first two sweeps from x = 0 in one pass),
+ *  "grid_transfers" (1: grid-hinted transfer kernels on levels whose hint was verified, mgb200_set_level_grid; 2: also
+ *  the block prolongation; 0: off), "gxp_quad" (1: quad-form prolongation with 64 registers, 2 / 3: 40 / 32; 0: line form),
+ *  "mrhs_march" (1/0: marching block kernel for nrhs >= 8),
+ *  multi-GPU: "fused_put" (1/0: the producing kernel stores the slab-end rows to the neighbours itself), "overlap_box"
+ *  (1/0: the box kernel runs beside the halo exchange of its input and waits for the ghost rows inside the kernel),
+ *  "overlap" (1/0: exchange beside the rows that read no ghost; measured slower, off),
+ *  "split_test" (rows: single-GPU test hook that forces the split launch sequence of the overlap path). */
 int mgb200_set_option(mgb200_handle h, const char* key, int64_t value);
 
 /* Host-only (no GPU): box structure of a row-relative dictionary (csrc/pattern.cuh::detect_box) - every column offset

@@ -324,29 +324,12 @@ __global__ void lower_apply_kernel(int n, int m, const TW* __restrict__ linv, co
     const int nch = (m + MC - 1) / MC;
     const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     if (w >= (long long)n * nch) return;
-    // longest rows first (row i holds i + 1 entries): the warp of the last row is the critical path of the kernel
-    const int i = n - 1 - (int)(w / nch), c0 = (int)(w % nch) * MC;
+    const int i = (int)(w / nch), c0 = (int)(w % nch) * MC;
     const int mc = m - c0 < MC ? m - c0 : MC;
     TW acc[MC];
 #pragma unroll
     for (int c = 0; c < MC; ++c) acc[c] = VT<TW>::zero();
-    int j = lane;
-    if (MC == 1) {
-        // eight independent 256-byte segments of the factor row in flight per warp (one per iteration left the kernel
-        // latency-bound: 731 dependent iterations for n = 23 376); the products are added in the same order as below
-        const TW* li = linv + (size_t)i * n;
-        for (; j + 7 * 32 <= i; j += 8 * 32) {
-            TW l[8];
-            TW bb[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) l[u] = li[j + 32 * u];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) bb[u] = widen(b[(size_t)perm[j + 32 * u] * m + c0]);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) acc[0] = acc[0] + l[u] * bb[u];
-        }
-    }
-    for (; j <= i; j += 32) {
+    for (int j = lane; j <= i; j += 32) {
         const TW l = linv[(size_t)i * n + j];
         const TV* bj = b + (size_t)perm[j] * m + c0;
 #pragma unroll
@@ -374,21 +357,7 @@ __global__ void upper_apply_kernel(int n, int m, const TW* __restrict__ uinv, co
     TW acc[MC];
 #pragma unroll
     for (int c = 0; c < MC; ++c) acc[c] = VT<TW>::zero();
-    int j = i + lane;
-    if (MC == 1) {
-        const TW* ui = uinv + (size_t)i * n;
-        for (; j + 7 * 32 < n; j += 8 * 32) {
-            TW l[8];
-            TW bb[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) l[u] = ui[j + 32 * u];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) bb[u] = y[(size_t)(j + 32 * u) * m + c0];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) acc[0] = acc[0] + l[u] * bb[u];
-        }
-    }
-    for (; j < n; j += 32) {
+    for (int j = i + lane; j < n; j += 32) {
         const TW u = uinv[(size_t)i * n + j];
         const TW* yj = y + (size_t)j * m + c0;
 #pragma unroll

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, call v (2 GPUs): this round's kernels on row-partitioned levels: parity (dist_check, multi-device tests), bench at
+# 2 GPUs: this round's kernels on row-partitioned levels: parity (dist_check, multi-device tests), bench at
 # N = 2 (cfg2 weak-scaled) and cfg5 at 256^3 cells strong-scaled over 2 GPUs against the oracle
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, call u (1 GPU): automatic box variants, marching block kernel with prefetch, block transfer kernels
+# 1 GPU: automatic box variants, marching block kernel with prefetch, block transfer kernels
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 timeout 1200 python -m pytest tests/test_patterns.py tests/test_replace_matrix.py tests/test_gpu_parity.py tests/test_baseline_sizes.py -m gpu -x -q > gpurun_out/r2u_pytest.log 2>&1; echo "pytest exit $?"; tail -12 gpurun_out/r2u_pytest.log
