@@ -18,6 +18,11 @@ from .mgsetup import (MGsetup, getRelaxPrec, getSPAIprec, adjustMemoryForNumRHS,
                       replaceMatrixInHierarchy, transposeHierarchy, defineCoarsestAinv)
 from .sa_amg import (SA_AMGsetup, getAggregation, getStrengthMatrix, neighborhoodAggregationNew,
                      aggrArray2P)
+from .classical_amg import (ClassicalAMGsetup, getStrengthMatrixClassical, getColoringFirst, getColoringSecond,
+                            getInterpolation)
+from .systems import (getLinearOperatorsSystemsFaces, getInjectionOperatorsSystemsFaces, getLinearInterpolationFacesUj,
+                      getRestrictionFacesFullWeightUj, getRestrictionFacesInjectionUj, getRestrictionCellCentered,
+                      getLinearInterpolationCellCentered, faces_size)
 from .device import DeviceHierarchy, MultiDeviceHierarchy, uploadHierarchy, MGB200Error, LIB_PATH
 from .solve import (solveMG, solveCG_MG, solveGMRES_MG, solveBiCGSTAB_MG, getMultigridPreconditioner, recursiveCycle,
                     SpMatMul)

@@ -93,19 +93,26 @@ def MGsetup(ATf, Mesh: RegularMesh, param: MGparam, nrhs: int = 1, verbose: bool
         PDEparam = ATf.param
     if A1.dtype != VAL:
         A1 = _csc(A1, dtype=VAL)
-    if param.transferOperatorType != "FullWeighting":
-        raise NotImplementedError("only FullWeighting transfer operators are in scope "
-                                  "(Systems faces operators: SURVEY section 2 row 9)")
+    if param.transferOperatorType not in ("FullWeighting", "SystemsFacesLinear", "SystemsFacesMixedLinear"):
+        raise ValueError(f"unknown transferOperatorType {param.transferOperatorType!r}")
+    withCellsBlock = param.transferOperatorType == "SystemsFacesMixedLinear"      # MGsetup.jl:48-51
     As, Ps, Rs, Meshes, relaxPrecs = [A1], [], [], [Mesh], []
     n = Mesh.n.copy()
     Cop = A1.nnz
     levels = param.levels
     for l in range(levels - 1):
         AT = As[l]
-        P, nc = getFWInterp(n + 1, geometric)
-        nc = nc - 1
-        RT = _csc(P.copy(), dtype=rVAL)
-        PT = _csc(P.T, dtype=rVAL)
+        if param.transferOperatorType == "FullWeighting":
+            P, nc = getFWInterp(n + 1, geometric)
+            nc = nc - 1
+            RT = _csc(P.copy(), dtype=rVAL)
+            PT = _csc(P.T, dtype=rVAL)
+        else:
+            # staggered-grid systems (MGsetup.jl:63-74, Systems.jl:33-76): n in cells, block-diagonal P and R
+            from .systems import getLinearOperatorsSystemsFaces
+            P, R, nc = getLinearOperatorsSystemsFaces(n, withCellsBlock)
+            PT = _csc(P.T, dtype=rVAL)
+            RT = _csc(R.T, dtype=rVAL)
         RT.data *= 0.5 ** Meshes[l].dim
         relaxPrecs.append(getRelaxPrec(AT, param.relaxType, relaxParamArr[l], VAL))
         if PT.shape[0] == PT.shape[1]:
