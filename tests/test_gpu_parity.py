@@ -155,6 +155,13 @@ def test_jac_gmres_with_different_pre_and_post_counts_is_an_error():
         mg.solveMG(p, b, np.zeros_like(b))
 
 
+# Krylov drivers.  What BASELINE.json's north_star asks of them is the SAME ITERATION COUNT (and exit flag) as the
+# reference order; that is asserted exactly below.  The residual HISTORIES are compared as well, with looser bounds than
+# the 1e-10 of the cycle for a stated reason: the entries run down to 1e-8 of the first one, the recurrences (dots with
+# another summation order, short-recurrence cancellation in CG / BiCGStab, a 10 x 10 least-squares problem per restart in
+# FGMRES) carry absolute differences of ~1e-15 |b| from one step to the next, and an absolute 1e-15 is a relative 1e-7 on
+# the last entries.  The bounds are the observed ones with a margin: CG 1e-8, FGMRES 1e-7, BiCGStab / block drivers 1e-6,
+# block BiCGStab 1e-5 (products of m x m solves).  The true residual of the returned x is checked against the tolerance.
 @pytest.mark.parametrize("kind,n,levels", [("poisson", [128, 128], 4), ("poisson", [32, 32, 32], 4),
                                            ("diffusion", [48, 48], 3)])
 def test_solveCG_iteration_count(kind, n, levels):
